@@ -1,0 +1,121 @@
+"""Load-stepping Newton driver that mirrors the reference's GoalPrimal loop.
+
+TEST INFRASTRUCTURE.  It reproduces, around any assembler object with the Oracle
+interface (oracle.Oracle, or the CUDA path's goal_b200.Assembler), the steps the
+reference performs around `assemble`:
+
+  Solver::solve          src/main_primal.cpp:68-90     load-step loop, states->update()
+  Primal::solve          src/goal_primal.cpp:111-137   Newton loop
+  Primal::compute_jacob  src/goal_primal.cpp:92-109    zero, assemble, tbcs, gather, jac dbcs
+  Primal::compute_resid  src/goal_primal.cpp:75-90     zero, assemble, tbcs, gather, resid dbcs
+  set_jac_dbcs / set_resid_dbcs   src/goal_dbcs.cpp:39-99
+  set_tbcs (apply_bc)    src/goal_tbcs.cpp:29-71        R[row] -= T_d * N_n * w * dv  (= T_d * area / 3)
+  Functional (avg disp)  src/goal_functional.cpp:62-70, src/goal_avg_disp.cpp:17-21
+
+The linear solve (Belos GMRES + MueLu in the reference, src/goal_linear_solve.cpp)
+is replaced by a sparse direct solve; the reference's linear tolerance is 1e-10.
+"""
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+
+def _traction_rhs(coords, sides, traction):
+    """ghost-R contribution of one traction BC: list of (row, value)."""
+    out = []
+    for tri in sides:
+        x = coords[np.asarray(tri)]
+        area = 0.5 * np.linalg.norm(np.cross(x[1] - x[0], x[2] - x[0]))
+        for n in tri:
+            for d in range(3):
+                out.append((4 * n + d, -traction[d] * (1.0 / 3.0) * 0.5 * (2.0 * area)))
+    return out
+
+
+def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_iters=5, log=None):
+    """dbcs: [(eq, node_ids, g(t))]; tbcs: [(side_tris, T(t) -> 3-vector)].
+
+    Returns dict(J=[per-step functional], newton=[iterations], plastic=[count at end of step]).
+    """
+    nn = len(coords)
+    u = np.zeros((nn, 3))
+    p = np.zeros(nn)
+    rowptr, colind = asm.rowptr, asm.colind
+    out = dict(J=[], newton=[], plastic=[])
+    t_old, t_now = 0.0, dt
+
+    def apply_tbcs(R, t):
+        for sides, T in tbcs:
+            for row, v in _traction_rhs(coords, sides, T(t)):
+                R[row] += v
+
+    def dbc_rows(t):
+        for eq, nodes, g in dbcs:
+            for n in nodes:
+                yield 4 * n + eq, (u[n, eq] if eq < 3 else p[n]) - g(t)
+
+    for step in range(num_steps):
+        it, converged = 1, False
+        while it <= max_iters and not converged:
+            asm.set_solution(u, p)
+            R, vals = asm.jacobian(save=True)
+            R = np.array(R, copy=True)
+            vals = np.array(vals, copy=True)
+            apply_tbcs(R, t_now)
+            for row, r in dbc_rows(t_now):
+                R[row] = r
+                vals[rowptr[row]:rowptr[row + 1]] = 0.0
+                k = rowptr[row] + np.searchsorted(colind[rowptr[row]:rowptr[row + 1]], row)
+                vals[k] = 1.0
+            A = sp.csr_matrix((vals, colind, rowptr), shape=(4 * nn, 4 * nn))
+            du = spla.spsolve(A.tocsc(), -R).reshape(nn, 4)
+            u += du[:, :3]
+            p += du[:, 3]
+            asm.set_solution(u, p)
+            R = np.array(asm.residual(save=True), copy=True)
+            apply_tbcs(R, t_now)
+            for row, r in dbc_rows(t_now):
+                R[row] = r
+            nrm = np.linalg.norm(R)
+            if log:
+                log(f"step {step + 1} newton {it} ||R|| = {nrm:.3e}")
+            converged = nrm < tol
+            it += 1
+        if not converged:
+            raise RuntimeError(f"newton's method failed in {max_iters} iterations")
+        out["newton"].append(it - 1)
+        out["plastic"].append(asm.plastic_count())
+        out["J"].append(asm.avg_disp())
+        asm.update_states()
+        t_old, t_now = t_now, t_now + dt
+    out["u"], out["p"] = u, p
+    return out
+
+
+# The reference's three 3D regression inputs (example/primal/*.yaml), all on
+# test/mesh/cube with E=1000, nu=0.25, K=100, Y=10, c0=1, 3 load steps of 1.0.
+GOLDEN = {
+    # name: (model, golden J, yaml)
+    "neohookean_uniaxial_3D": ("neohookean", 2.541285341193943e-03, "example/primal/neohookean_uniaxial_3D.yaml:34-36"),
+    "J2_uniaxial_3D": ("J2", 1.073955612775838e-03, "example/primal/J2_uniaxial_3D.yaml:36-38"),
+    "J2_traction_3D": ("J2", 2.512233163668167e-04, "example/primal/J2_traction_3D.yaml:37-39"),
+}
+# survey-time per-step values: intermediate known answers
+GOLDEN_STEPS = {
+    "neohookean_uniaxial_3D": [8.379491376688085e-04, 1.685073358995205e-03, 2.541285341193988e-03],
+    "J2_uniaxial_3D": [8.379491377532382e-04, 9.454391681366886e-04, 1.073955612775823e-03],
+    "J2_traction_3D": [8.346891869851834e-05, 1.672096850639751e-04, 2.512233163668262e-04],
+}
+
+
+def golden_case(name, fixture):
+    """(dbcs, tbcs) of one reference regression input on the cube fixture."""
+    ns, ss = fixture["node_sets"], fixture["side_sets"]
+    zero = lambda t: 0.0
+    dbcs = [(0, ns["xmin"], zero), (1, ns["ymin"], zero), (2, ns["zmin"], zero)]
+    tbcs = []
+    if name.endswith("uniaxial_3D"):
+        dbcs.append((0, ns["xmax"], lambda t: 0.01 * t))
+    else:
+        tbcs.append((ss["ymax"], lambda t: (0.0, 1.0 * t, 0.0)))
+    return dbcs, tbcs
