@@ -1,0 +1,283 @@
+"""ctypes binding of the C-ABI (include/goal_b200.h) -> libgoal_b200.so.
+
+`Assembler` mirrors, call for call, what the reference's Primal / NestedAdjoint do
+around goal::assemble (src/goal_primal.cpp:75-109, src/goal_nested_adjoint.cpp:163-234):
+set the solution fields, compute_resid / compute_jacob, localize, states->update().
+There is no CPU path: if the CUDA library is missing or no GPU is visible the
+constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgoal_b200.so")
+
+MODEL = {"neohookean": 0, "J2": 1}
+NONE, PRIMAL, ADJOINT = 0, 1, 2
+
+STATUS = {0: "GX_OK", 1: "GX_ERR_ARG", 2: "GX_ERR_CUDA", 3: "GX_ERR_INVERTED_ELEMENT",
+          4: "GX_ERR_INVERTED_DEFORMATION", 5: "GX_ERR_J2_RETURN_MAP", 6: "GX_ERR_NCCL", 7: "GX_ERR_UNSUPPORTED"}
+
+# every symbol include/goal_b200.h declares (tests/test_abi.py checks the .so exports them all)
+SYMBOLS = [
+    "gx_create", "gx_destroy", "gx_last_error", "gx_graph", "gx_graph_size", "gx_scatter_map",
+    "gx_set_solution", "gx_get_state", "gx_set_state", "gx_update_states", "gx_compute_residual",
+    "gx_compute_jacobian", "gx_localize_error", "gx_element_error", "gx_comm_init", "gx_nccl_unique_id",
+    "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
+    "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
+    "gx_stream", "gx_last_timing", "gx_set_option",
+]
+
+
+class GxError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"{STATUS.get(status, status)}: {msg}")
+        self.status = status
+
+
+class GxDesc(C.Structure):
+    _fields_ = [
+        ("n_nodes", C.c_int32), ("n_elems", C.c_int32),
+        ("conn", C.POINTER(C.c_int32)), ("coords", C.POINTER(C.c_double)),
+        ("elem_set", C.POINTER(C.c_int32)), ("n_elem_sets", C.c_int32), ("model", C.c_int32),
+        ("materials", C.POINTER(C.c_double)), ("device", C.c_int32), ("flags", C.c_uint32),
+        ("rank", C.c_int32), ("n_ranks", C.c_int32),
+        ("node_gid", C.POINTER(C.c_int64)), ("node_owner", C.POINTER(C.c_int32)),
+        ("n_peers", C.c_int32), ("peer_rank", C.POINTER(C.c_int32)),
+        ("peer_offset", C.POINTER(C.c_int32)), ("peer_nodes", C.POINTER(C.c_int32)),
+    ]
+
+
+_LIB = None
+
+
+def load_library():
+    """Load libgoal_b200.so; raises (never falls back) when it is not built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(f"{LIB_PATH} is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(goal_b200 has no CPU fallback)")
+    L = C.CDLL(LIB_PATH)
+    dp, ip, lp, vp = C.POINTER(C.c_double), C.POINTER(C.c_int32), C.POINTER(C.c_int64), C.c_void_p
+    L.gx_create.argtypes = [C.POINTER(GxDesc), C.POINTER(vp)]
+    L.gx_destroy.argtypes = [vp]
+    L.gx_last_error.restype = C.c_char_p
+    L.gx_last_error.argtypes = [vp]
+    L.gx_graph.argtypes = [vp, lp, C.POINTER(lp), C.POINTER(ip)]
+    L.gx_graph_size.argtypes = [vp, lp, ip]
+    L.gx_scatter_map.argtypes = [vp, C.POINTER(C.c_uint8)]
+    L.gx_set_solution.argtypes = [vp, vp, vp]
+    L.gx_get_state.argtypes = [vp, C.c_char_p, dp]
+    L.gx_set_state.argtypes = [vp, C.c_char_p, dp]
+    L.gx_update_states.argtypes = [vp]
+    L.gx_compute_residual.argtypes = [vp, C.c_int, vp]
+    L.gx_compute_jacobian.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.gx_localize_error.argtypes = [vp, vp, vp, vp, vp]
+    L.gx_element_error.argtypes = [vp, dp, dp, ip, C.c_int32, dp, dp, dp]
+    L.gx_comm_init.argtypes = [vp, vp, C.c_size_t]
+    L.gx_nccl_unique_id.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.gx_reduce_interfaces.argtypes = [vp, C.c_int]
+    L.gx_allreduce_sum.argtypes = [vp, dp, C.c_int]
+    L.gx_interface_bytes.argtypes = [vp, C.c_int, C.c_int, lp, lp]
+    L.gx_pack_interface.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+    L.gx_unpack_add_interface.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.gx_result_dev.argtypes = [vp, C.POINTER(vp), C.POINTER(vp)]
+    L.gx_fetch.argtypes = [vp, vp, vp]
+    L.gx_plastic_count.argtypes = [vp, lp]
+    L.gx_num_colors.argtypes = [vp, ip]
+    L.gx_stream.restype = vp
+    L.gx_stream.argtypes = [vp]
+    L.gx_last_timing.argtypes = [vp, dp]
+    L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    _LIB = L
+    return L
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _ip(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int32))
+
+
+def _addr(a):
+    """host address of a numpy array or a (pinned) torch tensor, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+        return C.c_void_p(a.ctypes.data)
+    assert a.dtype.is_floating_point and a.element_size() == 8 and a.is_contiguous() and not a.is_cuda
+    return C.c_void_p(a.data_ptr())
+
+
+class Assembler:
+    """One mesh part on one GPU (a gx_ctx)."""
+
+    def __init__(self, coords, conn, model, materials, elem_set=None, device=0, partition=None):
+        self.L = load_library()
+        self.coords = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, 3)
+        self.conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
+        self.nn, self.ne = len(self.coords), len(self.conn)
+        self.model = model
+        mats = np.ascontiguousarray(materials, dtype=np.float64).reshape(-1, 5)
+        self._keep = [mats]
+        d = GxDesc()
+        d.n_nodes, d.n_elems = self.nn, self.ne
+        d.conn, d.coords = _ip(self.conn), _dp(self.coords)
+        if elem_set is not None:
+            es = np.ascontiguousarray(elem_set, dtype=np.int32)
+            self._keep.append(es)
+            d.elem_set = _ip(es)
+        d.n_elem_sets, d.model, d.materials, d.device = len(mats), MODEL[model], _dp(mats), device
+        if partition is not None:
+            d.rank, d.n_ranks = partition["rank"], partition["n_ranks"]
+            gid = np.ascontiguousarray(partition["node_gid"], dtype=np.int64)
+            own = np.ascontiguousarray(partition["node_owner"], dtype=np.int32)
+            pr = np.ascontiguousarray(partition["peer_rank"], dtype=np.int32)
+            po = np.ascontiguousarray(partition["peer_offset"], dtype=np.int32)
+            pn = np.ascontiguousarray(partition["peer_nodes"], dtype=np.int32)
+            self._keep += [gid, own, pr, po, pn]
+            d.node_gid = gid.ctypes.data_as(C.POINTER(C.c_int64))
+            d.node_owner, d.n_peers = _ip(own), len(pr)
+            d.peer_rank, d.peer_offset, d.peer_nodes = _ip(pr), _ip(po), _ip(pn)
+        self.h = C.c_void_p()
+        rc = self.L.gx_create(C.byref(d), C.byref(self.h))
+        if rc:
+            raise GxError(rc, self.L.gx_last_error(None).decode())
+        nnz, nrows = C.c_int64(), C.c_int32()
+        self._ck(self.L.gx_graph_size(self.h, C.byref(nnz), C.byref(nrows)))
+        self.nnz = nnz.value
+        self._rowptr = self._colind = None
+        self._R = np.zeros(4 * self.nn)
+        self._vals = None
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.L.gx_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise GxError(rc, self.L.gx_last_error(self.h).decode())
+
+    # ---- Disc::build_data products
+    def _graph(self):
+        if self._rowptr is None:
+            nnz = C.c_int64()
+            rp, ci = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+            self._ck(self.L.gx_graph(self.h, C.byref(nnz), C.byref(rp), C.byref(ci)))
+            self._rowptr = np.ctypeslib.as_array(rp, (4 * self.nn + 1,)).copy()
+            self._colind = np.ctypeslib.as_array(ci, (nnz.value,)).copy()
+
+    @property
+    def rowptr(self):
+        self._graph()
+        return self._rowptr
+
+    @property
+    def colind(self):
+        self._graph()
+        return self._colind
+
+    def scatter_map(self):
+        b = np.zeros((self.ne, 16), dtype=np.uint8)
+        self._ck(self.L.gx_scatter_map(self.h, b.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return b
+
+    @property
+    def num_colors(self):
+        n = C.c_int32()
+        self._ck(self.L.gx_num_colors(self.h, C.byref(n)))
+        return n.value
+
+    # ---- fields and state
+    def set_solution(self, u, p):
+        if isinstance(u, np.ndarray):
+            u = np.ascontiguousarray(u, dtype=np.float64).reshape(-1)
+            p = np.ascontiguousarray(p, dtype=np.float64).reshape(-1)
+            assert u.size == 3 * self.nn and p.size == self.nn
+        self._ck(self.L.gx_set_solution(self.h, _addr(u), _addr(p)))
+
+    def get_state(self, name):
+        out = np.zeros((self.ne, 9) if name in ("sigma", "Fp", "Fp_old") else (self.ne,))
+        self._ck(self.L.gx_get_state(self.h, name.encode(), _dp(out)))
+        return out
+
+    def set_state(self, name, val):
+        val = np.ascontiguousarray(val, dtype=np.float64)
+        assert val.size == self.ne * (9 if name in ("sigma", "Fp", "Fp_old") else 1)
+        self._ck(self.L.gx_set_state(self.h, name.encode(), _dp(val)))
+
+    def update_states(self):
+        self._ck(self.L.gx_update_states(self.h))
+
+    # ---- the hot path
+    def residual(self, save=True, out=True):
+        """Primal::compute_resid minus BCs. out=False leaves R on the device."""
+        self._ck(self.L.gx_compute_residual(self.h, int(save), _addr(self._R) if out is True else _addr(out) if out is not False else None))
+        return self._R if out is True else out
+
+    def jacobian(self, mode=PRIMAL, save=True, out=True, R_out=None, values_out=None):
+        """Primal::compute_jacob / NestedAdjoint::compute_adjoint minus BCs -> (R, values)."""
+        if out is True and R_out is None:
+            if self._vals is None:
+                self._vals = np.zeros(self.nnz)
+            R_out, values_out = self._R, self._vals
+        self._ck(self.L.gx_compute_jacobian(self.h, mode, int(save), _addr(R_out), _addr(values_out)))
+        return R_out, values_out
+
+    def localize(self, zu_diff, zp_diff, zp_coarse):
+        a = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1) for x in (zu_diff, zp_diff, zp_coarse)]
+        self._ck(self.L.gx_localize_error(self.h, _addr(a[0]), _addr(a[1]), _addr(a[2]), _addr(self._R)))
+        return self._R
+
+    def element_error(self, u_err, p_err, parent=None, n_parent=0):
+        u_err = np.ascontiguousarray(u_err, dtype=np.float64).reshape(-1)
+        p_err = np.ascontiguousarray(p_err, dtype=np.float64).reshape(-1)
+        eta, bound = np.zeros(self.ne), C.c_double()
+        etap = None
+        if parent is not None:
+            parent = np.ascontiguousarray(parent, dtype=np.int32)
+            etap = np.zeros(n_parent)
+        self._ck(self.L.gx_element_error(self.h, _dp(u_err), _dp(p_err), None if parent is None else _ip(parent),
+                                         n_parent, _dp(eta), None if etap is None else _dp(etap), C.byref(bound)))
+        return eta, etap, bound.value
+
+    def fetch(self, R=True, values=True):
+        Rv = np.zeros(4 * self.nn) if R else None
+        Vv = np.zeros(self.nnz) if values else None
+        self._ck(self.L.gx_fetch(self.h, _addr(Rv), _addr(Vv)))
+        return Rv, Vv
+
+    # ---- introspection
+    def plastic_count(self):
+        n = C.c_int64()
+        self._ck(self.L.gx_plastic_count(self.h, C.byref(n)))
+        return n.value
+
+    def last_timing(self):
+        t = (C.c_double * 4)()
+        self._ck(self.L.gx_last_timing(self.h, t))
+        return dict(zero_ms=t[0], assemble_ms=t[1], exchange_ms=t[2], launches=int(t[3]))
+
+    def stream(self):
+        return self.L.gx_stream(self.h)
+
+    def set_option(self, key, value):
+        self._ck(self.L.gx_set_option(self.h, key.encode(), int(value)))
+
+    def csr(self, values):
+        import scipy.sparse as sp
+        return sp.csr_matrix((values, self.colind, self.rowptr), shape=(4 * self.nn, 4 * self.nn))

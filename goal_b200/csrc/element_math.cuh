@@ -1,0 +1,425 @@
+// element_math.cuh -- per-element arithmetic of the mixed u/p tet assembly path.
+//
+// One linear tet, one integration point (goal_assembly.cpp:78-80).  The functions
+// here are what each CUDA thread runs; they are also compiled for the host by
+// tests/hostcheck (a test-only build used to verify this arithmetic against the
+// oracle in a container without a GPU -- it is not a product path).
+//
+// What replaces Sacado FAD (goal_scalar_types.hpp:9): the reference seeds 16
+// directions dx[n*4+d] (goal_displacement.cpp:139-156, goal_pressure.cpp:136-151)
+// and pushes 17-wide numbers through every evaluator.  Here forward mode is
+// carried out per seed direction in closed form.  A displacement seed (m,k)
+// perturbs F by the rank-one tensor e_k (x) G_m, so with the spatial shape
+// gradients w_n = F^{-T} G_n every directional derivative collapses to a few
+// scalars per (m,k) and a few 3-vectors per node m:
+//     dJ        = J w_m[k]
+//     d w_n     = -w_m w_n[k]
+//     d B       = e_k (x) r_m + r_m (x) e_k,   B = F Cp^{-1} F^T,  r_m = F Cp^{-1} G_m
+// (neo-Hookean is Cp = I).  The residual is written in spatial form,
+// P G_n = tau w_n with tau = J sigma (Kirchhoff), so
+//     K[(n,i),(m,k)] = vol { (d tau w_n)_i - (tau w_m)_i w_n[k] }.
+// Everything stays in registers; nothing 16-wide is ever formed.
+//
+// Evaluator order and formulas follow (file:line under /root/reference/src):
+//   kinematics      goal_kinematics.cpp:18-25
+//   neohookean      goal_neohookean.cpp:44-52, 60-72, 80-86
+//   J2              goal_J2.cpp:54-64, 72-143, 151-157
+//   mixed           goal_mixed.cpp:34-46
+//   mresidual       goal_mresidual.cpp:26-32
+//   presidual       goal_presidual.cpp:54-59
+//   stabilization   goal_stabilization.cpp:59-81
+//   adjoint weights goal_displacement_adjoint.cpp:37-53, goal_pressure_adjoint.cpp:38-49
+#pragma once
+
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define GX_HD __host__ __device__ __forceinline__
+#else
+#define GX_HD inline
+#endif
+
+namespace gx {
+
+enum { MODEL_NEOHOOKEAN = 0, MODEL_J2 = 1 };
+
+// error codes reported per launch (first failing element wins)
+enum { ERR_NONE = 0, ERR_INVERTED_ELEMENT = 1, ERR_INVERTED_DEFORMATION = 2, ERR_J2_RETURN_MAP = 3 };
+
+struct Material {  // per elem set; kappa/mu as in goal_neohookean.cpp:50-51
+  double kappa, mu, K, Y, c0;
+};
+
+// symmetric 3x3 storage: 00 11 22 01 02 12
+template <class S> GX_HD void sym_mv(S const t[6], S const v[3], S o[3]) {
+  o[0] = t[0] * v[0] + t[3] * v[1] + t[4] * v[2];
+  o[1] = t[3] * v[0] + t[1] * v[1] + t[5] * v[2];
+  o[2] = t[4] * v[0] + t[5] * v[1] + t[2] * v[2];
+}
+template <class S> GX_HD S dot3(S const a[3], S const b[3]) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <class S> GX_HD void cross3(S const a[3], S const b[3], S o[3]) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <class S> GX_HD S det3(S const A[9]) {
+  return A[0] * (A[4] * A[8] - A[5] * A[7]) - A[1] * (A[3] * A[8] - A[5] * A[6]) + A[2] * (A[3] * A[7] - A[4] * A[6]);
+}
+// inverse given the determinant's reciprocal
+template <class S> GX_HD void inv3(S const A[9], S rdet, S o[9]) {
+  o[0] = (A[4] * A[8] - A[5] * A[7]) * rdet;
+  o[1] = (A[2] * A[7] - A[1] * A[8]) * rdet;
+  o[2] = (A[1] * A[5] - A[2] * A[4]) * rdet;
+  o[3] = (A[5] * A[6] - A[3] * A[8]) * rdet;
+  o[4] = (A[0] * A[8] - A[2] * A[6]) * rdet;
+  o[5] = (A[2] * A[3] - A[0] * A[5]) * rdet;
+  o[6] = (A[3] * A[7] - A[4] * A[6]) * rdet;
+  o[7] = (A[1] * A[6] - A[0] * A[7]) * rdet;
+  o[8] = (A[0] * A[4] - A[1] * A[3]) * rdet;
+}
+template <class S> GX_HD void mm3(S const A[9], S const B[9], S o[9]) {
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) o[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+
+// exp of a 3x3 matrix: [3/3] Pade when ||A||_1 <= 1.4956e-2 (truncation error below
+// double round-off, the branch minitensor::exp takes for every realistic plastic
+// increment), otherwise [13/13] Pade with scaling and squaring (Higham 2005).
+template <class S> GX_HD void expm3(S const A[9], S o[9]) {
+  S n1 = 0;
+  for (int j = 0; j < 3; ++j) {
+    S c = fabs(A[j]) + fabs(A[3 + j]) + fabs(A[6 + j]);
+    n1 = c > n1 ? c : n1;
+  }
+  S A2[9], U[9], V[9], T[9];
+  if (n1 <= S(1.495585217958292e-2)) {
+    mm3(A, A, A2);
+    for (int i = 0; i < 9; ++i) { T[i] = A2[i]; V[i] = S(12.) * A2[i]; }
+    T[0] += S(60.); T[4] += S(60.); T[8] += S(60.);
+    V[0] += S(120.); V[4] += S(120.); V[8] += S(120.);
+    mm3(A, T, U);
+  } else {
+    int sq = 0;
+    S As[9];
+    S const th13 = S(5.371920351148152);
+    S sc = S(1.0);
+    while (n1 * sc > th13 && sq < 60) { sc *= S(0.5); ++sq; }
+    for (int i = 0; i < 9; ++i) As[i] = A[i] * sc;
+    S A4[9], A6[9];
+    mm3(As, As, A2); mm3(A2, A2, A4); mm3(A2, A4, A6);
+    S const b[14] = {64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800.,
+                     129060195264000., 10559470521600., 670442572800., 33522128640., 1323241920.,
+                     40840800., 960960., 16380., 182., 1.};
+    S W1[9], W2[9];
+    for (int i = 0; i < 9; ++i) W1[i] = b[13] * A6[i] + b[11] * A4[i] + b[9] * A2[i];
+    mm3(A6, W1, W2);
+    for (int i = 0; i < 9; ++i) W2[i] += b[7] * A6[i] + b[5] * A4[i] + b[3] * A2[i];
+    W2[0] += b[1]; W2[4] += b[1]; W2[8] += b[1];
+    mm3(As, W2, U);
+    for (int i = 0; i < 9; ++i) W1[i] = b[12] * A6[i] + b[10] * A4[i] + b[8] * A2[i];
+    mm3(A6, W1, V);
+    for (int i = 0; i < 9; ++i) V[i] += b[6] * A6[i] + b[4] * A4[i] + b[2] * A2[i];
+    V[0] += b[0]; V[4] += b[0]; V[8] += b[0];
+    for (int i = 0; i < 9; ++i) { T[i] = V[i] - U[i]; A2[i] = V[i] + U[i]; }
+    S Ti[9];
+    inv3(T, S(1.0) / det3(T), Ti);
+    mm3(Ti, A2, o);
+    for (int s = 0; s < sq; ++s) { mm3(o, o, T); for (int i = 0; i < 9; ++i) o[i] = T[i]; }
+    return;
+  }
+  for (int i = 0; i < 9; ++i) { T[i] = V[i] - U[i]; A2[i] = V[i] + U[i]; }
+  S Ti[9];
+  inv3(T, S(1.0) / det3(T), Ti);
+  mm3(Ti, A2, o);
+}
+
+// ---------------------------------------------------------------------------
+// Value-level state of one element shared by the residual and every Jacobian
+// column.  All vectors are indexed by local node n = 0..3.
+// ---------------------------------------------------------------------------
+template <class S>
+struct Core {
+  S vol;       // w*dv = det(J_geom)/6                       goal_assembly.cpp:78-80
+  S taus;      // 0.5*c0*h^2/mu                              goal_stabilization.cpp:72
+  S J;         // det F                                      goal_kinematics.cpp:24
+  S pv;        // p at the centroid                          goal_pressure.cpp:153-158
+  S w[4][3];   // spatial shape gradients F^{-T} G_n
+  S r[4][3];   // F Cp^{-1} G_n (neo-Hookean: F G_n)
+  S q[3];      // F^{-T} grad p
+  S tau[6];    // Kirchhoff stress of the mixed Cauchy stress, J*sigma
+  S s[6];      // trial deviatoric Kirchhoff stress (goal_J2.cpp:89)
+  S A1;        // beta*mu*J^{-2/3}
+  S beta;      // radial-return scaling of s (1 when elastic)
+  // plastic branch only
+  S N[6], smag, mubar, dgam, D, c1;
+  int plastic;
+  // geometry kept for the adjoint-weighted residual
+  S G[4][3];
+  S Finv[9];
+};
+
+// Geometry + kinematics + stress update.  x,u: [4][3]; p: [4].
+// Fp_old/eqps_old are read only for MODEL_J2.  When `save` is set the state the
+// reference's evaluators would leave behind is written to sigma_out (mixed Cauchy,
+// goal_mixed.cpp:44-45), eqps_out, and -- plastic branch only -- Fp_out
+// (goal_J2.cpp:128-136; on the elastic branch Fp is deliberately left untouched).
+// Returns an ERR_* code.
+template <int MODEL, class S>
+GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material const& mat, S const Fp_old[9],
+                       S eqps_old, bool save, S sigma_out[9], S& eqps_out, S Fp_out[9], bool& write_Fp,
+                       Core<S>& c) {
+  write_Fp = false;
+  // ---- linear tet geometry: G_n = grad N_n, vol = det/6, h^2 = mean squared edge length
+  S e1[3], e2[3], e3[3];
+  for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; e3[j] = x[3][j] - x[0][j]; }
+  S c23[3], c31[3], c12[3];
+  cross3(e2, e3, c23); cross3(e3, e1, c31); cross3(e1, e2, c12);
+  S const dv = dot3(e1, c23);
+  if (!(dv > S(0.0))) return ERR_INVERTED_ELEMENT;
+  S const rdv = S(1.0) / dv;
+  for (int j = 0; j < 3; ++j) {
+    c.G[1][j] = c23[j] * rdv; c.G[2][j] = c31[j] * rdv; c.G[3][j] = c12[j] * rdv;
+    c.G[0][j] = -(c.G[1][j] + c.G[2][j] + c.G[3][j]);
+  }
+  c.vol = dv * S(1.0 / 6.0);
+  S h2 = dot3(e1, e1) + dot3(e2, e2) + dot3(e3, e3);
+  for (int j = 0; j < 3; ++j) {
+    S a = x[2][j] - x[1][j], b = x[3][j] - x[1][j], d = x[3][j] - x[2][j];
+    h2 += a * a + b * b + d * d;
+  }
+  c.taus = S(0.5) * mat.c0 * (h2 * S(1.0 / 6.0)) / mat.mu;
+
+  // ---- F = I + grad u, J, F^{-1}; p and grad p at the centroid
+  S F[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      F[3 * i + j] = (u[1][i] - u[0][i]) * c.G[1][j] + (u[2][i] - u[0][i]) * c.G[2][j] + (u[3][i] - u[0][i]) * c.G[3][j];
+  F[0] += S(1.0); F[4] += S(1.0); F[8] += S(1.0);
+  S const J = det3(F);
+  if (!(J > S(0.0))) return ERR_INVERTED_DEFORMATION;
+  c.J = J;
+  S const rJ = S(1.0) / J;
+  inv3(F, rJ, c.Finv);
+  c.pv = S(0.25) * p[0] + S(0.25) * p[1] + S(0.25) * p[2] + S(0.25) * p[3];
+  S gp[3];
+  for (int j = 0; j < 3; ++j) gp[j] = (p[1] - p[0]) * c.G[1][j] + (p[2] - p[0]) * c.G[2][j] + (p[3] - p[0]) * c.G[3][j];
+  for (int k = 0; k < 3; ++k) c.q[k] = c.Finv[k] * gp[0] + c.Finv[3 + k] * gp[1] + c.Finv[6 + k] * gp[2];
+  for (int n = 1; n < 4; ++n)
+    for (int k = 0; k < 3; ++k) c.w[n][k] = c.Finv[k] * c.G[n][0] + c.Finv[3 + k] * c.G[n][1] + c.Finv[6 + k] * c.G[n][2];
+  for (int k = 0; k < 3; ++k) c.w[0][k] = -(c.w[1][k] + c.w[2][k] + c.w[3][k]);
+
+  S const pr = S(0.5) * mat.kappa * (J - rJ);  // U'(J) kappa, replaced by p in Mixed
+  S Jm23;
+  S snew[6];
+  c.plastic = 0;
+  c.beta = S(1.0);
+  if (MODEL == MODEL_NEOHOOKEAN) {
+    S const Jm13 = S(1.0) / cbrt(J);
+    Jm23 = Jm13 * Jm13;
+    // b = F F^T
+    S b[6];
+    b[0] = F[0] * F[0] + F[1] * F[1] + F[2] * F[2];
+    b[1] = F[3] * F[3] + F[4] * F[4] + F[5] * F[5];
+    b[2] = F[6] * F[6] + F[7] * F[7] + F[8] * F[8];
+    b[3] = F[0] * F[3] + F[1] * F[4] + F[2] * F[5];
+    b[4] = F[0] * F[6] + F[1] * F[7] + F[2] * F[8];
+    b[5] = F[3] * F[6] + F[4] * F[7] + F[5] * F[8];
+    S const tr3 = (b[0] + b[1] + b[2]) * S(1.0 / 3.0);
+    S const c1 = mat.mu * Jm23;
+    c.s[0] = c1 * (b[0] - tr3); c.s[1] = c1 * (b[1] - tr3); c.s[2] = c1 * (b[2] - tr3);
+    c.s[3] = c1 * b[3]; c.s[4] = c1 * b[4]; c.s[5] = c1 * b[5];
+    c.c1 = c1;
+    for (int n = 1; n < 4; ++n)
+      for (int i = 0; i < 3; ++i) c.r[n][i] = F[3 * i] * c.G[n][0] + F[3 * i + 1] * c.G[n][1] + F[3 * i + 2] * c.G[n][2];
+    for (int i = 0; i < 6; ++i) snew[i] = c.s[i];
+  } else {
+    Jm23 = pow(J, S(-2.0 / 3.0));
+    S Fpi[9];
+    inv3(Fp_old, S(1.0) / det3(Fp_old), Fpi);
+    // Cp^{-1} = Fp^{-1} Fp^{-T} (symmetric)
+    S Cp[6];
+    Cp[0] = Fpi[0] * Fpi[0] + Fpi[1] * Fpi[1] + Fpi[2] * Fpi[2];
+    Cp[1] = Fpi[3] * Fpi[3] + Fpi[4] * Fpi[4] + Fpi[5] * Fpi[5];
+    Cp[2] = Fpi[6] * Fpi[6] + Fpi[7] * Fpi[7] + Fpi[8] * Fpi[8];
+    Cp[3] = Fpi[0] * Fpi[3] + Fpi[1] * Fpi[4] + Fpi[2] * Fpi[5];
+    Cp[4] = Fpi[0] * Fpi[6] + Fpi[1] * Fpi[7] + Fpi[2] * Fpi[8];
+    Cp[5] = Fpi[3] * Fpi[6] + Fpi[4] * Fpi[7] + Fpi[5] * Fpi[8];
+    // M = F Cp^{-1}; B = M F^T (symmetric)
+    S M[9];
+    for (int i = 0; i < 3; ++i) {
+      S const* f = &F[3 * i];
+      M[3 * i + 0] = f[0] * Cp[0] + f[1] * Cp[3] + f[2] * Cp[4];
+      M[3 * i + 1] = f[0] * Cp[3] + f[1] * Cp[1] + f[2] * Cp[5];
+      M[3 * i + 2] = f[0] * Cp[4] + f[1] * Cp[5] + f[2] * Cp[2];
+    }
+    S B[6];
+    B[0] = M[0] * F[0] + M[1] * F[1] + M[2] * F[2];
+    B[1] = M[3] * F[3] + M[4] * F[4] + M[5] * F[5];
+    B[2] = M[6] * F[6] + M[7] * F[7] + M[8] * F[8];
+    B[3] = M[0] * F[3] + M[1] * F[4] + M[2] * F[5];
+    B[4] = M[0] * F[6] + M[1] * F[7] + M[2] * F[8];
+    B[5] = M[3] * F[6] + M[4] * F[7] + M[5] * F[8];
+    S const c1 = mat.mu * Jm23;
+    c.c1 = c1;
+    S const trB = B[0] + B[1] + B[2];
+    S const tr3 = trB * S(1.0 / 3.0);
+    c.s[0] = c1 * (B[0] - tr3); c.s[1] = c1 * (B[1] - tr3); c.s[2] = c1 * (B[2] - tr3);
+    c.s[3] = c1 * B[3]; c.s[4] = c1 * B[4]; c.s[5] = c1 * B[5];
+    c.mubar = c1 * tr3;  // mu * trace(be) / 3
+    for (int n = 1; n < 4; ++n)
+      for (int i = 0; i < 3; ++i) c.r[n][i] = M[3 * i] * c.G[n][0] + M[3 * i + 1] * c.G[n][1] + M[3 * i + 2] * c.G[n][2];
+    S const smag = sqrt(c.s[0] * c.s[0] + c.s[1] * c.s[1] + c.s[2] * c.s[2] +
+                        S(2.0) * (c.s[3] * c.s[3] + c.s[4] * c.s[4] + c.s[5] * c.s[5]));
+    S const sq23 = S(0.81649658092772603273);  // sqrt(2/3)
+    S const f = smag - sq23 * (mat.Y + mat.K * eqps_old);
+    eqps_out = eqps_old;
+    for (int i = 0; i < 6; ++i) snew[i] = c.s[i];
+    if (f > S(1.0e-12)) {
+      // Radial return.  With linear hardening the reference's Newton loop on X
+      // (goal_J2.cpp:108-121) lands on X = f / (2 mubar + 2K/3) in two iterations.
+      c.plastic = 1;
+      c.smag = smag;
+      c.D = S(2.0) * c.mubar + S(2.0 / 3.0) * mat.K;
+      c.dgam = f / c.D;
+      S const rs = S(1.0) / smag;
+      for (int i = 0; i < 6; ++i) c.N[i] = c.s[i] * rs;
+      c.beta = S(1.0) - S(2.0) * c.mubar * c.dgam * rs;
+      for (int i = 0; i < 6; ++i) snew[i] = c.s[i] - S(2.0) * c.mubar * c.dgam * c.N[i];
+      eqps_out = eqps_old + sq23 * c.dgam;
+      if (save) {
+        S A[9] = {c.dgam * c.N[0], c.dgam * c.N[3], c.dgam * c.N[4], c.dgam * c.N[3], c.dgam * c.N[1],
+                  c.dgam * c.N[5], c.dgam * c.N[4], c.dgam * c.N[5], c.dgam * c.N[2]};
+        S E[9];
+        expm3(A, E);
+        mm3(E, Fp_old, Fp_out);
+        write_Fp = true;
+      }
+    }
+  }
+  c.r[0][0] = -(c.r[1][0] + c.r[2][0] + c.r[3][0]);
+  c.r[0][1] = -(c.r[1][1] + c.r[2][1] + c.r[3][1]);
+  c.r[0][2] = -(c.r[1][2] + c.r[2][2] + c.r[3][2]);
+  c.A1 = c.beta * c.c1;
+  // sigma = s/J + pr*I (model), then Mixed: sigma_ii += p - tr(sigma)/3
+  S sig[6];
+  for (int i = 0; i < 3; ++i) sig[i] = snew[i] * rJ + pr;
+  for (int i = 3; i < 6; ++i) sig[i] = snew[i] * rJ;
+  S const pbar = (sig[0] + sig[1] + sig[2]) * S(1.0 / 3.0);
+  for (int i = 0; i < 3; ++i) sig[i] += c.pv - pbar;
+  if (save) {
+    sigma_out[0] = sig[0]; sigma_out[4] = sig[1]; sigma_out[8] = sig[2];
+    sigma_out[1] = sigma_out[3] = sig[3];
+    sigma_out[2] = sigma_out[6] = sig[4];
+    sigma_out[5] = sigma_out[7] = sig[5];
+  }
+  for (int i = 0; i < 6; ++i) c.tau[i] = J * sig[i];
+  return ERR_NONE;
+}
+
+// Element residual: ru[n*3+i] (momentum), rp[n] (pressure + stabilization).
+template <class S> GX_HD void element_residual(Core<S> const& c, Material const& mat, S ru[12], S rp[4]) {
+  S const base = (c.pv / mat.kappa - S(0.5) * (c.J - S(1.0) / c.J)) * S(0.25);
+  S const tj = c.taus * c.J;
+  for (int n = 0; n < 4; ++n) {
+    S tw[3];
+    sym_mv(c.tau, c.w[n], tw);
+    ru[3 * n] = c.vol * tw[0]; ru[3 * n + 1] = c.vol * tw[1]; ru[3 * n + 2] = c.vol * tw[2];
+    rp[n] = c.vol * (base + tj * dot3(c.q, c.w[n]));
+  }
+}
+
+// Per-column-node quantities of the Jacobian: everything that depends on m only.
+template <class S>
+struct ColNode {
+  S w[3], r[3], tw[3];  // w_m, r_m, tau w_m
+  S gam[3];             // gamma_mk multiplying s w_n
+  S qw;                 // q . w_m
+};
+
+template <class S> GX_HD void column_node(Core<S> const& c, int m, ColNode<S>& cn) {
+  for (int k = 0; k < 3; ++k) { cn.w[k] = c.w[m][k]; cn.r[k] = c.r[m][k]; }
+  sym_mv(c.tau, cn.w, cn.tw);
+  cn.qw = dot3(c.q, cn.w);
+  S const t23 = S(2.0 / 3.0);
+  if (c.plastic) {
+    S Nr[3];
+    sym_mv(c.N, cn.r, Nr);
+    S const rs = S(1.0) / c.smag;
+    for (int k = 0; k < 3; ++k) {
+      S const dmubar = t23 * (c.c1 * cn.r[k] - cn.w[k] * c.mubar);
+      S const dsmag = S(2.0) * c.c1 * Nr[k] - t23 * cn.w[k] * c.smag;
+      S const ddgam = (dsmag - S(2.0) * c.dgam * dmubar) / c.D;
+      S const dbeta = S(-2.0) * ((dmubar * c.dgam + c.mubar * ddgam) * rs - c.mubar * c.dgam * dsmag * rs * rs);
+      cn.gam[k] = dbeta - c.beta * t23 * cn.w[k];
+    }
+  } else {
+    for (int k = 0; k < 3; ++k) cn.gam[k] = -t23 * cn.w[k];
+  }
+}
+
+// 4x4 block K[(n,i),(m,k)], i,k = 0..3 (eq 3 = pressure), row-major in `blk`; m is the node `cn` was built for.
+// sw_n = s w_n is passed in because it is shared by the four column nodes.
+template <class S>
+GX_HD void jacobian_block(Core<S> const& c, Material const& mat, int n, ColNode<S> const& cn, S const sw[3],
+                          S blk[16]) {
+  S const* wn = c.w[n];
+  S const rw = dot3(cn.r, wn);
+  S const W = dot3(cn.w, wn);
+  S const qwn = dot3(c.q, wn);
+  S const Jp = c.J * c.pv;
+  S const t23 = S(2.0 / 3.0);
+  for (int i = 0; i < 3; ++i) {
+    for (int k = 0; k < 3; ++k) {
+      S v = c.A1 * (cn.r[i] * wn[k] - t23 * cn.r[k] * wn[i]) + cn.gam[k] * sw[i] + Jp * cn.w[k] * wn[i] - cn.tw[i] * wn[k];
+      if (i == k) v += c.A1 * rw;
+      blk[4 * i + k] = c.vol * v;
+    }
+    blk[4 * i + 3] = c.vol * c.J * S(0.25) * wn[i];  // d R_u / d p_m
+  }
+  S const tj = c.taus * c.J;
+  S const a = S(-0.125) * (S(1.0) + S(1.0) / (c.J * c.J)) * c.J;
+  for (int k = 0; k < 3; ++k) blk[12 + k] = c.vol * (a * cn.w[k] + tj * (cn.w[k] * qwn - c.q[k] * W - cn.qw * wn[k]));
+  blk[15] = c.vol * (S(1.0 / 16.0) / mat.kappa + tj * W);
+}
+
+// Residual of the error chain: the same integrand tested with the adjoint-weighted
+// partition of unity  w_n^i = z_i N_n,  d_j w_n^i = d_j z_i N_n + z_i d_j N_n
+// (goal_displacement_adjoint.cpp:48-52); PResidual uses z_p-diff, Stabilization uses
+// z_p-coarse (goal_mechanics.cpp:214).  zu: [4][3] nodal u_z_diff; zp, zpc: [4].
+template <class S>
+GX_HD void element_error_residual(Core<S> const& c, Material const& mat, S const zu[4][3], S const zp[4],
+                                  S const zpc[4], S ru[12], S rp[4]) {
+  S z[3], gz[9];
+  for (int i = 0; i < 3; ++i) {
+    z[i] = S(0.25) * zu[0][i] + S(0.25) * zu[1][i] + S(0.25) * zu[2][i] + S(0.25) * zu[3][i];
+    for (int j = 0; j < 3; ++j)
+      gz[3 * i + j] = (zu[1][i] - zu[0][i]) * c.G[1][j] + (zu[2][i] - zu[0][i]) * c.G[2][j] + (zu[3][i] - zu[0][i]) * c.G[3][j];
+  }
+  S const zs = S(0.25) * zp[0] + S(0.25) * zp[1] + S(0.25) * zp[2] + S(0.25) * zp[3];
+  S const zc = S(0.25) * zpc[0] + S(0.25) * zpc[1] + S(0.25) * zpc[2] + S(0.25) * zpc[3];
+  S gzc[3], hz[3];
+  for (int j = 0; j < 3; ++j) gzc[j] = (zpc[1] - zpc[0]) * c.G[1][j] + (zpc[2] - zpc[0]) * c.G[2][j] + (zpc[3] - zpc[0]) * c.G[3][j];
+  for (int k = 0; k < 3; ++k) hz[k] = c.Finv[k] * gzc[0] + c.Finv[3 + k] * gzc[1] + c.Finv[6 + k] * gzc[2];  // F^{-T} grad z_pc
+  // P = tau F^{-T}:  P_ij = sum_l tau_il Finv_jl ;  pg_i = sum_j P_ij gz_ij
+  S const T[9] = {c.tau[0], c.tau[3], c.tau[4], c.tau[3], c.tau[1], c.tau[5], c.tau[4], c.tau[5], c.tau[2]};
+  S pg[3];
+  for (int i = 0; i < 3; ++i) {
+    S acc = S(0.0);
+    for (int j = 0; j < 3; ++j) {
+      S const Pij = T[3 * i] * c.Finv[3 * j] + T[3 * i + 1] * c.Finv[3 * j + 1] + T[3 * i + 2] * c.Finv[3 * j + 2];
+      acc += Pij * gz[3 * i + j];
+    }
+    pg[i] = acc;
+  }
+  S const base = (c.pv / mat.kappa - S(0.5) * (c.J - S(1.0) / c.J)) * zs * S(0.25);
+  S const tj = c.taus * c.J;
+  S const qh = dot3(c.q, hz) * S(0.25);
+  for (int n = 0; n < 4; ++n) {
+    S tw[3];
+    sym_mv(c.tau, c.w[n], tw);
+    for (int i = 0; i < 3; ++i) ru[3 * n + i] = c.vol * (S(0.25) * pg[i] + z[i] * tw[i]);
+    rp[n] = c.vol * (base + tj * (qh + zc * dot3(c.q, c.w[n])));
+  }
+}
+
+}  // namespace gx

@@ -1,0 +1,544 @@
+// gx_api.cu -- C-ABI entry points (include/goal_b200.h) and launch plumbing.
+#include <cstdio>
+#include <cstring>
+
+#include "gx_internal.h"
+#include "gx_kernels.cuh"
+
+using namespace gx;
+
+#define GX_CUDA(call)                                                                          \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_);                           \
+      return GX_ERR_CUDA;                                                                      \
+    }                                                                                          \
+  } while (0)
+
+static thread_local std::string g_create_err;
+
+// ---------------------------------------------------------------------------
+// small utility kernels
+// ---------------------------------------------------------------------------
+__global__ void pack_solution_kernel(NodeRec* nodes, double const* u, double const* p, int nn) {
+  int const n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  nodes[n].u[0] = u[3 * (int64_t)n];
+  nodes[n].u[1] = u[3 * (int64_t)n + 1];
+  nodes[n].u[2] = u[3 * (int64_t)n + 2];
+  nodes[n].p = p[n];
+}
+
+__global__ void pack_z_kernel(ZRec* z, double const* zu, double const* zp, double const* zpc, int nn) {
+  int const n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  z[n].zu[0] = zu[3 * (int64_t)n];
+  z[n].zu[1] = zu[3 * (int64_t)n + 1];
+  z[n].zu[2] = zu[3 * (int64_t)n + 2];
+  z[n].zp = zp[n];
+  z[n].zpc = zpc[n];
+}
+
+// AoS (user element order, ncomp per element) <-> SoA (device element order)
+__global__ void aos_to_soa_kernel(double* soa, int64_t stride, double const* aos, int32_t const* perm, int ne, int ncomp) {
+  int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)ne * ncomp) return;
+  int const d = (int)(i / ncomp), k = (int)(i % ncomp);
+  soa[k * stride + d] = aos[(int64_t)perm[d] * ncomp + k];
+}
+__global__ void soa_to_aos_kernel(double* aos, double const* soa, int64_t stride, int32_t const* perm, int ne, int ncomp) {
+  int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)ne * ncomp) return;
+  int const d = (int)(i / ncomp), k = (int)(i % ncomp);
+  aos[(int64_t)perm[d] * ncomp + k] = soa[k * stride + d];
+}
+
+// compute_error (src/goal_error.cpp:7-35): |sum_d u_err_d(xi_c) + p_err(xi_c)|; err4 = [Nn][4] (u0,u1,u2,p)
+__global__ void element_error_kernel(double* eta, double4 const* err4, int4 const* conn, int32_t const* perm, int ne) {
+  int const d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= ne) return;
+  int4 const cn = __ldg(conn + d);
+  int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+  double ue[3] = {0, 0, 0}, pe = 0;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    double4 const v = err4[nd[n]];
+    pe += v.w * 0.25;
+    ue[0] += v.x * 0.25; ue[1] += v.y * 0.25; ue[2] += v.z * 0.25;
+  }
+  double total = 0.0;
+  total += ue[0]; total += ue[1]; total += ue[2];
+  total += pe;
+  eta[perm[d]] = fabs(total);
+}
+
+// Nested::set_error (src/goal_nested.cpp:395-412): parent error = sum of its children, in element order
+__global__ void parent_sum_kernel(double* eta_parent, double const* eta, int32_t const* child_off, int32_t const* child, int np) {
+  int const k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= np) return;
+  double s = 0.0;
+  for (int j = child_off[k]; j < child_off[k + 1]; ++j) s += eta[child[j]];
+  eta_parent[k] = s;
+}
+
+// sum_contribs (src/goal_error.cpp:37-56): sum over vertices of |u0+u1+u2+p|; fixed-shape tree -> deterministic
+__global__ void bound_partial_kernel(double* partial, double4 const* err4, int nn) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; n < nn; n += (int64_t)gridDim.x * blockDim.x) {
+    double4 const v = err4[n];
+    double t = 0.0;
+    t += v.x; t += v.y; t += v.z; t += v.w;
+    s += fabs(t);
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+__global__ void bound_final_kernel(double* out, double const* partial, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += partial[i];
+    *out = s;
+  }
+}
+__global__ void pack_err4_kernel(double4* err4, double const* ue, double const* pe, int nn) {
+  int const n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  err4[n] = make_double4(ue[3 * (int64_t)n], ue[3 * (int64_t)n + 1], ue[3 * (int64_t)n + 2], pe[n]);
+}
+
+// ---------------------------------------------------------------------------
+template <int MODEL, int PASS, bool SAVE>
+static cudaError_t launch_colours(gx_ctx* ctx, KParams& P) {
+  int const bs = (int)ctx->opt_block;
+  for (int k = 0; k < ctx->ncolors; ++k) {
+    P.e0 = ctx->color_off[k];
+    P.e1 = ctx->color_off[k + 1];
+    int const n = P.e1 - P.e0;
+    if (n <= 0) continue;
+    assemble_kernel<MODEL, PASS, SAVE><<<(n + bs - 1) / bs, bs, 0, ctx->stream>>>(P);
+    ctx->launches++;
+  }
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
+  switch (pass) {
+    case PASS_RESIDUAL: return save ? launch_colours<MODEL, PASS_RESIDUAL, true>(ctx, P) : launch_colours<MODEL, PASS_RESIDUAL, false>(ctx, P);
+    case PASS_JACOBIAN: return save ? launch_colours<MODEL, PASS_JACOBIAN, true>(ctx, P) : launch_colours<MODEL, PASS_JACOBIAN, false>(ctx, P);
+    case PASS_JACOBIAN_T: return save ? launch_colours<MODEL, PASS_JACOBIAN_T, true>(ctx, P) : launch_colours<MODEL, PASS_JACOBIAN_T, false>(ctx, P);
+    default: return launch_colours<MODEL, PASS_ERROR, false>(ctx, P);
+  }
+}
+
+static void fill_params(gx_ctx* ctx, KParams& P) {
+  P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
+  P.Fp_old = ctx->d_Fp_old; P.eqps_old = ctx->d_eqps_old; P.Fp = ctx->d_Fp; P.eqps = ctx->d_eqps; P.sigma = ctx->d_sigma;
+  P.sstride = ctx->sstride; P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
+  P.e0 = 0; P.e1 = 0;
+  for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
+}
+
+static int status_of_element_error(int code) {
+  switch (code) {
+    case ERR_INVERTED_ELEMENT: return GX_ERR_INVERTED_ELEMENT;
+    case ERR_INVERTED_DEFORMATION: return GX_ERR_INVERTED_DEFORMATION;
+    case ERR_J2_RETURN_MAP: return GX_ERR_J2_RETURN_MAP;
+    default: return GX_ERR_CUDA;
+  }
+}
+
+// zero + assemble on the ctx stream, then synchronise and collect the error flag / counters.
+static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
+  GX_CUDA(cudaSetDevice(ctx->device));
+  ctx->launches = 0;
+  int const zero2[2] = {0, 0};
+  GX_CUDA(cudaMemcpyAsync(ctx->d_err, zero2, sizeof zero2, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemsetAsync(ctx->d_plastic, 0, sizeof(unsigned long long), ctx->stream));
+  GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64)
+  GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
+  if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
+  GX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+  KParams P;
+  fill_params(ctx, P);
+  cudaError_t le = ctx->model == GX_MODEL_J2 ? launch_model<MODEL_J2>(ctx, P, pass, save)
+                                             : launch_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
+  if (le != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(le); return GX_ERR_CUDA; }
+  GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
+  int herr[2];
+  unsigned long long hpl = 0;
+  GX_CUDA(cudaMemcpyAsync(herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(&hpl, ctx->d_plastic, sizeof hpl, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  float t0 = 0, t1 = 0;
+  GX_CUDA(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
+  GX_CUDA(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
+  ctx->timing[0] = t0; ctx->timing[1] = t1; ctx->timing[2] = 0.0; ctx->timing[3] = ctx->launches;
+  ctx->last_plastic = (int64_t)hpl;
+  ctx->have_result = true;
+  ctx->have_values = with_values;
+  if (herr[0]) {
+    static const char* const what[] = {"", "inverted element (dv <= 0)", "inverted deformation (det F <= 0)", "J2: return mapping failed"};
+    char buf[160];
+    snprintf(buf, sizeof buf, "%s in element %d", what[herr[0] & 3], ctx->perm[herr[1]]);
+    ctx->err = buf;
+    return status_of_element_error(herr[0]);
+  }
+  return GX_OK;
+}
+
+static int fetch(gx_ctx* ctx, double* R_out, double* values_out) {
+  if (R_out) GX_CUDA(cudaMemcpyAsync(R_out, ctx->d_R, sizeof(double) * 4 * (size_t)ctx->nn, cudaMemcpyDeviceToHost, ctx->stream));
+  if (values_out) GX_CUDA(cudaMemcpyAsync(values_out, ctx->d_values, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (R_out || values_out) GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+static double** state_slot(gx_ctx* ctx, const char* name, int* ncomp) {
+  std::string n(name ? name : "");
+  *ncomp = 9;
+  if (n == "sigma") return &ctx->d_sigma;
+  if (ctx->model != GX_MODEL_J2) return nullptr;
+  if (n == "Fp") return &ctx->d_Fp;
+  if (n == "Fp_old") return &ctx->d_Fp_old;
+  *ncomp = 1;
+  if (n == "eqps") return &ctx->d_eqps;
+  if (n == "eqps_old") return &ctx->d_eqps_old;
+  return nullptr;
+}
+
+static void free_device(gx_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_sigma, ctx->d_eqps,
+                  ctx->d_eqps_old, ctx->d_Fp, ctx->d_Fp_old, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
+                  ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+}
+
+namespace gx { void comm_destroy(gx_ctx*); int comm_setup_lists(gx_ctx*, const gx_desc*); }
+
+// ---------------------------------------------------------------------------
+extern "C" {
+
+const char* gx_last_error(const gx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int gx_create(const gx_desc* d, gx_ctx** out) {
+  if (!d || !out) { g_create_err = "gx_create: null argument"; return GX_ERR_ARG; }
+  *out = nullptr;
+  if (d->n_nodes <= 0 || d->n_elems <= 0 || !d->conn || !d->coords || !d->materials || d->n_elem_sets < 1 ||
+      d->n_elem_sets > GX_MAX_ELEM_SETS || (d->model != GX_MODEL_NEOHOOKEAN && d->model != GX_MODEL_J2)) {
+    g_create_err = "gx_create: invalid description";
+    return GX_ERR_ARG;
+  }
+  if (d->flags & GX_FLAG_NO_STABILIZATION) { g_create_err = "gx_create: stabilization: false is not supported"; return GX_ERR_UNSUPPORTED; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || d->device < 0 || d->device >= ndev) {
+    g_create_err = "gx_create: no usable CUDA device (this library has no CPU path)";
+    return GX_ERR_CUDA;
+  }
+  gx_ctx* ctx = new gx_ctx;
+  ctx->nn = d->n_nodes; ctx->ne = d->n_elems; ctx->nsets = d->n_elem_sets; ctx->model = d->model;
+  ctx->device = d->device; ctx->flags = d->flags;
+  ctx->rank = d->n_ranks > 1 ? d->rank : 0;
+  ctx->nranks = d->n_ranks > 1 ? d->n_ranks : 1;
+  ctx->conn.assign(d->conn, d->conn + 4 * (size_t)d->n_elems);
+  ctx->coords.assign(d->coords, d->coords + 3 * (size_t)d->n_nodes);
+  if (d->elem_set && d->n_elem_sets > 1) ctx->eset.assign(d->elem_set, d->elem_set + d->n_elems);
+  for (int s = 0; s < ctx->nsets; ++s) {
+    double const E = d->materials[5 * s], nu = d->materials[5 * s + 1];
+    ctx->mats[s].kappa = E / (3.0 * (1.0 - 2.0 * nu));  // goal_neohookean.cpp:50, goal_J2.cpp:62
+    ctx->mats[s].mu = E / (2.0 * (1.0 + nu));           // goal_neohookean.cpp:51, goal_J2.cpp:63
+    ctx->mats[s].K = d->materials[5 * s + 2];
+    ctx->mats[s].Y = d->materials[5 * s + 3];
+    ctx->mats[s].c0 = d->materials[5 * s + 4];
+  }
+  auto fail = [&](int rc) { g_create_err = ctx->err; free_device(ctx); comm_destroy(ctx); delete ctx; return rc; };
+  for (int e = 0; e < ctx->ne && !ctx->eset.empty(); ++e)
+    if (ctx->eset[e] < 0 || ctx->eset[e] >= ctx->nsets) { ctx->err = "elem_set entry out of range"; return fail(GX_ERR_ARG); }
+  int rc = build_graph_and_schedule(ctx);
+  if (rc) return fail(rc);
+  rc = comm_setup_lists(ctx, d);
+  if (rc) return fail(rc);
+
+  auto body = [&]() -> int {
+    GX_CUDA(cudaSetDevice(ctx->device));
+    GX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    for (auto& e : ctx->ev) GX_CUDA(cudaEventCreate(&e));
+    int const nn = ctx->nn, ne = ctx->ne;
+    ctx->sstride = ((int64_t)ne + 31) / 32 * 32;
+    // ---- nodes and elements (device element order = colour-sorted)
+    HostPack hp;
+    pack_host(ctx, hp);
+    GX_CUDA(cudaMalloc(&ctx->d_nodes, sizeof(NodeRec) * (size_t)nn));
+    GX_CUDA(cudaMemcpy(ctx->d_nodes, hp.nodes.data(), sizeof(NodeRec) * (size_t)nn, cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_z, sizeof(ZRec) * (size_t)nn));
+    GX_CUDA(cudaMemset(ctx->d_z, 0, sizeof(ZRec) * (size_t)nn));
+    GX_CUDA(cudaMalloc(&ctx->d_conn, sizeof(int4) * (size_t)ne));
+    GX_CUDA(cudaMemcpy(ctx->d_conn, hp.conn4.data(), sizeof(int4) * (size_t)ne, cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_bpos, sizeof(uint4) * (size_t)ne));
+    GX_CUDA(cudaMemcpy(ctx->d_bpos, hp.bpos.data(), sizeof(uint4) * (size_t)ne, cudaMemcpyHostToDevice));
+    if (!hp.eset.empty()) {
+      GX_CUDA(cudaMalloc(&ctx->d_eset, (size_t)ne));
+      GX_CUDA(cudaMemcpy(ctx->d_eset, hp.eset.data(), (size_t)ne, cudaMemcpyHostToDevice));
+    }
+    GX_CUDA(cudaMalloc(&ctx->d_perm, sizeof(int32_t) * (size_t)ne));
+    GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
+    // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
+    size_t const s9 = sizeof(double) * 9 * (size_t)ctx->sstride, s1 = sizeof(double) * (size_t)ctx->sstride;
+    GX_CUDA(cudaMalloc(&ctx->d_sigma, s9));
+    GX_CUDA(cudaMemset(ctx->d_sigma, 0, s9));
+    if (ctx->model == GX_MODEL_J2) {
+      GX_CUDA(cudaMalloc(&ctx->d_eqps, s1)); GX_CUDA(cudaMemset(ctx->d_eqps, 0, s1));
+      GX_CUDA(cudaMalloc(&ctx->d_eqps_old, s1)); GX_CUDA(cudaMemset(ctx->d_eqps_old, 0, s1));
+      GX_CUDA(cudaMalloc(&ctx->d_Fp, s9));
+      GX_CUDA(cudaMalloc(&ctx->d_Fp_old, s9));
+      std::vector<double> I9(9 * (size_t)ctx->sstride, 0.0);
+      for (int k = 0; k < 9; k += 4) std::fill(I9.begin() + k * ctx->sstride, I9.begin() + (k + 1) * ctx->sstride, 1.0);
+      GX_CUDA(cudaMemcpy(ctx->d_Fp, I9.data(), s9, cudaMemcpyHostToDevice));
+      GX_CUDA(cudaMemcpy(ctx->d_Fp_old, I9.data(), s9, cudaMemcpyHostToDevice));
+    }
+    // ---- linear objects (SolInfo ghost R / dRdu, src/goal_sol_info.cpp:6-22)
+    GX_CUDA(cudaMalloc(&ctx->d_R, sizeof(double) * 4 * (size_t)nn));
+    GX_CUDA(cudaMemset(ctx->d_R, 0, sizeof(double) * 4 * (size_t)nn));
+    GX_CUDA(cudaMalloc(&ctx->d_values, sizeof(double) * (size_t)std::max<int64_t>(ctx->nnz, 1)));
+    GX_CUDA(cudaMemset(ctx->d_values, 0, sizeof(double) * (size_t)std::max<int64_t>(ctx->nnz, 1)));
+    ctx->stage_len = std::max<int64_t>(8 * (int64_t)nn, 9 * (int64_t)ne) + 64;
+    GX_CUDA(cudaMalloc(&ctx->d_stage, sizeof(double) * (size_t)ctx->stage_len));
+    GX_CUDA(cudaMalloc(&ctx->d_err, 2 * sizeof(int)));
+    GX_CUDA(cudaMalloc(&ctx->d_plastic, sizeof(unsigned long long)));
+    GX_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * 1024));
+    return GX_OK;
+  };
+  rc = body();
+  if (rc) return fail(rc);
+  *out = ctx;
+  return GX_OK;
+}
+
+int gx_destroy(gx_ctx* ctx) {
+  if (!ctx) return GX_OK;
+  comm_destroy(ctx);
+  free_device(ctx);
+  delete ctx;
+  return GX_OK;
+}
+
+int gx_graph(gx_ctx* ctx, int64_t* nnz, const int64_t** rowptr, const int32_t** colind) {
+  if (!ctx) return GX_ERR_ARG;
+  materialise_crs(ctx);
+  if (nnz) *nnz = ctx->nnz;
+  if (rowptr) *rowptr = ctx->rowptr.data();
+  if (colind) *colind = ctx->colind.data();
+  return GX_OK;
+}
+
+int gx_graph_size(gx_ctx* ctx, int64_t* nnz, int32_t* n_rows) {
+  if (!ctx) return GX_ERR_ARG;
+  if (nnz) *nnz = ctx->nnz;
+  if (n_rows) *n_rows = 4 * ctx->nn;
+  return GX_OK;
+}
+
+int gx_scatter_map(gx_ctx* ctx, uint8_t* bpos) {
+  if (!ctx || !bpos) return GX_ERR_ARG;
+  memcpy(bpos, ctx->bpos.data(), ctx->bpos.size());
+  return GX_OK;
+}
+
+int gx_set_solution(gx_ctx* ctx, const double* u, const double* p) {
+  if (!ctx || !u || !p) { if (ctx) ctx->err = "gx_set_solution: null argument"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nn = ctx->nn;
+  double* du = ctx->d_stage;
+  double* dp = ctx->d_stage + 3 * (size_t)nn;
+  GX_CUDA(cudaMemcpyAsync(du, u, sizeof(double) * 3 * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(dp, p, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  pack_solution_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nodes, du, dp, nn);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_get_state(gx_ctx* ctx, const char* name, double* out) {
+  if (!ctx || !out) return GX_ERR_ARG;
+  int nc;
+  double** slot = state_slot(ctx, name, &nc);
+  if (!slot || !*slot) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int64_t const tot = (int64_t)ctx->ne * nc;
+  soa_to_aos_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stage, *slot, ctx->sstride, ctx->d_perm, ctx->ne, nc);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaMemcpyAsync(out, ctx->d_stage, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_set_state(gx_ctx* ctx, const char* name, const double* in) {
+  if (!ctx || !in) return GX_ERR_ARG;
+  int nc;
+  double** slot = state_slot(ctx, name, &nc);
+  if (!slot || !*slot) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int64_t const tot = (int64_t)ctx->ne * nc;
+  GX_CUDA(cudaMemcpyAsync(ctx->d_stage, in, sizeof(double) * (size_t)tot, cudaMemcpyHostToDevice, ctx->stream));
+  aos_to_soa_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(*slot, ctx->sstride, ctx->d_stage, ctx->d_perm, ctx->ne, nc);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_update_states(gx_ctx* ctx) {
+  if (!ctx) return GX_ERR_ARG;
+  if (ctx->model != GX_MODEL_J2) return GX_OK;  // only J2 registers old states (goal_mechanics.cpp:90-93)
+  GX_CUDA(cudaSetDevice(ctx->device));
+  GX_CUDA(cudaMemcpyAsync(ctx->d_eqps_old, ctx->d_eqps, sizeof(double) * (size_t)ctx->sstride, cudaMemcpyDeviceToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(ctx->d_Fp_old, ctx->d_Fp, sizeof(double) * 9 * (size_t)ctx->sstride, cudaMemcpyDeviceToDevice, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_compute_residual(gx_ctx* ctx, int save_state, double* R_out) {
+  if (!ctx) return GX_ERR_ARG;
+  int rc = run_pass(ctx, PASS_RESIDUAL, save_state != 0, false);
+  if (rc) return rc;
+  return fetch(ctx, R_out, nullptr);
+}
+
+int gx_compute_jacobian(gx_ctx* ctx, int mode, int save_state, double* R_out, double* values_out) {
+  if (!ctx) return GX_ERR_ARG;
+  if (mode != GX_MODE_PRIMAL && mode != GX_MODE_ADJOINT) { ctx->err = "gx_compute_jacobian: mode must be PRIMAL or ADJOINT"; return GX_ERR_ARG; }
+  int rc = run_pass(ctx, mode == GX_MODE_PRIMAL ? PASS_JACOBIAN : PASS_JACOBIAN_T, save_state != 0, true);
+  if (rc) return rc;
+  return fetch(ctx, R_out, values_out);
+}
+
+int gx_localize_error(gx_ctx* ctx, const double* zu_diff, const double* zp_diff, const double* zp_coarse, double* R_out) {
+  if (!ctx || !zu_diff || !zp_diff || !zp_coarse) { if (ctx) ctx->err = "gx_localize_error: null argument"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nn = ctx->nn;
+  double* a = ctx->d_stage;
+  double* b = a + 3 * (size_t)nn;
+  double* c = b + nn;
+  GX_CUDA(cudaMemcpyAsync(a, zu_diff, sizeof(double) * 3 * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(b, zp_diff, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(c, zp_coarse, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  pack_z_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_z, a, b, c, nn);
+  GX_CUDA(cudaGetLastError());
+  int rc = run_pass(ctx, PASS_ERROR, false, false);
+  if (rc) return rc;
+  return fetch(ctx, R_out, nullptr);
+}
+
+int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, const int32_t* parent, int32_t n_parent,
+                     double* eta_elem, double* eta_parent, double* bound) {
+  if (!ctx || !u_err || !p_err) { if (ctx) ctx->err = "gx_element_error: null argument"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nn = ctx->nn, ne = ctx->ne;
+  // stage layout: [0,3nn) u_err, [3nn,4nn) p_err, [4nn,8nn) err4; eta reuses d_values-independent scratch below
+  double* a = ctx->d_stage;
+  double* b = a + 3 * (size_t)nn;
+  double4* err4 = reinterpret_cast<double4*>(a + 4 * (size_t)nn);
+  GX_CUDA(cudaMemcpyAsync(a, u_err, sizeof(double) * 3 * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(b, p_err, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  pack_err4_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(err4, a, b, nn);
+  GX_CUDA(cudaGetLastError());
+  double* d_eta = nullptr;
+  double* d_etap = nullptr;
+  GX_CUDA(cudaMallocAsync(&d_eta, sizeof(double) * (size_t)ne, ctx->stream));
+  element_error_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(d_eta, err4, ctx->d_conn, ctx->d_perm, ne);
+  GX_CUDA(cudaGetLastError());
+  if (parent && eta_parent && n_parent > 0) {
+    if (ctx->n_parent_cached != n_parent || ctx->parent_cached.size() != (size_t)ne ||
+        memcmp(ctx->parent_cached.data(), parent, sizeof(int32_t) * (size_t)ne) != 0) {
+      for (int e = 0; e < ne; ++e)
+        if (parent[e] < 0 || parent[e] >= n_parent) { ctx->err = "gx_element_error: parent index out of range"; cudaFreeAsync(d_eta, ctx->stream); return GX_ERR_ARG; }
+      std::vector<int32_t> off(n_parent + 1, 0), child(ne);
+      for (int e = 0; e < ne; ++e) off[parent[e] + 1]++;
+      for (int k = 0; k < n_parent; ++k) off[k + 1] += off[k];
+      std::vector<int32_t> cur(off.begin(), off.end() - 1);
+      for (int e = 0; e < ne; ++e) child[cur[parent[e]]++] = e;
+      if (ctx->d_child_off) { cudaFree(ctx->d_child_off); ctx->d_child_off = nullptr; }
+      if (ctx->d_child) { cudaFree(ctx->d_child); ctx->d_child = nullptr; }
+      GX_CUDA(cudaMalloc(&ctx->d_child_off, sizeof(int32_t) * (size_t)(n_parent + 1)));
+      GX_CUDA(cudaMalloc(&ctx->d_child, sizeof(int32_t) * (size_t)ne));
+      GX_CUDA(cudaMemcpy(ctx->d_child_off, off.data(), sizeof(int32_t) * (size_t)(n_parent + 1), cudaMemcpyHostToDevice));
+      GX_CUDA(cudaMemcpy(ctx->d_child, child.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
+      ctx->parent_cached.assign(parent, parent + ne);
+      ctx->n_parent_cached = n_parent;
+    }
+    GX_CUDA(cudaMallocAsync(&d_etap, sizeof(double) * (size_t)n_parent, ctx->stream));
+    parent_sum_kernel<<<(n_parent + 255) / 256, 256, 0, ctx->stream>>>(d_etap, d_eta, ctx->d_child_off, ctx->d_child, n_parent);
+    GX_CUDA(cudaGetLastError());
+    GX_CUDA(cudaMemcpyAsync(eta_parent, d_etap, sizeof(double) * (size_t)n_parent, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (bound) {
+    int const nb = std::min(1024, (nn + 255) / 256);
+    bound_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, err4, nn);
+    bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb < 1023 ? nb : 1023);
+    GX_CUDA(cudaGetLastError());
+    GX_CUDA(cudaMemcpyAsync(bound, ctx->d_red + 1023, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (eta_elem) GX_CUDA(cudaMemcpyAsync(eta_elem, d_eta, sizeof(double) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaFreeAsync(d_eta, ctx->stream));
+  if (d_etap) GX_CUDA(cudaFreeAsync(d_etap, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_result_dev(gx_ctx* ctx, double** R_dev, double** values_dev) {
+  if (!ctx) return GX_ERR_ARG;
+  if (R_dev) *R_dev = ctx->d_R;
+  if (values_dev) *values_dev = ctx->d_values;
+  return GX_OK;
+}
+
+int gx_fetch(gx_ctx* ctx, double* R_out, double* values_out) {
+  if (!ctx) return GX_ERR_ARG;
+  if (!ctx->have_result) { ctx->err = "gx_fetch: no result yet"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  return fetch(ctx, R_out, values_out);
+}
+
+int gx_plastic_count(gx_ctx* ctx, int64_t* n) {
+  if (!ctx || !n) return GX_ERR_ARG;
+  *n = ctx->last_plastic;
+  return GX_OK;
+}
+
+int gx_num_colors(gx_ctx* ctx, int32_t* n) {
+  if (!ctx || !n) return GX_ERR_ARG;
+  *n = ctx->ncolors;
+  return GX_OK;
+}
+
+void* gx_stream(gx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int gx_last_timing(gx_ctx* ctx, double t[4]) {
+  if (!ctx || !t) return GX_ERR_ARG;
+  for (int i = 0; i < 4; ++i) t[i] = ctx->timing[i];
+  return GX_OK;
+}
+
+int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
+  if (!ctx || !key) return GX_ERR_ARG;
+  std::string k(key);
+  if (k == "block_size") {
+    if (value < 32 || value > 128 || (value & 31)) { ctx->err = "block_size must be 32, 64, 96 or 128"; return GX_ERR_ARG; }
+    ctx->opt_block = value;
+    return GX_OK;
+  }
+  ctx->err = "unknown option: " + k;
+  return GX_ERR_ARG;
+}
+
+}  // extern "C"

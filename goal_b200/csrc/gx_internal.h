@@ -1,0 +1,130 @@
+// gx_internal.h -- context layout shared by the host setup code and the CUDA side.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/goal_b200.h"
+#include "element_math.cuh"
+
+namespace gx {
+
+// One node as the kernels gather it: 64 bytes, one aligned line-half.
+//   d0 = (x, y)  d1 = (z, ux)  d2 = (uy, uz)  d3 = (p, {blk0, nblk})
+// blk0 = index of the node's first 4x4 block in the block-CRS (value offset of
+// dof row 4a+i is 16*blk0 + i*4*nblk), nblk = number of node blocks in its row.
+struct alignas(64) NodeRec {
+  double x[3];
+  double u[3];
+  double p;
+  int32_t blk0;
+  int32_t nblk;
+};
+static_assert(sizeof(NodeRec) == 64, "NodeRec must be 64 bytes");
+
+// adjoint weights gathered by the error-localisation kernel: (zu0,zu1) (zu2,zp) (zpc,-) -> 48 B padded to 64
+struct alignas(64) ZRec {
+  double zu[3];
+  double zp;
+  double zpc;
+  double pad[3];
+};
+static_assert(sizeof(ZRec) == 64, "ZRec must be 64 bytes");
+
+struct Peer {
+  int rank = -1;
+  std::vector<int32_t> nodes;       // shared nodes, agreed order
+  std::vector<int32_t> send_nodes;  // subset owned by the peer   (we send our partial rows)
+  std::vector<int32_t> recv_nodes;  // subset owned by this rank  (we receive and add)
+  // device side
+  int32_t* d_send_nodes = nullptr;
+  int32_t* d_recv_nodes = nullptr;
+  int64_t* d_send_off = nullptr;  // [n_send+1] offsets (in doubles) of each node's packed block rows
+  int64_t* d_recv_off = nullptr;
+  // column translation for received rows: for recv node j, for each block sent by the peer, the
+  // local block position it adds into (or -1 if this part does not have that column)
+  int32_t* d_recv_map = nullptr;
+  std::vector<int64_t> send_off, recv_off;
+  int64_t send_vals = 0, recv_vals = 0;  // doubles of CRS payload
+  double* d_send = nullptr;
+  double* d_recv = nullptr;
+};
+
+struct NcclApi;  // resolved with dlopen (gx_nccl.cpp)
+
+}  // namespace gx
+
+struct gx_ctx {
+  // ---- description
+  int nn = 0, ne = 0, nsets = 1, model = 0, device = 0;
+  uint32_t flags = 0;
+  int rank = 0, nranks = 1;
+  gx::Material mats[GX_MAX_ELEM_SETS];
+  std::vector<int32_t> conn;    // user order
+  std::vector<double> coords;
+  std::vector<int32_t> eset;
+  std::vector<int64_t> node_gid;
+  std::vector<int32_t> node_owner;
+  // ---- graph (host)
+  std::vector<int64_t> nrow;    // [nn+1] block-row offsets
+  std::vector<int32_t> ncol;    // [nblocks] neighbour node of each block, sorted per row
+  int64_t nnz = 0;
+  std::vector<int64_t> rowptr;  // lazily materialised dof-level CRS
+  std::vector<int32_t> colind;
+  std::vector<uint8_t> bpos;    // [ne*16] user order
+  // ---- schedule
+  int ncolors = 0;
+  std::vector<int32_t> color_off;  // [ncolors+1] in device element order
+  std::vector<int32_t> perm;       // device slot -> user element
+  // ---- device
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  gx::NodeRec* d_nodes = nullptr;
+  gx::ZRec* d_z = nullptr;
+  int4* d_conn = nullptr;
+  uint4* d_bpos = nullptr;
+  uint8_t* d_eset = nullptr;
+  int32_t* d_perm = nullptr;
+  int64_t sstride = 0;  // SoA stride of state arrays (elements, padded)
+  double *d_sigma = nullptr, *d_eqps = nullptr, *d_eqps_old = nullptr, *d_Fp = nullptr, *d_Fp_old = nullptr;
+  double* d_R = nullptr;
+  double* d_values = nullptr;
+  double* d_stage = nullptr;  // staging for host<->device field copies, >= max(4*nn, 10*ne) doubles
+  int64_t stage_len = 0;
+  int* d_err = nullptr;                 // {code, element}
+  unsigned long long* d_plastic = nullptr;
+  double* d_red = nullptr;              // reduction scratch
+  int32_t* d_child_off = nullptr;       // parent -> children CRS for set_error
+  int32_t* d_child = nullptr;
+  int n_parent_cached = -1;
+  std::vector<int32_t> parent_cached;
+  // ---- partition
+  std::vector<gx::Peer> peers;
+  gx::NcclApi* nccl = nullptr;
+  void* comm = nullptr;
+  // ---- bookkeeping
+  int64_t last_plastic = 0;
+  double timing[4] = {0, 0, 0, 0};
+  int launches = 0;
+  bool have_result = false;
+  bool have_values = false;
+  int64_t opt_block = 128;
+  std::string err;
+};
+
+namespace gx {
+// host setup (gx_setup.cpp)
+int build_graph_and_schedule(gx_ctx* c);
+void materialise_crs(gx_ctx* c);
+// host images of the device arrays, in device (colour-sorted) element order
+struct HostPack {
+  std::vector<NodeRec> nodes;
+  std::vector<int4> conn4;
+  std::vector<uint4> bpos;
+  std::vector<uint8_t> eset;
+};
+void pack_host(gx_ctx const* c, HostPack& h);
+}  // namespace gx

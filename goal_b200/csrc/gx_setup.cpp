@@ -1,0 +1,170 @@
+// gx_setup.cpp -- host-side, once-per-mesh setup: the CRS operator skeleton, the
+// element -> nonzero scatter map and the conflict-free element schedule.
+//
+// Replaces Disc::compute_graphs (src/goal_disc.cpp:307-332), which inserts every
+// (row dof, col dof) pair of every element one column at a time and lets Tpetra
+// sort and merge at fillComplete.  Because dofs are node-blocked with 4 equations
+// per node (src/goal_disc.cpp:195-201) the dof graph is the node adjacency graph
+// with every entry expanded to a 4x4 block, so the graph is built at node level:
+//   nrow/ncol : block-CRS of "nodes sharing an element", each row sorted
+//   dof row 4a+i  = the same block row, columns 4b+k, b in ncol order, k = 0..3
+// which is exactly Tpetra's sorted-unique local layout for the ghost graph (the
+// ghost column map equals the ghost row map).
+//
+// The schedule is a greedy element colouring: two elements of one colour share no
+// node, so their scatters into R and into the CRS values touch disjoint rows and
+// the assembly needs no atomics and is bit-reproducible run to run.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "gx_internal.h"
+
+namespace gx {
+
+int build_graph_and_schedule(gx_ctx* c) {
+  int const nn = c->nn, ne = c->ne;
+  int32_t const* conn = c->conn.data();
+  for (int64_t i = 0; i < 4 * (int64_t)ne; ++i)
+    if (conn[i] < 0 || conn[i] >= nn) { c->err = "conn entry out of range"; return GX_ERR_ARG; }
+
+  // ---- node -> elements (counting sort)
+  std::vector<int64_t> n2e_off(nn + 1, 0);
+  for (int64_t i = 0; i < 4 * (int64_t)ne; ++i) n2e_off[conn[i] + 1]++;
+  for (int n = 0; n < nn; ++n) n2e_off[n + 1] += n2e_off[n];
+  std::vector<int32_t> n2e(n2e_off[nn]);
+  {
+    std::vector<int64_t> cur(n2e_off.begin(), n2e_off.end() - 1);
+    for (int e = 0; e < ne; ++e)
+      for (int a = 0; a < 4; ++a) n2e[cur[conn[4 * (int64_t)e + a]]++] = e;
+  }
+
+  // ---- node adjacency, sorted unique per row (two passes: count, fill)
+  c->nrow.assign(nn + 1, 0);
+  int bad_row = 0;
+#pragma omp parallel
+  {
+    std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 4096)
+    for (int n = 0; n < nn; ++n) {
+      tmp.clear();
+      for (int64_t k = n2e_off[n]; k < n2e_off[n + 1]; ++k) {
+        int32_t const* en = conn + 4 * (int64_t)n2e[k];
+        tmp.insert(tmp.end(), en, en + 4);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      int64_t const cnt = std::unique(tmp.begin(), tmp.end()) - tmp.begin();
+      if (cnt > 255) bad_row = 1;
+      c->nrow[n + 1] = cnt;
+    }
+  }
+  if (bad_row) { c->err = "a node has more than 255 neighbours (scatter map is 8-bit)"; return GX_ERR_UNSUPPORTED; }
+  for (int n = 0; n < nn; ++n) c->nrow[n + 1] += c->nrow[n];
+  if (c->nrow[nn] > 0x7fffffffLL) { c->err = "more than 2^31 node blocks"; return GX_ERR_UNSUPPORTED; }
+  c->ncol.resize(c->nrow[nn]);
+  c->nnz = 16 * c->nrow[nn];
+#pragma omp parallel
+  {
+    std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 4096)
+    for (int n = 0; n < nn; ++n) {
+      tmp.clear();
+      for (int64_t k = n2e_off[n]; k < n2e_off[n + 1]; ++k) {
+        int32_t const* en = conn + 4 * (int64_t)n2e[k];
+        tmp.insert(tmp.end(), en, en + 4);
+      }
+      std::sort(tmp.begin(), tmp.end());
+      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+      std::copy(tmp.begin(), tmp.end(), c->ncol.begin() + c->nrow[n]);
+    }
+  }
+
+  // ---- scatter map: position of block (a_n, a_m) in a_n's block row
+  c->bpos.resize(16 * (size_t)ne);
+#pragma omp parallel for schedule(static)
+  for (int e = 0; e < ne; ++e) {
+    int32_t const* en = conn + 4 * (int64_t)e;
+    for (int n = 0; n < 4; ++n) {
+      int32_t const* b = c->ncol.data() + c->nrow[en[n]];
+      int32_t const* end = c->ncol.data() + c->nrow[en[n] + 1];
+      for (int m = 0; m < 4; ++m) c->bpos[16 * (size_t)e + 4 * n + m] = (uint8_t)(std::lower_bound(b, end, en[m]) - b);
+    }
+  }
+
+  // ---- greedy colouring over node conflicts (elements sharing a node get different colours)
+  constexpr int W = 4;  // 256 colours at most
+  std::vector<uint64_t> used((size_t)nn * W, 0);
+  std::vector<uint8_t> color(ne);
+  int ncolors = 0;
+  for (int e = 0; e < ne; ++e) {
+    int32_t const* en = conn + 4 * (int64_t)e;
+    int col = -1;
+    for (int w = 0; w < W && col < 0; ++w) {
+      uint64_t m = used[(size_t)en[0] * W + w] | used[(size_t)en[1] * W + w] | used[(size_t)en[2] * W + w] |
+                   used[(size_t)en[3] * W + w];
+      if (~m) col = 64 * w + __builtin_ctzll(~m);
+    }
+    if (col < 0) { c->err = "element colouring needs more than 256 colours"; return GX_ERR_UNSUPPORTED; }
+    color[e] = (uint8_t)col;
+    for (int a = 0; a < 4; ++a) used[(size_t)en[a] * W + col / 64] |= 1ull << (col % 64);
+    ncolors = std::max(ncolors, col + 1);
+  }
+  c->ncolors = ncolors;
+  c->color_off.assign(ncolors + 1, 0);
+  for (int e = 0; e < ne; ++e) c->color_off[color[e] + 1]++;
+  for (int k = 0; k < ncolors; ++k) c->color_off[k + 1] += c->color_off[k];
+  c->perm.resize(ne);
+  {
+    std::vector<int32_t> cur(c->color_off.begin(), c->color_off.end() - 1);
+    for (int e = 0; e < ne; ++e) c->perm[cur[color[e]]++] = e;  // stable: natural order inside a colour
+  }
+  return GX_OK;
+}
+
+void pack_host(gx_ctx const* c, HostPack& h) {
+  int const nn = c->nn, ne = c->ne;
+  h.nodes.resize(nn);
+  for (int n = 0; n < nn; ++n) {
+    NodeRec& r = h.nodes[n];
+    for (int j = 0; j < 3; ++j) { r.x[j] = c->coords[3 * (size_t)n + j]; r.u[j] = 0.0; }
+    r.p = 0.0;
+    r.blk0 = (int32_t)c->nrow[n];
+    r.nblk = (int32_t)(c->nrow[n + 1] - c->nrow[n]);
+  }
+  h.conn4.resize(ne);
+  h.bpos.resize(ne);
+  h.eset.clear();
+  if (!c->eset.empty()) h.eset.resize(ne);
+  for (int d = 0; d < ne; ++d) {
+    int const e = c->perm[d];
+    int32_t const* c4 = &c->conn[4 * (size_t)e];
+    h.conn4[d].x = c4[0]; h.conn4[d].y = c4[1]; h.conn4[d].z = c4[2]; h.conn4[d].w = c4[3];
+    memcpy(&h.bpos[d], &c->bpos[16 * (size_t)e], 16);
+    if (!h.eset.empty()) h.eset[d] = (uint8_t)c->eset[e];
+  }
+}
+
+void materialise_crs(gx_ctx* c) {
+  if (!c->rowptr.empty()) return;
+  int const nn = c->nn;
+  c->rowptr.resize(4 * (size_t)nn + 1);
+  c->colind.resize(c->nnz);
+  c->rowptr[0] = 0;
+  for (int n = 0; n < nn; ++n) {
+    int64_t const len = 4 * (c->nrow[n + 1] - c->nrow[n]);
+    for (int i = 0; i < 4; ++i) c->rowptr[4 * (size_t)n + i + 1] = 16 * c->nrow[n] + (i + 1) * len;
+  }
+#pragma omp parallel for schedule(static)
+  for (int n = 0; n < nn; ++n) {
+    int64_t const nb = c->nrow[n + 1] - c->nrow[n];
+    for (int i = 0; i < 4; ++i) {
+      int32_t* dst = c->colind.data() + c->rowptr[4 * (size_t)n + i];
+      for (int64_t j = 0; j < nb; ++j) {
+        int32_t const b = c->ncol[c->nrow[n] + j];
+        dst[4 * j] = 4 * b; dst[4 * j + 1] = 4 * b + 1; dst[4 * j + 2] = 4 * b + 2; dst[4 * j + 3] = 4 * b + 3;
+      }
+    }
+  }
+}
+
+}  // namespace gx

@@ -1,0 +1,163 @@
+/* goal_b200.h -- C-ABI of the B200 assembly path for bgranzow/goal.
+ *
+ * The reference has no FFI: its assembly hot path is the C++ plug-in loop
+ *   goal::assemble(Evaluators const&, SolInfo*)          src/goal_assembly.hpp:17
+ * driven by
+ *   Primal::compute_resid / compute_jacob                src/goal_primal.cpp:75-109
+ *   NestedAdjoint::compute_adjoint / localize            src/goal_nested_adjoint.cpp:163-234
+ * over Disc's maps/graphs (src/goal_disc.hpp:27-93), SolInfo's owned/ghost
+ * R/dRdu (src/goal_sol_info.hpp:12-39) and the States history fields
+ * (src/goal_states.hpp:13-23).  Each entry point below replaces one of those
+ * call sites; the replaced reference interface is cited per function and the
+ * binding a Goal maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C, no C++/torch types; every function returns gx_status (0 = ok) and
+ *    leaves a message for gx_last_error().  The reference aborts through
+ *    goal::fail() (src/goal_control.cpp:91-99); a shim maps non-zero to fail().
+ *  - LO = int32_t local index, GO = int64_t global index (src/goal_data_types.hpp:13-14).
+ *  - dof = node*4 + eq, eq 0..2 = u, eq 3 = p (src/goal_disc.cpp:195-201).
+ *  - "ghost" numbering = all nodes present on the part (apf::numberOverlapNodes,
+ *    src/goal_disc.cpp:294); "owned" = the subset this part owns (:273).
+ *  - host pointers unless a name ends in _dev.  Host buffers should be pinned
+ *    (cudaHostAlloc/cudaHostRegister) for full PCIe rate; pageable memory works.
+ *  - one gx_ctx per GPU / MPI rank; calls on one ctx are serialised by the caller;
+ *    every entry point is synchronous on return.
+ *  - there is NO CPU fallback: without a CUDA device gx_create fails.
+ */
+#ifndef GOAL_B200_H
+#define GOAL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gx_ctx gx_ctx;
+
+typedef enum {
+  GX_OK = 0,
+  GX_ERR_ARG = 1,                   /* bad argument / call order */
+  GX_ERR_CUDA = 2,                  /* CUDA runtime failure (message has the cudaError) */
+  GX_ERR_INVERTED_ELEMENT = 3,      /* dv <= 0 (apf::getDV), element id in message */
+  GX_ERR_INVERTED_DEFORMATION = 4,  /* det F <= 0, element id in message */
+  GX_ERR_J2_RETURN_MAP = 5,         /* "J2: return mapping failed" src/goal_J2.cpp:119-120 */
+  GX_ERR_NCCL = 6,
+  GX_ERR_UNSUPPORTED = 7
+} gx_status;
+
+/* constitutive models named by north_star: src/goal_neohookean.cpp, src/goal_J2.cpp */
+enum { GX_MODEL_NEOHOOKEAN = 0, GX_MODEL_J2 = 1 };
+/* scatter modes, src/goal_eval_modes.hpp:6 */
+enum { GX_MODE_NONE = 0, GX_MODE_PRIMAL = 1, GX_MODE_ADJOINT = 2 };
+/* gx_desc.flags */
+enum { GX_FLAG_NO_STABILIZATION = 1 /* mechanics: stabilization: false, src/goal_mechanics.cpp:55-56 */ };
+
+#define GX_MAX_ELEM_SETS 16
+
+/* What Disc + Mechanics hold for one mesh part (src/goal_disc.cpp:224-235,
+ * src/goal_mechanics.cpp:41-63).  All arrays are copied; the caller may free them. */
+typedef struct {
+  int32_t n_nodes;          /* ghost (overlap) node count on this part */
+  int32_t n_elems;          /* elements of this part (no ghost element layers) */
+  const int32_t* conn;      /* [n_elems*4] ghost-local node ids, det(x1-x0,x2-x0,x3-x0) > 0 */
+  const double* coords;     /* [n_nodes*3] */
+  const int32_t* elem_set;  /* [n_elems] elem-set index per element, or NULL (one set) */
+  int32_t n_elem_sets;      /* <= GX_MAX_ELEM_SETS */
+  int32_t model;            /* GX_MODEL_* (mechanics: model) */
+  const double* materials;  /* [n_elem_sets*5] E, nu, K, Y, c0 per set (src/goal_J2.cpp:12-24) */
+  int32_t device;           /* CUDA device ordinal */
+  uint32_t flags;
+  /* ---- partition (all zero / NULL for a single part) ------------------------
+   * PUMI remotes as the .smb stores them: for each neighbouring part the list of
+   * local vertices shared with it, in an order agreed by both sides.            */
+  int32_t rank, n_ranks;
+  const int64_t* node_gid;      /* [n_nodes] global node id (apf::makeGlobal numbering) or NULL */
+  const int32_t* node_owner;    /* [n_nodes] owning rank of each node, or NULL (= all owned) */
+  int32_t n_peers;
+  const int32_t* peer_rank;     /* [n_peers] */
+  const int32_t* peer_offset;   /* [n_peers+1] offsets into peer_nodes */
+  const int32_t* peer_nodes;    /* concatenated shared-vertex lists (ghost-local ids) */
+} gx_desc;
+
+/* Disc::build_data + Primal::build_data (src/goal_disc.cpp:224-235, goal_primal.cpp:57-60):
+ * builds the ghost CRS graph, the element->nonzero scatter map and the conflict-free
+ * element schedule, allocates device mirrors of R / dRdu / states. */
+int gx_create(const gx_desc* desc, gx_ctx** out);
+int gx_destroy(gx_ctx* ctx);
+const char* gx_last_error(const gx_ctx* ctx); /* never NULL; ctx may be NULL for gx_create failures */
+
+/* Ghost CRS graph in Tpetra's local layout after fillComplete (Disc::compute_graphs,
+ * src/goal_disc.cpp:307-332): rows sorted & unique, local column index == ghost row LID.
+ * Pointers stay valid until gx_destroy. nnz may exceed 2^31 -> 64-bit row offsets. */
+int gx_graph(gx_ctx* ctx, int64_t* nnz, const int64_t** rowptr /*[4*n_nodes+1]*/, const int32_t** colind /*[nnz]*/);
+/* Same graph without materialising colind (nnz and rowptr only). */
+int gx_graph_size(gx_ctx* ctx, int64_t* nnz, int32_t* n_rows);
+
+/* Element -> nonzero scatter map (what sumIntoLocalValues searches for on every call,
+ * src/goal_displacement.cpp:191): for element e, local nodes (n,m), the position of the
+ * 4x4 node block inside node a_n's block row; value index of entry ((n,i),(m,k)) is
+ *   rowptr[4*a_n+i] + 4*bpos + k.  out: [n_elems*16] uint8, user element order. */
+int gx_scatter_map(gx_ctx* ctx, uint8_t* bpos);
+
+/* Solution fields "u","p" (Disc::add_soln writes them, src/goal_disc.cpp:398-422;
+ * Displacement/Pressure::gather read them, src/goal_displacement.cpp:139-156). */
+int gx_set_solution(gx_ctx* ctx, const double* u /*[n_nodes*3]*/, const double* p /*[n_nodes]*/);
+
+/* History state, AoS as apf stores it (src/goal_states.cpp:21-57): names "sigma",
+ * "eqps", "eqps_old", "Fp", "Fp_old"; tensors are 9 doubles row-major per element. */
+int gx_get_state(gx_ctx* ctx, const char* name, double* out);
+int gx_set_state(gx_ctx* ctx, const char* name, const double* in);
+int gx_update_states(gx_ctx* ctx); /* States::update: X_old <- X  (src/goal_states.cpp:130-141) */
+
+/* Primal::compute_resid minus BCs (src/goal_primal.cpp:81-83): zero_R + assemble(residual).
+ * R_out (ghost layout, [4*n_nodes]) may be NULL to leave the result on the device. */
+int gx_compute_residual(gx_ctx* ctx, int save_state, double* R_out);
+/* Primal::compute_jacob / NestedAdjoint::compute_adjoint minus BCs
+ * (src/goal_primal.cpp:98-101, goal_nested_adjoint.cpp:169-172): zero_all + assemble(jacobian).
+ * mode PRIMAL scatters dRdu, ADJOINT its transpose (src/goal_displacement.cpp:196-214).
+ * R_out / values_out ([nnz], ghost CRS order) may be NULL. */
+int gx_compute_jacobian(gx_ctx* ctx, int mode, int save_state, double* R_out, double* values_out);
+/* NestedAdjoint::localize minus BCs (src/goal_nested_adjoint.cpp:224-226): zero_R +
+ * assemble(error chain of Mechanics::build_error, src/goal_mechanics.cpp:169-218). */
+int gx_localize_error(gx_ctx* ctx, const double* zu_diff /*[n_nodes*3]*/, const double* zp_diff /*[n_nodes]*/,
+                      const double* zp_coarse /*[n_nodes]*/, double* R_out);
+/* compute_error + sum_contribs + Nested::set_error (src/goal_error.cpp:7-56,
+ * goal_nested.cpp:395-412).  parent may be NULL.  *bound is this part's sum; across
+ * parts use gx_allreduce_sum (== PCU_Add_Doubles, src/goal_error.cpp:54). */
+int gx_element_error(gx_ctx* ctx, const double* u_err /*[n_nodes*3]*/, const double* p_err /*[n_nodes]*/,
+                     const int32_t* parent /*[n_elems]*/, int32_t n_parent, double* eta_elem /*[n_elems]*/,
+                     double* eta_parent /*[n_parent]*/, double* bound);
+
+/* SolInfo::gather_R / gather_dRdu (Tpetra Export ghost->owned, ADD; src/goal_sol_info.cpp:33-43)
+ * over NCCL.  After it, rows of nodes this part owns hold the sum over all parts, rows of
+ * nodes owned elsewhere are left as local partial sums.  what: bit 0 = R, bit 1 = dRdu. */
+int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes);
+int gx_nccl_unique_id(void* out, size_t* id_bytes); /* helper: rank 0 creates, host code broadcasts */
+int gx_reduce_interfaces(gx_ctx* ctx, int what);
+int gx_allreduce_sum(gx_ctx* ctx, double* x, int n);
+/* Pack / unpack halves of the exchange for hosts that bring their own transport
+ * (MPI, torch.distributed): interface rows of peer `p` as a flat device buffer. */
+int gx_interface_bytes(gx_ctx* ctx, int peer_index, int what, int64_t* send_bytes, int64_t* recv_bytes);
+int gx_pack_interface(gx_ctx* ctx, int peer_index, int what, void** send_dev);
+int gx_unpack_add_interface(gx_ctx* ctx, int peer_index, int what, const void* recv_dev);
+
+/* Results of the last compute call, device resident (for a GPU-resident consumer). */
+int gx_result_dev(gx_ctx* ctx, double** R_dev, double** values_dev);
+int gx_fetch(gx_ctx* ctx, double* R_out, double* values_out); /* D2H copy of the above */
+
+/* Introspection */
+int gx_plastic_count(gx_ctx* ctx, int64_t* n);  /* elements on the plastic branch in the last call */
+int gx_num_colors(gx_ctx* ctx, int32_t* n);
+void* gx_stream(gx_ctx* ctx);                   /* the cudaStream_t every kernel of ctx runs on */
+/* Device time (ms, CUDA events on gx_stream) of the last compute call:
+ * t[0] zeroing, t[1] assembly kernels, t[2] interface exchange, t[3] kernel launches counted */
+int gx_last_timing(gx_ctx* ctx, double t[4]);
+int gx_set_option(gx_ctx* ctx, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,143 @@
+// hostcheck.cpp -- TEST-ONLY host build of goal_b200/csrc/element_math.cuh.
+// Lets the CPU test-suite (no GPU in the build container) verify the arithmetic
+// every CUDA thread runs against the oracle.  Not linked into, nor reachable
+// from, the product library.
+#include "../../goal_b200/csrc/element_math.cuh"
+
+extern "C" int hc_element(int model, const double* x, const double* u, const double* p, const double* mat5,
+                          const double* Fp_old, double eqps_old, int save, double* K /*16x16 row-major, dof=n*4+eq*/,
+                          double* R /*16*/, double* sigma /*9*/, double* eqps, double* Fp /*9*/, int* wrote_Fp,
+                          int* plastic) {
+  gx::Material m;
+  double E = mat5[0], nu = mat5[1];
+  m.kappa = E / (3.0 * (1.0 - 2.0 * nu)); m.mu = E / (2.0 * (1.0 + nu));
+  m.K = mat5[2]; m.Y = mat5[3]; m.c0 = mat5[4];
+  double X[4][3], U[4][3];
+  for (int n = 0; n < 4; ++n) for (int j = 0; j < 3; ++j) { X[n][j] = x[3 * n + j]; U[n][j] = u[3 * n + j]; }
+  gx::Core<double> c;
+  bool wf = false;
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Fp_old, eqps_old, save != 0, sigma, *eqps, Fp, wf, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Fp_old, eqps_old, save != 0, sigma, *eqps, Fp, wf, c);
+  if (rc) return rc;
+  *wrote_Fp = wf; *plastic = c.plastic;
+  double ru[12], rp[4];
+  gx::element_residual(c, m, ru, rp);
+  for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
+  for (int mm = 0; mm < 4; ++mm) {
+    gx::ColNode<double> cn;
+    gx::column_node(c, mm, cn);
+    for (int n = 0; n < 4; ++n) {
+      double sw[3], blk[16];
+      gx::sym_mv(c.s, c.w[n], sw);
+      gx::jacobian_block(c, m, n, cn, sw, blk);
+      for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) K[(4 * n + i) * 16 + 4 * mm + k] = blk[4 * i + k];
+    }
+  }
+  return 0;
+}
+
+extern "C" int hc_error_residual(int model, const double* x, const double* u, const double* p, const double* mat5,
+                                 const double* Fp_old, double eqps_old, const double* zu, const double* zp,
+                                 const double* zpc, double* R) {
+  gx::Material m;
+  double E = mat5[0], nu = mat5[1];
+  m.kappa = E / (3.0 * (1.0 - 2.0 * nu)); m.mu = E / (2.0 * (1.0 + nu));
+  m.K = mat5[2]; m.Y = mat5[3]; m.c0 = mat5[4];
+  double X[4][3], U[4][3], Z[4][3];
+  for (int n = 0; n < 4; ++n) for (int j = 0; j < 3; ++j) { X[n][j] = x[3 * n + j]; U[n][j] = u[3 * n + j]; Z[n][j] = zu[3 * n + j]; }
+  gx::Core<double> c;
+  bool wf; double sg[9], eq, fp[9];
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Fp_old, eqps_old, false, sg, eq, fp, wf, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Fp_old, eqps_old, false, sg, eq, fp, wf, c);
+  if (rc) return rc;
+  double ru[12], rp[4];
+  gx::element_error_residual(c, m, Z, zp, zpc, ru, rp);
+  for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
+  return 0;
+}
+
+extern "C" void hc_expm3(const double* A, double* o) { gx::expm3(A, o); }
+
+// ---------------------------------------------------------------------------
+// Whole-mesh emulation: the product's own setup code (gx_setup.cpp) and the
+// product's own element body (gx_kernels.cuh), run colour by colour on the host.
+// Checks indexing, the scatter map, the colour schedule and the SoA state layout
+// before any GPU time is spent.
+// ---------------------------------------------------------------------------
+#include "../../goal_b200/csrc/gx_kernels.cuh"
+
+template <int MODEL, int PASS, bool SAVE>
+static int64_t run_colours(gx_ctx& c, gx::KParams& P) {
+  int64_t plastic = 0;
+  for (int k = 0; k < c.ncolors; ++k)
+    for (int e = c.color_off[k]; e < c.color_off[k + 1]; ++e) plastic += gx::assemble_element<MODEL, PASS, SAVE>(P, e);
+  return plastic;
+}
+
+// states in/out are AoS user order: sigma[ne*9], eqps[ne], eqps_old[ne], Fp[ne*9], Fp_old[ne*9]
+extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const int32_t* conn, const double* coords,
+                           const double* mat5, const double* u, const double* p, const double* z5 /*[nn*5] or NULL*/,
+                           double* sigma, double* eqps, const double* eqps_old, double* Fp, const double* Fp_old,
+                           double* R, double* values, int64_t* nnz_out, int64_t* rowptr_out, int32_t* colind_out,
+                           int32_t* ncolors, int64_t* plastic) {
+  gx_ctx c;
+  c.nn = nn; c.ne = ne; c.model = model; c.nsets = 1;
+  c.conn.assign(conn, conn + 4 * (size_t)ne);
+  c.coords.assign(coords, coords + 3 * (size_t)nn);
+  double E = mat5[0], nu = mat5[1];
+  c.mats[0].kappa = E / (3.0 * (1.0 - 2.0 * nu)); c.mats[0].mu = E / (2.0 * (1.0 + nu));
+  c.mats[0].K = mat5[2]; c.mats[0].Y = mat5[3]; c.mats[0].c0 = mat5[4];
+  int rc = gx::build_graph_and_schedule(&c);
+  if (rc) return rc;
+  *nnz_out = c.nnz; *ncolors = c.ncolors;
+  if (rowptr_out) {
+    gx::materialise_crs(&c);
+    std::copy(c.rowptr.begin(), c.rowptr.end(), rowptr_out);
+    std::copy(c.colind.begin(), c.colind.end(), colind_out);
+  }
+  if (!R) return 0;
+  gx::HostPack hp;
+  gx::pack_host(&c, hp);
+  for (int n = 0; n < nn; ++n) {
+    for (int j = 0; j < 3; ++j) hp.nodes[n].u[j] = u[3 * (size_t)n + j];
+    hp.nodes[n].p = p[n];
+  }
+  std::vector<gx::ZRec> z(nn);
+  if (z5) for (int n = 0; n < nn; ++n) { for (int j = 0; j < 3; ++j) z[n].zu[j] = z5[5 * (size_t)n + j]; z[n].zp = z5[5 * (size_t)n + 3]; z[n].zpc = z5[5 * (size_t)n + 4]; }
+  int64_t const st = ((int64_t)ne + 31) / 32 * 32;
+  std::vector<double> s_sig(9 * st, 0.0), s_eq(st, 0.0), s_eqo(st, 0.0), s_fp(9 * st, 0.0), s_fpo(9 * st, 0.0);
+  for (int d = 0; d < ne; ++d) {
+    int const e = c.perm[d];
+    for (int k = 0; k < 9; ++k) { s_sig[k * st + d] = sigma[9 * (size_t)e + k]; }
+    if (model == 1) {
+      s_eq[d] = eqps[e]; s_eqo[d] = eqps_old[e];
+      for (int k = 0; k < 9; ++k) { s_fp[k * st + d] = Fp[9 * (size_t)e + k]; s_fpo[k * st + d] = Fp_old[9 * (size_t)e + k]; }
+    }
+  }
+  int err[2] = {0, 0};
+  unsigned long long pl = 0;
+  gx::KParams P;
+  P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
+  P.Fp_old = s_fpo.data(); P.eqps_old = s_eqo.data(); P.Fp = s_fp.data(); P.eqps = s_eq.data(); P.sigma = s_sig.data();
+  P.sstride = st; P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne;
+  for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
+  int64_t npl = 0;
+  using namespace gx;
+#define HC_RUN(M) \
+  switch (pass) { \
+    case PASS_RESIDUAL: npl = save ? run_colours<M, PASS_RESIDUAL, true>(c, P) : run_colours<M, PASS_RESIDUAL, false>(c, P); break; \
+    case PASS_JACOBIAN: npl = save ? run_colours<M, PASS_JACOBIAN, true>(c, P) : run_colours<M, PASS_JACOBIAN, false>(c, P); break; \
+    case PASS_JACOBIAN_T: npl = save ? run_colours<M, PASS_JACOBIAN_T, true>(c, P) : run_colours<M, PASS_JACOBIAN_T, false>(c, P); break; \
+    default: npl = run_colours<M, PASS_ERROR, false>(c, P); }
+  if (model == 1) { HC_RUN(MODEL_J2) } else { HC_RUN(MODEL_NEOHOOKEAN) }
+  *plastic = npl;
+  for (int d = 0; d < ne; ++d) {
+    int const e = c.perm[d];
+    for (int k = 0; k < 9; ++k) sigma[9 * (size_t)e + k] = s_sig[k * st + d];
+    if (model == 1) {
+      eqps[e] = s_eq[d];
+      for (int k = 0; k < 9; ++k) Fp[9 * (size_t)e + k] = s_fp[k * st + d];
+    }
+  }
+  return err[0] ? 100 + err[0] : 0;
+}

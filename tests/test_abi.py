@@ -1,0 +1,49 @@
+"""The C-ABI library loads and exports every symbol include/goal_b200.h declares; the product has no CPU path."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+def test_exports_match_header(gxlib):
+    hdr = open(os.path.join(ROOT, "include", "goal_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(gx_[a-z_0-9]+)\s*\(", hdr)))
+    assert len(declared) >= 25
+    missing = [s for s in declared if not hasattr(gxlib, s)]
+    assert not missing, missing
+    from goal_b200.binding import SYMBOLS
+    assert sorted(SYMBOLS) == declared
+
+
+def test_header_is_plain_c():
+    import subprocess
+    src = '#include "goal_b200.h"\nint main(void){gx_desc d; (void)d; return GX_OK;}\n'
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), "-x", "c", "-"],
+                   input=src.encode(), check=True)
+
+
+def test_no_cpu_fallback(gxlib):
+    """Without a GPU gx_create must fail loudly; bad descriptions are rejected either way."""
+    import torch
+    import goal_b200
+    from goal_b200.synthetic import MATERIAL, kuhn_cube
+    co, cn = kuhn_cube(2)
+    if not torch.cuda.is_available():
+        with pytest.raises(goal_b200.GxError) as e:
+            goal_b200.Assembler(co, cn, "J2", [MATERIAL])
+        assert "no usable CUDA device" in str(e.value)
+    with pytest.raises(goal_b200.GxError):
+        goal_b200.Assembler(co, cn, "J2", np.zeros((0, 5)))
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under goal_b200/ may import, link or execute the oracle."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "goal_b200")):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                txt = open(os.path.join(dirpath, fn)).read()
+                assert "goal_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn

@@ -1,0 +1,118 @@
+"""CPU checks of the CUDA path's own code (no GPU needed): the closed-form per-seed
+tangent of goal_b200/csrc/element_math.cuh and the launch/scatter logic of gx_kernels.cuh +
+gx_setup.cpp are compiled for the host by tests/hostcheck and compared with the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+from goal_b200.synthetic import MATERIAL, fields, kuhn_cube
+from oracle.oracle import ADJOINT, PRIMAL, Oracle
+
+dp = lambda a: None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
+ip = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
+lp = lambda a: a.ctypes.data_as(C.POINTER(C.c_int64))
+
+
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+def test_element_math_matches_fad_oracle(hostcheck, model):
+    rng = np.random.RandomState(1)
+    mat = np.array(MATERIAL)
+    seen = set()
+    for trial in range(120):
+        x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]]) * 0.1 + 0.01 * rng.randn(4, 3)
+        if np.linalg.det(x[1:] - x[0]) < 0:
+            x[[1, 2]] = x[[2, 1]]
+        u = (0.0001, 0.0005, 0.003)[trial % 3] * rng.randn(4, 3)
+        p = rng.randn(4)
+        Fpo = (np.eye(3) + 1e-3 * rng.randn(3, 3)).reshape(-1)
+        eqo = 0.01 * rng.rand()
+        o = Oracle(x, np.array([[0, 1, 2, 3]], dtype=np.int32), model, [MATERIAL])
+        o.set_solution(u, p)
+        if model == "J2":
+            o.state("Fp_old")[:] = Fpo
+            o.state("eqps_old")[:] = eqo
+            o.state("Fp")[:] = 7.0
+        R, vals = o.jacobian(PRIMAL, save=True)
+        Ko = o.csr(vals).toarray()
+        K, Rh, sig, Fp = np.zeros(256), np.zeros(16), np.zeros(9), np.full(9, 7.0)
+        eq, wf, pl = C.c_double(0), C.c_int(0), C.c_int(0)
+        rc = hostcheck.hc_element(0 if model == "neohookean" else 1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eqo),
+                                  1, dp(K), dp(Rh), dp(sig), C.byref(eq), dp(Fp), C.byref(wf), C.byref(pl))
+        assert rc == 0
+        seen.add(pl.value)
+        assert relerr(K.reshape(16, 16), Ko) < 1e-12
+        assert relerr(Rh, R) < 1e-12
+        assert relerr(sig, o.state("sigma")[0]) < 1e-10
+        if model == "J2":
+            assert pl.value == o.plastic_count()
+            assert abs(eq.value - o.state("eqps")[0]) < 1e-12
+            assert np.abs(Fp - o.state("Fp")[0]).max() < 1e-10  # elastic: both still 7.0
+        zu, zp, zpc = 1e-2 * rng.randn(4, 3), 1e-2 * rng.randn(4), 1e-2 * rng.randn(4)
+        Re, Rh2 = o.localize(zu, zp, zpc), np.zeros(16)
+        hostcheck.hc_error_residual(0 if model == "neohookean" else 1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eqo),
+                                    dp(zu), dp(zp), dp(zpc), dp(Rh2))
+        assert relerr(Rh2, Re) < 1e-12
+    assert seen == ({0, 1} if model == "J2" else {0})
+
+
+def test_expm_matches_scipy(hostcheck):
+    import scipy.linalg
+    rng = np.random.RandomState(2)
+    for sc in (1e-4, 1e-3, 1e-2, 0.1, 1.0, 10.0):
+        A = sc * rng.randn(3, 3)
+        o = np.zeros(9)
+        hostcheck.hc_expm3(dp(A.reshape(-1).copy()), dp(o))
+        E = scipy.linalg.expm(A)
+        assert np.abs(o.reshape(3, 3) - E).max() < 5e-14 * np.abs(E).max()
+
+
+def _emulate(hostcheck, model, pass_, save, co, cn, f, z5=None):
+    nn, ne = len(co), len(cn)
+    nnz, ncol, pl = C.c_int64(0), C.c_int32(0), C.c_int64(0)
+    mat = np.array(MATERIAL)
+    nul = None
+    rc = hostcheck.hc_assemble(model, 0, 0, nn, ne, ip(cn), dp(co), dp(mat), nul, nul, nul, nul, nul, nul, nul, nul, nul, nul,
+                               C.byref(nnz), nul, nul, C.byref(ncol), C.byref(pl))
+    assert rc == 0
+    rowptr, colind = np.zeros(4 * nn + 1, dtype=np.int64), np.zeros(nnz.value, dtype=np.int32)
+    sig, eq, eqo = np.zeros((ne, 9)), np.zeros(ne), f["eqps_old"].copy()
+    Fp, Fpo = np.full((ne, 9), 7.0), f["Fp_old"].copy()
+    R, vals = np.zeros(4 * nn), np.zeros(nnz.value)
+    u, p = np.ascontiguousarray(f["u"]), np.ascontiguousarray(f["p"])
+    rc = hostcheck.hc_assemble(model, pass_, save, nn, ne, ip(cn), dp(co), dp(mat), dp(u), dp(p), dp(z5), dp(sig), dp(eq),
+                               dp(eqo), dp(Fp), dp(Fpo), dp(R), dp(vals), C.byref(nnz), lp(rowptr), ip(colind),
+                               C.byref(ncol), C.byref(pl))
+    assert rc == 0
+    return dict(R=R, vals=vals, rowptr=rowptr, colind=colind, sigma=sig, eqps=eq, Fp=Fp, ncolors=ncol.value, plastic=pl.value)
+
+
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+@pytest.mark.parametrize("mesh", ["cube", "kuhn5"])
+def test_whole_mesh_emulation_matches_oracle(hostcheck, cube, model, mesh):
+    co, cn = (cube["coords"], cube["tets"]) if mesh == "cube" else kuhn_cube(5)
+    mi = 0 if model == "neohookean" else 1
+    f = fields(co, len(cn), strain=0.004)
+    o = Oracle(co, cn, model, [MATERIAL])
+    o.set_solution(f["u"], f["p"])
+    if model == "J2":
+        o.state("Fp_old")[:] = f["Fp_old"]
+        o.state("eqps_old")[:] = f["eqps_old"]
+        o.state("Fp")[:] = 7.0
+    Ro, Ao = o.jacobian(PRIMAL, save=True)
+    h = _emulate(hostcheck, mi, 1, 1, co, cn, f)
+    assert np.array_equal(h["rowptr"], o.rowptr) and np.array_equal(h["colind"], o.colind)  # graph bit-exact
+    assert h["plastic"] == o.plastic_count()
+    assert relerr(h["R"], Ro) < 1e-12 and relerr(h["vals"], Ao) < 1e-12
+    assert relerr(h["sigma"], o.state("sigma")) < 1e-10
+    if model == "J2":
+        assert np.abs(h["eqps"] - o.state("eqps")).max() < 1e-12
+        assert np.abs(h["Fp"] - o.state("Fp")).max() < 1e-10
+    _, At = o.jacobian(ADJOINT, save=False)
+    h2 = _emulate(hostcheck, mi, 2, 0, co, cn, f)
+    assert relerr(h2["vals"], At) < 1e-12 and np.all(h2["sigma"] == 0.0)
+    assert relerr(_emulate(hostcheck, mi, 0, 0, co, cn, f)["R"], o.residual(save=False)) < 1e-12
+    z5 = np.concatenate([f["zu_diff"], f["zp_diff"][:, None], f["zp_coarse"][:, None]], 1).copy()
+    Re = o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])
+    assert relerr(_emulate(hostcheck, mi, 3, 0, co, cn, f, z5=z5)["R"], Re) < 1e-12
