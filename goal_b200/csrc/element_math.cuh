@@ -328,6 +328,14 @@ template <class S> GX_HD void element_residual(Core<S> const& c, Material const&
   }
 }
 
+// One node's rows of the element residual: out = (R_u[n][0..2], R_p[n]) for the node whose spatial gradient is wn.
+template <class S> GX_HD void element_residual_row(Core<S> const& c, Material const& mat, S const wn[3], S out[4]) {
+  S tw[3];
+  sym_mv(c.tau, wn, tw);
+  out[0] = c.vol * tw[0]; out[1] = c.vol * tw[1]; out[2] = c.vol * tw[2];
+  out[3] = c.vol * ((c.pv / mat.kappa - S(0.5) * (c.J - S(1.0) / c.J)) * S(0.25) + c.taus * c.J * dot3(c.q, wn));
+}
+
 // Per-column-node quantities of the Jacobian: everything that depends on m only.
 template <class S>
 struct ColNode {
@@ -336,8 +344,10 @@ struct ColNode {
   S qw;                 // q . w_m
 };
 
-template <class S> GX_HD void column_node(Core<S> const& c, int m, ColNode<S>& cn) {
-  for (int k = 0; k < 3; ++k) { cn.w[k] = c.w[m][k]; cn.r[k] = c.r[m][k]; }
+// wm = w_m, rm = r_m (passed explicitly so that callers with a run-time node index can select them
+// without indexing the register-resident Core dynamically)
+template <class S> GX_HD void column_node(Core<S> const& c, S const wm[3], S const rm[3], ColNode<S>& cn) {
+  for (int k = 0; k < 3; ++k) { cn.w[k] = wm[k]; cn.r[k] = rm[k]; }
   sym_mv(c.tau, cn.w, cn.tw);
   cn.qw = dot3(c.q, cn.w);
   S const t23 = S(2.0 / 3.0);
@@ -357,12 +367,11 @@ template <class S> GX_HD void column_node(Core<S> const& c, int m, ColNode<S>& c
   }
 }
 
-// 4x4 block K[(n,i),(m,k)], i,k = 0..3 (eq 3 = pressure), row-major in `blk`; m is the node `cn` was built for.
-// sw_n = s w_n is passed in because it is shared by the four column nodes.
+// 4x4 block K[(n,i),(m,k)], i,k = 0..3 (eq 3 = pressure), row-major in `blk`; m is the node `cn` was built
+// for, wn = w_n the row node's spatial gradient, sw = s w_n (shared by the four column nodes).
 template <class S>
-GX_HD void jacobian_block(Core<S> const& c, Material const& mat, int n, ColNode<S> const& cn, S const sw[3],
+GX_HD void jacobian_block(Core<S> const& c, Material const& mat, S const wn[3], ColNode<S> const& cn, S const sw[3],
                           S blk[16]) {
-  S const* wn = c.w[n];
   S const rw = dot3(cn.r, wn);
   S const W = dot3(cn.w, wn);
   S const qwn = dot3(c.q, wn);

@@ -40,22 +40,32 @@ __global__ void pack_z_kernel(ZRec* z, double const* zu, double const* zp, doubl
   z[n].zpc = zpc[n];
 }
 
-// AoS (user element order, ncomp per element) <-> SoA (device element order)
-__global__ void aos_to_soa_kernel(double* soa, int64_t stride, double const* aos, int32_t const* perm, int ne, int ncomp) {
+// user field array [ne][ncomp] <-> a slice of the per-element state records
+__global__ void field_to_record_kernel(double* rec, int stride, int off, double const* field, int ne, int ncomp) {
   int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)ne * ncomp) return;
-  int const d = (int)(i / ncomp), k = (int)(i % ncomp);
-  soa[k * stride + d] = aos[(int64_t)perm[d] * ncomp + k];
+  int64_t const e = i / ncomp;
+  int const k = (int)(i % ncomp);
+  rec[e * stride + off + k] = field[i];
 }
-__global__ void soa_to_aos_kernel(double* aos, double const* soa, int64_t stride, int32_t const* perm, int ne, int ncomp) {
+__global__ void record_to_field_kernel(double* field, double const* rec, int stride, int off, int ne, int ncomp) {
   int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (i >= (int64_t)ne * ncomp) return;
-  int const d = (int)(i / ncomp), k = (int)(i % ncomp);
-  aos[(int64_t)perm[d] * ncomp + k] = soa[k * stride + d];
+  int64_t const e = i / ncomp;
+  int const k = (int)(i % ncomp);
+  field[i] = rec[e * stride + off + k];
+}
+// States::update (src/goal_states.cpp:130-141): Fp_old <- Fp, eqps_old <- eqps
+__global__ void update_states_kernel(double* sin, double const* sout, int ne) {
+  int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= (int64_t)ne * STATE_IN) return;
+  int64_t const e = i / STATE_IN;
+  int const k = (int)(i % STATE_IN);
+  sin[i] = sout[e * STATE_OUT + 9 + k];  // Fp[0..8], eqps
 }
 
 // compute_error (src/goal_error.cpp:7-35): |sum_d u_err_d(xi_c) + p_err(xi_c)|; err4 = [Nn][4] (u0,u1,u2,p)
-__global__ void element_error_kernel(double* eta, double4 const* err4, int4 const* conn, int32_t const* perm, int ne) {
+__global__ void element_error_kernel(double* eta, double4 const* err4, int4 const* conn, int ne) {
   int const d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= ne) return;
   int4 const cn = __ldg(conn + d);
@@ -70,7 +80,7 @@ __global__ void element_error_kernel(double* eta, double4 const* err4, int4 cons
   double total = 0.0;
   total += ue[0]; total += ue[1]; total += ue[2];
   total += pe;
-  eta[perm[d]] = fabs(total);
+  eta[d] = fabs(total);
 }
 
 // Nested::set_error (src/goal_nested.cpp:395-412): parent error = sum of its children, in element order
@@ -140,10 +150,35 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
-  P.Fp_old = ctx->d_Fp_old; P.eqps_old = ctx->d_eqps_old; P.Fp = ctx->d_Fp; P.eqps = ctx->d_eqps; P.sigma = ctx->d_sigma;
-  P.sstride = ctx->sstride; P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
-  P.e0 = 0; P.e1 = 0;
+  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
+  P.state_in = ctx->d_state_in; P.state_out = ctx->d_state_out;
+  P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
+  P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
+}
+
+static size_t row_owner_smem(gx_ctx const* ctx, int warps) {
+  size_t const per_warp = 16 * 32 * sizeof(double) + (size_t)16 * ctx->max_nblk * sizeof(double) +
+                          (size_t)((ctx->max_nblk + 3) & ~3) * sizeof(uint32_t);
+  return per_warp * warps;
+}
+
+template <int MODEL, bool TRANSPOSE, bool SAVE>
+static cudaError_t launch_row_owner(gx_ctx* ctx, KParams& P) {
+  int const warps = (int)ctx->opt_row_warps;
+  size_t const smem = row_owner_smem(ctx, warps);
+  auto kern = row_owner_kernel<MODEL, TRANSPOSE, SAVE>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+template <int MODEL>
+static cudaError_t launch_row_owner_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
+  if (pass == PASS_JACOBIAN) return save ? launch_row_owner<MODEL, false, true>(ctx, P) : launch_row_owner<MODEL, false, false>(ctx, P);
+  return save ? launch_row_owner<MODEL, true, true>(ctx, P) : launch_row_owner<MODEL, true, false>(ctx, P);
 }
 
 static int status_of_element_error(int code) {
@@ -163,14 +198,24 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaMemcpyAsync(ctx->d_err, zero2, sizeof zero2, cudaMemcpyHostToDevice, ctx->stream));
   GX_CUDA(cudaMemsetAsync(ctx->d_plastic, 0, sizeof(unsigned long long), ctx->stream));
   GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64)
-  GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
-  if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
+  bool const row_owner = with_values && ctx->opt_kernel == 0 &&
+                         row_owner_smem(ctx, (int)ctx->opt_row_warps) <= 200 * 1024;
+  if (!row_owner) {
+    // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The row-owner schedule writes every
+    // entry of R and of the CRS values exactly once, so it needs no zeroing pass.
+    GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
+    if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
+  }
   GX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   KParams P;
   fill_params(ctx, P);
-  cudaError_t le = ctx->model == GX_MODEL_J2 ? launch_model<MODEL_J2>(ctx, P, pass, save)
-                                             : launch_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
+  cudaError_t le;
+  if (row_owner)
+    le = ctx->model == GX_MODEL_J2 ? launch_row_owner_model<MODEL_J2>(ctx, P, pass, save)
+                                   : launch_row_owner_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
+  else
+    le = ctx->model == GX_MODEL_J2 ? launch_model<MODEL_J2>(ctx, P, pass, save)
+                                   : launch_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   if (le != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(le); return GX_ERR_CUDA; }
   GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   int herr[2];
@@ -188,7 +233,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   if (herr[0]) {
     static const char* const what[] = {"", "inverted element (dv <= 0)", "inverted deformation (det F <= 0)", "J2: return mapping failed"};
     char buf[160];
-    snprintf(buf, sizeof buf, "%s in element %d", what[herr[0] & 3], ctx->perm[herr[1]]);
+    snprintf(buf, sizeof buf, "%s in element %d", what[herr[0] & 3], herr[1]);
     ctx->err = buf;
     return status_of_element_error(herr[0]);
   }
@@ -202,23 +247,23 @@ static int fetch(gx_ctx* ctx, double* R_out, double* values_out) {
   return GX_OK;
 }
 
-static double** state_slot(gx_ctx* ctx, const char* name, int* ncomp) {
+// where a named apf state field lives inside the per-element records
+struct StateLoc { double* rec; int stride, off, ncomp; };
+static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
   std::string n(name ? name : "");
-  *ncomp = 9;
-  if (n == "sigma") return &ctx->d_sigma;
-  if (ctx->model != GX_MODEL_J2) return nullptr;
-  if (n == "Fp") return &ctx->d_Fp;
-  if (n == "Fp_old") return &ctx->d_Fp_old;
-  *ncomp = 1;
-  if (n == "eqps") return &ctx->d_eqps;
-  if (n == "eqps_old") return &ctx->d_eqps_old;
-  return nullptr;
+  if (n == "sigma") { L = {ctx->d_state_out, STATE_OUT, 0, 9}; return true; }
+  if (ctx->model != GX_MODEL_J2) return false;  // only J2 registers eqps / Fp (goal_mechanics.cpp:90-93)
+  if (n == "Fp") { L = {ctx->d_state_out, STATE_OUT, 9, 9}; return true; }
+  if (n == "eqps") { L = {ctx->d_state_out, STATE_OUT, 18, 1}; return true; }
+  if (n == "Fp_old") { L = {ctx->d_state_in, STATE_IN, 0, 9}; return true; }
+  if (n == "eqps_old") { L = {ctx->d_state_in, STATE_IN, 9, 1}; return true; }
+  return false;
 }
 
 static void free_device(gx_ctx* ctx) {
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_sigma, ctx->d_eqps,
-                  ctx->d_eqps_old, ctx->d_Fp, ctx->d_Fp_old, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
+  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj,
+                  ctx->d_state_in, ctx->d_state_out, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -275,7 +320,6 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     for (auto& e : ctx->ev) GX_CUDA(cudaEventCreate(&e));
     int const nn = ctx->nn, ne = ctx->ne;
-    ctx->sstride = ((int64_t)ne + 31) / 32 * 32;
     // ---- nodes and elements (device element order = colour-sorted)
     HostPack hp;
     pack_host(ctx, hp);
@@ -293,19 +337,20 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     }
     GX_CUDA(cudaMalloc(&ctx->d_perm, sizeof(int32_t) * (size_t)ne));
     GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_adj_off, sizeof(uint32_t) * (size_t)(nn + 1)));
+    GX_CUDA(cudaMemcpy(ctx->d_adj_off, ctx->adj_off.data(), sizeof(uint32_t) * (size_t)(nn + 1), cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_adj, sizeof(int2) * ctx->adj.size()));
+    GX_CUDA(cudaMemcpy(ctx->d_adj, ctx->adj.data(), sizeof(int2) * ctx->adj.size(), cudaMemcpyHostToDevice));
     // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
-    size_t const s9 = sizeof(double) * 9 * (size_t)ctx->sstride, s1 = sizeof(double) * (size_t)ctx->sstride;
-    GX_CUDA(cudaMalloc(&ctx->d_sigma, s9));
-    GX_CUDA(cudaMemset(ctx->d_sigma, 0, s9));
-    if (ctx->model == GX_MODEL_J2) {
-      GX_CUDA(cudaMalloc(&ctx->d_eqps, s1)); GX_CUDA(cudaMemset(ctx->d_eqps, 0, s1));
-      GX_CUDA(cudaMalloc(&ctx->d_eqps_old, s1)); GX_CUDA(cudaMemset(ctx->d_eqps_old, 0, s1));
-      GX_CUDA(cudaMalloc(&ctx->d_Fp, s9));
-      GX_CUDA(cudaMalloc(&ctx->d_Fp_old, s9));
-      std::vector<double> I9(9 * (size_t)ctx->sstride, 0.0);
-      for (int k = 0; k < 9; k += 4) std::fill(I9.begin() + k * ctx->sstride, I9.begin() + (k + 1) * ctx->sstride, 1.0);
-      GX_CUDA(cudaMemcpy(ctx->d_Fp, I9.data(), s9, cudaMemcpyHostToDevice));
-      GX_CUDA(cudaMemcpy(ctx->d_Fp_old, I9.data(), s9, cudaMemcpyHostToDevice));
+    {
+      std::vector<double> sin((size_t)STATE_IN * ne, 0.0), sout((size_t)STATE_OUT * ne, 0.0);
+      if (ctx->model == GX_MODEL_J2)
+        for (int e = 0; e < ne; ++e)
+          for (int k = 0; k < 9; k += 4) { sin[(size_t)STATE_IN * e + k] = 1.0; sout[(size_t)STATE_OUT * e + 9 + k] = 1.0; }
+      GX_CUDA(cudaMalloc(&ctx->d_state_in, sizeof(double) * sin.size()));
+      GX_CUDA(cudaMalloc(&ctx->d_state_out, sizeof(double) * sout.size()));
+      GX_CUDA(cudaMemcpy(ctx->d_state_in, sin.data(), sizeof(double) * sin.size(), cudaMemcpyHostToDevice));
+      GX_CUDA(cudaMemcpy(ctx->d_state_out, sout.data(), sizeof(double) * sout.size(), cudaMemcpyHostToDevice));
     }
     // ---- linear objects (SolInfo ghost R / dRdu, src/goal_sol_info.cpp:6-22)
     GX_CUDA(cudaMalloc(&ctx->d_R, sizeof(double) * 4 * (size_t)nn));
@@ -371,12 +416,11 @@ int gx_set_solution(gx_ctx* ctx, const double* u, const double* p) {
 
 int gx_get_state(gx_ctx* ctx, const char* name, double* out) {
   if (!ctx || !out) return GX_ERR_ARG;
-  int nc;
-  double** slot = state_slot(ctx, name, &nc);
-  if (!slot || !*slot) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
+  StateLoc L;
+  if (!state_loc(ctx, name, L)) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
-  int64_t const tot = (int64_t)ctx->ne * nc;
-  soa_to_aos_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stage, *slot, ctx->sstride, ctx->d_perm, ctx->ne, nc);
+  int64_t const tot = (int64_t)ctx->ne * L.ncomp;
+  record_to_field_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_stage, L.rec, L.stride, L.off, ctx->ne, L.ncomp);
   GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaMemcpyAsync(out, ctx->d_stage, sizeof(double) * (size_t)tot, cudaMemcpyDeviceToHost, ctx->stream));
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -385,13 +429,12 @@ int gx_get_state(gx_ctx* ctx, const char* name, double* out) {
 
 int gx_set_state(gx_ctx* ctx, const char* name, const double* in) {
   if (!ctx || !in) return GX_ERR_ARG;
-  int nc;
-  double** slot = state_slot(ctx, name, &nc);
-  if (!slot || !*slot) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
+  StateLoc L;
+  if (!state_loc(ctx, name, L)) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
-  int64_t const tot = (int64_t)ctx->ne * nc;
+  int64_t const tot = (int64_t)ctx->ne * L.ncomp;
   GX_CUDA(cudaMemcpyAsync(ctx->d_stage, in, sizeof(double) * (size_t)tot, cudaMemcpyHostToDevice, ctx->stream));
-  aos_to_soa_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(*slot, ctx->sstride, ctx->d_stage, ctx->d_perm, ctx->ne, nc);
+  field_to_record_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L.rec, L.stride, L.off, ctx->d_stage, ctx->ne, L.ncomp);
   GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
@@ -401,8 +444,9 @@ int gx_update_states(gx_ctx* ctx) {
   if (!ctx) return GX_ERR_ARG;
   if (ctx->model != GX_MODEL_J2) return GX_OK;  // only J2 registers old states (goal_mechanics.cpp:90-93)
   GX_CUDA(cudaSetDevice(ctx->device));
-  GX_CUDA(cudaMemcpyAsync(ctx->d_eqps_old, ctx->d_eqps, sizeof(double) * (size_t)ctx->sstride, cudaMemcpyDeviceToDevice, ctx->stream));
-  GX_CUDA(cudaMemcpyAsync(ctx->d_Fp_old, ctx->d_Fp, sizeof(double) * 9 * (size_t)ctx->sstride, cudaMemcpyDeviceToDevice, ctx->stream));
+  int64_t const tot = (int64_t)ctx->ne * STATE_IN;
+  update_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_state_out, ctx->ne);
+  GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
@@ -455,7 +499,7 @@ int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, cons
   double* d_eta = nullptr;
   double* d_etap = nullptr;
   GX_CUDA(cudaMallocAsync(&d_eta, sizeof(double) * (size_t)ne, ctx->stream));
-  element_error_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(d_eta, err4, ctx->d_conn, ctx->d_perm, ne);
+  element_error_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(d_eta, err4, ctx->d_conn, ne);
   GX_CUDA(cudaGetLastError());
   if (parent && eta_parent && n_parent > 0) {
     if (ctx->n_parent_cached != n_parent || ctx->parent_cached.size() != (size_t)ne ||
@@ -532,6 +576,16 @@ int gx_last_timing(gx_ctx* ctx, double t[4]) {
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return GX_ERR_ARG;
   std::string k(key);
+  if (k == "kernel") {  // 0 = row-owner Jacobian kernel (default), 1 = coloured element kernel
+    if (value != 0 && value != 1) { ctx->err = "kernel must be 0 or 1"; return GX_ERR_ARG; }
+    ctx->opt_kernel = value;
+    return GX_OK;
+  }
+  if (k == "row_warps") {
+    if (value < 1 || value > 8) { ctx->err = "row_warps must be 1..8"; return GX_ERR_ARG; }
+    ctx->opt_row_warps = value;
+    return GX_OK;
+  }
   if (k == "block_size") {
     if (value < 32 || value > 128 || (value & 31)) { ctx->err = "block_size must be 32, 64, 96 or 128"; return GX_ERR_ARG; }
     ctx->opt_block = value;

@@ -75,6 +75,10 @@ struct gx_ctx {
   std::vector<int64_t> rowptr;  // lazily materialised dof-level CRS
   std::vector<int32_t> colind;
   std::vector<uint8_t> bpos;    // [ne*16] user order
+  // node -> (element, local node) incidences, elements ascending: the row-owner kernel's work list
+  std::vector<uint32_t> adj_off;  // [nn+1]
+  std::vector<int2> adj;          // [4*ne]  x = e*4+n, y = block positions of (a, a_m), m = 0..3, one byte each
+  int max_nblk = 0, max_deg = 0;
   // ---- schedule
   int ncolors = 0;
   std::vector<int32_t> color_off;  // [ncolors+1] in device element order
@@ -84,12 +88,17 @@ struct gx_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   gx::NodeRec* d_nodes = nullptr;
   gx::ZRec* d_z = nullptr;
-  int4* d_conn = nullptr;
-  uint4* d_bpos = nullptr;
-  uint8_t* d_eset = nullptr;
-  int32_t* d_perm = nullptr;
-  int64_t sstride = 0;  // SoA stride of state arrays (elements, padded)
-  double *d_sigma = nullptr, *d_eqps = nullptr, *d_eqps_old = nullptr, *d_Fp = nullptr, *d_Fp_old = nullptr;
+  int4* d_conn = nullptr;       // user element order
+  uint4* d_bpos = nullptr;      // user element order
+  uint8_t* d_eset = nullptr;    // user element order
+  int32_t* d_perm = nullptr;    // colour schedule: slot -> user element
+  uint32_t* d_adj_off = nullptr;
+  int2* d_adj = nullptr;
+  // history state, one record per element (user order):
+  //   in : Fp_old[9], eqps_old                      (80 B)
+  //   out: sigma[9], Fp[9], eqps, pad               (160 B)
+  double* d_state_in = nullptr;
+  double* d_state_out = nullptr;
   double* d_R = nullptr;
   double* d_values = nullptr;
   double* d_stage = nullptr;  // staging for host<->device field copies, >= max(4*nn, 10*ne) doubles
@@ -112,6 +121,8 @@ struct gx_ctx {
   bool have_result = false;
   bool have_values = false;
   int64_t opt_block = 128;
+  int64_t opt_kernel = 0;  // 0 = row-owner Jacobian kernel, 1 = coloured element kernel
+  int64_t opt_row_warps = 8;
   std::string err;
 };
 
@@ -122,9 +133,11 @@ void materialise_crs(gx_ctx* c);
 // host images of the device arrays, in device (colour-sorted) element order
 struct HostPack {
   std::vector<NodeRec> nodes;
-  std::vector<int4> conn4;
-  std::vector<uint4> bpos;
+  std::vector<int4> conn4;   // user element order
+  std::vector<uint4> bpos;   // user element order
   std::vector<uint8_t> eset;
 };
+constexpr int STATE_IN = 10;   // doubles per element
+constexpr int STATE_OUT = 20;
 void pack_host(gx_ctx const* c, HostPack& h);
 }  // namespace gx

@@ -1,22 +1,31 @@
-// gx_kernels.cuh -- the assembly kernels: one element per thread.
+// gx_kernels.cuh -- the assembly kernels.
 //
 // Replaces the element loop of goal::assemble (src/goal_assembly.cpp:65-88) together
 // with the gather/scatter halves of Displacement/Pressure (src/goal_displacement.cpp,
 // src/goal_pressure.cpp) and States get/set (src/goal_states.cpp:21-57).
 //
 // Data layout in HBM
-//   nodes   NodeRec[Nn]  64 B per node: x, u, p and the node's block-row descriptor;
-//                        one element gathers 4 records = 4 full 64 B segments (4 LDG.128 each)
-//   conn    int4[Ne]     one coalesced 128-bit load per thread
-//   bpos    uint4[Ne]    16 x uint8 block positions, one coalesced 128-bit load per thread
-//   state   SoA, component-major with stride `sstride`: Fp_old[9][Ne], eqps_old[Ne], ...
-//                        -> every state load/store of a warp is one 256 B contiguous run
-//   R       double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
-// Elements are stored colour-sorted (gx_setup.cpp); a launch covers one colour, so all
-// read-modify-writes below are conflict free without atomics.
+//   nodes     NodeRec[Nn]  64 B per node: x, u, p and the node's block-row descriptor; an element
+//                          gathers 4 records = 4 aligned 64 B segments (4 LDG.128 each)
+//   conn      int4[Ne]     one 128-bit load per element
+//   bpos      uint4[Ne]    element -> nonzero scatter map, 16 x uint8 block positions
+//   adj       int2[4 Ne]   node -> (element, local node) incidences + the 4 block positions that
+//                          incidence writes, grouped by node (adj_off[Nn+1]); the row-owner work list
+//   state_in  double[Ne][10]  Fp_old[9], eqps_old          80 B record  (5 LDG.128)
+//   state_out double[Ne][20]  sigma[9], Fp[9], eqps, pad   160 B record (10 STG.128)
+//   R         double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
 //
-// The element bodies are __host__ __device__ so that tests/hostcheck can run exactly
-// this code, launch order included, on the CPU (test-only; there is no CPU product path).
+// Two schedules, both free of atomics on the data path and bit-reproducible:
+//  (1) row-owner (Jacobian pass, default): one warp per node a, one lane per incident element
+//      (a, e).  Each lane evaluates its element and the four 4x4 blocks of node a's rows, the warp
+//      sums them per target block through shared memory in a fixed order and writes node a's four
+//      CRS rows exactly once, fully coalesced.  No zeroing pass, no read-modify-write traffic.
+//  (2) coloured elements (residual / error-localisation passes, Jacobian fallback): one thread per
+//      element, launches cover one colour (no two elements of a colour share a node), plain
+//      read-modify-write into R / values.
+//
+// The element bodies are __host__ __device__ so that tests/hostcheck can run schedule (2) exactly as
+// written, launch order included, on the CPU (test-only; there is no CPU product path).
 #pragma once
 
 #include <stdint.h>
@@ -32,17 +41,18 @@ struct KParams {
   int4 const* conn;
   uint4 const* bpos;
   uint8_t const* eset;  // may be null (single elem set)
-  double const* Fp_old;
-  double const* eqps_old;
-  double* Fp;
-  double* eqps;
-  double* sigma;
-  int64_t sstride;
+  int32_t const* elems; // colour schedule: slot -> element
+  uint32_t const* adj_off;
+  int2 const* adj;
+  double const* state_in;
+  double* state_out;
   double* R;
   double* values;
-  int* err;                     // {code, device element}
+  int* err;                     // {code, element}
   unsigned long long* plastic;  // counter
-  int e0, e1;                   // device element range of this launch
+  int e0, e1;                   // slot range of this launch (coloured schedule)
+  int nn;
+  int max_nblk;
   Material mat[GX_MAX_ELEM_SETS];
 };
 
@@ -88,39 +98,54 @@ GX_HD void add4(double* dst, double a, double b, double c, double d) {
   q[0] = v0; q[1] = v1;
 }
 
-// One element of one colour.  Returns 1 when the element took the plastic branch.
-template <int MODEL, int PASS, bool SAVE>
-GX_HD int assemble_element(KParams const& P, int e) {
+// gather + stress update of one element; writes the history state when SAVE && write_state
+template <int MODEL, bool SAVE>
+GX_HD int load_and_update(KParams const& P, int e, bool write_state, int nd[4], int blk0[4], int nblk[4],
+                          Material const*& mat, Core<double>& c) {
   int4 const cn = ldg(P.conn + e);
-  int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+  nd[0] = cn.x; nd[1] = cn.y; nd[2] = cn.z; nd[3] = cn.w;
   double x[4][3], u[4][3], p[4];
-  int blk0[4], nblk[4];
 #pragma unroll
   for (int n = 0; n < 4; ++n) load_node(P.nodes, nd[n], x[n], u[n], p[n], blk0[n], nblk[n]);
-  Material const& mat = P.mat[P.eset ? P.eset[e] : 0];
-
+  mat = &P.mat[P.eset ? P.eset[e] : 0];
   double Fp_old[9], eqps_old = 0.0;
   if (MODEL == MODEL_J2) {
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Fp_old[k] = ldg(P.Fp_old + k * P.sstride + e);
-    eqps_old = ldg(P.eqps_old + e);
+    double2 const* q = reinterpret_cast<double2 const*>(P.state_in + (int64_t)STATE_IN * e);
+    double2 const a0 = ldg(q), a1 = ldg(q + 1), a2 = ldg(q + 2), a3 = ldg(q + 3), a4 = ldg(q + 4);
+    Fp_old[0] = a0.x; Fp_old[1] = a0.y; Fp_old[2] = a1.x; Fp_old[3] = a1.y; Fp_old[4] = a2.x;
+    Fp_old[5] = a2.y; Fp_old[6] = a3.x; Fp_old[7] = a3.y; Fp_old[8] = a4.x; eqps_old = a4.y;
   }
-  Core<double> c;
   double sig[9], eqps_new = 0.0, Fp_new[9];
   bool write_Fp = false;
-  int const rc = element_core<MODEL>(x, u, p, mat, Fp_old, eqps_old, SAVE, sig, eqps_new, Fp_new, write_Fp, c);
-  if (rc != ERR_NONE) { report_error(P.err, rc, e); return 0; }
-  if (SAVE) {
+  int const rc = element_core<MODEL>(x, u, p, *mat, Fp_old, eqps_old, SAVE && write_state, sig, eqps_new, Fp_new, write_Fp, c);
+  if (rc != ERR_NONE) return rc;
+  if (SAVE && write_state) {
+    double* so = P.state_out + (int64_t)STATE_OUT * e;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) P.sigma[k * P.sstride + e] = sig[k];
+    for (int k = 0; k < 9; ++k) so[k] = sig[k];
     if (MODEL == MODEL_J2) {
-      P.eqps[e] = eqps_new;
-      if (write_Fp) {
+      so[18] = eqps_new;
+      if (write_Fp) {  // elastic branch: Fp deliberately untouched (goal_J2.cpp:135-136)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) P.Fp[k * P.sstride + e] = Fp_new[k];
+        for (int k = 0; k < 9; ++k) so[9 + k] = Fp_new[k];
       }
     }
   }
+  return ERR_NONE;
+}
+
+// ---------------------------------------------------------------------------
+// Schedule (2): one element of one colour.  Returns 1 when the element took the plastic branch.
+// ---------------------------------------------------------------------------
+template <int MODEL, int PASS, bool SAVE>
+GX_HD int assemble_element(KParams const& P, int slot) {
+  int const e = ldg(P.elems + slot);
+  int nd[4], blk0[4], nblk[4];
+  Material const* matp;
+  Core<double> c;
+  int const rc = load_and_update<MODEL, SAVE>(P, e, true, nd, blk0, nblk, matp, c);
+  if (rc != ERR_NONE) { report_error(P.err, rc, e); return 0; }
+  Material const& mat = *matp;
 
   // ---- residual (Displacement/Pressure::scatter_primal, R[row] += resid)
   double ru[12], rp[4];
@@ -149,11 +174,11 @@ GX_HD int assemble_element(KParams const& P, int e) {
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       ColNode<double> cnm;
-      column_node(c, m, cnm);
+      column_node(c, c.w[m], c.r[m], cnm);
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         double blk[16];
-        jacobian_block(c, mat, n, cnm, sw[n], blk);
+        jacobian_block(c, mat, c.w[n], cnm, sw[n], blk);
         if (PASS == PASS_JACOBIAN) {
           // A(row (n,i), col (m,k)) += blk[i][k]      (scatter_primal, goal_displacement.cpp:177-194)
           int64_t const rowlen = 4 * (int64_t)nblk[n];
@@ -176,12 +201,151 @@ GX_HD int assemble_element(KParams const& P, int e) {
 #if defined(__CUDACC__)
 template <int MODEL, int PASS, bool SAVE>
 __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ KParams P) {
-  int const e = P.e0 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  int const slot = P.e0 + (int)(blockIdx.x * blockDim.x + threadIdx.x);
   int plastic = 0;
-  if (e < P.e1) plastic = assemble_element<MODEL, PASS, SAVE>(P, e);
+  if (slot < P.e1) plastic = assemble_element<MODEL, PASS, SAVE>(P, slot);
   if (MODEL == MODEL_J2) {
     unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
     if ((threadIdx.x & 31) == 0 && b) atomicAdd(P.plastic, (unsigned long long)__popc(b));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Schedule (1): row-owner Jacobian kernel.  Warp = node a; lane = incidence (a, e) with a = local
+// node n of e.  Lane work: element core, then for each column node m the 4x4 block
+//   PRIMAL : K[(n,.),(m,.)]           -> block (a, a_m) of node a's rows
+//   ADJOINT: K[(m,.),(n,.)]^T         -> block (a, a_m) of the transposed operator
+// staged in shared memory as stg[16][32]; lanes whose target block position coincides are found with
+// __match_any_sync and summed by the entry's owner lane in ascending lane order (= ascending element id),
+// so every CRS entry is produced by exactly one thread in a fixed order: deterministic, write-once.
+// Nodes with more than 32 incident elements take several rounds; the row accumulates in shared memory.
+// Shared memory per warp: stg 4 KB + row 128*max_nblk B + mask 4*max_nblk B.
+// ---------------------------------------------------------------------------
+template <int MODEL, bool TRANSPOSE, bool SAVE>
+__global__ void __launch_bounds__(256) row_owner_kernel(const __grid_constant__ KParams P) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int const warps = blockDim.x >> 5;
+  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const mb = P.max_nblk;
+  size_t const per_warp = 16 * 32 * sizeof(double) + (size_t)16 * mb * sizeof(double) + (size_t)((mb + 3) & ~3) * sizeof(uint32_t);
+  unsigned char* base = smem_raw + per_warp * wib;
+  double* stg = reinterpret_cast<double*>(base);
+  double* row = stg + 16 * 32;
+  uint32_t* maskOf = reinterpret_cast<uint32_t*>(row + 16 * mb);
+  (void)warps;
+
+  int const a = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (a >= P.nn) return;  // whole warp exits together
+  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
+  int blk0a, nblka;
+  {
+    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
+    blk0a = __double2loint(d3.y);
+    nblka = __double2hiint(d3.y);
+  }
+  int const nent = 16 * nblka;
+  for (int g = lane; g < nent; g += 32) row[g] = 0.0;
+  double racc[4] = {0.0, 0.0, 0.0, 0.0};
+  int nplastic = 0;
+
+  for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
+    bool const active = r0 + lane < o1;
+    int e = -1, n = 0;
+    uint32_t jpack = 0;
+    Core<double> c;
+    Material const* matp = &P.mat[0];
+    bool ok = false;
+    if (active) {
+      int2 const ad = __ldg(P.adj + r0 + lane);
+      e = ad.x >> 2; n = ad.x & 3; jpack = (uint32_t)ad.y;
+      int nd[4], b0[4], nb[4];
+      int const rc = load_and_update<MODEL, SAVE>(P, e, n == 0, nd, b0, nb, matp, c);
+      if (rc != ERR_NONE) report_error(P.err, rc, e);
+      ok = rc == ERR_NONE;
+      if (ok && n == 0) nplastic += c.plastic;
+    }
+    // this lane's row node: select w_n, r_n by predication (never index the register-resident Core dynamically)
+    double wn[3], rn[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      wn[k] = n == 0 ? c.w[0][k] : n == 1 ? c.w[1][k] : n == 2 ? c.w[2][k] : c.w[3][k];
+      rn[k] = n == 0 ? c.r[0][k] : n == 1 ? c.r[1][k] : n == 2 ? c.r[2][k] : c.r[3][k];
+    }
+    double swn[3] = {0, 0, 0};
+    ColNode<double> cnn;
+    if (ok) {
+      double r4[4];
+      element_residual_row(c, *matp, wn, r4);
+      racc[0] += r4[0]; racc[1] += r4[1]; racc[2] += r4[2]; racc[3] += r4[3];
+      if (!TRANSPOSE) sym_mv(c.s, wn, swn);
+      else column_node(c, wn, rn, cnn);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      for (int j = lane; j < nblka; j += 32) maskOf[j] = 0u;
+      uint32_t jm = 0xffffu;
+      if (ok) {
+        double blk[16];
+        if (!TRANSPOSE) {
+          ColNode<double> cnm;
+          column_node(c, c.w[m], c.r[m], cnm);
+          jacobian_block(c, *matp, wn, cnm, swn, blk);
+#pragma unroll
+          for (int t = 0; t < 16; ++t) stg[t * 32 + lane] = blk[t];
+        } else {
+          double swm[3];
+          sym_mv(c.s, c.w[m], swm);
+          jacobian_block(c, *matp, c.w[m], cnn, swm, blk);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) stg[(4 * i + k) * 32 + lane] = blk[4 * k + i];
+        }
+        jm = (jpack >> (8 * m)) & 0xffu;
+      }
+      uint32_t const peers = __match_any_sync(0xffffffffu, jm);
+      __syncwarp();
+      if (ok) maskOf[jm] = peers;  // all lanes of a group write the same value
+      __syncwarp();
+      for (int g = lane; g < nent; g += 32) {
+        uint32_t mk = maskOf[g >> 4];
+        if (mk) {
+          double acc = row[g];
+          int const t = g & 15;
+          while (mk) {
+            int const l = __ffs(mk) - 1;
+            acc += stg[t * 32 + l];
+            mk &= mk - 1;
+          }
+          row[g] = acc;
+        }
+      }
+      __syncwarp();
+    }
+  }
+  // ---- R rows of node a: fixed butterfly over the lanes
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double v = racc[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    racc[i] = v;
+  }
+  if (lane == 0) {
+    double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
+    q[0] = make_double2(racc[0], racc[1]);
+    q[1] = make_double2(racc[2], racc[3]);
+  }
+  // ---- node a's four CRS rows, written once: row i = [4 nblk] contiguous doubles, gathered from the
+  //      block-major accumulator row[16 j + 4 i + k]
+  double* out = P.values + 16 * (int64_t)blk0a;
+  int const rl = 4 * nblka;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    for (int cidx = lane; cidx < rl; cidx += 32) out[i * rl + cidx] = row[16 * (cidx >> 2) + 4 * i + (cidx & 3)];
+  if (MODEL == MODEL_J2) {
+    unsigned const tot = __reduce_add_sync(0xffffffffu, (unsigned)nplastic);
+    if (lane == 0 && tot) atomicAdd(P.plastic, (unsigned long long)tot);
   }
 }
 #endif

@@ -27,6 +27,13 @@ int build_graph_and_schedule(gx_ctx* c) {
   int32_t const* conn = c->conn.data();
   for (int64_t i = 0; i < 4 * (int64_t)ne; ++i)
     if (conn[i] < 0 || conn[i] >= nn) { c->err = "conn entry out of range"; return GX_ERR_ARG; }
+  for (int e = 0; e < ne; ++e) {
+    int32_t const* en = conn + 4 * (int64_t)e;
+    if (en[0] == en[1] || en[0] == en[2] || en[0] == en[3] || en[1] == en[2] || en[1] == en[3] || en[2] == en[3]) {
+      c->err = "element " + std::to_string(e) + " repeats a node"; return GX_ERR_ARG;
+    }
+  }
+  if ((int64_t)ne >= (1ll << 29)) { c->err = "more than 2^29 elements per part"; return GX_ERR_UNSUPPORTED; }
 
   // ---- node -> elements (counting sort)
   std::vector<int64_t> n2e_off(nn + 1, 0);
@@ -38,6 +45,12 @@ int build_graph_and_schedule(gx_ctx* c) {
     for (int e = 0; e < ne; ++e)
       for (int a = 0; a < 4; ++a) n2e[cur[conn[4 * (int64_t)e + a]]++] = e;
   }
+
+  // ---- row-owner work list: incidences (e, n) of every node, elements ascending
+  c->adj_off.resize(nn + 1);
+  c->max_deg = 0;
+  for (int n = 0; n <= nn; ++n) c->adj_off[n] = (uint32_t)n2e_off[n];
+  for (int n = 0; n < nn; ++n) c->max_deg = std::max<int>(c->max_deg, (int)(n2e_off[n + 1] - n2e_off[n]));
 
   // ---- node adjacency, sorted unique per row (two passes: count, fill)
   c->nrow.assign(nn + 1, 0);
@@ -91,6 +104,21 @@ int build_graph_and_schedule(gx_ctx* c) {
     }
   }
 
+  c->max_nblk = 0;
+  for (int n = 0; n < nn; ++n) c->max_nblk = std::max<int>(c->max_nblk, (int)(c->nrow[n + 1] - c->nrow[n]));
+  c->adj.resize(n2e.size());
+#pragma omp parallel for schedule(static)
+  for (int a = 0; a < nn; ++a)
+    for (int64_t k = n2e_off[a]; k < n2e_off[a + 1]; ++k) {
+      int const e = n2e[k];
+      int32_t const* en = conn + 4 * (int64_t)e;
+      int n = 0;
+      while (en[n] != a) ++n;
+      uint8_t const* b = &c->bpos[16 * (size_t)e + 4 * n];
+      c->adj[k].x = e * 4 + n;
+      c->adj[k].y = (int)((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
+    }
+
   // ---- greedy colouring over node conflicts (elements sharing a node get different colours)
   constexpr int W = 4;  // 256 colours at most
   std::vector<uint64_t> used((size_t)nn * W, 0);
@@ -135,12 +163,11 @@ void pack_host(gx_ctx const* c, HostPack& h) {
   h.bpos.resize(ne);
   h.eset.clear();
   if (!c->eset.empty()) h.eset.resize(ne);
-  for (int d = 0; d < ne; ++d) {
-    int const e = c->perm[d];
+  for (int e = 0; e < ne; ++e) {
     int32_t const* c4 = &c->conn[4 * (size_t)e];
-    h.conn4[d].x = c4[0]; h.conn4[d].y = c4[1]; h.conn4[d].z = c4[2]; h.conn4[d].w = c4[3];
-    memcpy(&h.bpos[d], &c->bpos[16 * (size_t)e], 16);
-    if (!h.eset.empty()) h.eset[d] = (uint8_t)c->eset[e];
+    h.conn4[e].x = c4[0]; h.conn4[e].y = c4[1]; h.conn4[e].z = c4[2]; h.conn4[e].w = c4[3];
+    memcpy(&h.bpos[e], &c->bpos[16 * (size_t)e], 16);
+    if (!h.eset.empty()) h.eset[e] = (uint8_t)c->eset[e];
   }
 }
 

@@ -16,7 +16,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 1 --cells 64 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
 tail -2 $OUT/${TAG}_ncu_launches.log
 echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:assemble_kernel -s 31 -c 3 -f -o $OUT/${TAG}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:row_owner_kernel -s 1 -c 2 -f -o $OUT/${TAG}_prof \
   python bench.py --steps 2 --warmup 1 --cells 64 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 tail -2 $OUT/${TAG}_ncu_full.log
 ls -la $OUT | tail -12

@@ -25,11 +25,11 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
   for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
   for (int mm = 0; mm < 4; ++mm) {
     gx::ColNode<double> cn;
-    gx::column_node(c, mm, cn);
+    gx::column_node(c, c.w[mm], c.r[mm], cn);
     for (int n = 0; n < 4; ++n) {
       double sw[3], blk[16];
       gx::sym_mv(c.s, c.w[n], sw);
-      gx::jacobian_block(c, m, n, cn, sw, blk);
+      gx::jacobian_block(c, m, c.w[n], cn, sw, blk);
       for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) K[(4 * n + i) * 16 + 4 * mm + k] = blk[4 * i + k];
     }
   }
@@ -104,22 +104,21 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   }
   std::vector<gx::ZRec> z(nn);
   if (z5) for (int n = 0; n < nn; ++n) { for (int j = 0; j < 3; ++j) z[n].zu[j] = z5[5 * (size_t)n + j]; z[n].zp = z5[5 * (size_t)n + 3]; z[n].zpc = z5[5 * (size_t)n + 4]; }
-  int64_t const st = ((int64_t)ne + 31) / 32 * 32;
-  std::vector<double> s_sig(9 * st, 0.0), s_eq(st, 0.0), s_eqo(st, 0.0), s_fp(9 * st, 0.0), s_fpo(9 * st, 0.0);
-  for (int d = 0; d < ne; ++d) {
-    int const e = c.perm[d];
-    for (int k = 0; k < 9; ++k) { s_sig[k * st + d] = sigma[9 * (size_t)e + k]; }
+  std::vector<double> sin((size_t)gx::STATE_IN * ne, 0.0), sout((size_t)gx::STATE_OUT * ne, 0.0);
+  for (int e = 0; e < ne; ++e) {
+    for (int k = 0; k < 9; ++k) sout[(size_t)gx::STATE_OUT * e + k] = sigma[9 * (size_t)e + k];
     if (model == 1) {
-      s_eq[d] = eqps[e]; s_eqo[d] = eqps_old[e];
-      for (int k = 0; k < 9; ++k) { s_fp[k * st + d] = Fp[9 * (size_t)e + k]; s_fpo[k * st + d] = Fp_old[9 * (size_t)e + k]; }
+      sout[(size_t)gx::STATE_OUT * e + 18] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 9] = eqps_old[e];
+      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + 9 + k] = Fp[9 * (size_t)e + k]; sin[(size_t)gx::STATE_IN * e + k] = Fp_old[9 * (size_t)e + k]; }
     }
   }
   int err[2] = {0, 0};
   unsigned long long pl = 0;
   gx::KParams P;
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
-  P.Fp_old = s_fpo.data(); P.eqps_old = s_eqo.data(); P.Fp = s_fp.data(); P.eqps = s_eq.data(); P.sigma = s_sig.data();
-  P.sstride = st; P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne;
+  P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data();
+  P.state_in = sin.data(); P.state_out = sout.data();
+  P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
   int64_t npl = 0;
   using namespace gx;
@@ -131,12 +130,11 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
     default: npl = run_colours<M, PASS_ERROR, false>(c, P); }
   if (model == 1) { HC_RUN(MODEL_J2) } else { HC_RUN(MODEL_NEOHOOKEAN) }
   *plastic = npl;
-  for (int d = 0; d < ne; ++d) {
-    int const e = c.perm[d];
-    for (int k = 0; k < 9; ++k) sigma[9 * (size_t)e + k] = s_sig[k * st + d];
+  for (int e = 0; e < ne; ++e) {
+    for (int k = 0; k < 9; ++k) sigma[9 * (size_t)e + k] = sout[(size_t)gx::STATE_OUT * e + k];
     if (model == 1) {
-      eqps[e] = s_eq[d];
-      for (int k = 0; k < 9; ++k) Fp[9 * (size_t)e + k] = s_fp[k * st + d];
+      eqps[e] = sout[(size_t)gx::STATE_OUT * e + 18];
+      for (int k = 0; k < 9; ++k) Fp[9 * (size_t)e + k] = sout[(size_t)gx::STATE_OUT * e + 9 + k];
     }
   }
   return err[0] ? 100 + err[0] : 0;
