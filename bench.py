@@ -45,6 +45,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-cells", type=int, default=44, help="cells per side of each host thread's sample block")
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (gx_set_option), repeatable")
     return ap.parse_args()
 
 
@@ -194,6 +195,9 @@ def run_b200(args):
         f = fields(co, len(cn), node_gid=part["node_gid"], elem_gid=part["elem_gid"])
         a = goal_b200.Assembler(co, cn, args.model, [MATERIAL], device=local, partition=part)
         a.comm_init_torch(dist)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        a.set_option(k, int(v))
     ne_local = a.ne
     # pinned host buffers for the end-to-end arm
     u_h = torch.from_numpy(np.ascontiguousarray(f["u"])).pin_memory()

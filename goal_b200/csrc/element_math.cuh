@@ -148,11 +148,21 @@ struct Core {
   S q[3];      // F^{-T} grad p
   S tau[6];    // Kirchhoff stress of the mixed Cauchy stress, J*sigma
   S s[6];      // trial deviatoric Kirchhoff stress (goal_J2.cpp:89)
-  S A1;        // beta*mu*J^{-2/3}
   S beta;      // radial-return scaling of s (1 when elastic)
-  // plastic branch only
-  S N[6], smag, mubar, dgam, D, c1;
+  S c1;        // mu*J^{-2/3}
+  S mubar;     // mu*tr(be)/3 (J2)
   int plastic;
+  // ---- tangent data, pre-scaled by vol (see "closed-form tangent" below)
+  S Tv[6];     // vol * tau
+  S Gm[6];     // vol * (g_r I + g_N N): maps r_m to the part of gamma_m that multiplies s w_n
+  S gwv;       // vol * g_w
+  S A1v;       // vol * beta * c1
+  S Jpv;       // vol * J * p
+  S upc;       // vol * J / 4                  d R_u / d p_m       = upc * w_n
+  S va;        // vol * (-1/8)(1 + 1/J^2) J    d R_p / d u (volumetric part)
+  S tjv;       // vol * taus * J
+  S ppc;       // vol / (16 kappa)
+  S rb;        // vol * (p/kappa - (J - 1/J)/2) / 4     R_p without stabilization
   // geometry kept for the adjoint-weighted residual
   S G[4][3];
   S Finv[9];
@@ -213,6 +223,9 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   S snew[6];
   c.plastic = 0;
   c.beta = S(1.0);
+  c.mubar = S(0.0);
+  S g_r = S(0.0), g_N = S(0.0), g_w = S(-2.0 / 3.0);  // elastic: gamma_m = -(2/3) w_m
+  S Nn[6] = {S(0.0), S(0.0), S(0.0), S(0.0), S(0.0), S(0.0)};
   if (MODEL == MODEL_NEOHOOKEAN) {
     S const Jm13 = S(1.0) / cbrt(J);
     Jm23 = Jm13 * Jm13;
@@ -278,17 +291,24 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
       // Radial return.  With linear hardening the reference's Newton loop on X
       // (goal_J2.cpp:108-121) lands on X = f / (2 mubar + 2K/3) in two iterations.
       c.plastic = 1;
-      c.smag = smag;
-      c.D = S(2.0) * c.mubar + S(2.0 / 3.0) * mat.K;
-      c.dgam = f / c.D;
+      S const mubar = c.mubar;
+      S const rD = S(1.0) / (S(2.0) * mubar + S(2.0 / 3.0) * mat.K);
+      S const dgam = f * rD;
       S const rs = S(1.0) / smag;
-      for (int i = 0; i < 6; ++i) c.N[i] = c.s[i] * rs;
-      c.beta = S(1.0) - S(2.0) * c.mubar * c.dgam * rs;
-      for (int i = 0; i < 6; ++i) snew[i] = c.s[i] - S(2.0) * c.mubar * c.dgam * c.N[i];
-      eqps_out = eqps_old + sq23 * c.dgam;
+      S N[6];
+      for (int i = 0; i < 6; ++i) N[i] = c.s[i] * rs;
+      c.beta = S(1.0) - S(2.0) * mubar * dgam * rs;
+      for (int i = 0; i < 6; ++i) snew[i] = c.s[i] - S(2.0) * mubar * dgam * N[i];
+      eqps_out = eqps_old + sq23 * dgam;
+      // gamma_mk = d beta(m,k) - (2/3) beta w_m[k] is linear in (r_m, N r_m, w_m):
+      //   gamma_m = (g_r I + g_N N) r_m + g_w w_m
+      g_r = S(-4.0 / 3.0) * rs * dgam * c1 * (S(1.0) - S(2.0) * mubar * rD);
+      g_N = S(4.0) * c1 * mubar * rs * (dgam * rs - rD);
+      g_w = S(2.0 / 3.0) * c.beta * (S(2.0) * mubar * rD - S(1.0));
+      for (int i = 0; i < 6; ++i) Nn[i] = N[i];
       if (save) {
-        S A[9] = {c.dgam * c.N[0], c.dgam * c.N[3], c.dgam * c.N[4], c.dgam * c.N[3], c.dgam * c.N[1],
-                  c.dgam * c.N[5], c.dgam * c.N[4], c.dgam * c.N[5], c.dgam * c.N[2]};
+        S A[9] = {dgam * N[0], dgam * N[3], dgam * N[4], dgam * N[3], dgam * N[1],
+                  dgam * N[5], dgam * N[4], dgam * N[5], dgam * N[2]};
         S E[9];
         expm3(A, E);
         mm3(E, Fp_old, Fp_out);
@@ -299,7 +319,6 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   c.r[0][0] = -(c.r[1][0] + c.r[2][0] + c.r[3][0]);
   c.r[0][1] = -(c.r[1][1] + c.r[2][1] + c.r[3][1]);
   c.r[0][2] = -(c.r[1][2] + c.r[2][2] + c.r[3][2]);
-  c.A1 = c.beta * c.c1;
   // sigma = s/J + pr*I (model), then Mixed: sigma_ii += p - tr(sigma)/3
   S sig[6];
   for (int i = 0; i < 3; ++i) sig[i] = snew[i] * rJ + pr;
@@ -313,82 +332,106 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
     sigma_out[5] = sigma_out[7] = sig[5];
   }
   for (int i = 0; i < 6; ++i) c.tau[i] = J * sig[i];
+  // ---- pre-scaled tangent data
+  S const vol = c.vol;
+  for (int i = 0; i < 6; ++i) c.Tv[i] = vol * c.tau[i];
+  S const vgN = vol * g_N, vgr = vol * g_r;
+  c.Gm[0] = vgN * Nn[0] + vgr; c.Gm[1] = vgN * Nn[1] + vgr; c.Gm[2] = vgN * Nn[2] + vgr;
+  c.Gm[3] = vgN * Nn[3]; c.Gm[4] = vgN * Nn[4]; c.Gm[5] = vgN * Nn[5];
+  c.gwv = vol * g_w;
+  c.A1v = vol * c.beta * c.c1;
+  S const vJ = vol * J;
+  c.Jpv = vJ * c.pv;
+  c.upc = S(0.25) * vJ;
+  c.va = S(-0.125) * (vJ + vol * rJ);  // vol * (-1/8)(1 + 1/J^2) J
+  c.tjv = c.taus * vJ;
+  S const rkappa = S(1.0) / mat.kappa;
+  c.ppc = S(1.0 / 16.0) * vol * rkappa;
+  c.rb = S(0.25) * vol * (c.pv * rkappa - S(0.5) * (J - rJ));
   return ERR_NONE;
 }
 
+// ---------------------------------------------------------------------------
+// Residual.  R_u[n] = vol tau w_n,  R_p[n] = rb + vol taus J (q . w_n)
+// ---------------------------------------------------------------------------
+// One node's rows: out = (R_u[n][0..2], R_p[n]) for the node whose spatial gradient is wn.
+template <class S> GX_HD void element_residual_row(Core<S> const& c, S const wn[3], S out[4]) {
+  sym_mv(c.Tv, wn, out);
+  out[3] = c.rb + c.tjv * dot3(c.q, wn);
+}
 // Element residual: ru[n*3+i] (momentum), rp[n] (pressure + stabilization).
-template <class S> GX_HD void element_residual(Core<S> const& c, Material const& mat, S ru[12], S rp[4]) {
-  S const base = (c.pv / mat.kappa - S(0.5) * (c.J - S(1.0) / c.J)) * S(0.25);
-  S const tj = c.taus * c.J;
+template <class S> GX_HD void element_residual(Core<S> const& c, S ru[12], S rp[4]) {
   for (int n = 0; n < 4; ++n) {
-    S tw[3];
-    sym_mv(c.tau, c.w[n], tw);
-    ru[3 * n] = c.vol * tw[0]; ru[3 * n + 1] = c.vol * tw[1]; ru[3 * n + 2] = c.vol * tw[2];
-    rp[n] = c.vol * (base + tj * dot3(c.q, c.w[n]));
+    S o[4];
+    element_residual_row(c, c.w[n], o);
+    ru[3 * n] = o[0]; ru[3 * n + 1] = o[1]; ru[3 * n + 2] = o[2]; rp[n] = o[3];
   }
 }
 
-// One node's rows of the element residual: out = (R_u[n][0..2], R_p[n]) for the node whose spatial gradient is wn.
-template <class S> GX_HD void element_residual_row(Core<S> const& c, Material const& mat, S const wn[3], S out[4]) {
-  S tw[3];
-  sym_mv(c.tau, wn, tw);
-  out[0] = c.vol * tw[0]; out[1] = c.vol * tw[1]; out[2] = c.vol * tw[2];
-  out[3] = c.vol * ((c.pv / mat.kappa - S(0.5) * (c.J - S(1.0) / c.J)) * S(0.25) + c.taus * c.J * dot3(c.q, wn));
-}
-
-// Per-column-node quantities of the Jacobian: everything that depends on m only.
+// ---------------------------------------------------------------------------
+// Closed-form tangent.  For the seed (m,k) (displacement k of node m):
+//   K[(n,i),(m,k)] = w_n[k] A_m[i] + w_n[i] B_m[k] + g_m[k] (s w_n)[i] + delta_ik (rA_m . w_n)
+//     A_m  = vol (beta c1 r_m - tau w_m)          material + geometric stiffness
+//     B_m  = vol (-(2/3) beta c1 r_m + J p w_m)   d(J^{-2/3}) and d(J p) terms
+//     g_m  = vol (Gamma r_m + g_w w_m)            radial-return scaling d beta (zero Gamma when elastic)
+//     rA_m = vol beta c1 r_m
+//   K[(n,p),(m,k)] = w_m[k] cq_n - (w_m . w_n) tq[k] - tqw_m w_n[k],
+//     cq_n = va + tjv (q . w_n),  tq = tjv q,  tqw_m = tjv (q . w_m)
+//   K[(n,i),(m,p)] = upc w_n[i]        K[(n,p),(m,p)] = ppc + tjv (w_m . w_n)
+// ---------------------------------------------------------------------------
 template <class S>
 struct ColNode {
-  S w[3], r[3], tw[3];  // w_m, r_m, tau w_m
-  S gam[3];             // gamma_mk multiplying s w_n
-  S qw;                 // q . w_m
+  S w[3];   // w_m
+  S A[3], B[3], g[3], rA[3];
+  S tqw;
 };
 
 // wm = w_m, rm = r_m (passed explicitly so that callers with a run-time node index can select them
 // without indexing the register-resident Core dynamically)
 template <class S> GX_HD void column_node(Core<S> const& c, S const wm[3], S const rm[3], ColNode<S>& cn) {
-  for (int k = 0; k < 3; ++k) { cn.w[k] = wm[k]; cn.r[k] = rm[k]; }
-  sym_mv(c.tau, cn.w, cn.tw);
-  cn.qw = dot3(c.q, cn.w);
-  S const t23 = S(2.0 / 3.0);
-  if (c.plastic) {
-    S Nr[3];
-    sym_mv(c.N, cn.r, Nr);
-    S const rs = S(1.0) / c.smag;
-    for (int k = 0; k < 3; ++k) {
-      S const dmubar = t23 * (c.c1 * cn.r[k] - cn.w[k] * c.mubar);
-      S const dsmag = S(2.0) * c.c1 * Nr[k] - t23 * cn.w[k] * c.smag;
-      S const ddgam = (dsmag - S(2.0) * c.dgam * dmubar) / c.D;
-      S const dbeta = S(-2.0) * ((dmubar * c.dgam + c.mubar * ddgam) * rs - c.mubar * c.dgam * dsmag * rs * rs);
-      cn.gam[k] = dbeta - c.beta * t23 * cn.w[k];
-    }
-  } else {
-    for (int k = 0; k < 3; ++k) cn.gam[k] = -t23 * cn.w[k];
+  S tw[3], gr[3];
+  sym_mv(c.Tv, wm, tw);
+  sym_mv(c.Gm, rm, gr);
+  S const m23 = S(-2.0 / 3.0);
+  for (int k = 0; k < 3; ++k) {
+    cn.w[k] = wm[k];
+    cn.rA[k] = c.A1v * rm[k];
+    cn.A[k] = cn.rA[k] - tw[k];
+    cn.B[k] = m23 * cn.rA[k] + c.Jpv * wm[k];
+    cn.g[k] = gr[k] + c.gwv * wm[k];
   }
+  cn.tqw = c.tjv * dot3(c.q, wm);
 }
 
-// 4x4 block K[(n,i),(m,k)], i,k = 0..3 (eq 3 = pressure), row-major in `blk`; m is the node `cn` was built
-// for, wn = w_n the row node's spatial gradient, sw = s w_n (shared by the four column nodes).
+// Row-node quantities shared by the four column nodes.
 template <class S>
-GX_HD void jacobian_block(Core<S> const& c, Material const& mat, S const wn[3], ColNode<S> const& cn, S const sw[3],
-                          S blk[16]) {
-  S const rw = dot3(cn.r, wn);
-  S const W = dot3(cn.w, wn);
-  S const qwn = dot3(c.q, wn);
-  S const Jp = c.J * c.pv;
-  S const t23 = S(2.0 / 3.0);
+struct RowNode {
+  S w[3];   // w_n
+  S sw[3];  // s w_n
+  S cq;     // va + tjv (q . w_n)
+  S up[3];  // upc w_n
+};
+template <class S> GX_HD void row_node(Core<S> const& c, S const wn[3], RowNode<S>& rn) {
+  for (int k = 0; k < 3; ++k) { rn.w[k] = wn[k]; rn.up[k] = c.upc * wn[k]; }
+  sym_mv(c.s, wn, rn.sw);
+  rn.cq = c.va + c.tjv * dot3(c.q, wn);
+}
+
+// 4x4 block K[(n,i),(m,k)], i,k = 0..3 (eq 3 = pressure), row-major in `blk`.
+template <class S>
+GX_HD void jacobian_block(Core<S> const& c, RowNode<S> const& rn, ColNode<S> const& cn, S blk[16]) {
+  S const d = dot3(cn.rA, rn.w);
+  S const W = dot3(cn.w, rn.w);
   for (int i = 0; i < 3; ++i) {
     for (int k = 0; k < 3; ++k) {
-      S v = c.A1 * (cn.r[i] * wn[k] - t23 * cn.r[k] * wn[i]) + cn.gam[k] * sw[i] + Jp * cn.w[k] * wn[i] - cn.tw[i] * wn[k];
-      if (i == k) v += c.A1 * rw;
-      blk[4 * i + k] = c.vol * v;
+      S v = rn.w[k] * cn.A[i] + rn.w[i] * cn.B[k] + cn.g[k] * rn.sw[i];
+      if (i == k) v += d;
+      blk[4 * i + k] = v;
     }
-    blk[4 * i + 3] = c.vol * c.J * S(0.25) * wn[i];  // d R_u / d p_m
+    blk[4 * i + 3] = rn.up[i];
   }
-  S const tj = c.taus * c.J;
-  S const a = S(-0.125) * (S(1.0) + S(1.0) / (c.J * c.J)) * c.J;
-  for (int k = 0; k < 3; ++k) blk[12 + k] = c.vol * (a * cn.w[k] + tj * (cn.w[k] * qwn - c.q[k] * W - cn.qw * wn[k]));
-  blk[15] = c.vol * (S(1.0 / 16.0) / mat.kappa + tj * W);
+  for (int k = 0; k < 3; ++k) blk[12 + k] = cn.w[k] * rn.cq - W * (c.tjv * c.q[k]) - cn.tqw * rn.w[k];
+  blk[15] = c.ppc + c.tjv * W;
 }
 
 // Residual of the error chain: the same integrand tested with the adjoint-weighted
@@ -396,7 +439,7 @@ GX_HD void jacobian_block(Core<S> const& c, Material const& mat, S const wn[3], 
 // (goal_displacement_adjoint.cpp:48-52); PResidual uses z_p-diff, Stabilization uses
 // z_p-coarse (goal_mechanics.cpp:214).  zu: [4][3] nodal u_z_diff; zp, zpc: [4].
 template <class S>
-GX_HD void element_error_residual(Core<S> const& c, Material const& mat, S const zu[4][3], S const zp[4],
+GX_HD void element_error_residual(Core<S> const& c, S const zu[4][3], S const zp[4],
                                   S const zpc[4], S ru[12], S rp[4]) {
   S z[3], gz[9];
   for (int i = 0; i < 3; ++i) {
@@ -420,14 +463,13 @@ GX_HD void element_error_residual(Core<S> const& c, Material const& mat, S const
     }
     pg[i] = acc;
   }
-  S const base = (c.pv / mat.kappa - S(0.5) * (c.J - S(1.0) / c.J)) * zs * S(0.25);
-  S const tj = c.taus * c.J;
+  S const base = c.rb * zs;
   S const qh = dot3(c.q, hz) * S(0.25);
   for (int n = 0; n < 4; ++n) {
     S tw[3];
-    sym_mv(c.tau, c.w[n], tw);
-    for (int i = 0; i < 3; ++i) ru[3 * n + i] = c.vol * (S(0.25) * pg[i] + z[i] * tw[i]);
-    rp[n] = c.vol * (base + tj * (qh + zc * dot3(c.q, c.w[n])));
+    sym_mv(c.Tv, c.w[n], tw);
+    for (int i = 0; i < 3; ++i) ru[3 * n + i] = S(0.25) * c.vol * pg[i] + z[i] * tw[i];
+    rp[n] = base + c.tjv * (qh + zc * dot3(c.q, c.w[n]));
   }
 }
 

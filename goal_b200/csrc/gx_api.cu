@@ -158,16 +158,15 @@ static void fill_params(gx_ctx* ctx, KParams& P) {
 }
 
 static size_t row_owner_smem(gx_ctx const* ctx, int warps) {
-  size_t const per_warp = 16 * 32 * sizeof(double) + (size_t)16 * ctx->max_nblk * sizeof(double) +
-                          (size_t)((ctx->max_nblk + 3) & ~3) * sizeof(uint32_t);
-  return per_warp * warps;
+  return row_owner_smem_per_warp(ctx->max_nblk) * warps;
 }
 
 template <int MODEL, bool TRANSPOSE, bool SAVE>
 static cudaError_t launch_row_owner(gx_ctx* ctx, KParams& P) {
   int const warps = (int)ctx->opt_row_warps;
   size_t const smem = row_owner_smem(ctx, warps);
-  auto kern = row_owner_kernel<MODEL, TRANSPOSE, SAVE>;
+  // MINB = 2 caps the kernel at 128 registers/thread (16 warps/SM) at the price of some spills
+  auto kern = ctx->opt_row_minblocks == 2 ? row_owner_kernel<MODEL, TRANSPOSE, SAVE, 2> : row_owner_kernel<MODEL, TRANSPOSE, SAVE, 1>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P);
@@ -579,6 +578,11 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (k == "kernel") {  // 0 = row-owner Jacobian kernel (default), 1 = coloured element kernel
     if (value != 0 && value != 1) { ctx->err = "kernel must be 0 or 1"; return GX_ERR_ARG; }
     ctx->opt_kernel = value;
+    return GX_OK;
+  }
+  if (k == "row_minblocks") {
+    if (value != 1 && value != 2) { ctx->err = "row_minblocks must be 1 or 2"; return GX_ERR_ARG; }
+    ctx->opt_row_minblocks = value;
     return GX_OK;
   }
   if (k == "row_warps") {

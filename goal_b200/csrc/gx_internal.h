@@ -122,7 +122,8 @@ struct gx_ctx {
   bool have_values = false;
   int64_t opt_block = 128;
   int64_t opt_kernel = 0;  // 0 = row-owner Jacobian kernel, 1 = coloured element kernel
-  int64_t opt_row_warps = 8;
+  int64_t opt_row_warps = 4;
+  int64_t opt_row_minblocks = 1;
   std::string err;
 };
 

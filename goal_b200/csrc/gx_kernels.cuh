@@ -145,7 +145,7 @@ GX_HD int assemble_element(KParams const& P, int slot) {
   Core<double> c;
   int const rc = load_and_update<MODEL, SAVE>(P, e, true, nd, blk0, nblk, matp, c);
   if (rc != ERR_NONE) { report_error(P.err, rc, e); return 0; }
-  Material const& mat = *matp;
+  (void)matp;
 
   // ---- residual (Displacement/Pressure::scatter_primal, R[row] += resid)
   double ru[12], rp[4];
@@ -157,9 +157,9 @@ GX_HD int assemble_element(KParams const& P, int slot) {
       double2 const a = ldg(q), b = ldg(q + 1), d = ldg(q + 2);
       zu[n][0] = a.x; zu[n][1] = a.y; zu[n][2] = b.x; zp[n] = b.y; zpc[n] = d.x;
     }
-    element_error_residual(c, mat, zu, zp, zpc, ru, rp);
+    element_error_residual(c, zu, zp, zpc, ru, rp);
   } else {
-    element_residual(c, mat, ru, rp);
+    element_residual(c, ru, rp);
   }
 #pragma unroll
   for (int n = 0; n < 4; ++n) add4(P.R + 4 * (int64_t)nd[n], ru[3 * n], ru[3 * n + 1], ru[3 * n + 2], rp[n]);
@@ -168,9 +168,9 @@ GX_HD int assemble_element(KParams const& P, int slot) {
   if (PASS == PASS_JACOBIAN || PASS == PASS_JACOBIAN_T) {
     uint4 const bq = ldg(P.bpos + e);
     uint32_t const bw[4] = {bq.x, bq.y, bq.z, bq.w};  // bw[n] byte m = position of block (n,m)
-    double sw[4][3];
+    RowNode<double> rn[4];
 #pragma unroll
-    for (int n = 0; n < 4; ++n) sym_mv(c.s, c.w[n], sw[n]);
+    for (int n = 0; n < 4; ++n) row_node(c, c.w[n], rn[n]);
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
       ColNode<double> cnm;
@@ -178,7 +178,7 @@ GX_HD int assemble_element(KParams const& P, int slot) {
 #pragma unroll
       for (int n = 0; n < 4; ++n) {
         double blk[16];
-        jacobian_block(c, mat, c.w[n], cnm, sw[n], blk);
+        jacobian_block(c, rn[n], cnm, blk);
         if (PASS == PASS_JACOBIAN) {
           // A(row (n,i), col (m,k)) += blk[i][k]      (scatter_primal, goal_displacement.cpp:177-194)
           int64_t const rowlen = 4 * (int64_t)nblk[n];
@@ -215,24 +215,27 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 // node n of e.  Lane work: element core, then for each column node m the 4x4 block
 //   PRIMAL : K[(n,.),(m,.)]           -> block (a, a_m) of node a's rows
 //   ADJOINT: K[(m,.),(n,.)]^T         -> block (a, a_m) of the transposed operator
-// staged in shared memory as stg[16][32]; lanes whose target block position coincides are found with
-// __match_any_sync and summed by the entry's owner lane in ascending lane order (= ascending element id),
-// so every CRS entry is produced by exactly one thread in a fixed order: deterministic, write-once.
-// Nodes with more than 32 incident elements take several rounds; the row accumulates in shared memory.
-// Shared memory per warp: stg 4 KB + row 128*max_nblk B + mask 4*max_nblk B.
+// staged in shared memory (stg[16][33]).  The blocks are then folded into the node's row accumulator
+// by a fixed schedule: half-warp h = 0/1 walks the staged blocks of lanes 16h .. 16h+15 in ascending
+// lane order (= ascending element id), lane t of the half adding entry t of each block into its own
+// accumulator copy acc[h][16 j + t]; the two copies are summed at the end.  Every CRS entry is therefore
+// produced by one thread in a fixed order: deterministic, atomics-free, written exactly once.
+// Nodes with more than 32 incident elements take several rounds.
+// Shared memory per warp: stg 16*33*8 B + acc 2*128*max_nblk B.
 // ---------------------------------------------------------------------------
-template <int MODEL, bool TRANSPOSE, bool SAVE>
-__global__ void __launch_bounds__(256) row_owner_kernel(const __grid_constant__ KParams P) {
+constexpr int STG_LD = 33;
+GX_HD size_t row_owner_smem_per_warp(int max_nblk) {
+  return (size_t)(16 * STG_LD + 2 * 16 * max_nblk) * sizeof(double);
+}
+
+template <int MODEL, bool TRANSPOSE, bool SAVE, int MINB>
+__global__ void __launch_bounds__(256, MINB) row_owner_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  int const warps = blockDim.x >> 5;
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int const mb = P.max_nblk;
-  size_t const per_warp = 16 * 32 * sizeof(double) + (size_t)16 * mb * sizeof(double) + (size_t)((mb + 3) & ~3) * sizeof(uint32_t);
-  unsigned char* base = smem_raw + per_warp * wib;
-  double* stg = reinterpret_cast<double*>(base);
-  double* row = stg + 16 * 32;
-  uint32_t* maskOf = reinterpret_cast<uint32_t*>(row + 16 * mb);
-  (void)warps;
+  int const half = lane >> 4, t16 = lane & 15;
+  double* stg = reinterpret_cast<double*>(smem_raw + row_owner_smem_per_warp(P.max_nblk) * wib);
+  double* acc = stg + 16 * STG_LD;  // [2][16*max_nblk], block-major: acc[h][16 j + 4 i + k]
+  int const accld = 16 * P.max_nblk;
 
   int const a = blockIdx.x * (blockDim.x >> 5) + wib;
   if (a >= P.nn) return;  // whole warp exits together
@@ -244,80 +247,78 @@ __global__ void __launch_bounds__(256) row_owner_kernel(const __grid_constant__ 
     nblka = __double2hiint(d3.y);
   }
   int const nent = 16 * nblka;
-  for (int g = lane; g < nent; g += 32) row[g] = 0.0;
+  for (int g = lane; g < nent; g += 32) { acc[g] = 0.0; acc[accld + g] = 0.0; }
   double racc[4] = {0.0, 0.0, 0.0, 0.0};
   int nplastic = 0;
 
   for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
-    bool const active = r0 + lane < o1;
-    int e = -1, n = 0;
+    int const nact = min(32, (int)(o1 - r0));  // active lanes of this round: 0 .. nact-1
+    bool const active = lane < nact;
+    int n = 0;
     uint32_t jpack = 0;
     Core<double> c;
-    Material const* matp = &P.mat[0];
     bool ok = false;
     if (active) {
       int2 const ad = __ldg(P.adj + r0 + lane);
-      e = ad.x >> 2; n = ad.x & 3; jpack = (uint32_t)ad.y;
+      int const e = ad.x >> 2;
+      n = ad.x & 3; jpack = (uint32_t)ad.y;
       int nd[4], b0[4], nb[4];
+      Material const* matp;
       int const rc = load_and_update<MODEL, SAVE>(P, e, n == 0, nd, b0, nb, matp, c);
       if (rc != ERR_NONE) report_error(P.err, rc, e);
       ok = rc == ERR_NONE;
       if (ok && n == 0) nplastic += c.plastic;
     }
-    // this lane's row node: select w_n, r_n by predication (never index the register-resident Core dynamically)
-    double wn[3], rn[3];
+    // this lane's own node: select w_n, r_n by predication (never index the register-resident Core dynamically)
+    double wn[3], rn3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
       wn[k] = n == 0 ? c.w[0][k] : n == 1 ? c.w[1][k] : n == 2 ? c.w[2][k] : c.w[3][k];
-      rn[k] = n == 0 ? c.r[0][k] : n == 1 ? c.r[1][k] : n == 2 ? c.r[2][k] : c.r[3][k];
+      rn3[k] = n == 0 ? c.r[0][k] : n == 1 ? c.r[1][k] : n == 2 ? c.r[2][k] : c.r[3][k];
     }
-    double swn[3] = {0, 0, 0};
-    ColNode<double> cnn;
+    RowNode<double> rown;  // PRIMAL: this lane's row node
+    ColNode<double> coln;  // ADJOINT: this lane's column node
     if (ok) {
       double r4[4];
-      element_residual_row(c, *matp, wn, r4);
+      element_residual_row(c, wn, r4);
       racc[0] += r4[0]; racc[1] += r4[1]; racc[2] += r4[2]; racc[3] += r4[3];
-      if (!TRANSPOSE) sym_mv(c.s, wn, swn);
-      else column_node(c, wn, rn, cnn);
+      if (!TRANSPOSE) row_node(c, wn, rown);
+      else column_node(c, wn, rn3, coln);
     }
 #pragma unroll
     for (int m = 0; m < 4; ++m) {
-      for (int j = lane; j < nblka; j += 32) maskOf[j] = 0u;
-      uint32_t jm = 0xffffu;
+      uint32_t jm = 0;
       if (ok) {
         double blk[16];
         if (!TRANSPOSE) {
           ColNode<double> cnm;
           column_node(c, c.w[m], c.r[m], cnm);
-          jacobian_block(c, *matp, wn, cnm, swn, blk);
+          jacobian_block(c, rown, cnm, blk);
 #pragma unroll
-          for (int t = 0; t < 16; ++t) stg[t * 32 + lane] = blk[t];
+          for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = blk[t];
         } else {
-          double swm[3];
-          sym_mv(c.s, c.w[m], swm);
-          jacobian_block(c, *matp, c.w[m], cnn, swm, blk);
+          RowNode<double> rnm;
+          row_node(c, c.w[m], rnm);
+          jacobian_block(c, rnm, coln, blk);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) stg[(4 * i + k) * 32 + lane] = blk[4 * k + i];
+            for (int k = 0; k < 4; ++k) stg[(4 * i + k) * STG_LD + lane] = blk[4 * k + i];
         }
         jm = (jpack >> (8 * m)) & 0xffu;
+      } else if (active) {
+#pragma unroll
+        for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = 0.0;  // failed element: contributes nothing
       }
-      uint32_t const peers = __match_any_sync(0xffffffffu, jm);
       __syncwarp();
-      if (ok) maskOf[jm] = peers;  // all lanes of a group write the same value
-      __syncwarp();
-      for (int g = lane; g < nent; g += 32) {
-        uint32_t mk = maskOf[g >> 4];
-        if (mk) {
-          double acc = row[g];
-          int const t = g & 15;
-          while (mk) {
-            int const l = __ffs(mk) - 1;
-            acc += stg[t * 32 + l];
-            mk &= mk - 1;
-          }
-          row[g] = acc;
+      // fold: half-warp h walks lanes 16h .. 16h+15 (those below nact), uniform trip count
+      {
+        int const trips = min(16, nact);
+        double* my = acc + half * accld + t16;
+        for (int it = 0; it < trips; ++it) {
+          int const l = 16 * half + it;
+          uint32_t const j = __shfl_sync(0xffffffffu, jm, l);
+          if (l < nact) my[16 * j] += stg[t16 * STG_LD + l];
         }
       }
       __syncwarp();
@@ -337,12 +338,15 @@ __global__ void __launch_bounds__(256) row_owner_kernel(const __grid_constant__ 
     q[1] = make_double2(racc[2], racc[3]);
   }
   // ---- node a's four CRS rows, written once: row i = [4 nblk] contiguous doubles, gathered from the
-  //      block-major accumulator row[16 j + 4 i + k]
+  //      block-major accumulators acc[h][16 j + 4 i + k]
   double* out = P.values + 16 * (int64_t)blk0a;
   int const rl = 4 * nblka;
 #pragma unroll
   for (int i = 0; i < 4; ++i)
-    for (int cidx = lane; cidx < rl; cidx += 32) out[i * rl + cidx] = row[16 * (cidx >> 2) + 4 * i + (cidx & 3)];
+    for (int cidx = lane; cidx < rl; cidx += 32) {
+      int const g = 16 * (cidx >> 2) + 4 * i + (cidx & 3);
+      out[i * rl + cidx] = acc[g] + acc[accld + g];
+    }
   if (MODEL == MODEL_J2) {
     unsigned const tot = __reduce_add_sync(0xffffffffu, (unsigned)nplastic);
     if (lane == 0 && tot) atomicAdd(P.plastic, (unsigned long long)tot);

@@ -21,15 +21,16 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
   if (rc) return rc;
   *wrote_Fp = wf; *plastic = c.plastic;
   double ru[12], rp[4];
-  gx::element_residual(c, m, ru, rp);
+  gx::element_residual(c, ru, rp);
   for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
   for (int mm = 0; mm < 4; ++mm) {
     gx::ColNode<double> cn;
     gx::column_node(c, c.w[mm], c.r[mm], cn);
     for (int n = 0; n < 4; ++n) {
-      double sw[3], blk[16];
-      gx::sym_mv(c.s, c.w[n], sw);
-      gx::jacobian_block(c, m, c.w[n], cn, sw, blk);
+      double blk[16];
+      gx::RowNode<double> rn;
+      gx::row_node(c, c.w[n], rn);
+      gx::jacobian_block(c, rn, cn, blk);
       for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) K[(4 * n + i) * 16 + 4 * mm + k] = blk[4 * i + k];
     }
   }
@@ -51,7 +52,7 @@ extern "C" int hc_error_residual(int model, const double* x, const double* u, co
                       : gx::element_core<gx::MODEL_J2>(X, U, p, m, Fp_old, eqps_old, false, sg, eq, fp, wf, c);
   if (rc) return rc;
   double ru[12], rp[4];
-  gx::element_error_residual(c, m, Z, zp, zpc, ru, rp);
+  gx::element_error_residual(c, Z, zp, zpc, ru, rp);
   for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
   return 0;
 }

@@ -72,7 +72,7 @@ def test_jacobian_residual_state_parity(cube, model, mesh):
     assert relerr(At, Ato) < 1e-12
     assert np.array_equal(a.get_state("sigma"), sig_before)
     Ap = a.jacobian(goal_b200.PRIMAL, save=False)[1].copy()
-    assert abs(a.csr(At) - a.csr(Ap).T).max() == 0.0
+    assert abs(a.csr(At) - a.csr(Ap).T).max() < 1e-12 * np.abs(Ap).max()  # same sums, different order
     # residual-only pass (Primal::compute_resid)
     assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12
     # States::update
@@ -198,7 +198,7 @@ def test_full_size_properties_1M():
     assert np.array_equal(R, R2) and np.array_equal(A, A2)
     K = a.csr(A)
     At = a.jacobian(goal_b200.ADJOINT, save=False)[1].copy()
-    assert abs(a.csr(At) - K.T).max() == 0.0
+    assert abs(a.csr(At) - K.T).max() < 1e-12 * np.abs(A).max()
     # rigid translation leaves F unchanged: residual invariant and K t = 0
     t = np.zeros((a.nn, 4)); t[:, :3] = (0.3, -0.2, 0.1)
     assert np.abs(K @ t.reshape(-1)).max() < 1e-9 * np.abs(A).max()
