@@ -27,7 +27,8 @@ SYMBOLS = [
     "gx_compute_jacobian", "gx_localize_error", "gx_element_error", "gx_comm_init", "gx_nccl_unique_id",
     "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
-    "gx_stream", "gx_last_timing", "gx_set_option",
+    "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
+    "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan",
 ]
 
 
@@ -93,6 +94,13 @@ def load_library():
     L.gx_stream.argtypes = [vp]
     L.gx_last_timing.argtypes = [vp, dp]
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.gx_num_peers.argtypes = [vp, ip]
+    L.gx_struct_pack.argtypes = [vp, C.c_int, C.POINTER(vp), lp]
+    L.gx_struct_unpack.argtypes = [vp, C.c_int, vp, C.c_int64]
+    L.gx_struct_finalize.argtypes = [vp]
+    L.gx_owned_graph.argtypes = [vp, ip, C.POINTER(ip), lp, C.POINTER(lp), C.POINTER(lp)]
+    L.gx_fetch_owned.argtypes = [vp, vp, vp]
+    L.gx_exchange_plan.argtypes = [vp, C.c_int, ip, ip, C.POINTER(ip), C.POINTER(ip), C.POINTER(ip), C.POINTER(ip)]
     _LIB = L
     return L
 
@@ -146,6 +154,7 @@ class Assembler:
             d.node_gid = gid.ctypes.data_as(C.POINTER(C.c_int64))
             d.node_owner, d.n_peers = _ip(own), len(pr)
             d.peer_rank, d.peer_offset, d.peer_nodes = _ip(pr), _ip(po), _ip(pn)
+            self._peer_ranks = pr
         self.h = C.c_void_p()
         rc = self.L.gx_create(C.byref(d), C.byref(self.h))
         if rc:
@@ -281,3 +290,102 @@ class Assembler:
     def csr(self, values):
         import scipy.sparse as sp
         return sp.csr_matrix((values, self.colind, self.rowptr), shape=(4 * self.nn, 4 * self.nn))
+
+    # ---- mesh parts (SolInfo::gather_*, Disc owned graph)
+    @property
+    def num_peers(self):
+        n = C.c_int32()
+        self._ck(self.L.gx_num_peers(self.h, C.byref(n)))
+        return n.value
+
+    def struct_pack(self, peer):
+        blob, nb = C.c_void_p(), C.c_int64()
+        self._ck(self.L.gx_struct_pack(self.h, peer, C.byref(blob), C.byref(nb)))
+        return C.string_at(blob, nb.value) if nb.value else b""
+
+    def struct_unpack(self, peer, data):
+        buf = C.create_string_buffer(data, len(data)) if data else None
+        self._ck(self.L.gx_struct_unpack(self.h, peer, buf, len(data)))
+
+    def struct_finalize(self):
+        self._ck(self.L.gx_struct_finalize(self.h))
+        nnz, nrows = C.c_int64(), C.c_int32()
+        self._ck(self.L.gx_graph_size(self.h, C.byref(nnz), C.byref(nrows)))
+
+    def exchange_structure(self, dist):
+        """structure exchange over torch.distributed point-to-point (any backend)."""
+        import torch
+        ops, recv = [], {}
+        peers = [self.exchange_plan_rank(p) for p in range(self.num_peers)]
+        out = [torch.frombuffer(bytearray(self.struct_pack(p)) or bytearray(8), dtype=torch.int64) for p in range(self.num_peers)]
+        lens_out = [torch.tensor([len(self.struct_pack(p)) // 8]) for p in range(self.num_peers)]
+        lens_in = [torch.zeros(1, dtype=torch.int64) for _ in peers]
+        for p, q in enumerate(peers):
+            ops += [dist.P2POp(dist.isend, lens_out[p], q), dist.P2POp(dist.irecv, lens_in[p], q)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        ops = []
+        for p, q in enumerate(peers):
+            recv[p] = torch.zeros(max(int(lens_in[p]), 1), dtype=torch.int64)
+            if int(lens_out[p]):
+                ops.append(dist.P2POp(dist.isend, out[p], q))
+            if int(lens_in[p]):
+                ops.append(dist.P2POp(dist.irecv, recv[p], q))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        for p in range(self.num_peers):
+            n = int(lens_in[p])
+            self.struct_unpack(p, recv[p][:n].numpy().tobytes() if n else b"")
+        self.struct_finalize()
+
+    def exchange_plan_rank(self, peer):
+        r = C.c_int32()
+        cnt = (C.c_int32 * 2)()
+        # before finalize only the rank is meaningful; use the description we were built with
+        return int(self._peer_ranks[peer])
+
+    def exchange_plan(self, peer):
+        r, cnt = C.c_int32(), (C.c_int32 * 2)()
+        sn, rn, rc, rm = (C.POINTER(C.c_int32)() for _ in range(4))
+        self._ck(self.L.gx_exchange_plan(self.h, peer, C.byref(r), cnt, C.byref(sn), C.byref(rn), C.byref(rc), C.byref(rm)))
+        ns, nr = cnt[0], cnt[1]
+        arr = lambda p, n: np.ctypeslib.as_array(p, (n,)).copy() if n else np.zeros(0, np.int32)
+        recv_cnt = arr(rc, nr)
+        return dict(rank=r.value, send_nodes=arr(sn, ns), recv_nodes=arr(rn, nr), recv_cnt=recv_cnt,
+                    recv_map=arr(rm, int(recv_cnt.sum())))
+
+    def owned_graph(self):
+        no, nnz = C.c_int32(), C.c_int64()
+        on, rp, cg = C.POINTER(C.c_int32)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)()
+        self._ck(self.L.gx_owned_graph(self.h, C.byref(no), C.byref(on), C.byref(nnz), C.byref(rp), C.byref(cg)))
+        return dict(nodes=np.ctypeslib.as_array(on, (no.value,)).copy(),
+                    rowptr=np.ctypeslib.as_array(rp, (4 * no.value + 1,)).copy(),
+                    col_gid=np.ctypeslib.as_array(cg, (nnz.value,)).copy())
+
+    def fetch_owned(self, values=True):
+        g = self.owned_graph()
+        R = np.zeros(4 * len(g["nodes"]))
+        V = np.zeros(len(g["col_gid"])) if values else None
+        self._ck(self.L.gx_fetch_owned(self.h, _addr(R), _addr(V)))
+        return R, V, g
+
+    def comm_init_torch(self, dist):
+        """NCCL communicator for this context; the unique id travels over torch.distributed."""
+        uid = C.create_string_buffer(128)
+        n = C.c_size_t(128)
+        if dist.get_rank() == 0:
+            rc = self.L.gx_nccl_unique_id(uid, C.byref(n))
+            if rc:
+                raise GxError(rc, "gx_nccl_unique_id failed (libnccl not loadable?)")
+        box = [uid.raw]
+        dist.broadcast_object_list(box, src=0)
+        self._ck(self.L.gx_comm_init(self.h, C.create_string_buffer(box[0], 128), 128))
+
+    def reduce_interfaces(self, what=3):
+        self._ck(self.L.gx_reduce_interfaces(self.h, what))
+
+    def allreduce_sum(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1).copy()
+        self._ck(self.L.gx_allreduce_sum(self.h, _dp(x), len(x)))
+        return x

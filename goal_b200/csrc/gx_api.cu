@@ -191,6 +191,8 @@ static int status_of_element_error(int code) {
 
 // zero + assemble on the ctx stream, then synchronise and collect the error flag / counters.
 static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
+  if (ctx->device < 0) { ctx->err = "host-only context (device = -1) cannot compute"; return GX_ERR_CUDA; }
+  if (!ctx->struct_done) { ctx->err = "partitioned context: finish the structure exchange (gx_comm_init or gx_struct_*) first"; return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
   ctx->launches = 0;
   int const zero2[2] = {0, 0};
@@ -203,7 +205,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
     // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The row-owner schedule writes every
     // entry of R and of the CRS values exactly once, so it needs no zeroing pass.
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
-    if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz, ctx->stream));
+    if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz_x, ctx->stream));
   }
   GX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   KParams P;
@@ -241,7 +243,12 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
 
 static int fetch(gx_ctx* ctx, double* R_out, double* values_out) {
   if (R_out) GX_CUDA(cudaMemcpyAsync(R_out, ctx->d_R, sizeof(double) * 4 * (size_t)ctx->nn, cudaMemcpyDeviceToHost, ctx->stream));
-  if (values_out) GX_CUDA(cudaMemcpyAsync(values_out, ctx->d_values, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+  if (values_out) {  // reference ghost layout (phantom blocks of a partitioned context dropped)
+    double* src = nullptr;
+    int rc = ghost_values_dev(ctx, &src);
+    if (rc) return rc;
+    GX_CUDA(cudaMemcpyAsync(values_out, src, sizeof(double) * (size_t)ctx->nnz, cudaMemcpyDeviceToHost, ctx->stream));
+  }
   if (R_out || values_out) GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
@@ -260,6 +267,7 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
 }
 
 static void free_device(gx_ctx* ctx) {
+  if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj,
                   ctx->d_state_in, ctx->d_state_out, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
@@ -269,7 +277,6 @@ static void free_device(gx_ctx* ctx) {
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
 }
 
-namespace gx { void comm_destroy(gx_ctx*); int comm_setup_lists(gx_ctx*, const gx_desc*); }
 
 // ---------------------------------------------------------------------------
 extern "C" {
@@ -285,8 +292,10 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     return GX_ERR_ARG;
   }
   if (d->flags & GX_FLAG_NO_STABILIZATION) { g_create_err = "gx_create: stabilization: false is not supported"; return GX_ERR_UNSUPPORTED; }
+  // device = -1 builds a host-only context: graph, scatter map and exchange plan only (for setup-time
+  // tools and CPU tests of the partition logic); every compute entry point refuses to run on it.
   int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || d->device < 0 || d->device >= ndev) {
+  if (d->device != -1 && (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0 || d->device < 0 || d->device >= ndev)) {
     g_create_err = "gx_create: no usable CUDA device (this library has no CPU path)";
     return GX_ERR_CUDA;
   }
@@ -363,8 +372,10 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * 1024));
     return GX_OK;
   };
-  rc = body();
-  if (rc) return fail(rc);
+  if (ctx->device >= 0) {
+    rc = body();
+    if (rc) return fail(rc);
+  }
   *out = ctx;
   return GX_OK;
 }
@@ -399,8 +410,15 @@ int gx_scatter_map(gx_ctx* ctx, uint8_t* bpos) {
   return GX_OK;
 }
 
+static int host_only(gx_ctx* ctx) {
+  if (ctx->device >= 0) return GX_OK;
+  ctx->err = "host-only context (device = -1) cannot compute";
+  return GX_ERR_CUDA;
+}
+
 int gx_set_solution(gx_ctx* ctx, const double* u, const double* p) {
   if (!ctx || !u || !p) { if (ctx) ctx->err = "gx_set_solution: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
   GX_CUDA(cudaSetDevice(ctx->device));
   int const nn = ctx->nn;
   double* du = ctx->d_stage;
@@ -415,6 +433,7 @@ int gx_set_solution(gx_ctx* ctx, const double* u, const double* p) {
 
 int gx_get_state(gx_ctx* ctx, const char* name, double* out) {
   if (!ctx || !out) return GX_ERR_ARG;
+  if (host_only(ctx)) return GX_ERR_CUDA;
   StateLoc L;
   if (!state_loc(ctx, name, L)) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
@@ -428,6 +447,7 @@ int gx_get_state(gx_ctx* ctx, const char* name, double* out) {
 
 int gx_set_state(gx_ctx* ctx, const char* name, const double* in) {
   if (!ctx || !in) return GX_ERR_ARG;
+  if (host_only(ctx)) return GX_ERR_CUDA;
   StateLoc L;
   if (!state_loc(ctx, name, L)) { ctx->err = std::string("unknown state: ") + (name ? name : "(null)"); return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
@@ -441,6 +461,7 @@ int gx_set_state(gx_ctx* ctx, const char* name, const double* in) {
 
 int gx_update_states(gx_ctx* ctx) {
   if (!ctx) return GX_ERR_ARG;
+  if (host_only(ctx)) return GX_ERR_CUDA;
   if (ctx->model != GX_MODEL_J2) return GX_OK;  // only J2 registers old states (goal_mechanics.cpp:90-93)
   GX_CUDA(cudaSetDevice(ctx->device));
   int64_t const tot = (int64_t)ctx->ne * STATE_IN;
@@ -467,6 +488,7 @@ int gx_compute_jacobian(gx_ctx* ctx, int mode, int save_state, double* R_out, do
 
 int gx_localize_error(gx_ctx* ctx, const double* zu_diff, const double* zp_diff, const double* zp_coarse, double* R_out) {
   if (!ctx || !zu_diff || !zp_diff || !zp_coarse) { if (ctx) ctx->err = "gx_localize_error: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
   GX_CUDA(cudaSetDevice(ctx->device));
   int const nn = ctx->nn;
   double* a = ctx->d_stage;
@@ -485,6 +507,7 @@ int gx_localize_error(gx_ctx* ctx, const double* zu_diff, const double* zp_diff,
 int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, const int32_t* parent, int32_t n_parent,
                      double* eta_elem, double* eta_parent, double* bound) {
   if (!ctx || !u_err || !p_err) { if (ctx) ctx->err = "gx_element_error: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
   GX_CUDA(cudaSetDevice(ctx->device));
   int const nn = ctx->nn, ne = ctx->ne;
   // stage layout: [0,3nn) u_err, [3nn,4nn) p_err, [4nn,8nn) err4; eta reuses d_values-independent scratch below
@@ -547,6 +570,7 @@ int gx_result_dev(gx_ctx* ctx, double** R_dev, double** values_dev) {
 
 int gx_fetch(gx_ctx* ctx, double* R_out, double* values_out) {
   if (!ctx) return GX_ERR_ARG;
+  if (host_only(ctx)) return GX_ERR_CUDA;
   if (!ctx->have_result) { ctx->err = "gx_fetch: no result yet"; return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
   return fetch(ctx, R_out, values_out);

@@ -39,18 +39,19 @@ struct Peer {
   std::vector<int32_t> nodes;       // shared nodes, agreed order
   std::vector<int32_t> send_nodes;  // subset owned by the peer   (we send our partial rows)
   std::vector<int32_t> recv_nodes;  // subset owned by this rank  (we receive and add)
+  // structure exchange: per send node [nblk, global column node ids...]
+  std::vector<int64_t> struct_out, struct_in;
+  bool struct_have = false;
+  // value exchange plan
+  std::vector<int64_t> send_off, recv_off;  // [n+1] offsets (doubles) of each node's packed block rows
+  std::vector<int64_t> recv_moff;           // [n_recv+1] offsets into recv_map
+  std::vector<int32_t> recv_cnt;            // sender's block count per recv node
+  std::vector<int32_t> recv_map;            // sender block -> block position in the owner's extended row
+  int64_t send_vals = 0, recv_vals = 0;     // doubles of CRS payload
   // device side
-  int32_t* d_send_nodes = nullptr;
-  int32_t* d_recv_nodes = nullptr;
-  int64_t* d_send_off = nullptr;  // [n_send+1] offsets (in doubles) of each node's packed block rows
-  int64_t* d_recv_off = nullptr;
-  // column translation for received rows: for recv node j, for each block sent by the peer, the
-  // local block position it adds into (or -1 if this part does not have that column)
-  int32_t* d_recv_map = nullptr;
-  std::vector<int64_t> send_off, recv_off;
-  int64_t send_vals = 0, recv_vals = 0;  // doubles of CRS payload
-  double* d_send = nullptr;
-  double* d_recv = nullptr;
+  int32_t *d_send_nodes = nullptr, *d_recv_nodes = nullptr, *d_recv_map = nullptr, *d_recv_cnt = nullptr;
+  int64_t *d_send_off = nullptr, *d_recv_off = nullptr, *d_recv_moff = nullptr;
+  double *d_send = nullptr, *d_recv = nullptr, *d_sendR = nullptr, *d_recvR = nullptr;
 };
 
 struct NcclApi;  // resolved with dlopen (gx_nccl.cpp)
@@ -114,6 +115,16 @@ struct gx_ctx {
   std::vector<gx::Peer> peers;
   gx::NcclApi* nccl = nullptr;
   void* comm = nullptr;
+  bool struct_done = true;
+  // extended block rows: ghost row + phantom columns appended (owned interface nodes only)
+  std::vector<int64_t> nrow_x;    // [nn+1]
+  std::vector<int64_t> xcol_gid;  // [nrow_x[nn]] global node id of every block
+  int64_t nnz_x = 0;
+  std::vector<int32_t> owned_nodes;
+  std::vector<int64_t> owned_rowptr, owned_colgid;
+  int32_t *d_blk0_x = nullptr, *d_nblk_x = nullptr, *d_nblk_g = nullptr;
+  int64_t* d_blk0_g = nullptr;
+  double* d_ghost_vals = nullptr;
   // ---- bookkeeping
   int64_t last_plastic = 0;
   double timing[4] = {0, 0, 0, 0};
@@ -141,4 +152,8 @@ struct HostPack {
 constexpr int STATE_IN = 10;   // doubles per element
 constexpr int STATE_OUT = 20;
 void pack_host(gx_ctx const* c, HostPack& h);
+// gx_comm.cu
+void comm_destroy(gx_ctx*);
+int comm_setup_lists(gx_ctx*, const gx_desc*);
+int ghost_values_dev(gx_ctx* ctx, double** out);
 }  // namespace gx

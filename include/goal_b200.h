@@ -68,7 +68,7 @@ typedef struct {
   int32_t n_elem_sets;      /* <= GX_MAX_ELEM_SETS */
   int32_t model;            /* GX_MODEL_* (mechanics: model) */
   const double* materials;  /* [n_elem_sets*5] E, nu, K, Y, c0 per set (src/goal_J2.cpp:12-24) */
-  int32_t device;           /* CUDA device ordinal */
+  int32_t device;           /* CUDA device ordinal; -1 = host-only context (graph / exchange plan only, cannot compute) */
   uint32_t flags;
   /* ---- partition (all zero / NULL for a single part) ------------------------
    * PUMI remotes as the .smb stores them: for each neighbouring part the list of
@@ -131,6 +131,27 @@ int gx_element_error(gx_ctx* ctx, const double* u_err /*[n_nodes*3]*/, const dou
                      const int32_t* parent /*[n_elems]*/, int32_t n_parent, double* eta_elem /*[n_elems]*/,
                      double* eta_parent /*[n_parent]*/, double* bound);
 
+/* ---- mesh parts ------------------------------------------------------------------------------
+ * Structure exchange == the owned_graph Export/INSERT of Disc::compute_graphs (src/goal_disc.cpp:327-329):
+ * once after gx_create on a partitioned context, every rank sends peer p the blob of gx_struct_pack(p),
+ * feeds what it received to gx_struct_unpack(p), then calls gx_struct_finalize.  Any transport works
+ * (MPI in the reference, torch.distributed in the tests); gx_comm_init does it over NCCL. */
+int gx_num_peers(gx_ctx* ctx, int32_t* n);
+int gx_struct_pack(gx_ctx* ctx, int peer_index, const void** blob, int64_t* bytes);
+int gx_struct_unpack(gx_ctx* ctx, int peer_index, const void* blob, int64_t bytes);
+int gx_struct_finalize(gx_ctx* ctx);
+/* Owned view (Disc owned_map / owned_graph, src/goal_disc.cpp:270-290, 327-329): the nodes this rank owns
+ * in ascending local id, dof-level row offsets, and GLOBAL column dof ids (4*global_node + eq) in stored
+ * order: the ghost row's columns (sorted by local id) followed by columns that exist only on other parts
+ * (sorted by global id). */
+int gx_owned_graph(gx_ctx* ctx, int32_t* n_owned_nodes, const int32_t** owned_nodes, int64_t* nnz_owned,
+                   const int64_t** rowptr /*[4*n_owned+1]*/, const int64_t** col_gid /*[nnz_owned]*/);
+int gx_fetch_owned(gx_ctx* ctx, double* R_owned /*[4*n_owned]*/, double* values_owned /*[nnz_owned]*/);
+/* The exchange plan of one peer (for hosts that verify or emulate the exchange). counts = {n_send, n_recv};
+ * recv_cnt[s] = sender's block count of receive node s, recv_map = concatenated block maps. */
+int gx_exchange_plan(gx_ctx* ctx, int peer_index, int32_t* peer_rank, int32_t counts[2], const int32_t** send_nodes,
+                     const int32_t** recv_nodes, const int32_t** recv_cnt, const int32_t** recv_map);
+
 /* SolInfo::gather_R / gather_dRdu (Tpetra Export ghost->owned, ADD; src/goal_sol_info.cpp:33-43)
  * over NCCL.  After it, rows of nodes this part owns hold the sum over all parts, rows of
  * nodes owned elsewhere are left as local partial sums.  what: bit 0 = R, bit 1 = dRdu. */
@@ -139,7 +160,8 @@ int gx_nccl_unique_id(void* out, size_t* id_bytes); /* helper: rank 0 creates, h
 int gx_reduce_interfaces(gx_ctx* ctx, int what);
 int gx_allreduce_sum(gx_ctx* ctx, double* x, int n);
 /* Pack / unpack halves of the exchange for hosts that bring their own transport
- * (MPI, torch.distributed): interface rows of peer `p` as a flat device buffer. */
+ * (MPI, torch.distributed): interface rows of peer `p` as a flat device buffer.
+ * `what` is 1 (R: 4 doubles per send node) or 2 (dRdu: the node's block rows). */
 int gx_interface_bytes(gx_ctx* ctx, int peer_index, int what, int64_t* send_bytes, int64_t* recv_bytes);
 int gx_pack_interface(gx_ctx* ctx, int peer_index, int what, void** send_dev);
 int gx_unpack_add_interface(gx_ctx* ctx, int peer_index, int what, const void* recv_dev);

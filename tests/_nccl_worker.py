@@ -1,0 +1,54 @@
+"""Worker of tests/test_gpu_parts.py::test_nccl_reduce_interfaces_two_gpus: one part per GPU,
+gx_comm_init + gx_reduce_interfaces over NCCL, owned rows checked against a serial oracle assembly."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import goal_b200
+    from goal_b200.partition import block_part
+    from goal_b200.synthetic import MATERIAL
+    from test_gpu_parts import _check_owned, _serial_truth
+    grid = {2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[world]
+    parts = [block_part(5, grid, r) for r in range(world)]
+    me = parts[rank]
+    for model in ("J2", "neohookean"):
+        o, fs, Rs, Vs = _serial_truth(parts, model)
+        a = goal_b200.Assembler(me["coords"], me["conn"], model, [MATERIAL], device=local, partition=me)
+        a.comm_init_torch(dist)
+        a.set_solution(fs["u"][me["node_gid"]], fs["p"][me["node_gid"]])
+        if model == "J2":
+            off = sum(len(p["conn"]) for p in parts[:rank])
+            a.set_state("Fp_old", fs["Fp_old"][off:off + a.ne]); a.set_state("eqps_old", fs["eqps_old"][off:off + a.ne])
+        for _ in range(2):  # repeated passes must give the same bits
+            a.jacobian(goal_b200.PRIMAL, save=False, out=False)
+            a.reduce_interfaces(3)
+            R1, V1, _ = a.fetch_owned()
+        a.jacobian(goal_b200.PRIMAL, save=False, out=False)
+        a.reduce_interfaces(3)
+        R2, V2, _ = a.fetch_owned()
+        assert np.array_equal(R1, R2) and np.array_equal(V1, V2)
+        _check_owned(a, me, o, Rs, Vs)
+        s = a.allreduce_sum(np.array([float(rank + 1)]))
+        assert s[0] == world * (world + 1) / 2
+        a.close()
+    dist.barrier()
+    if rank == 0:
+        print(f"OK nccl world={world}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
