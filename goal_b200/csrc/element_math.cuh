@@ -48,7 +48,49 @@ enum { ERR_NONE = 0, ERR_INVERTED_ELEMENT = 1, ERR_INVERTED_DEFORMATION = 2, ERR
 
 struct Material {  // per elem set; kappa/mu as in goal_neohookean.cpp:50-51
   double kappa, mu, K, Y, c0;
+  double rkappa;  // 1/kappa
+  double tauc;    // 0.5*c0/(6*mu): tau = tauc * (sum of the 6 squared edge lengths)  goal_stabilization.cpp:59-72
 };
+GX_HD Material make_material(double E, double nu, double K, double Y, double c0) {
+  Material m;
+  m.kappa = E / (3.0 * (1.0 - 2.0 * nu));
+  m.mu = E / (2.0 * (1.0 + nu));
+  m.K = K; m.Y = Y; m.c0 = c0;
+  m.rkappa = 1.0 / m.kappa;
+  m.tauc = 0.5 * c0 / (6.0 * m.mu);
+  return m;
+}
+// 1/cbrt(x) and 1/sqrt(x): single device intrinsics, plain libm on the host build
+template <class S> GX_HD S gx_rcbrt(S x) {
+#if defined(__CUDA_ARCH__)
+  return rcbrt(x);
+#else
+  return S(1.0) / cbrt(x);
+#endif
+}
+template <class S> GX_HD S gx_rsqrt(S x) {
+#if defined(__CUDA_ARCH__)
+  return rsqrt(x);
+#else
+  return S(1.0) / sqrt(x);
+#endif
+}
+// Cp^{-1} = Fp^{-1} Fp^{-T} (symmetric, 00 11 22 01 02 12) of a plastic deformation gradient
+// (goal_J2.cpp:84-87).  Depends on the old state only, so it is cached per element, not per pass.
+template <class S> GX_HD void cp_inverse(S const Fp[9], S Cp[6]) {
+  S Fpi[9];
+  S const d = Fp[0] * (Fp[4] * Fp[8] - Fp[5] * Fp[7]) - Fp[1] * (Fp[3] * Fp[8] - Fp[5] * Fp[6]) + Fp[2] * (Fp[3] * Fp[7] - Fp[4] * Fp[6]);
+  S const rd = S(1.0) / d;
+  Fpi[0] = (Fp[4] * Fp[8] - Fp[5] * Fp[7]) * rd; Fpi[1] = (Fp[2] * Fp[7] - Fp[1] * Fp[8]) * rd; Fpi[2] = (Fp[1] * Fp[5] - Fp[2] * Fp[4]) * rd;
+  Fpi[3] = (Fp[5] * Fp[6] - Fp[3] * Fp[8]) * rd; Fpi[4] = (Fp[0] * Fp[8] - Fp[2] * Fp[6]) * rd; Fpi[5] = (Fp[2] * Fp[3] - Fp[0] * Fp[5]) * rd;
+  Fpi[6] = (Fp[3] * Fp[7] - Fp[4] * Fp[6]) * rd; Fpi[7] = (Fp[1] * Fp[6] - Fp[0] * Fp[7]) * rd; Fpi[8] = (Fp[0] * Fp[4] - Fp[1] * Fp[3]) * rd;
+  Cp[0] = Fpi[0] * Fpi[0] + Fpi[1] * Fpi[1] + Fpi[2] * Fpi[2];
+  Cp[1] = Fpi[3] * Fpi[3] + Fpi[4] * Fpi[4] + Fpi[5] * Fpi[5];
+  Cp[2] = Fpi[6] * Fpi[6] + Fpi[7] * Fpi[7] + Fpi[8] * Fpi[8];
+  Cp[3] = Fpi[0] * Fpi[3] + Fpi[1] * Fpi[4] + Fpi[2] * Fpi[5];
+  Cp[4] = Fpi[0] * Fpi[6] + Fpi[1] * Fpi[7] + Fpi[2] * Fpi[8];
+  Cp[5] = Fpi[3] * Fpi[6] + Fpi[4] * Fpi[7] + Fpi[5] * Fpi[8];
+}
 
 // symmetric 3x3 storage: 00 11 22 01 02 12
 template <class S> GX_HD void sym_mv(S const t[6], S const v[3], S o[3]) {
@@ -82,9 +124,9 @@ template <class S> GX_HD void mm3(S const A[9], S const B[9], S o[9]) {
     for (int j = 0; j < 3; ++j) o[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 
-// exp of a 3x3 matrix: [3/3] Pade when ||A||_1 <= 1.4956e-2 (truncation error below
-// double round-off, the branch minitensor::exp takes for every realistic plastic
-// increment), otherwise [13/13] Pade with scaling and squaring (Higham 2005).
+// exp of a 3x3 matrix by Pade approximation with Higham's (2005) order selection, which is what
+// minitensor::exp does: [3/3] for ||A||_1 <= 1.4956e-2, [5/5] for <= 2.5394e-1 (every realistic plastic
+// increment dgam*N lands in one of these two), otherwise [13/13] with scaling and squaring.
 template <class S> GX_HD void expm3(S const A[9], S o[9]) {
   S n1 = 0;
   for (int j = 0; j < 3; ++j) {
@@ -92,11 +134,19 @@ template <class S> GX_HD void expm3(S const A[9], S o[9]) {
     n1 = c > n1 ? c : n1;
   }
   S A2[9], U[9], V[9], T[9];
-  if (n1 <= S(1.495585217958292e-2)) {
+  if (n1 <= S(2.539398330063230e-1)) {
     mm3(A, A, A2);
-    for (int i = 0; i < 9; ++i) { T[i] = A2[i]; V[i] = S(12.) * A2[i]; }
-    T[0] += S(60.); T[4] += S(60.); T[8] += S(60.);
-    V[0] += S(120.); V[4] += S(120.); V[8] += S(120.);
+    if (n1 <= S(1.495585217958292e-2)) {
+      for (int i = 0; i < 9; ++i) { T[i] = A2[i]; V[i] = S(12.) * A2[i]; }
+      T[0] += S(60.); T[4] += S(60.); T[8] += S(60.);
+      V[0] += S(120.); V[4] += S(120.); V[8] += S(120.);
+    } else {
+      S A4[9];
+      mm3(A2, A2, A4);
+      for (int i = 0; i < 9; ++i) { T[i] = A4[i] + S(420.) * A2[i]; V[i] = S(30.) * A4[i] + S(3360.) * A2[i]; }
+      T[0] += S(15120.); T[4] += S(15120.); T[8] += S(15120.);
+      V[0] += S(30240.); V[4] += S(30240.); V[8] += S(30240.);
+    }
     mm3(A, T, U);
   } else {
     int sq = 0;
@@ -163,22 +213,24 @@ struct Core {
   S tjv;       // vol * taus * J
   S ppc;       // vol / (16 kappa)
   S rb;        // vol * (p/kappa - (J - 1/J)/2) / 4     R_p without stabilization
+  S dN[6];     // plastic branch: flow increment dgam*N (symmetric), input of plastic_update
   // geometry kept for the adjoint-weighted residual
   S G[4][3];
   S Finv[9];
 };
 
 // Geometry + kinematics + stress update.  x,u: [4][3]; p: [4].
-// Fp_old/eqps_old are read only for MODEL_J2.  When `save` is set the state the
+// Cp (= Cp^{-1} of the old plastic state, see cp_inverse) and eqps_old are read only for MODEL_J2.
+// The plastic flow increment dgam*N is returned in c.dN; the caller turns it into the new Fp with
+// plastic_update() after the Jacobian work (keeps the matrix exponential's temporaries out of the
+// register-critical section).  When `save` is set the state the
 // reference's evaluators would leave behind is written to sigma_out (mixed Cauchy,
-// goal_mixed.cpp:44-45), eqps_out, and -- plastic branch only -- Fp_out
+// goal_mixed.cpp:44-45) and eqps_out; Fp is the caller's job -- plastic branch only
 // (goal_J2.cpp:128-136; on the elastic branch Fp is deliberately left untouched).
 // Returns an ERR_* code.
 template <int MODEL, class S>
-GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material const& mat, S const Fp_old[9],
-                       S eqps_old, bool save, S sigma_out[9], S& eqps_out, S Fp_out[9], bool& write_Fp,
-                       Core<S>& c) {
-  write_Fp = false;
+GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material const& mat, S const Cp[6],
+                       S eqps_old, bool save, S sigma_out[9], S& eqps_out, Core<S>& c) {
   // ---- linear tet geometry: G_n = grad N_n, vol = det/6, h^2 = mean squared edge length
   S e1[3], e2[3], e3[3];
   for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; e3[j] = x[3][j] - x[0][j]; }
@@ -186,6 +238,11 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   cross3(e2, e3, c23); cross3(e3, e1, c31); cross3(e1, e2, c12);
   S const dv = dot3(e1, c23);
   if (!(dv > S(0.0))) return ERR_INVERTED_ELEMENT;
+  // grad u = (1/dv) sum_n (u_n - u_0) (x) c_n with c_n the cofactor columns
+  S Fd[9];  // dv * grad u
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      Fd[3 * i + j] = (u[1][i] - u[0][i]) * c23[j] + (u[2][i] - u[0][i]) * c31[j] + (u[3][i] - u[0][i]) * c12[j];
   S const rdv = S(1.0) / dv;
   for (int j = 0; j < 3; ++j) {
     c.G[1][j] = c23[j] * rdv; c.G[2][j] = c31[j] * rdv; c.G[3][j] = c12[j] * rdv;
@@ -197,13 +254,11 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
     S a = x[2][j] - x[1][j], b = x[3][j] - x[1][j], d = x[3][j] - x[2][j];
     h2 += a * a + b * b + d * d;
   }
-  c.taus = S(0.5) * mat.c0 * (h2 * S(1.0 / 6.0)) / mat.mu;
+  c.taus = mat.tauc * h2;
 
   // ---- F = I + grad u, J, F^{-1}; p and grad p at the centroid
   S F[9];
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j)
-      F[3 * i + j] = (u[1][i] - u[0][i]) * c.G[1][j] + (u[2][i] - u[0][i]) * c.G[2][j] + (u[3][i] - u[0][i]) * c.G[3][j];
+  for (int i = 0; i < 9; ++i) F[i] = Fd[i] * rdv;
   F[0] += S(1.0); F[4] += S(1.0); F[8] += S(1.0);
   S const J = det3(F);
   if (!(J > S(0.0))) return ERR_INVERTED_DEFORMATION;
@@ -227,7 +282,7 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   S g_r = S(0.0), g_N = S(0.0), g_w = S(-2.0 / 3.0);  // elastic: gamma_m = -(2/3) w_m
   S Nn[6] = {S(0.0), S(0.0), S(0.0), S(0.0), S(0.0), S(0.0)};
   if (MODEL == MODEL_NEOHOOKEAN) {
-    S const Jm13 = S(1.0) / cbrt(J);
+    S const Jm13 = gx_rcbrt(J);
     Jm23 = Jm13 * Jm13;
     // b = F F^T
     S b[6];
@@ -246,17 +301,10 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
       for (int i = 0; i < 3; ++i) c.r[n][i] = F[3 * i] * c.G[n][0] + F[3 * i + 1] * c.G[n][1] + F[3 * i + 2] * c.G[n][2];
     for (int i = 0; i < 6; ++i) snew[i] = c.s[i];
   } else {
-    Jm23 = pow(J, S(-2.0 / 3.0));
-    S Fpi[9];
-    inv3(Fp_old, S(1.0) / det3(Fp_old), Fpi);
-    // Cp^{-1} = Fp^{-1} Fp^{-T} (symmetric)
-    S Cp[6];
-    Cp[0] = Fpi[0] * Fpi[0] + Fpi[1] * Fpi[1] + Fpi[2] * Fpi[2];
-    Cp[1] = Fpi[3] * Fpi[3] + Fpi[4] * Fpi[4] + Fpi[5] * Fpi[5];
-    Cp[2] = Fpi[6] * Fpi[6] + Fpi[7] * Fpi[7] + Fpi[8] * Fpi[8];
-    Cp[3] = Fpi[0] * Fpi[3] + Fpi[1] * Fpi[4] + Fpi[2] * Fpi[5];
-    Cp[4] = Fpi[0] * Fpi[6] + Fpi[1] * Fpi[7] + Fpi[2] * Fpi[8];
-    Cp[5] = Fpi[3] * Fpi[6] + Fpi[4] * Fpi[7] + Fpi[5] * Fpi[8];
+    {
+      S const Jm13 = gx_rcbrt(J);  // J^{-2/3} (goal_J2.cpp:80 uses pow; same value to round-off)
+      Jm23 = Jm13 * Jm13;
+    }
     // M = F Cp^{-1}; B = M F^T (symmetric)
     S M[9];
     for (int i = 0; i < 3; ++i) {
@@ -281,8 +329,10 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
     c.mubar = c1 * tr3;  // mu * trace(be) / 3
     for (int n = 1; n < 4; ++n)
       for (int i = 0; i < 3; ++i) c.r[n][i] = M[3 * i] * c.G[n][0] + M[3 * i + 1] * c.G[n][1] + M[3 * i + 2] * c.G[n][2];
-    S const smag = sqrt(c.s[0] * c.s[0] + c.s[1] * c.s[1] + c.s[2] * c.s[2] +
-                        S(2.0) * (c.s[3] * c.s[3] + c.s[4] * c.s[4] + c.s[5] * c.s[5]));
+    S const s2 = c.s[0] * c.s[0] + c.s[1] * c.s[1] + c.s[2] * c.s[2] +
+                 S(2.0) * (c.s[3] * c.s[3] + c.s[4] * c.s[4] + c.s[5] * c.s[5]);
+    S const rs = s2 > S(0.0) ? gx_rsqrt(s2) : S(0.0);
+    S const smag = s2 * rs;
     S const sq23 = S(0.81649658092772603273);  // sqrt(2/3)
     S const f = smag - sq23 * (mat.Y + mat.K * eqps_old);
     eqps_out = eqps_old;
@@ -294,7 +344,6 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
       S const mubar = c.mubar;
       S const rD = S(1.0) / (S(2.0) * mubar + S(2.0 / 3.0) * mat.K);
       S const dgam = f * rD;
-      S const rs = S(1.0) / smag;
       S N[6];
       for (int i = 0; i < 6; ++i) N[i] = c.s[i] * rs;
       c.beta = S(1.0) - S(2.0) * mubar * dgam * rs;
@@ -305,15 +354,7 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
       g_r = S(-4.0 / 3.0) * rs * dgam * c1 * (S(1.0) - S(2.0) * mubar * rD);
       g_N = S(4.0) * c1 * mubar * rs * (dgam * rs - rD);
       g_w = S(2.0 / 3.0) * c.beta * (S(2.0) * mubar * rD - S(1.0));
-      for (int i = 0; i < 6; ++i) Nn[i] = N[i];
-      if (save) {
-        S A[9] = {dgam * N[0], dgam * N[3], dgam * N[4], dgam * N[3], dgam * N[1],
-                  dgam * N[5], dgam * N[4], dgam * N[5], dgam * N[2]};
-        S E[9];
-        expm3(A, E);
-        mm3(E, Fp_old, Fp_out);
-        write_Fp = true;
-      }
+      for (int i = 0; i < 6; ++i) { Nn[i] = N[i]; c.dN[i] = dgam * N[i]; }
     }
   }
   c.r[0][0] = -(c.r[1][0] + c.r[2][0] + c.r[3][0]);
@@ -345,10 +386,18 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   c.upc = S(0.25) * vJ;
   c.va = S(-0.125) * (vJ + vol * rJ);  // vol * (-1/8)(1 + 1/J^2) J
   c.tjv = c.taus * vJ;
-  S const rkappa = S(1.0) / mat.kappa;
-  c.ppc = S(1.0 / 16.0) * vol * rkappa;
-  c.rb = S(0.25) * vol * (c.pv * rkappa - S(0.5) * (J - rJ));
+  c.ppc = S(1.0 / 16.0) * vol * mat.rkappa;
+  c.rb = S(0.25) * vol * (c.pv * mat.rkappa - S(0.5) * (J - rJ));
   return ERR_NONE;
+}
+
+// Fp = exp(dgam N) Fp_old  (goal_J2.cpp:128-131).  Only called for elements on the plastic branch; on the
+// elastic branch the reference leaves Fp untouched (goal_J2.cpp:135-136).
+template <class S> GX_HD void plastic_update(S const dN[6], S const Fp_old[9], S Fp_new[9]) {
+  S const A[9] = {dN[0], dN[3], dN[4], dN[3], dN[1], dN[5], dN[4], dN[5], dN[2]};
+  S E[9];
+  expm3(A, E);
+  mm3(E, Fp_old, Fp_new);
 }
 
 // ---------------------------------------------------------------------------

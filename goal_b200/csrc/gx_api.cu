@@ -55,13 +55,18 @@ __global__ void record_to_field_kernel(double* field, double const* rec, int str
   int const k = (int)(i % ncomp);
   field[i] = rec[e * stride + off + k];
 }
-// States::update (src/goal_states.cpp:130-141): Fp_old <- Fp, eqps_old <- eqps
-__global__ void update_states_kernel(double* sin, double const* sout, int ne) {
-  int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (i >= (int64_t)ne * STATE_IN) return;
-  int64_t const e = i / STATE_IN;
-  int const k = (int)(i % STATE_IN);
-  sin[i] = sout[e * STATE_OUT + 9 + k];  // Fp[0..8], eqps
+// States::update (src/goal_states.cpp:130-141): Fp_old <- Fp, eqps_old <- eqps; refresh the cached Cp^{-1}
+__global__ void update_states_kernel(double* sin, double* fp_old, double const* sout, int ne, int copy) {
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double Fp[9], Cp[6];
+  for (int k = 0; k < 9; ++k) {
+    if (copy) fp_old[9 * (int64_t)e + k] = sout[(int64_t)STATE_OUT * e + 9 + k];
+    Fp[k] = fp_old[9 * (int64_t)e + k];
+  }
+  cp_inverse(Fp, Cp);
+  for (int k = 0; k < 6; ++k) sin[(int64_t)STATE_IN * e + k] = Cp[k];
+  if (copy) sin[(int64_t)STATE_IN * e + 6] = sout[(int64_t)STATE_OUT * e + 18];
 }
 
 // compute_error (src/goal_error.cpp:7-35): |sum_d u_err_d(xi_c) + p_err(xi_c)|; err4 = [Nn][4] (u0,u1,u2,p)
@@ -151,7 +156,7 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
   P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
-  P.state_in = ctx->d_state_in; P.state_out = ctx->d_state_out;
+  P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
   P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
@@ -165,8 +170,10 @@ template <int MODEL, bool TRANSPOSE, bool SAVE>
 static cudaError_t launch_row_owner(gx_ctx* ctx, KParams& P) {
   int const warps = (int)ctx->opt_row_warps;
   size_t const smem = row_owner_smem(ctx, warps);
-  // MINB = 2 caps the kernel at 128 registers/thread (16 warps/SM) at the price of some spills
-  auto kern = ctx->opt_row_minblocks == 2 ? row_owner_kernel<MODEL, TRANSPOSE, SAVE, 2> : row_owner_kernel<MODEL, TRANSPOSE, SAVE, 1>;
+  // 128-thread blocks; MINB blocks/SM bounds the registers: 2 -> 255, 3 -> 168 (12 warps/SM), 4 -> 128 (16 warps/SM)
+  auto kern = ctx->opt_row_minblocks == 4   ? row_owner_kernel<MODEL, TRANSPOSE, SAVE, 4>
+              : ctx->opt_row_minblocks == 3 ? row_owner_kernel<MODEL, TRANSPOSE, SAVE, 3>
+                                            : row_owner_kernel<MODEL, TRANSPOSE, SAVE, 2>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P);
@@ -261,8 +268,8 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
   if (ctx->model != GX_MODEL_J2) return false;  // only J2 registers eqps / Fp (goal_mechanics.cpp:90-93)
   if (n == "Fp") { L = {ctx->d_state_out, STATE_OUT, 9, 9}; return true; }
   if (n == "eqps") { L = {ctx->d_state_out, STATE_OUT, 18, 1}; return true; }
-  if (n == "Fp_old") { L = {ctx->d_state_in, STATE_IN, 0, 9}; return true; }
-  if (n == "eqps_old") { L = {ctx->d_state_in, STATE_IN, 9, 1}; return true; }
+  if (n == "Fp_old") { L = {ctx->d_fp_old, 9, 0, 9}; return true; }
+  if (n == "eqps_old") { L = {ctx->d_state_in, STATE_IN, 6, 1}; return true; }
   return false;
 }
 
@@ -270,7 +277,7 @@ static void free_device(gx_ctx* ctx) {
   if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj,
-                  ctx->d_state_in, ctx->d_state_out, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
+                  ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -308,12 +315,8 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
   ctx->coords.assign(d->coords, d->coords + 3 * (size_t)d->n_nodes);
   if (d->elem_set && d->n_elem_sets > 1) ctx->eset.assign(d->elem_set, d->elem_set + d->n_elems);
   for (int s = 0; s < ctx->nsets; ++s) {
-    double const E = d->materials[5 * s], nu = d->materials[5 * s + 1];
-    ctx->mats[s].kappa = E / (3.0 * (1.0 - 2.0 * nu));  // goal_neohookean.cpp:50, goal_J2.cpp:62
-    ctx->mats[s].mu = E / (2.0 * (1.0 + nu));           // goal_neohookean.cpp:51, goal_J2.cpp:63
-    ctx->mats[s].K = d->materials[5 * s + 2];
-    ctx->mats[s].Y = d->materials[5 * s + 3];
-    ctx->mats[s].c0 = d->materials[5 * s + 4];
+    double const* m5 = d->materials + 5 * s;  // kappa, mu: goal_neohookean.cpp:50-51, goal_J2.cpp:62-63
+    ctx->mats[s] = make_material(m5[0], m5[1], m5[2], m5[3], m5[4]);
   }
   auto fail = [&](int rc) { g_create_err = ctx->err; free_device(ctx); comm_destroy(ctx); delete ctx; return rc; };
   for (int e = 0; e < ctx->ne && !ctx->eset.empty(); ++e)
@@ -351,13 +354,17 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemcpy(ctx->d_adj, ctx->adj.data(), sizeof(int2) * ctx->adj.size(), cudaMemcpyHostToDevice));
     // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
     {
-      std::vector<double> sin((size_t)STATE_IN * ne, 0.0), sout((size_t)STATE_OUT * ne, 0.0);
+      std::vector<double> sin((size_t)STATE_IN * ne, 0.0), sout((size_t)STATE_OUT * ne, 0.0), fpo((size_t)9 * ne, 0.0);
       if (ctx->model == GX_MODEL_J2)
-        for (int e = 0; e < ne; ++e)
-          for (int k = 0; k < 9; k += 4) { sin[(size_t)STATE_IN * e + k] = 1.0; sout[(size_t)STATE_OUT * e + 9 + k] = 1.0; }
+        for (int e = 0; e < ne; ++e) {
+          for (int k = 0; k < 3; ++k) sin[(size_t)STATE_IN * e + k] = 1.0;  // Cp^{-1} of Fp_old = I
+          for (int k = 0; k < 9; k += 4) { fpo[(size_t)9 * e + k] = 1.0; sout[(size_t)STATE_OUT * e + 9 + k] = 1.0; }
+        }
       GX_CUDA(cudaMalloc(&ctx->d_state_in, sizeof(double) * sin.size()));
+      GX_CUDA(cudaMalloc(&ctx->d_fp_old, sizeof(double) * fpo.size()));
       GX_CUDA(cudaMalloc(&ctx->d_state_out, sizeof(double) * sout.size()));
       GX_CUDA(cudaMemcpy(ctx->d_state_in, sin.data(), sizeof(double) * sin.size(), cudaMemcpyHostToDevice));
+      GX_CUDA(cudaMemcpy(ctx->d_fp_old, fpo.data(), sizeof(double) * fpo.size(), cudaMemcpyHostToDevice));
       GX_CUDA(cudaMemcpy(ctx->d_state_out, sout.data(), sizeof(double) * sout.size(), cudaMemcpyHostToDevice));
     }
     // ---- linear objects (SolInfo ghost R / dRdu, src/goal_sol_info.cpp:6-22)
@@ -455,6 +462,10 @@ int gx_set_state(gx_ctx* ctx, const char* name, const double* in) {
   GX_CUDA(cudaMemcpyAsync(ctx->d_stage, in, sizeof(double) * (size_t)tot, cudaMemcpyHostToDevice, ctx->stream));
   field_to_record_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L.rec, L.stride, L.off, ctx->d_stage, ctx->ne, L.ncomp);
   GX_CUDA(cudaGetLastError());
+  if (L.rec == ctx->d_fp_old) {  // Fp_old changed: refresh the cached Cp^{-1}
+    update_states_kernel<<<(ctx->ne + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->ne, 0);
+    GX_CUDA(cudaGetLastError());
+  }
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
@@ -464,8 +475,7 @@ int gx_update_states(gx_ctx* ctx) {
   if (host_only(ctx)) return GX_ERR_CUDA;
   if (ctx->model != GX_MODEL_J2) return GX_OK;  // only J2 registers old states (goal_mechanics.cpp:90-93)
   GX_CUDA(cudaSetDevice(ctx->device));
-  int64_t const tot = (int64_t)ctx->ne * STATE_IN;
-  update_states_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_state_out, ctx->ne);
+  update_states_kernel<<<(ctx->ne + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->ne, 1);
   GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
@@ -605,12 +615,12 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
     return GX_OK;
   }
   if (k == "row_minblocks") {
-    if (value != 1 && value != 2) { ctx->err = "row_minblocks must be 1 or 2"; return GX_ERR_ARG; }
+    if (value < 2 || value > 4) { ctx->err = "row_minblocks must be 2, 3 or 4"; return GX_ERR_ARG; }
     ctx->opt_row_minblocks = value;
     return GX_OK;
   }
   if (k == "row_warps") {
-    if (value < 1 || value > 8) { ctx->err = "row_warps must be 1..8"; return GX_ERR_ARG; }
+    if (value < 1 || value > 4) { ctx->err = "row_warps must be 1..4"; return GX_ERR_ARG; }
     ctx->opt_row_warps = value;
     return GX_OK;
   }

@@ -96,9 +96,11 @@ struct gx_ctx {
   uint32_t* d_adj_off = nullptr;
   int2* d_adj = nullptr;
   // history state, one record per element (user order):
-  //   in : Fp_old[9], eqps_old                      (80 B)
-  //   out: sigma[9], Fp[9], eqps, pad               (160 B)
+  //   in    : Cp^{-1}[6] (of Fp_old, cached), eqps_old, pad   (64 B)  read by every incidence of the element
+  //   fp_old: Fp_old[9]                                       (72 B)  read only when a plastic element saves Fp
+  //   out   : sigma[9], Fp[9], eqps, pad                      (160 B)
   double* d_state_in = nullptr;
+  double* d_fp_old = nullptr;
   double* d_state_out = nullptr;
   double* d_R = nullptr;
   double* d_values = nullptr;
@@ -134,7 +136,7 @@ struct gx_ctx {
   int64_t opt_block = 128;
   int64_t opt_kernel = 0;  // 0 = row-owner Jacobian kernel, 1 = coloured element kernel
   int64_t opt_row_warps = 4;
-  int64_t opt_row_minblocks = 1;
+  int64_t opt_row_minblocks = 2;
   std::string err;
 };
 
@@ -149,7 +151,7 @@ struct HostPack {
   std::vector<uint4> bpos;   // user element order
   std::vector<uint8_t> eset;
 };
-constexpr int STATE_IN = 10;   // doubles per element
+constexpr int STATE_IN = 8;    // doubles per element
 constexpr int STATE_OUT = 20;
 void pack_host(gx_ctx const* c, HostPack& h);
 // gx_comm.cu

@@ -11,8 +11,9 @@
 //   bpos      uint4[Ne]    element -> nonzero scatter map, 16 x uint8 block positions
 //   adj       int2[4 Ne]   node -> (element, local node) incidences + the 4 block positions that
 //                          incidence writes, grouped by node (adj_off[Nn+1]); the row-owner work list
-//   state_in  double[Ne][10]  Fp_old[9], eqps_old          80 B record  (5 LDG.128)
-//   state_out double[Ne][20]  sigma[9], Fp[9], eqps, pad   160 B record (10 STG.128)
+//   state_in  double[Ne][8]   Cp^{-1}[6] of Fp_old (cached), eqps_old, pad   64 B record (4 LDG.128)
+//   fp_old    double[Ne][9]   read only by the one incidence that saves a plastic element's Fp
+//   state_out double[Ne][20]  sigma[9], Fp[9], eqps, pad                     160 B record
 //   R         double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
 //
 // Two schedules, both free of atomics on the data path and bit-reproducible:
@@ -45,6 +46,7 @@ struct KParams {
   uint32_t const* adj_off;
   int2 const* adj;
   double const* state_in;
+  double const* fp_old;
   double* state_out;
   double* R;
   double* values;
@@ -108,30 +110,34 @@ GX_HD int load_and_update(KParams const& P, int e, bool write_state, int nd[4], 
 #pragma unroll
   for (int n = 0; n < 4; ++n) load_node(P.nodes, nd[n], x[n], u[n], p[n], blk0[n], nblk[n]);
   mat = &P.mat[P.eset ? P.eset[e] : 0];
-  double Fp_old[9], eqps_old = 0.0;
+  double Cp[6], eqps_old = 0.0;
   if (MODEL == MODEL_J2) {
     double2 const* q = reinterpret_cast<double2 const*>(P.state_in + (int64_t)STATE_IN * e);
-    double2 const a0 = ldg(q), a1 = ldg(q + 1), a2 = ldg(q + 2), a3 = ldg(q + 3), a4 = ldg(q + 4);
-    Fp_old[0] = a0.x; Fp_old[1] = a0.y; Fp_old[2] = a1.x; Fp_old[3] = a1.y; Fp_old[4] = a2.x;
-    Fp_old[5] = a2.y; Fp_old[6] = a3.x; Fp_old[7] = a3.y; Fp_old[8] = a4.x; eqps_old = a4.y;
+    double2 const a0 = ldg(q), a1 = ldg(q + 1), a2 = ldg(q + 2), a3 = ldg(q + 3);
+    Cp[0] = a0.x; Cp[1] = a0.y; Cp[2] = a1.x; Cp[3] = a1.y; Cp[4] = a2.x; Cp[5] = a2.y; eqps_old = a3.x;
   }
-  double sig[9], eqps_new = 0.0, Fp_new[9];
-  bool write_Fp = false;
-  int const rc = element_core<MODEL>(x, u, p, *mat, Fp_old, eqps_old, SAVE && write_state, sig, eqps_new, Fp_new, write_Fp, c);
+  double sig[9], eqps_new = 0.0;
+  int const rc = element_core<MODEL>(x, u, p, *mat, Cp, eqps_old, SAVE && write_state, sig, eqps_new, c);
   if (rc != ERR_NONE) return rc;
   if (SAVE && write_state) {
     double* so = P.state_out + (int64_t)STATE_OUT * e;
 #pragma unroll
     for (int k = 0; k < 9; ++k) so[k] = sig[k];
-    if (MODEL == MODEL_J2) {
-      so[18] = eqps_new;
-      if (write_Fp) {  // elastic branch: Fp deliberately untouched (goal_J2.cpp:135-136)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) so[9 + k] = Fp_new[k];
-      }
-    }
+    if (MODEL == MODEL_J2) so[18] = eqps_new;
   }
   return ERR_NONE;
+}
+
+// Fp of a plastic element, done after the Jacobian work; elastic elements leave Fp untouched (goal_J2.cpp:135-136)
+GX_HD void save_plastic_Fp(KParams const& P, int e, double const dN[6]) {
+  double Fpo[9], Fpn[9];
+  double const* src = P.fp_old + 9 * (int64_t)e;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) Fpo[k] = ldg(src + k);
+  plastic_update(dN, Fpo, Fpn);
+  double* so = P.state_out + (int64_t)STATE_OUT * e + 9;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) so[k] = Fpn[k];
 }
 
 // ---------------------------------------------------------------------------
@@ -195,6 +201,7 @@ GX_HD int assemble_element(KParams const& P, int slot) {
       }
     }
   }
+  if (SAVE && MODEL == MODEL_J2 && c.plastic) save_plastic_Fp(P, e, c.dN);
   return c.plastic;
 }
 
@@ -216,25 +223,27 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 //   PRIMAL : K[(n,.),(m,.)]           -> block (a, a_m) of node a's rows
 //   ADJOINT: K[(m,.),(n,.)]^T         -> block (a, a_m) of the transposed operator
 // staged in shared memory (stg[16][33]).  The blocks are then folded into the node's row accumulator
-// by a fixed schedule: half-warp h = 0/1 walks the staged blocks of lanes 16h .. 16h+15 in ascending
-// lane order (= ascending element id), lane t of the half adding entry t of each block into its own
+// by a fixed schedule: half-warp h = 0/1 walks the staged blocks of the lower / upper half of the active
+// lanes in ascending lane order (= ascending element id), lane t of the half adding entry t of each block into its own
 // accumulator copy acc[h][16 j + t]; the two copies are summed at the end.  Every CRS entry is therefore
 // produced by one thread in a fixed order: deterministic, atomics-free, written exactly once.
 // Nodes with more than 32 incident elements take several rounds.
-// Shared memory per warp: stg 16*33*8 B + acc 2*128*max_nblk B.
+// Shared memory per warp: stg 16*33*8 B + wr 24*32*8 B + acc 2*128*max_nblk B.
 // ---------------------------------------------------------------------------
 constexpr int STG_LD = 33;
+constexpr int WR_LD = 32;  // per-lane spatial vectors w_n, r_n (n = 0..3): wr[24][32]
 GX_HD size_t row_owner_smem_per_warp(int max_nblk) {
-  return (size_t)(16 * STG_LD + 2 * 16 * max_nblk) * sizeof(double);
+  return (size_t)(16 * STG_LD + 24 * WR_LD + 2 * 16 * max_nblk) * sizeof(double);
 }
 
 template <int MODEL, bool TRANSPOSE, bool SAVE, int MINB>
-__global__ void __launch_bounds__(256, MINB) row_owner_kernel(const __grid_constant__ KParams P) {
+__global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_constant__ KParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int const half = lane >> 4, t16 = lane & 15;
   double* stg = reinterpret_cast<double*>(smem_raw + row_owner_smem_per_warp(P.max_nblk) * wib);
-  double* acc = stg + 16 * STG_LD;  // [2][16*max_nblk], block-major: acc[h][16 j + 4 i + k]
+  double* wr = stg + 16 * STG_LD + lane;  // this lane's column of wr[24][32]: w_n[k] at 3n+k, r_n[k] at 12+3n+k
+  double* acc = stg + 16 * STG_LD + 24 * WR_LD;  // [2][16*max_nblk], block-major: acc[h][16 j + 4 i + k]
   int const accld = 16 * P.max_nblk;
 
   int const a = blockIdx.x * (blockDim.x >> 5) + wib;
@@ -254,13 +263,13 @@ __global__ void __launch_bounds__(256, MINB) row_owner_kernel(const __grid_const
   for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
     int const nact = min(32, (int)(o1 - r0));  // active lanes of this round: 0 .. nact-1
     bool const active = lane < nact;
-    int n = 0;
+    int n = 0, e = 0;
     uint32_t jpack = 0;
     Core<double> c;
     bool ok = false;
     if (active) {
       int2 const ad = __ldg(P.adj + r0 + lane);
-      int const e = ad.x >> 2;
+      e = ad.x >> 2;
       n = ad.x & 3; jpack = (uint32_t)ad.y;
       int nd[4], b0[4], nb[4];
       Material const* matp;
@@ -268,13 +277,21 @@ __global__ void __launch_bounds__(256, MINB) row_owner_kernel(const __grid_const
       if (rc != ERR_NONE) report_error(P.err, rc, e);
       ok = rc == ERR_NONE;
       if (ok && n == 0) nplastic += c.plastic;
+      // park the 24 spatial vectors in shared memory: frees 48 registers for the phases and lets the
+      // run-time node indices (n, m) address them directly
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wr[(3 * q + k) * WR_LD] = c.w[q][k];
+          wr[(12 + 3 * q + k) * WR_LD] = c.r[q][k];
+        }
     }
-    // this lane's own node: select w_n, r_n by predication (never index the register-resident Core dynamically)
     double wn[3], rn3[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-      wn[k] = n == 0 ? c.w[0][k] : n == 1 ? c.w[1][k] : n == 2 ? c.w[2][k] : c.w[3][k];
-      rn3[k] = n == 0 ? c.r[0][k] : n == 1 ? c.r[1][k] : n == 2 ? c.r[2][k] : c.r[3][k];
+      wn[k] = wr[(3 * n + k) * WR_LD];
+      rn3[k] = wr[(12 + 3 * n + k) * WR_LD];
     }
     RowNode<double> rown;  // PRIMAL: this lane's row node
     ColNode<double> coln;  // ADJOINT: this lane's column node
@@ -285,20 +302,27 @@ __global__ void __launch_bounds__(256, MINB) row_owner_kernel(const __grid_const
       if (!TRANSPOSE) row_node(c, wn, rown);
       else column_node(c, wn, rn3, coln);
     }
-#pragma unroll
+#pragma unroll 1
     for (int m = 0; m < 4; ++m) {
       uint32_t jm = 0;
       if (ok) {
+        // column node m of this phase
+        double wm[3], rm[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wm[k] = wr[(3 * m + k) * WR_LD];
+          rm[k] = wr[(12 + 3 * m + k) * WR_LD];
+        }
         double blk[16];
         if (!TRANSPOSE) {
           ColNode<double> cnm;
-          column_node(c, c.w[m], c.r[m], cnm);
+          column_node(c, wm, rm, cnm);
           jacobian_block(c, rown, cnm, blk);
 #pragma unroll
           for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = blk[t];
         } else {
           RowNode<double> rnm;
-          row_node(c, c.w[m], rnm);
+          row_node(c, wm, rnm);
           jacobian_block(c, rnm, coln, blk);
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -311,18 +335,23 @@ __global__ void __launch_bounds__(256, MINB) row_owner_kernel(const __grid_const
         for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = 0.0;  // failed element: contributes nothing
       }
       __syncwarp();
-      // fold: half-warp h walks lanes 16h .. 16h+15 (those below nact), uniform trip count
+      // fold: the staged blocks of lanes [0, split) go to half-warp 0, [split, nact) to half-warp 1,
+      // each in ascending lane order; lane t of a half adds entry t of every block it walks
       {
-        int const trips = min(16, nact);
+        int const split = (nact + 1) >> 1;
+        int const lbase = half ? split : 0;
+        int const lend = half ? nact : split;
         double* my = acc + half * accld + t16;
-        for (int it = 0; it < trips; ++it) {
-          int const l = 16 * half + it;
-          uint32_t const j = __shfl_sync(0xffffffffu, jm, l);
-          if (l < nact) my[16 * j] += stg[t16 * STG_LD + l];
+#pragma unroll 4
+        for (int it = 0; it < split; ++it) {
+          int const l = lbase + it;
+          uint32_t const j = __shfl_sync(0xffffffffu, jm, l & 31);
+          if (l < lend) my[16 * j] += stg[t16 * STG_LD + l];
         }
       }
       __syncwarp();
     }
+    if (SAVE && MODEL == MODEL_J2 && ok && n == 0 && c.plastic) save_plastic_Fp(P, e, c.dN);
   }
   // ---- R rows of node a: fixed butterfly over the lanes
 #pragma unroll

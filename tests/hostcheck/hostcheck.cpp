@@ -8,17 +8,17 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
                           const double* Fp_old, double eqps_old, int save, double* K /*16x16 row-major, dof=n*4+eq*/,
                           double* R /*16*/, double* sigma /*9*/, double* eqps, double* Fp /*9*/, int* wrote_Fp,
                           int* plastic) {
-  gx::Material m;
-  double E = mat5[0], nu = mat5[1];
-  m.kappa = E / (3.0 * (1.0 - 2.0 * nu)); m.mu = E / (2.0 * (1.0 + nu));
-  m.K = mat5[2]; m.Y = mat5[3]; m.c0 = mat5[4];
+  gx::Material m = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
   double X[4][3], U[4][3];
   for (int n = 0; n < 4; ++n) for (int j = 0; j < 3; ++j) { X[n][j] = x[3 * n + j]; U[n][j] = u[3 * n + j]; }
   gx::Core<double> c;
   bool wf = false;
-  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Fp_old, eqps_old, save != 0, sigma, *eqps, Fp, wf, c)
-                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Fp_old, eqps_old, save != 0, sigma, *eqps, Fp, wf, c);
+  double Cp[6];
+  gx::cp_inverse(Fp_old, Cp);
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Cp, eqps_old, save != 0, sigma, *eqps, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Cp, eqps_old, save != 0, sigma, *eqps, c);
   if (rc) return rc;
+  if (save && model == 1 && c.plastic) { gx::plastic_update(c.dN, Fp_old, Fp); wf = true; }
   *wrote_Fp = wf; *plastic = c.plastic;
   double ru[12], rp[4];
   gx::element_residual(c, ru, rp);
@@ -40,16 +40,15 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
 extern "C" int hc_error_residual(int model, const double* x, const double* u, const double* p, const double* mat5,
                                  const double* Fp_old, double eqps_old, const double* zu, const double* zp,
                                  const double* zpc, double* R) {
-  gx::Material m;
-  double E = mat5[0], nu = mat5[1];
-  m.kappa = E / (3.0 * (1.0 - 2.0 * nu)); m.mu = E / (2.0 * (1.0 + nu));
-  m.K = mat5[2]; m.Y = mat5[3]; m.c0 = mat5[4];
+  gx::Material m = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
   double X[4][3], U[4][3], Z[4][3];
   for (int n = 0; n < 4; ++n) for (int j = 0; j < 3; ++j) { X[n][j] = x[3 * n + j]; U[n][j] = u[3 * n + j]; Z[n][j] = zu[3 * n + j]; }
   gx::Core<double> c;
-  bool wf; double sg[9], eq, fp[9];
-  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Fp_old, eqps_old, false, sg, eq, fp, wf, c)
-                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Fp_old, eqps_old, false, sg, eq, fp, wf, c);
+  double sg[9], eq;
+  double Cp[6];
+  gx::cp_inverse(Fp_old, Cp);
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Cp, eqps_old, false, sg, eq, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Cp, eqps_old, false, sg, eq, c);
   if (rc) return rc;
   double ru[12], rp[4];
   gx::element_error_residual(c, Z, zp, zpc, ru, rp);
@@ -85,9 +84,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   c.nn = nn; c.ne = ne; c.model = model; c.nsets = 1;
   c.conn.assign(conn, conn + 4 * (size_t)ne);
   c.coords.assign(coords, coords + 3 * (size_t)nn);
-  double E = mat5[0], nu = mat5[1];
-  c.mats[0].kappa = E / (3.0 * (1.0 - 2.0 * nu)); c.mats[0].mu = E / (2.0 * (1.0 + nu));
-  c.mats[0].K = mat5[2]; c.mats[0].Y = mat5[3]; c.mats[0].c0 = mat5[4];
+  c.mats[0] = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
   int rc = gx::build_graph_and_schedule(&c);
   if (rc) return rc;
   *nnz_out = c.nnz; *ncolors = c.ncolors;
@@ -105,12 +102,13 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   }
   std::vector<gx::ZRec> z(nn);
   if (z5) for (int n = 0; n < nn; ++n) { for (int j = 0; j < 3; ++j) z[n].zu[j] = z5[5 * (size_t)n + j]; z[n].zp = z5[5 * (size_t)n + 3]; z[n].zpc = z5[5 * (size_t)n + 4]; }
-  std::vector<double> sin((size_t)gx::STATE_IN * ne, 0.0), sout((size_t)gx::STATE_OUT * ne, 0.0);
+  std::vector<double> sin((size_t)gx::STATE_IN * ne, 0.0), sout((size_t)gx::STATE_OUT * ne, 0.0), fpo((size_t)9 * ne, 0.0);
   for (int e = 0; e < ne; ++e) {
     for (int k = 0; k < 9; ++k) sout[(size_t)gx::STATE_OUT * e + k] = sigma[9 * (size_t)e + k];
     if (model == 1) {
-      sout[(size_t)gx::STATE_OUT * e + 18] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 9] = eqps_old[e];
-      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + 9 + k] = Fp[9 * (size_t)e + k]; sin[(size_t)gx::STATE_IN * e + k] = Fp_old[9 * (size_t)e + k]; }
+      sout[(size_t)gx::STATE_OUT * e + 18] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 6] = eqps_old[e];
+      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + 9 + k] = Fp[9 * (size_t)e + k]; fpo[(size_t)9 * e + k] = Fp_old[9 * (size_t)e + k]; }
+      gx::cp_inverse(&fpo[(size_t)9 * e], &sin[(size_t)gx::STATE_IN * e]);
     }
   }
   int err[2] = {0, 0};
@@ -118,7 +116,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   gx::KParams P;
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
   P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data();
-  P.state_in = sin.data(); P.state_out = sout.data();
+  P.state_in = sin.data(); P.fp_old = fpo.data(); P.state_out = sout.data();
   P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
   int64_t npl = 0;
