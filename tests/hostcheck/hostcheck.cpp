@@ -138,3 +138,73 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   }
   return err[0] ? 100 + err[0] : 0;
 }
+
+// ---------------------------------------------------------------------------
+// Operation counts of the kernel's own formulation ("counted, not guessed"): the element
+// math instantiated with a counting scalar.  add/sub, mul, div and special (sqrt, cbrt, fabs, compare)
+// are tallied separately; a fused multiply-add executes as one instruction but is counted here as
+// 1 mul + 1 add = 2 flops, the usual convention.
+// ---------------------------------------------------------------------------
+namespace {
+struct Cnt {
+  static long add, mul, dv, sp;
+  double v;
+  Cnt() : v(0) {}
+  Cnt(double x) : v(x) {}
+  explicit operator double() const { return v; }
+};
+long Cnt::add = 0, Cnt::mul = 0, Cnt::dv = 0, Cnt::sp = 0;
+inline Cnt operator+(Cnt a, Cnt b) { ++Cnt::add; return Cnt(a.v + b.v); }
+inline Cnt operator-(Cnt a, Cnt b) { ++Cnt::add; return Cnt(a.v - b.v); }
+inline Cnt operator-(Cnt a) { return Cnt(-a.v); }
+inline Cnt operator*(Cnt a, Cnt b) { ++Cnt::mul; return Cnt(a.v * b.v); }
+inline Cnt operator/(Cnt a, Cnt b) { ++Cnt::dv; return Cnt(a.v / b.v); }
+inline Cnt& operator+=(Cnt& a, Cnt b) { a = a + b; return a; }
+inline Cnt& operator-=(Cnt& a, Cnt b) { a = a - b; return a; }
+inline Cnt& operator*=(Cnt& a, Cnt b) { a = a * b; return a; }
+inline bool operator>(Cnt a, Cnt b) { ++Cnt::sp; return a.v > b.v; }
+inline bool operator<=(Cnt a, Cnt b) { ++Cnt::sp; return a.v <= b.v; }
+inline Cnt sqrt(Cnt a) { ++Cnt::sp; return Cnt(std::sqrt(a.v)); }
+inline Cnt cbrt(Cnt a) { ++Cnt::sp; return Cnt(std::cbrt(a.v)); }
+inline Cnt fabs(Cnt a) { ++Cnt::sp; return Cnt(std::fabs(a.v)); }
+// Material fields are doubles: mixed double*Cnt goes through Cnt(double)
+}  // namespace
+
+// out[0..3] = add, mul, div, special for: what = 0 element core (+ state save), 1 one incidence of the
+// row-owner kernel (core + residual row + 4 blocks), 2 one whole element matrix (core + residual + 16 blocks)
+extern "C" int hc_count_ops(int model, int what, int save, const double* x, const double* u, const double* p,
+                            const double* mat5, const double* Fp_old, double eqps_old, long* out, int* plastic) {
+  gx::Material m = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
+  Cnt X[4][3], U[4][3], Pn[4], Cp[6], sig[9], eq, FpO[9], FpN[9];
+  double Cpd[6];
+  gx::cp_inverse(Fp_old, Cpd);
+  for (int n = 0; n < 4; ++n) { for (int j = 0; j < 3; ++j) { X[n][j] = x[3 * n + j]; U[n][j] = u[3 * n + j]; } Pn[n] = p[n]; }
+  for (int k = 0; k < 6; ++k) Cp[k] = Cpd[k];
+  for (int k = 0; k < 9; ++k) FpO[k] = Fp_old[k];
+  Cnt::add = Cnt::mul = Cnt::dv = Cnt::sp = 0;
+  gx::Core<Cnt> c;
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, Pn, m, Cp, Cnt(eqps_old), save != 0, sig, eq, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, Pn, m, Cp, Cnt(eqps_old), save != 0, sig, eq, c);
+  if (rc) return rc;
+  *plastic = c.plastic;
+  if (save && model == 1 && c.plastic) gx::plastic_update(c.dN, FpO, FpN);
+  if (what == 1) {
+    Cnt r4[4], blk[16];
+    gx::element_residual_row(c, c.w[1], r4);
+    gx::RowNode<Cnt> rn;
+    gx::row_node(c, c.w[1], rn);
+    for (int mm = 0; mm < 4; ++mm) { gx::ColNode<Cnt> cn; gx::column_node(c, c.w[mm], c.r[mm], cn); gx::jacobian_block(c, rn, cn, blk); }
+  } else if (what == 2) {
+    Cnt ru[12], rp[4], blk[16];
+    gx::element_residual(c, ru, rp);
+    gx::RowNode<Cnt> rn[4];
+    for (int n = 0; n < 4; ++n) gx::row_node(c, c.w[n], rn[n]);
+    for (int mm = 0; mm < 4; ++mm) {
+      gx::ColNode<Cnt> cn;
+      gx::column_node(c, c.w[mm], c.r[mm], cn);
+      for (int n = 0; n < 4; ++n) gx::jacobian_block(c, rn[n], cn, blk);
+    }
+  }
+  out[0] = Cnt::add; out[1] = Cnt::mul; out[2] = Cnt::dv; out[3] = Cnt::sp;
+  return 0;
+}
