@@ -155,7 +155,7 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
-  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
+  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj; P.fold_ord = ctx->d_fold_ord; P.nblk_g = ctx->nnz_x != ctx->nnz ? ctx->d_nblk_g : nullptr;
   P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
   P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
@@ -177,6 +177,47 @@ static cudaError_t launch_row_owner(gx_ctx* ctx, KParams& P) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
+// two-kernel row-owner pass: element records, then node rows
+template <int MODEL>
+static cudaError_t launch_two_stage(gx_ctx* ctx, KParams& P, int pass, bool save) {
+  int const ne = ctx->ne;
+  if (save) elem_record_kernel<MODEL, true><<<(ne + 63) / 64, 64, 0, ctx->stream>>>(P, ctx->d_elemrec, ne);
+  else elem_record_kernel<MODEL, false><<<(ne + 63) / 64, 64, 0, ctx->stream>>>(P, ctx->d_elemrec, ne);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  int const warps = (int)ctx->opt_row_warps;
+  bool const tr = pass == PASS_JACOBIAN_T;
+  int const mb = (int)ctx->opt_fold_minblocks;
+  bool const sorted = ctx->opt_fold_sorted != 0;
+  if (sorted) {  // nodes with <= 32 incidences
+    size_t const smem = row_fold_smem_per_warp(ctx->max_nblk) * warps;
+    auto kern = tr ? (mb == 4 ? row_fold_sorted_kernel<true, 4> : mb == 3 ? row_fold_sorted_kernel<true, 3> : row_fold_sorted_kernel<true, 2>)
+                   : (mb == 4 ? row_fold_sorted_kernel<false, 4> : mb == 3 ? row_fold_sorted_kernel<false, 3> : row_fold_sorted_kernel<false, 2>);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P, ctx->d_elemrec);
+    ctx->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess || ctx->max_deg <= 32) return e;
+  }
+  // generic fold: every node (sorted == 0) or only the nodes with more than 32 incidences
+  P.e0 = sorted ? 33 : 0;  // minimum number of incidences this launch handles
+  size_t const smem = row_owner_smem(ctx, warps);
+  auto kern = tr ? (mb == 4 ? row_fold_kernel<true, 4> : mb == 3 ? row_fold_kernel<true, 3> : row_fold_kernel<true, 2>)
+                 : (mb == 4 ? row_fold_kernel<false, 4> : mb == 3 ? row_fold_kernel<false, 3> : row_fold_kernel<false, 2>);
+  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  // persistent warps: as many blocks as fit on the device at once (a multiple of the SM count)
+  int per_sm = 1;
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+  if (e != cudaSuccess) return e;
+  int const blocks = std::max(1, std::min((ctx->nn + warps - 1) / warps, ctx->num_sms * std::max(per_sm, 1) * (int)ctx->opt_fold_waves));
+  kern<<<blocks, warps * 32, smem, ctx->stream>>>(P, ctx->d_elemrec);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -206,8 +247,11 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaMemcpyAsync(ctx->d_err, zero2, sizeof zero2, cudaMemcpyHostToDevice, ctx->stream));
   GX_CUDA(cudaMemsetAsync(ctx->d_plastic, 0, sizeof(unsigned long long), ctx->stream));
   GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  bool const row_owner = with_values && ctx->opt_kernel == 0 &&
+  bool const row_owner = with_values && ctx->opt_kernel != 1 &&
                          row_owner_smem(ctx, (int)ctx->opt_row_warps) <= 200 * 1024;
+  bool const two_stage = row_owner && ctx->opt_kernel == 0;
+  if (two_stage && !ctx->d_elemrec)
+    GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
   if (!row_owner) {
     // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The row-owner schedule writes every
     // entry of R and of the CRS values exactly once, so it needs no zeroing pass.
@@ -218,7 +262,10 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   KParams P;
   fill_params(ctx, P);
   cudaError_t le;
-  if (row_owner)
+  if (two_stage)
+    le = ctx->model == GX_MODEL_J2 ? launch_two_stage<MODEL_J2>(ctx, P, pass, save)
+                                   : launch_two_stage<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
+  else if (row_owner)
     le = ctx->model == GX_MODEL_J2 ? launch_row_owner_model<MODEL_J2>(ctx, P, pass, save)
                                    : launch_row_owner_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   else
@@ -276,8 +323,8 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
 static void free_device(gx_ctx* ctx) {
   if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj,
-                  ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
+  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord,
+                  ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -329,6 +376,7 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
   auto body = [&]() -> int {
     GX_CUDA(cudaSetDevice(ctx->device));
     GX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    GX_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
     for (auto& e : ctx->ev) GX_CUDA(cudaEventCreate(&e));
     int const nn = ctx->nn, ne = ctx->ne;
     // ---- nodes and elements (device element order = colour-sorted)
@@ -350,6 +398,8 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj_off, sizeof(uint32_t) * (size_t)(nn + 1)));
     GX_CUDA(cudaMemcpy(ctx->d_adj_off, ctx->adj_off.data(), sizeof(uint32_t) * (size_t)(nn + 1), cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_fold_ord, sizeof(uint32_t) * std::max<size_t>(ctx->fold_ord.size(), 1)));
+    GX_CUDA(cudaMemcpy(ctx->d_fold_ord, ctx->fold_ord.data(), sizeof(uint32_t) * ctx->fold_ord.size(), cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj, sizeof(int2) * ctx->adj.size()));
     GX_CUDA(cudaMemcpy(ctx->d_adj, ctx->adj.data(), sizeof(int2) * ctx->adj.size(), cudaMemcpyHostToDevice));
     // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
@@ -609,9 +659,23 @@ int gx_last_timing(gx_ctx* ctx, double t[4]) {
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return GX_ERR_ARG;
   std::string k(key);
-  if (k == "kernel") {  // 0 = row-owner Jacobian kernel (default), 1 = coloured element kernel
-    if (value != 0 && value != 1) { ctx->err = "kernel must be 0 or 1"; return GX_ERR_ARG; }
+  if (k == "kernel") {  // Jacobian pass: 0 = element records + row fold (default), 1 = coloured elements, 2 = fused row-owner
+    if (value < 0 || value > 2) { ctx->err = "kernel must be 0, 1 or 2"; return GX_ERR_ARG; }
     ctx->opt_kernel = value;
+    return GX_OK;
+  }
+  if (k == "fold_waves") {
+    if (value < 1 || value > 64) { ctx->err = "fold_waves must be 1..64"; return GX_ERR_ARG; }
+    ctx->opt_fold_waves = value;
+    return GX_OK;
+  }
+  if (k == "fold_sorted") {
+    ctx->opt_fold_sorted = value != 0;
+    return GX_OK;
+  }
+  if (k == "fold_minblocks") {
+    if (value < 2 || value > 4) { ctx->err = "fold_minblocks must be 2, 3 or 4"; return GX_ERR_ARG; }
+    ctx->opt_fold_minblocks = value;
     return GX_OK;
   }
   if (k == "row_minblocks") {

@@ -80,6 +80,10 @@ struct gx_ctx {
   std::vector<uint32_t> adj_off;  // [nn+1]
   std::vector<int2> adj;          // [4*ne]  x = e*4+n, y = block positions of (a, a_m), m = 0..3, one byte each
   int max_nblk = 0, max_deg = 0;
+  // sorted fold schedule of the row fold kernel: for node a, entries [4*adj_off[a], 4*adj_off[a+1]) list the
+  // 4*deg staged blocks of its incidences sorted by target block; entry = smem offset (m*16*33 + lane) |
+  // target block << 12 | run-end flag << 31.  Only used for nodes with at most 32 incidences.
+  std::vector<uint32_t> fold_ord;
   // ---- schedule
   int ncolors = 0;
   std::vector<int32_t> color_off;  // [ncolors+1] in device element order
@@ -95,6 +99,7 @@ struct gx_ctx {
   int32_t* d_perm = nullptr;    // colour schedule: slot -> user element
   uint32_t* d_adj_off = nullptr;
   int2* d_adj = nullptr;
+  uint32_t* d_fold_ord = nullptr;
   // history state, one record per element (user order):
   //   in    : Cp^{-1}[6] (of Fp_old, cached), eqps_old, pad   (64 B)  read by every incidence of the element
   //   fp_old: Fp_old[9]                                       (72 B)  read only when a plastic element saves Fp
@@ -102,6 +107,7 @@ struct gx_ctx {
   double* d_state_in = nullptr;
   double* d_fp_old = nullptr;
   double* d_state_out = nullptr;
+  double* d_elemrec = nullptr;  // [ne][ELEM_REC] tangent records of the two-kernel Jacobian pass (lazy)
   double* d_R = nullptr;
   double* d_values = nullptr;
   double* d_stage = nullptr;  // staging for host<->device field copies, >= max(4*nn, 10*ne) doubles
@@ -134,9 +140,13 @@ struct gx_ctx {
   bool have_result = false;
   bool have_values = false;
   int64_t opt_block = 128;
-  int64_t opt_kernel = 0;  // 0 = row-owner Jacobian kernel, 1 = coloured element kernel
+  int64_t opt_kernel = 0;  // Jacobian pass: 0 = element records + row fold, 1 = coloured elements, 2 = fused row-owner
   int64_t opt_row_warps = 4;
   int64_t opt_row_minblocks = 2;
+  int64_t opt_fold_minblocks = 3;
+  int64_t opt_fold_sorted = 0;
+  int64_t opt_fold_waves = 1;
+  int num_sms = 148;
   std::string err;
 };
 

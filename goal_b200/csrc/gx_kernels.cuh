@@ -17,7 +17,7 @@
 //   R         double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
 //
 // Two schedules, both free of atomics on the data path and bit-reproducible:
-//  (1) row-owner (Jacobian pass, default): one warp per node a, one lane per incident element
+//  (1) row-owner (Jacobian pass; default in its two-kernel form, see (1b) below): one warp per node a, one lane per incident element
 //      (a, e).  Each lane evaluates its element and the four 4x4 blocks of node a's rows, the warp
 //      sums them per target block through shared memory in a fixed order and writes node a's four
 //      CRS rows exactly once, fully coalesced.  No zeroing pass, no read-modify-write traffic.
@@ -45,6 +45,8 @@ struct KParams {
   int32_t const* elems; // colour schedule: slot -> element
   uint32_t const* adj_off;
   int2 const* adj;
+  uint32_t const* fold_ord;
+  int32_t const* nblk_g;  // partitioned contexts: local (ghost) block count per node; blocks beyond it are phantom
   double const* state_in;
   double const* fp_old;
   double* state_out;
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 constexpr int STG_LD = 33;
 constexpr int WR_LD = 32;  // per-lane spatial vectors w_n, r_n (n = 0..3): wr[24][32]
 GX_HD size_t row_owner_smem_per_warp(int max_nblk) {
-  return (size_t)(16 * STG_LD + 24 * WR_LD + 2 * 16 * max_nblk) * sizeof(double);
+  return (size_t)(16 * STG_LD + 24 * WR_LD + 4 * 16 * max_nblk) * sizeof(double);
 }
 
 template <int MODEL, bool TRANSPOSE, bool SAVE, int MINB>
@@ -380,6 +382,376 @@ __global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_const
     unsigned const tot = __reduce_add_sync(0xffffffffu, (unsigned)nplastic);
     if (lane == 0 && tot) atomicAdd(P.plastic, (unsigned long long)tot);
   }
+}
+
+// ---------------------------------------------------------------------------
+// Schedule (1b), the default Jacobian pass: the row-owner schedule split in two kernels so that the
+// element core is evaluated once per element instead of once per incidence.
+//   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the
+//            56-double "tangent record" of the element (everything the 4x4 blocks are built from):
+//              w_n[4][3] r_n[4][3] | Tv[6] Gm[6] s[6] | q[3] gwv A1v Jpv upc va tjv ppc rb | pad[3]
+//   stage B  row_fold_kernel    : one warp per node, one lane per incidence.  Each lane reads its
+//            element's record (448 B, contiguous), builds the four blocks of the node's rows, and the
+//            warp folds and writes the node's CRS rows once, exactly like row_owner_kernel.
+// Costs 448 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
+// element core (about 60 % of all instructions of the fused kernel).
+// ---------------------------------------------------------------------------
+constexpr int ELEM_REC = 56;  // doubles
+
+template <int MODEL, bool SAVE>
+__global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
+  // records leave through shared memory so that a warp writes its 32 records (14 KB, contiguous) with
+  // fully coalesced 128-bit stores instead of 28 stride-448 B stores per thread
+  __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 57 doubles (odd): conflict-free column writes
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* mine = &srec[wib][lane * (ELEM_REC + 1)];
+  int plastic = 0;
+  if (e < ne) {
+    int nd[4], b0[4], nb[4];
+    Material const* matp;
+    Core<double> c;
+    int const rc = load_and_update<MODEL, SAVE>(P, e, true, nd, b0, nb, matp, c);
+    if (rc != ERR_NONE) {
+      report_error(P.err, rc, e);
+#pragma unroll
+      for (int k = 0; k < ELEM_REC; ++k) mine[k] = 0.0;
+    } else {
+      plastic = c.plastic;
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { mine[3 * q + k] = c.w[q][k]; mine[12 + 3 * q + k] = c.r[q][k]; }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) { mine[24 + k] = c.Tv[k]; mine[30 + k] = c.Gm[k]; mine[36 + k] = c.s[k]; }
+      mine[42] = c.q[0]; mine[43] = c.q[1]; mine[44] = c.q[2]; mine[45] = c.gwv; mine[46] = c.A1v; mine[47] = c.Jpv;
+      mine[48] = c.upc; mine[49] = c.va; mine[50] = c.tjv; mine[51] = c.ppc; mine[52] = c.rb;
+      mine[53] = 0.0; mine[54] = 0.0; mine[55] = 0.0;
+      if (SAVE && MODEL == MODEL_J2 && c.plastic) save_plastic_Fp(P, e, c.dN);
+    }
+  }
+  __syncwarp();
+  {
+    int const e0 = (blockIdx.x * blockDim.x + wib * 32);  // first element of this warp
+    int const nrec = min(32, ne - e0);
+    if (nrec > 0) {
+      double* dst = rec + (int64_t)ELEM_REC * e0;
+      int const total = nrec * ELEM_REC;  // doubles, contiguous in global memory
+      for (int g = 2 * lane; g < total; g += 64) {
+        int const r = g / ELEM_REC, k = g - r * ELEM_REC;  // ELEM_REC is even: the pair stays inside one record
+        double const* src = &srec[wib][r * (ELEM_REC + 1) + k];
+        *reinterpret_cast<double2*>(dst + g) = make_double2(src[0], src[1]);
+      }
+    }
+  }
+  if (MODEL == MODEL_J2) {
+    unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(P.plastic, (unsigned long long)__popc(b));
+  }
+}
+
+// Per-lane tangent data of stage B: the record minus w/r (those stay in shared memory).
+struct LaneTangent {
+  double Tv[6], Gm[6], s[6], q[3], gwv, A1v, Jpv, upc, va, tjv, ppc, rb;
+};
+
+template <bool TRANSPOSE, int MINB>
+__global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const half = lane >> 4, t16 = lane & 15;
+  double* stg = reinterpret_cast<double*>(smem_raw + row_owner_smem_per_warp(P.max_nblk) * wib);
+  double* wr = stg + 16 * STG_LD + lane;
+  double* acc = stg + 16 * STG_LD + 24 * WR_LD;  // [4][16*max_nblk]: copy = 2*half + (trip parity)
+  int const accld = 16 * P.max_nblk;
+
+  // Persistent warps: warp gw handles nodes gw, gw + W, gw + 2W, ...  The node -> incidence -> record chain is
+  // three dependent global loads; it is software-pipelined across nodes: while node a is processed the
+  // incidences of node a + 2W are being loaded and the records of node a + W are being pulled into L2.
+  int const W = gridDim.x * (blockDim.x >> 5);
+  int a = blockIdx.x * (blockDim.x >> 5) + wib;
+  uint32_t o0 = 0, o1 = 0, p0 = 0, p1 = 0;
+  int2 ad = make_int2(0, 0), adp = make_int2(0, 0);
+  if (a < P.nn) {
+    o0 = __ldg(P.adj_off + a); o1 = __ldg(P.adj_off + a + 1);
+    if (o0 + lane < o1) ad = __ldg(P.adj + o0 + lane);
+  }
+  if (a + W < P.nn) {
+    p0 = __ldg(P.adj_off + a + W); p1 = __ldg(P.adj_off + a + W + 1);
+    if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
+  }
+  for (; a < P.nn; a += W) {
+    // stage 1 of the pipeline: records of the next node -> L2 (4 lines cover the 448 B record)
+    if (p0 + lane < p1) {
+      char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
+#pragma unroll
+      for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
+    }
+    // stage 0: incidences of the node after next
+    uint32_t q0 = 0, q1 = 0;
+    int2 adq = make_int2(0, 0);
+    if (a + 2 * W < P.nn) {
+      q0 = __ldg(P.adj_off + a + 2 * W); q1 = __ldg(P.adj_off + a + 2 * W + 1);
+      if (q0 + lane < q1) adq = __ldg(P.adj + q0 + lane);
+    }
+    if ((int)(o1 - o0) >= P.e0) {  // nodes below the threshold are left to row_fold_sorted_kernel
+      int blk0a, nblka;
+      {
+        double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
+        blk0a = __double2loint(d3.y);
+        nblka = __double2hiint(d3.y);
+      }
+      int const nent = 16 * nblka;
+      for (int g = lane; g < nent; g += 32) { acc[g] = 0.0; acc[accld + g] = 0.0; acc[2 * accld + g] = 0.0; acc[3 * accld + g] = 0.0; }
+      double racc[4] = {0.0, 0.0, 0.0, 0.0};
+
+      for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
+        int const nact = min(32, (int)(o1 - r0));
+        bool const active = lane < nact;
+        int n = 0;
+        uint32_t jpack = 0;
+        Core<double> c;  // only the tangent fields are filled
+        if (active) {
+          int2 const adr = r0 == o0 ? ad : __ldg(P.adj + r0 + lane);
+          int const e = adr.x >> 2;
+          n = adr.x & 3; jpack = (uint32_t)adr.y;
+          double2 const* q = reinterpret_cast<double2 const*>(rec + (int64_t)ELEM_REC * e);
+#pragma unroll
+          for (int k = 0; k < 12; ++k) {  // w, r -> shared memory (this lane's column)
+            double2 const v = __ldg(q + k);
+            wr[(2 * k) * WR_LD] = v.x;
+            wr[(2 * k + 1) * WR_LD] = v.y;
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
+            v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
+            v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
+          }
+          double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
+          v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
+          v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
+          v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
+          v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
+          v = __ldg(q + 26); c.rb = v.x;
+        }
+        double wn[3], rn3[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wn[k] = wr[(3 * n + k) * WR_LD];
+          rn3[k] = wr[(12 + 3 * n + k) * WR_LD];
+        }
+        RowNode<double> rown;
+        ColNode<double> coln;
+        if (active) {
+          double r4[4];
+          element_residual_row(c, wn, r4);
+          racc[0] += r4[0]; racc[1] += r4[1]; racc[2] += r4[2]; racc[3] += r4[3];
+          if (!TRANSPOSE) row_node(c, wn, rown);
+          else column_node(c, wn, rn3, coln);
+        }
+#pragma unroll 1
+        for (int m = 0; m < 4; ++m) {
+          uint32_t jm = 0;
+          if (active) {
+            double wm[3], rm[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              wm[k] = wr[(3 * m + k) * WR_LD];
+              rm[k] = wr[(12 + 3 * m + k) * WR_LD];
+            }
+            double blk[16];
+            if (!TRANSPOSE) {
+              ColNode<double> cnm;
+              column_node(c, wm, rm, cnm);
+              jacobian_block(c, rown, cnm, blk);
+#pragma unroll
+              for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = blk[t];
+            } else {
+              RowNode<double> rnm;
+              row_node(c, wm, rnm);
+              jacobian_block(c, rnm, coln, blk);
+#pragma unroll
+              for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) stg[(4 * i + k) * STG_LD + lane] = blk[4 * k + i];
+            }
+            jm = (jpack >> (8 * m)) & 0xffu;
+          }
+          __syncwarp();
+          {
+            int const split = (nact + 1) >> 1;
+            int const lbase = half ? split : 0;
+            int const lend = half ? nact : split;
+            // two accumulator copies per half, alternated by trip parity: consecutive trips are independent
+            double* __restrict__ my0 = acc + (2 * half) * accld + t16;
+            double* __restrict__ my1 = acc + (2 * half + 1) * accld + t16;
+            double const* __restrict__ sg = stg + t16 * STG_LD;
+            for (int it = 0; it < split; it += 2) {
+              int const l = lbase + it;
+              uint32_t const j0 = __shfl_sync(0xffffffffu, jm, l & 31);
+              uint32_t const j1 = __shfl_sync(0xffffffffu, jm, (l + 1) & 31);
+              double const v0 = sg[l], v1 = sg[(l + 1) & 31];
+              if (l < lend) my0[16 * j0] += v0;
+              if (l + 1 < lend) my1[16 * j1] += v1;
+            }
+          }
+          __syncwarp();
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double v = racc[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        racc[i] = v;
+      }
+      if (lane == 0) {
+        double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
+        q[0] = make_double2(racc[0], racc[1]);
+        q[1] = make_double2(racc[2], racc[3]);
+      }
+      double* out = P.values + 16 * (int64_t)blk0a;
+      int const rl = 4 * nblka;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        for (int cidx = lane; cidx < rl; cidx += 32) {
+          int const g = 16 * (cidx >> 2) + 4 * i + (cidx & 3);
+          out[i * rl + cidx] = (acc[g] + acc[accld + g]) + (acc[2 * accld + g] + acc[3 * accld + g]);
+        }
+      __syncwarp();
+    }
+    o0 = p0; o1 = p1; ad = adp;
+    p0 = q0; p1 = q1; adp = adq;
+  }
+}
+
+// Stage B, sorted fold (nodes with at most 32 incidences -- every node of a Kuhn mesh).  All four phases
+// are staged (stg4[64][33] per warp), then each half-warp walks half of the node's precomputed,
+// target-sorted contribution list (KParams::fold_ord): lane t accumulates entry t of the current target
+// block in a register and stores it straight into the CRS row when the run ends.  No accumulator array,
+// no zeroing, no second pass; a run that straddles the two halves is closed by one shuffle.
+constexpr int STG4 = 64 * STG_LD;  // doubles per warp
+GX_HD size_t row_fold_smem_per_warp(int max_nblk) {
+  size_t const sorted = (size_t)STG4 * sizeof(double);
+  size_t const generic = row_owner_smem_per_warp(max_nblk);
+  return sorted > generic ? sorted : generic;
+}
+
+template <bool TRANSPOSE, int MINB>
+__global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const half = lane >> 4, t16 = lane & 15;
+  double* stg = reinterpret_cast<double*>(smem_raw + row_fold_smem_per_warp(P.max_nblk) * wib);
+
+  int const a = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (a >= P.nn) return;
+  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
+  int const deg = (int)(o1 - o0);
+  if (deg > 32) return;  // handled by row_fold_kernel
+  if (lane * 32 < 4 * deg)  // 16*deg bytes of fold schedule, one 128 B line per lane: pull them into L1 now
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)o0 + 32 * lane));
+  int blk0a, nblka;
+  {
+    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
+    blk0a = __double2loint(d3.y);
+    nblka = __double2hiint(d3.y);
+  }
+  double r4[4] = {0.0, 0.0, 0.0, 0.0};
+  if (lane < deg) {
+    int2 const ad = __ldg(P.adj + o0 + lane);
+    int const e = ad.x >> 2, n = ad.x & 3;
+    double const* rp = rec + (int64_t)ELEM_REC * e;
+    double2 const* q = reinterpret_cast<double2 const*>(rp);
+    Core<double> c;  // only the tangent fields are filled
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
+      v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
+      v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
+    }
+    double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
+    v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
+    v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
+    v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
+    v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
+    v = __ldg(q + 26); c.rb = v.x;
+    double wn[3], rn3[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { wn[k] = __ldg(rp + 3 * n + k); rn3[k] = __ldg(rp + 12 + 3 * n + k); }
+    element_residual_row(c, wn, r4);
+    RowNode<double> rown;
+    ColNode<double> coln;
+    if (!TRANSPOSE) row_node(c, wn, rown);
+    else column_node(c, wn, rn3, coln);
+#pragma unroll 1
+    for (int m = 0; m < 4; ++m) {
+      double wm[3], rm[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { wm[k] = __ldg(rp + 3 * m + k); rm[k] = __ldg(rp + 12 + 3 * m + k); }
+      double blk[16];
+      double* dst = stg + (m * 16) * STG_LD + lane;
+      if (!TRANSPOSE) {
+        ColNode<double> cnm;
+        column_node(c, wm, rm, cnm);
+        jacobian_block(c, rown, cnm, blk);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) dst[t * STG_LD] = blk[t];
+      } else {
+        RowNode<double> rnm;
+        row_node(c, wm, rnm);
+        jacobian_block(c, rnm, coln, blk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) dst[(4 * i + k) * STG_LD] = blk[4 * k + i];
+      }
+    }
+  }
+  __syncwarp();
+  // ---- R rows of node a: fixed butterfly over the lanes
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double v = r4[i];
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    r4[i] = v;
+  }
+  if (lane == 0) {
+    double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
+    q[0] = make_double2(r4[0], r4[1]);
+    q[1] = make_double2(r4[2], r4[3]);
+  }
+  // ---- sorted fold: both halves walk S = 2*deg entries, two per iteration, branch-free
+  int const S = 2 * deg;
+  uint2 const* ord = reinterpret_cast<uint2 const*>(P.fold_ord + 4 * (int64_t)o0 + (half ? S : 0));
+  double const* src = stg + t16 * STG_LD;
+  double* out = P.values + 16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + (t16 & 3);
+  double acc = 0.0;
+  uint32_t last = 0x80000000u;
+#pragma unroll 4
+  for (int i = 0; i < deg; ++i) {
+    uint2 const en = __ldg(ord + i);
+    double const v0 = src[en.x & 0xfffu], v1 = src[en.y & 0xfffu];
+    acc += v0;
+    if (en.x & 0x80000000u) out[4 * ((en.x >> 12) & 0xffu)] = acc;
+    acc = (en.x & 0x80000000u) ? 0.0 : acc;
+    acc += v1;
+    if (en.y & 0x80000000u) out[4 * ((en.y >> 12) & 0xffu)] = acc;
+    acc = (en.y & 0x80000000u) ? 0.0 : acc;
+    last = en.y;
+  }
+  // a run that straddles the halves: both halves end on an open partial sum of the same block
+  // (gx_setup.cpp orders half 1 that way); lower half first
+  bool const open = !(last & 0x80000000u);  // same in both halves
+  if (__any_sync(0xffffffffu, open)) {
+    double const open0 = __shfl_sync(0xffffffffu, acc, t16);
+    if (half == 1) out[4 * ((last >> 12) & 0xffu)] = open0 + acc;
+  }
+  // phantom blocks (columns that live only on other parts) receive remote contributions later: start at zero
+  if (P.nblk_g)
+    for (int j = __ldg(P.nblk_g + a) + half; j < nblka; j += 2) out[4 * j] = 0.0;
 }
 #endif
 

@@ -119,6 +119,46 @@ int build_graph_and_schedule(gx_ctx* c) {
       c->adj[k].y = (int)((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
     }
 
+  // ---- sorted fold schedule (see gx_internal.h): per node, the staged blocks ordered by target block,
+  //      ascending incidence inside a run
+  c->fold_ord.assign(4 * n2e.size(), 0u);
+#pragma omp parallel
+  {
+    std::vector<uint32_t> keys;
+#pragma omp for schedule(dynamic, 4096)
+    for (int a = 0; a < nn; ++a) {
+      int const deg = (int)(n2e_off[a + 1] - n2e_off[a]);
+      if (deg == 0 || deg > 32) continue;
+      keys.clear();
+      for (int l = 0; l < deg; ++l) {
+        uint32_t const jp = (uint32_t)c->adj[n2e_off[a] + l].y;
+        for (int m = 0; m < 4; ++m) keys.push_back((((jp >> (8 * m)) & 0xffu) << 16) | ((uint32_t)l << 2) | (uint32_t)m);
+      }
+      std::sort(keys.begin(), keys.end());
+      uint32_t* dst = c->fold_ord.data() + 4 * n2e_off[a];
+      size_t const T = keys.size(), S = T / 2;
+      std::vector<uint32_t> ent(T);
+      for (size_t t = 0; t < T; ++t) {
+        uint32_t const j = keys[t] >> 16, l = (keys[t] >> 2) & 31u, m = keys[t] & 3u;
+        bool const last = t + 1 == T || (keys[t + 1] >> 16) != j;
+        ent[t] = (m * 16u * 33u + l) | (j << 12) | (last ? 0x80000000u : 0u);
+      }
+      // Half-warp 0 walks [0,S), half-warp 1 walks [S,T).  If a run straddles S, half 1 walks the rest of
+      // that run LAST and unflagged, so both halves end with an open partial sum of the same block, which
+      // the kernel joins with one shuffle (half 0's part first).
+      std::copy(ent.begin(), ent.begin() + S, dst);
+      if (S > 0 && !(ent[S - 1] & 0x80000000u)) {
+        size_t E = S;
+        while (!(ent[E] & 0x80000000u)) ++E;
+        size_t o = S;
+        for (size_t t = E + 1; t < T; ++t) dst[o++] = ent[t];
+        for (size_t t = S; t <= E; ++t) dst[o++] = ent[t] & 0x7fffffffu;
+      } else {
+        std::copy(ent.begin() + S, ent.end(), dst + S);
+      }
+    }
+  }
+
   // ---- greedy colouring over node conflicts (elements sharing a node get different colours)
   constexpr int W = 4;  // 256 colours at most
   std::vector<uint64_t> used((size_t)nn * W, 0);
