@@ -200,7 +200,11 @@ static cudaError_t launch_two_stage(gx_ctx* ctx, KParams& P, int pass, bool save
                    : (mb == 4 ? row_fold_sorted_kernel<false, 4> : mb == 3 ? row_fold_sorted_kernel<false, 3> : row_fold_sorted_kernel<false, 2>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P, ctx->d_elemrec);
+    int per_sm = 1;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
+    if (e != cudaSuccess) return e;
+    int const blocks = std::max(1, std::min((ctx->nn + warps - 1) / warps, ctx->num_sms * std::max(per_sm, 1) * (int)ctx->opt_fold_waves));
+    kern<<<blocks, warps * 32, smem, ctx->stream>>>(P, ctx->d_elemrec);
     ctx->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess || ctx->max_deg <= 32) return e;

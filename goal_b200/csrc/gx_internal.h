@@ -80,9 +80,10 @@ struct gx_ctx {
   std::vector<uint32_t> adj_off;  // [nn+1]
   std::vector<int2> adj;          // [4*ne]  x = e*4+n, y = block positions of (a, a_m), m = 0..3, one byte each
   int max_nblk = 0, max_deg = 0;
-  // sorted fold schedule of the row fold kernel: for node a, entries [4*adj_off[a], 4*adj_off[a+1]) list the
-  // 4*deg staged blocks of its incidences sorted by target block; entry = smem offset (m*16*33 + lane) |
-  // target block << 12 | run-end flag << 31.  Only used for nodes with at most 32 incidences.
+  // sorted fold schedule of row_fold_sorted_kernel: node a's list starts at 4*adj_off[a] + 8*a; word 0 is the
+  // number of words, the words start at index 4 (padded to groups of four); each names two staged blocks with the same target block, one per half-warp:
+  //   staging offset (m*16*33 + lane) of each [11 bits each] | target block << 22 | last-word-of-block << 30.
+  // Only built for nodes with at most 32 incidences.
   std::vector<uint32_t> fold_ord;
   // ---- schedule
   int ncolors = 0;
@@ -144,7 +145,7 @@ struct gx_ctx {
   int64_t opt_row_warps = 4;
   int64_t opt_row_minblocks = 2;
   int64_t opt_fold_minblocks = 3;
-  int64_t opt_fold_sorted = 0;
+  int64_t opt_fold_sorted = 1;
   int64_t opt_fold_waves = 1;
   int num_sms = 148;
   std::string err;

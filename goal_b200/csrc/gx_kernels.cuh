@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 constexpr int STG_LD = 33;
 constexpr int WR_LD = 32;  // per-lane spatial vectors w_n, r_n (n = 0..3): wr[24][32]
 GX_HD size_t row_owner_smem_per_warp(int max_nblk) {
-  return (size_t)(16 * STG_LD + 24 * WR_LD + 4 * 16 * max_nblk) * sizeof(double);
+  return (size_t)(16 * STG_LD + 24 * WR_LD + 2 * 16 * max_nblk) * sizeof(double);
 }
 
 template <int MODEL, bool TRANSPOSE, bool SAVE, int MINB>
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
   int const half = lane >> 4, t16 = lane & 15;
   double* stg = reinterpret_cast<double*>(smem_raw + row_owner_smem_per_warp(P.max_nblk) * wib);
   double* wr = stg + 16 * STG_LD + lane;
-  double* acc = stg + 16 * STG_LD + 24 * WR_LD;  // [4][16*max_nblk]: copy = 2*half + (trip parity)
+  double* acc = stg + 16 * STG_LD + 24 * WR_LD;  // [2][16*max_nblk], one copy per half-warp
   int const accld = 16 * P.max_nblk;
 
   // Persistent warps: warp gw handles nodes gw, gw + W, gw + 2W, ...  The node -> incidence -> record chain is
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
         nblka = __double2hiint(d3.y);
       }
       int const nent = 16 * nblka;
-      for (int g = lane; g < nent; g += 32) { acc[g] = 0.0; acc[accld + g] = 0.0; acc[2 * accld + g] = 0.0; acc[3 * accld + g] = 0.0; }
+      for (int g = lane; g < nent; g += 32) { acc[g] = 0.0; acc[accld + g] = 0.0; }
       double racc[4] = {0.0, 0.0, 0.0, 0.0};
 
       for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
@@ -583,17 +583,12 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
             int const split = (nact + 1) >> 1;
             int const lbase = half ? split : 0;
             int const lend = half ? nact : split;
-            // two accumulator copies per half, alternated by trip parity: consecutive trips are independent
-            double* __restrict__ my0 = acc + (2 * half) * accld + t16;
-            double* __restrict__ my1 = acc + (2 * half + 1) * accld + t16;
-            double const* __restrict__ sg = stg + t16 * STG_LD;
-            for (int it = 0; it < split; it += 2) {
+            double* my = acc + half * accld + t16;
+#pragma unroll 4
+            for (int it = 0; it < split; ++it) {
               int const l = lbase + it;
-              uint32_t const j0 = __shfl_sync(0xffffffffu, jm, l & 31);
-              uint32_t const j1 = __shfl_sync(0xffffffffu, jm, (l + 1) & 31);
-              double const v0 = sg[l], v1 = sg[(l + 1) & 31];
-              if (l < lend) my0[16 * j0] += v0;
-              if (l + 1 < lend) my1[16 * j1] += v1;
+              uint32_t const j = __shfl_sync(0xffffffffu, jm, l & 31);
+              if (l < lend) my[16 * j] += stg[t16 * STG_LD + l];
             }
           }
           __syncwarp();
@@ -617,7 +612,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
       for (int i = 0; i < 4; ++i)
         for (int cidx = lane; cidx < rl; cidx += 32) {
           int const g = 16 * (cidx >> 2) + 4 * i + (cidx & 3);
-          out[i * rl + cidx] = (acc[g] + acc[accld + g]) + (acc[2 * accld + g] + acc[3 * accld + g]);
+          out[i * rl + cidx] = acc[g] + acc[accld + g];
         }
       __syncwarp();
     }
@@ -626,11 +621,12 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
   }
 }
 
-// Stage B, sorted fold (nodes with at most 32 incidences -- every node of a Kuhn mesh).  All four phases
-// are staged (stg4[64][33] per warp), then each half-warp walks half of the node's precomputed,
-// target-sorted contribution list (KParams::fold_ord): lane t accumulates entry t of the current target
-// block in a register and stores it straight into the CRS row when the run ends.  No accumulator array,
-// no zeroing, no second pass; a run that straddles the two halves is closed by one shuffle.
+// Stage B, sorted fold (nodes with at most 32 incidences -- every node of a Kuhn mesh).  All four blocks of
+// every incidence are staged (stg4[64][33] per warp); then the warp walks the node's precomputed schedule
+// (KParams::fold_ord, gx_setup.cpp): the staged blocks grouped by target block, two per word.  Half-warp 0
+// takes the first block of a word, half-warp 1 the second; lane t accumulates entry t in a register.  At the
+// end of a group the two halves are joined by one shuffle and half-warp 0 stores the finished 4x4 block
+// straight into the CRS rows.  Control flow is warp-uniform; no accumulator array, no zeroing, no second pass.
 constexpr int STG4 = 64 * STG_LD;  // doubles per warp
 GX_HD size_t row_fold_smem_per_warp(int max_nblk) {
   size_t const sorted = (size_t)STG4 * sizeof(double);
@@ -644,114 +640,154 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int const half = lane >> 4, t16 = lane & 15;
   double* stg = reinterpret_cast<double*>(smem_raw + row_fold_smem_per_warp(P.max_nblk) * wib);
+  stg[lane * STG_LD + 32] = 0.0;         // pad column: the schedule's "no block" slot reads as zero
+  stg[(32 + lane) * STG_LD + 32] = 0.0;
 
-  int const a = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (a >= P.nn) return;
-  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
-  int const deg = (int)(o1 - o0);
-  if (deg > 32) return;  // handled by row_fold_kernel
-  if (lane * 32 < 4 * deg)  // 16*deg bytes of fold schedule, one 128 B line per lane: pull them into L1 now
-    asm volatile("prefetch.global.L1 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)o0 + 32 * lane));
-  int blk0a, nblka;
-  {
-    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
-    blk0a = __double2loint(d3.y);
-    nblka = __double2hiint(d3.y);
+  // persistent warps with the same three-deep software pipeline as row_fold_kernel
+  int const W = gridDim.x * (blockDim.x >> 5);
+  int a = blockIdx.x * (blockDim.x >> 5) + wib;
+  uint32_t o0 = 0, o1 = 0, p0 = 0, p1 = 0;
+  int2 ad = make_int2(0, 0), adp = make_int2(0, 0);
+  if (a < P.nn) {
+    o0 = __ldg(P.adj_off + a); o1 = __ldg(P.adj_off + a + 1);
+    if (o0 + lane < o1) ad = __ldg(P.adj + o0 + lane);
   }
-  double r4[4] = {0.0, 0.0, 0.0, 0.0};
-  if (lane < deg) {
-    int2 const ad = __ldg(P.adj + o0 + lane);
-    int const e = ad.x >> 2, n = ad.x & 3;
-    double const* rp = rec + (int64_t)ELEM_REC * e;
-    double2 const* q = reinterpret_cast<double2 const*>(rp);
-    Core<double> c;  // only the tangent fields are filled
+  if (a + W < P.nn) {
+    p0 = __ldg(P.adj_off + a + W); p1 = __ldg(P.adj_off + a + W + 1);
+    if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
+  }
+  for (; a < P.nn; a += W) {
+    if (p0 + lane < p1) {
+      char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
-      v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
-      v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
+      for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
     }
-    double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
-    v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
-    v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
-    v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
-    v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
-    v = __ldg(q + 26); c.rb = v.x;
-    double wn[3], rn3[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) { wn[k] = __ldg(rp + 3 * n + k); rn3[k] = __ldg(rp + 12 + 3 * n + k); }
-    element_residual_row(c, wn, r4);
-    RowNode<double> rown;
-    ColNode<double> coln;
-    if (!TRANSPOSE) row_node(c, wn, rown);
-    else column_node(c, wn, rn3, coln);
-#pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
-      double wm[3], rm[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { wm[k] = __ldg(rp + 3 * m + k); rm[k] = __ldg(rp + 12 + 3 * m + k); }
-      double blk[16];
-      double* dst = stg + (m * 16) * STG_LD + lane;
-      if (!TRANSPOSE) {
-        ColNode<double> cnm;
-        column_node(c, wm, rm, cnm);
-        jacobian_block(c, rown, cnm, blk);
-#pragma unroll
-        for (int t = 0; t < 16; ++t) dst[t * STG_LD] = blk[t];
-      } else {
-        RowNode<double> rnm;
-        row_node(c, wm, rnm);
-        jacobian_block(c, rnm, coln, blk);
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int k = 0; k < 4; ++k) dst[(4 * i + k) * STG_LD] = blk[4 * k + i];
+    if (lane < 4 && p1 - p0 <= 32) {  // next node's schedule (at most 132 words) -> L2
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)p0 + 8 * (int64_t)(a + W) + 32 * lane));
+    }
+    uint32_t q0 = 0, q1 = 0;
+    int2 adq = make_int2(0, 0);
+    if (a + 2 * W < P.nn) {
+      q0 = __ldg(P.adj_off + a + 2 * W); q1 = __ldg(P.adj_off + a + 2 * W + 1);
+      if (q0 + lane < q1) adq = __ldg(P.adj + q0 + lane);
+    }
+    int const deg = (int)(o1 - o0);
+    if (deg <= 32) {  // larger nodes are handled by row_fold_kernel
+      int blk0a, nblka;
+      {
+        double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
+        blk0a = __double2loint(d3.y);
+        nblka = __double2hiint(d3.y);
       }
+      uint4 const* ord = reinterpret_cast<uint4 const*>(P.fold_ord + 4 * (int64_t)o0 + 8 * (int64_t)a);
+      int nw = 0;
+      uint4 wq = make_uint4(32u | (32u << 11), 32u | (32u << 11), 32u | (32u << 11), 32u | (32u << 11));
+      if (deg > 0) { nw = (int)__ldg(reinterpret_cast<uint32_t const*>(ord)); wq = __ldg(ord + 1); }  // issued early
+      double r4[4] = {0.0, 0.0, 0.0, 0.0};
+      if (lane < deg) {
+        int const e = ad.x >> 2, n = ad.x & 3;
+        double2 const* q = reinterpret_cast<double2 const*>(rec + (int64_t)ELEM_REC * e);
+        Core<double> c;  // only the tangent fields are filled
+        double wv[4][3], rv[4][3];
+        {
+          double2 v[12];
+#pragma unroll
+          for (int k = 0; k < 12; ++k) v[k] = __ldg(q + k);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) {
+            (&wv[0][0])[2 * k] = v[k].x; (&wv[0][0])[2 * k + 1] = v[k].y;
+            (&rv[0][0])[2 * k] = v[6 + k].x; (&rv[0][0])[2 * k + 1] = v[6 + k].y;
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
+          v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
+          v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
+        }
+        double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
+        v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
+        v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
+        v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
+        v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
+        v = __ldg(q + 26); c.rb = v.x;
+        double wn[3], rn3[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          wn[k] = n == 0 ? wv[0][k] : n == 1 ? wv[1][k] : n == 2 ? wv[2][k] : wv[3][k];
+          rn3[k] = n == 0 ? rv[0][k] : n == 1 ? rv[1][k] : n == 2 ? rv[2][k] : rv[3][k];
+        }
+        element_residual_row(c, wn, r4);
+        RowNode<double> rown;
+        ColNode<double> coln;
+        if (!TRANSPOSE) row_node(c, wn, rown);
+        else column_node(c, wn, rn3, coln);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          double blk[16];
+          double* dst = stg + (m * 16) * STG_LD + lane;
+          if (!TRANSPOSE) {
+            ColNode<double> cnm;
+            column_node(c, wv[m], rv[m], cnm);
+            jacobian_block(c, rown, cnm, blk);
+#pragma unroll
+            for (int t = 0; t < 16; ++t) dst[t * STG_LD] = blk[t];
+          } else {
+            RowNode<double> rnm;
+            row_node(c, wv[m], rnm);
+            jacobian_block(c, rnm, coln, blk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) dst[(4 * i + k) * STG_LD] = blk[4 * k + i];
+          }
+        }
+      }
+      __syncwarp();
+      // ---- R rows of node a: fixed butterfly over the lanes
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        double v = r4[i];
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+        r4[i] = v;
+      }
+      if (lane == 0) {
+        double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
+        q[0] = make_double2(r4[0], r4[1]);
+        q[1] = make_double2(r4[2], r4[3]);
+      }
+      // ---- sorted fold, warp-uniform control flow
+      double const* src = stg + t16 * STG_LD;
+      double* out = P.values + 16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + (t16 & 3);
+      int const sh = half ? 11 : 0;
+      double acc = 0.0;
+      for (int i = 0; i < nw; i += 4) {
+        uint4 const w = wq;
+        if (i + 4 < nw) wq = __ldg(ord + 2 + (i >> 2));  // next group, in flight while this one is folded
+        // the four staged values first (independent shared loads), then the dependent adds
+        double const v0 = src[(w.x >> sh) & 0x7ffu], v1 = src[(w.y >> sh) & 0x7ffu];
+        double const v2 = src[(w.z >> sh) & 0x7ffu], v3 = src[(w.w >> sh) & 0x7ffu];
+        uint32_t const ws[4] = {w.x, w.y, w.z, w.w};
+        double const vs[4] = {v0, v1, v2, v3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          acc += vs[k];
+          if (ws[k] & 0x40000000u) {  // same word in every lane: uniform branch
+            double const tot = acc + __shfl_xor_sync(0xffffffffu, acc, 16);
+            if (half == 0) out[4 * ((ws[k] >> 22) & 0xffu)] = tot;
+            acc = 0.0;
+          }
+        }
+      }
+      // phantom blocks (columns that live only on other parts) receive remote contributions later: start at zero
+      if (P.nblk_g)
+        for (int j = __ldg(P.nblk_g + a) + half; j < nblka; j += 2) out[4 * j] = 0.0;
+      __syncwarp();
     }
+    o0 = p0; o1 = p1; ad = adp;
+    p0 = q0; p1 = q1; adp = adq;
   }
-  __syncwarp();
-  // ---- R rows of node a: fixed butterfly over the lanes
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double v = r4[i];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    r4[i] = v;
-  }
-  if (lane == 0) {
-    double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
-    q[0] = make_double2(r4[0], r4[1]);
-    q[1] = make_double2(r4[2], r4[3]);
-  }
-  // ---- sorted fold: both halves walk S = 2*deg entries, two per iteration, branch-free
-  int const S = 2 * deg;
-  uint2 const* ord = reinterpret_cast<uint2 const*>(P.fold_ord + 4 * (int64_t)o0 + (half ? S : 0));
-  double const* src = stg + t16 * STG_LD;
-  double* out = P.values + 16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + (t16 & 3);
-  double acc = 0.0;
-  uint32_t last = 0x80000000u;
-#pragma unroll 4
-  for (int i = 0; i < deg; ++i) {
-    uint2 const en = __ldg(ord + i);
-    double const v0 = src[en.x & 0xfffu], v1 = src[en.y & 0xfffu];
-    acc += v0;
-    if (en.x & 0x80000000u) out[4 * ((en.x >> 12) & 0xffu)] = acc;
-    acc = (en.x & 0x80000000u) ? 0.0 : acc;
-    acc += v1;
-    if (en.y & 0x80000000u) out[4 * ((en.y >> 12) & 0xffu)] = acc;
-    acc = (en.y & 0x80000000u) ? 0.0 : acc;
-    last = en.y;
-  }
-  // a run that straddles the halves: both halves end on an open partial sum of the same block
-  // (gx_setup.cpp orders half 1 that way); lower half first
-  bool const open = !(last & 0x80000000u);  // same in both halves
-  if (__any_sync(0xffffffffu, open)) {
-    double const open0 = __shfl_sync(0xffffffffu, acc, t16);
-    if (half == 1) out[4 * ((last >> 12) & 0xffu)] = open0 + acc;
-  }
-  // phantom blocks (columns that live only on other parts) receive remote contributions later: start at zero
-  if (P.nblk_g)
-    for (int j = __ldg(P.nblk_g + a) + half; j < nblka; j += 2) out[4 * j] = 0.0;
 }
 #endif
 

@@ -119,9 +119,9 @@ int build_graph_and_schedule(gx_ctx* c) {
       c->adj[k].y = (int)((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
     }
 
-  // ---- sorted fold schedule (see gx_internal.h): per node, the staged blocks ordered by target block,
-  //      ascending incidence inside a run
-  c->fold_ord.assign(4 * n2e.size(), 0u);
+  // ---- sorted fold schedule (see gx_internal.h): per node, its 4*deg staged blocks grouped by target block;
+  //      inside a group ascending incidence; two blocks per word (one per half-warp)
+  c->fold_ord.assign(4 * n2e.size() + 8 * (size_t)nn, 0u);
 #pragma omp parallel
   {
     std::vector<uint32_t> keys;
@@ -135,27 +135,25 @@ int build_graph_and_schedule(gx_ctx* c) {
         for (int m = 0; m < 4; ++m) keys.push_back((((jp >> (8 * m)) & 0xffu) << 16) | ((uint32_t)l << 2) | (uint32_t)m);
       }
       std::sort(keys.begin(), keys.end());
-      uint32_t* dst = c->fold_ord.data() + 4 * n2e_off[a];
-      size_t const T = keys.size(), S = T / 2;
-      std::vector<uint32_t> ent(T);
-      for (size_t t = 0; t < T; ++t) {
-        uint32_t const j = keys[t] >> 16, l = (keys[t] >> 2) & 31u, m = keys[t] & 3u;
-        bool const last = t + 1 == T || (keys[t + 1] >> 16) != j;
-        ent[t] = (m * 16u * 33u + l) | (j << 12) | (last ? 0x80000000u : 0u);
+      uint32_t* dst = c->fold_ord.data() + 4 * n2e_off[a] + 8 * (size_t)a;  // [0] = word count, words from [4]
+      uint32_t nw = 0;
+      size_t t = 0;
+      while (t < keys.size()) {
+        uint32_t const j = keys[t] >> 16;
+        size_t e = t;
+        while (e < keys.size() && (keys[e] >> 16) == j) ++e;
+        for (size_t q = t; q < e; q += 2) {
+          auto off = [&](size_t i) -> uint32_t {
+            if (i >= e) return 32u;  // the always-zero pad column of staging row 0
+            return (keys[i] & 3u) * 16u * 33u + ((keys[i] >> 2) & 31u);
+          };
+          bool const last = q + 2 >= e;
+          dst[4 + nw++] = off(q) | (off(q + 1) << 11) | (j << 22) | (last ? 0x40000000u : 0u);
+        }
+        t = e;
       }
-      // Half-warp 0 walks [0,S), half-warp 1 walks [S,T).  If a run straddles S, half 1 walks the rest of
-      // that run LAST and unflagged, so both halves end with an open partial sum of the same block, which
-      // the kernel joins with one shuffle (half 0's part first).
-      std::copy(ent.begin(), ent.begin() + S, dst);
-      if (S > 0 && !(ent[S - 1] & 0x80000000u)) {
-        size_t E = S;
-        while (!(ent[E] & 0x80000000u)) ++E;
-        size_t o = S;
-        for (size_t t = E + 1; t < T; ++t) dst[o++] = ent[t];
-        for (size_t t = S; t <= E; ++t) dst[o++] = ent[t] & 0x7fffffffu;
-      } else {
-        std::copy(ent.begin() + S, ent.end(), dst + S);
-      }
+      dst[0] = nw;
+      for (uint32_t q = nw; q < ((nw + 3u) & ~3u); ++q) dst[4 + q] = 32u | (32u << 11);  // pad to groups of 4 with no-ops
     }
   }
 

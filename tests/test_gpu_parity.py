@@ -83,6 +83,30 @@ def test_jacobian_residual_state_parity(cube, model, mesh):
     a.close()
 
 
+@pytest.mark.parametrize("opts", [dict(fold_sorted=1), dict(kernel=2), dict(kernel=1), dict(fold_sorted=1, fold_minblocks=2, row_warps=2)])
+@pytest.mark.parametrize("mesh", ["cube", "kuhn7"])
+def test_kernel_variants_parity(cube, mesh, opts):
+    """Every Jacobian schedule (sorted fold, generic fold, fused row-owner, coloured) against the oracle,
+    primal and adjoint, incl. the fixture whose nodes have up to 56 incident elements."""
+    import goal_b200
+    co, cn = _mesh(cube, mesh)
+    f = fields(co, len(cn), strain=0.004)
+    a, o = _pair(co, cn, "J2", f)
+    for k, v in opts.items():
+        a.set_option(k, v)
+    R, A = a.jacobian(goal_b200.PRIMAL, save=True)
+    Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=True)
+    assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
+    assert relerr(a.get_state("sigma"), o.state("sigma")) < 1e-10
+    assert np.abs(a.get_state("Fp") - o.state("Fp")).max() < 1e-10 and a.plastic_count() == o.plastic_count()
+    At = a.jacobian(goal_b200.ADJOINT, save=False)[1].copy()
+    assert relerr(At, o.jacobian(goal_b200.ADJOINT, save=False)[1]) < 1e-12
+    R1, A1 = [x.copy() for x in a.jacobian(goal_b200.PRIMAL, save=False)]
+    R2, A2 = a.jacobian(goal_b200.PRIMAL, save=False)
+    assert np.array_equal(R1, R2) and np.array_equal(A1, A2)  # bit-reproducible
+    a.close()
+
+
 def test_multiple_elem_sets(cube):
     import goal_b200
     co, cn = kuhn_cube(6)
