@@ -155,7 +155,7 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
-  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj; P.fold_ord = ctx->d_fold_ord; P.nblk_g = ctx->nnz_x != ctx->nnz ? ctx->d_nblk_g : nullptr;
+  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj; P.fold_ord = ctx->d_fold_ord; P.nblk_g = ctx->nnz_x != ctx->nnz ? ctx->d_nblk_g : nullptr; P.fold_ld = ctx->fold_ld;
   P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
   P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
@@ -195,7 +195,7 @@ static cudaError_t launch_two_stage(gx_ctx* ctx, KParams& P, int pass, bool save
   int const mb = (int)ctx->opt_fold_minblocks;
   bool const sorted = ctx->opt_fold_sorted != 0;
   if (sorted) {  // nodes with <= 32 incidences
-    size_t const smem = row_fold_smem_per_warp(ctx->max_nblk) * warps;
+    size_t const smem = (size_t)64 * ctx->fold_ld * sizeof(double) * warps;
     auto kern = tr ? (mb == 4 ? row_fold_sorted_kernel<true, 4> : mb == 3 ? row_fold_sorted_kernel<true, 3> : row_fold_sorted_kernel<true, 2>)
                    : (mb == 4 ? row_fold_sorted_kernel<false, 4> : mb == 3 ? row_fold_sorted_kernel<false, 3> : row_fold_sorted_kernel<false, 2>);
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -85,6 +85,7 @@ struct gx_ctx {
   //   staging offset (m*16*33 + lane) of each [11 bits each] | target block << 22 | last-word-of-block << 30.
   // Only built for nodes with at most 32 incidences.
   std::vector<uint32_t> fold_ord;
+  int fold_ld = 33;  // staging row stride the schedule was built for
   // ---- schedule
   int ncolors = 0;
   std::vector<int32_t> color_off;  // [ncolors+1] in device element order

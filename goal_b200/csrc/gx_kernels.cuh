@@ -47,6 +47,7 @@ struct KParams {
   int2 const* adj;
   uint32_t const* fold_ord;
   int32_t const* nblk_g;  // partitioned contexts: local (ghost) block count per node; blocks beyond it are phantom
+  int fold_ld;            // row stride of the sorted fold's staging array: odd, > max incidences per node (<= 33)
   double const* state_in;
   double const* fp_old;
   double* state_out;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 // Nodes with more than 32 incident elements take several rounds.
 // Shared memory per warp: stg 16*33*8 B + wr 24*32*8 B + acc 2*128*max_nblk B.
 // ---------------------------------------------------------------------------
+GX_HD int std_min_int(int a, int b) { return a < b ? a : b; }
 constexpr int STG_LD = 33;
 constexpr int WR_LD = 32;  // per-lane spatial vectors w_n, r_n (n = 0..3): wr[24][32]
 GX_HD size_t row_owner_smem_per_warp(int max_nblk) {
@@ -627,10 +629,13 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
 // takes the first block of a word, half-warp 1 the second; lane t accumulates entry t in a register.  At the
 // end of a group the two halves are joined by one shuffle and half-warp 0 stores the finished 4x4 block
 // straight into the CRS rows.  Control flow is warp-uniform; no accumulator array, no zeroing, no second pass.
-constexpr int STG4 = 64 * STG_LD;  // doubles per warp
-GX_HD size_t row_fold_smem_per_warp(int max_nblk) {
-  size_t const sorted = (size_t)STG4 * sizeof(double);
-  size_t const generic = row_owner_smem_per_warp(max_nblk);
+GX_HD int fold_row_stride(int max_deg) {  // staging row stride: one pad column past the widest node, odd, <= 33
+  int const ld = (std_min_int(max_deg, 32) + 1) | 1;
+  return ld;
+}
+GX_HD size_t row_fold_smem_per_warp(int max_nblk, int fold_ld, bool need_generic) {
+  size_t const sorted = (size_t)64 * fold_ld * sizeof(double);
+  size_t const generic = need_generic ? row_owner_smem_per_warp(max_nblk) : 0;
   return sorted > generic ? sorted : generic;
 }
 
@@ -639,9 +644,10 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int const half = lane >> 4, t16 = lane & 15;
-  double* stg = reinterpret_cast<double*>(smem_raw + row_fold_smem_per_warp(P.max_nblk) * wib);
-  stg[lane * STG_LD + 32] = 0.0;         // pad column: the schedule's "no block" slot reads as zero
-  stg[(32 + lane) * STG_LD + 32] = 0.0;
+  int const ld = P.fold_ld;
+  double* stg = reinterpret_cast<double*>(smem_raw + (size_t)64 * ld * sizeof(double) * wib);
+  stg[lane * ld + ld - 1] = 0.0;         // pad column: the schedule's "no block" slot reads as zero
+  stg[(32 + lane) * ld + ld - 1] = 0.0;
 
   // persistent warps with the same three-deep software pipeline as row_fold_kernel
   int const W = gridDim.x * (blockDim.x >> 5);
@@ -681,7 +687,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
       }
       uint4 const* ord = reinterpret_cast<uint4 const*>(P.fold_ord + 4 * (int64_t)o0 + 8 * (int64_t)a);
       int nw = 0;
-      uint4 wq = make_uint4(32u | (32u << 11), 32u | (32u << 11), 32u | (32u << 11), 32u | (32u << 11));
+      uint32_t const nop = (uint32_t)(ld - 1) | ((uint32_t)(ld - 1) << 11);
+      uint4 wq = make_uint4(nop, nop, nop, nop);
       if (deg > 0) { nw = (int)__ldg(reinterpret_cast<uint32_t const*>(ord)); wq = __ldg(ord + 1); }  // issued early
       double r4[4] = {0.0, 0.0, 0.0, 0.0};
       if (lane < deg) {
@@ -725,13 +732,13 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 #pragma unroll
         for (int m = 0; m < 4; ++m) {
           double blk[16];
-          double* dst = stg + (m * 16) * STG_LD + lane;
+          double* dst = stg + (m * 16) * ld + lane;
           if (!TRANSPOSE) {
             ColNode<double> cnm;
             column_node(c, wv[m], rv[m], cnm);
             jacobian_block(c, rown, cnm, blk);
 #pragma unroll
-            for (int t = 0; t < 16; ++t) dst[t * STG_LD] = blk[t];
+            for (int t = 0; t < 16; ++t) dst[t * ld] = blk[t];
           } else {
             RowNode<double> rnm;
             row_node(c, wv[m], rnm);
@@ -739,7 +746,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-              for (int k = 0; k < 4; ++k) dst[(4 * i + k) * STG_LD] = blk[4 * k + i];
+              for (int k = 0; k < 4; ++k) dst[(4 * i + k) * ld] = blk[4 * k + i];
           }
         }
       }
@@ -758,7 +765,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
         q[1] = make_double2(r4[2], r4[3]);
       }
       // ---- sorted fold, warp-uniform control flow
-      double const* src = stg + t16 * STG_LD;
+      double const* src = stg + t16 * ld;
       double* out = P.values + 16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + (t16 & 3);
       int const sh = half ? 11 : 0;
       double acc = 0.0;

@@ -122,6 +122,8 @@ int build_graph_and_schedule(gx_ctx* c) {
   // ---- sorted fold schedule (see gx_internal.h): per node, its 4*deg staged blocks grouped by target block;
   //      inside a group ascending incidence; two blocks per word (one per half-warp)
   c->fold_ord.assign(4 * n2e.size() + 8 * (size_t)nn, 0u);
+  uint32_t const ld = (uint32_t)((std::min(c->max_deg, 32) + 1) | 1);  // == fold_row_stride(max_deg), gx_kernels.cuh
+  c->fold_ld = (int)ld;
 #pragma omp parallel
   {
     std::vector<uint32_t> keys;
@@ -144,8 +146,8 @@ int build_graph_and_schedule(gx_ctx* c) {
         while (e < keys.size() && (keys[e] >> 16) == j) ++e;
         for (size_t q = t; q < e; q += 2) {
           auto off = [&](size_t i) -> uint32_t {
-            if (i >= e) return 32u;  // the always-zero pad column of staging row 0
-            return (keys[i] & 3u) * 16u * 33u + ((keys[i] >> 2) & 31u);
+            if (i >= e) return ld - 1u;  // the always-zero pad column of staging row 0
+            return (keys[i] & 3u) * 16u * ld + ((keys[i] >> 2) & 31u);
           };
           bool const last = q + 2 >= e;
           dst[4 + nw++] = off(q) | (off(q + 1) << 11) | (j << 22) | (last ? 0x40000000u : 0u);
@@ -153,7 +155,7 @@ int build_graph_and_schedule(gx_ctx* c) {
         t = e;
       }
       dst[0] = nw;
-      for (uint32_t q = nw; q < ((nw + 3u) & ~3u); ++q) dst[4 + q] = 32u | (32u << 11);  // pad to groups of 4 with no-ops
+      for (uint32_t q = nw; q < ((nw + 3u) & ~3u); ++q) dst[4 + q] = (ld - 1u) | ((ld - 1u) << 11);  // pad to groups of 4 with no-ops
     }
   }
 
