@@ -37,7 +37,7 @@ B_ALG = {"J2": 16 + 16 + (24 + 32 + 32) / 6 + 80 + 152 + 320, "neohookean": 16 +
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cells", type=int, default=128, help="cells per side of each GPU's block")
@@ -134,7 +134,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -291,7 +291,8 @@ def run_b200(args):
         "plastic_fraction": plastic / ne_local, "colours": a.num_colors,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": f"gx::row_owner_kernel<{args.model},primal,save> (one launch per pass)",
+                     "kernel": f"gx::elem_record_kernel<{args.model},save> + gx::row_fold_sorted_kernel<primal> "
+                               "(the two launches of one Jacobian pass; achieved = B_alg * elements / their summed device time)",
                      "kernel_ms_per_pass": k_ms, "zero_ms_per_pass": statistics.mean(zero_ms),
                      "exchange_ms_per_pass": statistics.mean(exch_ms),
                      "algorithmic_bytes_per_element": B_ALG[args.model]},
