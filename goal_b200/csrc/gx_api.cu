@@ -155,7 +155,7 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
-  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj; P.fold_ord = ctx->d_fold_ord; P.nblk_g = ctx->nnz_x != ctx->nnz ? ctx->d_nblk_g : nullptr; P.fold_ld = ctx->fold_ld;
+  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj; P.fold_ord = ctx->d_fold_ord; P.nblk_g = ctx->nnz_x != ctx->nnz ? ctx->d_nblk_g : nullptr; P.fold_ld = ctx->fold_ld; P.node_order = ctx->d_node_order;
   P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
   P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
@@ -327,7 +327,7 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
 static void free_device(gx_ctx* ctx) {
   if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord,
+  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord, ctx->d_node_order,
                   ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -402,6 +402,8 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj_off, sizeof(uint32_t) * (size_t)(nn + 1)));
     GX_CUDA(cudaMemcpy(ctx->d_adj_off, ctx->adj_off.data(), sizeof(uint32_t) * (size_t)(nn + 1), cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_node_order, sizeof(int32_t) * (size_t)nn));
+    GX_CUDA(cudaMemcpy(ctx->d_node_order, ctx->node_order.data(), sizeof(int32_t) * (size_t)nn, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_fold_ord, sizeof(uint32_t) * std::max<size_t>(ctx->fold_ord.size(), 1)));
     GX_CUDA(cudaMemcpy(ctx->d_fold_ord, ctx->fold_ord.data(), sizeof(uint32_t) * ctx->fold_ord.size(), cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj, sizeof(int2) * ctx->adj.size()));

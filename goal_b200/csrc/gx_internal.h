@@ -86,6 +86,9 @@ struct gx_ctx {
   // Only built for nodes with at most 32 incidences.
   std::vector<uint32_t> fold_ord;
   int fold_ld = 33;  // staging row stride the schedule was built for
+  // order in which stage B visits the nodes: Morton (Z-curve) order of the node coordinates, so that the four
+  // incidences of an element are processed close in time and its tangent record is fetched from HBM once
+  std::vector<int32_t> node_order;
   // ---- schedule
   int ncolors = 0;
   std::vector<int32_t> color_off;  // [ncolors+1] in device element order
@@ -102,6 +105,7 @@ struct gx_ctx {
   uint32_t* d_adj_off = nullptr;
   int2* d_adj = nullptr;
   uint32_t* d_fold_ord = nullptr;
+  int32_t* d_node_order = nullptr;
   // history state, one record per element (user order):
   //   in    : Cp^{-1}[6] (of Fp_old, cached), eqps_old, pad   (64 B)  read by every incidence of the element
   //   fp_old: Fp_old[9]                                       (72 B)  read only when a plastic element saves Fp

@@ -48,6 +48,7 @@ struct KParams {
   uint32_t const* fold_ord;
   int32_t const* nblk_g;  // partitioned contexts: local (ghost) block count per node; blocks beyond it are phantom
   int fold_ld;            // row stride of the sorted fold's staging array: odd, > max incidences per node (<= 33)
+  int32_t const* node_order;  // stage B visiting order (Z-curve)
   double const* state_in;
   double const* fp_old;
   double* state_out;
@@ -471,18 +472,21 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
   // three dependent global loads; it is software-pipelined across nodes: while node a is processed the
   // incidences of node a + 2W are being loaded and the records of node a + W are being pulled into L2.
   int const W = gridDim.x * (blockDim.x >> 5);
-  int a = blockIdx.x * (blockDim.x >> 5) + wib;
+  int slot = blockIdx.x * (blockDim.x >> 5) + wib;  // position in the visiting order
+  int a = 0, ap = 0;
   uint32_t o0 = 0, o1 = 0, p0 = 0, p1 = 0;
   int2 ad = make_int2(0, 0), adp = make_int2(0, 0);
-  if (a < P.nn) {
+  if (slot < P.nn) {
+    a = __ldg(P.node_order + slot);
     o0 = __ldg(P.adj_off + a); o1 = __ldg(P.adj_off + a + 1);
     if (o0 + lane < o1) ad = __ldg(P.adj + o0 + lane);
   }
-  if (a + W < P.nn) {
-    p0 = __ldg(P.adj_off + a + W); p1 = __ldg(P.adj_off + a + W + 1);
+  if (slot + W < P.nn) {
+    ap = __ldg(P.node_order + slot + W);
+    p0 = __ldg(P.adj_off + ap); p1 = __ldg(P.adj_off + ap + 1);
     if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
   }
-  for (; a < P.nn; a += W) {
+  for (; slot < P.nn; slot += W) {
     // stage 1 of the pipeline: records of the next node -> L2 (4 lines cover the 448 B record)
     if (p0 + lane < p1) {
       char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
@@ -491,9 +495,11 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
     }
     // stage 0: incidences of the node after next
     uint32_t q0 = 0, q1 = 0;
+    int aq = 0;
     int2 adq = make_int2(0, 0);
-    if (a + 2 * W < P.nn) {
-      q0 = __ldg(P.adj_off + a + 2 * W); q1 = __ldg(P.adj_off + a + 2 * W + 1);
+    if (slot + 2 * W < P.nn) {
+      aq = __ldg(P.node_order + slot + 2 * W);
+      q0 = __ldg(P.adj_off + aq); q1 = __ldg(P.adj_off + aq + 1);
       if (q0 + lane < q1) adq = __ldg(P.adj + q0 + lane);
     }
     if ((int)(o1 - o0) >= P.e0) {  // nodes below the threshold are left to row_fold_sorted_kernel
@@ -618,8 +624,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
         }
       __syncwarp();
     }
-    o0 = p0; o1 = p1; ad = adp;
-    p0 = q0; p1 = q1; adp = adq;
+    a = ap; o0 = p0; o1 = p1; ad = adp;
+    ap = aq; p0 = q0; p1 = q1; adp = adq;
   }
 }
 
@@ -651,30 +657,35 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 
   // persistent warps with the same three-deep software pipeline as row_fold_kernel
   int const W = gridDim.x * (blockDim.x >> 5);
-  int a = blockIdx.x * (blockDim.x >> 5) + wib;
+  int slot = blockIdx.x * (blockDim.x >> 5) + wib;  // position in the visiting order
+  int a = 0, ap = 0;
   uint32_t o0 = 0, o1 = 0, p0 = 0, p1 = 0;
   int2 ad = make_int2(0, 0), adp = make_int2(0, 0);
-  if (a < P.nn) {
+  if (slot < P.nn) {
+    a = __ldg(P.node_order + slot);
     o0 = __ldg(P.adj_off + a); o1 = __ldg(P.adj_off + a + 1);
     if (o0 + lane < o1) ad = __ldg(P.adj + o0 + lane);
   }
-  if (a + W < P.nn) {
-    p0 = __ldg(P.adj_off + a + W); p1 = __ldg(P.adj_off + a + W + 1);
+  if (slot + W < P.nn) {
+    ap = __ldg(P.node_order + slot + W);
+    p0 = __ldg(P.adj_off + ap); p1 = __ldg(P.adj_off + ap + 1);
     if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
   }
-  for (; a < P.nn; a += W) {
+  for (; slot < P.nn; slot += W) {
     if (p0 + lane < p1) {
       char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
 #pragma unroll
       for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
     }
     if (lane < 4 && p1 - p0 <= 32) {  // next node's schedule (at most 132 words) -> L2
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)p0 + 8 * (int64_t)(a + W) + 32 * lane));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)p0 + 8 * (int64_t)ap + 32 * lane));
     }
     uint32_t q0 = 0, q1 = 0;
+    int aq = 0;
     int2 adq = make_int2(0, 0);
-    if (a + 2 * W < P.nn) {
-      q0 = __ldg(P.adj_off + a + 2 * W); q1 = __ldg(P.adj_off + a + 2 * W + 1);
+    if (slot + 2 * W < P.nn) {
+      aq = __ldg(P.node_order + slot + 2 * W);
+      q0 = __ldg(P.adj_off + aq); q1 = __ldg(P.adj_off + aq + 1);
       if (q0 + lane < q1) adq = __ldg(P.adj + q0 + lane);
     }
     int const deg = (int)(o1 - o0);
@@ -792,8 +803,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
         for (int j = __ldg(P.nblk_g + a) + half; j < nblka; j += 2) out[4 * j] = 0.0;
       __syncwarp();
     }
-    o0 = p0; o1 = p1; ad = adp;
-    p0 = q0; p1 = q1; adp = adq;
+    a = ap; o0 = p0; o1 = p1; ad = adp;
+    ap = aq; p0 = q0; p1 = q1; adp = adq;
   }
 }
 #endif

@@ -159,6 +159,38 @@ int build_graph_and_schedule(gx_ctx* c) {
     }
   }
 
+  // ---- stage B node order: Z-curve over the bounding box (10 bits per axis), ties by node id
+  {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    for (int a = 0; a < nn; ++a)
+      for (int d = 0; d < 3; ++d) {
+        lo[d] = std::min(lo[d], c->coords[3 * (size_t)a + d]);
+        hi[d] = std::max(hi[d], c->coords[3 * (size_t)a + d]);
+      }
+    auto spread = [](uint64_t v) {  // 10 bits -> every third bit
+      v &= 0x3ff;
+      v = (v | (v << 16)) & 0x30000ff;
+      v = (v | (v << 8)) & 0x300f00f;
+      v = (v | (v << 4)) & 0x30c30c3;
+      v = (v | (v << 2)) & 0x9249249;
+      return v;
+    };
+    std::vector<uint64_t> key(nn);
+#pragma omp parallel for schedule(static)
+    for (int a = 0; a < nn; ++a) {
+      uint64_t code = 0;
+      for (int d = 0; d < 3; ++d) {
+        double const ext = hi[d] - lo[d];
+        uint64_t const q = ext > 0 ? (uint64_t)std::min(1023.0, (c->coords[3 * (size_t)a + d] - lo[d]) / ext * 1024.0) : 0;
+        code |= spread(q) << d;
+      }
+      key[a] = (code << 32) | (uint32_t)a;
+    }
+    std::sort(key.begin(), key.end());
+    c->node_order.resize(nn);
+    for (int a = 0; a < nn; ++a) c->node_order[a] = (int32_t)(key[a] & 0xffffffffu);
+  }
+
   // ---- greedy colouring over node conflicts (elements sharing a node get different colours)
   constexpr int W = 4;  // 256 colours at most
   std::vector<uint64_t> used((size_t)nn * W, 0);

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Run on the B200 box via gpurun: build check, GPU tests, smoke, bench, ncu launch list + full capture.
+# Run on the B200 box via gpurun: GPU tests, smoke, bench (both arms), ncu launch list + full capture.
 # Usage: scripts/gpu_check.sh [tag]   (outputs under gpurun_out/<tag>_*)
 set -u
 TAG=${1:-run}
@@ -7,16 +7,18 @@ OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/${TAG}_gpu.txt 2>&1
 nproc >> $OUT/${TAG}_gpu.txt; free -g | head -2 >> $OUT/${TAG}_gpu.txt
-echo "== pytest gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee $OUT/${TAG}_pytest.txt
-echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5 | tee $OUT/${TAG}_smoke.txt
-echo "== bench"; timeout 900 python bench.py --steps 10 --warmup 3 2>&1 | tail -3 | tee $OUT/${TAG}_bench.json
-echo "== bench neohookean"; timeout 600 python bench.py --steps 10 --warmup 3 --model neohookean --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/${TAG}_bench_neo.json
-echo "== ncu launches"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
-  python bench.py --steps 2 --warmup 1 --cells 64 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
-tail -2 $OUT/${TAG}_ncu_launches.log
-echo "== ncu full"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:row_owner_kernel -s 1 -c 2 -f -o $OUT/${TAG}_prof \
-  python bench.py --steps 2 --warmup 1 --cells 64 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
-tail -2 $OUT/${TAG}_ncu_full.log
-ls -la $OUT | tail -12
+echo "== pytest gpu"; timeout 1200 python -m pytest tests -m gpu -x -q 2>&1 | tail -8 | tee $OUT/${TAG}_pytest.txt
+echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3 | tee $OUT/${TAG}_smoke.txt
+echo "== bench reference arm"; timeout 900 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1 | tee $OUT/${TAG}_bench_reference.json
+echo "== bench"; timeout 900 python bench.py 2>&1 | tail -1 | tee $OUT/${TAG}_bench.json
+echo "== bench neohookean"; timeout 600 python bench.py --model neohookean --no-cpu-baseline 2>&1 | tail -1 | tee $OUT/${TAG}_bench_neo.json
+echo "== passes"; timeout 600 python scripts/time_passes.py 128 J2 2>&1 | tail -1 | tee $OUT/${TAG}_passes.json
+echo "== ncu launches (same command as the bench, 2 steps)"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
+  python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
+tail -1 $OUT/${TAG}_ncu_launches.log | cut -c1-120
+echo "== ncu full (both kernels of the Jacobian pass)"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"row_fold_sorted_kernel|elem_record_kernel" -s 2 -c 2 -f -o $OUT/${TAG}_prof \
+  python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
+tail -1 $OUT/${TAG}_ncu_full.log | cut -c1-120
+ls -la $OUT | grep ${TAG}

@@ -115,7 +115,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   unsigned long long pl = 0;
   gx::KParams P;
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
-  P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data(); P.fold_ord = c.fold_ord.data(); P.nblk_g = nullptr; P.fold_ld = c.fold_ld;
+  P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data(); P.fold_ord = c.fold_ord.data(); P.nblk_g = nullptr; P.fold_ld = c.fold_ld; P.node_order = c.node_order.data();
   P.state_in = sin.data(); P.fp_old = fpo.data(); P.state_out = sout.data();
   P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
