@@ -28,7 +28,8 @@ SYMBOLS = [
     "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
     "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
-    "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan",
+    "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
+    "gx_apply_dbcs",
 ]
 
 
@@ -94,6 +95,8 @@ def load_library():
     L.gx_stream.argtypes = [vp]
     L.gx_last_timing.argtypes = [vp, dp]
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.gx_functional_avg_disp.argtypes = [vp, dp, vp]
+    L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
     L.gx_num_peers.argtypes = [vp, ip]
     L.gx_struct_pack.argtypes = [vp, C.c_int, C.POINTER(vp), lp]
     L.gx_struct_unpack.argtypes = [vp, C.c_int, vp, C.c_int64]
@@ -263,6 +266,19 @@ class Assembler:
         self._ck(self.L.gx_element_error(self.h, _dp(u_err), _dp(p_err), None if parent is None else _ip(parent),
                                          n_parent, _dp(eta), None if etap is None else _dp(etap), C.byref(bound)))
         return eta, etap, bound.value
+
+    def avg_disp(self, with_dMdu=False):
+        """Functional "avg disp" of the current solution on the device (src/goal_avg_disp.cpp:17-21)."""
+        J = C.c_double()
+        d = np.zeros(4 * self.nn) if with_dMdu else None
+        self._ck(self.L.gx_functional_avg_disp(self.h, C.byref(J), _addr(d)))
+        return (J.value, d) if with_dMdu else J.value
+
+    def apply_dbcs(self, rows, g, with_jacobian):
+        """set_resid_dbcs / set_jac_dbcs on the device-resident result (src/goal_dbcs.cpp:39-99)."""
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        g = np.ascontiguousarray(g, dtype=np.float64)
+        self._ck(self.L.gx_apply_dbcs(self.h, len(rows), _ip(rows), _dp(g), int(with_jacobian)))
 
     def fetch(self, R=True, values=True):
         Rv = np.zeros(4 * self.nn) if R else None

@@ -128,6 +128,66 @@ __global__ void pack_err4_kernel(double4* err4, double const* ue, double const* 
   err4[n] = make_double4(ue[3 * (int64_t)n], ue[3 * (int64_t)n + 1], ue[3 * (int64_t)n + 2], pe[n]);
 }
 
+// AvgDisp (src/goal_avg_disp.cpp:17-21): per element (sum_i u_i(xi_c)) * vol / 3; block partials in fixed order
+__global__ void avg_disp_partial_kernel(double* partial, NodeRec const* nodes, int4 const* conn, int ne) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    int4 const cn = conn[e];
+    int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+    double x[4][3], us = 0.0;
+    for (int n = 0; n < 4; ++n) {
+      NodeRec const& r = nodes[nd[n]];
+      x[n][0] = r.x[0]; x[n][1] = r.x[1]; x[n][2] = r.x[2];
+      us += 0.25 * (r.u[0] + r.u[1] + r.u[2]);
+    }
+    double e1[3], e2[3], e3[3], c23[3];
+    for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; e3[j] = x[3][j] - x[0][j]; }
+    cross3(e2, e3, c23);
+    s += us * (dot3(e1, c23) * (1.0 / 6.0)) * (1.0 / 3.0);
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+// QoI<FADT>::scatter for avg disp: dMdu[(a,i)] = sum over incident elements of N_a w dv / 3 = vol/12, i = 0..2
+__global__ void avg_disp_dMdu_kernel(double* dMdu, NodeRec const* nodes, int4 const* conn, uint32_t const* adj_off,
+                                     int2 const* adj, int nn) {
+  int const a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nn) return;
+  double s = 0.0;
+  for (uint32_t k = adj_off[a]; k < adj_off[a + 1]; ++k) {
+    int4 const cn = conn[adj[k].x >> 2];
+    int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+    double x[4][3];
+    for (int n = 0; n < 4; ++n) { x[n][0] = nodes[nd[n]].x[0]; x[n][1] = nodes[nd[n]].x[1]; x[n][2] = nodes[nd[n]].x[2]; }
+    double e1[3], e2[3], e3[3], c23[3];
+    for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; e3[j] = x[3][j] - x[0][j]; }
+    cross3(e2, e3, c23);
+    s += 0.25 * (dot3(e1, c23) * (1.0 / 6.0)) * (1.0 / 3.0);
+  }
+  dMdu[4 * (int64_t)a] = s; dMdu[4 * (int64_t)a + 1] = s; dMdu[4 * (int64_t)a + 2] = s; dMdu[4 * (int64_t)a + 3] = 0.0;
+}
+// set_resid_dbcs / set_jac_dbcs (src/goal_dbcs.cpp:39-99): one warp per Dirichlet row
+__global__ void apply_dbcs_kernel(double* R, double* values, NodeRec const* nodes, uint8_t const* diag_pos,
+                                  int32_t const* rows, double const* g, int n, int with_jacobian) {
+  int const w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n) return;
+  int const row = rows[w], a = row >> 2, i = row & 3;
+  NodeRec const& r = nodes[a];
+  if (with_jacobian) {
+    int const rl = 4 * r.nblk;
+    double* v = values + 16 * (int64_t)r.blk0 + (int64_t)i * rl;
+    int const d = 4 * diag_pos[a] + i;
+    for (int c = lane; c < rl; c += 32) v[c] = c == d ? 1.0 : 0.0;
+  }
+  if (lane == 0) R[row] = (i < 3 ? r.u[i] : r.p) - g[w];
+}
+
 // ---------------------------------------------------------------------------
 template <int MODEL, int PASS, bool SAVE>
 static cudaError_t launch_colours(gx_ctx* ctx, KParams& P) {
@@ -327,7 +387,7 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
 static void free_device(gx_ctx* ctx) {
   if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord, ctx->d_node_order,
+  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord, ctx->d_node_order, ctx->d_diag_pos,
                   ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -402,6 +462,8 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj_off, sizeof(uint32_t) * (size_t)(nn + 1)));
     GX_CUDA(cudaMemcpy(ctx->d_adj_off, ctx->adj_off.data(), sizeof(uint32_t) * (size_t)(nn + 1), cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMalloc(&ctx->d_diag_pos, (size_t)nn));
+    GX_CUDA(cudaMemcpy(ctx->d_diag_pos, ctx->diag_pos.data(), (size_t)nn, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_node_order, sizeof(int32_t) * (size_t)nn));
     GX_CUDA(cudaMemcpy(ctx->d_node_order, ctx->node_order.data(), sizeof(int32_t) * (size_t)nn, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_fold_ord, sizeof(uint32_t) * std::max<size_t>(ctx->fold_ord.size(), 1)));
@@ -623,6 +685,45 @@ int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, cons
   if (eta_elem) GX_CUDA(cudaMemcpyAsync(eta_elem, d_eta, sizeof(double) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
   GX_CUDA(cudaFreeAsync(d_eta, ctx->stream));
   if (d_etap) GX_CUDA(cudaFreeAsync(d_etap, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_functional_avg_disp(gx_ctx* ctx, double* J, double* dMdu_out) {
+  if (!ctx || !J) { if (ctx) ctx->err = "gx_functional_avg_disp: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nb = std::min(1023, (ctx->ne + 255) / 256);
+  avg_disp_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, ctx->d_nodes, ctx->d_conn, ctx->ne);
+  bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaMemcpyAsync(J, ctx->d_red + 1023, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dMdu_out) {
+    avg_disp_dMdu_kernel<<<(ctx->nn + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_stage, ctx->d_nodes, ctx->d_conn, ctx->d_adj_off, ctx->d_adj, ctx->nn);
+    GX_CUDA(cudaGetLastError());
+    GX_CUDA(cudaMemcpyAsync(dMdu_out, ctx->d_stage, sizeof(double) * 4 * (size_t)ctx->nn, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, int with_jacobian) {
+  if (!ctx || n < 0 || (n > 0 && (!rows || !g))) { if (ctx) ctx->err = "gx_apply_dbcs: bad argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  if (!ctx->have_result || (with_jacobian && !ctx->have_values)) { ctx->err = "gx_apply_dbcs: no matching result on the device"; return GX_ERR_ARG; }
+  if (n == 0) return GX_OK;
+  for (int k = 0; k < n; ++k) {
+    if (rows[k] < 0 || rows[k] >= 4 * ctx->nn) { ctx->err = "gx_apply_dbcs: row out of range"; return GX_ERR_ARG; }
+    if (!ctx->node_owner.empty() && ctx->node_owner[rows[k] >> 2] != ctx->rank) { ctx->err = "gx_apply_dbcs: row is not owned by this rank"; return GX_ERR_ARG; }
+  }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  if ((int64_t)n * 2 > ctx->stage_len) { ctx->err = "gx_apply_dbcs: too many rows"; return GX_ERR_ARG; }
+  int32_t* d_rows = reinterpret_cast<int32_t*>(ctx->d_stage);
+  double* d_g = ctx->d_stage + (n + 1) / 2 + 1;
+  GX_CUDA(cudaMemcpyAsync(d_rows, rows, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(d_g, g, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+  apply_dbcs_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_R, ctx->d_values, ctx->d_nodes, ctx->d_diag_pos, d_rows, d_g, n, with_jacobian);
+  GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }

@@ -89,6 +89,7 @@ struct gx_ctx {
   // order in which stage B visits the nodes: Morton (Z-curve) order of the node coordinates, so that the four
   // incidences of an element are processed close in time and its tangent record is fetched from HBM once
   std::vector<int32_t> node_order;
+  std::vector<uint8_t> diag_pos;  // position of block (a,a) in node a's block row
   // ---- schedule
   int ncolors = 0;
   std::vector<int32_t> color_off;  // [ncolors+1] in device element order
@@ -106,6 +107,7 @@ struct gx_ctx {
   int2* d_adj = nullptr;
   uint32_t* d_fold_ord = nullptr;
   int32_t* d_node_order = nullptr;
+  uint8_t* d_diag_pos = nullptr;   // position of block (a,a) in node a's block row
   // history state, one record per element (user order):
   //   in    : Cp^{-1}[6] (of Fp_old, cached), eqps_old, pad   (64 B)  read by every incidence of the element
   //   fp_old: Fp_old[9]                                       (72 B)  read only when a plastic element saves Fp

@@ -159,6 +159,15 @@ int build_graph_and_schedule(gx_ctx* c) {
     }
   }
 
+  // ---- diagonal block position per node (Dirichlet rows put their 1 there)
+  c->diag_pos.assign(nn, 0);
+#pragma omp parallel for schedule(static)
+  for (int a = 0; a < nn; ++a) {
+    int32_t const* b = c->ncol.data() + c->nrow[a];
+    int32_t const* e = c->ncol.data() + c->nrow[a + 1];
+    c->diag_pos[a] = (uint8_t)(std::lower_bound(b, e, a) - b);
+  }
+
   // ---- stage B node order: Z-curve over the bounding box (10 bits per axis), ties by node id
   {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};

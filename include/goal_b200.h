@@ -131,6 +131,17 @@ int gx_element_error(gx_ctx* ctx, const double* u_err /*[n_nodes*3]*/, const dou
                      const int32_t* parent /*[n_elems]*/, int32_t n_parent, double* eta_elem /*[n_elems]*/,
                      double* eta_parent /*[n_parent]*/, double* bound);
 
+/* ---- "next" rows of SURVEY.md 8(f): what sits either side of the assembly in the same drivers ---------------
+ * Functional "avg disp" (Functional::compute src/goal_functional.cpp:62-70, AvgDisp src/goal_avg_disp.cpp:17-21):
+ *   *J = sum over this part's elements of (sum_i u_i(xi_c)) w dv / 3   (PCU_Add across parts: gx_allreduce_sum)
+ * dMdu_out ([4*n_nodes], ghost layout, may be NULL) receives what QoI<FADT>::scatter adds (src/goal_qoi.cpp:63-76). */
+int gx_functional_avg_disp(gx_ctx* ctx, double* J, double* dMdu_out);
+/* Dirichlet rows on the device-resident result of the last compute call (set_resid_dbcs / set_jac_dbcs,
+ * src/goal_dbcs.cpp:39-99): for each listed ghost-local dof row (which must be owned by this rank):
+ * R[row] = solution - g; with_jacobian != 0 additionally zeroes the CRS row and puts 1 on the diagonal.
+ * As in the reference this runs after the interface reduction and does not eliminate columns. */
+int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, int with_jacobian);
+
 /* ---- mesh parts ------------------------------------------------------------------------------
  * Structure exchange == the owned_graph Export/INSERT of Disc::compute_graphs (src/goal_disc.cpp:327-329):
  * once after gx_create on a partitioned context, every rank sends peer p the blob of gx_struct_pack(p),

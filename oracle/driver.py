@@ -32,8 +32,10 @@ def _traction_rhs(coords, sides, traction):
     return out
 
 
-def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_iters=5, log=None):
+def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_iters=5, log=None, device_bcs=False):
     """dbcs: [(eq, node_ids, g(t))]; tbcs: [(side_tris, T(t) -> 3-vector)].
+    device_bcs: apply the Dirichlet rows with asm.apply_dbcs (the CUDA path's gx_apply_dbcs) instead of on the host;
+    only valid without traction BCs (those are added to the ghost R on the host before the Dirichlet rows).
 
     Returns dict(J=[per-step functional], newton=[iterations], plastic=[count at end of step]).
     """
@@ -58,24 +60,37 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
         it, converged = 1, False
         while it <= max_iters and not converged:
             asm.set_solution(u, p)
-            R, vals = asm.jacobian(save=True)
-            R = np.array(R, copy=True)
-            vals = np.array(vals, copy=True)
-            apply_tbcs(R, t_now)
-            for row, r in dbc_rows(t_now):
-                R[row] = r
-                vals[rowptr[row]:rowptr[row + 1]] = 0.0
-                k = rowptr[row] + np.searchsorted(colind[rowptr[row]:rowptr[row + 1]], row)
-                vals[k] = 1.0
+            if device_bcs:
+                assert not tbcs
+                asm.jacobian(save=True, out=False)
+                rows_g = [(4 * n + eq, g(t_now)) for eq, nodes, g in dbcs for n in nodes]
+                asm.apply_dbcs([r for r, _ in rows_g], [v for _, v in rows_g], True)
+                R, vals = asm.fetch()
+            else:
+                R, vals = asm.jacobian(save=True)
+                R = np.array(R, copy=True)
+                vals = np.array(vals, copy=True)
+                apply_tbcs(R, t_now)
+                for row, r in dbc_rows(t_now):
+                    R[row] = r
+                    vals[rowptr[row]:rowptr[row + 1]] = 0.0
+                    k = rowptr[row] + np.searchsorted(colind[rowptr[row]:rowptr[row + 1]], row)
+                    vals[k] = 1.0
             A = sp.csr_matrix((vals, colind, rowptr), shape=(4 * nn, 4 * nn))
             du = spla.spsolve(A.tocsc(), -R).reshape(nn, 4)
             u += du[:, :3]
             p += du[:, 3]
             asm.set_solution(u, p)
-            R = np.array(asm.residual(save=True), copy=True)
-            apply_tbcs(R, t_now)
-            for row, r in dbc_rows(t_now):
-                R[row] = r
+            if device_bcs:
+                asm.residual(save=True, out=False)
+                rows_g = [(4 * n + eq, g(t_now)) for eq, nodes, g in dbcs for n in nodes]
+                asm.apply_dbcs([r for r, _ in rows_g], [v for _, v in rows_g], False)
+                R = asm.fetch(values=False)[0]
+            else:
+                R = np.array(asm.residual(save=True), copy=True)
+                apply_tbcs(R, t_now)
+                for row, r in dbc_rows(t_now):
+                    R[row] = r
             nrm = np.linalg.norm(R)
             if log:
                 log(f"step {step + 1} newton {it} ||R|| = {nrm:.3e}")

@@ -138,6 +138,31 @@ def test_error_localisation_parity(cube, model):
     a.close()
 
 
+def test_functional_and_device_dbcs(cube):
+    """'next' rows: avg-disp functional + dMdu (src/goal_avg_disp.cpp, goal_qoi.cpp:63-76) and Dirichlet rows
+    (src/goal_dbcs.cpp:39-99) on the device against the oracle / the host construction."""
+    import goal_b200
+    co, cn = kuhn_cube(6)
+    f = fields(co, len(cn), strain=0.004)
+    a, o = _pair(co, cn, "J2", f)
+    J, d = a.avg_disp(with_dMdu=True)
+    Jo, do = o.avg_disp(with_dMdu=True)
+    assert abs(J - Jo) < 1e-13 * abs(Jo) and relerr(d, do) < 1e-13
+    R, A = [x.copy() for x in a.jacobian(goal_b200.PRIMAL, save=False)]
+    rows = np.array([4 * n + eq for eq in (0, 2, 3) for n in range(0, a.nn, 7)], dtype=np.int32)
+    g = np.linspace(-1, 1, len(rows))
+    a.apply_dbcs(rows, g, True)
+    R2, A2 = a.fetch()
+    sol = np.concatenate([f["u"], f["p"][:, None]], 1).reshape(-1)
+    for k, row in enumerate(rows):
+        lo, hi = a.rowptr[row], a.rowptr[row + 1]
+        want = (a.colind[lo:hi] == row).astype(float)
+        assert np.array_equal(A2[lo:hi], want) and R2[row] == sol[row] - g[k]
+        A[lo:hi] = want; R[row] = sol[row] - g[k]
+    assert np.array_equal(A, A2) and np.array_equal(R, R2)  # every other row untouched
+    a.close()
+
+
 def test_bitwise_determinism(cube):
     """No atomics on the data path: repeated passes give identical bits."""
     import goal_b200
@@ -176,6 +201,12 @@ def test_reference_goldens_through_gpu_path(cube, name):
 
     dbcs, tbcs = driver.golden_case(name, cube)
     r = driver.run_primal(WithFunctional(), co, dbcs, tbcs)
+    if not tbcs:
+        # same run with the Dirichlet rows (gx_apply_dbcs) and the functional (gx_functional_avg_disp) on the device
+        a2 = goal_b200.Assembler(cube["coords"], cube["tets"], model, [MATERIAL])
+        r2 = driver.run_primal(a2, co, dbcs, tbcs, device_bcs=True)
+        assert np.abs(np.array(r2["J"]) - np.array(r["J"])).max() < 1e-13 and r2["newton"] == r["newton"]
+        a2.close()
     assert abs(r["J"][-1] - J_gold) < 1e-12
     for got, want in zip(r["J"], driver.GOLDEN_STEPS[name]):
         assert abs(got - want) < 1e-12
