@@ -29,7 +29,7 @@ SYMBOLS = [
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
     "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
-    "gx_apply_dbcs",
+    "gx_apply_dbcs", "gx_node_graph",
 ]
 
 
@@ -71,6 +71,7 @@ def load_library():
     L.gx_last_error.argtypes = [vp]
     L.gx_graph.argtypes = [vp, lp, C.POINTER(lp), C.POINTER(ip)]
     L.gx_graph_size.argtypes = [vp, lp, ip]
+    L.gx_node_graph.argtypes = [vp, C.POINTER(lp), C.POINTER(ip)]
     L.gx_scatter_map.argtypes = [vp, C.POINTER(C.c_uint8)]
     L.gx_set_solution.argtypes = [vp, vp, vp]
     L.gx_get_state.argtypes = [vp, C.c_char_p, dp]
@@ -202,6 +203,19 @@ class Assembler:
     def colind(self):
         self._graph()
         return self._colind
+
+    def node_graph(self):
+        """(nrow [Nn+1] int64, ncol [nblocks] int32): zero-copy views of the library's block-CRS graph."""
+        nr, nc = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        self._ck(self.L.gx_node_graph(self.h, C.byref(nr), C.byref(nc)))
+        nrow = np.ctypeslib.as_array(nr, (self.nn + 1,))
+        return nrow, np.ctypeslib.as_array(nc, (int(nrow[-1]),))
+
+    def result_dev(self):
+        """device addresses (ints) of R and of the CRS values of the last compute call."""
+        r, v = C.c_void_p(), C.c_void_p()
+        self._ck(self.L.gx_result_dev(self.h, C.byref(r), C.byref(v)))
+        return r.value, v.value
 
     def scatter_map(self):
         b = np.zeros((self.ne, 16), dtype=np.uint8)

@@ -529,6 +529,13 @@ int gx_graph_size(gx_ctx* ctx, int64_t* nnz, int32_t* n_rows) {
   return GX_OK;
 }
 
+int gx_node_graph(gx_ctx* ctx, const int64_t** nrow, const int32_t** ncol) {
+  if (!ctx) return GX_ERR_ARG;
+  if (nrow) *nrow = ctx->nrow.data();
+  if (ncol) *ncol = ctx->ncol.data();
+  return GX_OK;
+}
+
 int gx_scatter_map(gx_ctx* ctx, uint8_t* bpos) {
   if (!ctx || !bpos) return GX_ERR_ARG;
   memcpy(bpos, ctx->bpos.data(), ctx->bpos.size());

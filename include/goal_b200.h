@@ -95,6 +95,9 @@ const char* gx_last_error(const gx_ctx* ctx); /* never NULL; ctx may be NULL for
 int gx_graph(gx_ctx* ctx, int64_t* nnz, const int64_t** rowptr /*[4*n_nodes+1]*/, const int32_t** colind /*[nnz]*/);
 /* Same graph without materialising colind (nnz and rowptr only). */
 int gx_graph_size(gx_ctx* ctx, int64_t* nnz, int32_t* n_rows);
+/* The node-level form the library stores: block row offsets [n_nodes+1] and the neighbour node of every 4x4 block,
+ * sorted per row.  dof row 4a+i starts at 16*nrow[a] + i*4*(nrow[a+1]-nrow[a]); its columns are 4*ncol[..]+k. */
+int gx_node_graph(gx_ctx* ctx, const int64_t** nrow, const int32_t** ncol);
 
 /* Element -> nonzero scatter map (what sumIntoLocalValues searches for on every call,
  * src/goal_displacement.cpp:191): for element e, local nodes (n,m), the position of the
