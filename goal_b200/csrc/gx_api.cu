@@ -286,6 +286,22 @@ static cudaError_t launch_two_stage(gx_ctx* ctx, KParams& P, int pass, bool save
   return cudaGetLastError();
 }
 
+// gather form of the residual / error-localisation passes
+template <int MODEL>
+static cudaError_t launch_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
+  int const ne = ctx->ne, nb = (ne + 127) / 128;
+  double* rvec = ctx->d_elemrec;  // [ne][16] fits inside the tangent-record buffer
+  if (pass == PASS_ERROR) elem_residual_kernel<MODEL, false, true><<<nb, 128, 0, ctx->stream>>>(P, rvec, ne);
+  else if (save) elem_residual_kernel<MODEL, true, false><<<nb, 128, 0, ctx->stream>>>(P, rvec, ne);
+  else elem_residual_kernel<MODEL, false, false><<<nb, 128, 0, ctx->stream>>>(P, rvec, ne);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  node_gather_kernel<<<(ctx->nn + 255) / 256, 256, 0, ctx->stream>>>(P, rvec);
+  ctx->launches++;
+  return cudaGetLastError();
+}
+
 template <int MODEL>
 static cudaError_t launch_row_owner_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
   if (pass == PASS_JACOBIAN) return save ? launch_row_owner<MODEL, false, true>(ctx, P) : launch_row_owner<MODEL, false, false>(ctx, P);
@@ -314,9 +330,10 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   bool const row_owner = with_values && ctx->opt_kernel != 1 &&
                          row_owner_smem(ctx, (int)ctx->opt_row_warps) <= 200 * 1024;
   bool const two_stage = row_owner && ctx->opt_kernel == 0;
-  if (two_stage && !ctx->d_elemrec)
+  bool const gather = !with_values && ctx->opt_kernel != 1;
+  if ((two_stage || gather) && !ctx->d_elemrec)
     GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
-  if (!row_owner) {
+  if (!row_owner && !gather) {
     // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The row-owner schedule writes every
     // entry of R and of the CRS values exactly once, so it needs no zeroing pass.
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
@@ -326,7 +343,9 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   KParams P;
   fill_params(ctx, P);
   cudaError_t le;
-  if (two_stage)
+  if (gather)
+    le = ctx->model == GX_MODEL_J2 ? launch_gather<MODEL_J2>(ctx, P, pass, save) : launch_gather<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
+  else if (two_stage)
     le = ctx->model == GX_MODEL_J2 ? launch_two_stage<MODEL_J2>(ctx, P, pass, save)
                                    : launch_two_stage<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   else if (row_owner)

@@ -21,7 +21,9 @@
 //      (a, e).  Each lane evaluates its element and the four 4x4 blocks of node a's rows, the warp
 //      sums them per target block through shared memory in a fixed order and writes node a's four
 //      CRS rows exactly once, fully coalesced.  No zeroing pass, no read-modify-write traffic.
-//  (2) coloured elements (residual / error-localisation passes, Jacobian fallback): one thread per
+//  (2) gather form of the residual / error-localisation passes (default): element residual vectors, then one
+//      thread per node sums its incidences.
+//  (3) coloured elements (fallback for every pass, gx_set_option("kernel", 1)): one thread per
 //      element, launches cover one colour (no two elements of a colour share a node), plain
 //      read-modify-write into R / values.
 //
@@ -806,6 +808,75 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
     a = ap; o0 = p0; o1 = p1; ad = adp;
     ap = aq; p0 = q0; p1 = q1; adp = adq;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Residual and error-localisation passes, gather form (default): no colouring, no zeroing, no atomics.
+//   elem_residual_kernel : one thread per element -> its 16 residual entries rvec[e][n][4] (128 B, one line),
+//                          state save as in stage A of the Jacobian pass.  ERROR selects the adjoint-weighted
+//                          residual of the error chain (goal_mechanics.cpp:169-218).
+//   node_gather_kernel   : one thread per node, sums rvec[e][n] over the node's incidences in ascending
+//                          element order and writes R[4a .. 4a+3] once.
+// ---------------------------------------------------------------------------
+template <int MODEL, bool SAVE, bool ERROR>
+__global__ void __launch_bounds__(128) elem_residual_kernel(const __grid_constant__ KParams P, double* __restrict__ rvec, int ne) {
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  int plastic = 0;
+  if (e < ne) {
+    int nd[4], b0[4], nb[4];
+    Material const* matp;
+    Core<double> c;
+    int const rc = load_and_update<MODEL, SAVE>(P, e, true, nd, b0, nb, matp, c);
+    double ru[12], rp[4];
+    if (rc != ERR_NONE) {
+      report_error(P.err, rc, e);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) ru[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rp[k] = 0.0;
+    } else {
+      plastic = c.plastic;
+      if (ERROR) {
+        double zu[4][3], zp[4], zpc[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          double2 const* q = reinterpret_cast<double2 const*>(P.z + nd[n]);
+          double2 const a = ldg(q), b = ldg(q + 1), d = ldg(q + 2);
+          zu[n][0] = a.x; zu[n][1] = a.y; zu[n][2] = b.x; zp[n] = b.y; zpc[n] = d.x;
+        }
+        element_error_residual(c, zu, zp, zpc, ru, rp);
+      } else {
+        element_residual(c, ru, rp);
+      }
+      if (SAVE && MODEL == MODEL_J2 && c.plastic) save_plastic_Fp(P, e, c.dN);
+    }
+    double2* o = reinterpret_cast<double2*>(rvec + 16 * (int64_t)e);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      o[2 * n] = make_double2(ru[3 * n], ru[3 * n + 1]);
+      o[2 * n + 1] = make_double2(ru[3 * n + 2], rp[n]);
+    }
+  }
+  if (MODEL == MODEL_J2) {
+    unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(P.plastic, (unsigned long long)__popc(b));
+  }
+}
+
+__global__ void __launch_bounds__(256) node_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rvec) {
+  int const a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= P.nn) return;
+  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
+  double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
+  for (uint32_t k = o0; k < o1; ++k) {
+    int const en = __ldg(P.adj + k).x;  // e*4 + n: rvec is [e][n][4]
+    double2 const* q = reinterpret_cast<double2 const*>(rvec + 4 * (int64_t)en);
+    double2 const v0 = __ldg(q), v1 = __ldg(q + 1);
+    r0 += v0.x; r1 += v0.y; r2 += v1.x; r3 += v1.y;
+  }
+  double2* out = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
+  out[0] = make_double2(r0, r1);
+  out[1] = make_double2(r2, r3);
 }
 #endif
 

@@ -104,6 +104,10 @@ def test_kernel_variants_parity(cube, mesh, opts):
     R1, A1 = [x.copy() for x in a.jacobian(goal_b200.PRIMAL, save=False)]
     R2, A2 = a.jacobian(goal_b200.PRIMAL, save=False)
     assert np.array_equal(R1, R2) and np.array_equal(A1, A2)  # bit-reproducible
+    # residual and error-localisation passes under the same option (kernel=1: coloured, otherwise gather form)
+    assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12
+    assert relerr(a.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"]),
+                  o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])) < 1e-12
     a.close()
 
 
