@@ -334,6 +334,8 @@ int gx_struct_finalize(gx_ctx* ctx) {
     }
   }
   ctx->nrow_x.assign(nn + 1, 0);
+  ctx->block_lists_built = false;
+  ctx->patch_state = 0;
   for (int a = 0; a < nn; ++a) {
     auto& ph = phantom[a];
     std::sort(ph.begin(), ph.end());

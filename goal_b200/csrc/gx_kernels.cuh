@@ -66,6 +66,13 @@ struct KParams {
 
 enum { PASS_RESIDUAL = 0, PASS_JACOBIAN = 1, PASS_JACOBIAN_T = 2, PASS_ERROR = 3 };
 
+#if defined(__CUDACC__)
+// one 32 B sector per lane (sm_100: LDG.E.256)
+__device__ __forceinline__ void ldg256(double const* p, double* o) {
+  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
+}
+#endif
+
 template <class T> GX_HD T ldg(T const* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
@@ -710,27 +717,18 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
         Core<double> c;  // only the tangent fields are filled
         double wv[4][3], rv[4][3];
         {
-          double2 v[12];
+          // the 448 B record as 14 sector-sized (256-bit) loads: the lanes of a warp read 32 different records, so the
+          // L1 data pipe spends one wavefront per lane and load instruction whatever its width
+          double f[56];
 #pragma unroll
-          for (int k = 0; k < 12; ++k) v[k] = __ldg(q + k);
+          for (int k = 0; k < 14; ++k) ldg256(reinterpret_cast<double const*>(q) + 4 * k, f + 4 * k);
 #pragma unroll
-          for (int k = 0; k < 6; ++k) {
-            (&wv[0][0])[2 * k] = v[k].x; (&wv[0][0])[2 * k + 1] = v[k].y;
-            (&rv[0][0])[2 * k] = v[6 + k].x; (&rv[0][0])[2 * k + 1] = v[6 + k].y;
-          }
+          for (int k = 0; k < 12; ++k) { (&wv[0][0])[k] = f[k]; (&rv[0][0])[k] = f[12 + k]; }
+#pragma unroll
+          for (int k = 0; k < 6; ++k) { c.Tv[k] = f[24 + k]; c.Gm[k] = f[30 + k]; c.s[k] = f[36 + k]; }
+          c.q[0] = f[42]; c.q[1] = f[43]; c.q[2] = f[44]; c.gwv = f[45]; c.A1v = f[46]; c.Jpv = f[47];
+          c.upc = f[48]; c.va = f[49]; c.tjv = f[50]; c.ppc = f[51]; c.rb = f[52];
         }
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
-          v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
-          v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
-        }
-        double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
-        v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
-        v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
-        v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
-        v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
-        v = __ldg(q + 26); c.rb = v.x;
         double wn[3], rn3[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -808,6 +806,295 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
     a = ap; o0 = p0; o1 = p1; ad = adp;
     ap = aq; p0 = q0; p1 = q1; adp = adq;
   }
+}
+
+// ---------------------------------------------------------------------------
+// Schedule (1c), gather form of the Jacobian pass (KParams-level option kernel = 3): stage A as above, then
+//   block_gather_kernel : one thread per off-diagonal 4x4 block of the operator.  The thread walks the block's
+//            contribution list (the elements containing that mesh edge, ascending), rebuilds each element's
+//            block from the tangent record, accumulates the 16 entries in registers and writes them once.
+//            No shared memory, no cross-thread traffic; neighbouring threads own neighbouring blocks of one
+//            block row, so they read the same records (L1) and their stores coalesce.
+//   diag_gather_kernel  : one warp per node, one lane per incidence: the diagonal block (as many contributions
+//            as the node has elements) and the node's four residual entries, summed across lanes through a
+//            shared-memory transpose in a fixed order.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void load_tangent_scalars(double2 const* __restrict__ q, Core<double>& c) {
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
+    v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
+    v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
+  }
+  double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
+  v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
+  v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
+  v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
+  v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
+  v = __ldg(q + 26); c.rb = v.x;
+}
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(128) block_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+                                                           uint32_t const* __restrict__ blk_row, uint32_t const* __restrict__ bc_off,
+                                                           int32_t const* __restrict__ bc, int64_t nblocks) {
+  int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nblocks) return;
+  uint32_t const ra = __ldg(blk_row + t);
+  if (ra & 0x80000000u) return;  // diagonal block: diag_gather_kernel
+  int const a = (int)ra;
+  int blk0a, nblka;
+  {
+    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
+    blk0a = __double2loint(d3.y);
+    nblka = __double2hiint(d3.y);
+  }
+  uint32_t const c0 = __ldg(bc_off + t), c1 = __ldg(bc_off + t + 1);
+  double acc[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  for (uint32_t ci = c0; ci < c1; ++ci) {
+    int const ent = __ldg(bc + ci);
+    int const e = ent >> 4, n = (ent >> 2) & 3, m = ent & 3;
+    double const* rp = rec + (int64_t)ELEM_REC * e;
+    Core<double> c;  // only the tangent fields are filled
+    load_tangent_scalars(reinterpret_cast<double2 const*>(rp), c);
+    // row node = the node of this block row in the primal operator; roles swap for the transpose
+    int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
+    double wr[3], wc[3], rc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      wr[k] = __ldg(rp + 3 * nr + k);
+      wc[k] = __ldg(rp + 3 * nc + k);
+      rc[k] = __ldg(rp + 12 + 3 * nc + k);
+    }
+    RowNode<double> rown;
+    ColNode<double> coln;
+    row_node(c, wr, rown);
+    column_node(c, wc, rc, coln);
+    double blk[16];
+    jacobian_block(c, rown, coln, blk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc[4 * i + k] += TRANSPOSE ? blk[4 * k + i] : blk[4 * i + k];
+  }
+  int const j = (int)(t - blk0a);
+  double* out = P.values + 16 * (int64_t)blk0a + 4 * j;
+  int const rl = 4 * nblka;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    double2* o = reinterpret_cast<double2*>(out + (int64_t)i * rl);
+    o[0] = make_double2(acc[4 * i], acc[4 * i + 1]);
+    o[1] = make_double2(acc[4 * i + 2], acc[4 * i + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Schedule (1d), patch gather (option kernel = 4): stage A as above, then one thread block per patch of the
+// precomputed patch schedule (build_patch_schedule, gx_setup.cpp).  The block stages the records of the patch's
+// elements in shared memory with coalesced asynchronous copies (every record crosses the L1 data pipe once per
+// patch instead of once per incident node and lane), then every thread runs one work item: up to 8 contributions to
+// one 4x4 block, rebuilt from the staged records and accumulated in registers.  Blocks with more contributions
+// are finished by their primary item from the secondaries' partial sums (fixed order).  Every block of the patch's
+// rows, and the rows' residual entries, are written exactly once.
+// ---------------------------------------------------------------------------
+constexpr int PATCH_REC_LD = 58;  // doubles between staged records: 464 B = 29 x 16 B, conflict-free 128-bit reads
+GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double) + PATCH_RECS * sizeof(int32_t); }
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(PATCH_THREADS, 3) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+                                                                        uint32_t const* __restrict__ sched) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* srec = reinterpret_cast<double*>(smem_raw);
+  int32_t* selem = reinterpret_cast<int32_t*>(smem_raw + (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double));
+  int const tid = threadIdx.x;
+  uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
+  int const n_recs = (int)__ldg(w);
+  selem[tid] = (int32_t)__ldg(w + 4 + tid);
+  uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
+  uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
+  __syncthreads();
+  {
+    uint32_t const sbase = (uint32_t)__cvta_generic_to_shared(srec);
+    int const total = n_recs * 28;  // 16-byte pieces
+    for (int u = tid; u < total; u += PATCH_THREADS) {
+      int const r = u / 28, piece = u - 28 * r;
+      char const* src = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * selem[r]) + 16 * piece;
+      uint32_t const dst = sbase + (uint32_t)(r * (PATCH_REC_LD * 8) + 16 * piece);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  int const kind = (int)(ot.z >> 30);
+  bool const diag = (ot.w & 0x80000000u) != 0;
+  double acc[16], r4[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  uint64_t elo = (uint64_t)it.x | ((uint64_t)it.y << 32), ehi = (uint64_t)it.z | ((uint64_t)it.w << 32);
+#pragma unroll 1
+  for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
+    uint32_t const ent = (uint32_t)elo & 0xffffu;
+    elo = (elo >> 16) | (ehi << 48); ehi >>= 16;
+    if (!(ent & 0x8000u)) break;
+    int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
+    double const* rp = srec + slot * PATCH_REC_LD;
+    Core<double> c;  // only the tangent fields are filled
+    {
+      double2 const* q = reinterpret_cast<double2 const*>(rp);
+#pragma unroll
+      for (int j = 0; j < 3; ++j) {
+        double2 v = q[12 + j]; c.Tv[2 * j] = v.x; c.Tv[2 * j + 1] = v.y;
+        v = q[15 + j]; c.Gm[2 * j] = v.x; c.Gm[2 * j + 1] = v.y;
+        v = q[18 + j]; c.s[2 * j] = v.x; c.s[2 * j + 1] = v.y;
+      }
+      double2 v = q[21]; c.q[0] = v.x; c.q[1] = v.y;
+      v = q[22]; c.q[2] = v.x; c.gwv = v.y;
+      v = q[23]; c.A1v = v.x; c.Jpv = v.y;
+      v = q[24]; c.upc = v.x; c.va = v.y;
+      v = q[25]; c.tjv = v.x; c.ppc = v.y;
+      c.rb = rp[52];
+    }
+    // row node = the node of this block row in the primal operator; roles swap for the transpose
+    int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
+    double wr[3], wc[3], rc[3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      wr[j] = rp[3 * nr + j];
+      wc[j] = rp[3 * nc + j];
+      rc[j] = rp[12 + 3 * nc + j];
+    }
+    RowNode<double> rown;
+    ColNode<double> coln;
+    row_node(c, wr, rown);
+    column_node(c, wc, rc, coln);
+    double blk[16];
+    jacobian_block(c, rown, coln, blk);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[4 * i + j] += TRANSPOSE ? blk[4 * j + i] : blk[4 * i + j];
+    if (diag) {  // n == m: the residual entries of the node
+      double t4[4];
+      element_residual_row(c, wr, t4);
+      r4[0] += t4[0]; r4[1] += t4[1]; r4[2] += t4[2]; r4[3] += t4[3];
+    }
+  }
+  __syncthreads();  // records are dead: their storage now carries the secondaries' partial sums, 20 doubles each
+  int const part = (int)((ot.z >> 16) & 0xffu);
+  if (kind == 2) {
+    double2* d = reinterpret_cast<double2*>(srec + 20 * part);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+    d[8] = make_double2(r4[0], r4[1]);
+    d[9] = make_double2(r4[2], r4[3]);
+  }
+  __syncthreads();
+  if (kind == 1) {
+    int const nsec = (int)((ot.z >> 24) & 0x3fu);
+    for (int s = 0; s < nsec; ++s) {
+      double2 const* d = reinterpret_cast<double2 const*>(srec + 20 * (part + s));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { double2 const v = d[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
+      if (diag) {
+        double2 v = d[8]; r4[0] += v.x; r4[1] += v.y;
+        v = d[9]; r4[2] += v.x; r4[3] += v.y;
+      }
+    }
+    int64_t const voff = (int64_t)(((uint64_t)ot.y << 32) | (uint64_t)ot.x);
+    int const rl = (int)(ot.z & 0xffffu);
+    double* out = P.values + voff;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      double2* o = reinterpret_cast<double2*>(out + (int64_t)i * rl);
+      o[0] = make_double2(acc[4 * i], acc[4 * i + 1]);
+      o[1] = make_double2(acc[4 * i + 2], acc[4 * i + 3]);
+    }
+    if (diag) {
+      double2* o = reinterpret_cast<double2*>(P.R + 4 * (int64_t)(ot.w & 0x7fffffffu));
+      o[0] = make_double2(r4[0], r4[1]);
+      o[1] = make_double2(r4[2], r4[3]);
+    }
+  }
+}
+
+constexpr int DIAG_LD = 33;
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(128) diag_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+                                                          uint8_t const* __restrict__ diag_pos) {
+  __shared__ double sm[4][20 * DIAG_LD];
+  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const slot = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (slot >= P.nn) return;
+  double* stg = sm[wib];
+  int const a = __ldg(P.node_order + slot);
+  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
+  int blk0a, nblka;
+  {
+    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
+    blk0a = __double2loint(d3.y);
+    nblka = __double2hiint(d3.y);
+  }
+  int const t16 = lane & 15, half = lane >> 4;
+  int const ri = lane & 3, rg = lane >> 2;
+  double tot = 0.0, rtot = 0.0;
+  for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
+    double blk[16], r4[4];
+    if (r0 + lane < o1) {
+      int2 const ad = __ldg(P.adj + r0 + lane);
+      int const e = ad.x >> 2, n = ad.x & 3;
+      double const* rp = rec + (int64_t)ELEM_REC * e;
+      Core<double> c;
+      load_tangent_scalars(reinterpret_cast<double2 const*>(rp), c);
+      double wn[3], rn3[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { wn[k] = __ldg(rp + 3 * n + k); rn3[k] = __ldg(rp + 12 + 3 * n + k); }
+      element_residual_row(c, wn, r4);
+      RowNode<double> rown;
+      ColNode<double> coln;
+      row_node(c, wn, rown);
+      column_node(c, wn, rn3, coln);
+      jacobian_block(c, rown, coln, blk);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) blk[k] = 0.0;
+      r4[0] = r4[1] = r4[2] = r4[3] = 0.0;
+    }
+    if (r0 != o0) __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) stg[(4 * i + k) * DIAG_LD + lane] = TRANSPOSE ? blk[4 * k + i] : blk[4 * i + k];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) stg[(16 + i) * DIAG_LD + lane] = r4[i];
+    __syncwarp();
+    // entry t16 of the block: each half-warp sums 16 lanes' values, the halves are joined by one shuffle
+    {
+      double const* src = stg + t16 * DIAG_LD + 16 * half;
+      double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < 16; l += 2) { s0 += src[l]; s1 += src[l + 1]; }
+      double s = s0 + s1;
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      tot += s;
+    }
+    // residual entry ri: eight groups of four lanes, joined by a butterfly over the groups
+    {
+      double const* src = stg + (16 + ri) * DIAG_LD + 4 * rg;
+      double s = (src[0] + src[1]) + (src[2] + src[3]);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      rtot += s;
+    }
+  }
+  if (lane < 16) {
+    int const dj = __ldg(diag_pos + a);
+    P.values[16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + 4 * dj + (t16 & 3)] = tot;
+  }
+  if (lane < 4) P.R[4 * (int64_t)a + lane] = rtot;
 }
 
 // ---------------------------------------------------------------------------

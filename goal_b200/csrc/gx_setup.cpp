@@ -230,6 +230,164 @@ int build_graph_and_schedule(gx_ctx* c) {
   return GX_OK;
 }
 
+// Contribution lists of the gather-form Jacobian pass, on the extended block rows (nrow_x): local blocks keep their
+// positions, phantom blocks (partitioned contexts) follow and receive nothing locally.
+void build_block_lists(gx_ctx* c) {
+  int const nn = c->nn;
+  std::vector<int64_t> const& nx = c->nrow_x;
+  size_t const nblocks = (size_t)nx[nn];
+  c->blk_row.assign(nblocks, 0u);
+  c->bc_off.assign(nblocks + 1, 0u);
+#pragma omp parallel for schedule(static)
+  for (int a = 0; a < nn; ++a) {
+    for (int64_t t = nx[a]; t < nx[a + 1]; ++t) c->blk_row[t] = (uint32_t)a;
+    c->blk_row[nx[a] + c->diag_pos[a]] |= 0x80000000u;
+    for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
+      uint32_t const jp = (uint32_t)c->adj[k].y;
+      for (int m = 0; m < 4; ++m) c->bc_off[nx[a] + ((jp >> (8 * m)) & 0xffu) + 1]++;  // blocks of one row: no races
+    }
+  }
+  for (size_t t = 0; t < nblocks; ++t) c->bc_off[t + 1] += c->bc_off[t];
+  c->bc.assign(c->bc_off[nblocks], 0);
+#pragma omp parallel
+  {
+    std::vector<uint32_t> cur;
+#pragma omp for schedule(static)
+    for (int a = 0; a < nn; ++a) {
+      cur.assign(c->bc_off.begin() + nx[a], c->bc_off.begin() + nx[a + 1]);
+      for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {  // incidences are in ascending element order
+        int const en = c->adj[k].x;                                    // e*4 + n
+        uint32_t const jp = (uint32_t)c->adj[k].y;
+        for (int m = 0; m < 4; ++m) c->bc[cur[(jp >> (8 * m)) & 0xffu]++] = (int32_t)(4 * en + m);
+      }
+    }
+  }
+  c->block_lists_built = true;
+}
+
+// Patch schedule of the patch-gather Jacobian pass.  A patch is a run of nodes of the Z-curve visiting order whose
+// incident elements (at most PATCH_RECS) are staged once in shared memory by one thread block.  The patch's work is
+// cut into items of at most PATCH_ITEM_LEN contributions to one 4x4 block; a block with more contributions (the
+// diagonal block, edges of high valence) has one primary item and secondaries whose partial sums the primary adds
+// in a fixed order.  Layout per patch (uint32 words, PATCH_WORDS):
+//   [0..3]   n_recs, n_items, 0, 0
+//   [4..]    elems[PATCH_RECS]                      element id of each staged record
+//   then     items[PATCH_THREADS][4]                8 x 16-bit contributions: slot | n << 8 | m << 10 | 0x8000
+//   then     outs[PATCH_THREADS][4]                 x,y = value offset of block entry (0,0) (int64, doubles)
+//                                                   z = row stride | part slot << 16 | n secondaries << 24 | kind << 30
+//                                                   w = node id | diagonal << 31
+//            kind: 0 idle thread, 1 primary, 2 secondary
+bool build_patch_schedule(gx_ctx* c) {
+  using namespace gx;
+  if (!c->block_lists_built) build_block_lists(c);
+  int const nn = c->nn;
+  std::vector<int64_t> const& nx = c->nrow_x;
+  int const CH = 4096;  // nodes per independent chunk of the visiting order
+  int const nch = (nn + CH - 1) / CH;
+  std::vector<std::vector<uint32_t>> out(nch);
+  bool ok = true;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int ch = 0; ch < nch; ++ch) {
+    struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; int64_t voff; uint32_t rl, node; int kind, nsec, part; bool diag; };
+    std::vector<Item> items;
+    std::vector<int32_t> recs;
+    int32_t hkey[512]; int16_t hval[512];
+    auto hclear = [&]() { for (int i = 0; i < 512; ++i) hkey[i] = -1; };
+    auto hfind = [&](int32_t e) -> int {
+      uint32_t h = ((uint32_t)e * 2654435761u) >> 23;
+      while (hkey[h] != -1) { if (hkey[h] == e) return hval[h]; h = (h + 1) & 511u; }
+      return -1;
+    };
+    auto hput = [&](int32_t e, int v) {
+      uint32_t h = ((uint32_t)e * 2654435761u) >> 23;
+      while (hkey[h] != -1) h = (h + 1) & 511u;
+      hkey[h] = e; hval[h] = (int16_t)v;
+    };
+    int nparts = 0;
+    auto flush = [&]() {
+      if (items.empty()) return;
+      // longest items first: the lanes of a warp then run the same number of contributions
+      std::vector<int> ord(items.size());
+      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
+      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return items[x].n > items[y].n; });
+      size_t const base = out[ch].size();
+      out[ch].resize(base + PATCH_WORDS, 0u);
+      uint32_t* w = out[ch].data() + base;
+      w[0] = (uint32_t)recs.size(); w[1] = (uint32_t)items.size();
+      for (size_t i = 0; i < recs.size(); ++i) w[4 + i] = (uint32_t)recs[i];
+      uint32_t* wi = w + 4 + PATCH_RECS;
+      uint32_t* wo = wi + 4 * PATCH_THREADS;
+      for (size_t t = 0; t < ord.size(); ++t) {
+        Item const& it = items[ord[t]];
+        for (int k = 0; k < 4; ++k) wi[4 * t + k] = (uint32_t)it.ent[2 * k] | ((uint32_t)it.ent[2 * k + 1] << 16);
+        wo[4 * t] = (uint32_t)((uint64_t)it.voff & 0xffffffffu);
+        wo[4 * t + 1] = (uint32_t)((uint64_t)it.voff >> 32);
+        wo[4 * t + 2] = it.rl | ((uint32_t)it.part << 16) | ((uint32_t)it.nsec << 24) | ((uint32_t)it.kind << 30);
+        wo[4 * t + 3] = it.node | (it.diag ? 0x80000000u : 0u);
+      }
+      items.clear(); recs.clear(); hclear(); nparts = 0;
+    };
+    hclear();
+    bool bad = false;
+    int const s1 = std::min(nn, (ch + 1) * CH);
+    for (int s = ch * CH; s < s1; ++s) {
+      int const a = c->node_order[s];
+      // new records this node would add
+      int add = 0;
+      for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) if (hfind(c->adj[k].x >> 2) < 0) ++add;
+      // its items (slots filled in once the node is accepted)
+      int nit = 0, nsecs = 0;
+      for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
+        int const cnt = (int)(c->bc_off[t + 1] - c->bc_off[t]);
+        int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
+        nit += parts; nsecs += parts - 1;
+      }
+      if (nit > PATCH_THREADS || (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > 63) { bad = true; break; }
+      if ((int)items.size() + nit > PATCH_THREADS || (int)recs.size() + add > PATCH_RECS || nparts + nsecs > PATCH_THREADS) flush();
+      for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
+        int32_t const e = c->adj[k].x >> 2;
+        if (hfind(e) < 0) { hput(e, (int)recs.size()); recs.push_back(e); }
+      }
+      int64_t const rl = 4 * (nx[a + 1] - nx[a]);
+      for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
+        uint32_t const c0 = c->bc_off[t], c1 = c->bc_off[t + 1];
+        int const cnt = (int)(c1 - c0);
+        int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
+        bool const diag = (c->blk_row[t] & 0x80000000u) != 0;
+        for (int pi = 0; pi < parts; ++pi) {
+          Item it{};
+          it.n = std::min(PATCH_ITEM_LEN, cnt - pi * PATCH_ITEM_LEN);
+          if (it.n < 0) it.n = 0;
+          for (int q = 0; q < it.n; ++q) {
+            int32_t const ent = c->bc[c0 + pi * PATCH_ITEM_LEN + q];
+            it.ent[q] = (uint16_t)(hfind(ent >> 4) | ((ent & 15) << 8) | 0x8000);  // n*4+m -> bits 8..11
+          }
+          it.voff = 16 * nx[a] + 4 * (t - nx[a]);
+          it.rl = (uint32_t)rl; it.node = (uint32_t)a; it.diag = diag;
+          if (pi == 0) { it.kind = 1; it.nsec = parts - 1; it.part = nparts; }
+          else { it.kind = 2; it.nsec = 0; it.part = nparts + pi - 1; }
+          items.push_back(it);
+        }
+        nparts += parts - 1;
+      }
+    }
+    flush();
+    if (bad) {
+#pragma omp atomic write
+      ok = false;
+    }
+  }
+  if (!ok) { c->patch_state = -1; return false; }
+  size_t total = 0;
+  for (auto& v : out) total += v.size();
+  c->patch_sched.clear();
+  c->patch_sched.reserve(total);
+  for (auto& v : out) { c->patch_sched.insert(c->patch_sched.end(), v.begin(), v.end()); std::vector<uint32_t>().swap(v); }
+  c->n_patches = (int)(total / PATCH_WORDS);
+  c->patch_state = 1;
+  return true;
+}
+
 void pack_host(gx_ctx const* c, HostPack& h) {
   int const nn = c->nn, ne = c->ne;
   h.nodes.resize(nn);
