@@ -286,30 +286,6 @@ static cudaError_t launch_two_stage(gx_ctx* ctx, KParams& P, int pass, bool save
   return cudaGetLastError();
 }
 
-// gather form of the Jacobian pass: element records, off-diagonal blocks (thread per block), diagonal blocks + R
-template <int MODEL>
-static cudaError_t launch_block_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
-  int const ne = ctx->ne;
-  if (save) elem_record_kernel<MODEL, true><<<(ne + 63) / 64, 64, 0, ctx->stream>>>(P, ctx->d_elemrec, ne);
-  else elem_record_kernel<MODEL, false><<<(ne + 63) / 64, 64, 0, ctx->stream>>>(P, ctx->d_elemrec, ne);
-  ctx->launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  bool const tr = pass == PASS_JACOBIAN_T;
-  int64_t const nblocks = ctx->nnz_x / 16;
-  unsigned const gb = (unsigned)((nblocks + 127) / 128);
-  if (tr) block_gather_kernel<true><<<gb, 128, 0, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_blk_row, ctx->d_bc_off, ctx->d_bc, nblocks);
-  else block_gather_kernel<false><<<gb, 128, 0, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_blk_row, ctx->d_bc_off, ctx->d_bc, nblocks);
-  ctx->launches++;
-  e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  unsigned const gd = (unsigned)((ctx->nn + 3) / 4);
-  if (tr) diag_gather_kernel<true><<<gd, 128, 0, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_diag_pos);
-  else diag_gather_kernel<false><<<gd, 128, 0, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_diag_pos);
-  ctx->launches++;
-  return cudaGetLastError();
-}
-
 // patch-gather form of the Jacobian pass: element records, then one thread block per patch
 template <int MODEL>
 static cudaError_t launch_patch_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
@@ -336,20 +312,6 @@ static int upload_patch_schedule(gx_ctx* ctx) {
   GX_CUDA(cudaMalloc(&ctx->d_patch_sched, sizeof(uint32_t) * std::max<size_t>(ctx->patch_sched.size(), 1)));
   GX_CUDA(cudaMemcpy(ctx->d_patch_sched, ctx->patch_sched.data(), sizeof(uint32_t) * ctx->patch_sched.size(), cudaMemcpyHostToDevice));
   std::vector<uint32_t>().swap(ctx->patch_sched);
-  return GX_OK;
-}
-
-static int upload_block_lists(gx_ctx* ctx) {
-  if (ctx->block_lists_built && ctx->d_bc) return GX_OK;
-  build_block_lists(ctx);
-  for (void* p : {(void*)ctx->d_blk_row, (void*)ctx->d_bc_off, (void*)ctx->d_bc}) if (p) cudaFree(p);
-  ctx->d_blk_row = ctx->d_bc_off = nullptr; ctx->d_bc = nullptr;
-  GX_CUDA(cudaMalloc(&ctx->d_blk_row, sizeof(uint32_t) * std::max<size_t>(ctx->blk_row.size(), 1)));
-  GX_CUDA(cudaMalloc(&ctx->d_bc_off, sizeof(uint32_t) * ctx->bc_off.size()));
-  GX_CUDA(cudaMalloc(&ctx->d_bc, sizeof(int32_t) * std::max<size_t>(ctx->bc.size(), 1)));
-  GX_CUDA(cudaMemcpy(ctx->d_blk_row, ctx->blk_row.data(), sizeof(uint32_t) * ctx->blk_row.size(), cudaMemcpyHostToDevice));
-  GX_CUDA(cudaMemcpy(ctx->d_bc_off, ctx->bc_off.data(), sizeof(uint32_t) * ctx->bc_off.size(), cudaMemcpyHostToDevice));
-  GX_CUDA(cudaMemcpy(ctx->d_bc, ctx->bc.data(), sizeof(int32_t) * ctx->bc.size(), cudaMemcpyHostToDevice));
   return GX_OK;
 }
 
@@ -396,26 +358,20 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   bool const row_owner = with_values && ctx->opt_kernel != 1 &&
                          row_owner_smem(ctx, (int)ctx->opt_row_warps) <= 200 * 1024;
-  bool patch_gather = with_values && ctx->opt_kernel == 4;
+  bool patch_gather = with_values && ctx->opt_kernel == 3;
   if (patch_gather) {
-    if (ctx->ne >= (1 << 27)) { ctx->err = "kernel=4 supports fewer than 2^27 elements per part"; return GX_ERR_UNSUPPORTED; }
+    if (ctx->ne >= (1 << 27)) { ctx->err = "kernel=3 supports fewer than 2^27 elements per part"; return GX_ERR_UNSUPPORTED; }
     int const rc = upload_patch_schedule(ctx);
     if (rc) return rc;
     patch_gather = ctx->patch_state == 1;
   }
-  bool const two_stage = row_owner && (ctx->opt_kernel == 0 || (ctx->opt_kernel == 4 && !patch_gather));
-  bool const block_gather = with_values && ctx->opt_kernel == 3;
+  bool const two_stage = row_owner && (ctx->opt_kernel == 0 || (ctx->opt_kernel == 3 && !patch_gather));
   bool const gather = !with_values && ctx->opt_kernel != 1;
-  if (block_gather) {
-    if (ctx->ne >= (1 << 27)) { ctx->err = "kernel=3 supports fewer than 2^27 elements per part"; return GX_ERR_UNSUPPORTED; }
-    int const rc = upload_block_lists(ctx);
-    if (rc) return rc;
-  }
-  if ((two_stage || gather || block_gather || patch_gather) && !ctx->d_elemrec)
+  if ((two_stage || gather || patch_gather) && !ctx->d_elemrec)
     GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
   if (patch_gather)  // nodes without elements have no work item
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
-  if (!row_owner && !gather && !block_gather && !patch_gather) {
+  if (!row_owner && !gather && !patch_gather) {
     // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The row-owner schedule writes every
     // entry of R and of the CRS values exactly once, so it needs no zeroing pass.
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
@@ -430,9 +386,6 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   else if (patch_gather)
     le = ctx->model == GX_MODEL_J2 ? launch_patch_gather<MODEL_J2>(ctx, P, pass, save)
                                    : launch_patch_gather<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
-  else if (block_gather)
-    le = ctx->model == GX_MODEL_J2 ? launch_block_gather<MODEL_J2>(ctx, P, pass, save)
-                                   : launch_block_gather<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   else if (two_stage)
     le = ctx->model == GX_MODEL_J2 ? launch_two_stage<MODEL_J2>(ctx, P, pass, save)
                                    : launch_two_stage<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
@@ -496,7 +449,7 @@ static void free_device(gx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord, ctx->d_node_order, ctx->d_diag_pos,
                   ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
-                  ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child, ctx->d_blk_row, ctx->d_bc_off, ctx->d_bc, ctx->d_patch_sched};
+                  ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -881,8 +834,15 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return GX_ERR_ARG;
   std::string k(key);
   if (k == "kernel") {  // Jacobian pass: 0 = element records + row fold (default), 1 = coloured elements, 2 = fused row-owner
-    if (value < 0 || value > 4) { ctx->err = "kernel must be 0..4"; return GX_ERR_ARG; }
+    if (value < 0 || value > 3) { ctx->err = "kernel must be 0..3"; return GX_ERR_ARG; }
     ctx->opt_kernel = value;
+    return GX_OK;
+  }
+  if (k == "patch_schedule_dryrun") {  // host-side build of the patch schedule (works on host-only contexts); GX_SCHED_STATS prints its statistics
+    bool const ok = build_patch_schedule(ctx);
+    std::vector<uint32_t>().swap(ctx->patch_sched);
+    ctx->patch_state = 0;
+    if (!ok) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
     return GX_OK;
   }
   if (k == "fold_waves") {

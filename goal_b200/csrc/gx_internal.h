@@ -90,14 +90,14 @@ struct gx_ctx {
   // incidences of an element are processed close in time and its tangent record is fetched from HBM once
   std::vector<int32_t> node_order;
   std::vector<uint8_t> diag_pos;  // position of block (a,a) in node a's block row
-  // ---- block gather schedule of the gather-form Jacobian pass (built lazily on the extended graph):
+  // ---- per-block contribution lists (host only, input of the patch schedule; built lazily on the extended graph):
   //   blk_row[t]  : row node of block t (bit 31 set for the diagonal block)
   //   bc_off/bc   : per block the contributing (element, row-local node n, column-local node m) = e*16 + n*4 + m,
   //                 ascending element; phantom blocks have none
   std::vector<uint32_t> blk_row, bc_off;
   std::vector<int32_t> bc;
   bool block_lists_built = false;
-  // ---- patch schedule of the patch-gather Jacobian pass (kernel = 4), see build_patch_schedule()
+  // ---- patch schedule of the patch-gather Jacobian pass (kernel = 3), see build_patch_schedule()
   std::vector<uint32_t> patch_sched;
   int n_patches = 0;
   int patch_state = 0;  // 0 = not built, 1 = built, -1 = mesh does not fit (a node exceeds a patch)
@@ -119,8 +119,6 @@ struct gx_ctx {
   uint32_t* d_fold_ord = nullptr;
   int32_t* d_node_order = nullptr;
   uint8_t* d_diag_pos = nullptr;   // position of block (a,a) in node a's block row
-  uint32_t *d_blk_row = nullptr, *d_bc_off = nullptr;
-  int32_t* d_bc = nullptr;
   uint32_t* d_patch_sched = nullptr;
   // history state, one record per element (user order):
   //   in    : Cp^{-1}[6] (of Fp_old, cached), eqps_old, pad   (64 B)  read by every incidence of the element

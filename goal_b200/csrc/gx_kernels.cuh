@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_const
 // element core is evaluated once per element instead of once per incidence.
 //   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the
 //            56-double "tangent record" of the element (everything the 4x4 blocks are built from):
-//              w_n[4][3] r_n[4][3] | Tv[6] Gm[6] s[6] | q[3] gwv A1v Jpv upc va tjv ppc rb | pad[3]
+//              {w_n[3] r_n[3]} x 4 nodes | Tv[6] Gm[6] s[6] | q[3] gwv A1v Jpv upc va tjv ppc rb | pad[3]
 //   stage B  row_fold_kernel    : one warp per node, one lane per incidence.  Each lane reads its
 //            element's record (448 B, contiguous), builds the four blocks of the node's rows, and the
 //            warp folds and writes the node's CRS rows once, exactly like row_owner_kernel.
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { mine[3 * q + k] = c.w[q][k]; mine[12 + 3 * q + k] = c.r[q][k]; }
+        for (int k = 0; k < 3; ++k) { mine[6 * q + k] = c.w[q][k]; mine[6 * q + 3 + k] = c.r[q][k]; }
 #pragma unroll
       for (int k = 0; k < 6; ++k) { mine[24 + k] = c.Tv[k]; mine[30 + k] = c.Gm[k]; mine[36 + k] = c.s[k]; }
       mine[42] = c.q[0]; mine[43] = c.q[1]; mine[44] = c.q[2]; mine[45] = c.gwv; mine[46] = c.A1v; mine[47] = c.Jpv;
@@ -555,8 +555,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
         double wn[3], rn3[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          wn[k] = wr[(3 * n + k) * WR_LD];
-          rn3[k] = wr[(12 + 3 * n + k) * WR_LD];
+          wn[k] = wr[(6 * n + k) * WR_LD];
+          rn3[k] = wr[(6 * n + 3 + k) * WR_LD];
         }
         RowNode<double> rown;
         ColNode<double> coln;
@@ -574,8 +574,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
             double wm[3], rm[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-              wm[k] = wr[(3 * m + k) * WR_LD];
-              rm[k] = wr[(12 + 3 * m + k) * WR_LD];
+              wm[k] = wr[(6 * m + k) * WR_LD];
+              rm[k] = wr[(6 * m + 3 + k) * WR_LD];
             }
             double blk[16];
             if (!TRANSPOSE) {
@@ -723,7 +723,9 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 #pragma unroll
           for (int k = 0; k < 14; ++k) ldg256(reinterpret_cast<double const*>(q) + 4 * k, f + 4 * k);
 #pragma unroll
-          for (int k = 0; k < 12; ++k) { (&wv[0][0])[k] = f[k]; (&rv[0][0])[k] = f[12 + k]; }
+          for (int n4 = 0; n4 < 4; ++n4)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { wv[n4][k] = f[6 * n4 + k]; rv[n4][k] = f[6 * n4 + 3 + k]; }
 #pragma unroll
           for (int k = 0; k < 6; ++k) { c.Tv[k] = f[24 + k]; c.Gm[k] = f[30 + k]; c.s[k] = f[36 + k]; }
           c.q[0] = f[42]; c.q[1] = f[43]; c.q[2] = f[44]; c.gwv = f[45]; c.A1v = f[46]; c.Jpv = f[47];
@@ -809,125 +811,51 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 }
 
 // ---------------------------------------------------------------------------
-// Schedule (1c), gather form of the Jacobian pass (KParams-level option kernel = 3): stage A as above, then
-//   block_gather_kernel : one thread per off-diagonal 4x4 block of the operator.  The thread walks the block's
-//            contribution list (the elements containing that mesh edge, ascending), rebuilds each element's
-//            block from the tangent record, accumulates the 16 entries in registers and writes them once.
-//            No shared memory, no cross-thread traffic; neighbouring threads own neighbouring blocks of one
-//            block row, so they read the same records (L1) and their stores coalesce.
-//   diag_gather_kernel  : one warp per node, one lane per incidence: the diagonal block (as many contributions
-//            as the node has elements) and the node's four residual entries, summed across lanes through a
-//            shared-memory transpose in a fixed order.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void load_tangent_scalars(double2 const* __restrict__ q, Core<double>& c) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) {
-    double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
-    v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
-    v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
-  }
-  double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
-  v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
-  v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
-  v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
-  v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
-  v = __ldg(q + 26); c.rb = v.x;
-}
-
-template <bool TRANSPOSE>
-__global__ void __launch_bounds__(128) block_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
-                                                           uint32_t const* __restrict__ blk_row, uint32_t const* __restrict__ bc_off,
-                                                           int32_t const* __restrict__ bc, int64_t nblocks) {
-  int64_t const t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nblocks) return;
-  uint32_t const ra = __ldg(blk_row + t);
-  if (ra & 0x80000000u) return;  // diagonal block: diag_gather_kernel
-  int const a = (int)ra;
-  int blk0a, nblka;
-  {
-    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
-    blk0a = __double2loint(d3.y);
-    nblka = __double2hiint(d3.y);
-  }
-  uint32_t const c0 = __ldg(bc_off + t), c1 = __ldg(bc_off + t + 1);
-  double acc[16];
-#pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-  for (uint32_t ci = c0; ci < c1; ++ci) {
-    int const ent = __ldg(bc + ci);
-    int const e = ent >> 4, n = (ent >> 2) & 3, m = ent & 3;
-    double const* rp = rec + (int64_t)ELEM_REC * e;
-    Core<double> c;  // only the tangent fields are filled
-    load_tangent_scalars(reinterpret_cast<double2 const*>(rp), c);
-    // row node = the node of this block row in the primal operator; roles swap for the transpose
-    int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
-    double wr[3], wc[3], rc[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      wr[k] = __ldg(rp + 3 * nr + k);
-      wc[k] = __ldg(rp + 3 * nc + k);
-      rc[k] = __ldg(rp + 12 + 3 * nc + k);
-    }
-    RowNode<double> rown;
-    ColNode<double> coln;
-    row_node(c, wr, rown);
-    column_node(c, wc, rc, coln);
-    double blk[16];
-    jacobian_block(c, rown, coln, blk);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) acc[4 * i + k] += TRANSPOSE ? blk[4 * k + i] : blk[4 * i + k];
-  }
-  int const j = (int)(t - blk0a);
-  double* out = P.values + 16 * (int64_t)blk0a + 4 * j;
-  int const rl = 4 * nblka;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double2* o = reinterpret_cast<double2*>(out + (int64_t)i * rl);
-    o[0] = make_double2(acc[4 * i], acc[4 * i + 1]);
-    o[1] = make_double2(acc[4 * i + 2], acc[4 * i + 3]);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Schedule (1d), patch gather (option kernel = 4): stage A as above, then one thread block per patch of the
+// Schedule (1c), patch gather (option kernel = 3): stage A as above, then one thread block per patch of the
 // precomputed patch schedule (build_patch_schedule, gx_setup.cpp).  The block stages the records of the patch's
-// elements in shared memory with coalesced asynchronous copies (every record crosses the L1 data pipe once per
-// patch instead of once per incident node and lane), then every thread runs one work item: up to 8 contributions to
+// elements in shared memory with bulk asynchronous copies (cp.async.bulk, one per record: every record crosses
+// the L1 data pipe once per patch instead of once per incident node and lane), then every thread runs one work item: up to 8 contributions to
 // one 4x4 block, rebuilt from the staged records and accumulated in registers.  Blocks with more contributions
 // are finished by their primary item from the secondaries' partial sums (fixed order).  Every block of the patch's
 // rows, and the rows' residual entries, are written exactly once.
 // ---------------------------------------------------------------------------
 constexpr int PATCH_REC_LD = 58;  // doubles between staged records: 464 B = 29 x 16 B, conflict-free 128-bit reads
-GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double) + PATCH_RECS * sizeof(int32_t); }
+GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double); }
 
 template <bool TRANSPOSE>
 __global__ void __launch_bounds__(PATCH_THREADS, 3) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
                                                                         uint32_t const* __restrict__ sched) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
   double* srec = reinterpret_cast<double*>(smem_raw);
-  int32_t* selem = reinterpret_cast<int32_t*>(smem_raw + (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double));
   int const tid = threadIdx.x;
   uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
   int const n_recs = (int)__ldg(w);
-  selem[tid] = (int32_t)__ldg(w + 4 + tid);
+  int const my_elem = (int)__ldg(w + 4 + tid);
   uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
   uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
-  __syncthreads();
-  {
-    uint32_t const sbase = (uint32_t)__cvta_generic_to_shared(srec);
-    int const total = n_recs * 28;  // 16-byte pieces
-    for (int u = tid; u < total; u += PATCH_THREADS) {
-      int const r = u / 28, piece = u - 28 * r;
-      char const* src = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * selem[r]) + 16 * piece;
-      uint32_t const dst = sbase + (uint32_t)(r * (PATCH_REC_LD * 8) + 16 * piece);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  // Record staging: thread r issues one bulk asynchronous copy (448 B, global -> shared) for record r; the copies
+  // report their bytes to an mbarrier that the whole block then waits on.
+  uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
+  if (tid < n_recs) {
+    uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + (uint32_t)(tid * (PATCH_REC_LD * 8));
+    double const* src = rec + (int64_t)ELEM_REC * my_elem;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(ELEM_REC * 8), "r"(mb)
+                 : "memory");
+  }
+  {
+    uint32_t done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+    } while (!done);
+  }
   int const kind = (int)(ot.z >> 30);
   bool const diag = (ot.w & 0x80000000u) != 0;
   double acc[16], r4[4] = {0.0, 0.0, 0.0, 0.0};
@@ -955,16 +883,20 @@ __global__ void __launch_bounds__(PATCH_THREADS, 3) patch_gather_kernel(const __
       v = q[23]; c.A1v = v.x; c.Jpv = v.y;
       v = q[24]; c.upc = v.x; c.va = v.y;
       v = q[25]; c.tjv = v.x; c.ppc = v.y;
-      c.rb = rp[52];
+      c.rb = 0.0;
+      if (diag) c.rb = rp[52];
     }
     // row node = the node of this block row in the primal operator; roles swap for the transpose
     int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
     double wr[3], wc[3], rc[3];
-#pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      wr[j] = rp[3 * nr + j];
-      wc[j] = rp[3 * nc + j];
-      rc[j] = rp[12 + 3 * nc + j];
+    {  // node block of the record: {w[3], r[3]}, 48 B
+      double2 const* qr = reinterpret_cast<double2 const*>(rp + 6 * nr);
+      double2 const* qc = reinterpret_cast<double2 const*>(rp + 6 * nc);
+      double2 const a0 = qr[0], a1 = qr[1];
+      double2 const b0 = qc[0], b1 = qc[1], b2 = qc[2];
+      wr[0] = a0.x; wr[1] = a0.y; wr[2] = a1.x;
+      wc[0] = b0.x; wc[1] = b0.y; wc[2] = b1.x;
+      rc[0] = b1.y; rc[1] = b2.x; rc[2] = b2.y;
     }
     RowNode<double> rown;
     ColNode<double> coln;
@@ -1018,83 +950,6 @@ __global__ void __launch_bounds__(PATCH_THREADS, 3) patch_gather_kernel(const __
       o[1] = make_double2(r4[2], r4[3]);
     }
   }
-}
-
-constexpr int DIAG_LD = 33;
-template <bool TRANSPOSE>
-__global__ void __launch_bounds__(128) diag_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
-                                                          uint8_t const* __restrict__ diag_pos) {
-  __shared__ double sm[4][20 * DIAG_LD];
-  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int const slot = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (slot >= P.nn) return;
-  double* stg = sm[wib];
-  int const a = __ldg(P.node_order + slot);
-  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
-  int blk0a, nblka;
-  {
-    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
-    blk0a = __double2loint(d3.y);
-    nblka = __double2hiint(d3.y);
-  }
-  int const t16 = lane & 15, half = lane >> 4;
-  int const ri = lane & 3, rg = lane >> 2;
-  double tot = 0.0, rtot = 0.0;
-  for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
-    double blk[16], r4[4];
-    if (r0 + lane < o1) {
-      int2 const ad = __ldg(P.adj + r0 + lane);
-      int const e = ad.x >> 2, n = ad.x & 3;
-      double const* rp = rec + (int64_t)ELEM_REC * e;
-      Core<double> c;
-      load_tangent_scalars(reinterpret_cast<double2 const*>(rp), c);
-      double wn[3], rn3[3];
-#pragma unroll
-      for (int k = 0; k < 3; ++k) { wn[k] = __ldg(rp + 3 * n + k); rn3[k] = __ldg(rp + 12 + 3 * n + k); }
-      element_residual_row(c, wn, r4);
-      RowNode<double> rown;
-      ColNode<double> coln;
-      row_node(c, wn, rown);
-      column_node(c, wn, rn3, coln);
-      jacobian_block(c, rown, coln, blk);
-    } else {
-#pragma unroll
-      for (int k = 0; k < 16; ++k) blk[k] = 0.0;
-      r4[0] = r4[1] = r4[2] = r4[3] = 0.0;
-    }
-    if (r0 != o0) __syncwarp();
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int k = 0; k < 4; ++k) stg[(4 * i + k) * DIAG_LD + lane] = TRANSPOSE ? blk[4 * k + i] : blk[4 * i + k];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) stg[(16 + i) * DIAG_LD + lane] = r4[i];
-    __syncwarp();
-    // entry t16 of the block: each half-warp sums 16 lanes' values, the halves are joined by one shuffle
-    {
-      double const* src = stg + t16 * DIAG_LD + 16 * half;
-      double s0 = 0.0, s1 = 0.0;
-#pragma unroll
-      for (int l = 0; l < 16; l += 2) { s0 += src[l]; s1 += src[l + 1]; }
-      double s = s0 + s1;
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      tot += s;
-    }
-    // residual entry ri: eight groups of four lanes, joined by a butterfly over the groups
-    {
-      double const* src = stg + (16 + ri) * DIAG_LD + 4 * rg;
-      double s = (src[0] + src[1]) + (src[2] + src[3]);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      rtot += s;
-    }
-  }
-  if (lane < 16) {
-    int const dj = __ldg(diag_pos + a);
-    P.values[16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + 4 * dj + (t16 & 3)] = tot;
-  }
-  if (lane < 4) P.R[4 * (int64_t)a + lane] = rtot;
 }
 
 // ---------------------------------------------------------------------------

@@ -15,6 +15,8 @@
 // node, so their scatters into R and into the CRS values touch disjoint rows and
 // the assembly needs no atomics and is bit-reproducible run to run.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -285,6 +287,9 @@ bool build_patch_schedule(gx_ctx* c) {
   int const CH = 4096;  // nodes per independent chunk of the visiting order
   int const nch = (nn + CH - 1) / CH;
   std::vector<std::vector<uint32_t>> out(nch);
+  bool const stats = getenv("GX_SCHED_STATS") != nullptr;
+  bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
+  std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0);
   bool ok = true;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int ch = 0; ch < nch; ++ch) {
@@ -310,6 +315,73 @@ bool build_patch_schedule(gx_ctx* c) {
       std::vector<int> ord(items.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
       std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return items[x].n > items[y].n; });
+      // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
+      // record is its slot modulo 8.  Within every group of 8 lanes, order each item's contributions so that the
+      // records read in the same round sit in different bank groups where possible (a bipartite matching of
+      // items to bank groups per round).
+      for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
+        int const gn = (int)std::min<size_t>(8, ord.size() - g0);
+        bool used[8][PATCH_ITEM_LEN] = {};
+        uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
+        int nmax = 0;
+        for (int i = 0; i < gn; ++i) nmax = std::max(nmax, items[ord[g0 + i]].n);
+        for (int k = 0; k < nmax && !nomatch; ++k) {
+          int match_res[8];   // bank group -> item
+          int pick[8];        // item -> contribution index
+          for (int r = 0; r < 8; ++r) match_res[r] = -1;
+          for (int i = 0; i < 8; ++i) pick[i] = -1;
+          // Kuhn's augmenting paths; items x bank groups, edges through unused contributions
+          auto try_item = [&](auto&& self, int i, bool* seen) -> bool {
+            Item const& it = items[ord[g0 + i]];
+            for (int q = 0; q < it.n; ++q) {
+              if (used[i][q]) continue;
+              int const r = it.ent[q] & 7;
+              if (seen[r]) continue;
+              seen[r] = true;
+              if (match_res[r] < 0 || self(self, match_res[r], seen)) { match_res[r] = i; pick[i] = q; return true; }
+            }
+            return false;
+          };
+          for (int i = 0; i < gn; ++i) {
+            if (items[ord[g0 + i]].n <= k) continue;
+            bool seen[8] = {};
+            try_item(try_item, i, seen);
+          }
+          for (int i = 0; i < gn; ++i) {
+            Item const& it = items[ord[g0 + i]];
+            if (it.n <= k) continue;
+            int q = -1;
+            for (int r = 0; r < 8 && q < 0; ++r)
+              if (match_res[r] == i) q = pick[i];
+            if (q < 0 || used[i][q])  // unmatched: any unused contribution
+              for (q = 0; used[i][q]; ++q) {}
+            used[i][q] = true;
+            sched_ent[i][k] = it.ent[q];
+          }
+        }
+        for (int i = 0; i < gn && !nomatch; ++i) {
+          Item& it = items[ord[g0 + i]];
+          for (int k = 0; k < it.n; ++k) it.ent[k] = sched_ent[i][k];
+        }
+        if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
+          for (int k = 0; k < nmax; ++k) {
+            int cnt[8] = {};
+            for (int i = 0; i < gn; ++i) {
+              Item const& it = items[ord[g0 + i]];
+              if (it.n <= k) continue;
+              bool dup = false;
+              for (int j = 0; j < i; ++j) {
+                Item const& jt = items[ord[g0 + j]];
+                if (jt.n > k && (jt.ent[k] & 0xff) == (it.ent[k] & 0xff)) dup = true;
+              }
+              if (!dup) cnt[it.ent[k] & 7]++;
+            }
+            int mx = 0;
+            for (int r = 0; r < 8; ++r) mx = std::max(mx, cnt[r]);
+            st_wave[ch] += mx; st_rounds[ch] += 1;
+          }
+        }
+      }
       size_t const base = out[ch].size();
       out[ch].resize(base + PATCH_WORDS, 0u);
       uint32_t* w = out[ch].data() + base;
@@ -385,6 +457,12 @@ bool build_patch_schedule(gx_ctx* c) {
   for (auto& v : out) { c->patch_sched.insert(c->patch_sched.end(), v.begin(), v.end()); std::vector<uint32_t>().swap(v); }
   c->n_patches = (int)(total / PATCH_WORDS);
   c->patch_state = 1;
+  if (stats) {
+    int64_t wv = 0, rd = 0;
+    for (int i = 0; i < nch; ++i) { wv += st_wave[i]; rd += st_rounds[i]; }
+    fprintf(stderr, "[gx] patch schedule: %d patches, %.2f nodes/patch, %.3f wavefronts per quarter-warp round\n", c->n_patches,
+            (double)nn / std::max(1, c->n_patches), rd ? (double)wv / (double)rd : 0.0);
+  }
   return true;
 }
 

@@ -83,7 +83,7 @@ def test_jacobian_residual_state_parity(cube, model, mesh):
     a.close()
 
 
-@pytest.mark.parametrize("opts", [dict(fold_sorted=1), dict(kernel=2), dict(kernel=1), dict(kernel=3), dict(kernel=4), dict(fold_sorted=1, fold_minblocks=2, row_warps=2)])
+@pytest.mark.parametrize("opts", [dict(fold_sorted=1), dict(kernel=2), dict(kernel=1), dict(kernel=3), dict(fold_sorted=1, fold_minblocks=2, row_warps=2)])
 @pytest.mark.parametrize("mesh", ["cube", "kuhn7"])
 def test_kernel_variants_parity(cube, mesh, opts):
     """Every Jacobian schedule (sorted fold, generic fold, fused row-owner, coloured, block gather) against the oracle,
