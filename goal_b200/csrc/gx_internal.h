@@ -189,7 +189,7 @@ bool build_patch_schedule(gx_ctx* c);
 
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
 constexpr int PATCH_THREADS = 128;  // work items per patch, one per thread
-constexpr int PATCH_RECS = 128;     // element records staged per patch
+constexpr int PATCH_RECS = 120;     // element records staged per patch (120 x 464 B: four blocks per SM)
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS;  // uint32 words per patch
 // gx_comm.cu

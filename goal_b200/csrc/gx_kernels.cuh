@@ -823,7 +823,7 @@ constexpr int PATCH_REC_LD = 58;  // doubles between staged records: 464 B = 29 
 GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double); }
 
 template <bool TRANSPOSE>
-__global__ void __launch_bounds__(PATCH_THREADS, 3) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+__global__ void __launch_bounds__(PATCH_THREADS, 4) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
                                                                         uint32_t const* __restrict__ sched) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar;

@@ -316,54 +316,97 @@ bool build_patch_schedule(gx_ctx* c) {
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
       std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return items[x].n > items[y].n; });
       // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
-      // record is its slot modulo 8.  Within every group of 8 lanes, order each item's contributions so that the
-      // records read in the same round sit in different bank groups where possible (a bipartite matching of
-      // items to bank groups per round).
-      for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
+      // record is its slot modulo 8.  Bank groups are given to the records by a greedy colouring (records feeding the
+      // same item get different groups where possible); then, within every group of 8 lanes, each item's
+      // contributions are ordered so that the records read in the same round sit in different groups where possible
+      // (per round a bipartite matching of items to bank groups).
+      int const nrec = (int)recs.size();
+      std::vector<int> res(nrec, -1);
+      int cap[8];
+      for (int r = 0; r < 8; ++r) cap[r] = nrec / 8 + (r < nrec % 8 ? 1 : 0);  // slots r, r + 8, ...: no gaps
+      {
+        // bank groups first: records that contribute to the same item get different groups where possible
+        std::vector<std::vector<int>> in_items(nrec);
+        for (size_t i = 0; i < items.size(); ++i)
+          for (int q = 0; q < items[i].n; ++q) in_items[items[i].ent[q] & 0xff].push_back((int)i);
+        for (int l = 0; l < nrec; ++l) {
+          int cnt[8] = {};
+          for (int i : in_items[l])
+            for (int q = 0; q < items[i].n; ++q) {
+              int const r = res[items[i].ent[q] & 0xff];
+              if (r >= 0) cnt[r]++;
+            }
+          int best = -1;
+          for (int r = 0; r < 8; ++r)
+            if (cap[r] > 0 && (best < 0 || cnt[r] < cnt[best] || (cnt[r] == cnt[best] && cap[r] > cap[best]))) best = r;
+          res[l] = best; cap[best]--;
+        }
+      }
+      for (size_t g0 = 0; g0 < ord.size() && !nomatch; g0 += 8) {
         int const gn = (int)std::min<size_t>(8, ord.size() - g0);
         bool used[8][PATCH_ITEM_LEN] = {};
         uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
         int nmax = 0;
         for (int i = 0; i < gn; ++i) nmax = std::max(nmax, items[ord[g0 + i]].n);
-        for (int k = 0; k < nmax && !nomatch; ++k) {
+        for (int k = 0; k < nmax; ++k) {
           int match_res[8];   // bank group -> item
           int pick[8];        // item -> contribution index
           for (int r = 0; r < 8; ++r) match_res[r] = -1;
           for (int i = 0; i < 8; ++i) pick[i] = -1;
-          // Kuhn's augmenting paths; items x bank groups, edges through unused contributions
+          // Kuhn's augmenting paths; items x bank groups, edges through unused contributions with a fixed group
           auto try_item = [&](auto&& self, int i, bool* seen) -> bool {
             Item const& it = items[ord[g0 + i]];
             for (int q = 0; q < it.n; ++q) {
               if (used[i][q]) continue;
-              int const r = it.ent[q] & 7;
-              if (seen[r]) continue;
+              int const r = res[it.ent[q] & 0xff];
+              if (r < 0 || seen[r]) continue;
               seen[r] = true;
               if (match_res[r] < 0 || self(self, match_res[r], seen)) { match_res[r] = i; pick[i] = q; return true; }
             }
             return false;
           };
+          bool matched[8] = {};
           for (int i = 0; i < gn; ++i) {
             if (items[ord[g0 + i]].n <= k) continue;
             bool seen[8] = {};
             try_item(try_item, i, seen);
           }
+          for (int r = 0; r < 8; ++r) if (match_res[r] >= 0) matched[match_res[r]] = true;
           for (int i = 0; i < gn; ++i) {
             Item const& it = items[ord[g0 + i]];
             if (it.n <= k) continue;
-            int q = -1;
-            for (int r = 0; r < 8 && q < 0; ++r)
-              if (match_res[r] == i) q = pick[i];
-            if (q < 0 || used[i][q])  // unmatched: any unused contribution
-              for (q = 0; used[i][q]; ++q) {}
+            int q = matched[i] ? pick[i] : -1;
+            if (q < 0) {  // conflict: prefer a record that somebody else reads in this round (broadcast), else any
+              for (int c2 = 0; c2 < it.n && q < 0; ++c2) {
+                if (used[i][c2]) continue;
+                for (int j = 0; j < gn && q < 0; ++j)
+                  if (j != i && matched[j] && pick[j] >= 0 && (items[ord[g0 + j]].ent[pick[j]] & 0xff) == (it.ent[c2] & 0xff)) q = c2;
+              }
+              if (q < 0) for (q = 0; used[i][q]; ++q) {}
+            }
             used[i][q] = true;
             sched_ent[i][k] = it.ent[q];
           }
         }
-        for (int i = 0; i < gn && !nomatch; ++i) {
+        for (int i = 0; i < gn; ++i) {
           Item& it = items[ord[g0 + i]];
           for (int k = 0; k < it.n; ++k) it.ent[k] = sched_ent[i][k];
         }
-        if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
+      }
+      {  // final slots: record with bank group r takes the next of r, r + 8, r + 16, ...
+        int next[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+        std::vector<int> slot(nrec);
+        std::vector<int32_t> recs2(nrec, 0);
+        for (int l = 0; l < nrec; ++l) { slot[l] = next[res[l]]; next[res[l]] += 8; recs2[slot[l]] = recs[l]; }
+        recs.swap(recs2);
+        for (auto& it : items)
+          for (int k = 0; k < it.n; ++k) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot[it.ent[k] & 0xff]);
+      }
+      if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
+        for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
+          int const gn = (int)std::min<size_t>(8, ord.size() - g0);
+          int nmax = 0;
+          for (int i = 0; i < gn; ++i) nmax = std::max(nmax, items[ord[g0 + i]].n);
           for (int k = 0; k < nmax; ++k) {
             int cnt[8] = {};
             for (int i = 0; i < gn; ++i) {
