@@ -360,7 +360,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
                          row_owner_smem(ctx, (int)ctx->opt_row_warps) <= 200 * 1024;
   bool patch_gather = with_values && ctx->opt_kernel == 3;
   if (patch_gather) {
-    if (ctx->ne >= (1 << 27)) { ctx->err = "kernel=3 supports fewer than 2^27 elements per part"; return GX_ERR_UNSUPPORTED; }
+    if (ctx->ne >= (1 << 27)) ctx->patch_state = -1;  // element ids no longer fit the schedule words: row fold instead
     int const rc = upload_patch_schedule(ctx);
     if (rc) return rc;
     patch_gather = ctx->patch_state == 1;
@@ -833,7 +833,8 @@ int gx_last_timing(gx_ctx* ctx, double t[4]) {
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return GX_ERR_ARG;
   std::string k(key);
-  if (k == "kernel") {  // Jacobian pass: 0 = element records + row fold (default), 1 = coloured elements, 2 = fused row-owner
+  if (k == "kernel") {  // Jacobian pass: 3 = element records + patch gather (default), 0 = element records + row fold,
+                        // 1 = coloured elements, 2 = fused row-owner
     if (value < 0 || value > 3) { ctx->err = "kernel must be 0..3"; return GX_ERR_ARG; }
     ctx->opt_kernel = value;
     return GX_OK;

@@ -160,7 +160,7 @@ struct gx_ctx {
   bool have_result = false;
   bool have_values = false;
   int64_t opt_block = 128;
-  int64_t opt_kernel = 0;  // Jacobian pass: 0 = element records + row fold, 1 = coloured elements, 2 = fused row-owner
+  int64_t opt_kernel = 3;  // Jacobian pass: 0 = element records + row fold, 1 = coloured elements, 2 = fused row-owner
   int64_t opt_row_warps = 4;
   int64_t opt_row_minblocks = 2;
   int64_t opt_fold_minblocks = 3;

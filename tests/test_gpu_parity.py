@@ -56,6 +56,7 @@ def test_jacobian_residual_state_parity(cube, model, mesh):
     f = fields(co, len(cn), strain=0.004)
     a, o = _pair(co, cn, model, f)
     R, A = a.jacobian(goal_b200.PRIMAL, save=True)
+    assert a.last_timing()["launches"] == 2  # element records + patch gather
     Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=True)
     assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
     assert relerr(a.get_state("sigma"), o.state("sigma")) < 1e-10
@@ -83,10 +84,10 @@ def test_jacobian_residual_state_parity(cube, model, mesh):
     a.close()
 
 
-@pytest.mark.parametrize("opts", [dict(fold_sorted=1), dict(kernel=2), dict(kernel=1), dict(kernel=3), dict(fold_sorted=1, fold_minblocks=2, row_warps=2)])
+@pytest.mark.parametrize("opts", [dict(), dict(kernel=0), dict(kernel=0, fold_sorted=0), dict(kernel=2), dict(kernel=1), dict(kernel=0, fold_minblocks=2, row_warps=2)])
 @pytest.mark.parametrize("mesh", ["cube", "kuhn7"])
 def test_kernel_variants_parity(cube, mesh, opts):
-    """Every Jacobian schedule (sorted fold, generic fold, fused row-owner, coloured, block gather) against the oracle,
+    """Every Jacobian schedule (patch gather = default, sorted fold, generic fold, fused row-owner, coloured) against the oracle,
     primal and adjoint, incl. the fixture whose nodes have up to 56 incident elements."""
     import goal_b200
     co, cn = _mesh(cube, mesh)
@@ -95,6 +96,8 @@ def test_kernel_variants_parity(cube, mesh, opts):
     for k, v in opts.items():
         a.set_option(k, v)
     R, A = a.jacobian(goal_b200.PRIMAL, save=True)
+    if not opts:
+        assert a.last_timing()["launches"] == 2  # element records + patch gather
     Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=True)
     assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
     assert relerr(a.get_state("sigma"), o.state("sigma")) < 1e-10
@@ -108,6 +111,36 @@ def test_kernel_variants_parity(cube, mesh, opts):
     assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12
     assert relerr(a.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"]),
                   o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])) < 1e-12
+    a.close()
+
+
+def _fan(k=9):
+    """k x k grid in the plane z = 0, every triangle joined to one apex: the apex has 2 (k-1)^2 incident elements."""
+    g = np.linspace(0.0, 1.0, k)
+    X, Y = np.meshgrid(g, g, indexing="ij")
+    co = np.concatenate([np.stack([X.ravel(), Y.ravel(), np.zeros(k * k)], axis=1), [[0.5, 0.5, 1.0]]])
+    apex = k * k
+    cn = []
+    for i in range(k - 1):
+        for j in range(k - 1):
+            a, b, c, d = i * k + j, (i + 1) * k + j, (i + 1) * k + j + 1, i * k + j + 1
+            cn += [[a, b, c, apex], [a, c, d, apex]]
+    return co, np.array(cn, dtype=np.int32)
+
+
+def test_patch_schedule_fallback():
+    """A node with more incident elements than a patch stages (128 > 120): the default Jacobian pass must fall back
+    to the row fold and still match the oracle."""
+    import goal_b200
+    co, cn = _fan(9)
+    f = fields(co, len(cn), strain=0.004)
+    a, o = _pair(co, cn, "J2", f)
+    R, A = a.jacobian(goal_b200.PRIMAL, save=True)
+    Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=True)
+    assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
+    assert a.last_timing()["launches"] == 3  # element records, sorted fold, generic fold (the apex): not the patch gather
+    At = a.jacobian(goal_b200.ADJOINT, save=False)[1].copy()
+    assert relerr(At, o.jacobian(goal_b200.ADJOINT, save=False)[1]) < 1e-12
     a.close()
 
 
