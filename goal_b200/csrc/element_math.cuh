@@ -203,8 +203,10 @@ struct Core {
   S mubar;     // mu*tr(be)/3 (J2)
   int plastic;
   // ---- tangent data, pre-scaled by vol (see "closed-form tangent" below)
-  S Tv[6];     // vol * tau
-  S Gm[6];     // vol * (g_r I + g_N N): maps r_m to the part of gamma_m that multiplies s w_n
+  // vol * tau = vb s + Jpv I and vol * (g_r I + g_N N) = gNs s + vgr I are carried as scalars next to s
+  S vb;        // vol * beta
+  S gNs;       // vol * g_N / |s|
+  S vgr;       // vol * g_r
   S gwv;       // vol * g_w
   S A1v;       // vol * beta * c1
   S Jpv;       // vol * J * p
@@ -280,7 +282,7 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   c.beta = S(1.0);
   c.mubar = S(0.0);
   S g_r = S(0.0), g_N = S(0.0), g_w = S(-2.0 / 3.0);  // elastic: gamma_m = -(2/3) w_m
-  S Nn[6] = {S(0.0), S(0.0), S(0.0), S(0.0), S(0.0), S(0.0)};
+  S gNs = S(0.0);
   if (MODEL == MODEL_NEOHOOKEAN) {
     S const Jm13 = gx_rcbrt(J);
     Jm23 = Jm13 * Jm13;
@@ -354,7 +356,8 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
       g_r = S(-4.0 / 3.0) * rs * dgam * c1 * (S(1.0) - S(2.0) * mubar * rD);
       g_N = S(4.0) * c1 * mubar * rs * (dgam * rs - rD);
       g_w = S(2.0 / 3.0) * c.beta * (S(2.0) * mubar * rD - S(1.0));
-      for (int i = 0; i < 6; ++i) { Nn[i] = N[i]; c.dN[i] = dgam * N[i]; }
+      gNs = g_N * rs;
+      for (int i = 0; i < 6; ++i) c.dN[i] = dgam * N[i];
     }
   }
   c.r[0][0] = -(c.r[1][0] + c.r[2][0] + c.r[3][0]);
@@ -375,10 +378,9 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
   for (int i = 0; i < 6; ++i) c.tau[i] = J * sig[i];
   // ---- pre-scaled tangent data
   S const vol = c.vol;
-  for (int i = 0; i < 6; ++i) c.Tv[i] = vol * c.tau[i];
-  S const vgN = vol * g_N, vgr = vol * g_r;
-  c.Gm[0] = vgN * Nn[0] + vgr; c.Gm[1] = vgN * Nn[1] + vgr; c.Gm[2] = vgN * Nn[2] + vgr;
-  c.Gm[3] = vgN * Nn[3]; c.Gm[4] = vgN * Nn[4]; c.Gm[5] = vgN * Nn[5];
+  c.vb = vol * c.beta;
+  c.gNs = vol * gNs;
+  c.vgr = vol * g_r;
   c.gwv = vol * g_w;
   c.A1v = vol * c.beta * c.c1;
   S const vJ = vol * J;
@@ -404,8 +406,14 @@ template <class S> GX_HD void plastic_update(S const dN[6], S const Fp_old[9], S
 // Residual.  R_u[n] = vol tau w_n,  R_p[n] = rb + vol taus J (q . w_n)
 // ---------------------------------------------------------------------------
 // One node's rows: out = (R_u[n][0..2], R_p[n]) for the node whose spatial gradient is wn.
+// (vol tau) w = vb (s w) + Jpv w
+template <class S> GX_HD void tau_mv(Core<S> const& c, S const w[3], S out[3]) {
+  S sw[3];
+  sym_mv(c.s, w, sw);
+  for (int k = 0; k < 3; ++k) out[k] = c.vb * sw[k] + c.Jpv * w[k];
+}
 template <class S> GX_HD void element_residual_row(Core<S> const& c, S const wn[3], S out[4]) {
-  sym_mv(c.Tv, wn, out);
+  tau_mv(c, wn, out);
   out[3] = c.rb + c.tjv * dot3(c.q, wn);
 }
 // Element residual: ru[n*3+i] (momentum), rp[n] (pressure + stabilization).
@@ -438,9 +446,10 @@ struct ColNode {
 // wm = w_m, rm = r_m (passed explicitly so that callers with a run-time node index can select them
 // without indexing the register-resident Core dynamically)
 template <class S> GX_HD void column_node(Core<S> const& c, S const wm[3], S const rm[3], ColNode<S>& cn) {
-  S tw[3], gr[3];
-  sym_mv(c.Tv, wm, tw);
-  sym_mv(c.Gm, rm, gr);
+  S tw[3], gr[3], sr[3];
+  tau_mv(c, wm, tw);
+  sym_mv(c.s, rm, sr);
+  for (int k = 0; k < 3; ++k) gr[k] = c.gNs * sr[k] + c.vgr * rm[k];
   S const m23 = S(-2.0 / 3.0);
   for (int k = 0; k < 3; ++k) {
     cn.w[k] = wm[k];
@@ -516,7 +525,7 @@ GX_HD void element_error_residual(Core<S> const& c, S const zu[4][3], S const zp
   S const qh = dot3(c.q, hz) * S(0.25);
   for (int n = 0; n < 4; ++n) {
     S tw[3];
-    sym_mv(c.Tv, c.w[n], tw);
+    tau_mv(c, c.w[n], tw);
     for (int i = 0; i < 3; ++i) ru[3 * n + i] = S(0.25) * c.vol * pg[i] + z[i] * tw[i];
     rp[n] = base + c.tjv * (qh + zc * dot3(c.q, c.w[n]));
   }

@@ -66,13 +66,6 @@ struct KParams {
 
 enum { PASS_RESIDUAL = 0, PASS_JACOBIAN = 1, PASS_JACOBIAN_T = 2, PASS_ERROR = 3 };
 
-#if defined(__CUDACC__)
-// one 32 B sector per lane (sm_100: LDG.E.256)
-__device__ __forceinline__ void ldg256(double const* p, double* o) {
-  asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p));
-}
-#endif
-
 template <class T> GX_HD T ldg(T const* p) {
 #if defined(__CUDA_ARCH__)
   return __ldg(p);
@@ -400,20 +393,35 @@ __global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_const
 // Schedule (1b), the default Jacobian pass: the row-owner schedule split in two kernels so that the
 // element core is evaluated once per element instead of once per incidence.
 //   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the
-//            56-double "tangent record" of the element (everything the 4x4 blocks are built from):
-//              {w_n[3] r_n[3]} x 4 nodes | Tv[6] Gm[6] s[6] | q[3] gwv A1v Jpv upc va tjv ppc rb | pad[3]
+//            46-double "tangent record" of the element (everything the 4x4 blocks are built from):
+//              {w_n[3] r_n[3]} x 4 nodes | s[6] | q[3] gwv A1v Jpv upc va tjv ppc vb gNs vgr rb | pad[2]
 //   stage B  row_fold_kernel    : one warp per node, one lane per incidence.  Each lane reads its
-//            element's record (448 B, contiguous), builds the four blocks of the node's rows, and the
+//            element's record (368 B, contiguous), builds the four blocks of the node's rows, and the
 //            warp folds and writes the node's CRS rows once, exactly like row_owner_kernel.
-// Costs 448 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
+// Costs 368 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
 // element core (about 60 % of all instructions of the fused kernel).
 // ---------------------------------------------------------------------------
-constexpr int ELEM_REC = 56;  // doubles
+constexpr int ELEM_REC = 46;  // doubles; 368 B = 23 x 16 B: an odd number of 16 B chunks, see patch_gather_kernel
+
+// chunks 12..21 of a record (16 B each) -> the tangent fields of Core
+template <bool GLOBAL>
+__device__ __forceinline__ void unpack_tangent(double2 const* q, Core<double>& c) {
+  auto ld = [&](int k) { return GLOBAL ? __ldg(q + k) : q[k]; };
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { double2 const v = ld(12 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y; }
+  double2 v = ld(15); c.q[0] = v.x; c.q[1] = v.y;
+  v = ld(16); c.q[2] = v.x; c.gwv = v.y;
+  v = ld(17); c.A1v = v.x; c.Jpv = v.y;
+  v = ld(18); c.upc = v.x; c.va = v.y;
+  v = ld(19); c.tjv = v.x; c.ppc = v.y;
+  v = ld(20); c.vb = v.x; c.gNs = v.y;
+  v = ld(21); c.vgr = v.x; c.rb = v.y;
+}
 
 template <int MODEL, bool SAVE>
 __global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
-  // records leave through shared memory so that a warp writes its 32 records (14 KB, contiguous) with
-  // fully coalesced 128-bit stores instead of 28 stride-448 B stores per thread
+  // records leave through shared memory so that a warp writes its 32 records (11.5 KB, contiguous) with
+  // fully coalesced 128-bit stores instead of 23 stride-368 B stores per thread
   __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 57 doubles (odd): conflict-free column writes
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -435,10 +443,10 @@ __global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__
 #pragma unroll
         for (int k = 0; k < 3; ++k) { mine[6 * q + k] = c.w[q][k]; mine[6 * q + 3 + k] = c.r[q][k]; }
 #pragma unroll
-      for (int k = 0; k < 6; ++k) { mine[24 + k] = c.Tv[k]; mine[30 + k] = c.Gm[k]; mine[36 + k] = c.s[k]; }
-      mine[42] = c.q[0]; mine[43] = c.q[1]; mine[44] = c.q[2]; mine[45] = c.gwv; mine[46] = c.A1v; mine[47] = c.Jpv;
-      mine[48] = c.upc; mine[49] = c.va; mine[50] = c.tjv; mine[51] = c.ppc; mine[52] = c.rb;
-      mine[53] = 0.0; mine[54] = 0.0; mine[55] = 0.0;
+      for (int k = 0; k < 6; ++k) mine[24 + k] = c.s[k];
+      mine[30] = c.q[0]; mine[31] = c.q[1]; mine[32] = c.q[2]; mine[33] = c.gwv; mine[34] = c.A1v; mine[35] = c.Jpv;
+      mine[36] = c.upc; mine[37] = c.va; mine[38] = c.tjv; mine[39] = c.ppc; mine[40] = c.vb; mine[41] = c.gNs;
+      mine[42] = c.vgr; mine[43] = c.rb; mine[44] = 0.0; mine[45] = 0.0;
       if (SAVE && MODEL == MODEL_J2 && c.plastic) save_plastic_Fp(P, e, c.dN);
     }
   }
@@ -462,10 +470,6 @@ __global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__
   }
 }
 
-// Per-lane tangent data of stage B: the record minus w/r (those stay in shared memory).
-struct LaneTangent {
-  double Tv[6], Gm[6], s[6], q[3], gwv, A1v, Jpv, upc, va, tjv, ppc, rb;
-};
 
 template <bool TRANSPOSE, int MINB>
 __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec) {
@@ -539,18 +543,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
             wr[(2 * k) * WR_LD] = v.x;
             wr[(2 * k + 1) * WR_LD] = v.y;
           }
-#pragma unroll
-          for (int k = 0; k < 3; ++k) {
-            double2 v = __ldg(q + 12 + k); c.Tv[2 * k] = v.x; c.Tv[2 * k + 1] = v.y;
-            v = __ldg(q + 15 + k); c.Gm[2 * k] = v.x; c.Gm[2 * k + 1] = v.y;
-            v = __ldg(q + 18 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y;
-          }
-          double2 v = __ldg(q + 21); c.q[0] = v.x; c.q[1] = v.y;
-          v = __ldg(q + 22); c.q[2] = v.x; c.gwv = v.y;
-          v = __ldg(q + 23); c.A1v = v.x; c.Jpv = v.y;
-          v = __ldg(q + 24); c.upc = v.x; c.va = v.y;
-          v = __ldg(q + 25); c.tjv = v.x; c.ppc = v.y;
-          v = __ldg(q + 26); c.rb = v.x;
+          unpack_tangent<true>(q, c);
         }
         double wn[3], rn3[3];
 #pragma unroll
@@ -717,20 +710,16 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
         Core<double> c;  // only the tangent fields are filled
         double wv[4][3], rv[4][3];
         {
-          // the 448 B record as 14 sector-sized (256-bit) loads: the lanes of a warp read 32 different records, so the
-          // L1 data pipe spends one wavefront per lane and load instruction whatever its width
-          double f[56];
+          double2 v[12];
 #pragma unroll
-          for (int k = 0; k < 14; ++k) ldg256(reinterpret_cast<double const*>(q) + 4 * k, f + 4 * k);
+          for (int k = 0; k < 12; ++k) v[k] = __ldg(q + k);
 #pragma unroll
-          for (int n4 = 0; n4 < 4; ++n4)
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { wv[n4][k] = f[6 * n4 + k]; rv[n4][k] = f[6 * n4 + 3 + k]; }
-#pragma unroll
-          for (int k = 0; k < 6; ++k) { c.Tv[k] = f[24 + k]; c.Gm[k] = f[30 + k]; c.s[k] = f[36 + k]; }
-          c.q[0] = f[42]; c.q[1] = f[43]; c.q[2] = f[44]; c.gwv = f[45]; c.A1v = f[46]; c.Jpv = f[47];
-          c.upc = f[48]; c.va = f[49]; c.tjv = f[50]; c.ppc = f[51]; c.rb = f[52];
+          for (int n4 = 0; n4 < 4; ++n4) {
+            wv[n4][0] = v[3 * n4].x; wv[n4][1] = v[3 * n4].y; wv[n4][2] = v[3 * n4 + 1].x;
+            rv[n4][0] = v[3 * n4 + 1].y; rv[n4][1] = v[3 * n4 + 2].x; rv[n4][2] = v[3 * n4 + 2].y;
+          }
         }
+        unpack_tangent<true>(q, c);
         double wn[3], rn3[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -819,7 +808,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 // are finished by their primary item from the secondaries' partial sums (fixed order).  Every block of the patch's
 // rows, and the rows' residual entries, are written exactly once.
 // ---------------------------------------------------------------------------
-constexpr int PATCH_REC_LD = 58;  // doubles between staged records: 464 B = 29 x 16 B, conflict-free 128-bit reads
+constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stride: 368 B = 23 x 16 B (odd), so the bank
+                                        // group of a record's chunk k is (7 slot + k) mod 8
 GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double); }
 
 template <bool TRANSPOSE>
@@ -834,7 +824,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 4) patch_gather_kernel(const __
   int const my_elem = (int)__ldg(w + 4 + tid);
   uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
   uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
-  // Record staging: thread r issues one bulk asynchronous copy (448 B, global -> shared) for record r; the copies
+  // Record staging: thread r issues one bulk asynchronous copy (368 B, global -> shared) for record r; the copies
   // report their bytes to an mbarrier that the whole block then waits on.
   uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
   if (tid == 0) {
@@ -870,22 +860,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, 4) patch_gather_kernel(const __
     int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
     double const* rp = srec + slot * PATCH_REC_LD;
     Core<double> c;  // only the tangent fields are filled
-    {
-      double2 const* q = reinterpret_cast<double2 const*>(rp);
-#pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        double2 v = q[12 + j]; c.Tv[2 * j] = v.x; c.Tv[2 * j + 1] = v.y;
-        v = q[15 + j]; c.Gm[2 * j] = v.x; c.Gm[2 * j + 1] = v.y;
-        v = q[18 + j]; c.s[2 * j] = v.x; c.s[2 * j + 1] = v.y;
-      }
-      double2 v = q[21]; c.q[0] = v.x; c.q[1] = v.y;
-      v = q[22]; c.q[2] = v.x; c.gwv = v.y;
-      v = q[23]; c.A1v = v.x; c.Jpv = v.y;
-      v = q[24]; c.upc = v.x; c.va = v.y;
-      v = q[25]; c.tjv = v.x; c.ppc = v.y;
-      c.rb = 0.0;
-      if (diag) c.rb = rp[52];
-    }
+    unpack_tangent<false>(reinterpret_cast<double2 const*>(rp), c);
     // row node = the node of this block row in the primal operator; roles swap for the transpose
     int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
     double wr[3], wc[3], rc[3];

@@ -289,7 +289,7 @@ bool build_patch_schedule(gx_ctx* c) {
   std::vector<std::vector<uint32_t>> out(nch);
   bool const stats = getenv("GX_SCHED_STATS") != nullptr;
   bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
-  std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0);
+  std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0), st_runs(nch, 0), st_recs(nch, 0);
   bool ok = true;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int ch = 0; ch < nch; ++ch) {
@@ -403,6 +403,10 @@ bool build_patch_schedule(gx_ctx* c) {
           for (int k = 0; k < it.n; ++k) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot[it.ent[k] & 0xff]);
       }
       if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
+        std::vector<int32_t> sr(recs);
+        std::sort(sr.begin(), sr.end());
+        for (size_t i = 0; i < sr.size(); ++i) if (i == 0 || sr[i] != sr[i - 1] + 1) st_runs[ch]++;
+        st_recs[ch] += (int64_t)sr.size();
         for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
           int const gn = (int)std::min<size_t>(8, ord.size() - g0);
           int nmax = 0;
@@ -502,9 +506,11 @@ bool build_patch_schedule(gx_ctx* c) {
   c->patch_state = 1;
   if (stats) {
     int64_t wv = 0, rd = 0;
-    for (int i = 0; i < nch; ++i) { wv += st_wave[i]; rd += st_rounds[i]; }
-    fprintf(stderr, "[gx] patch schedule: %d patches, %.2f nodes/patch, %.3f wavefronts per quarter-warp round\n", c->n_patches,
-            (double)nn / std::max(1, c->n_patches), rd ? (double)wv / (double)rd : 0.0);
+    int64_t runs = 0, nrecs = 0;
+    for (int i = 0; i < nch; ++i) { wv += st_wave[i]; rd += st_rounds[i]; runs += st_runs[i]; nrecs += st_recs[i]; }
+    fprintf(stderr, "[gx] patch schedule: %d patches, %.2f nodes/patch, %.1f records/patch in %.1f runs, %.3f wavefronts per quarter-warp round\n",
+            c->n_patches, (double)nn / std::max(1, c->n_patches), (double)nrecs / std::max(1, c->n_patches),
+            (double)runs / std::max(1, c->n_patches), rd ? (double)wv / (double)rd : 0.0);
   }
   return true;
 }
