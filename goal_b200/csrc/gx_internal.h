@@ -188,8 +188,14 @@ void build_block_lists(gx_ctx* c);
 bool build_patch_schedule(gx_ctx* c);
 
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
-constexpr int PATCH_THREADS = 128;  // work items per patch, one per thread
-constexpr int PATCH_RECS = 120;     // element records staged per patch (120 x 464 B: four blocks per SM)
+#ifndef GX_PATCH_THREADS
+#define GX_PATCH_THREADS 128
+#define GX_PATCH_RECS 120
+#define GX_PATCH_MINB 4
+#endif
+constexpr int PATCH_THREADS = GX_PATCH_THREADS;  // work items per patch, one per thread
+constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (368 B each)
+constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS;  // uint32 words per patch
 // gx_comm.cu

@@ -428,6 +428,11 @@ __global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__
   double* mine = &srec[wib][lane * (ELEM_REC + 1)];
   int plastic = 0;
   if (e < ne) {
+    if (SAVE && MODEL == MODEL_J2) {  // Fp_old is needed last (plastic elements only): have it in L1 by then
+      char const* f = reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)e);
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(f));
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(f + 64));
+    }
     int nd[4], b0[4], nb[4];
     Material const* matp;
     Core<double> c;
@@ -813,7 +818,7 @@ constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stri
 GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double); }
 
 template <bool TRANSPOSE>
-__global__ void __launch_bounds__(PATCH_THREADS, 4) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+__global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
                                                                         uint32_t const* __restrict__ sched) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
