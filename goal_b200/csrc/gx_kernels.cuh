@@ -815,7 +815,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 // ---------------------------------------------------------------------------
 constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stride: 368 B = 23 x 16 B (odd), so the bank
                                         // group of a record's chunk k is (7 slot + k) mod 8
-GX_HD size_t patch_smem_bytes() { return (size_t)PATCH_RECS * PATCH_REC_LD * sizeof(double); }
+GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * 20) * sizeof(double); }
 
 template <bool TRANSPOSE>
 __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
@@ -861,7 +861,10 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
     uint32_t const ent = (uint32_t)elo & 0xffffu;
     elo = (elo >> 16) | (ehi << 48); ehi >>= 16;
-    if (!(ent & 0x8000u)) break;
+    if (!(ent & 0x8000u)) {  // an empty round of this item (bank-conflict avoidance), or the end of its list
+      if ((elo | ehi) == 0) break;
+      continue;
+    }
     int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
     double const* rp = srec + slot * PATCH_REC_LD;
     Core<double> c;  // only the tangent fields are filled
@@ -894,27 +897,12 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
       r4[0] += t4[0]; r4[1] += t4[1]; r4[2] += t4[2]; r4[3] += t4[3];
     }
   }
-  __syncthreads();  // records are dead: their storage now carries the secondaries' partial sums, 20 doubles each
+  // Finish.  Items without secondaries write their block and leave; only the few items that exchange partial sums
+  // (diagonal blocks, edges of high valence: the longest items, i.e. the first warp) meet at the barrier.
   int const part = (int)((ot.z >> 16) & 0xffu);
-  if (kind == 2) {
-    double2* d = reinterpret_cast<double2*>(srec + 20 * part);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
-    d[8] = make_double2(r4[0], r4[1]);
-    d[9] = make_double2(r4[2], r4[3]);
-  }
-  __syncthreads();
-  if (kind == 1) {
-    int const nsec = (int)((ot.z >> 24) & 0x3fu);
-    for (int s = 0; s < nsec; ++s) {
-      double2 const* d = reinterpret_cast<double2 const*>(srec + 20 * (part + s));
-#pragma unroll
-      for (int k = 0; k < 8; ++k) { double2 const v = d[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
-      if (diag) {
-        double2 v = d[8]; r4[0] += v.x; r4[1] += v.y;
-        v = d[9]; r4[2] += v.x; r4[3] += v.y;
-      }
-    }
+  int const nsec = (int)((ot.z >> 24) & 0x3fu);
+  double* spart = srec + (size_t)PATCH_RECS * PATCH_REC_LD;  // [PATCH_PARTS][20]
+  auto write_out = [&]() {
     int64_t const voff = (int64_t)(((uint64_t)ot.y << 32) | (uint64_t)ot.x);
     int const rl = (int)(ot.z & 0xffffu);
     double* out = P.values + voff;
@@ -929,6 +917,28 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
       o[0] = make_double2(r4[0], r4[1]);
       o[1] = make_double2(r4[2], r4[3]);
     }
+  };
+  if (kind == 0) return;
+  if (kind == 1 && nsec == 0) { write_out(); return; }
+  if (kind == 2) {
+    double2* d = reinterpret_cast<double2*>(spart + 20 * part);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) d[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
+    d[8] = make_double2(r4[0], r4[1]);
+    d[9] = make_double2(r4[2], r4[3]);
+  }
+  __syncthreads();  // the threads that are still here
+  if (kind == 1) {
+    for (int s2 = 0; s2 < nsec; ++s2) {
+      double2 const* d = reinterpret_cast<double2 const*>(spart + 20 * (part + s2));
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { double2 const v = d[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
+      if (diag) {
+        double2 v = d[8]; r4[0] += v.x; r4[1] += v.y;
+        v = d[9]; r4[2] += v.x; r4[3] += v.y;
+      }
+    }
+    write_out();
   }
 }
 

@@ -274,7 +274,7 @@ void build_block_lists(gx_ctx* c) {
 // in a fixed order.  Layout per patch (uint32 words, PATCH_WORDS):
 //   [0..3]   n_recs, n_items, 0, 0
 //   [4..]    elems[PATCH_RECS]                      element id of each staged record
-//   then     items[PATCH_THREADS][4]                8 x 16-bit contributions: slot | n << 8 | m << 10 | 0x8000
+//   then     items[PATCH_THREADS][4]                8 rounds x 16 bit: slot | m << 8 | n << 10 | 0x8000, 0 = sits the round out
 //   then     outs[PATCH_THREADS][4]                 x,y = value offset of block entry (0,0) (int64, doubles)
 //                                                   z = row stride | part slot << 16 | n secondaries << 24 | kind << 30
 //                                                   w = node id | diagonal << 31
@@ -344,39 +344,55 @@ bool build_patch_schedule(gx_ctx* c) {
       }
       for (size_t g0 = 0; g0 < ord.size() && !nomatch; g0 += 8) {
         int const gn = (int)std::min<size_t>(8, ord.size() - g0);
+        // Rounds available to this group of 8 lanes: its warp runs as many rounds as its longest item, so an item
+        // may sit out a round (an empty entry) as long as it still finishes -- which lets the schedule dodge
+        // conflicts that a packed order cannot.
+        int const R = items[ord[(g0 / 32) * 32]].n;
         bool used[8][PATCH_ITEM_LEN] = {};
         uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
-        int nmax = 0;
-        for (int i = 0; i < gn; ++i) nmax = std::max(nmax, items[ord[g0 + i]].n);
-        for (int k = 0; k < nmax; ++k) {
+        int remaining[8] = {};
+        for (int i = 0; i < gn; ++i) remaining[i] = items[ord[g0 + i]].n;
+        for (int k = 0; k < R; ++k) {
+          int const left = R - k;
           int match_res[8];   // bank group -> item
           int pick[8];        // item -> contribution index
           for (int r = 0; r < 8; ++r) match_res[r] = -1;
           for (int i = 0; i < 8; ++i) pick[i] = -1;
-          // Kuhn's augmenting paths; items x bank groups, edges through unused contributions with a fixed group
+          // Kuhn's augmenting paths; items x bank groups, edges through unused contributions
+          int order[8][PATCH_ITEM_LEN], no[8] = {};
+          for (int i = 0; i < gn; ++i) {
+            Item const& it = items[ord[g0 + i]];
+            for (int q = 0; q < it.n; ++q) if (!used[i][q]) order[i][no[i]++] = q;
+          }
           auto try_item = [&](auto&& self, int i, bool* seen) -> bool {
             Item const& it = items[ord[g0 + i]];
-            for (int q = 0; q < it.n; ++q) {
-              if (used[i][q]) continue;
-              int const r = res[it.ent[q] & 0xff];
-              if (r < 0 || seen[r]) continue;
+            for (int oq = 0; oq < no[i]; ++oq) {  // a free bank group first
+              int const q = order[i][oq], r = res[it.ent[q] & 0xff];
+              if (match_res[r] < 0) { seen[r] = true; match_res[r] = i; pick[i] = q; return true; }
+            }
+            for (int oq = 0; oq < no[i]; ++oq) {
+              int const q = order[i][oq], r = res[it.ent[q] & 0xff];
+              if (seen[r]) continue;
               seen[r] = true;
-              if (match_res[r] < 0 || self(self, match_res[r], seen)) { match_res[r] = i; pick[i] = q; return true; }
+              if (self(self, match_res[r], seen)) { match_res[r] = i; pick[i] = q; return true; }
             }
             return false;
           };
+          for (int pass = 0; pass < 2; ++pass)  // items that cannot wait first
+            for (int i = 0; i < gn; ++i) {
+              if (remaining[i] == 0 || (remaining[i] == left) != (pass == 0)) continue;
+              bool seen[8] = {};
+              try_item(try_item, i, seen);
+            }
           bool matched[8] = {};
-          for (int i = 0; i < gn; ++i) {
-            if (items[ord[g0 + i]].n <= k) continue;
-            bool seen[8] = {};
-            try_item(try_item, i, seen);
-          }
           for (int r = 0; r < 8; ++r) if (match_res[r] >= 0) matched[match_res[r]] = true;
           for (int i = 0; i < gn; ++i) {
             Item const& it = items[ord[g0 + i]];
-            if (it.n <= k) continue;
+            if (remaining[i] == 0) continue;
             int q = matched[i] ? pick[i] : -1;
-            if (q < 0) {  // conflict: prefer a record that somebody else reads in this round (broadcast), else any
+            if (q < 0) {
+              if (remaining[i] < left) continue;  // sits this round out
+              // conflict: prefer a record that somebody else reads in this round (broadcast), else any
               for (int c2 = 0; c2 < it.n && q < 0; ++c2) {
                 if (used[i][c2]) continue;
                 for (int j = 0; j < gn && q < 0; ++j)
@@ -385,12 +401,13 @@ bool build_patch_schedule(gx_ctx* c) {
               if (q < 0) for (q = 0; used[i][q]; ++q) {}
             }
             used[i][q] = true;
+            remaining[i]--;
             sched_ent[i][k] = it.ent[q];
           }
         }
         for (int i = 0; i < gn; ++i) {
           Item& it = items[ord[g0 + i]];
-          for (int k = 0; k < it.n; ++k) it.ent[k] = sched_ent[i][k];
+          for (int k = 0; k < PATCH_ITEM_LEN; ++k) it.ent[k] = sched_ent[i][k];
         }
       }
       {  // final slots: record with bank group r takes the next of r, r + 8, r + 16, ...
@@ -400,7 +417,8 @@ bool build_patch_schedule(gx_ctx* c) {
         for (int l = 0; l < nrec; ++l) { slot[l] = next[res[l]]; next[res[l]] += 8; recs2[slot[l]] = recs[l]; }
         recs.swap(recs2);
         for (auto& it : items)
-          for (int k = 0; k < it.n; ++k) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot[it.ent[k] & 0xff]);
+          for (int k = 0; k < PATCH_ITEM_LEN; ++k)
+            if (it.ent[k] & 0x8000) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot[it.ent[k] & 0xff]);
       }
       if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
         std::vector<int32_t> sr(recs);
@@ -409,20 +427,21 @@ bool build_patch_schedule(gx_ctx* c) {
         st_recs[ch] += (int64_t)sr.size();
         for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
           int const gn = (int)std::min<size_t>(8, ord.size() - g0);
-          int nmax = 0;
-          for (int i = 0; i < gn; ++i) nmax = std::max(nmax, items[ord[g0 + i]].n);
-          for (int k = 0; k < nmax; ++k) {
+          for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
             int cnt[8] = {};
+            bool any = false;
             for (int i = 0; i < gn; ++i) {
               Item const& it = items[ord[g0 + i]];
-              if (it.n <= k) continue;
+              if (!(it.ent[k] & 0x8000)) continue;
+              any = true;
               bool dup = false;
               for (int j = 0; j < i; ++j) {
                 Item const& jt = items[ord[g0 + j]];
-                if (jt.n > k && (jt.ent[k] & 0xff) == (it.ent[k] & 0xff)) dup = true;
+                if ((jt.ent[k] & 0x8000) && (jt.ent[k] & 0xff) == (it.ent[k] & 0xff)) dup = true;
               }
               if (!dup) cnt[it.ent[k] & 7]++;
             }
+            if (!any) continue;
             int mx = 0;
             for (int r = 0; r < 8; ++r) mx = std::max(mx, cnt[r]);
             st_wave[ch] += mx; st_rounds[ch] += 1;
@@ -461,8 +480,8 @@ bool build_patch_schedule(gx_ctx* c) {
         int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
         nit += parts; nsecs += parts - 1;
       }
-      if (nit > PATCH_THREADS || (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > 63) { bad = true; break; }
-      if ((int)items.size() + nit > PATCH_THREADS || (int)recs.size() + add > PATCH_RECS || nparts + nsecs > PATCH_THREADS) flush();
+      if (nit > PATCH_THREADS || (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > PATCH_PARTS) { bad = true; break; }
+      if ((int)items.size() + nit > PATCH_THREADS || (int)recs.size() + add > PATCH_RECS || nparts + nsecs > PATCH_PARTS) flush();
       for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
         int32_t const e = c->adj[k].x >> 2;
         if (hfind(e) < 0) { hput(e, (int)recs.size()); recs.push_back(e); }
