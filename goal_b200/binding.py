@@ -29,8 +29,17 @@ SYMBOLS = [
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
     "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
-    "gx_apply_dbcs", "gx_node_graph",
+    "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
+    "gx_fetch_dmdu",
 ]
+
+# Mechanics::build_functional types by their yaml name (src/goal_mechanics.cpp:149-167)
+QOI = {"avg disp": 0, "avg disp subdomain": 1, "avg vm": 2, "max vm": 3, "point wise": 4}
+
+
+class GxQoi(C.Structure):
+    _fields_ = [("type", C.c_int32), ("elem_set", C.c_int32), ("rho", C.c_double), ("ks_max", C.c_double),
+                ("ks_scale", C.c_double), ("point_node", C.c_int32), ("point_idx", C.c_int32)]
 
 
 class GxError(RuntimeError):
@@ -98,6 +107,11 @@ def load_library():
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.gx_functional_avg_disp.argtypes = [vp, dp, vp]
     L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
+    L.gx_functional.argtypes = [vp, C.POINTER(GxQoi), dp, vp]
+    L.gx_ks_vm_max.argtypes = [vp, dp]
+    L.gx_ks_vm_scale.argtypes = [vp, C.c_double, C.c_double, dp]
+    L.gx_dmdu_dev.argtypes = [vp, C.POINTER(vp)]
+    L.gx_fetch_dmdu.argtypes = [vp, vp]
     L.gx_num_peers.argtypes = [vp, ip]
     L.gx_struct_pack.argtypes = [vp, C.c_int, C.POINTER(vp), lp]
     L.gx_struct_unpack.argtypes = [vp, C.c_int, vp, C.c_int64]
@@ -287,6 +301,32 @@ class Assembler:
         d = np.zeros(4 * self.nn) if with_dMdu else None
         self._ck(self.L.gx_functional_avg_disp(self.h, C.byref(J), _addr(d)))
         return (J.value, d) if with_dMdu else J.value
+
+    def functional(self, type, elem_set=0, rho=1.0, point=(0, 0), with_dMdu=False, ks=None):
+        """Any functional of Mechanics::build_functional by its yaml `type` (src/goal_mechanics.cpp:149-167) on the
+        device; with_dMdu also returns QoI<FADT>::scatter's dMdu (ghost layout).  ks = (max, scale) reduced over
+        parts for "max vm" on a partitioned mesh."""
+        q = GxQoi(QOI[type], elem_set, rho, 0.0 if ks is None else ks[0], 0.0 if ks is None else ks[1], point[0], point[1])
+        J = C.c_double()
+        d = np.zeros(4 * self.nn) if with_dMdu else None
+        self._ck(self.L.gx_functional(self.h, C.byref(q), C.byref(J), _addr(d)))
+        self.last_ks = (q.ks_max, q.ks_scale)
+        return (J.value, d) if with_dMdu else J.value
+
+    def ks_vm_max(self):
+        v = C.c_double()
+        self._ck(self.L.gx_ks_vm_max(self.h, C.byref(v)))
+        return v.value
+
+    def ks_vm_scale(self, rho, max_vm):
+        v = C.c_double()
+        self._ck(self.L.gx_ks_vm_scale(self.h, rho, max_vm, C.byref(v)))
+        return v.value
+
+    def fetch_dMdu(self):
+        d = np.zeros(4 * self.nn)
+        self._ck(self.L.gx_fetch_dmdu(self.h, _addr(d)))
+        return d
 
     def apply_dbcs(self, rows, g, with_jacobian):
         """set_resid_dbcs / set_jac_dbcs on the device-resident result (src/goal_dbcs.cpp:39-99)."""

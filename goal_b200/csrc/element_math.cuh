@@ -531,4 +531,34 @@ GX_HD void element_error_residual(Core<S> const& c, S const zu[4][3], S const zp
   }
 }
 
+// ---------------------------------------------------------------------------
+// Functionals of the stress (AvgVM goal_avg_vm.cpp:43-61, KSVM goal_ks_vm.cpp:89-99): von Mises stress of the
+// mixed Cauchy stress (compute_von_mises, goal_von_mises.cpp:6-18) and, in place of the FADT evaluation, its
+// closed-form derivative.  dev(sigma) = beta s / J, so vm = sqrt(3/2) beta |s| / J, independent of p, and for the
+// seed (m,k), with d(beta s) = gamma_mk s + beta c1 dev(e_k (x) r_m + r_m (x) e_k)  (gamma as in element_core),
+//   d vm = sqrt(3/2)/J { |s| gamma_mk + 2 beta c1 (N r_m)[k] - beta |s| w_m[k] },   N = s/|s|.
+// Returns vm; dvm[m][k] = vol * d vm / d u_(m,k)  (vol = w dv, the weight both functionals integrate with).
+// ---------------------------------------------------------------------------
+template <class S> GX_HD S element_von_mises(Core<S> const& c, S dvm[4][3]) {
+  S const s2 = c.s[0] * c.s[0] + c.s[1] * c.s[1] + c.s[2] * c.s[2] + S(2.0) * (c.s[3] * c.s[3] + c.s[4] * c.s[4] + c.s[5] * c.s[5]);
+  S const rs = s2 > S(0.0) ? gx_rsqrt(s2) : S(0.0);
+  S const smag = s2 * rs;
+  S const k = S(1.2247448713915890491) / c.J;  // sqrt(3/2) / J
+  for (int m = 0; m < 4; ++m) {
+    S sr[3];
+    sym_mv(c.s, c.r[m], sr);
+    for (int d = 0; d < 3; ++d) {
+      S const g = c.gNs * sr[d] + c.vgr * c.r[m][d] + c.gwv * c.w[m][d];  // vol * gamma_m[d]
+      dvm[m][d] = k * (smag * g + S(2.0) * c.A1v * rs * sr[d] - c.vb * smag * c.w[m][d]);
+    }
+  }
+  return k * (c.vb / c.vol) * smag;
+}
+// von Mises stress of a stored stress tensor (row-major 3x3), the reference's formula
+template <class S> GX_HD S von_mises9(S const t[9]) {
+  S const s1 = (t[0] - t[4]) * (t[0] - t[4]), s2 = (t[4] - t[8]) * (t[4] - t[8]), s3 = (t[8] - t[0]) * (t[8] - t[0]);
+  S const s4 = t[1] * t[1], s5 = t[5] * t[5], s6 = t[6] * t[6];
+  return sqrt(S(0.5) * (s1 + s2 + s3 + S(6.0) * (s4 + s5 + s6)));
+}
+
 }  // namespace gx

@@ -449,7 +449,7 @@ static void free_device(gx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord, ctx->d_node_order, ctx->d_diag_pos,
                   ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
-                  ctx->d_plastic, ctx->d_red, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
+                  ctx->d_plastic, ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -770,6 +770,123 @@ int gx_functional_avg_disp(gx_ctx* ctx, double* J, double* dMdu_out) {
     GX_CUDA(cudaGetLastError());
     GX_CUDA(cudaMemcpyAsync(dMdu_out, ctx->d_stage, sizeof(double) * 4 * (size_t)ctx->nn, cudaMemcpyDeviceToHost, ctx->stream));
   }
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+// KSVM<T>::pre_process (src/goal_ks_vm.cpp:36-87) on the saved sigma state of this part
+static int ks_vm_reduce(gx_ctx* ctx, int pass, double ks_max, double rho, double* out) {
+  int const nb = std::min(1023, (ctx->ne + 255) / 256);
+  ks_vm_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, ctx->d_state_out, ctx->d_nodes, ctx->d_conn, ctx->ne, pass, ks_max, rho);
+  GX_CUDA(cudaGetLastError());
+  double part[1023];
+  GX_CUDA(cudaMemcpyAsync(part, ctx->d_red, sizeof(double) * (size_t)nb, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  double r = 0.0;
+  for (int i = 0; i < nb; ++i) r = pass == 0 ? std::max(r, part[i]) : r + part[i];
+  *out = r;
+  return GX_OK;
+}
+
+int gx_ks_vm_max(gx_ctx* ctx, double* max_vm) {
+  if (!ctx || !max_vm) { if (ctx) ctx->err = "gx_ks_vm_max: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  return ks_vm_reduce(ctx, 0, 0.0, 0.0, max_vm);
+}
+int gx_ks_vm_scale(gx_ctx* ctx, double rho, double max_vm, double* scale) {
+  if (!ctx || !scale) { if (ctx) ctx->err = "gx_ks_vm_scale: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  return ks_vm_reduce(ctx, 1, max_vm, rho, scale);
+}
+
+int gx_functional(gx_ctx* ctx, gx_qoi* q, double* J, double* dMdu_out) {
+  if (!ctx || !q || !J) { if (ctx) ctx->err = "gx_functional: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  int const nn = ctx->nn, ne = ctx->ne;
+  if (q->type < GX_QOI_AVG_DISP || q->type > GX_QOI_POINT_WISE) { ctx->err = "gx_functional: unknown functional type"; return GX_ERR_ARG; }
+  if ((q->type == GX_QOI_AVG_DISP_SUBDOMAIN || q->type == GX_QOI_AVG_VM) && (q->elem_set < 0 || q->elem_set >= ctx->nsets)) {
+    ctx->err = "gx_functional: elem set out of range";
+    return GX_ERR_ARG;
+  }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->d_dMdu) GX_CUDA(cudaMalloc(&ctx->d_dMdu, sizeof(double) * 4 * (size_t)nn));
+  ctx->have_dMdu = false;
+  if (q->type == GX_QOI_POINT_WISE) {  // PointWise<T>::post_process (src/goal_point_wise.cpp:37-56): owned vertex only
+    if (q->point_node >= nn || q->point_idx < 0 || q->point_idx > 2) { ctx->err = "gx_functional: point out of range"; return GX_ERR_ARG; }
+    bool const mine = q->point_node >= 0 && (ctx->node_owner.empty() || ctx->node_owner[q->point_node] == ctx->rank);
+    *J = 0.0;
+    if (dMdu_out) {
+      GX_CUDA(cudaMemsetAsync(ctx->d_dMdu, 0, sizeof(double) * 4 * (size_t)nn, ctx->stream));
+      double const one = 1.0;
+      if (mine) GX_CUDA(cudaMemcpyAsync(ctx->d_dMdu + 4 * (size_t)q->point_node + q->point_idx, &one, sizeof one, cudaMemcpyHostToDevice, ctx->stream));
+      GX_CUDA(cudaMemcpyAsync(dMdu_out, ctx->d_dMdu, sizeof(double) * 4 * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
+      ctx->have_dMdu = true;
+    }
+    if (mine) GX_CUDA(cudaMemcpyAsync(J, &ctx->d_nodes[q->point_node].u[q->point_idx], sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GX_OK;
+  }
+  QoiParams Q;
+  Q.type = q->type; Q.es_idx = q->elem_set; Q.rho = q->rho; Q.ks_max = q->ks_max; Q.ks_scale = q->ks_scale;
+  if (q->type == GX_QOI_KS_VM) {
+    if (!(q->rho > 0.0)) { ctx->err = "gx_functional: max vm needs rho > 0"; return GX_ERR_ARG; }
+    if (!(q->ks_scale > 0.0)) {  // single part: pre_process here; several parts: the caller reduces gx_ks_vm_max / _scale
+      int rc = ks_vm_reduce(ctx, 0, 0.0, 0.0, &Q.ks_max);
+      if (rc) return rc;
+      if ((rc = ks_vm_reduce(ctx, 1, Q.ks_max, Q.rho, &Q.ks_scale))) return rc;
+      q->ks_max = Q.ks_max; q->ks_scale = Q.ks_scale;
+    }
+    if (!(Q.ks_scale > 0.0)) { ctx->err = "gx_functional: max vm: scale <= 0 (no stress state saved yet?)"; return GX_ERR_ARG; }
+  }
+  if (!ctx->d_elemrec) GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ne));
+  int const zero2[2] = {0, 0};
+  GX_CUDA(cudaMemcpyAsync(ctx->d_err, zero2, sizeof zero2, cudaMemcpyHostToDevice, ctx->stream));
+  KParams P;
+  fill_params(ctx, P);
+  P.R = ctx->d_dMdu;
+  double* rvec = dMdu_out ? ctx->d_elemrec : nullptr;
+  double* ev = ctx->d_stage;  // [ne]
+  if (ctx->model == GX_MODEL_J2) elem_qoi_kernel<MODEL_J2><<<(ne + 127) / 128, 128, 0, ctx->stream>>>(P, Q, rvec, ev, ne);
+  else elem_qoi_kernel<MODEL_NEOHOOKEAN><<<(ne + 127) / 128, 128, 0, ctx->stream>>>(P, Q, rvec, ev, ne);
+  int const nb = std::min(1023, (ne + 255) / 256);
+  sum_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, ev, ne);
+  bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb);
+  if (dMdu_out) node_gather_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(P, rvec);
+  GX_CUDA(cudaGetLastError());
+  int herr[2];
+  GX_CUDA(cudaMemcpyAsync(herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(J, ctx->d_red + 1023, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (dMdu_out) {
+    GX_CUDA(cudaMemcpyAsync(dMdu_out, ctx->d_dMdu, sizeof(double) * 4 * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
+    ctx->have_dMdu = true;
+  }
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (herr[0]) {
+    static const char* const what[] = {"", "inverted element (dv <= 0)", "inverted deformation (det F <= 0)", "J2: return mapping failed"};
+    char buf[160];
+    snprintf(buf, sizeof buf, "%s in element %d", what[herr[0] & 3], herr[1]);
+    ctx->err = buf;
+    return status_of_element_error(herr[0]);
+  }
+  // KSVM<T>::post_process (src/goal_ks_vm.cpp:102-105) replaces the element sum; with several parts the caller does
+  // the same with the reduced max / scale
+  if (q->type == GX_QOI_KS_VM) *J = Q.ks_max + (1.0 / Q.rho) * std::log(Q.ks_scale);
+  return GX_OK;
+}
+
+int gx_dmdu_dev(gx_ctx* ctx, double** dMdu_dev) {
+  if (!ctx || !dMdu_dev) return GX_ERR_ARG;
+  if (!ctx->have_dMdu) { ctx->err = "gx_dmdu_dev: no functional derivative on the device"; return GX_ERR_ARG; }
+  *dMdu_dev = ctx->d_dMdu;
+  return GX_OK;
+}
+int gx_fetch_dmdu(gx_ctx* ctx, double* dMdu_out) {
+  if (!ctx || !dMdu_out) return GX_ERR_ARG;
+  if (!ctx->have_dMdu) { ctx->err = "gx_fetch_dmdu: no functional derivative on the device"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  GX_CUDA(cudaMemcpyAsync(dMdu_out, ctx->d_dMdu, sizeof(double) * 4 * (size_t)ctx->nn, cudaMemcpyDeviceToHost, ctx->stream));
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }

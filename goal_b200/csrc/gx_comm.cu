@@ -458,7 +458,7 @@ int gx_interface_bytes(gx_ctx* ctx, int peer_index, int what, int64_t* send_byte
   if (!ctx->struct_done) { ctx->err = "structure exchange not finished"; return GX_ERR_ARG; }
   Peer& P = ctx->peers[peer_index];
   int64_t s = 0, r = 0;
-  if (what & 1) { s += 32 * (int64_t)P.send_nodes.size(); r += 32 * (int64_t)P.recv_nodes.size(); }
+  if (what & 5) { s += 32 * (int64_t)P.send_nodes.size(); r += 32 * (int64_t)P.recv_nodes.size(); }
   if (what & 2) { s += 8 * P.send_vals; r += 8 * P.recv_vals; }
   if (send_bytes) *send_bytes = s;
   if (recv_bytes) *recv_bytes = r;
@@ -468,7 +468,8 @@ int gx_interface_bytes(gx_ctx* ctx, int peer_index, int what, int64_t* send_byte
 static int pack_peer(gx_ctx* ctx, Peer& P, int what) {
   int const ns = (int)P.send_nodes.size();
   if (!ns) return GX_OK;
-  if (what & 1) pack_R_kernel<<<(4 * ns + 255) / 256, 256, 0, ctx->stream>>>(P.d_sendR, ctx->d_R, P.d_send_nodes, ns);
+  // what = 4: dMdu of the last gx_functional travels like R (gather_dMdu, goal_sol_info.cpp:37-39)
+  if (what & 5) pack_R_kernel<<<(4 * ns + 255) / 256, 256, 0, ctx->stream>>>(P.d_sendR, (what & 4) ? ctx->d_dMdu : ctx->d_R, P.d_send_nodes, ns);
   if (what & 2) pack_rows_kernel<<<ns, 128, 0, ctx->stream>>>(P.d_send, ctx->d_values, P.d_send_nodes, P.d_send_off, ctx->d_blk0_x, ctx->d_nblk_g, ns);
   GX_CUDA(cudaGetLastError());
   return GX_OK;
@@ -476,7 +477,7 @@ static int pack_peer(gx_ctx* ctx, Peer& P, int what) {
 static int unpack_peer(gx_ctx* ctx, Peer& P, int what, double const* bufR, double const* bufV) {
   int const nr = (int)P.recv_nodes.size();
   if (!nr) return GX_OK;
-  if (what & 1) unpack_R_kernel<<<(4 * nr + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_R, bufR, P.d_recv_nodes, nr);
+  if (what & 5) unpack_R_kernel<<<(4 * nr + 255) / 256, 256, 0, ctx->stream>>>((what & 4) ? ctx->d_dMdu : ctx->d_R, bufR, P.d_recv_nodes, nr);
   if (what & 2)
     unpack_rows_kernel<<<nr, 128, 0, ctx->stream>>>(ctx->d_values, bufV, P.d_recv_nodes, P.d_recv_off, P.d_recv_cnt, P.d_recv_map,
                                                     P.d_recv_moff, ctx->d_blk0_x, ctx->d_nblk_x, nr);
@@ -489,12 +490,13 @@ int gx_pack_interface(gx_ctx* ctx, int peer_index, int what, void** send_dev) {
   int rc = check_peer(ctx, peer_index);
   if (rc) return rc;
   if ((rc = need_device(ctx, "gx_pack_interface"))) return rc;
-  if (what != 1 && what != 2) { ctx->err = "what must be 1 (R) or 2 (dRdu)"; return GX_ERR_ARG; }
+  if (what != 1 && what != 2 && what != 4) { ctx->err = "what must be 1 (R), 2 (dRdu) or 4 (dMdu)"; return GX_ERR_ARG; }
+  if (what == 4 && !ctx->have_dMdu) { ctx->err = "no functional derivative on the device"; return GX_ERR_ARG; }
   Peer& P = ctx->peers[peer_index];
   GX_CUDA(cudaSetDevice(ctx->device));
   if ((rc = pack_peer(ctx, P, what))) return rc;
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (send_dev) *send_dev = what == 1 ? (void*)P.d_sendR : (void*)P.d_send;
+  if (send_dev) *send_dev = what != 2 ? (void*)P.d_sendR : (void*)P.d_send;
   return GX_OK;
 }
 
@@ -502,7 +504,8 @@ int gx_unpack_add_interface(gx_ctx* ctx, int peer_index, int what, const void* r
   int rc = check_peer(ctx, peer_index);
   if (rc) return rc;
   if ((rc = need_device(ctx, "gx_unpack_add_interface"))) return rc;
-  if (what != 1 && what != 2) { ctx->err = "what must be 1 (R) or 2 (dRdu)"; return GX_ERR_ARG; }
+  if (what != 1 && what != 2 && what != 4) { ctx->err = "what must be 1 (R), 2 (dRdu) or 4 (dMdu)"; return GX_ERR_ARG; }
+  if (what == 4 && !ctx->have_dMdu) { ctx->err = "no functional derivative on the device"; return GX_ERR_ARG; }
   Peer& P = ctx->peers[peer_index];
   GX_CUDA(cudaSetDevice(ctx->device));
   if ((rc = unpack_peer(ctx, P, what, (double const*)recv_dev, (double const*)recv_dev))) return rc;
@@ -586,15 +589,16 @@ int gx_reduce_interfaces(gx_ctx* ctx, int what) {
   int rc = need_device(ctx, "gx_reduce_interfaces");
   if (rc) return rc;
   if (!ctx->comm || !ctx->struct_done) { ctx->err = "gx_reduce_interfaces: call gx_comm_init first"; return GX_ERR_ARG; }
-  if (!(what & 3)) return GX_OK;
+  if (!(what & 7)) return GX_OK;
+  if ((what & 4) && (what != 4 || !ctx->have_dMdu)) { ctx->err = "gx_reduce_interfaces: what = 4 (dMdu) goes alone, after gx_functional with a derivative"; return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
   GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   for (auto& P : ctx->peers) if ((rc = pack_peer(ctx, P, what))) return rc;
   GX_NCCL(ctx->nccl->GroupStart());
   for (auto& P : ctx->peers) {
     size_t const ns = P.send_nodes.size(), nr = P.recv_nodes.size();
-    if ((what & 1) && ns) GX_NCCL(ctx->nccl->Send(P.d_sendR, 4 * ns, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
-    if ((what & 1) && nr) GX_NCCL(ctx->nccl->Recv(P.d_recvR, 4 * nr, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
+    if ((what & 5) && ns) GX_NCCL(ctx->nccl->Send(P.d_sendR, 4 * ns, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
+    if ((what & 5) && nr) GX_NCCL(ctx->nccl->Recv(P.d_recvR, 4 * nr, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
     if ((what & 2) && P.send_vals) GX_NCCL(ctx->nccl->Send(P.d_send, (size_t)P.send_vals, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
     if ((what & 2) && P.recv_vals) GX_NCCL(ctx->nccl->Recv(P.d_recv, (size_t)P.recv_vals, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
   }

@@ -135,6 +135,8 @@ struct gx_ctx {
   int* d_err = nullptr;                 // {code, element}
   unsigned long long* d_plastic = nullptr;
   double* d_red = nullptr;              // reduction scratch
+  double* d_dMdu = nullptr;             // [4 nn] ghost dMdu of the last gx_functional (lazy)
+  bool have_dMdu = false;
   int32_t* d_child_off = nullptr;       // parent -> children CRS for set_error
   int32_t* d_child = nullptr;
   int n_parent_cached = -1;

@@ -1010,6 +1010,117 @@ __global__ void __launch_bounds__(256) node_gather_kernel(const __grid_constant_
   out[0] = make_double2(r0, r1);
   out[1] = make_double2(r2, r3);
 }
+// ---------------------------------------------------------------------------
+// Functionals (Mechanics::build_functional, goal_mechanics.cpp:149-167; QoI<T> goal_qoi.cpp:21-82): one thread per
+// element evaluates the QoI evaluator behind the save=false chain and writes the element value ev[e] and, when
+// rvec != nullptr, d elem_value / d dof as one 128 B line rvec[e][n][4] -- node_gather_kernel then sums them per
+// node into dMdu exactly like the residual (QoI<FADT>::scatter, goal_qoi.cpp:63-76), no atomics.
+//   type: GX_QOI_AVG_DISP / _SUBDOMAIN (goal_avg_disp.cpp:17-21, goal_avg_disp_subdomain.cpp:37-53),
+//         GX_QOI_AVG_VM (goal_avg_vm.cpp:43-61), GX_QOI_KS_VM (goal_ks_vm.cpp:89-99; ks = max, scale, rho)
+// ---------------------------------------------------------------------------
+struct QoiParams { int type, es_idx; double ks_max, ks_scale, rho; };
+enum { QOI_AVG_DISP = 0, QOI_AVG_DISP_SUBDOMAIN = 1, QOI_AVG_VM = 2, QOI_KS_VM = 3 };
+
+template <int MODEL>
+__global__ void __launch_bounds__(128) elem_qoi_kernel(const __grid_constant__ KParams P, QoiParams const Q, double* __restrict__ rvec,
+                                                       double* __restrict__ ev, int ne) {
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double d[4][3], val = 0.0;
+#pragma unroll
+  for (int n = 0; n < 4; ++n) d[n][0] = d[n][1] = d[n][2] = 0.0;
+  bool const in_set = Q.type == QOI_AVG_DISP || Q.type == QOI_KS_VM || (P.eset ? P.eset[e] : 0) == Q.es_idx;
+  if (in_set) {
+    int nd[4], b0[4], nb[4];
+    Material const* matp;
+    Core<double> c;
+    // the whole chain runs in the reference too (Functional builds build_resid<T> first, goal_functional.cpp:41-45),
+    // so an inverted element / deformation is reported here as well
+    int const rc = load_and_update<MODEL, false>(P, e, false, nd, b0, nb, matp, c);
+    if (rc != ERR_NONE) {
+      report_error(P.err, rc, e);
+    } else if (Q.type == QOI_AVG_DISP || Q.type == QOI_AVG_DISP_SUBDOMAIN) {
+      double us = 0.0;
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        double2 const* q = reinterpret_cast<double2 const*>(P.nodes + nd[n]);
+        double2 const d1 = ldg(q + 1), d2 = ldg(q + 2);
+        us += 0.25 * (d1.y + d2.x + d2.y);
+      }
+      val = us * c.vol * (1.0 / 3.0);
+      double const g = 0.25 * c.vol * (1.0 / 3.0);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) d[n][0] = d[n][1] = d[n][2] = g;
+    } else {
+      double const vm = element_von_mises(c, d);
+      double f = 1.0;  // d elem_value / d vm, per unit volume
+      if (Q.type == QOI_KS_VM) {
+        double const ex = exp(Q.rho * (vm - Q.ks_max));
+        val = (1.0 / (Q.rho * Q.ks_scale)) * ex * c.vol;
+        f = ex / Q.ks_scale;
+      } else {
+        val = vm * c.vol;
+      }
+#pragma unroll
+      for (int n = 0; n < 4; ++n) { d[n][0] *= f; d[n][1] *= f; d[n][2] *= f; }
+    }
+  }
+  ev[e] = val;
+  if (rvec) {
+    double2* o = reinterpret_cast<double2*>(rvec + 16 * (int64_t)e);
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      o[2 * n] = make_double2(d[n][0], d[n][1]);
+      o[2 * n + 1] = make_double2(d[n][2], 0.0);
+    }
+  }
+}
+
+// KSVM<T>::pre_process (goal_ks_vm.cpp:36-87) over the saved "sigma" state: pass 0 = max vm per block,
+// pass 1 = sum of exp(rho (vm - max)) w dv per block (fixed-shape tree: deterministic)
+__global__ void __launch_bounds__(256) ks_vm_partial_kernel(double* partial, double const* state_out, NodeRec const* nodes, int4 const* conn,
+                                                            int ne, int pass, double ks_max, double rho) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    double t[9];
+    for (int k = 0; k < 9; ++k) t[k] = state_out[(int64_t)STATE_OUT * e + k];
+    double const vm = von_mises9(t);
+    if (pass == 0) {
+      s = fmax(s, vm);
+    } else {
+      int4 const cn = conn[e];
+      int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+      double x[4][3];
+      for (int n = 0; n < 4; ++n) { x[n][0] = nodes[nd[n]].x[0]; x[n][1] = nodes[nd[n]].x[1]; x[n][2] = nodes[nd[n]].x[2]; }
+      double e1[3], e2[3], e3[3], c23[3];
+      for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; e3[j] = x[3][j] - x[0][j]; }
+      cross3(e2, e3, c23);
+      s += exp(rho * (vm - ks_max)) * (dot3(e1, c23) * (1.0 / 6.0));
+    }
+  }
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] = pass == 0 ? fmax(sh[threadIdx.x], sh[threadIdx.x + w]) : sh[threadIdx.x] + sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+// sum of x[0..n) in a fixed-shape tree (block partials; the caller adds them in index order)
+__global__ void __launch_bounds__(256) sum_partial_kernel(double* partial, double const* x, int64_t n) {
+  __shared__ double sh[256];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += x[i];
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
 #endif
+
 
 }  // namespace gx

@@ -139,6 +139,33 @@ int gx_element_error(gx_ctx* ctx, const double* u_err /*[n_nodes*3]*/, const dou
  *   *J = sum over this part's elements of (sum_i u_i(xi_c)) w dv / 3   (PCU_Add across parts: gx_allreduce_sum)
  * dMdu_out ([4*n_nodes], ghost layout, may be NULL) receives what QoI<FADT>::scatter adds (src/goal_qoi.cpp:63-76). */
 int gx_functional_avg_disp(gx_ctx* ctx, double* J, double* dMdu_out);
+/* Every functional of Mechanics::build_functional (src/goal_mechanics.cpp:149-167), evaluated behind the save=false
+ * residual chain like Functional::compute (src/goal_functional.cpp:41-45, 62-70):
+ *   GX_QOI_AVG_DISP            "avg disp"            src/goal_avg_disp.cpp:17-21
+ *   GX_QOI_AVG_DISP_SUBDOMAIN  "avg disp subdomain"  src/goal_avg_disp_subdomain.cpp:37-53   (elem_set)
+ *   GX_QOI_AVG_VM              "avg vm"              src/goal_avg_vm.cpp:43-61, goal_von_mises.cpp:6-18 (elem_set)
+ *   GX_QOI_KS_VM               "max vm"              src/goal_ks_vm.cpp:36-105 (rho; max/scale from the saved sigma)
+ *   GX_QOI_POINT_WISE          "point wise"          src/goal_point_wise.cpp:37-56 (point_node ghost-local or -1, point_idx)
+ * *J = this part's value (PCU_Add across parts: gx_allreduce_sum).  dMdu_out ([4*n_nodes] ghost layout, may be
+ * NULL) receives what QoI<FADT>::scatter adds (src/goal_qoi.cpp:63-76); the derivative of the stress functionals
+ * is closed-form (no FAD).  It also stays on the device: gx_dmdu_dev, and gx_reduce_interfaces(ctx, 4) ==
+ * SolInfo::gather_dMdu (src/goal_sol_info.cpp:37-39).
+ * "max vm": with ks_scale <= 0 on entry the part-local max / scale are computed here and returned in *q (single
+ * part).  With several parts reduce gx_ks_vm_max (PCU_Max) and gx_ks_vm_scale (PCU_Add) on the host, pass them in
+ * q, and take J = ks_max + log(ks_scale)/rho (KSVM::post_process). */
+enum { GX_QOI_AVG_DISP = 0, GX_QOI_AVG_DISP_SUBDOMAIN = 1, GX_QOI_AVG_VM = 2, GX_QOI_KS_VM = 3, GX_QOI_POINT_WISE = 4 };
+typedef struct {
+  int32_t type;        /* GX_QOI_* */
+  int32_t elem_set;    /* "elem set" index (subdomain / avg vm) */
+  double rho;          /* "max vm" */
+  double ks_max, ks_scale; /* "max vm": in (ks_scale > 0) or out */
+  int32_t point_node, point_idx; /* "point wise" */
+} gx_qoi;
+int gx_functional(gx_ctx* ctx, gx_qoi* q, double* J, double* dMdu_out);
+int gx_ks_vm_max(gx_ctx* ctx, double* max_vm);
+int gx_ks_vm_scale(gx_ctx* ctx, double rho, double max_vm, double* scale);
+int gx_dmdu_dev(gx_ctx* ctx, double** dMdu_dev);
+int gx_fetch_dmdu(gx_ctx* ctx, double* dMdu_out);
 /* Dirichlet rows on the device-resident result of the last compute call (set_resid_dbcs / set_jac_dbcs,
  * src/goal_dbcs.cpp:39-99): for each listed ghost-local dof row (which must be owned by this rank):
  * R[row] = solution - g; with_jacobian != 0 additionally zeroes the CRS row and puts 1 on the diagonal.
@@ -168,7 +195,8 @@ int gx_exchange_plan(gx_ctx* ctx, int peer_index, int32_t* peer_rank, int32_t co
 
 /* SolInfo::gather_R / gather_dRdu (Tpetra Export ghost->owned, ADD; src/goal_sol_info.cpp:33-43)
  * over NCCL.  After it, rows of nodes this part owns hold the sum over all parts, rows of
- * nodes owned elsewhere are left as local partial sums.  what: bit 0 = R, bit 1 = dRdu. */
+ * nodes owned elsewhere are left as local partial sums.  what: bit 0 = R, bit 1 = dRdu; or what = 4 alone:
+ * dMdu of the last gx_functional (gather_dMdu, src/goal_sol_info.cpp:37-39). */
 int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes);
 int gx_nccl_unique_id(void* out, size_t* id_bytes); /* helper: rank 0 creates, host code broadcasts */
 int gx_reduce_interfaces(gx_ctx* ctx, int what);

@@ -349,7 +349,7 @@ template <class T> void store_tensor(double* dst, Ten<T> const& A) {  // set_ten
 // ru[n*3+i], rp[n] are the element residuals the u / p evaluators own.
 template <class T>
 bool chain(go_ctx& c, int e, TetGeom const& g, Weights const& w, bool save, T ru[12], T rp[4],
-           T* uval /*[3], optional*/) {
+           T* uval /*[3], optional*/, Ten<T>* cauchy = nullptr /* model->get_cauchy() after Mixed, optional */) {
   Material const m = material(c, c.eset.empty() ? 0 : c.eset[e]);
   int32_t const* nd = &c.conn[4 * (size_t)e];
 
@@ -458,6 +458,7 @@ bool chain(go_ctx& c, int e, TetGeom const& g, Weights const& w, bool save, T ru
     pbar /= 3;
     for (int i = 0; i < 3; ++i) sigma(i, i) += pv - pbar;
     if (save) store_tensor(sig_dst, sigma);
+    if (cauchy) *cauchy = sigma;
   }
   // --- MResidual<T>::at_point (goal_mresidual.cpp:26-32) with
   //     Model::get_first_pk (goal_neohookean.cpp:80-86, goal_J2.cpp:151-157)
@@ -643,6 +644,108 @@ double go_functional_avg_disp(go_ctx* c, double* dMdu) {
   }
   return J;
 }
+
+}  // extern "C"
+
+namespace {
+// compute_von_mises (goal_von_mises.cpp:6-18)
+template <class T> T von_mises(Ten<T> const& sigma) {
+  T s1 = (sigma(0, 0) - sigma(1, 1)) * (sigma(0, 0) - sigma(1, 1));
+  T s2 = (sigma(1, 1) - sigma(2, 2)) * (sigma(1, 1) - sigma(2, 2));
+  T s3 = (sigma(2, 2) - sigma(0, 0)) * (sigma(2, 2) - sigma(0, 0));
+  T s4 = sigma(0, 1) * sigma(0, 1);
+  T s5 = sigma(1, 2) * sigma(1, 2);
+  T s6 = sigma(2, 0) * sigma(2, 0);
+  T s7 = 0.5 * (s1 + s2 + s3 + 6.0 * (s4 + s5 + s6));
+  return sqrt(s7);
+}
+inline Fad exp(Fad const& a) { double e = std::exp(a.v); return fn1(a, e, e); }
+using std::exp;
+
+// One element of the functional chain: build_resid<T>(save = false) followed by the QoI evaluator
+// (goal_functional.cpp:41-45, goal_mechanics.cpp:149-167).  ks = {max, scale, rho} for "max vm".
+template <class T>
+bool qoi_element(go_ctx& c, int e, int type, int es_idx, double const ks[3], T& elem_value) {
+  TetGeom g; Weights w;
+  if (!elem_geometry(c, e, g)) return false;
+  plain_weights(g, w);
+  T ru[12], rp[4], uv[3];
+  Ten<T> sigma;
+  if (!chain<T>(c, e, g, w, false, ru, rp, uv, &sigma)) return false;
+  // QoI<T>::gather: elem_value = 0 (FADT: diff(0, num_dofs) with dx(0) = 0, goal_qoi.cpp:54-60)
+  elem_value = T(0.0);
+  if constexpr (std::is_same<T, Fad>::value) { elem_value.diff(0, ND); elem_value.d[0] = 0.0; }
+  int const es = c.eset.empty() ? 0 : c.eset[e];
+  switch (type) {
+    case GO_QOI_AVG_DISP:  // goal_avg_disp.cpp:17-21
+      for (int i = 0; i < 3; ++i) elem_value += uv[i] * g.w * g.dv;
+      elem_value /= 3;
+      break;
+    case GO_QOI_AVG_DISP_SUBDOMAIN:  // goal_avg_disp_subdomain.cpp:37-53
+      if (es == es_idx) {
+        for (int i = 0; i < 3; ++i) elem_value += uv[i] * g.w * g.dv;
+        elem_value /= 3;
+      }
+      break;
+    case GO_QOI_AVG_VM:  // goal_avg_vm.cpp:43-61
+      if (es == es_idx) {
+        T vm = von_mises(sigma);
+        elem_value += vm * g.w * g.dv;
+      }
+      break;
+    case GO_QOI_KS_VM: {  // goal_ks_vm.cpp:89-99
+      T vm = von_mises(sigma);
+      elem_value += (1.0 / (ks[2] * ks[1])) * exp(ks[2] * (vm - ks[0])) * g.w * g.dv;
+      break;
+    }
+    default: return false;
+  }
+  return true;
+}
+}  // namespace
+
+extern "C" double go_functional(go_ctx* c, int type, int elem_set, double rho, int point_node, int point_idx,
+                                double* dMdu) {
+  c->err.clear();
+  if (type == GO_QOI_POINT_WISE) {  // PointWise<T>::post_process (goal_point_wise.cpp:37-56)
+    if (dMdu) dMdu[4 * (size_t)point_node + point_idx] = 1.0;
+    return c->u[3 * (size_t)point_node + point_idx];
+  }
+  double ks[3] = {0.0, 0.0, rho};
+  if (type == GO_QOI_KS_VM) {
+    // KSVM<T>::pre_process: get_max_vm / get_scale over the saved "sigma" state (goal_ks_vm.cpp:36-87)
+    for (int e = 0; e < c->ne; ++e) {
+      Ten<double> sg;
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sg(i, j) = c->sigma[9 * (size_t)e + 3 * i + j];
+      ks[0] = std::max(ks[0], von_mises(sg));
+    }
+    for (int e = 0; e < c->ne; ++e) {
+      TetGeom g;
+      if (!elem_geometry(*c, e, g)) return NAN;
+      Ten<double> sg;
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) sg(i, j) = c->sigma[9 * (size_t)e + 3 * i + j];
+      ks[1] += std::exp(rho * (von_mises(sg) - ks[0])) * g.w * g.dv;
+    }
+  }
+  double J = 0.0;
+  for (int e = 0; e < c->ne; ++e) {
+    if (dMdu) {  // QoI<FADT>::scatter (goal_qoi.cpp:63-76)
+      Fad ev;
+      if (!qoi_element<Fad>(*c, e, type, elem_set, ks, ev)) return NAN;
+      for (int n = 0; n < 4; ++n)
+        for (int eq = 0; eq < 4; ++eq) dMdu[4 * (size_t)c->conn[4 * (size_t)e + n] + eq] += ev.dx(4 * n + eq);
+      J += ev.v;
+    } else {  // QoI<ST>::scatter (goal_qoi.cpp:31-34)
+      double ev;
+      if (!qoi_element<double>(*c, e, type, elem_set, ks, ev)) return NAN;
+      J += ev;
+    }
+  }
+  if (type == GO_QOI_KS_VM) J = ks[0] + (1.0 / rho) * std::log(ks[1]);  // KSVM<T>::post_process (goal_ks_vm.cpp:102-105)
+  return J;
+}
+
+extern "C" {
 
 int go_assemble_error(go_ctx* c, const double* zu_diff, const double* zp_diff, const double* zp_coarse,
                       double* R) {

@@ -63,6 +63,13 @@ int go_assemble_jacobian(go_ctx*, int mode, int save_state, double* R, double* v
  * if dMdu != NULL, its FAD derivative scattered like QoI<FADT>::scatter. */
 double go_functional_avg_disp(go_ctx*, double* dMdu /*[4Nn] or NULL*/);
 
+/* The reference's functionals (Mechanics::build_functional, src/goal_mechanics.cpp:149-167) evaluated behind the
+ * save=false residual chain like Functional::compute (src/goal_functional.cpp:62-70); with dMdu != NULL the FADT
+ * chain and QoI<FADT>::scatter (src/goal_qoi.cpp:63-76; dMdu is NOT zeroed here).  elem_set: "elem set" index of
+ * the subdomain / avg-vm functionals; rho: KS parameter of "max vm"; point_node/point_idx: "point wise". */
+enum { GO_QOI_AVG_DISP = 0, GO_QOI_AVG_DISP_SUBDOMAIN = 1, GO_QOI_AVG_VM = 2, GO_QOI_KS_VM = 3, GO_QOI_POINT_WISE = 4 };
+double go_functional(go_ctx*, int type, int elem_set, double rho, int point_node, int point_idx, double* dMdu);
+
 /* error chain (src/goal_mechanics.cpp:169-218) with adjoint-weighted test
  * functions (goal_displacement_adjoint.cpp:37-53, goal_pressure_adjoint.cpp:38-49) */
 int go_assemble_error(go_ctx*, const double* zu_diff /*[Nn*3]*/, const double* zp_diff /*[Nn]*/,

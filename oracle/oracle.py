@@ -14,6 +14,7 @@ _LIB = None
 
 MODEL = {"neohookean": 0, "J2": 1}
 NONE, PRIMAL, ADJOINT = 0, 1, 2
+QOI = {"avg disp": 0, "avg disp subdomain": 1, "avg vm": 2, "max vm": 3, "point wise": 4}
 
 
 def build(force=False):
@@ -47,6 +48,8 @@ def lib():
         L.go_functional_avg_disp.restype = C.c_double
         L.go_functional_avg_disp.argtypes = [C.c_void_p, dp]
         L.go_assemble_error.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.go_functional.restype = C.c_double
+        L.go_functional.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, dp]
         L.go_element_error.restype = C.c_double
         L.go_element_error.argtypes = [C.c_void_p, dp, dp, dp, ip, C.c_int, dp]
         L.go_last_plastic_count.restype = C.c_int64
@@ -127,6 +130,14 @@ class Oracle:
             d = np.zeros(4 * self.nn)
             return self.L.go_functional_avg_disp(self.h, _dp(d)), d
         return self.L.go_functional_avg_disp(self.h, None)
+
+    def functional(self, type, elem_set=0, rho=1.0, point=(0, 0), with_dMdu=False):
+        """Any of the reference's functionals by its yaml `type` (src/goal_mechanics.cpp:149-167)."""
+        d = np.zeros(4 * self.nn) if with_dMdu else None
+        J = self.L.go_functional(self.h, QOI[type], elem_set, rho, point[0], point[1], None if d is None else _dp(d))
+        if J != J:
+            raise RuntimeError(self.L.go_last_error(self.h).decode())
+        return (J, d) if with_dMdu else J
 
     def localize(self, zu_diff, zp_diff, zp_coarse, R=None):
         R = np.zeros(4 * self.nn) if R is None else R

@@ -56,6 +56,24 @@ extern "C" int hc_error_residual(int model, const double* x, const double* u, co
   return 0;
 }
 
+// von Mises stress and vol * d vm / d u of one element (element_von_mises): out[0] = vm, out[1] = vol, dvm[12]
+extern "C" int hc_von_mises(int model, const double* x, const double* u, const double* p, const double* mat5,
+                            const double* Fp_old, double eqps_old, double* out, double* dvm) {
+  gx::Material m = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
+  double X[4][3], U[4][3];
+  for (int n = 0; n < 4; ++n) for (int j = 0; j < 3; ++j) { X[n][j] = x[3 * n + j]; U[n][j] = u[3 * n + j]; }
+  gx::Core<double> c;
+  double sg[9], eq, Cp[6], d[4][3];
+  gx::cp_inverse(Fp_old, Cp);
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Cp, eqps_old, false, sg, eq, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Cp, eqps_old, false, sg, eq, c);
+  if (rc) return rc;
+  out[0] = gx::element_von_mises(c, d);
+  out[1] = c.vol;
+  for (int n = 0; n < 4; ++n) for (int k = 0; k < 3; ++k) dvm[3 * n + k] = d[n][k];
+  return 0;
+}
+
 extern "C" void hc_expm3(const double* A, double* o) { gx::expm3(A, o); }
 
 // ---------------------------------------------------------------------------

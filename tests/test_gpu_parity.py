@@ -200,6 +200,34 @@ def test_functional_and_device_dbcs(cube):
     a.close()
 
 
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+@pytest.mark.parametrize("mesh", ["cube", "kuhn6"])
+def test_all_functionals_match_fad_oracle(cube, model, mesh):
+    """SURVEY 8(f) rank 1: every functional of Mechanics::build_functional (src/goal_mechanics.cpp:149-167) and
+    its dMdu (QoI<FADT>::scatter, src/goal_qoi.cpp:63-76) on the device against the oracle's ST / FADT evaluation:
+    avg disp, avg disp subdomain, avg vm (closed-form von Mises derivative), max vm (KS), point wise."""
+    co, cn = _mesh(cube, mesh)
+    f = fields(co, len(cn), strain=0.004)
+    es = (np.arange(len(cn)) % 3 == 1).astype(np.int32)
+    a, o = _pair(co, cn, model, f, elem_set=es, mats=(MATERIAL, MATERIAL))
+    a.residual(save=True); o.residual(save=True)  # "max vm" reads the saved sigma state
+    for t in ("avg disp", "avg disp subdomain", "avg vm", "max vm", "point wise"):
+        kw = dict(elem_set=1, rho=0.05, point=(len(co) // 2, 1))
+        J, d = a.functional(t, with_dMdu=True, **kw)
+        Jo, do = o.functional(t, with_dMdu=True, **kw)
+        assert abs(J - Jo) <= 1e-12 * abs(Jo), t
+        assert relerr(d, do) < 1e-12, t
+        assert np.array_equal(d, a.fetch_dMdu())
+        assert abs(a.functional(t, **kw) - o.functional(t, **kw)) <= 1e-12 * abs(Jo), t  # ST chain: value only
+        J2, d2 = a.functional(t, with_dMdu=True, **kw)
+        assert J2 == J and np.array_equal(d, d2), t  # deterministic
+    # the dedicated avg-disp entry point agrees with the generic one
+    assert abs(a.avg_disp() - a.functional("avg disp")) < 1e-15
+    if model == "J2":
+        assert o.plastic_count() > 0
+    a.close()
+
+
 def test_bitwise_determinism(cube):
     """No atomics on the data path: repeated passes give identical bits."""
     import goal_b200

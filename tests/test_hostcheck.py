@@ -57,6 +57,39 @@ def test_element_math_matches_fad_oracle(hostcheck, model):
     assert seen == ({0, 1} if model == "J2" else {0})
 
 
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+def test_von_mises_derivative_matches_fad_oracle(hostcheck, model):
+    """element_von_mises (closed-form d vm / d u) against the oracle's FADT evaluation of AvgVM
+    (src/goal_avg_vm.cpp:43-61, goal_von_mises.cpp:6-18) on single elements, elastic and plastic."""
+    rng = np.random.RandomState(5)
+    mat = np.array(MATERIAL)
+    seen = set()
+    for trial in range(60):
+        x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]]) * 0.1 + 0.01 * rng.randn(4, 3)
+        if np.linalg.det(x[1:] - x[0]) < 0:
+            x[[1, 2]] = x[[2, 1]]
+        u = (0.0001, 0.0005, 0.003)[trial % 3] * rng.randn(4, 3)
+        p = rng.randn(4)
+        Fpo = (np.eye(3) + 1e-3 * rng.randn(3, 3)).reshape(-1)
+        eqo = 0.01 * rng.rand()
+        o = Oracle(x, np.array([[0, 1, 2, 3]], dtype=np.int32), model, [MATERIAL])
+        o.set_solution(u, p)
+        if model == "J2":
+            o.state("Fp_old")[:] = Fpo
+            o.state("eqps_old")[:] = eqo
+        Jo, do = o.functional("avg vm", with_dMdu=True)
+        seen.add(o.plastic_count() > 0)
+        out, dvm = np.zeros(2), np.zeros(12)
+        rc = hostcheck.hc_von_mises(0 if model == "neohookean" else 1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eqo),
+                                    dp(out), dp(dvm))
+        assert rc == 0
+        assert abs(out[0] * out[1] - Jo) < 1e-12 * abs(Jo)
+        do = do.reshape(4, 4)
+        assert np.all(do[:, 3] == 0.0)  # von Mises does not see the pressure
+        assert relerr(dvm.reshape(4, 3), do[:, :3]) < 1e-11
+    assert seen == ({False, True} if model == "J2" else {False})
+
+
 def test_expm_matches_scipy(hostcheck):
     import scipy.linalg
     rng = np.random.RandomState(2)
