@@ -30,7 +30,7 @@ SYMBOLS = [
     "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
-    "gx_fetch_dmdu",
+    "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs",
 ]
 
 # Mechanics::build_functional types by their yaml name (src/goal_mechanics.cpp:149-167)
@@ -107,6 +107,8 @@ def load_library():
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.gx_functional_avg_disp.argtypes = [vp, dp, vp]
     L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
+    L.gx_apply_tbcs.argtypes = [vp, C.c_int32, ip, dp]
+    L.gx_apply_ibcs.argtypes = [vp, C.c_int32, ip, C.c_double, dp]
     L.gx_functional.argtypes = [vp, C.POINTER(GxQoi), dp, vp]
     L.gx_ks_vm_max.argtypes = [vp, dp]
     L.gx_ks_vm_scale.argtypes = [vp, C.c_double, C.c_double, dp]
@@ -333,6 +335,18 @@ class Assembler:
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         g = np.ascontiguousarray(g, dtype=np.float64)
         self._ck(self.L.gx_apply_dbcs(self.h, len(rows), _ip(rows), _dp(g), int(with_jacobian)))
+
+    def apply_tbcs(self, sides, traction):
+        """set_tbcs on the device-resident ghost R (src/goal_tbcs.cpp:29-71); traction: [n_sides, 3] or one 3-vector."""
+        sides = np.ascontiguousarray(sides, dtype=np.int32).reshape(-1, 3)
+        T = np.ascontiguousarray(np.broadcast_to(np.asarray(traction, dtype=np.float64), (len(sides), 3)))
+        self._ck(self.L.gx_apply_tbcs(self.h, len(sides), _ip(sides), _dp(T)))
+
+    def apply_ibcs(self, sides, scale, center):
+        """set_ibcs (src/goal_ibcs.cpp:41-83): inward traction T = scale (x_c - center)."""
+        sides = np.ascontiguousarray(sides, dtype=np.int32).reshape(-1, 3)
+        c = np.ascontiguousarray(center, dtype=np.float64)
+        self._ck(self.L.gx_apply_ibcs(self.h, len(sides), _ip(sides), float(scale), _dp(c)))
 
     def fetch(self, R=True, values=True):
         Rv = np.zeros(4 * self.nn) if R else None

@@ -188,6 +188,39 @@ __global__ void apply_dbcs_kernel(double* R, double* values, NodeRec const* node
   if (lane == 0) R[row] = (i < 3 ? r.u[i] : r.p) - g[w];
 }
 
+// set_tbcs / set_ibcs (src/goal_tbcs.cpp:29-71, goal_ibcs.cpp:41-83): R[row(n,d)] -= T_d N_n(xi_c) w dv over the
+// triangles of a side set.  One thread per boundary node walks the node's sides in ascending side order -- the
+// order the reference's side loop adds them in -- so the result is bit-reproducible without atomics.
+// T == nullptr selects the inward traction T = scale (x_c - center) of set_ibcs.
+__global__ void side_bcs_kernel(double* R, NodeRec const* nodes, int32_t const* bnode, int32_t const* off, int32_t const* inc,
+                                int32_t const* side_nodes, double const* T, double scale, double cx, double cy, double cz, int nb) {
+  int const b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  int const a = bnode[b];
+  double r[3] = {R[4 * (int64_t)a], R[4 * (int64_t)a + 1], R[4 * (int64_t)a + 2]};
+  for (int k = off[b]; k < off[b + 1]; ++k) {
+    int const s = inc[k];
+    double x[3][3];
+    for (int n = 0; n < 3; ++n) {
+      NodeRec const& nr = nodes[side_nodes[3 * (int64_t)s + n]];
+      x[n][0] = nr.x[0]; x[n][1] = nr.x[1]; x[n][2] = nr.x[2];
+    }
+    double e1[3], e2[3], cr[3];
+    for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; }
+    cross3(e1, e2, cr);
+    double const dv = sqrt(dot3(cr, cr));  // apf::getDV of a triangle in 3D: twice its area
+    double t[3];
+    if (T) {
+      t[0] = T[3 * (int64_t)s]; t[1] = T[3 * (int64_t)s + 1]; t[2] = T[3 * (int64_t)s + 2];
+    } else {
+      double const c[3] = {cx, cy, cz};
+      for (int j = 0; j < 3; ++j) t[j] = ((x[0][j] + x[1][j] + x[2][j]) * (1.0 / 3.0) - c[j]) * scale;
+    }
+    for (int d = 0; d < 3; ++d) r[d] -= t[d] * (1.0 / 3.0) * 0.5 * dv;
+  }
+  R[4 * (int64_t)a] = r[0]; R[4 * (int64_t)a + 1] = r[1]; R[4 * (int64_t)a + 2] = r[2];
+}
+
 // ---------------------------------------------------------------------------
 template <int MODEL, int PASS, bool SAVE>
 static cudaError_t launch_colours(gx_ctx* ctx, KParams& P) {
@@ -910,6 +943,60 @@ int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, 
   GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
+}
+
+static int side_bcs(gx_ctx* ctx, const char* who, int32_t n_sides, const int32_t* side_nodes, const double* T, double scale,
+                    const double* center) {
+  if (!ctx || n_sides < 0 || (n_sides > 0 && !side_nodes)) { if (ctx) ctx->err = std::string(who) + ": bad argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  if (!ctx->have_result) { ctx->err = std::string(who) + ": no residual on the device"; return GX_ERR_ARG; }
+  if (n_sides == 0) return GX_OK;
+  int const nn = ctx->nn;
+  // node -> sides incidence of this side set, sides ascending per node (O(boundary) host work)
+  std::vector<int32_t> cnt(nn, 0);
+  for (int64_t k = 0; k < 3 * (int64_t)n_sides; ++k) {
+    if (side_nodes[k] < 0 || side_nodes[k] >= nn) { ctx->err = std::string(who) + ": side node out of range"; return GX_ERR_ARG; }
+    cnt[side_nodes[k]]++;
+  }
+  std::vector<int32_t> bnode, off(1, 0), slot(nn, -1);
+  for (int a = 0; a < nn; ++a)
+    if (cnt[a]) { slot[a] = (int32_t)bnode.size(); bnode.push_back(a); off.push_back(off.back() + cnt[a]); }
+  std::vector<int32_t> inc(off.back()), fill(off.begin(), off.end() - 1);
+  for (int32_t sd = 0; sd < n_sides; ++sd)
+    for (int n = 0; n < 3; ++n) inc[fill[slot[side_nodes[3 * (int64_t)sd + n]]]++] = sd;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nb = (int)bnode.size();
+  int32_t *d_b = nullptr, *d_off = nullptr, *d_inc = nullptr, *d_sn = nullptr;
+  double* d_T = nullptr;
+  GX_CUDA(cudaMallocAsync(&d_b, sizeof(int32_t) * (size_t)nb, ctx->stream));
+  GX_CUDA(cudaMallocAsync(&d_off, sizeof(int32_t) * (size_t)(nb + 1), ctx->stream));
+  GX_CUDA(cudaMallocAsync(&d_inc, sizeof(int32_t) * inc.size(), ctx->stream));
+  GX_CUDA(cudaMallocAsync(&d_sn, sizeof(int32_t) * 3 * (size_t)n_sides, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(d_b, bnode.data(), sizeof(int32_t) * (size_t)nb, cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int32_t) * (size_t)(nb + 1), cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(d_inc, inc.data(), sizeof(int32_t) * inc.size(), cudaMemcpyHostToDevice, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(d_sn, side_nodes, sizeof(int32_t) * 3 * (size_t)n_sides, cudaMemcpyHostToDevice, ctx->stream));
+  if (T) {
+    GX_CUDA(cudaMallocAsync(&d_T, sizeof(double) * 3 * (size_t)n_sides, ctx->stream));
+    GX_CUDA(cudaMemcpyAsync(d_T, T, sizeof(double) * 3 * (size_t)n_sides, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  side_bcs_kernel<<<(nb + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_R, ctx->d_nodes, d_b, d_off, d_inc, d_sn, d_T, scale,
+                                                           center ? center[0] : 0.0, center ? center[1] : 0.0, center ? center[2] : 0.0, nb);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaFreeAsync(d_b, ctx->stream)); GX_CUDA(cudaFreeAsync(d_off, ctx->stream));
+  GX_CUDA(cudaFreeAsync(d_inc, ctx->stream)); GX_CUDA(cudaFreeAsync(d_sn, ctx->stream));
+  if (d_T) GX_CUDA(cudaFreeAsync(d_T, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_apply_tbcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, const double* traction) {
+  if (ctx && n_sides > 0 && !traction) { ctx->err = "gx_apply_tbcs: null traction"; return GX_ERR_ARG; }
+  return side_bcs(ctx, "gx_apply_tbcs", n_sides, side_nodes, traction, 0.0, nullptr);
+}
+int gx_apply_ibcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, double scale, const double* center) {
+  if (ctx && !center) { ctx->err = "gx_apply_ibcs: null center"; return GX_ERR_ARG; }
+  return side_bcs(ctx, "gx_apply_ibcs", n_sides, side_nodes, nullptr, scale, center);
 }
 
 int gx_result_dev(gx_ctx* ctx, double** R_dev, double** values_dev) {

@@ -171,6 +171,15 @@ int gx_fetch_dmdu(gx_ctx* ctx, double* dMdu_out);
  * R[row] = solution - g; with_jacobian != 0 additionally zeroes the CRS row and puts 1 on the diagonal.
  * As in the reference this runs after the interface reduction and does not eliminate columns. */
 int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, int with_jacobian);
+/* Traction and inward-traction boundary terms on the device-resident ghost R of the last compute call, before the
+ * interface reduction (set_tbcs src/goal_tbcs.cpp:29-71, set_ibcs src/goal_ibcs.cpp:41-83; call order of
+ * Primal::compute_resid/compute_jacob, src/goal_primal.cpp:84-85, 102-103): for every triangle of the side set
+ * R[row(n,d)] -= T_d N_n(xi_c) w dv.  side_nodes: [n_sides*3] ghost-local vertex ids.  traction: [n_sides*3], the
+ * side's expression evaluated by the host at the triangle centroid and the current time (goal::eval); the
+ * inward form computes T = scale (x_c - center) itself.  Sides sharing a node are added in ascending side order
+ * (the reference's loop order), without atomics. */
+int gx_apply_tbcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, const double* traction);
+int gx_apply_ibcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, double scale, const double center[3]);
 
 /* ---- mesh parts ------------------------------------------------------------------------------
  * Structure exchange == the owned_graph Export/INSERT of Disc::compute_graphs (src/goal_disc.cpp:327-329):

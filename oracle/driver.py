@@ -32,10 +32,23 @@ def _traction_rhs(coords, sides, traction):
     return out
 
 
+def _inward_rhs(coords, sides, scale, center):
+    """set_ibcs (src/goal_ibcs.cpp:33-83): T = scale (x_c - center) at the side centroid; list of (row, value)."""
+    out = []
+    for tri in sides:
+        x = coords[np.asarray(tri)]
+        area = 0.5 * np.linalg.norm(np.cross(x[1] - x[0], x[2] - x[0]))
+        T = (x.sum(0) / 3.0 - np.asarray(center)) * scale
+        for n in tri:
+            for d in range(3):
+                out.append((4 * n + d, -T[d] * (1.0 / 3.0) * 0.5 * (2.0 * area)))
+    return out
+
+
 def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_iters=5, log=None, device_bcs=False):
     """dbcs: [(eq, node_ids, g(t))]; tbcs: [(side_tris, T(t) -> 3-vector)].
-    device_bcs: apply the Dirichlet rows with asm.apply_dbcs (the CUDA path's gx_apply_dbcs) instead of on the host;
-    only valid without traction BCs (those are added to the ghost R on the host before the Dirichlet rows).
+    device_bcs: apply the traction terms and the Dirichlet rows with asm.apply_tbcs / asm.apply_dbcs (the CUDA path's
+    gx_apply_tbcs / gx_apply_dbcs) on the device-resident result instead of on the host.
 
     Returns dict(J=[per-step functional], newton=[iterations], plastic=[count at end of step]).
     """
@@ -61,8 +74,9 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
         while it <= max_iters and not converged:
             asm.set_solution(u, p)
             if device_bcs:
-                assert not tbcs
                 asm.jacobian(save=True, out=False)
+                for sides, T in tbcs:
+                    asm.apply_tbcs(sides, T(t_now))
                 rows_g = [(4 * n + eq, g(t_now)) for eq, nodes, g in dbcs for n in nodes]
                 asm.apply_dbcs([r for r, _ in rows_g], [v for _, v in rows_g], True)
                 R, vals = asm.fetch()
@@ -83,6 +97,8 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
             asm.set_solution(u, p)
             if device_bcs:
                 asm.residual(save=True, out=False)
+                for sides, T in tbcs:
+                    asm.apply_tbcs(sides, T(t_now))
                 rows_g = [(4 * n + eq, g(t_now)) for eq, nodes, g in dbcs for n in nodes]
                 asm.apply_dbcs([r for r, _ in rows_g], [v for _, v in rows_g], False)
                 R = asm.fetch(values=False)[0]

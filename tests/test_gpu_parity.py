@@ -228,6 +228,53 @@ def test_all_functionals_match_fad_oracle(cube, model, mesh):
     a.close()
 
 
+def test_side_set_boundary_terms(cube):
+    """set_tbcs / set_ibcs (src/goal_tbcs.cpp:29-71, goal_ibcs.cpp:41-83) on the device-resident
+    ghost R against the host construction of oracle/driver.py, on the reference fixture's ymax side set (16 faces)
+    and on every boundary face of a Kuhn cube (sides sharing nodes; per-side traction values)."""
+    from oracle import driver
+    co, cn = cube["coords"], cube["tets"]
+    f = fields(co, len(cn), strain=0.004)
+    a, _ = _pair(co, cn, "neohookean", f)
+    sides = np.array(cube["side_sets"]["ymax"], dtype=np.int32)
+    R0 = a.residual(save=False).copy()
+    a.apply_tbcs(sides, (0.3, -1.0, 0.25))
+    want = R0.copy()
+    for row, v in driver._traction_rhs(co, sides, (0.3, -1.0, 0.25)):
+        want[row] += v
+    got = a.fetch(values=False)[0]
+    assert relerr(got - R0, want - R0) < 1e-13 and relerr(got, want) < 1e-14
+    a.apply_ibcs(sides, 2.5, (0.5, 0.25, 0.75))
+    for row, v in driver._inward_rhs(co, sides, 2.5, (0.5, 0.25, 0.75)):
+        want[row] += v
+    got2 = a.fetch(values=False)[0]
+    assert relerr(got2 - got, want - got) < 1e-13
+    a.close()
+    # all boundary faces of a Kuhn cube, a different traction on every side
+    co, cn = kuhn_cube(5)
+    faces = np.concatenate([cn[:, [1, 2, 3]], cn[:, [0, 3, 2]], cn[:, [0, 1, 3]], cn[:, [0, 2, 1]]])
+    key = np.sort(faces, 1)
+    _, idx, cnt = np.unique(key, axis=0, return_index=True, return_counts=True)
+    bf = np.ascontiguousarray(faces[idx[cnt == 1]], dtype=np.int32)
+    assert len(bf) == 6 * 2 * 25
+    f = fields(co, len(cn), strain=0.004)
+    a, _ = _pair(co, cn, "J2", f)
+    R0 = a.residual(save=False).copy()
+    T = np.random.RandomState(3).randn(len(bf), 3)
+    a.apply_tbcs(bf, T)
+    want = R0.copy()
+    for s_, tri in enumerate(bf):
+        for row, v in driver._traction_rhs(co, [tri], T[s_]):
+            want[row] += v
+    got = a.fetch(values=False)[0]
+    assert relerr(got - R0, want - R0) < 1e-13
+    a.apply_tbcs(bf, T)  # repeated application is deterministic
+    a2, _ = _pair(co, cn, "J2", f)
+    a2.residual(save=False); a2.apply_tbcs(bf, T); a2.apply_tbcs(bf, T)
+    assert np.array_equal(a.fetch(values=False)[0], a2.fetch(values=False)[0])
+    a.close(); a2.close()
+
+
 def test_bitwise_determinism(cube):
     """No atomics on the data path: repeated passes give identical bits."""
     import goal_b200
@@ -266,12 +313,12 @@ def test_reference_goldens_through_gpu_path(cube, name):
 
     dbcs, tbcs = driver.golden_case(name, cube)
     r = driver.run_primal(WithFunctional(), co, dbcs, tbcs)
-    if not tbcs:
-        # same run with the Dirichlet rows (gx_apply_dbcs) and the functional (gx_functional_avg_disp) on the device
-        a2 = goal_b200.Assembler(cube["coords"], cube["tets"], model, [MATERIAL])
-        r2 = driver.run_primal(a2, co, dbcs, tbcs, device_bcs=True)
-        assert np.abs(np.array(r2["J"]) - np.array(r["J"])).max() < 1e-13 and r2["newton"] == r["newton"]
-        a2.close()
+    # same run with the traction terms (gx_apply_tbcs), the Dirichlet rows (gx_apply_dbcs) and the functional
+    # (gx_functional_avg_disp) on the device
+    a2 = goal_b200.Assembler(cube["coords"], cube["tets"], model, [MATERIAL])
+    r2 = driver.run_primal(a2, co, dbcs, tbcs, device_bcs=True)
+    assert np.abs(np.array(r2["J"]) - np.array(r["J"])).max() < 1e-13 and r2["newton"] == r["newton"]
+    a2.close()
     assert abs(r["J"][-1] - J_gold) < 1e-12
     for got, want in zip(r["J"], driver.GOLDEN_STEPS[name]):
         assert abs(got - want) < 1e-12
