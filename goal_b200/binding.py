@@ -30,7 +30,8 @@ SYMBOLS = [
     "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
-    "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs",
+    "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs", "gx_add_solution", "gx_get_solution", "gx_sync_solution",
+    "gx_pack_solution", "gx_unpack_solution", "gx_size_field",
 ]
 
 # Mechanics::build_functional types by their yaml name (src/goal_mechanics.cpp:149-167)
@@ -109,6 +110,12 @@ def load_library():
     L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
     L.gx_apply_tbcs.argtypes = [vp, C.c_int32, ip, dp]
     L.gx_apply_ibcs.argtypes = [vp, C.c_int32, ip, C.c_double, dp]
+    L.gx_add_solution.argtypes = [vp, vp]
+    L.gx_get_solution.argtypes = [vp, vp, vp]
+    L.gx_sync_solution.argtypes = [vp]
+    L.gx_pack_solution.argtypes = [vp, C.c_int, C.POINTER(vp), lp]
+    L.gx_unpack_solution.argtypes = [vp, C.c_int, vp]
+    L.gx_size_field.argtypes = [vp, dp, C.c_int32, C.c_int32, dp, dp, dp]
     L.gx_functional.argtypes = [vp, C.POINTER(GxQoi), dp, vp]
     L.gx_ks_vm_max.argtypes = [vp, dp]
     L.gx_ks_vm_scale.argtypes = [vp, C.c_double, C.c_double, dp]
@@ -335,6 +342,29 @@ class Assembler:
         rows = np.ascontiguousarray(rows, dtype=np.int32)
         g = np.ascontiguousarray(g, dtype=np.float64)
         self._ck(self.L.gx_apply_dbcs(self.h, len(rows), _ip(rows), _dp(g), int(with_jacobian)))
+
+    def add_solution(self, du):
+        """Disc::add_soln (src/goal_disc.cpp:398-422): du in ghost dof layout [4 nn]."""
+        du = np.ascontiguousarray(du, dtype=np.float64).reshape(-1)
+        assert du.size == 4 * self.nn
+        self._ck(self.L.gx_add_solution(self.h, _addr(du)))
+
+    def get_solution(self):
+        u, p = np.zeros((self.nn, 3)), np.zeros(self.nn)
+        self._ck(self.L.gx_get_solution(self.h, _addr(u), _addr(p)))
+        return u, p
+
+    def sync_solution(self):
+        self._ck(self.L.gx_sync_solution(self.h))
+
+    def size_field(self, eta, target, p_order=1, G=0.0, counts=False):
+        """get_iso_target_size (src/goal_size_field.cpp:39-150) -> (vertex sizes [nn], G[, counts])."""
+        eta = np.ascontiguousarray(eta, dtype=np.float64)
+        g = C.c_double(G)
+        v = np.zeros(self.nn)
+        c = np.zeros(self.nn) if counts else None
+        self._ck(self.L.gx_size_field(self.h, _dp(eta), target, p_order, C.byref(g), _dp(v), None if c is None else _dp(c)))
+        return (v, g.value, c) if counts else (v, g.value)
 
     def apply_tbcs(self, sides, traction):
         """set_tbcs on the device-resident ghost R (src/goal_tbcs.cpp:29-71); traction: [n_sides, 3] or one 3-vector."""

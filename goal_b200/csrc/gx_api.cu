@@ -188,6 +188,70 @@ __global__ void apply_dbcs_kernel(double* R, double* values, NodeRec const* node
   if (lane == 0) R[row] = (i < 3 ? r.u[i] : r.p) - g[w];
 }
 
+// Disc::add_soln (src/goal_disc.cpp:398-422): u += du, p += dp from a ghost-layout dof vector [4 nn]
+__global__ void add_solution_kernel(NodeRec* nodes, double const* du, int nn) {
+  int const n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  double2 const a = reinterpret_cast<double2 const*>(du)[2 * (int64_t)n], b = reinterpret_cast<double2 const*>(du)[2 * (int64_t)n + 1];
+  nodes[n].u[0] += a.x; nodes[n].u[1] += a.y; nodes[n].u[2] += b.x; nodes[n].p += b.y;
+}
+__global__ void unpack_solution_kernel(double* u, double* p, NodeRec const* nodes, int nn) {
+  int const n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= nn) return;
+  u[3 * (int64_t)n] = nodes[n].u[0]; u[3 * (int64_t)n + 1] = nodes[n].u[1]; u[3 * (int64_t)n + 2] = nodes[n].u[2];
+  p[n] = nodes[n].p;
+}
+
+// get_iso_target_size (src/goal_size_field.cpp:39-150), p_order = 1, d = 3.
+//   pass 0: block partials of sum_e |eta_e|^(2d/(2p+d))                          (sum_contributions, :39-52)
+//   pass 1: h_new[e] = clamp(size_factor |eta_e|^(-2/(2p+d)) h_e, alpha h_e, beta h_e), h_e = sqrt(sum l^2 / 6)   (:61-81)
+__global__ void __launch_bounds__(256) size_field_elem_kernel(double* out, double const* eta, NodeRec const* nodes, int4 const* conn, int ne,
+                                                              int pass, double p_order, double size_factor) {
+  __shared__ double sh[256];
+  double const d = 3.0;
+  double s = 0.0;
+  for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < ne; e += (int64_t)gridDim.x * blockDim.x) {
+    double const v = fabs(eta[e]);
+    if (pass == 0) {
+      s += pow(v, (2.0 * d) / (2.0 * p_order + d));
+    } else {
+      int4 const cn = conn[e];
+      int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+      double x[4][3];
+      for (int n = 0; n < 4; ++n) { x[n][0] = nodes[nd[n]].x[0]; x[n][1] = nodes[nd[n]].x[1]; x[n][2] = nodes[nd[n]].x[2]; }
+      double h2 = 0.0;
+      for (int a = 0; a < 4; ++a)
+        for (int b = a + 1; b < 4; ++b)
+          for (int j = 0; j < 3; ++j) { double const t = x[b][j] - x[a][j]; h2 += t * t; }
+      double const h = sqrt(h2 / 6.0);
+      double hn = size_factor * pow(v, -2.0 / (2.0 * p_order + d)) * h;
+      if (hn < 0.25 * h) hn = 0.25 * h;
+      if (hn > 2.0 * h) hn = 2.0 * h;
+      out[e] = hn;
+    }
+  }
+  if (pass != 0) return;
+  sh[threadIdx.x] = s;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = sh[0];
+}
+// avg_to_vtx (src/goal_size_field.cpp:95-106): vertex size = mean of the adjacent elements' sizes (ascending element order)
+__global__ void size_field_vtx_kernel(double* vsize, double* vcount, double const* hnew, uint32_t const* adj_off, int2 const* adj, int nn,
+                                      int average) {
+  int const a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nn) return;
+  uint32_t const o0 = adj_off[a], o1 = adj_off[a + 1];
+  double s = 0.0;
+  for (uint32_t k = o0; k < o1; ++k) s += hnew[adj[k].x >> 2];
+  double const c = (double)(o1 - o0);
+  vsize[a] = average ? (o1 > o0 ? s / c : 0.0) : s;
+  if (vcount) vcount[a] = c;
+}
+
 // set_tbcs / set_ibcs (src/goal_tbcs.cpp:29-71, goal_ibcs.cpp:41-83): R[row(n,d)] -= T_d N_n(xi_c) w dv over the
 // triangles of a side set.  One thread per boundary node walks the node's sides in ascending side order -- the
 // order the reference's side loop adds them in -- so the result is bit-reproducible without atomics.
@@ -652,6 +716,62 @@ int gx_set_solution(gx_ctx* ctx, const double* u, const double* p) {
   GX_CUDA(cudaMemcpyAsync(dp, p, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
   pack_solution_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nodes, du, dp, nn);
   GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_add_solution(gx_ctx* ctx, const double* du) {
+  if (!ctx || !du) { if (ctx) ctx->err = "gx_add_solution: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nn = ctx->nn;
+  GX_CUDA(cudaMemcpyAsync(ctx->d_stage, du, sizeof(double) * 4 * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+  add_solution_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nodes, ctx->d_stage, nn);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_get_solution(gx_ctx* ctx, double* u, double* p) {
+  if (!ctx || !u || !p) { if (ctx) ctx->err = "gx_get_solution: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nn = ctx->nn;
+  double* du = ctx->d_stage;
+  double* dp = ctx->d_stage + 3 * (size_t)nn;
+  unpack_solution_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(du, dp, ctx->d_nodes, nn);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaMemcpyAsync(u, du, sizeof(double) * 3 * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(p, dp, sizeof(double) * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
+int gx_size_field(gx_ctx* ctx, const double* eta_elem, int32_t target, int32_t p_order, double* G, double* vtx_size, double* vtx_count) {
+  if (!ctx || !eta_elem || !G || target <= 0 || p_order < 1) { if (ctx) ctx->err = "gx_size_field: bad argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const nn = ctx->nn, ne = ctx->ne;
+  double* d_eta = ctx->d_stage;                   // [ne]
+  double* d_h = ctx->d_stage + (size_t)ne;        // [ne]
+  double* d_v = ctx->d_stage + 2 * (size_t)ne;    // [nn] sizes, [nn] counts   (stage_len >= 9 ne, nn <= 4 ne)
+  if (2 * (int64_t)ne + 2 * (int64_t)nn > ctx->stage_len) { ctx->err = "gx_size_field: mesh has too many isolated nodes"; return GX_ERR_UNSUPPORTED; }
+  GX_CUDA(cudaMemcpyAsync(d_eta, eta_elem, sizeof(double) * (size_t)ne, cudaMemcpyHostToDevice, ctx->stream));
+  if (!(*G > 0.0)) {  // this part's sum_contributions; with several parts the caller adds them (PCU_Add_Doubles) and calls again
+    int const nb = std::min(1023, (ne + 255) / 256);
+    size_field_elem_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, d_eta, ctx->d_nodes, ctx->d_conn, ne, 0, (double)p_order, 0.0);
+    bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb);
+    GX_CUDA(cudaGetLastError());
+    GX_CUDA(cudaMemcpyAsync(G, ctx->d_red + 1023, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (!vtx_size) return GX_OK;
+  double const size_factor = std::pow(*G / (double)target, 1.0 / 3.0);  // compute_size_factor (:54-59)
+  size_field_elem_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(d_h, d_eta, ctx->d_nodes, ctx->d_conn, ne, 1, (double)p_order, size_factor);
+  size_field_vtx_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(d_v, vtx_count ? d_v + nn : nullptr, d_h, ctx->d_adj_off, ctx->d_adj, nn, vtx_count ? 0 : 1);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaMemcpyAsync(vtx_size, d_v, sizeof(double) * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
+  if (vtx_count) GX_CUDA(cudaMemcpyAsync(vtx_count, d_v + nn, sizeof(double) * (size_t)nn, cudaMemcpyDeviceToHost, ctx->stream));
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }

@@ -141,6 +141,19 @@ __global__ void unpack_R_kernel(double* R, double const* buf, int32_t const* nod
   if (t >= 4 * nrecv) return;
   R[4 * (int64_t)nodes[t >> 2] + (t & 3)] += buf[t];
 }
+// apf::synchronize of "u","p" (src/goal_disc.cpp:420-421): the owner's nodal values overwrite the copies
+__global__ void pack_sol_kernel(double* buf, NodeRec const* nd, int32_t const* nodes, int n) {
+  int const t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  NodeRec const& r = nd[nodes[t]];
+  buf[4 * (int64_t)t] = r.u[0]; buf[4 * (int64_t)t + 1] = r.u[1]; buf[4 * (int64_t)t + 2] = r.u[2]; buf[4 * (int64_t)t + 3] = r.p;
+}
+__global__ void unpack_sol_kernel(NodeRec* nd, double const* buf, int32_t const* nodes, int n) {
+  int const t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  NodeRec& r = nd[nodes[t]];
+  r.u[0] = buf[4 * (int64_t)t]; r.u[1] = buf[4 * (int64_t)t + 1]; r.u[2] = buf[4 * (int64_t)t + 2]; r.p = buf[4 * (int64_t)t + 3];
+}
 // extended rows -> reference ghost layout (drop the phantom blocks)
 __global__ void compact_ghost_kernel(double* ghost, double const* ext, int32_t const* blk0_x, int32_t const* nblk_x,
                                      int64_t const* blk0_g, int nn) {
@@ -513,6 +526,37 @@ int gx_unpack_add_interface(gx_ctx* ctx, int peer_index, int what, const void* r
   return GX_OK;
 }
 
+// Solution synchronisation, owner -> copies: the reverse direction of the R exchange, so the owner packs its
+// recv_nodes (into the R receive buffer) and the copy holder overwrites its send_nodes.
+int gx_pack_solution(gx_ctx* ctx, int peer_index, void** send_dev, int64_t* send_bytes) {
+  int rc = check_peer(ctx, peer_index);
+  if (rc) return rc;
+  if ((rc = need_device(ctx, "gx_pack_solution"))) return rc;
+  Peer& P = ctx->peers[peer_index];
+  int const n = (int)P.recv_nodes.size();
+  GX_CUDA(cudaSetDevice(ctx->device));
+  if (n) pack_sol_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P.d_recvR, ctx->d_nodes, P.d_recv_nodes, n);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (send_dev) *send_dev = P.d_recvR;
+  if (send_bytes) *send_bytes = 32 * (int64_t)n;
+  return GX_OK;
+}
+int gx_unpack_solution(gx_ctx* ctx, int peer_index, const void* recv_dev) {
+  int rc = check_peer(ctx, peer_index);
+  if (rc) return rc;
+  if ((rc = need_device(ctx, "gx_unpack_solution"))) return rc;
+  Peer& P = ctx->peers[peer_index];
+  int const n = (int)P.send_nodes.size();
+  if (!n) return GX_OK;
+  if (!recv_dev) { ctx->err = "gx_unpack_solution: null buffer"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  unpack_sol_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nodes, (double const*)recv_dev, P.d_send_nodes, n);
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GX_OK;
+}
+
 int gx_nccl_unique_id(void* out, size_t* id_bytes) {
   std::string err;
   NcclApi* api = load_nccl(err);
@@ -609,6 +653,35 @@ int gx_reduce_interfaces(gx_ctx* ctx, int what) {
   float ms = 0;
   GX_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]));
   ctx->timing[2] = ms;
+  return GX_OK;
+}
+
+// apf::synchronize(u), apf::synchronize(p) after Disc::add_soln (src/goal_disc.cpp:420-421) over NCCL
+int gx_sync_solution(gx_ctx* ctx) {
+  if (!ctx) return GX_ERR_ARG;
+  if (ctx->nranks <= 1 || ctx->peers.empty()) return GX_OK;
+  int rc = need_device(ctx, "gx_sync_solution");
+  if (rc) return rc;
+  if (!ctx->comm || !ctx->struct_done) { ctx->err = "gx_sync_solution: call gx_comm_init first"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  for (auto& P : ctx->peers) {
+    int const n = (int)P.recv_nodes.size();
+    if (n) pack_sol_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(P.d_recvR, ctx->d_nodes, P.d_recv_nodes, n);
+  }
+  GX_CUDA(cudaGetLastError());
+  GX_NCCL(ctx->nccl->GroupStart());
+  for (auto& P : ctx->peers) {
+    size_t const ns = P.send_nodes.size(), nr = P.recv_nodes.size();
+    if (nr) GX_NCCL(ctx->nccl->Send(P.d_recvR, 4 * nr, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
+    if (ns) GX_NCCL(ctx->nccl->Recv(P.d_sendR, 4 * ns, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
+  }
+  GX_NCCL(ctx->nccl->GroupEnd());
+  for (auto& P : ctx->peers) {
+    int const n = (int)P.send_nodes.size();
+    if (n) unpack_sol_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_nodes, P.d_sendR, P.d_send_nodes, n);
+  }
+  GX_CUDA(cudaGetLastError());
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
 

@@ -109,6 +109,16 @@ int gx_scatter_map(gx_ctx* ctx, uint8_t* bpos);
  * Displacement/Pressure::gather read them, src/goal_displacement.cpp:139-156). */
 int gx_set_solution(gx_ctx* ctx, const double* u /*[n_nodes*3]*/, const double* p /*[n_nodes]*/);
 
+/* Disc::add_soln (src/goal_disc.cpp:398-422): u += du[4a+d], p += du[4a+3] on the device-resident solution, du in
+ * ghost dof layout [4*n_nodes].  The reference updates owned nodes and then apf::synchronize()s the copies
+ * (:420-421): on a partitioned context follow with gx_sync_solution (NCCL) or the gx_pack_solution /
+ * gx_unpack_solution halves (own transport), after which non-owned entries of du no longer matter. */
+int gx_add_solution(gx_ctx* ctx, const double* du /*[4*n_nodes]*/);
+int gx_get_solution(gx_ctx* ctx, double* u /*[n_nodes*3]*/, double* p /*[n_nodes]*/);
+int gx_sync_solution(gx_ctx* ctx);
+int gx_pack_solution(gx_ctx* ctx, int peer_index, void** send_dev, int64_t* send_bytes); /* owner side */
+int gx_unpack_solution(gx_ctx* ctx, int peer_index, const void* recv_dev);               /* copy side: overwrite */
+
 /* History state, AoS as apf stores it (src/goal_states.cpp:21-57): names "sigma",
  * "eqps", "eqps_old", "Fp", "Fp_old"; tensors are 9 doubles row-major per element. */
 int gx_get_state(gx_ctx* ctx, const char* name, double* out);
@@ -133,6 +143,15 @@ int gx_localize_error(gx_ctx* ctx, const double* zu_diff /*[n_nodes*3]*/, const 
 int gx_element_error(gx_ctx* ctx, const double* u_err /*[n_nodes*3]*/, const double* p_err /*[n_nodes]*/,
                      const int32_t* parent /*[n_elems]*/, int32_t n_parent, double* eta_elem /*[n_elems]*/,
                      double* eta_parent /*[n_parent]*/, double* bound);
+
+/* get_iso_target_size (src/goal_size_field.cpp:39-150; Nested adaptation input): from the element error
+ * indicators, G = sum_e |eta_e|^(2d/(2p+d)), size_factor = (G/target)^(1/d), element size
+ * clamp(size_factor |eta_e|^(-2/(2p+d)) h_e, h_e/4, 2 h_e) with h_e = sqrt(mean squared edge length), and the vertex
+ * size = mean over the adjacent elements.  *G <= 0 on entry: this part's G is computed and returned (several parts:
+ * PCU_Add it, then call again with the sum); vtx_size == NULL stops after G.  vtx_count != NULL returns per-vertex
+ * sums and adjacent-element counts instead of means, so that parts can add both before dividing. */
+int gx_size_field(gx_ctx* ctx, const double* eta_elem /*[n_elems]*/, int32_t target, int32_t p_order, double* G,
+                  double* vtx_size /*[n_nodes] or NULL*/, double* vtx_count /*[n_nodes] or NULL*/);
 
 /* ---- "next" rows of SURVEY.md 8(f): what sits either side of the assembly in the same drivers ---------------
  * Functional "avg disp" (Functional::compute src/goal_functional.cpp:62-70, AvgDisp src/goal_avg_disp.cpp:17-21):

@@ -707,6 +707,7 @@ bool qoi_element(go_ctx& c, int e, int type, int es_idx, double const ks[3], T& 
 extern "C" double go_functional(go_ctx* c, int type, int elem_set, double rho, int point_node, int point_idx,
                                 double* dMdu) {
   c->err.clear();
+  c->plastic = 0;
   if (type == GO_QOI_POINT_WISE) {  // PointWise<T>::post_process (goal_point_wise.cpp:37-56)
     if (dMdu) dMdu[4 * (size_t)point_node + point_idx] = 1.0;
     return c->u[3 * (size_t)point_node + point_idx];
@@ -802,6 +803,40 @@ double go_element_error(go_ctx* c, const double* u_err, const double* p_err, dou
     sum += std::fabs(tmp);
   }
   return sum;
+}
+
+// get_iso_target_size (goal_size_field.cpp:39-150), single part; returns G = sum_contributions
+double go_size_field(go_ctx* c, const double* eta, int target, int p_order, double* vtx_size) {
+  double const d = 3.0, p = p_order, alpha = 0.25, beta = 2.0;
+  double G = 0.0;
+  for (int e = 0; e < c->ne; ++e) G += std::pow(std::abs(eta[e]), ((2.0 * d) / (2.0 * p + d)));  // :39-52
+  double const size_factor = std::pow((G / (double)target), (1.0 / d));                             // :54-59
+  std::vector<double> hn(c->ne);
+  static const int ev[6][2] = {{0, 1}, {1, 2}, {2, 0}, {0, 3}, {1, 3}, {2, 3}};
+  for (int e = 0; e < c->ne; ++e) {
+    double h = 0.0;  // get_current_size (:61-69)
+    for (int k = 0; k < 6; ++k) {
+      double l2 = 0.0;
+      for (int j = 0; j < 3; ++j) {
+        double t = c->coords[3 * (size_t)c->conn[4 * (size_t)e + ev[k][1]] + j] - c->coords[3 * (size_t)c->conn[4 * (size_t)e + ev[k][0]] + j];
+        l2 += t * t;
+      }
+      double const l = std::sqrt(l2);
+      h += l * l;
+    }
+    h = std::sqrt(h / 6);
+    double const r = std::pow(std::abs(eta[e]), ((-2.0) / (2.0 * p + d)));  // get_new_size (:71-81)
+    double h_new = size_factor * r * h;
+    if (h_new < alpha * h) h_new = alpha * h;
+    if (h_new > beta * h) h_new = beta * h;
+    hn[e] = h_new;
+  }
+  std::vector<double> sum(c->nn, 0.0);
+  std::vector<int> cnt(c->nn, 0);
+  for (int e = 0; e < c->ne; ++e)  // avg_to_vtx (:95-106)
+    for (int n = 0; n < 4; ++n) { sum[c->conn[4 * (size_t)e + n]] += hn[e]; cnt[c->conn[4 * (size_t)e + n]]++; }
+  for (int v = 0; v < c->nn; ++v) vtx_size[v] = cnt[v] ? sum[v] / cnt[v] : 0.0;
+  return G;
 }
 
 int64_t go_last_plastic_count(go_ctx* c) { return c->plastic; }

@@ -79,6 +79,9 @@ int go_assemble_error(go_ctx*, const double* zu_diff /*[Nn*3]*/, const double* z
 double go_element_error(go_ctx*, const double* u_err, const double* p_err, double* eta_elem,
                         const int32_t* parent, int n_parent, double* eta_parent);
 
+/* get_iso_target_size (src/goal_size_field.cpp:39-150), one part: vertex sizes [Nn]; returns sum_contributions */
+double go_size_field(go_ctx*, const double* eta /*[Ne]*/, int target, int p_order, double* vtx_size);
+
 /* number of elements that took the plastic branch in the last assemble call */
 int64_t go_last_plastic_count(go_ctx*);
 const char* go_last_error(go_ctx*);

@@ -48,6 +48,8 @@ def lib():
         L.go_functional_avg_disp.restype = C.c_double
         L.go_functional_avg_disp.argtypes = [C.c_void_p, dp]
         L.go_assemble_error.argtypes = [C.c_void_p, dp, dp, dp, dp]
+        L.go_size_field.restype = C.c_double
+        L.go_size_field.argtypes = [C.c_void_p, dp, C.c_int, C.c_int, dp]
         L.go_functional.restype = C.c_double
         L.go_functional.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, dp]
         L.go_element_error.restype = C.c_double
@@ -156,6 +158,12 @@ class Oracle:
             return eta, etap, b
         b = self.L.go_element_error(self.h, _dp(u_err), _dp(p_err), _dp(eta), None, 0, None)
         return eta, None, b
+
+    def size_field(self, eta, target, p_order=1):
+        eta = np.ascontiguousarray(eta, dtype=np.float64)
+        v = np.zeros(self.nn)
+        G = self.L.go_size_field(self.h, _dp(eta), target, p_order, _dp(v))
+        return v, G
 
     def plastic_count(self):
         return self.L.go_last_plastic_count(self.h)

@@ -41,6 +41,27 @@ def main():
         R2, V2, _ = a.fetch_owned()
         assert np.array_equal(R1, R2) and np.array_equal(V1, V2)
         _check_owned(a, me, o, Rs, Vs)
+        # Disc::add_soln + apf::synchronize over NCCL (gx_add_solution, gx_sync_solution): right on owned nodes,
+        # garbage on copies, the owner's value wins everywhere
+        dug = 1e-3 * np.random.RandomState(9).randn(len(fs["u"]), 4)
+        du = dug[me["node_gid"]].copy()
+        du[me["node_owner"] != rank] = 123.0
+        a.add_solution(du)
+        a.sync_solution()
+        u, pr = a.get_solution()
+        assert np.array_equal(u, fs["u"][me["node_gid"]] + dug[me["node_gid"], :3])
+        assert np.array_equal(pr, fs["p"][me["node_gid"]] + dug[me["node_gid"], 3])
+        # functional derivative reduced like gather_dMdu: owned rows equal the serial dMdu
+        from oracle.oracle import Oracle
+        a.set_solution(fs["u"][me["node_gid"]], fs["p"][me["node_gid"]])
+        J, _ = a.functional("avg vm", with_dMdu=True)
+        a.reduce_interfaces(4)
+        d = a.fetch_dMdu().reshape(-1, 4)
+        Jg = a.allreduce_sum(np.array([J]))[0]
+        Jo, do = o.functional("avg vm", with_dMdu=True)
+        own = me["node_owner"] == rank
+        assert abs(Jg - Jo) < 1e-12 * abs(Jo)
+        assert np.abs(d[own] - do.reshape(-1, 4)[me["node_gid"][own]]).max() < 1e-12 * np.abs(do).max()
         s = a.allreduce_sum(np.array([float(rank + 1)]))
         assert s[0] == world * (world + 1) / 2
         a.close()

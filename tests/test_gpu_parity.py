@@ -275,6 +275,35 @@ def test_side_set_boundary_terms(cube):
     a.close(); a2.close()
 
 
+@pytest.mark.parametrize("mesh", ["cube", "kuhn6"])
+def test_solution_update_and_size_field(cube, mesh):
+    """SURVEY 8(f) rank 4: Disc::add_soln (src/goal_disc.cpp:398-422) on the device-resident solution and
+    get_iso_target_size (src/goal_size_field.cpp:39-150) from the element indicators, against the oracle."""
+    co, cn = _mesh(cube, mesh)
+    f = fields(co, len(cn), strain=0.004)
+    a, o = _pair(co, cn, "neohookean", f)
+    rng = np.random.RandomState(4)
+    du = 1e-3 * rng.randn(len(co), 4)
+    a.add_solution(du)
+    u, p = a.get_solution()
+    assert np.array_equal(u, f["u"] + du[:, :3]) and np.array_equal(p, f["p"] + du[:, 3])
+    o.set_solution(u, p)
+    assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12  # the kernels see the updated fields
+    eta = np.abs(rng.randn(len(cn))) * 10.0 ** rng.uniform(-8, -2, len(cn))  # spans both clamps
+    target = 3 * len(cn)
+    v, G = a.size_field(eta, target)
+    vo, Go = o.size_field(eta, target)
+    assert abs(G - Go) < 1e-13 * Go and relerr(v, vo) < 1e-13
+    x = co[cn]
+    h = np.sqrt(sum(((x[:, i] - x[:, j]) ** 2).sum(1) for i in range(4) for j in range(i + 1, 4)) / 6)
+    assert v.min() >= 0.25 * h.min() * (1 - 1e-12) and v.max() <= 2.0 * h.max() * (1 + 1e-12)
+    # partitioned form: sums and counts, with the reduced G passed in
+    s2, G2, c2 = a.size_field(eta, target, G=G, counts=True)
+    assert G2 == G and relerr(s2 / c2, v) < 1e-15
+    assert np.array_equal(c2, np.bincount(cn.reshape(-1), minlength=len(co)))
+    a.close()
+
+
 def test_bitwise_determinism(cube):
     """No atomics on the data path: repeated passes give identical bits."""
     import goal_b200

@@ -77,7 +77,8 @@ def test_interface_exchange_host_transport(cube, case, model, kernel):
         Rg, Vg = a.fetch()
         assert Vg.shape == (a.nnz,)
     L = A[0].L
-    for what in (1, 2):
+
+    def exchange(what):
         for q, aq in enumerate(A):  # owner side, peers ascending
             for pj in range(aq.num_peers):
                 r = int(parts[q]["peer_rank"][pj])
@@ -88,8 +89,42 @@ def test_interface_exchange_host_transport(cube, case, model, kernel):
                 L.gx_interface_bytes(aq.h, pj, what, C.byref(sb), C.byref(rb))
                 if rb.value:
                     assert L.gx_unpack_add_interface(aq.h, pj, what, buf) == 0
+
+    exchange(1)
+    exchange(2)
     for r, a in enumerate(A):
         _check_owned(a, parts[r], o, Rs, Vs)
+    # functional + gather_dMdu (src/goal_sol_info.cpp:37-39): part values add up, owned dMdu rows equal the serial ones
+    Jo, do = o.functional("avg vm", with_dMdu=True)
+    Js = [a.functional("avg vm", with_dMdu=True)[0] for a in A]
+    exchange(4)
+    assert abs(sum(Js) - Jo) < 1e-12 * abs(Jo)
+    for r, a in enumerate(A):
+        own = parts[r]["node_owner"] == r
+        d = a.fetch_dMdu().reshape(-1, 4)
+        assert np.abs(d[own] - do.reshape(-1, 4)[parts[r]["node_gid"][own]]).max() < 1e-12 * np.abs(do).max()
+    # Disc::add_soln + apf::synchronize (src/goal_disc.cpp:398-422): every part adds an increment that is right on
+    # the nodes it owns and garbage on its copies; after the owner -> copies push all parts hold the global field
+    ngl = len(fs["u"])
+    dug = 1e-3 * np.random.RandomState(9).randn(ngl, 4)
+    for r, a in enumerate(A):
+        p = parts[r]
+        du = dug[p["node_gid"]].copy()
+        du[p["node_owner"] != r] = 123.0
+        a.add_solution(du)
+    for q, aq in enumerate(A):  # owner q packs for each peer, the peer overwrites its copies
+        for pj in range(aq.num_peers):
+            r = int(parts[q]["peer_rank"][pj])
+            pi = list(parts[r]["peer_rank"]).index(q)
+            buf, nb = C.c_void_p(), C.c_int64()
+            assert L.gx_pack_solution(aq.h, pj, C.byref(buf), C.byref(nb)) == 0
+            if nb.value:
+                assert L.gx_unpack_solution(A[r].h, pi, buf) == 0
+    for r, a in enumerate(A):
+        p = parts[r]
+        u, pr = a.get_solution()
+        assert np.array_equal(u, fs["u"][p["node_gid"]] + dug[p["node_gid"], :3])
+        assert np.array_equal(pr, fs["p"][p["node_gid"]] + dug[p["node_gid"], 3])
         a.close()
 
 
