@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgoal_b200.so")
+# GOAL_B200_LIB: developer switch for A/B timing of two builds of the same library (never a different backend)
+LIB_PATH = os.environ.get("GOAL_B200_LIB") or os.path.join(_HERE, "libgoal_b200.so")
 
 MODEL = {"neohookean": 0, "J2": 1}
 NONE, PRIMAL, ADJOINT = 0, 1, 2

@@ -61,12 +61,12 @@ __global__ void update_states_kernel(double* sin, double* fp_old, double const* 
   if (e >= ne) return;
   double Fp[9], Cp[6];
   for (int k = 0; k < 9; ++k) {
-    if (copy) fp_old[9 * (int64_t)e + k] = sout[(int64_t)STATE_OUT * e + 9 + k];
+    if (copy) fp_old[9 * (int64_t)e + k] = sout[(int64_t)STATE_OUT * e + SO_FP + k];
     Fp[k] = fp_old[9 * (int64_t)e + k];
   }
   cp_inverse(Fp, Cp);
   for (int k = 0; k < 6; ++k) sin[(int64_t)STATE_IN * e + k] = Cp[k];
-  if (copy) sin[(int64_t)STATE_IN * e + 6] = sout[(int64_t)STATE_OUT * e + 18];
+  if (copy) sin[(int64_t)STATE_IN * e + 6] = sout[(int64_t)STATE_OUT * e + SO_EQPS];
 }
 
 // compute_error (src/goal_error.cpp:7-35): |sum_d u_err_d(xi_c) + p_err(xi_c)|; err4 = [Nn][4] (u0,u1,u2,p)
@@ -534,8 +534,8 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
   std::string n(name ? name : "");
   if (n == "sigma") { L = {ctx->d_state_out, STATE_OUT, 0, 9}; return true; }
   if (ctx->model != GX_MODEL_J2) return false;  // only J2 registers eqps / Fp (goal_mechanics.cpp:90-93)
-  if (n == "Fp") { L = {ctx->d_state_out, STATE_OUT, 9, 9}; return true; }
-  if (n == "eqps") { L = {ctx->d_state_out, STATE_OUT, 18, 1}; return true; }
+  if (n == "Fp") { L = {ctx->d_state_out, STATE_OUT, SO_FP, 9}; return true; }
+  if (n == "eqps") { L = {ctx->d_state_out, STATE_OUT, SO_EQPS, 1}; return true; }
   if (n == "Fp_old") { L = {ctx->d_fp_old, 9, 0, 9}; return true; }
   if (n == "eqps_old") { L = {ctx->d_state_in, STATE_IN, 6, 1}; return true; }
   return false;
@@ -633,7 +633,7 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
       if (ctx->model == GX_MODEL_J2)
         for (int e = 0; e < ne; ++e) {
           for (int k = 0; k < 3; ++k) sin[(size_t)STATE_IN * e + k] = 1.0;  // Cp^{-1} of Fp_old = I
-          for (int k = 0; k < 9; k += 4) { fpo[(size_t)9 * e + k] = 1.0; sout[(size_t)STATE_OUT * e + 9 + k] = 1.0; }
+          for (int k = 0; k < 9; k += 4) { fpo[(size_t)9 * e + k] = 1.0; sout[(size_t)STATE_OUT * e + SO_FP + k] = 1.0; }
         }
       GX_CUDA(cudaMalloc(&ctx->d_state_in, sizeof(double) * sin.size()));
       GX_CUDA(cudaMalloc(&ctx->d_fp_old, sizeof(double) * fpo.size()));

@@ -184,7 +184,8 @@ struct HostPack {
   std::vector<uint8_t> eset;
 };
 constexpr int STATE_IN = 8;    // doubles per element
-constexpr int STATE_OUT = 20;
+constexpr int STATE_OUT = 20;   // sigma[9] | eqps | Fp[9] | pad: 16 B pairs 0-4 are always written, pairs 5-9 only on the plastic branch
+constexpr int SO_SIGMA = 0, SO_EQPS = 9, SO_FP = 10;
 void pack_host(gx_ctx const* c, HostPack& h);
 void build_block_lists(gx_ctx* c);
 bool build_patch_schedule(gx_ctx* c);

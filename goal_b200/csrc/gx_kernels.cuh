@@ -13,7 +13,7 @@
 //                          incidence writes, grouped by node (adj_off[Nn+1]); the row-owner work list
 //   state_in  double[Ne][8]   Cp^{-1}[6] of Fp_old (cached), eqps_old, pad   64 B record (4 LDG.128)
 //   fp_old    double[Ne][9]   read only by the one incidence that saves a plastic element's Fp
-//   state_out double[Ne][20]  sigma[9], Fp[9], eqps, pad                     160 B record
+//   state_out double[Ne][20]  sigma[9], eqps, Fp[9], pad                     160 B record
 //   R         double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
 //
 // Two schedules, both free of atomics on the data path and bit-reproducible:
@@ -74,18 +74,34 @@ template <class T> GX_HD T ldg(T const* p) {
 #endif
 }
 
-GX_HD void load_node(NodeRec const* nodes, int id, double x[3], double u[3], double& p, int& blk0, int& nblk) {
-  double2 const* q = reinterpret_cast<double2 const*>(nodes + id);
-  double2 const d0 = ldg(q), d1 = ldg(q + 1), d2 = ldg(q + 2), d3 = ldg(q + 3);
-  x[0] = d0.x; x[1] = d0.y; x[2] = d1.x;
-  u[0] = d1.y; u[1] = d2.x; u[2] = d2.y;
-  p = d3.x;
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one request where two 128-bit ones were needed, which halves
+// the L1TEX tag-stage work of the scattered record gathers and block stores.  p must be 32 B aligned.
+GX_HD void ldg256(double const* p, double& a, double& b, double& c, double& d) {
 #if defined(__CUDA_ARCH__)
-  blk0 = __double2loint(d3.y);
-  nblk = __double2hiint(d3.y);
+  asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+#else
+  a = p[0]; b = p[1]; c = p[2]; d = p[3];
+#endif
+}
+GX_HD void stg256(double* p, double a, double b, double c, double d) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+#else
+  p[0] = a; p[1] = b; p[2] = c; p[3] = d;
+#endif
+}
+
+GX_HD void load_node(NodeRec const* nodes, int id, double x[3], double u[3], double& p, int& blk0, int& nblk) {
+  double const* q = reinterpret_cast<double const*>(nodes + id);
+  double t3;
+  ldg256(q, x[0], x[1], x[2], u[0]);
+  ldg256(q + 4, u[1], u[2], p, t3);
+#if defined(__CUDA_ARCH__)
+  blk0 = __double2loint(t3);
+  nblk = __double2hiint(t3);
 #else
   int32_t t[2];
-  __builtin_memcpy(t, &d3.y, 8);
+  __builtin_memcpy(t, &t3, 8);
   blk0 = t[0]; nblk = t[1];
 #endif
 }
@@ -106,10 +122,11 @@ GX_HD void add4(double* dst, double a, double b, double c, double d) {
   q[0] = v0; q[1] = v1;
 }
 
-// gather + stress update of one element; writes the history state when SAVE && write_state
-template <int MODEL, bool SAVE>
-GX_HD int load_and_update(KParams const& P, int e, bool write_state, int nd[4], int blk0[4], int nblk[4],
-                          Material const*& mat, Core<double>& c) {
+// gather + stress update of one element.  want_state: also return the state the evaluators would save
+// (mixed Cauchy stress sig[9], eqps) -- writing it is the caller's job.
+template <int MODEL>
+GX_HD int load_element(KParams const& P, int e, bool want_state, int nd[4], int blk0[4], int nblk[4], Material const*& mat,
+                       Core<double>& c, double sig[9], double& eqps_new) {
   int4 const cn = ldg(P.conn + e);
   nd[0] = cn.x; nd[1] = cn.y; nd[2] = cn.z; nd[3] = cn.w;
   double x[4][3], u[4][3], p[4];
@@ -118,19 +135,33 @@ GX_HD int load_and_update(KParams const& P, int e, bool write_state, int nd[4], 
   mat = &P.mat[P.eset ? P.eset[e] : 0];
   double Cp[6], eqps_old = 0.0;
   if (MODEL == MODEL_J2) {
-    double2 const* q = reinterpret_cast<double2 const*>(P.state_in + (int64_t)STATE_IN * e);
-    double2 const a0 = ldg(q), a1 = ldg(q + 1), a2 = ldg(q + 2), a3 = ldg(q + 3);
-    Cp[0] = a0.x; Cp[1] = a0.y; Cp[2] = a1.x; Cp[3] = a1.y; Cp[4] = a2.x; Cp[5] = a2.y; eqps_old = a3.x;
+    double const* q = P.state_in + (int64_t)STATE_IN * e;
+    double pad;
+    ldg256(q, Cp[0], Cp[1], Cp[2], Cp[3]);
+    ldg256(q + 4, Cp[4], Cp[5], eqps_old, pad);
   }
+  eqps_new = 0.0;
+  return element_core<MODEL>(x, u, p, *mat, Cp, eqps_old, want_state, sig, eqps_new, c);
+}
+
+// sigma and eqps of one element -> pairs 0-4 of its state record: two 256-bit stores and one 128-bit store
+template <int MODEL>
+GX_HD void store_sigma_eqps(KParams const& P, int e, double const sig[9], double eqps_new) {
+  double* so = P.state_out + (int64_t)STATE_OUT * e;  // 160 B records: 32 B aligned
+  stg256(so, sig[0], sig[1], sig[2], sig[3]);
+  stg256(so + 4, sig[4], sig[5], sig[6], sig[7]);
+  if (MODEL == MODEL_J2) *reinterpret_cast<double2*>(so + 8) = make_double2(sig[8], eqps_new);
+  else so[8] = sig[8];
+}
+
+// gather + stress update of one element; writes the history state when SAVE && write_state
+template <int MODEL, bool SAVE>
+GX_HD int load_and_update(KParams const& P, int e, bool write_state, int nd[4], int blk0[4], int nblk[4],
+                          Material const*& mat, Core<double>& c) {
   double sig[9], eqps_new = 0.0;
-  int const rc = element_core<MODEL>(x, u, p, *mat, Cp, eqps_old, SAVE && write_state, sig, eqps_new, c);
+  int const rc = load_element<MODEL>(P, e, SAVE && write_state, nd, blk0, nblk, mat, c, sig, eqps_new);
   if (rc != ERR_NONE) return rc;
-  if (SAVE && write_state) {
-    double* so = P.state_out + (int64_t)STATE_OUT * e;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) so[k] = sig[k];
-    if (MODEL == MODEL_J2) so[18] = eqps_new;
-  }
+  if (SAVE && write_state) store_sigma_eqps<MODEL>(P, e, sig, eqps_new);
   return ERR_NONE;
 }
 
@@ -141,7 +172,7 @@ GX_HD void save_plastic_Fp(KParams const& P, int e, double const dN[6]) {
 #pragma unroll
   for (int k = 0; k < 9; ++k) Fpo[k] = ldg(src + k);
   plastic_update(dN, Fpo, Fpn);
-  double* so = P.state_out + (int64_t)STATE_OUT * e + 9;
+  double* so = P.state_out + (int64_t)STATE_OUT * e + SO_FP;
 #pragma unroll
   for (int k = 0; k < 9; ++k) so[k] = Fpn[k];
 }
@@ -418,21 +449,62 @@ __device__ __forceinline__ void unpack_tangent(double2 const* q, Core<double>& c
   v = ld(21); c.vgr = v.x; c.rb = v.y;
 }
 
+// Warp-cooperative Fp update of 32 consecutive elements e0 .. e0+nrec-1 (lane = element), plastic branch only:
+// Fp = exp(dgam N) Fp_old (goal_J2.cpp:128-131); on the elastic branch the reference leaves Fp untouched (:135-136).
+// Per-thread accesses of the 72 B Fp_old / Fp records touch 32 different 128 B lines per instruction (9 + 9
+// instructions); staged through shared memory the warp reads its 2.3 KB of Fp_old with 5 coalesced 128-bit loads and
+// writes the Fp halves of its state records (pairs 5-9, 80 B each) with 5 coalesced 128-bit stores.
+// buf: >= WSAVE_DOUBLES doubles of shared memory that belong to the warp and are free (callers __syncwarp first).
+constexpr int WSAVE_ST = 288, WSAVE_LD = 11;  // Fp_old block at [0, 288), Fp rows of 11 doubles (odd: conflict-free) behind it
+constexpr int WSAVE_DOUBLES = WSAVE_ST + 32 * WSAVE_LD;
+__device__ __forceinline__ void warp_save_Fp(KParams const& P, int e0, int nrec, int lane, int plastic, double const dN[6], double* buf) {
+  unsigned const pmask = __ballot_sync(0xffffffffu, plastic != 0);
+  if (!pmask) return;
+  double const* src = P.fp_old + 9 * (int64_t)e0;  // 72 B * e0, e0 a multiple of 32: 16 B aligned
+  int const tot = 9 * nrec;
+  for (int g = 2 * lane; g < tot; g += 64) {
+    if (g + 1 < tot) { double2 const v = __ldg(reinterpret_cast<double2 const*>(src + g)); buf[g] = v.x; buf[g + 1] = v.y; }
+    else buf[g] = __ldg(src + g);
+  }
+  __syncwarp();
+  if (plastic) {
+    double Fpo[9], Fpn[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) Fpo[k] = buf[9 * lane + k];
+    plastic_update(dN, Fpo, Fpn);
+    double* st = buf + WSAVE_ST + lane * WSAVE_LD;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) st[k] = Fpn[k];
+    st[9] = 0.0;
+  }
+  __syncwarp();
+  double* dst = P.state_out + (int64_t)STATE_OUT * e0 + SO_FP;
+  for (int g = lane; g < nrec * 5; g += 32) {
+    int const r = g / 5, j = g - r * 5;
+    if (!((pmask >> r) & 1u)) continue;
+    double const* q = buf + WSAVE_ST + r * WSAVE_LD + 2 * j;
+    *reinterpret_cast<double2*>(dst + STATE_OUT * r + 2 * j) = make_double2(q[0], q[1]);
+  }
+}
+
 template <int MODEL, bool SAVE>
-__global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
+__global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
   // records leave through shared memory so that a warp writes its 32 records (11.5 KB, contiguous) with
-  // fully coalesced 128-bit stores instead of 23 stride-368 B stores per thread
-  __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 57 doubles (odd): conflict-free column writes
+  // fully coalesced 128-bit stores instead of 23 stride-368 B stores per thread; the Fp update reuses the buffer
+  __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 47 doubles (odd): conflict-free column writes
+  static_assert(32 * ELEM_REC + 32 >= WSAVE_DOUBLES, "state staging must fit the record buffer");
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const e0 = blockIdx.x * blockDim.x + wib * 32;  // first element of this warp
+  int const nrec = min(32, ne - e0);
   double* mine = &srec[wib][lane * (ELEM_REC + 1)];
   int plastic = 0;
+  double dN[6];
+  if (SAVE && MODEL == MODEL_J2 && nrec > 0 && lane < 19) {  // the warp's Fp_old block is read last: have it in L2 by then
+    char const* f = reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)e0) + 128 * lane;
+    if (f < reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)(e0 + nrec))) asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
+  }
   if (e < ne) {
-    if (SAVE && MODEL == MODEL_J2) {  // Fp_old is needed last (plastic elements only): have it in L1 by then
-      char const* f = reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)e);
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(f));
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(f + 64));
-    }
     int nd[4], b0[4], nb[4];
     Material const* matp;
     Core<double> c;
@@ -452,21 +524,24 @@ __global__ void __launch_bounds__(64) elem_record_kernel(const __grid_constant__
       mine[30] = c.q[0]; mine[31] = c.q[1]; mine[32] = c.q[2]; mine[33] = c.gwv; mine[34] = c.A1v; mine[35] = c.Jpv;
       mine[36] = c.upc; mine[37] = c.va; mine[38] = c.tjv; mine[39] = c.ppc; mine[40] = c.vb; mine[41] = c.gNs;
       mine[42] = c.vgr; mine[43] = c.rb; mine[44] = 0.0; mine[45] = 0.0;
-      if (SAVE && MODEL == MODEL_J2 && c.plastic) save_plastic_Fp(P, e, c.dN);
+      if (SAVE && MODEL == MODEL_J2 && plastic) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dN[k] = c.dN[k];
+      }
     }
   }
   __syncwarp();
-  {
-    int const e0 = (blockIdx.x * blockDim.x + wib * 32);  // first element of this warp
-    int const nrec = min(32, ne - e0);
-    if (nrec > 0) {
-      double* dst = rec + (int64_t)ELEM_REC * e0;
-      int const total = nrec * ELEM_REC;  // doubles, contiguous in global memory
-      for (int g = 2 * lane; g < total; g += 64) {
-        int const r = g / ELEM_REC, k = g - r * ELEM_REC;  // ELEM_REC is even: the pair stays inside one record
-        double const* src = &srec[wib][r * (ELEM_REC + 1) + k];
-        *reinterpret_cast<double2*>(dst + g) = make_double2(src[0], src[1]);
-      }
+  if (nrec > 0) {
+    double* dst = rec + (int64_t)ELEM_REC * e0;
+    int const total = nrec * ELEM_REC;  // doubles, contiguous in global memory
+    for (int g = 2 * lane; g < total; g += 64) {
+      int const r = g / ELEM_REC, k = g - r * ELEM_REC;  // ELEM_REC is even: the pair stays inside one record
+      double const* src = &srec[wib][r * (ELEM_REC + 1) + k];
+      *reinterpret_cast<double2*>(dst + g) = make_double2(src[0], src[1]);
+    }
+    if (SAVE && MODEL == MODEL_J2) {
+      __syncwarp();  // the record buffer is free again
+      warp_save_Fp(P, e0, nrec, lane, plastic, dN, srec[wib]);
     }
   }
   if (MODEL == MODEL_J2) {
@@ -907,16 +982,8 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
     int const rl = (int)(ot.z & 0xffffu);
     double* out = P.values + voff;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      double2* o = reinterpret_cast<double2*>(out + (int64_t)i * rl);
-      o[0] = make_double2(acc[4 * i], acc[4 * i + 1]);
-      o[1] = make_double2(acc[4 * i + 2], acc[4 * i + 3]);
-    }
-    if (diag) {
-      double2* o = reinterpret_cast<double2*>(P.R + 4 * (int64_t)(ot.w & 0x7fffffffu));
-      o[0] = make_double2(r4[0], r4[1]);
-      o[1] = make_double2(r4[2], r4[3]);
-    }
+    for (int i = 0; i < 4; ++i) stg256(out + (int64_t)i * rl, acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);  // one 32 B sector each
+    if (diag) stg256(P.R + 4 * (int64_t)(ot.w & 0x7fffffffu), r4[0], r4[1], r4[2], r4[3]);
   };
   if (kind == 0) return;
   if (kind == 1 && nsec == 0) { write_out(); return; }
@@ -951,9 +1018,22 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
 //                          element order and writes R[4a .. 4a+3] once.
 // ---------------------------------------------------------------------------
 template <int MODEL, bool SAVE, bool ERROR>
-__global__ void __launch_bounds__(128) elem_residual_kernel(const __grid_constant__ KParams P, double* __restrict__ rvec, int ne) {
+__global__ void __launch_bounds__(128, 4) elem_residual_kernel(const __grid_constant__ KParams P, double* __restrict__ rvec, int ne) {
+  // the element residual lines (128 B each) and the state leave through shared memory: coalesced 128-bit stores
+  // instead of 32 different 128 B lines per store instruction
+  __shared__ double sbuf[4][WSAVE_DOUBLES];
+  static_assert(WSAVE_DOUBLES >= 32 * 17, "residual staging must fit");
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int const e0 = blockIdx.x * blockDim.x + wib * 32;
+  int const nrec = min(32, ne - e0);
+  double* buf = sbuf[wib];
   int plastic = 0;
+  double dN[6];
+  if (SAVE && MODEL == MODEL_J2 && nrec > 0 && lane < 19) {
+    char const* f = reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)e0) + 128 * lane;
+    if (f < reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)(e0 + nrec))) asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
+  }
   if (e < ne) {
     int nd[4], b0[4], nb[4];
     Material const* matp;
@@ -980,13 +1060,25 @@ __global__ void __launch_bounds__(128) elem_residual_kernel(const __grid_constan
       } else {
         element_residual(c, ru, rp);
       }
-      if (SAVE && MODEL == MODEL_J2 && c.plastic) save_plastic_Fp(P, e, c.dN);
-    }
-    double2* o = reinterpret_cast<double2*>(rvec + 16 * (int64_t)e);
+      if (SAVE && MODEL == MODEL_J2 && plastic) {
 #pragma unroll
-    for (int n = 0; n < 4; ++n) {
-      o[2 * n] = make_double2(ru[3 * n], ru[3 * n + 1]);
-      o[2 * n + 1] = make_double2(ru[3 * n + 2], rp[n]);
+        for (int k = 0; k < 6; ++k) dN[k] = c.dN[k];
+      }
+    }
+    double* o = buf + 17 * lane;  // row stride 17 (odd): conflict-free
+#pragma unroll
+    for (int n = 0; n < 4; ++n) { o[4 * n] = ru[3 * n]; o[4 * n + 1] = ru[3 * n + 1]; o[4 * n + 2] = ru[3 * n + 2]; o[4 * n + 3] = rp[n]; }
+  }
+  __syncwarp();
+  if (nrec > 0) {
+    double* dst = rvec + 16 * (int64_t)e0;
+    for (int g = lane; g < nrec * 8; g += 32) {
+      double const* q = buf + 17 * (g >> 3) + 2 * (g & 7);
+      *reinterpret_cast<double2*>(dst + 2 * g) = make_double2(q[0], q[1]);
+    }
+    if (SAVE && MODEL == MODEL_J2) {
+      __syncwarp();
+      warp_save_Fp(P, e0, nrec, lane, plastic, dN, buf);
     }
   }
   if (MODEL == MODEL_J2) {

@@ -124,8 +124,8 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   for (int e = 0; e < ne; ++e) {
     for (int k = 0; k < 9; ++k) sout[(size_t)gx::STATE_OUT * e + k] = sigma[9 * (size_t)e + k];
     if (model == 1) {
-      sout[(size_t)gx::STATE_OUT * e + 18] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 6] = eqps_old[e];
-      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + 9 + k] = Fp[9 * (size_t)e + k]; fpo[(size_t)9 * e + k] = Fp_old[9 * (size_t)e + k]; }
+      sout[(size_t)gx::STATE_OUT * e + gx::SO_EQPS] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 6] = eqps_old[e];
+      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + gx::SO_FP + k] = Fp[9 * (size_t)e + k]; fpo[(size_t)9 * e + k] = Fp_old[9 * (size_t)e + k]; }
       gx::cp_inverse(&fpo[(size_t)9 * e], &sin[(size_t)gx::STATE_IN * e]);
     }
   }
@@ -150,8 +150,8 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   for (int e = 0; e < ne; ++e) {
     for (int k = 0; k < 9; ++k) sigma[9 * (size_t)e + k] = sout[(size_t)gx::STATE_OUT * e + k];
     if (model == 1) {
-      eqps[e] = sout[(size_t)gx::STATE_OUT * e + 18];
-      for (int k = 0; k < 9; ++k) Fp[9 * (size_t)e + k] = sout[(size_t)gx::STATE_OUT * e + 9 + k];
+      eqps[e] = sout[(size_t)gx::STATE_OUT * e + gx::SO_EQPS];
+      for (int k = 0; k < 9; ++k) Fp[9 * (size_t)e + k] = sout[(size_t)gx::STATE_OUT * e + gx::SO_FP + k];
     }
   }
   return err[0] ? 100 + err[0] : 0;
