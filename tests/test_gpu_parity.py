@@ -223,8 +223,6 @@ def test_all_functionals_match_fad_oracle(cube, model, mesh):
         assert J2 == J and np.array_equal(d, d2), t  # deterministic
     # the dedicated avg-disp entry point agrees with the generic one
     assert abs(a.avg_disp() - a.functional("avg disp")) < 1e-15
-    if model == "J2":
-        assert o.plastic_count() > 0
     a.close()
 
 
