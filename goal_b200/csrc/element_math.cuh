@@ -215,6 +215,7 @@ struct Core {
   S tjv;       // vol * taus * J
   S ppc;       // vol / (16 kappa)
   S rb;        // vol * (p/kappa - (J - 1/J)/2) / 4     R_p without stabilization
+  S rc1, tb3;  // 1/c1 and tr(B)/3:  r_n = B w_n = rc1 (s w_n) + tb3 w_n   (B = s/c1 + tr(B)/3 I), see node_r()
   S dN[6];     // plastic branch: flow increment dgam*N (symmetric), input of plastic_update
   // geometry kept for the adjoint-weighted residual
   S G[4][3];
@@ -299,6 +300,7 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
     c.s[0] = c1 * (b[0] - tr3); c.s[1] = c1 * (b[1] - tr3); c.s[2] = c1 * (b[2] - tr3);
     c.s[3] = c1 * b[3]; c.s[4] = c1 * b[4]; c.s[5] = c1 * b[5];
     c.c1 = c1;
+    c.rc1 = S(1.0) / c1; c.tb3 = tr3;
     for (int n = 1; n < 4; ++n)
       for (int i = 0; i < 3; ++i) c.r[n][i] = F[3 * i] * c.G[n][0] + F[3 * i + 1] * c.G[n][1] + F[3 * i + 2] * c.G[n][2];
     for (int i = 0; i < 6; ++i) snew[i] = c.s[i];
@@ -329,6 +331,7 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
     c.s[0] = c1 * (B[0] - tr3); c.s[1] = c1 * (B[1] - tr3); c.s[2] = c1 * (B[2] - tr3);
     c.s[3] = c1 * B[3]; c.s[4] = c1 * B[4]; c.s[5] = c1 * B[5];
     c.mubar = c1 * tr3;  // mu * trace(be) / 3
+    c.rc1 = S(1.0) / c1; c.tb3 = tr3;
     for (int n = 1; n < 4; ++n)
       for (int i = 0; i < 3; ++i) c.r[n][i] = M[3 * i] * c.G[n][0] + M[3 * i + 1] * c.G[n][1] + M[3 * i + 2] * c.G[n][2];
     S const s2 = c.s[0] * c.s[0] + c.s[1] * c.s[1] + c.s[2] * c.s[2] +
@@ -457,6 +460,28 @@ template <class S> GX_HD void column_node(Core<S> const& c, S const wm[3], S con
     cn.A[k] = cn.rA[k] - tw[k];
     cn.B[k] = m23 * cn.rA[k] + c.Jpv * wm[k];
     cn.g[k] = gr[k] + c.gwv * wm[k];
+  }
+  cn.tqw = c.tjv * dot3(c.q, wm);
+}
+
+// r_m = F Cp^{-1} G_m = B w_m with B = F Cp^{-1} F^T = s/c1 + tr(B)/3 I: rebuilt from the spatial gradient, so the
+// tangent records of the two-kernel Jacobian pass carry w_n only.  sw = s w (returned: the callers need it too).
+template <class S> GX_HD void node_r(Core<S> const& c, S const w[3], S sw[3], S r[3]) {
+  sym_mv(c.s, w, sw);
+  for (int k = 0; k < 3; ++k) r[k] = c.rc1 * sw[k] + c.tb3 * w[k];
+}
+// column_node for callers that hold w_m only
+template <class S> GX_HD void column_node_w(Core<S> const& c, S const wm[3], ColNode<S>& cn) {
+  S sw[3], rm[3], sr[3];
+  node_r(c, wm, sw, rm);
+  sym_mv(c.s, rm, sr);
+  S const m23 = S(-2.0 / 3.0);
+  for (int k = 0; k < 3; ++k) {
+    cn.w[k] = wm[k];
+    cn.rA[k] = c.A1v * rm[k];
+    cn.A[k] = cn.rA[k] - (c.vb * sw[k] + c.Jpv * wm[k]);
+    cn.B[k] = m23 * cn.rA[k] + c.Jpv * wm[k];
+    cn.g[k] = (c.gNs * sr[k] + c.vgr * rm[k]) + c.gwv * wm[k];
   }
   cn.tqw = c.tjv * dot3(c.q, wm);
 }

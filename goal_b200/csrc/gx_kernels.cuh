@@ -424,29 +424,41 @@ __global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_const
 // Schedule (1b), the default Jacobian pass: the row-owner schedule split in two kernels so that the
 // element core is evaluated once per element instead of once per incidence.
 //   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the
-//            46-double "tangent record" of the element (everything the 4x4 blocks are built from):
-//              {w_n[3] r_n[3]} x 4 nodes | s[6] | q[3] gwv A1v Jpv upc va tjv ppc vb gNs vgr rb | pad[2]
+//            34-double "tangent record" of the element (everything the 4x4 blocks are built from):
+//              w_n[3] x 4 nodes | s[6] | q[3] gwv A1v Jpv upc va tjv ppc vb gNs vgr rb rc1 tb3
+//            (r_n = F Cp^{-1} G_n is not stored: r_n = rc1 (s w_n) + tb3 w_n, element_math.cuh node_r)
 //   stage B  row_fold_kernel    : one warp per node, one lane per incidence.  Each lane reads its
 //            element's record (368 B, contiguous), builds the four blocks of the node's rows, and the
 //            warp folds and writes the node's CRS rows once, exactly like row_owner_kernel.
 // Costs 368 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
 // element core (about 60 % of all instructions of the fused kernel).
 // ---------------------------------------------------------------------------
-constexpr int ELEM_REC = 46;  // doubles; 368 B = 23 x 16 B: an odd number of 16 B chunks, see patch_gather_kernel
+constexpr int ELEM_REC = 34;  // doubles; 272 B = 17 x 16 B: an odd number of 16 B chunks, see patch_gather_kernel
 
-// chunks 12..21 of a record (16 B each) -> the tangent fields of Core
+// chunks 6..16 of a record (16 B each) -> the tangent fields of Core
 template <bool GLOBAL>
 __device__ __forceinline__ void unpack_tangent(double2 const* q, Core<double>& c) {
   auto ld = [&](int k) { return GLOBAL ? __ldg(q + k) : q[k]; };
 #pragma unroll
-  for (int k = 0; k < 3; ++k) { double2 const v = ld(12 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y; }
-  double2 v = ld(15); c.q[0] = v.x; c.q[1] = v.y;
-  v = ld(16); c.q[2] = v.x; c.gwv = v.y;
-  v = ld(17); c.A1v = v.x; c.Jpv = v.y;
-  v = ld(18); c.upc = v.x; c.va = v.y;
-  v = ld(19); c.tjv = v.x; c.ppc = v.y;
-  v = ld(20); c.vb = v.x; c.gNs = v.y;
-  v = ld(21); c.vgr = v.x; c.rb = v.y;
+  for (int k = 0; k < 3; ++k) { double2 const v = ld(6 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y; }
+  double2 v = ld(9); c.q[0] = v.x; c.q[1] = v.y;
+  v = ld(10); c.q[2] = v.x; c.gwv = v.y;
+  v = ld(11); c.A1v = v.x; c.Jpv = v.y;
+  v = ld(12); c.upc = v.x; c.va = v.y;
+  v = ld(13); c.tjv = v.x; c.ppc = v.y;
+  v = ld(14); c.vb = v.x; c.gNs = v.y;
+  v = ld(15); c.vgr = v.x; c.rb = v.y;
+  v = ld(16); c.rc1 = v.x; c.tb3 = v.y;
+}
+// chunks 0..5 of a record -> w_n of the four nodes
+template <bool GLOBAL>
+__device__ __forceinline__ void unpack_w(double2 const* q, double wv[4][3]) {
+  auto ld = [&](int k) { return GLOBAL ? __ldg(q + k) : q[k]; };
+  double2 const v0 = ld(0), v1 = ld(1), v2 = ld(2), v3 = ld(3), v4 = ld(4), v5 = ld(5);
+  wv[0][0] = v0.x; wv[0][1] = v0.y; wv[0][2] = v1.x;
+  wv[1][0] = v1.y; wv[1][1] = v2.x; wv[1][2] = v2.y;
+  wv[2][0] = v3.x; wv[2][1] = v3.y; wv[2][2] = v4.x;
+  wv[3][0] = v4.y; wv[3][1] = v5.x; wv[3][2] = v5.y;
 }
 
 // Warp-cooperative Fp update of 32 consecutive elements e0 .. e0+nrec-1 (lane = element), plastic branch only:
@@ -489,9 +501,9 @@ __device__ __forceinline__ void warp_save_Fp(KParams const& P, int e0, int nrec,
 
 template <int MODEL, bool SAVE>
 __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
-  // records leave through shared memory so that a warp writes its 32 records (11.5 KB, contiguous) with
-  // fully coalesced 128-bit stores instead of 23 stride-368 B stores per thread; the Fp update reuses the buffer
-  __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 47 doubles (odd): conflict-free column writes
+  // records leave through shared memory so that a warp writes its 32 records (8.5 KB, contiguous) with
+  // fully coalesced 128-bit stores instead of 17 stride-272 B stores per thread; the Fp update reuses the buffer
+  __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 35 doubles (odd): conflict-free column writes
   static_assert(32 * ELEM_REC + 32 >= WSAVE_DOUBLES, "state staging must fit the record buffer");
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,12 +530,12 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
 #pragma unroll
       for (int q = 0; q < 4; ++q)
 #pragma unroll
-        for (int k = 0; k < 3; ++k) { mine[6 * q + k] = c.w[q][k]; mine[6 * q + 3 + k] = c.r[q][k]; }
+        for (int k = 0; k < 3; ++k) mine[3 * q + k] = c.w[q][k];
 #pragma unroll
-      for (int k = 0; k < 6; ++k) mine[24 + k] = c.s[k];
-      mine[30] = c.q[0]; mine[31] = c.q[1]; mine[32] = c.q[2]; mine[33] = c.gwv; mine[34] = c.A1v; mine[35] = c.Jpv;
-      mine[36] = c.upc; mine[37] = c.va; mine[38] = c.tjv; mine[39] = c.ppc; mine[40] = c.vb; mine[41] = c.gNs;
-      mine[42] = c.vgr; mine[43] = c.rb; mine[44] = 0.0; mine[45] = 0.0;
+      for (int k = 0; k < 6; ++k) mine[12 + k] = c.s[k];
+      mine[18] = c.q[0]; mine[19] = c.q[1]; mine[20] = c.q[2]; mine[21] = c.gwv; mine[22] = c.A1v; mine[23] = c.Jpv;
+      mine[24] = c.upc; mine[25] = c.va; mine[26] = c.tjv; mine[27] = c.ppc; mine[28] = c.vb; mine[29] = c.gNs;
+      mine[30] = c.vgr; mine[31] = c.rb; mine[32] = c.rc1; mine[33] = c.tb3;
       if (SAVE && MODEL == MODEL_J2 && plastic) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) dN[k] = c.dN[k];
@@ -580,11 +592,11 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
     if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
   }
   for (; slot < P.nn; slot += W) {
-    // stage 1 of the pipeline: records of the next node -> L2 (4 lines cover the 448 B record)
+    // stage 1 of the pipeline: records of the next node -> L2 (3 lines cover the 272 B record)
     if (p0 + lane < p1) {
       char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
+      for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
     }
     // stage 0: incidences of the node after next
     uint32_t q0 = 0, q1 = 0;
@@ -617,13 +629,16 @@ __global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_consta
           int const e = adr.x >> 2;
           n = adr.x & 3; jpack = (uint32_t)adr.y;
           double2 const* q = reinterpret_cast<double2 const*>(rec + (int64_t)ELEM_REC * e);
-#pragma unroll
-          for (int k = 0; k < 12; ++k) {  // w, r -> shared memory (this lane's column)
-            double2 const v = __ldg(q + k);
-            wr[(2 * k) * WR_LD] = v.x;
-            wr[(2 * k + 1) * WR_LD] = v.y;
-          }
           unpack_tangent<true>(q, c);
+          double wv[4][3];
+          unpack_w<true>(q, wv);
+#pragma unroll
+          for (int n4 = 0; n4 < 4; ++n4) {  // w, r -> shared memory (this lane's column)
+            double sw[3], r3[3];
+            node_r(c, wv[n4], sw, r3);
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { wr[(6 * n4 + k) * WR_LD] = wv[n4][k]; wr[(6 * n4 + 3 + k) * WR_LD] = r3[k]; }
+          }
         }
         double wn[3], rn3[3];
 #pragma unroll
@@ -757,7 +772,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
     if (p0 + lane < p1) {
       char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
+      for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
     }
     if (lane < 4 && p1 - p0 <= 32) {  // next node's schedule (at most 132 words) -> L2
       asm volatile("prefetch.global.L2 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)p0 + 8 * (int64_t)ap + 32 * lane));
@@ -789,17 +804,10 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
         double2 const* q = reinterpret_cast<double2 const*>(rec + (int64_t)ELEM_REC * e);
         Core<double> c;  // only the tangent fields are filled
         double wv[4][3], rv[4][3];
-        {
-          double2 v[12];
-#pragma unroll
-          for (int k = 0; k < 12; ++k) v[k] = __ldg(q + k);
-#pragma unroll
-          for (int n4 = 0; n4 < 4; ++n4) {
-            wv[n4][0] = v[3 * n4].x; wv[n4][1] = v[3 * n4].y; wv[n4][2] = v[3 * n4 + 1].x;
-            rv[n4][0] = v[3 * n4 + 1].y; rv[n4][1] = v[3 * n4 + 2].x; rv[n4][2] = v[3 * n4 + 2].y;
-          }
-        }
         unpack_tangent<true>(q, c);
+        unpack_w<true>(q, wv);
+#pragma unroll
+        for (int n4 = 0; n4 < 4; ++n4) { double sw[3]; node_r(c, wv[n4], sw, rv[n4]); }
         double wn[3], rn3[3];
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
@@ -888,8 +896,8 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 // are finished by their primary item from the secondaries' partial sums (fixed order).  Every block of the patch's
 // rows, and the rows' residual entries, are written exactly once.
 // ---------------------------------------------------------------------------
-constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stride: 368 B = 23 x 16 B (odd), so the bank
-                                        // group of a record's chunk k is (7 slot + k) mod 8
+constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stride: 272 B = 17 x 16 B (odd), so the bank
+                                        // group of a record's chunk k is (slot + k) mod 8
 GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * 20) * sizeof(double); }
 
 template <bool TRANSPOSE>
@@ -944,22 +952,26 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
     double const* rp = srec + slot * PATCH_REC_LD;
     Core<double> c;  // only the tangent fields are filled
     unpack_tangent<false>(reinterpret_cast<double2 const*>(rp), c);
+    // Every lane reads the same 17 chunks of its record, so a quarter-warp whose records sit in 8 different bank
+    // groups (the host schedule sees to that) reads without conflicts; the two nodes the block needs are then
+    // selected in registers.  (Loading only w_n / w_m would put the chunk offset, and with it the bank group,
+    // at the mercy of the local node numbers.)
+    double wv[4][3];
+    unpack_w<false>(reinterpret_cast<double2 const*>(rp), wv);
     // row node = the node of this block row in the primal operator; roles swap for the transpose
     int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
-    double wr[3], wc[3], rc[3];
-    {  // node block of the record: {w[3], r[3]}, 48 B
-      double2 const* qr = reinterpret_cast<double2 const*>(rp + 6 * nr);
-      double2 const* qc = reinterpret_cast<double2 const*>(rp + 6 * nc);
-      double2 const a0 = qr[0], a1 = qr[1];
-      double2 const b0 = qc[0], b1 = qc[1], b2 = qc[2];
-      wr[0] = a0.x; wr[1] = a0.y; wr[2] = a1.x;
-      wc[0] = b0.x; wc[1] = b0.y; wc[2] = b1.x;
-      rc[0] = b1.y; rc[1] = b2.x; rc[2] = b2.y;
+    double wr[3], wc[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double const a01 = (nr & 1) ? wv[1][k] : wv[0][k], a23 = (nr & 1) ? wv[3][k] : wv[2][k];
+      wr[k] = (nr & 2) ? a23 : a01;
+      double const b01 = (nc & 1) ? wv[1][k] : wv[0][k], b23 = (nc & 1) ? wv[3][k] : wv[2][k];
+      wc[k] = (nc & 2) ? b23 : b01;
     }
     RowNode<double> rown;
     ColNode<double> coln;
     row_node(c, wr, rown);
-    column_node(c, wc, rc, coln);
+    column_node_w(c, wc, coln);
     double blk[16];
     jacobian_block(c, rown, coln, blk);
 #pragma unroll

@@ -11,6 +11,9 @@
 //   gx::Primal       goal::Primal       compute_resid / compute_jacob       src/goal_primal.cpp:75-109
 //   gx::NestedAdjoint (localize part)   compute_adjoint / localize          src/goal_nested_adjoint.cpp:163-234
 //   gx::compute_error / sum_contribs    goal::compute_error / sum_contribs  src/goal_error.cpp:7-56
+//   gx::Functional   goal::Functional + QoI evaluators                      src/goal_functional.cpp:30-70, goal_qoi.cpp
+//   gx::set_tbcs / set_ibcs / set_*_dbcs                                    src/goal_tbcs.cpp, goal_ibcs.cpp, goal_dbcs.cpp
+//   gx::add_soln, gx::get_iso_target_size                                   src/goal_disc.cpp:398-422, goal_size_field.cpp
 //
 // Errors: the reference calls goal::fail(), which prints and abort()s (src/goal_control.cpp:91-99).
 // Here every non-zero gx_status is turned into gx::fail(), which throws std::runtime_error by default
@@ -190,6 +193,66 @@ inline double compute_error(Disc* nested, std::vector<double> const& u_error, st
                        e_nested.data(), parent.empty() ? nullptr : e_base.data(), &bound))
     fail(gx_last_error(nested->ctx));
   return bound;
+}
+
+// Functional (src/goal_functional.cpp:30-70) over Mechanics::build_functional's evaluators
+// (src/goal_mechanics.cpp:149-167).  type is the yaml string; compute() is the ST chain (value only),
+// compute_adjoint_rhs() the FADT chain that also fills dMdu (QoI<FADT>::scatter, src/goal_qoi.cpp:63-76).
+class Functional {
+ public:
+  Functional(Disc* d, std::string const& type, int elem_set = 0, double rho = 0.0, LO point_node = -1, int point_idx = 0)
+      : disc(d) {
+    q = gx_qoi{};
+    if (type == "avg disp") q.type = GX_QOI_AVG_DISP;
+    else if (type == "avg disp subdomain") q.type = GX_QOI_AVG_DISP_SUBDOMAIN;
+    else if (type == "avg vm") q.type = GX_QOI_AVG_VM;
+    else if (type == "max vm") q.type = GX_QOI_KS_VM;
+    else if (type == "point wise") q.type = GX_QOI_POINT_WISE;
+    else fail("unknown functional type: " + type);  // src/goal_mechanics.cpp:165
+    q.elem_set = elem_set; q.rho = rho; q.point_node = point_node; q.point_idx = point_idx;
+  }
+  void compute() {
+    q.ks_scale = 0.0;
+    if (gx_functional(disc->ctx, &q, &value, nullptr)) fail(gx_last_error(disc->ctx));
+  }
+  void compute_adjoint_rhs(std::vector<double>& dMdu) {
+    dMdu.resize(4 * (size_t)disc->get_num_nodes());
+    q.ks_scale = 0.0;
+    if (gx_functional(disc->ctx, &q, &value, dMdu.data())) fail(gx_last_error(disc->ctx));
+  }
+  double get_value() const { return value; }
+
+ private:
+  Disc* disc;
+  gx_qoi q;
+  double value = 0.0;
+};
+
+// Boundary terms on the device-resident result of the last compute call, in the reference's order
+// (src/goal_primal.cpp:84-88, 102-106): set_tbcs, set_ibcs, [gather], set_resid_dbcs / set_jac_dbcs.
+inline void set_tbcs(Disc* d, std::vector<LO> const& side_nodes, std::vector<double> const& traction) {
+  if (traction.size() != side_nodes.size()) fail("set_tbcs: one traction vector per side expected");
+  if (gx_apply_tbcs(d->ctx, (LO)(side_nodes.size() / 3), side_nodes.data(), traction.data())) fail(gx_last_error(d->ctx));
+}
+inline void set_ibcs(Disc* d, std::vector<LO> const& side_nodes, double scale, double const center[3]) {
+  if (gx_apply_ibcs(d->ctx, (LO)(side_nodes.size() / 3), side_nodes.data(), scale, center)) fail(gx_last_error(d->ctx));
+}
+inline void set_resid_dbcs(Disc* d, std::vector<LO> const& rows, std::vector<double> const& g) {
+  if (gx_apply_dbcs(d->ctx, (LO)rows.size(), rows.data(), g.data(), 0)) fail(gx_last_error(d->ctx));
+}
+inline void set_jac_dbcs(Disc* d, std::vector<LO> const& rows, std::vector<double> const& g) {
+  if (gx_apply_dbcs(d->ctx, (LO)rows.size(), rows.data(), g.data(), 1)) fail(gx_last_error(d->ctx));
+}
+// Disc::add_soln (src/goal_disc.cpp:398-422)
+inline void add_soln(Disc* d, std::vector<double> const& du) {
+  if (du.size() != 4 * (size_t)d->get_num_nodes()) fail("add_soln: bad vector size");
+  if (gx_add_solution(d->ctx, du.data()) || gx_sync_solution(d->ctx)) fail(gx_last_error(d->ctx));
+}
+// get_iso_target_size (src/goal_size_field.cpp:140-150), single part
+inline void get_iso_target_size(Disc* d, std::vector<double> const& e_elem, int target, std::vector<double>& vtx_size) {
+  vtx_size.resize(d->get_num_nodes());
+  double G = 0.0;
+  if (gx_size_field(d->ctx, e_elem.data(), target, 1, &G, vtx_size.data(), nullptr)) fail(gx_last_error(d->ctx));
 }
 
 }  // namespace gx

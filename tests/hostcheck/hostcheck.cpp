@@ -15,17 +15,18 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
   bool wf = false;
   double Cp[6];
   gx::cp_inverse(Fp_old, Cp);
-  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Cp, eqps_old, save != 0, sigma, *eqps, c)
-                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Cp, eqps_old, save != 0, sigma, *eqps, c);
+  int rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, p, m, Cp, eqps_old, (save & 1) != 0, sigma, *eqps, c)
+                      : gx::element_core<gx::MODEL_J2>(X, U, p, m, Cp, eqps_old, (save & 1) != 0, sigma, *eqps, c);
   if (rc) return rc;
-  if (save && model == 1 && c.plastic) { gx::plastic_update(c.dN, Fp_old, Fp); wf = true; }
+  if ((save & 1) && model == 1 && c.plastic) { gx::plastic_update(c.dN, Fp_old, Fp); wf = true; }
   *wrote_Fp = wf; *plastic = c.plastic;
   double ru[12], rp[4];
   gx::element_residual(c, ru, rp);
   for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
   for (int mm = 0; mm < 4; ++mm) {
     gx::ColNode<double> cn;
-    gx::column_node(c, c.w[mm], c.r[mm], cn);
+    if (save & 2) gx::column_node_w(c, c.w[mm], cn);  // the form the tangent records use: r_m rebuilt from w_m
+    else gx::column_node(c, c.w[mm], c.r[mm], cn);
     for (int n = 0; n < 4; ++n) {
       double blk[16];
       gx::RowNode<double> rn;
