@@ -900,45 +900,13 @@ constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stri
                                         // group of a record's chunk k is (slot + k) mod 8
 GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * 20) * sizeof(double); }
 
+// One work item: up to PATCH_ITEM_LEN contributions to one 4x4 block (and, for diagonal items, to the node's residual
+// entries), rebuilt from the records staged at srec and accumulated in registers.
 template <bool TRANSPOSE>
-__global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
-                                                                        uint32_t const* __restrict__ sched) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t mbar;
-  double* srec = reinterpret_cast<double*>(smem_raw);
-  int const tid = threadIdx.x;
-  uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
-  int const n_recs = (int)__ldg(w);
-  int const my_elem = (int)__ldg(w + 4 + tid);
-  uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
-  uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
-  // Record staging: thread r issues one bulk asynchronous copy (368 B, global -> shared) for record r; the copies
-  // report their bytes to an mbarrier that the whole block then waits on.
-  uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
-  if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  __syncthreads();
-  if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
-  if (tid < n_recs) {
-    uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + (uint32_t)(tid * (PATCH_REC_LD * 8));
-    double const* src = rec + (int64_t)ELEM_REC * my_elem;
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(ELEM_REC * 8), "r"(mb)
-                 : "memory");
-  }
-  {
-    uint32_t done;
-    do {
-      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
-    } while (!done);
-  }
-  int const kind = (int)(ot.z >> 30);
-  bool const diag = (ot.w & 0x80000000u) != 0;
-  double acc[16], r4[4] = {0.0, 0.0, 0.0, 0.0};
+__device__ __forceinline__ void patch_item(double const* srec, uint4 const it, bool const diag, double acc[16], double r4[4]) {
 #pragma unroll
   for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+  r4[0] = r4[1] = r4[2] = r4[3] = 0.0;
   uint64_t elo = (uint64_t)it.x | ((uint64_t)it.y << 32), ehi = (uint64_t)it.z | ((uint64_t)it.w << 32);
 #pragma unroll 1
   for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
@@ -984,6 +952,46 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
       r4[0] += t4[0]; r4[1] += t4[1]; r4[2] += t4[2]; r4[3] += t4[3];
     }
   }
+}
+
+template <bool TRANSPOSE>
+__global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+                                                                        uint32_t const* __restrict__ sched) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t mbar;
+  double* srec = reinterpret_cast<double*>(smem_raw);
+  int const tid = threadIdx.x;
+  uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
+  int const n_recs = (int)__ldg(w);
+  int const my_elem = (int)__ldg(w + 4 + tid);
+  uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
+  uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
+  // Record staging: thread r issues one bulk asynchronous copy (272 B, global -> shared) for record r; the copies
+  // report their bytes to an mbarrier that the whole block then waits on.
+  uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
+  if (tid < n_recs) {
+    uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + (uint32_t)(tid * (PATCH_REC_LD * 8));
+    double const* src = rec + (int64_t)ELEM_REC * my_elem;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(ELEM_REC * 8), "r"(mb)
+                 : "memory");
+  }
+  {
+    uint32_t done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+    } while (!done);
+  }
+  int const kind = (int)(ot.z >> 30);
+  bool const diag = (ot.w & 0x80000000u) != 0;
+  double acc[16], r4[4];
+  patch_item<TRANSPOSE>(srec, it, diag, acc, r4);
   // Finish.  Items without secondaries write their block and leave; only the few items that exchange partial sums
   // (diagonal blocks, edges of high valence: the longest items, i.e. the first warp) meet at the barrier.
   int const part = (int)((ot.z >> 16) & 0xffu);
@@ -1020,6 +1028,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
     write_out();
   }
 }
+
 
 // ---------------------------------------------------------------------------
 // Residual and error-localisation passes, gather form (default): no colouring, no zeroing, no atomics.

@@ -9,6 +9,8 @@ cells = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 model = sys.argv[2] if len(sys.argv) > 2 else "J2"
 t0 = time.time(); co, cn = kuhn_cube(cells); f = fields(co, len(cn)); t1 = time.time()
 a = goal_b200.Assembler(co, cn, model, [MATERIAL]); t2 = time.time()
+for kv in filter(None, os.environ.get("GX_OPTS", "").split(",")):  # library options k=v[,k=v]
+    k, v = kv.split("="); a.set_option(k, int(v))
 a.set_solution(f["u"], f["p"])
 if model == "J2":
     a.set_state("Fp_old", f["Fp_old"]); a.set_state("eqps_old", f["eqps_old"])
