@@ -470,10 +470,10 @@ template <class S> GX_HD void node_r(Core<S> const& c, S const w[3], S sw[3], S 
   sym_mv(c.s, w, sw);
   for (int k = 0; k < 3; ++k) r[k] = c.rc1 * sw[k] + c.tb3 * w[k];
 }
-// column_node for callers that hold w_m only (sw = s w_m is handed in when the caller has it already)
-template <class S> GX_HD void column_node_sw(Core<S> const& c, S const wm[3], S const sw[3], ColNode<S>& cn) {
-  S rm[3], sr[3];
-  for (int k = 0; k < 3; ++k) rm[k] = c.rc1 * sw[k] + c.tb3 * wm[k];
+// column_node for callers that hold w_m only
+template <class S> GX_HD void column_node_w(Core<S> const& c, S const wm[3], ColNode<S>& cn) {
+  S sw[3], rm[3], sr[3];
+  node_r(c, wm, sw, rm);
   sym_mv(c.s, rm, sr);
   S const m23 = S(-2.0 / 3.0);
   for (int k = 0; k < 3; ++k) {
@@ -484,11 +484,6 @@ template <class S> GX_HD void column_node_sw(Core<S> const& c, S const wm[3], S 
     cn.g[k] = (c.gNs * sr[k] + c.vgr * rm[k]) + c.gwv * wm[k];
   }
   cn.tqw = c.tjv * dot3(c.q, wm);
-}
-template <class S> GX_HD void column_node_w(Core<S> const& c, S const wm[3], ColNode<S>& cn) {
-  S sw[3];
-  sym_mv(c.s, wm, sw);
-  column_node_sw(c, wm, sw, cn);
 }
 
 // Row-node quantities shared by the four column nodes.

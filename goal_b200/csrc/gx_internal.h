@@ -193,16 +193,15 @@ bool build_patch_schedule(gx_ctx* c);
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
 #ifndef GX_PATCH_THREADS
 #define GX_PATCH_THREADS 128
-#define GX_PATCH_RECS 200
-#define GX_PATCH_MINB 3
+#define GX_PATCH_RECS 120
+#define GX_PATCH_MINB 4
 #endif
 constexpr int PATCH_THREADS = GX_PATCH_THREADS;  // work items per patch, one per thread
 constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (368 B each)
 constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_PARTS = 32;     // secondary items (partial sums handed to a primary) per patch
-constexpr int PATCH_PART_LD = 36;    // doubles per partial sum: 32 block entries (two blocks of a paired item) + 4 residual entries
-constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS + 4 * PATCH_THREADS;  // uint32 words per patch
+constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS;  // uint32 words per patch
 // gx_comm.cu
 void comm_destroy(gx_ctx*);
 int comm_setup_lists(gx_ctx*, const gx_desc*);

@@ -898,7 +898,7 @@ __global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid
 // ---------------------------------------------------------------------------
 constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stride: 272 B = 17 x 16 B (odd), so the bank
                                         // group of a record's chunk k is (slot + k) mod 8
-GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * PATCH_PART_LD) * sizeof(double); }
+GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * 20) * sizeof(double); }
 
 // One work item: up to PATCH_ITEM_LEN contributions to one 4x4 block (and, for diagonal items, to the node's residual
 // entries), rebuilt from the records staged at srec and accumulated in registers.
@@ -954,68 +954,6 @@ __device__ __forceinline__ void patch_item(double const* srec, uint4 const it, b
   }
 }
 
-// A paired work item: block (a,b) and its mirror (b,a) from the same contributions.  K[(n,.),(m,.)] goes to acc[0..15]
-// (block (a,b)), K[(m,.),(n,.)] to acc[16..31] (block (b,a)); for the transposed operator the two swap and transpose.
-// What the two blocks share is done once: the 17 record loads, the node selection, s w_n and s w_m, q . w, w_n . w_m.
-template <bool TRANSPOSE>
-__device__ __forceinline__ void patch_item_pair(double const* srec, uint4 const it, double acc[32]) {
-#pragma unroll
-  for (int k = 0; k < 32; ++k) acc[k] = 0.0;
-  uint64_t elo = (uint64_t)it.x | ((uint64_t)it.y << 32), ehi = (uint64_t)it.z | ((uint64_t)it.w << 32);
-#pragma unroll 1
-  for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
-    uint32_t const ent = (uint32_t)elo & 0xffffu;
-    elo = (elo >> 16) | (ehi << 48); ehi >>= 16;
-    if (!(ent & 0x8000u)) {
-      if ((elo | ehi) == 0) break;
-      continue;
-    }
-    int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
-    double const* rp = srec + slot * PATCH_REC_LD;
-    Core<double> c;  // only the tangent fields are filled
-    unpack_tangent<false>(reinterpret_cast<double2 const*>(rp), c);
-    double wv[4][3];
-    unpack_w<false>(reinterpret_cast<double2 const*>(rp), wv);
-    double wn[3], wm[3];
-#pragma unroll
-    for (int q = 0; q < 3; ++q) {
-      double const a01 = (n & 1) ? wv[1][q] : wv[0][q], a23 = (n & 1) ? wv[3][q] : wv[2][q];
-      wn[q] = (n & 2) ? a23 : a01;
-      double const b01 = (m & 1) ? wv[1][q] : wv[0][q], b23 = (m & 1) ? wv[3][q] : wv[2][q];
-      wm[q] = (m & 2) ? b23 : b01;
-    }
-    double blk[16];
-    {  // K[(n,.),(m,.)]
-      RowNode<double> rn;
-      ColNode<double> cm;
-      row_node(c, wn, rn);
-      column_node_w(c, wm, cm);
-      jacobian_block(c, rn, cm, blk);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!TRANSPOSE) acc[4 * i + j] += blk[4 * i + j];
-          else acc[16 + 4 * j + i] += blk[4 * i + j];
-        }
-    }
-    {  // K[(m,.),(n,.)]
-      RowNode<double> rm;
-      ColNode<double> cn;
-      row_node(c, wm, rm);
-      column_node_w(c, wn, cn);
-      jacobian_block(c, rm, cn, blk);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (!TRANSPOSE) acc[16 + 4 * i + j] += blk[4 * i + j];
-          else acc[4 * j + i] += blk[4 * i + j];
-        }
-    }
-  }
-}
-
 template <bool TRANSPOSE>
 __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
                                                                         uint32_t const* __restrict__ sched) {
@@ -1026,7 +964,6 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
   int const n_recs = (int)__ldg(w);
   int const my_elem = (int)__ldg(w + 4 + tid);
-  int const my_elem2 = PATCH_RECS > PATCH_THREADS ? (int)__ldg(w + 4 + min(tid + PATCH_THREADS, PATCH_RECS - 1)) : 0;
   uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
   uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
   // Record staging: thread r issues one bulk asynchronous copy (272 B, global -> shared) for record r; the copies
@@ -1038,17 +975,12 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   }
   __syncthreads();
   if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
-  static_assert(PATCH_RECS <= 2 * PATCH_THREADS, "a thread stages at most two records");
-#pragma unroll
-  for (int h = 0; h < (PATCH_RECS > PATCH_THREADS ? 2 : 1); ++h) {
-    int const r = tid + h * PATCH_THREADS;
-    if (r < n_recs) {
-      uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + (uint32_t)(r * (PATCH_REC_LD * 8));
-      double const* src = rec + (int64_t)ELEM_REC * (h ? my_elem2 : my_elem);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                   "r"(ELEM_REC * 8), "r"(mb)
-                   : "memory");
-    }
+  if (tid < n_recs) {
+    uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + (uint32_t)(tid * (PATCH_REC_LD * 8));
+    double const* src = rec + (int64_t)ELEM_REC * my_elem;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(ELEM_REC * 8), "r"(mb)
+                 : "memory");
   }
   {
     uint32_t done;
@@ -1058,56 +990,39 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   }
   int const kind = (int)(ot.z >> 30);
   bool const diag = (ot.w & 0x80000000u) != 0;
-  uint4 const ot2 = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 8 * PATCH_THREADS) + tid);
-  bool const paired = (ot2.z & 0x80000000u) != 0;
-  double acc[32], r4[4] = {0.0, 0.0, 0.0, 0.0};
-  if (paired) patch_item_pair<TRANSPOSE>(srec, it, acc);
-  else patch_item<TRANSPOSE>(srec, it, diag, acc, r4);
+  double acc[16], r4[4];
+  patch_item<TRANSPOSE>(srec, it, diag, acc, r4);
   // Finish.  Items without secondaries write their block and leave; only the few items that exchange partial sums
   // (diagonal blocks, edges of high valence: the longest items, i.e. the first warp) meet at the barrier.
   int const part = (int)((ot.z >> 16) & 0xffu);
   int const nsec = (int)((ot.z >> 24) & 0x3fu);
-  double* spart = srec + (size_t)PATCH_RECS * PATCH_REC_LD;  // [PATCH_PARTS][PATCH_PART_LD]
+  double* spart = srec + (size_t)PATCH_RECS * PATCH_REC_LD;  // [PATCH_PARTS][20]
   auto write_out = [&]() {
     int64_t const voff = (int64_t)(((uint64_t)ot.y << 32) | (uint64_t)ot.x);
     int const rl = (int)(ot.z & 0xffffu);
     double* out = P.values + voff;
 #pragma unroll
     for (int i = 0; i < 4; ++i) stg256(out + (int64_t)i * rl, acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);  // one 32 B sector each
-    if (paired) {
-      double* out2 = P.values + (int64_t)(((uint64_t)ot2.y << 32) | (uint64_t)ot2.x);
-      int const rl2 = (int)(ot2.z & 0xffffu);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) stg256(out2 + (int64_t)i * rl2, acc[16 + 4 * i], acc[16 + 4 * i + 1], acc[16 + 4 * i + 2], acc[16 + 4 * i + 3]);
-    }
     if (diag) stg256(P.R + 4 * (int64_t)(ot.w & 0x7fffffffu), r4[0], r4[1], r4[2], r4[3]);
   };
   if (kind == 0) return;
   if (kind == 1 && nsec == 0) { write_out(); return; }
   if (kind == 2) {
-    double2* d = reinterpret_cast<double2*>(spart + PATCH_PART_LD * part);
+    double2* d = reinterpret_cast<double2*>(spart + 20 * part);
 #pragma unroll
     for (int k = 0; k < 8; ++k) d[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
-    if (paired) {
-#pragma unroll
-      for (int k = 8; k < 16; ++k) d[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
-    }
-    d[16] = make_double2(r4[0], r4[1]);
-    d[17] = make_double2(r4[2], r4[3]);
+    d[8] = make_double2(r4[0], r4[1]);
+    d[9] = make_double2(r4[2], r4[3]);
   }
   __syncthreads();  // the threads that are still here
   if (kind == 1) {
     for (int s2 = 0; s2 < nsec; ++s2) {
-      double2 const* d = reinterpret_cast<double2 const*>(spart + PATCH_PART_LD * (part + s2));
+      double2 const* d = reinterpret_cast<double2 const*>(spart + 20 * (part + s2));
 #pragma unroll
       for (int k = 0; k < 8; ++k) { double2 const v = d[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
-      if (paired) {
-#pragma unroll
-        for (int k = 8; k < 16; ++k) { double2 const v = d[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
-      }
       if (diag) {
-        double2 v = d[16]; r4[0] += v.x; r4[1] += v.y;
-        v = d[17]; r4[2] += v.x; r4[3] += v.y;
+        double2 v = d[8]; r4[0] += v.x; r4[1] += v.y;
+        v = d[9]; r4[2] += v.x; r4[3] += v.y;
       }
     }
     write_out();

@@ -279,12 +279,6 @@ void build_block_lists(gx_ctx* c) {
 //                                                   z = row stride | part slot << 16 | n secondaries << 24 | kind << 30
 //                                                   w = node id | diagonal << 31
 //            kind: 0 idle thread, 1 primary, 2 secondary
-//   then     outs2[PATCH_THREADS][4]                paired items: x,y = value offset of the mirror block (b,a), z = its row stride | 1 << 31
-// Pairing: the contributions to block (a,b) and to its mirror (b,a) come from the same elements with the local node
-// roles swapped, and share everything that is per element or per node -- so the two blocks are one PAIRED item,
-// owned by the patch of whichever of a, b comes first in the visiting order (all elements of the edge are incident to
-// that node, hence staged there).  The owner writes block (b,a) into b's rows although b may live in another patch;
-// every block of the operator still has exactly one writer.
 bool build_patch_schedule(gx_ctx* c) {
   using namespace gx;
   if (!c->block_lists_built) build_block_lists(c);
@@ -297,17 +291,9 @@ bool build_patch_schedule(gx_ctx* c) {
   bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
   std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0), st_runs(nch, 0), st_recs(nch, 0);
   bool ok = true;
-  std::vector<int32_t> pos(nn);  // position of a node in the visiting order
-  for (int s0 = 0; s0 < nn; ++s0) pos[c->node_order[s0]] = s0;
-  bool const pairing = getenv("GX_SCHED_NOPAIR") == nullptr;
-  // column node of block t = (row a, position j) when it is a local block with a mirror (b,a); -1 for phantom blocks
-  auto col_node = [&](int a, int64_t t) -> int {
-    int64_t const j = t - nx[a];
-    return j < c->nrow[a + 1] - c->nrow[a] ? c->ncol[c->nrow[a] + j] : -1;
-  };
 #pragma omp parallel for schedule(dynamic, 1)
   for (int ch = 0; ch < nch; ++ch) {
-    struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; int64_t voff; uint32_t rl, node; int kind, nsec, part; bool diag; bool paired; int64_t voff2; uint32_t rl2; };
+    struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; int64_t voff; uint32_t rl, node; int kind, nsec, part; bool diag; };
     std::vector<Item> items;
     std::vector<int32_t> recs;
     int32_t hkey[512]; int16_t hval[512];
@@ -328,9 +314,7 @@ bool build_patch_schedule(gx_ctx* c) {
       // longest items first: the lanes of a warp then run the same number of contributions
       std::vector<int> ord(items.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
-      // single-block items (diagonal blocks) first, then the paired ones, empty items last: warps stay homogeneous
-      auto cls = [&](int x) { return items[x].n == 0 ? 2 : items[x].paired ? 1 : 0; };
-      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return cls(x) != cls(y) ? cls(x) < cls(y) : items[x].n > items[y].n; });
+      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return items[x].n > items[y].n; });
       // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
       // record is its slot modulo 8.  Bank groups are given to the records by a greedy colouring (records feeding the
       // same item get different groups where possible); then, within every group of 8 lanes, each item's
@@ -363,8 +347,7 @@ bool build_patch_schedule(gx_ctx* c) {
         // Rounds available to this group of 8 lanes: its warp runs as many rounds as its longest item, so an item
         // may sit out a round (an empty entry) as long as it still finishes -- which lets the schedule dodge
         // conflicts that a packed order cannot.
-        int R = 0;
-        for (size_t i = (g0 / 32) * 32; i < std::min(ord.size(), (g0 / 32) * 32 + 32); ++i) R = std::max(R, items[ord[i]].n);
+        int const R = items[ord[(g0 / 32) * 32]].n;
         bool used[8][PATCH_ITEM_LEN] = {};
         uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
         int remaining[8] = {};
@@ -479,12 +462,6 @@ bool build_patch_schedule(gx_ctx* c) {
         wo[4 * t + 1] = (uint32_t)((uint64_t)it.voff >> 32);
         wo[4 * t + 2] = it.rl | ((uint32_t)it.part << 16) | ((uint32_t)it.nsec << 24) | ((uint32_t)it.kind << 30);
         wo[4 * t + 3] = it.node | (it.diag ? 0x80000000u : 0u);
-        if (it.paired) {
-          uint32_t* w2 = wo + 4 * PATCH_THREADS;
-          w2[4 * t] = (uint32_t)((uint64_t)it.voff2 & 0xffffffffu);
-          w2[4 * t + 1] = (uint32_t)((uint64_t)it.voff2 >> 32);
-          w2[4 * t + 2] = it.rl2 | 0x80000000u;
-        }
       }
       items.clear(); recs.clear(); hclear(); nparts = 0;
     };
@@ -499,8 +476,6 @@ bool build_patch_schedule(gx_ctx* c) {
       // its items (slots filled in once the node is accepted)
       int nit = 0, nsecs = 0;
       for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
-        int const b = col_node(a, t);
-        if (pairing && b >= 0 && b != a && pos[b] < pos[a]) continue;  // written by b's patch as the mirror of (b,a)
         int const cnt = (int)(c->bc_off[t + 1] - c->bc_off[t]);
         int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
         nit += parts; nsecs += parts - 1;
@@ -517,18 +492,6 @@ bool build_patch_schedule(gx_ctx* c) {
         int const cnt = (int)(c1 - c0);
         int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
         bool const diag = (c->blk_row[t] & 0x80000000u) != 0;
-        int const b = col_node(a, t);
-        bool const paired = pairing && b >= 0 && b != a;
-        if (paired && pos[b] < pos[a]) continue;
-        int64_t voff2 = 0;
-        uint32_t rl2 = 0;
-        if (paired) {  // the mirror block (b,a): position of a in b's sorted block row
-          int32_t const* r0 = c->ncol.data() + c->nrow[b];
-          int32_t const* r1 = c->ncol.data() + c->nrow[b + 1];
-          int64_t const j2 = std::lower_bound(r0, r1, (int32_t)a) - r0;
-          voff2 = 16 * nx[b] + 4 * j2;
-          rl2 = (uint32_t)(4 * (nx[b + 1] - nx[b]));
-        }
         for (int pi = 0; pi < parts; ++pi) {
           Item it{};
           it.n = std::min(PATCH_ITEM_LEN, cnt - pi * PATCH_ITEM_LEN);
@@ -539,7 +502,6 @@ bool build_patch_schedule(gx_ctx* c) {
           }
           it.voff = 16 * nx[a] + 4 * (t - nx[a]);
           it.rl = (uint32_t)rl; it.node = (uint32_t)a; it.diag = diag;
-          it.paired = paired; it.voff2 = voff2; it.rl2 = rl2;
           if (pi == 0) { it.kind = 1; it.nsec = parts - 1; it.part = nparts; }
           else { it.kind = 2; it.nsec = 0; it.part = nparts + pi - 1; }
           items.push_back(it);
