@@ -32,7 +32,7 @@ SYMBOLS = [
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
     "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs", "gx_add_solution", "gx_get_solution", "gx_sync_solution",
-    "gx_pack_solution", "gx_unpack_solution", "gx_size_field",
+    "gx_pack_solution", "gx_unpack_solution", "gx_size_field", "gx_patch_schedule",
 ]
 
 # Mechanics::build_functional types by their yaml name (src/goal_mechanics.cpp:149-167)
@@ -117,6 +117,7 @@ def load_library():
     L.gx_pack_solution.argtypes = [vp, C.c_int, C.POINTER(vp), lp]
     L.gx_unpack_solution.argtypes = [vp, C.c_int, vp]
     L.gx_size_field.argtypes = [vp, dp, C.c_int32, C.c_int32, dp, dp, dp]
+    L.gx_patch_schedule.argtypes = [vp, C.POINTER(C.POINTER(C.c_uint32)), ip]
     L.gx_functional.argtypes = [vp, C.POINTER(GxQoi), dp, vp]
     L.gx_ks_vm_max.argtypes = [vp, dp]
     L.gx_ks_vm_scale.argtypes = [vp, C.c_double, C.c_double, dp]
@@ -366,6 +367,13 @@ class Assembler:
         c = np.zeros(self.nn) if counts else None
         self._ck(self.L.gx_size_field(self.h, _dp(eta), target, p_order, C.byref(g), _dp(v), None if c is None else _dp(c)))
         return (v, g.value, c) if counts else (v, g.value)
+
+    def patch_schedule(self):
+        """(words [n_patches, words_per_patch] uint32, record slots per patch, threads per patch) of the patch gather."""
+        ptr, dims = C.POINTER(C.c_uint32)(), (C.c_int32 * 4)()
+        self._ck(self.L.gx_patch_schedule(self.h, C.byref(ptr), dims))
+        w = np.ctypeslib.as_array(ptr, (dims[0] * dims[1],)).reshape(dims[0], dims[1]).copy()
+        return w, dims[2], dims[3]
 
     def apply_tbcs(self, sides, traction):
         """set_tbcs on the device-resident ghost R (src/goal_tbcs.cpp:29-71); traction: [n_sides, 3] or one 3-vector."""

@@ -1154,6 +1154,20 @@ int gx_last_timing(gx_ctx* ctx, double t[4]) {
   return GX_OK;
 }
 
+// Introspection: the patch schedule as the device reads it (built on demand; host-only contexts keep it for the
+// CPU tests of the schedule's invariants).  dims = {n_patches, words per patch, records per patch, threads per patch}
+int gx_patch_schedule(gx_ctx* ctx, const uint32_t** words, int32_t dims[4]) {
+  if (!ctx || !words || !dims) return GX_ERR_ARG;
+  if (ctx->patch_sched.empty()) {
+    ctx->patch_state = 0;
+    if (!build_patch_schedule(ctx)) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
+    if (ctx->device >= 0) ctx->patch_state = 0;  // the device copy is (re)built by the next Jacobian pass
+  }
+  *words = ctx->patch_sched.data();
+  dims[0] = ctx->n_patches; dims[1] = PATCH_WORDS; dims[2] = PATCH_RECS; dims[3] = PATCH_THREADS;
+  return GX_OK;
+}
+
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return GX_ERR_ARG;
   std::string k(key);

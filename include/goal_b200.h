@@ -248,6 +248,10 @@ void* gx_stream(gx_ctx* ctx);                   /* the cudaStream_t every kernel
  * t[0] zeroing, t[1] assembly kernels, t[2] interface exchange, t[3] kernel launches counted */
 int gx_last_timing(gx_ctx* ctx, double t[4]);
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value);
+/* The work list of the patch-gather Jacobian pass as the device reads it (layout: goal_b200/csrc/gx_setup.cpp,
+ * build_patch_schedule); dims = {patches, words per patch, record slots per patch, threads per patch}.  Valid until
+ * the next call on ctx.  Host-only contexts can build it too: the CPU tests check its invariants. */
+int gx_patch_schedule(gx_ctx* ctx, const uint32_t** words, int32_t dims[4]);
 
 #ifdef __cplusplus
 }
