@@ -423,7 +423,7 @@ static cudaError_t launch_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  node_gather_kernel<<<(ctx->nn + 255) / 256, 256, 0, ctx->stream>>>(P, rvec);
+  node_gather_kernel<<<(unsigned)((8 * (int64_t)ctx->nn + 255) / 256), 256, 0, ctx->stream>>>(P, rvec);
   ctx->launches++;
   return cudaGetLastError();
 }
@@ -1006,7 +1006,7 @@ int gx_functional(gx_ctx* ctx, gx_qoi* q, double* J, double* dMdu_out) {
   int const nb = std::min(1023, (ne + 255) / 256);
   sum_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, ev, ne);
   bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb);
-  if (dMdu_out) node_gather_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(P, rvec);
+  if (dMdu_out) node_gather_kernel<<<(unsigned)((8 * (int64_t)nn + 255) / 256), 256, 0, ctx->stream>>>(P, rvec);
   GX_CUDA(cudaGetLastError());
   int herr[2];
   GX_CUDA(cudaMemcpyAsync(herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));

@@ -1035,8 +1035,8 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
 //   elem_residual_kernel : one thread per element -> its 16 residual entries rvec[e][n][4] (128 B, one line),
 //                          state save as in stage A of the Jacobian pass.  ERROR selects the adjoint-weighted
 //                          residual of the error chain (goal_mechanics.cpp:169-218).
-//   node_gather_kernel   : one thread per node, sums rvec[e][n] over the node's incidences in ascending
-//                          element order and writes R[4a .. 4a+3] once.
+//   node_gather_kernel   : 8 lanes per node sum rvec[e][n] over the node's incidences (fixed order) and write
+//                          R[4a .. 4a+3] once.
 // ---------------------------------------------------------------------------
 template <int MODEL, bool SAVE, bool ERROR>
 __global__ void __launch_bounds__(128, 4) elem_residual_kernel(const __grid_constant__ KParams P, double* __restrict__ rvec, int ne) {
@@ -1109,19 +1109,29 @@ __global__ void __launch_bounds__(128, 4) elem_residual_kernel(const __grid_cons
 }
 
 __global__ void __launch_bounds__(256) node_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rvec) {
-  int const a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a >= P.nn) return;
-  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
+  // 8 lanes per node: lane j sums the incidences j, j + 8, j + 16, ... (ascending element order), then the 8 partial
+  // sums are added in a fixed xor tree -- the same order on every run, so the result is bit-reproducible.  Compared
+  // with one thread walking all (about 24) incidences this puts 8 times as many independent 32 B loads in flight.
+  int const t = blockIdx.x * blockDim.x + threadIdx.x;
+  int const a = t >> 3, sub = t & 7;
   double r0 = 0.0, r1 = 0.0, r2 = 0.0, r3 = 0.0;
-  for (uint32_t k = o0; k < o1; ++k) {
-    int const en = __ldg(P.adj + k).x;  // e*4 + n: rvec is [e][n][4]
-    double2 const* q = reinterpret_cast<double2 const*>(rvec + 4 * (int64_t)en);
-    double2 const v0 = __ldg(q), v1 = __ldg(q + 1);
-    r0 += v0.x; r1 += v0.y; r2 += v1.x; r3 += v1.y;
+  if (a < P.nn) {
+    uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
+    for (uint32_t k = o0 + sub; k < o1; k += 8) {
+      int const en = __ldg(P.adj + k).x;  // e*4 + n: rvec is [e][n][4]
+      double v0, v1, v2, v3;
+      ldg256(rvec + 4 * (int64_t)en, v0, v1, v2, v3);
+      r0 += v0; r1 += v1; r2 += v2; r3 += v3;
+    }
   }
-  double2* out = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
-  out[0] = make_double2(r0, r1);
-  out[1] = make_double2(r2, r3);
+#pragma unroll
+  for (int w = 4; w > 0; w >>= 1) {
+    r0 += __shfl_xor_sync(0xffffffffu, r0, w);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, w);
+    r2 += __shfl_xor_sync(0xffffffffu, r2, w);
+    r3 += __shfl_xor_sync(0xffffffffu, r3, w);
+  }
+  if (a < P.nn && sub == 0) stg256(P.R + 4 * (int64_t)a, r0, r1, r2, r3);
 }
 // ---------------------------------------------------------------------------
 // Functionals (Mechanics::build_functional, goal_mechanics.cpp:149-167; QoI<T> goal_qoi.cpp:21-82): one thread per
