@@ -940,12 +940,7 @@ __device__ __forceinline__ void patch_item(double const* srec, uint4 const it, b
     ColNode<double> coln;
     row_node(c, wr, rown);
     column_node_w(c, wc, coln);
-    double blk[16];
-    jacobian_block(c, rown, coln, blk);
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[4 * i + j] += TRANSPOSE ? blk[4 * j + i] : blk[4 * i + j];
+    jacobian_block_add<TRANSPOSE>(c, rown, coln, acc);
     if (diag) {  // n == m: the residual entries of the node
       double t4[4];
       element_residual_row(c, wr, t4);

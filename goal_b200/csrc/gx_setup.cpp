@@ -291,6 +291,13 @@ bool build_patch_schedule(gx_ctx* c) {
   bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
   std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0), st_runs(nch, 0), st_recs(nch, 0);
   bool ok = true;
+  // Blocks with many contributions (the diagonal block: one per incident element) are cut into items of at most
+  // `split` contributions, as evenly as possible.  A thread block lives as long as its longest item, so the cut
+  // follows the length of the ordinary items (an edge of a Kuhn mesh has 4 or 6 elements) rather than the capacity
+  // of an item: with 8 the first warp ran 8 rounds while the others had left after 5 or 6.
+  int split = 6;
+  if (char const* e = getenv("GX_SCHED_SPLIT")) split = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
+  auto n_parts = [&](int cnt) { return std::max(1, (cnt + split - 1) / split); };
 #pragma omp parallel for schedule(dynamic, 1)
   for (int ch = 0; ch < nch; ++ch) {
     struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; int64_t voff; uint32_t rl, node; int kind, nsec, part; bool diag; };
@@ -477,7 +484,7 @@ bool build_patch_schedule(gx_ctx* c) {
       int nit = 0, nsecs = 0;
       for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
         int const cnt = (int)(c->bc_off[t + 1] - c->bc_off[t]);
-        int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
+        int const parts = n_parts(cnt);
         nit += parts; nsecs += parts - 1;
       }
       if (nit > PATCH_THREADS || (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > PATCH_PARTS) { bad = true; break; }
@@ -490,20 +497,21 @@ bool build_patch_schedule(gx_ctx* c) {
       for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
         uint32_t const c0 = c->bc_off[t], c1 = c->bc_off[t + 1];
         int const cnt = (int)(c1 - c0);
-        int const parts = std::max(1, (cnt + PATCH_ITEM_LEN - 1) / PATCH_ITEM_LEN);
+        int const parts = n_parts(cnt);
         bool const diag = (c->blk_row[t] & 0x80000000u) != 0;
+        int first = 0;  // contributions in ascending element order, cut into `parts` runs of almost equal length
         for (int pi = 0; pi < parts; ++pi) {
           Item it{};
-          it.n = std::min(PATCH_ITEM_LEN, cnt - pi * PATCH_ITEM_LEN);
-          if (it.n < 0) it.n = 0;
+          it.n = cnt / parts + (pi < cnt % parts ? 1 : 0);
           for (int q = 0; q < it.n; ++q) {
-            int32_t const ent = c->bc[c0 + pi * PATCH_ITEM_LEN + q];
+            int32_t const ent = c->bc[c0 + first + q];
             it.ent[q] = (uint16_t)(hfind(ent >> 4) | ((ent & 15) << 8) | 0x8000);  // n*4+m -> bits 8..11
           }
           it.voff = 16 * nx[a] + 4 * (t - nx[a]);
           it.rl = (uint32_t)rl; it.node = (uint32_t)a; it.diag = diag;
           if (pi == 0) { it.kind = 1; it.nsec = parts - 1; it.part = nparts; }
           else { it.kind = 2; it.nsec = 0; it.part = nparts + pi - 1; }
+          first += it.n;
           items.push_back(it);
         }
         nparts += parts - 1;
