@@ -69,6 +69,41 @@ int main(int argc, char** argv) {
     double sE = 0;
     for (double v : adj.get_sol_info()->ghost.R) sE += v * v;
     std::printf("localize(z=1) |R|^2 %.17e\n", sE);
+    // ---- the steps either side of the assembly: functional + dMdu, traction term, solution update, size field
+    {
+      primal.set_solution(u, p);
+      primal.compute_resid();  // leaves the ghost R on the device and the sigma state "max vm" reads
+      gx::Functional avm(&disc, "avg vm"), ks(&disc, "max vm", 0, 0.05);
+      std::vector<double> dMdu;
+      avm.compute_adjoint_rhs(dMdu);
+      double sD = 0;
+      for (double v : dMdu) sD += v * v;
+      ks.compute();
+      std::printf("functional avg_vm %.17e |dMdu|^2 %.17e max_vm %.17e\n", avm.get_value(), sD, ks.get_value());
+      // traction (0.3, -1, 0.25) on the faces of the first element: three sides sharing nodes
+      std::vector<gx::LO> sides = {cn[1], cn[2], cn[3], cn[0], cn[3], cn[2], cn[0], cn[1], cn[3]};
+      std::vector<double> T;
+      for (int k = 0; k < 3; ++k) T.insert(T.end(), {0.3, -1.0, 0.25});
+      gx::set_tbcs(&disc, sides, T);
+      std::vector<double> R(4 * nn);
+      if (gx_fetch(disc.ctx, R.data(), nullptr)) gx::fail(gx_last_error(disc.ctx));
+      sR = 0;
+      for (double v : R) sR += v * v;
+      std::printf("resid+tbcs |R|^2 %.17e\n", sR);
+      std::vector<double> du(4 * nn);
+      for (size_t k = 0; k < du.size(); ++k) du[k] = 1e-4 * std::sin(0.37 * (double)k);
+      gx::add_soln(&disc, du);
+      primal.compute_resid();
+      sR = 0;
+      for (double v : primal.get_sol_info()->ghost.R) sR += v * v;
+      std::printf("resid(u+du) |R|^2 %.17e\n", sR);
+      std::vector<double> eta(disc.get_num_elems()), vs;
+      for (size_t e = 0; e < eta.size(); ++e) eta[e] = 1e-5 * (1.0 + (double)(e % 7));
+      gx::get_iso_target_size(&disc, eta, 2 * disc.get_num_elems(), vs);
+      double sV = 0;
+      for (double v : vs) sV += v;
+      std::printf("size field sum %.17e\n", sV);
+    }
     try {  // error behaviour: unknown state name -> fail()
       std::vector<double> bad;
       states.get("no_such_state", bad);

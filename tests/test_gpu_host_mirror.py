@@ -42,3 +42,25 @@ def test_cpp_host_mirror_matches_oracle(model):
     o.update_states()  # the self-test calls States::update() before localising
     Rz = o.residual(save=False)
     assert abs(grab(r"localize\(z=1\) \|R\|\^2 (\S+)") - (Rz * Rz).sum()) < 1e-11 * (Rz * Rz).sum()
+    # the steps either side of the assembly through the C++ mirror: Functional, set_tbcs, add_soln, get_iso_target_size
+    from oracle import driver
+    o.set_solution(u, p)
+    Rr = o.residual(save=True)
+    Jv, dM = o.functional("avg vm", with_dMdu=True)
+    assert abs(grab(r"functional avg_vm (\S+)") - Jv) < 1e-11 * abs(Jv)
+    assert abs(grab(r"\|dMdu\|\^2 (\S+)") - (dM * dM).sum()) < 1e-11 * (dM * dM).sum()
+    Jk = o.functional("max vm", rho=0.05)
+    assert abs(grab(r"max_vm (\S+)") - Jk) < 1e-11 * abs(Jk)
+    t = cn[0]
+    sides = [[t[1], t[2], t[3]], [t[0], t[3], t[2]], [t[0], t[1], t[3]]]
+    Rt = Rr.copy()
+    for row, v in driver._traction_rhs(co, sides, (0.3, -1.0, 0.25)):
+        Rt[row] += v
+    assert abs(grab(r"resid\+tbcs \|R\|\^2 (\S+)") - (Rt * Rt).sum()) < 1e-11 * (Rt * Rt).sum()
+    du = 1e-4 * np.sin(0.37 * np.arange(4 * o.nn)).reshape(-1, 4)
+    o.set_solution(u + du[:, :3], p + du[:, 3])
+    Ru = o.residual(save=False)
+    assert abs(grab(r"resid\(u\+du\) \|R\|\^2 (\S+)") - (Ru * Ru).sum()) < 1e-11 * (Ru * Ru).sum()
+    eta = 1e-5 * (1.0 + (np.arange(o.ne) % 7))
+    vs, _ = o.size_field(eta, 2 * o.ne)
+    assert abs(grab(r"size field sum (\S+)") - vs.sum()) < 1e-12 * vs.sum()
