@@ -173,7 +173,7 @@ __global__ void avg_disp_dMdu_kernel(double* dMdu, NodeRec const* nodes, int4 co
   dMdu[4 * (int64_t)a] = s; dMdu[4 * (int64_t)a + 1] = s; dMdu[4 * (int64_t)a + 2] = s; dMdu[4 * (int64_t)a + 3] = 0.0;
 }
 // set_resid_dbcs / set_jac_dbcs (src/goal_dbcs.cpp:39-99): one warp per Dirichlet row
-__global__ void apply_dbcs_kernel(double* R, double* values, NodeRec const* nodes, uint8_t const* diag_pos,
+__global__ void apply_dbcs_kernel(double* R, double* values, double* dMdu, NodeRec const* nodes, uint8_t const* diag_pos,
                                   int32_t const* rows, double const* g, int n, int with_jacobian) {
   int const w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n) return;
@@ -185,7 +185,10 @@ __global__ void apply_dbcs_kernel(double* R, double* values, NodeRec const* node
     int const d = 4 * diag_pos[a] + i;
     for (int c = lane; c < rl; c += 32) v[c] = c == d ? 1.0 : 0.0;
   }
-  if (lane == 0) R[row] = (i < 3 ? r.u[i] : r.p) - g[w];
+  if (lane == 0) {
+    R[row] = (i < 3 ? r.u[i] : r.p) - g[w];
+    if (with_jacobian && dMdu) dMdu[row] = 0.0;  // set_jac_dbcs also clears the functional derivative (goal_dbcs.cpp:86)
+  }
 }
 
 // Disc::add_soln (src/goal_disc.cpp:398-422): u += du, p += dp from a ghost-layout dof vector [4 nn]
@@ -1059,7 +1062,8 @@ int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, 
   double* d_g = ctx->d_stage + (n + 1) / 2 + 1;
   GX_CUDA(cudaMemcpyAsync(d_rows, rows, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
   GX_CUDA(cudaMemcpyAsync(d_g, g, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
-  apply_dbcs_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_R, ctx->d_values, ctx->d_nodes, ctx->d_diag_pos, d_rows, d_g, n, with_jacobian);
+  apply_dbcs_kernel<<<(n + 3) / 4, 128, 0, ctx->stream>>>(ctx->d_R, ctx->d_values, ctx->have_dMdu ? ctx->d_dMdu : nullptr, ctx->d_nodes,
+                                                         ctx->d_diag_pos, d_rows, d_g, n, with_jacobian);
   GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;

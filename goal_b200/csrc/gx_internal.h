@@ -197,7 +197,7 @@ bool build_patch_schedule(gx_ctx* c);
 #define GX_PATCH_MINB 4
 #endif
 constexpr int PATCH_THREADS = GX_PATCH_THREADS;  // work items per patch, one per thread
-constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (368 B each)
+constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (272 B each)
 constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_PARTS = 32;     // secondary items (partial sums handed to a primary) per patch

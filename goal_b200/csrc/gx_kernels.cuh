@@ -428,9 +428,9 @@ __global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_const
 //              w_n[3] x 4 nodes | s[6] | q[3] gwv A1v Jpv upc va tjv ppc vb gNs vgr rb rc1 tb3
 //            (r_n = F Cp^{-1} G_n is not stored: r_n = rc1 (s w_n) + tb3 w_n, element_math.cuh node_r)
 //   stage B  row_fold_kernel    : one warp per node, one lane per incidence.  Each lane reads its
-//            element's record (368 B, contiguous), builds the four blocks of the node's rows, and the
+//            element's record (272 B, contiguous), builds the four blocks of the node's rows, and the
 //            warp folds and writes the node's CRS rows once, exactly like row_owner_kernel.
-// Costs 368 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
+// Costs 272 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
 // element core (about 60 % of all instructions of the fused kernel).
 // ---------------------------------------------------------------------------
 constexpr int ELEM_REC = 34;  // doubles; 272 B = 17 x 16 B: an odd number of 16 B chunks, see patch_gather_kernel

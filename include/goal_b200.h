@@ -187,7 +187,8 @@ int gx_dmdu_dev(gx_ctx* ctx, double** dMdu_dev);
 int gx_fetch_dmdu(gx_ctx* ctx, double* dMdu_out);
 /* Dirichlet rows on the device-resident result of the last compute call (set_resid_dbcs / set_jac_dbcs,
  * src/goal_dbcs.cpp:39-99): for each listed ghost-local dof row (which must be owned by this rank):
- * R[row] = solution - g; with_jacobian != 0 additionally zeroes the CRS row and puts 1 on the diagonal.
+ * R[row] = solution - g; with_jacobian != 0 additionally zeroes the CRS row, puts 1 on the diagonal and clears
+ * dMdu[row] of the last gx_functional (src/goal_dbcs.cpp:86), if there is one on the device.
  * As in the reference this runs after the interface reduction and does not eliminate columns. */
 int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, int with_jacobian);
 /* Traction and inward-traction boundary terms on the device-resident ghost R of the last compute call, before the

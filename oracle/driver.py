@@ -117,10 +117,78 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
         out["newton"].append(it - 1)
         out["plastic"].append(asm.plastic_count())
         out["J"].append(asm.avg_disp())
+        try:  # the old states this step was solved with (what an error estimate at the end of the step evaluates with)
+            get = asm.get_state if hasattr(asm, "get_state") else asm.state
+            out["states_old"] = {k: np.array(get(k), copy=True) for k in ("Fp_old", "eqps_old")}
+        except Exception:
+            out["states_old"] = {}
         asm.update_states()
         t_old, t_now = t_now, t_now + dt
     out["u"], out["p"] = u, p
     return out
+
+
+def _set_state(asm, name, arr):
+    if hasattr(asm, "set_state"):
+        asm.set_state(name, arr)
+    else:
+        asm.state(name)[:] = arr
+
+
+def run_nested_cycle(asm, nested, u_base, p_base, states_base, dbcs, qoi="avg disp", qoi_kw=None, t_now=1.0, device_bcs=False):
+    """One adjoint error-estimation cycle on a nested mesh, the sequence of NestedAdjoint::run
+    (src/goal_nested_adjoint.cpp:236-247) around any assembler with the Oracle interface:
+
+      primal state on the nested mesh        P1 fields interpolated, element states inherited from the parent
+      compute_adjoint  (:163-180)            transposed Jacobian + dMdu (FADT chain, save=false), jac dbcs
+      solve            (:197-215)            dRdu^T z = dMdu; z_fine, z_coarse = set_coarse(z_fine), z_diff; e = -(R . z)
+      localize         (:217-234)            error chain weighted with z_diff / z_p-coarse, resid dbcs -> u_error, p_error
+      sum_contribs, compute_error, set_error (src/goal_error.cpp:7-56, goal_nested.cpp:395-412)
+
+    asm: assembler built on nested["coords"], nested["tets"].  dbcs: [(eq, node_ids on the nested mesh, g(t))].
+    device_bcs: Dirichlet rows through asm.apply_dbcs (gx_apply_dbcs) instead of on the host."""
+    from goal_b200.nested import prolong, set_coarse
+    nn = len(nested["coords"])
+    u, p = prolong(u_base, nested), prolong(p_base, nested)
+    asm.set_solution(u, p)
+    for name, arr in (states_base or {}).items():
+        _set_state(asm, name, np.ascontiguousarray(np.asarray(arr)[nested["parent"]]))
+    rows = np.array([4 * n + eq for eq, nodes, g in dbcs for n in nodes], dtype=np.int64)
+    gval = np.array([g(t_now) for eq, nodes, g in dbcs for n in nodes])
+    sol = np.concatenate([u, p[:, None]], 1).reshape(-1)
+    rowptr, colind = asm.rowptr, asm.colind
+    kw = dict(qoi_kw or {})
+    if device_bcs:
+        asm.jacobian(2, save=False, out=False)  # ADJOINT
+        J, _ = asm.functional(qoi, with_dMdu=True, **kw)
+        asm.apply_dbcs(rows, gval, True)
+        R, AT = asm.fetch()
+        dMdu = asm.fetch_dMdu()
+    else:
+        R, AT = [np.array(x, copy=True) for x in asm.jacobian(2, save=False)]
+        J, dMdu = asm.functional(qoi, with_dMdu=True, **kw)
+        for row, g in zip(rows, gval):  # set_jac_dbcs (src/goal_dbcs.cpp:60-97)
+            R[row] = sol[row] - g
+            dMdu[row] = 0.0
+            AT[rowptr[row]:rowptr[row + 1]] = 0.0
+            AT[rowptr[row] + np.searchsorted(colind[rowptr[row]:rowptr[row + 1]], row)] = 1.0
+    A = sp.csr_matrix((AT, colind, rowptr), shape=(4 * nn, 4 * nn))
+    z = spla.spsolve(A.tocsc(), dMdu)
+    zf = z.reshape(nn, 4)
+    zc = set_coarse(zf, nested)       # apf::copyData + Nested::set_coarse
+    zd = zf - zc                       # NestedAdjoint::subtract
+    e_est = -float(R @ z)
+    if device_bcs:
+        asm.localize(zd[:, :3], zd[:, 3], zc[:, 3])
+        asm.apply_dbcs(rows, gval, False)
+        Re = asm.fetch(values=False)[0]
+    else:
+        Re = np.array(asm.localize(zd[:, :3], zd[:, 3], zc[:, 3]), copy=True)
+        Re[rows] = sol[rows] - gval    # set_resid_dbcs
+    err = Re.reshape(nn, 4)
+    n_base = int(nested["parent"].max()) + 1
+    eta, eta_parent, bound = asm.element_error(err[:, :3].copy(), err[:, 3].copy(), nested["parent"], n_base)
+    return dict(J=J, z=z, e_est=e_est, eta=eta, eta_parent=eta_parent, bound=bound, u=u, p=p)
 
 
 # The reference's three 3D regression inputs (example/primal/*.yaml), all on

@@ -1,0 +1,95 @@
+"""BASELINE.json configs[3]: the nested-mesh adjoint solve + error localisation that drives one adapt cycle
+(NestedAdjoint::run, src/goal_nested_adjoint.cpp:236-247), on a uniform 1:8 refinement of the reference's cube
+fixture (goal_b200/nested.py stands in for MeshAdapt; oracle/driver.py:run_nested_cycle is the sequence).
+
+CPU: the oracle's cycle is validated by what it is for -- the adjoint-weighted estimate e = -(R . z) must predict
+the change of the functional between the base solution and the solution on the nested mesh (effectivity near 1),
+for neo-Hookean and for J2 with every element on the plastic branch.  This pins the transposed Jacobian, dMdu, the
+Dirichlet handling of the adjoint problem and the state transfer, none of which a reference golden covers.
+GPU: the same cycle with every assembly, boundary and error step on the device against the oracle's."""
+import numpy as np
+import pytest
+
+from goal_b200.nested import refine_uniform, set_coarse
+from goal_b200.synthetic import MATERIAL
+
+CASES = {"neohookean": (0.02, 1), "J2": (0.008, 2)}  # (end displacement per step, load steps)
+
+
+def _bcs(c, amp):
+    """clamped at x = 0, pulled at x = 1: a non-homogeneous deformation (the reference's uniaxial cases are exact on any mesh)"""
+    xmin, xmax = np.nonzero(c[:, 0] < 1e-12)[0], np.nonzero(c[:, 0] > 1 - 1e-12)[0]
+    z = lambda t: 0.0
+    return [(0, xmin, z), (1, xmin, z), (2, xmin, z), (0, xmax, lambda t: amp * t), (1, xmax, z), (2, xmax, z)]
+
+
+def _base(cube, model):
+    from oracle import driver
+    from oracle.oracle import Oracle
+    amp, steps = CASES[model]
+    co, cn = cube["coords"], cube["tets"]
+    o = Oracle(co, cn, model, [MATERIAL])
+    r = driver.run_primal(o, co, _bcs(co, amp), (), num_steps=steps, max_iters=8)
+    return r, refine_uniform(co, cn)
+
+
+def test_uniform_refinement_bookkeeping(cube):
+    co, cn = cube["coords"], cube["tets"]
+    n = refine_uniform(co, cn)
+    x, x0 = n["coords"][n["tets"]], co[cn]
+    vol, vol0 = np.linalg.det(x[:, 1:] - x[:, :1]) / 6, np.linalg.det(x0[:, 1:] - x0[:, :1]) / 6
+    assert len(n["tets"]) == 8 * len(cn) and len(n["coords"]) == 51 + 230  # one new vertex per edge
+    assert np.allclose(vol.reshape(-1, 8), vol0[:, None] / 8, rtol=1e-12, atol=0)  # eight children of equal volume
+    assert np.array_equal(n["parent"], np.repeat(np.arange(len(cn)), 8))
+    f = set_coarse(n["coords"] @ np.array([1.0, -2.0, 0.5]) + 7.0, n)  # a linear field is reproduced
+    assert np.allclose(f, n["coords"] @ np.array([1.0, -2.0, 0.5]) + 7.0, rtol=0, atol=1e-14)
+    faces = np.sort(np.concatenate([n["tets"][:, [1, 2, 3]], n["tets"][:, [0, 2, 3]], n["tets"][:, [0, 1, 3]], n["tets"][:, [0, 1, 2]]]), 1)
+    _, cnt = np.unique(faces, axis=0, return_counts=True)
+    assert cnt.max() == 2 and (cnt == 1).sum() == 4 * 96  # conforming: 6 x 16 boundary faces of the fixture, each split in 4
+
+
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+def test_oracle_error_estimate_predicts_functional_change(cube, model):
+    from oracle import driver
+    from oracle.oracle import Oracle
+    amp, steps = CASES[model]
+    r, nested = _base(cube, model)
+    nco = nested["coords"]
+    on = Oracle(nco, nested["tets"], model, [MATERIAL])
+    c = driver.run_nested_cycle(on, nested, r["u"], r["p"], r["states_old"], _bcs(nco, amp), t_now=float(steps))
+    if model == "J2":
+        assert r["plastic"][-1] == 132
+    fine = driver.run_primal(Oracle(nco, nested["tets"], model, [MATERIAL]), nco, _bcs(nco, amp), (), num_steps=steps, max_iters=8)
+    true = fine["J"][-1] - r["J"][-1]
+    assert abs(c["J"] - r["J"][-1]) < 1e-15  # the prolonged solution carries the base functional
+    assert 0.8 < c["e_est"] / true < 1.2, (c["e_est"], true)
+    assert abs(c["eta_parent"].sum() - c["eta"].sum()) < 1e-12 * c["eta"].sum() and len(c["eta_parent"]) == 132
+    assert c["bound"] > 0 and np.all(c["eta"] >= 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+def test_nested_cycle_on_the_device_matches_oracle(cube, model):
+    import goal_b200
+    from oracle import driver
+    from oracle.oracle import Oracle
+    amp, steps = CASES[model]
+    r, nested = _base(cube, model)
+    nco = nested["coords"]
+    co_ = driver.run_nested_cycle(Oracle(nco, nested["tets"], model, [MATERIAL]), nested, r["u"], r["p"], r["states_old"],
+                                  _bcs(nco, amp), t_now=float(steps))
+    a = goal_b200.Assembler(nco, nested["tets"], model, [MATERIAL])
+    for dev in (False, True):  # Dirichlet rows on the host / on the device (gx_apply_dbcs incl. dMdu rows)
+        cg = driver.run_nested_cycle(a, nested, r["u"], r["p"], r["states_old"], _bcs(nco, amp), t_now=float(steps), device_bcs=dev)
+        assert abs(cg["J"] - co_["J"]) < 1e-13 * abs(co_["J"])
+        assert np.abs(cg["z"] - co_["z"]).max() < 1e-8 * np.abs(co_["z"]).max()
+        assert abs(cg["e_est"] - co_["e_est"]) < 1e-8 * abs(co_["e_est"])
+        assert np.abs(cg["eta_parent"] - co_["eta_parent"]).max() < 1e-8 * co_["eta_parent"].max()
+        assert abs(cg["bound"] - co_["bound"]) < 1e-8 * co_["bound"]
+    a.close()
+    # the adapt input: target size field on the base mesh from the parents' indicators (get_iso_target_size)
+    ab = goal_b200.Assembler(cube["coords"], cube["tets"], model, [MATERIAL])
+    v, G = ab.size_field(cg["eta_parent"], 2 * 132)
+    vo, Go = Oracle(cube["coords"], cube["tets"], model, [MATERIAL]).size_field(co_["eta_parent"], 2 * 132)
+    assert abs(G - Go) < 1e-7 * Go and np.abs(v - vo).max() < 1e-7 * vo.max()
+    ab.close()
