@@ -156,7 +156,7 @@ def _addr(a):
 class Assembler:
     """One mesh part on one GPU (a gx_ctx)."""
 
-    def __init__(self, coords, conn, model, materials, elem_set=None, device=0, partition=None):
+    def __init__(self, coords, conn, model, materials, elem_set=None, device=0, partition=None, flags=0):
         self.L = load_library()
         self.coords = np.ascontiguousarray(coords, dtype=np.float64).reshape(-1, 3)
         self.conn = np.ascontiguousarray(conn, dtype=np.int32).reshape(-1, 4)
@@ -165,6 +165,7 @@ class Assembler:
         mats = np.ascontiguousarray(materials, dtype=np.float64).reshape(-1, 5)
         self._keep = [mats]
         d = GxDesc()
+        d.flags = flags  # GX_FLAG_NO_STABILIZATION = 1
         d.n_nodes, d.n_elems = self.nn, self.ne
         d.conn, d.coords = _ip(self.conn), _dp(self.coords)
         if elem_set is not None:

@@ -569,7 +569,6 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     g_create_err = "gx_create: invalid description";
     return GX_ERR_ARG;
   }
-  if (d->flags & GX_FLAG_NO_STABILIZATION) { g_create_err = "gx_create: stabilization: false is not supported"; return GX_ERR_UNSUPPORTED; }
   // device = -1 builds a host-only context: graph, scatter map and exchange plan only (for setup-time
   // tools and CPU tests of the partition logic); every compute entry point refuses to run on it.
   int ndev = 0;
@@ -588,6 +587,9 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
   for (int s = 0; s < ctx->nsets; ++s) {
     double const* m5 = d->materials + 5 * s;  // kappa, mu: goal_neohookean.cpp:50-51, goal_J2.cpp:62-63
     ctx->mats[s] = make_material(m5[0], m5[1], m5[2], m5[3], m5[4]);
+    // mechanics: stabilization: false (goal_mechanics.cpp:55-56, 140-143: the Stabilization evaluator is not built).
+    // Every term it adds carries tau = c0 h^2 / (2 mu) as a factor, so tau = 0 is the same assembly.
+    if (d->flags & GX_FLAG_NO_STABILIZATION) ctx->mats[s].tauc = 0.0;
   }
   auto fail = [&](int rc) { g_create_err = ctx->err; free_device(ctx); comm_destroy(ctx); delete ctx; return rc; };
   for (int e = 0; e < ctx->ne && !ctx->eset.empty(); ++e)

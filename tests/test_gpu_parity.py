@@ -302,6 +302,32 @@ def test_solution_update_and_size_field(cube, mesh):
     a.close()
 
 
+def test_stabilization_off(cube):
+    """mechanics: stabilization: false (src/goal_mechanics.cpp:55-56, 140-143): the Stabilization evaluator is left out.
+    All its terms carry tau = c0 h^2 / (2 mu), so the oracle with c0 = 0 is the reference chain without it."""
+    import goal_b200
+    from oracle.oracle import Oracle
+    co, cn = kuhn_cube(5)
+    f = fields(co, len(cn), strain=0.004)
+    nostab = list(MATERIAL[:4]) + [0.0]
+    a = goal_b200.Assembler(co, cn, "J2", [MATERIAL], flags=1)
+    o = Oracle(co, cn, "J2", [nostab])
+    for s_ in (a, o):
+        s_.set_solution(f["u"], f["p"])
+    a.set_state("Fp_old", f["Fp_old"]); a.set_state("eqps_old", f["eqps_old"])
+    o.state("Fp_old")[:] = f["Fp_old"]; o.state("eqps_old")[:] = f["eqps_old"]
+    R, A = a.jacobian(goal_b200.PRIMAL, save=False)
+    Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=False)
+    assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
+    zu, zp, zc = f["zu_diff"], f["zp_diff"], f["zp_coarse"]
+    assert relerr(a.localize(zu, zp, zc), o.localize(zu, zp, zc)) < 1e-12
+    # and it is not the stabilized operator: the pressure-pressure blocks differ
+    o2 = Oracle(co, cn, "J2", [MATERIAL])
+    o2.set_solution(f["u"], f["p"]); o2.state("Fp_old")[:] = f["Fp_old"]; o2.state("eqps_old")[:] = f["eqps_old"]
+    assert relerr(A, o2.jacobian(goal_b200.PRIMAL, save=False)[1]) > 1e-6
+    a.close()
+
+
 def test_bitwise_determinism(cube):
     """No atomics on the data path: repeated passes give identical bits."""
     import goal_b200
