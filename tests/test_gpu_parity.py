@@ -321,10 +321,10 @@ def test_stabilization_off(cube):
     assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
     zu, zp, zc = f["zu_diff"], f["zp_diff"], f["zp_coarse"]
     assert relerr(a.localize(zu, zp, zc), o.localize(zu, zp, zc)) < 1e-12
-    # and it is not the stabilized operator: the pressure-pressure blocks differ
+    # and it is not the stabilized chain: the pressure residual differs (4e-4 norm-wise on this input)
     o2 = Oracle(co, cn, "J2", [MATERIAL])
     o2.set_solution(f["u"], f["p"]); o2.state("Fp_old")[:] = f["Fp_old"]; o2.state("eqps_old")[:] = f["eqps_old"]
-    assert relerr(A, o2.jacobian(goal_b200.PRIMAL, save=False)[1]) > 1e-6
+    assert relerr(R, o2.jacobian(goal_b200.PRIMAL, save=False)[0]) > 1e-5
     a.close()
 
 
