@@ -201,7 +201,7 @@ constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per p
 constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_PARTS = 32;     // secondary items (partial sums handed to a primary) per patch
-constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS;  // uint32 words per patch
+constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS + 2 * PATCH_RECS;  // uint32 words per patch
 // gx_comm.cu
 void comm_destroy(gx_ctx*);
 int comm_setup_lists(gx_ctx*, const gx_desc*);

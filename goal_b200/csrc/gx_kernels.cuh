@@ -958,11 +958,14 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   int const tid = threadIdx.x;
   uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
   int const n_recs = (int)__ldg(w);
-  int const my_elem = (int)__ldg(w + 4 + tid);
+  int const n_runs = (int)__ldg(w + 2);
+  uint2 const my_run = __ldg(reinterpret_cast<uint2 const*>(w + 4 + PATCH_RECS + 8 * PATCH_THREADS) + min(tid, PATCH_RECS - 1));
   uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
   uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
-  // Record staging: thread r issues one bulk asynchronous copy (272 B, global -> shared) for record r; the copies
-  // report their bytes to an mbarrier that the whole block then waits on.
+  // Record staging: thread r issues one bulk asynchronous copy (global -> shared) for run r of the schedule -- a run is
+  // a number of consecutive elements' records (272 B each, contiguous in global memory) that go to consecutive slots;
+  // the copies report their bytes to an mbarrier that the whole block then waits on.
+  static_assert(PATCH_RECS <= PATCH_THREADS, "one thread per run");
   uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
@@ -970,11 +973,12 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   }
   __syncthreads();
   if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
-  if (tid < n_recs) {
-    uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + (uint32_t)(tid * (PATCH_REC_LD * 8));
-    double const* src = rec + (int64_t)ELEM_REC * my_elem;
+  if (tid < n_runs) {
+    uint32_t const sl = my_run.y & 0xffu, len = my_run.y >> 8;
+    uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + sl * (uint32_t)(PATCH_REC_LD * 8);
+    double const* src = rec + (int64_t)ELEM_REC * (int64_t)my_run.x;
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-                 "r"(ELEM_REC * 8), "r"(mb)
+                 "r"(len * (uint32_t)(ELEM_REC * 8)), "r"(mb)
                  : "memory");
   }
   {

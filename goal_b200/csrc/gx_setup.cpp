@@ -275,10 +275,12 @@ void build_block_lists(gx_ctx* c) {
 //   [0..3]   n_recs, n_items, 0, 0
 //   [4..]    elems[PATCH_RECS]                      element id of each staged record
 //   then     items[PATCH_THREADS][4]                8 rounds x 16 bit: slot | m << 8 | n << 10 | 0x8000, 0 = sits the round out
+//   [0..3]   (cont.) word 2 = number of runs
 //   then     outs[PATCH_THREADS][4]                 x,y = value offset of block entry (0,0) (int64, doubles)
 //                                                   z = row stride | part slot << 16 | n secondaries << 24 | kind << 30
 //                                                   w = node id | diagonal << 31
 //            kind: 0 idle thread, 1 primary, 2 secondary
+//   then     runs[PATCH_RECS][2]                    bulk copies: first element id, first slot | number of records << 8
 bool build_patch_schedule(gx_ctx* c) {
   using namespace gx;
   if (!c->block_lists_built) build_block_lists(c);
@@ -289,6 +291,7 @@ bool build_patch_schedule(gx_ctx* c) {
   std::vector<std::vector<uint32_t>> out(nch);
   bool const stats = getenv("GX_SCHED_STATS") != nullptr;
   bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
+  bool const use_runs = getenv("GX_SCHED_RUNS") == nullptr || atoi(getenv("GX_SCHED_RUNS")) != 0;  // 0: one copy per record
   std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0), st_runs(nch, 0), st_recs(nch, 0);
   bool ok = true;
   // Blocks with many contributions (the diagonal block: one per incident element) are cut into items of at most
@@ -329,20 +332,66 @@ bool build_patch_schedule(gx_ctx* c) {
       // (per round a bipartite matching of items to bank groups).
       int const nrec = (int)recs.size();
       std::vector<int> res(nrec, -1);
-      int cap[8];
-      for (int r = 0; r < 8; ++r) cap[r] = nrec / 8 + (r < nrec % 8 ? 1 : 0);  // slots r, r + 8, ...: no gaps
-      {
+      std::vector<int> slot_of(nrec, -1);   // run placement only: final slot of every record
+      std::vector<uint32_t> run_e0, run_sl; // runs of consecutive elements in consecutive slots: one bulk copy each
+      std::vector<std::vector<int>> in_items(nrec);
+      for (size_t i = 0; i < items.size(); ++i)
+        for (int q = 0; q < items[i].n; ++q) in_items[items[i].ent[q] & 0xff].push_back((int)i);
+      auto conflicts = [&](int l, int r) {  // records already placed in bank group r that share an item with record l
+        int cnt = 0;
+        for (int i : in_items[l])
+          for (int q = 0; q < items[i].n; ++q) cnt += res[items[i].ent[q] & 0xff] == r;
+        return cnt;
+      };
+      if (use_runs) {
+        // Records of consecutive elements are consecutive in global memory: placed in consecutive slots they arrive with
+        // ONE bulk copy.  A run's records then sit in consecutive bank groups, so the greedy colouring works on runs:
+        // longest first, each at the free position where its records meet the fewest already placed records of the
+        // items they feed (ties: the lowest slot).
+        std::vector<int> byel(nrec);
+        for (int l = 0; l < nrec; ++l) byel[l] = l;
+        std::sort(byel.begin(), byel.end(), [&](int x, int y) { return recs[x] < recs[y]; });
+        struct Run { int first, len; };
+        std::vector<Run> runs;
+        for (int i = 0; i < nrec;) {
+          int j = i + 1;
+          while (j < nrec && recs[byel[j]] == recs[byel[j - 1]] + 1 && j - i < 8) ++j;  // at most 8: distinct bank groups
+          runs.push_back({i, j - i});
+          i = j;
+        }
+        std::stable_sort(runs.begin(), runs.end(), [](Run const& a, Run const& b) { return a.len > b.len; });
+        bool taken[PATCH_RECS] = {};
+        for (size_t ri = 0; ri < runs.size(); ++ri) {
+          Run const run = runs[ri];
+          int best = -1, best_cost = 1 << 30;
+          for (int s0 = 0; s0 + run.len <= PATCH_RECS; ++s0) {
+            bool free_ = true;
+            for (int j = 0; j < run.len && free_; ++j) free_ = !taken[s0 + j];
+            if (!free_) continue;
+            int cost = 0;
+            for (int j = 0; j < run.len; ++j) cost += conflicts(byel[run.first + j], (s0 + j) & 7);
+            if (cost < best_cost) { best_cost = cost; best = s0; }
+            if (cost == 0) break;
+          }
+          if (best < 0) {  // fragmented: cut the run in two and place the halves
+            runs.push_back({run.first, run.len / 2});
+            runs.push_back({run.first + run.len / 2, run.len - run.len / 2});
+            continue;
+          }
+          for (int j = 0; j < run.len; ++j) {
+            int const l = byel[run.first + j];
+            taken[best + j] = true; slot_of[l] = best + j; res[l] = (best + j) & 7;
+          }
+          run_e0.push_back((uint32_t)recs[byel[run.first]]);
+          run_sl.push_back((uint32_t)best | ((uint32_t)run.len << 8));
+        }
+      } else {
+        int cap[8];
+        for (int r = 0; r < 8; ++r) cap[r] = nrec / 8 + (r < nrec % 8 ? 1 : 0);  // slots r, r + 8, ...: no gaps
         // bank groups first: records that contribute to the same item get different groups where possible
-        std::vector<std::vector<int>> in_items(nrec);
-        for (size_t i = 0; i < items.size(); ++i)
-          for (int q = 0; q < items[i].n; ++q) in_items[items[i].ent[q] & 0xff].push_back((int)i);
         for (int l = 0; l < nrec; ++l) {
-          int cnt[8] = {};
-          for (int i : in_items[l])
-            for (int q = 0; q < items[i].n; ++q) {
-              int const r = res[items[i].ent[q] & 0xff];
-              if (r >= 0) cnt[r]++;
-            }
+          int cnt[8];
+          for (int r = 0; r < 8; ++r) cnt[r] = conflicts(l, r);
           int best = -1;
           for (int r = 0; r < 8; ++r)
             if (cap[r] > 0 && (best < 0 || cnt[r] < cnt[best] || (cnt[r] == cnt[best] && cap[r] > cap[best]))) best = r;
@@ -420,18 +469,22 @@ bool build_patch_schedule(gx_ctx* c) {
       {  // final slots: record with bank group r takes the next of r, r + 8, r + 16, ...
         int next[8] = {0, 1, 2, 3, 4, 5, 6, 7};
         std::vector<int> slot(nrec);
-        std::vector<int32_t> recs2(nrec, 0);
-        for (int l = 0; l < nrec; ++l) { slot[l] = next[res[l]]; next[res[l]] += 8; recs2[slot[l]] = recs[l]; }
+        std::vector<int32_t> recs2(use_runs ? PATCH_RECS : nrec, 0);
+        for (int l = 0; l < nrec; ++l) {
+          if (use_runs) slot[l] = slot_of[l];
+          else { slot[l] = next[res[l]]; next[res[l]] += 8; }
+          recs2[slot[l]] = recs[l];
+        }
+        if (!use_runs)  // one copy per record
+          for (int l = 0; l < nrec; ++l) { run_e0.push_back((uint32_t)recs[l]); run_sl.push_back((uint32_t)slot[l] | (1u << 8)); }
         recs.swap(recs2);
         for (auto& it : items)
           for (int k = 0; k < PATCH_ITEM_LEN; ++k)
             if (it.ent[k] & 0x8000) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot[it.ent[k] & 0xff]);
       }
       if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
-        std::vector<int32_t> sr(recs);
-        std::sort(sr.begin(), sr.end());
-        for (size_t i = 0; i < sr.size(); ++i) if (i == 0 || sr[i] != sr[i - 1] + 1) st_runs[ch]++;
-        st_recs[ch] += (int64_t)sr.size();
+        st_runs[ch] += (int64_t)run_e0.size();
+        st_recs[ch] += (int64_t)nrec;
         for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
           int const gn = (int)std::min<size_t>(8, ord.size() - g0);
           for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
@@ -458,8 +511,10 @@ bool build_patch_schedule(gx_ctx* c) {
       size_t const base = out[ch].size();
       out[ch].resize(base + PATCH_WORDS, 0u);
       uint32_t* w = out[ch].data() + base;
-      w[0] = (uint32_t)recs.size(); w[1] = (uint32_t)items.size();
+      w[0] = (uint32_t)nrec; w[1] = (uint32_t)items.size(); w[2] = (uint32_t)run_e0.size();
       for (size_t i = 0; i < recs.size(); ++i) w[4 + i] = (uint32_t)recs[i];
+      uint32_t* wr = w + 4 + PATCH_RECS + 8 * PATCH_THREADS;  // runs[2 PATCH_RECS]: first element, first slot | length << 8
+      for (size_t i = 0; i < run_e0.size(); ++i) { wr[2 * i] = run_e0[i]; wr[2 * i + 1] = run_sl[i]; }
       uint32_t* wi = w + 4 + PATCH_RECS;
       uint32_t* wo = wi + 4 * PATCH_THREADS;
       for (size_t t = 0; t < ord.size(); ++t) {

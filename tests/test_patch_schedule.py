@@ -33,11 +33,21 @@ def _check(co, cn):
         n_recs, n_items = int(pw[0]), int(pw[1])
         recs = pw[4:4 + RECS]
         assert n_recs <= RECS and n_items <= T
-        assert len(set(recs[:n_recs].tolist())) == n_recs  # a record is staged once per patch
+        # the bulk copies: runs of consecutive elements into consecutive slots; they fill exactly the slots the items read
+        n_runs = int(pw[2])
+        runs = pw[4 + RECS + 8 * T:4 + RECS + 8 * T + 2 * n_runs].reshape(n_runs, 2)
+        staged = {}
+        for e0, sl in runs:
+            s0, ln = int(sl) & 0xff, int(sl) >> 8
+            assert 1 <= ln <= 8 and s0 + ln <= RECS
+            for j in range(ln):
+                assert s0 + j not in staged
+                staged[s0 + j] = int(e0) + j
+        assert len(staged) == n_recs and len(set(staged.values())) == n_recs  # a record is staged once per patch
+        assert all(int(recs[k]) == v for k, v in staged.items())
         it = pw[4 + RECS:4 + RECS + 4 * T].reshape(T, 4)
         ot = pw[4 + RECS + 4 * T:4 + RECS + 8 * T].reshape(T, 4)
-        has2 = len(pw) >= 4 + RECS + 12 * T  # layout with mirror outputs (paired items)
-        o2 = pw[4 + RECS + 8 * T:4 + RECS + 12 * T].reshape(T, 4) if has2 else np.zeros((T, 4), dtype=np.uint32)
+        o2 = np.zeros((T, 4), dtype=np.uint32)  # no paired items in this layout
         parts = {}
         for t in range(T):
             kind = int(ot[t, 2]) >> 30
@@ -50,7 +60,7 @@ def _check(co, cn):
                     v = (int(it[t, k]) >> h) & 0xffff
                     if v & 0x8000:
                         ents.append((int(recs[v & 0xff]), (v >> 10) & 3, (v >> 8) & 3))
-                        assert (v & 0xff) < n_recs
+                        assert (v & 0xff) in staged
             voff = int(ot[t, 0]) | (int(ot[t, 1]) << 32)
             rl = int(ot[t, 2]) & 0xffff
             key = blk_of_off[(voff, rl)]
