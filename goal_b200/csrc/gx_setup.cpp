@@ -15,6 +15,7 @@
 // node, so their scatters into R and into the CRS values touch disjoint rows and
 // the assembly needs no atomics and is bit-reproducible run to run.
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -337,11 +338,13 @@ bool build_patch_schedule(gx_ctx* c) {
       std::vector<std::vector<int>> in_items(nrec);
       for (size_t i = 0; i < items.size(); ++i)
         for (int q = 0; q < items[i].n; ++q) in_items[items[i].ent[q] & 0xff].push_back((int)i);
-      auto conflicts = [&](int l, int r) {  // records already placed in bank group r that share an item with record l
-        int cnt = 0;
+      // cnt8[l][r] = records already placed in bank group r that share an item with record l (with multiplicity)
+      std::vector<std::array<int, 8>> cnt8(nrec, std::array<int, 8>{});
+      auto conflicts = [&](int l, int r) { return cnt8[l][r]; };
+      auto place = [&](int l, int r) {
+        res[l] = r;
         for (int i : in_items[l])
-          for (int q = 0; q < items[i].n; ++q) cnt += res[items[i].ent[q] & 0xff] == r;
-        return cnt;
+          for (int q = 0; q < items[i].n; ++q) cnt8[items[i].ent[q] & 0xff][r]++;
       };
       if (use_runs) {
         // Records of consecutive elements are consecutive in global memory: placed in consecutive slots they arrive with
@@ -380,7 +383,7 @@ bool build_patch_schedule(gx_ctx* c) {
           }
           for (int j = 0; j < run.len; ++j) {
             int const l = byel[run.first + j];
-            taken[best + j] = true; slot_of[l] = best + j; res[l] = (best + j) & 7;
+            taken[best + j] = true; slot_of[l] = best + j; place(l, (best + j) & 7);
           }
           run_e0.push_back((uint32_t)recs[byel[run.first]]);
           run_sl.push_back((uint32_t)best | ((uint32_t)run.len << 8));
@@ -395,7 +398,7 @@ bool build_patch_schedule(gx_ctx* c) {
           int best = -1;
           for (int r = 0; r < 8; ++r)
             if (cap[r] > 0 && (best < 0 || cnt[r] < cnt[best] || (cnt[r] == cnt[best] && cap[r] > cap[best]))) best = r;
-          res[l] = best; cap[best]--;
+          place(l, best); cap[best]--;
         }
       }
       for (size_t g0 = 0; g0 < ord.size() && !nomatch; g0 += 8) {
