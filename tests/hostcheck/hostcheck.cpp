@@ -31,7 +31,18 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
       double blk[16];
       gx::RowNode<double> rn;
       gx::row_node(c, c.w[n], rn);
-      gx::jacobian_block(c, rn, cn, blk);
+      if (save & 4) {  // the accumulating form the patch gather uses (fused multiply-adds into the accumulator)
+        for (int q = 0; q < 16; ++q) blk[q] = 0.0;
+        if (save & 8) {  // transposed accumulation, undone here
+          double t[16] = {};
+          gx::jacobian_block_add<true>(c, rn, cn, t);
+          for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) blk[4 * i + k] = t[4 * k + i];
+        } else {
+          gx::jacobian_block_add<false>(c, rn, cn, blk);
+        }
+      } else {
+        gx::jacobian_block(c, rn, cn, blk);
+      }
       for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) K[(4 * n + i) * 16 + 4 * mm + k] = blk[4 * i + k];
     }
   }

@@ -49,6 +49,12 @@ def test_element_math_matches_fad_oracle(hostcheck, model):
                                   2, dp(Kw), dp(np.zeros(16)), dp(np.zeros(9)), C.byref(C.c_double(0)), dp(np.zeros(9)),
                                   C.byref(C.c_int(0)), C.byref(C.c_int(0)))
         assert rc == 0 and relerr(Kw.reshape(16, 16), Ko) < 1e-12
+        for mode in (2 | 4, 2 | 4 | 8):  # + jacobian_block_add (plain and transposed): the patch gather's inner loop
+            Ka = np.zeros(256)
+            rc = hostcheck.hc_element(0 if model == "neohookean" else 1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eqo),
+                                      mode, dp(Ka), dp(np.zeros(16)), dp(np.zeros(9)), C.byref(C.c_double(0)), dp(np.zeros(9)),
+                                      C.byref(C.c_int(0)), C.byref(C.c_int(0)))
+            assert rc == 0 and relerr(Ka.reshape(16, 16), Ko) < 1e-12
         assert relerr(sig, o.state("sigma")[0]) < 1e-10
         if model == "J2":
             assert pl.value == o.plastic_count()
