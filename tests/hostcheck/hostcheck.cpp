@@ -238,3 +238,113 @@ extern "C" int hc_count_ops(int model, int what, int save, const double* x, cons
   out[0] = Cnt::add; out[1] = Cnt::mul; out[2] = Cnt::dv; out[3] = Cnt::sp;
   return 0;
 }
+
+// ---------------------------------------------------------------------------
+// CPU replay of the patch-gather Jacobian pass (the default GPU schedule): builds the patch schedule with the product's
+// own host code (gx_setup.cpp), then interprets its words the way patch_gather_kernel does -- staged record slots,
+// work items of up to 8 contributions, primaries adding their secondaries' partial sums in order, one writer per
+// 4x4 block and per node's residual entries -- with the device's element math compiled for the host.  The element
+// "records" are the Core structs themselves (the 34-double packing is device-only code).
+//   values [nnz] and R [4 nn] must come in zeroed; every entry the schedule owns is written exactly once.
+// ---------------------------------------------------------------------------
+template <int MODEL, bool TRANSPOSE>
+static int replay_patch_gather(gx_ctx& c, std::vector<gx::Core<double>> const& core, double* R, double* values) {
+  using namespace gx;
+  uint32_t const* sched = c.patch_sched.data();
+  for (int pch = 0; pch < c.n_patches; ++pch) {
+    uint32_t const* w = sched + (size_t)pch * PATCH_WORDS;
+    int const n_recs = (int)w[0], n_runs = (int)w[2];
+    std::vector<int64_t> slot_elem(PATCH_RECS, -1);  // what the bulk copies stage: runs of consecutive elements
+    int staged = 0;
+    uint32_t const* wr = w + 4 + PATCH_RECS + 8 * PATCH_THREADS;
+    for (int r = 0; r < n_runs; ++r)
+      for (uint32_t j = 0; j < (wr[2 * r + 1] >> 8); ++j) { slot_elem[(wr[2 * r + 1] & 0xffu) + j] = (int64_t)wr[2 * r] + j; ++staged; }
+    if (staged != n_recs) return 10;
+    uint32_t const* wi = w + 4 + PATCH_RECS;
+    uint32_t const* wo = wi + 4 * PATCH_THREADS;
+    double acc[PATCH_THREADS][16], r4[PATCH_THREADS][4], parts[PATCH_PARTS][20];
+    for (int t = 0; t < PATCH_THREADS; ++t) {
+      uint32_t const* ot = wo + 4 * t;
+      int const kind = (int)(ot[2] >> 30);
+      bool const diag = (ot[3] & 0x80000000u) != 0;
+      for (int k = 0; k < 16; ++k) acc[t][k] = 0.0;
+      for (int k = 0; k < 4; ++k) r4[t][k] = 0.0;
+      if (kind == 0) continue;
+      for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
+        uint32_t const ent = (wi[4 * t + k / 2] >> (16 * (k & 1))) & 0xffffu;
+        if (!(ent & 0x8000u)) continue;
+        int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
+        if (slot_elem[slot] < 0) return 11;
+        Core<double> const& cr = core[(size_t)slot_elem[slot]];
+        int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
+        RowNode<double> rn;
+        ColNode<double> cn;
+        row_node(cr, cr.w[nr], rn);
+        column_node_w(cr, cr.w[nc], cn);
+        jacobian_block_add<TRANSPOSE>(cr, rn, cn, acc[t]);
+        if (diag) {
+          double t4[4];
+          element_residual_row(cr, cr.w[nr], t4);
+          for (int q = 0; q < 4; ++q) r4[t][q] += t4[q];
+        }
+      }
+      if (kind == 2) {
+        int const part = (int)((ot[2] >> 16) & 0xffu);
+        if (part >= PATCH_PARTS) return 12;
+        for (int k = 0; k < 16; ++k) parts[part][k] = acc[t][k];
+        for (int k = 0; k < 4; ++k) parts[part][16 + k] = r4[t][k];
+      }
+    }
+    for (int t = 0; t < PATCH_THREADS; ++t) {
+      uint32_t const* ot = wo + 4 * t;
+      if ((ot[2] >> 30) != 1u) continue;
+      bool const diag = (ot[3] & 0x80000000u) != 0;
+      int const part = (int)((ot[2] >> 16) & 0xffu), nsec = (int)((ot[2] >> 24) & 0x3fu);
+      for (int s2 = 0; s2 < nsec; ++s2) {
+        for (int k = 0; k < 16; ++k) acc[t][k] += parts[part + s2][k];
+        if (diag) for (int k = 0; k < 4; ++k) r4[t][k] += parts[part + s2][16 + k];
+      }
+      int64_t const voff = (int64_t)(((uint64_t)ot[1] << 32) | (uint64_t)ot[0]);
+      int const rl = (int)(ot[2] & 0xffffu);
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          if (values[voff + (int64_t)i * rl + j] != 0.0) return 13;  // a second writer
+          values[voff + (int64_t)i * rl + j] = acc[t][4 * i + j];
+        }
+      if (diag) for (int k = 0; k < 4; ++k) R[4 * (size_t)(ot[3] & 0x7fffffffu) + k] = r4[t][k];
+    }
+  }
+  return 0;
+}
+
+extern "C" int hc_patch_gather(int model, int transpose, int nn, int ne, const int32_t* conn, const double* coords,
+                               const double* mat5, const double* u, const double* p, const double* eqps_old,
+                               const double* Fp_old, double* R, double* values, int32_t* n_patches) {
+  gx_ctx c;
+  c.nn = nn; c.ne = ne; c.model = model; c.nsets = 1;
+  c.conn.assign(conn, conn + 4 * (size_t)ne);
+  c.coords.assign(coords, coords + 3 * (size_t)nn);
+  gx::Material const mat = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
+  int rc = gx::build_graph_and_schedule(&c);
+  if (rc) return rc;
+  c.nrow_x = c.nrow;  // single part: no phantom blocks (comm_setup_lists does this in the library)
+  if (!gx::build_patch_schedule(&c)) return 20;
+  *n_patches = c.n_patches;
+  std::vector<gx::Core<double>> core(ne);
+  for (int e = 0; e < ne; ++e) {  // stage A: the element core, once per element
+    double X[4][3], U[4][3], P4[4], Cp[6], sg[9], eq;
+    for (int n = 0; n < 4; ++n) {
+      int const a = conn[4 * (size_t)e + n];
+      for (int j = 0; j < 3; ++j) { X[n][j] = coords[3 * (size_t)a + j]; U[n][j] = u[3 * (size_t)a + j]; }
+      P4[n] = p[a];
+    }
+    if (model == 1) gx::cp_inverse(Fp_old + 9 * (size_t)e, Cp);
+    rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, P4, mat, Cp, 0.0, false, sg, eq, core[e])
+                    : gx::element_core<gx::MODEL_J2>(X, U, P4, mat, Cp, eqps_old[e], false, sg, eq, core[e]);
+    if (rc) return rc;
+  }
+  if (model == 0) return transpose ? replay_patch_gather<gx::MODEL_NEOHOOKEAN, true>(c, core, R, values)
+                                   : replay_patch_gather<gx::MODEL_NEOHOOKEAN, false>(c, core, R, values);
+  return transpose ? replay_patch_gather<gx::MODEL_J2, true>(c, core, R, values)
+                   : replay_patch_gather<gx::MODEL_J2, false>(c, core, R, values);
+}

@@ -160,3 +160,29 @@ def test_whole_mesh_emulation_matches_oracle(hostcheck, cube, model, mesh):
     z5 = np.concatenate([f["zu_diff"], f["zp_diff"][:, None], f["zp_coarse"][:, None]], 1).copy()
     Re = o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])
     assert relerr(_emulate(hostcheck, mi, 3, 0, co, cn, f, z5=z5)["R"], Re) < 1e-12
+
+
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+@pytest.mark.parametrize("mesh", ["cube", "kuhn5"])
+def test_patch_gather_replay_matches_oracle(hostcheck, cube, model, mesh):
+    """The default GPU schedule of the Jacobian pass, replayed on the CPU: the patch schedule built by the product's
+    host code and interpreted like patch_gather_kernel (record slots from the bulk-copy runs, work items, partial
+    sums, one writer per block) with the device's element math -> the oracle's operator, primal and transposed."""
+    co, cn = (cube["coords"], cube["tets"]) if mesh == "cube" else kuhn_cube(5)
+    co, cn = np.ascontiguousarray(co, dtype=np.float64), np.ascontiguousarray(cn, dtype=np.int32)
+    f = fields(co, len(cn), strain=0.004)
+    o = Oracle(co, cn, model, [MATERIAL])
+    o.set_solution(f["u"], f["p"])
+    if model == "J2":
+        o.state("Fp_old")[:] = f["Fp_old"]
+        o.state("eqps_old")[:] = f["eqps_old"]
+    mat = np.array(MATERIAL)
+    u, p = np.ascontiguousarray(f["u"]), np.ascontiguousarray(f["p"])
+    eqo, Fpo = np.ascontiguousarray(f["eqps_old"]), np.ascontiguousarray(f["Fp_old"])
+    for mode, tr in ((PRIMAL, 0), (ADJOINT, 1)):
+        Ro, Ao = o.jacobian(mode, save=False)
+        R, A, npch = np.zeros(4 * len(co)), np.zeros(o.nnz), C.c_int32(0)
+        rc = hostcheck.hc_patch_gather(0 if model == "neohookean" else 1, tr, len(co), len(cn), ip(cn), dp(co), dp(mat), dp(u), dp(p),
+                                       dp(eqo), dp(Fpo), dp(R), dp(A), C.byref(npch))
+        assert rc == 0 and npch.value >= 1
+        assert relerr(A, Ao) < 1e-12 and relerr(R, Ro) < 1e-12
