@@ -291,7 +291,7 @@ def run_b200(args):
         "plastic_fraction": plastic / ne_local, "colours": a.num_colors,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                      "traffic": traffic, "peak_source": peak_src,
-                     "kernel": f"gx::elem_record_kernel<{args.model},save> + gx::patch_gather_kernel<primal> "
+                     "kernel": f"gx::elem_record_kernel<{args.model},save> + gx::patch_pair_kernel<primal> "
                                "(the two launches of one Jacobian pass; achieved = B_alg * elements / their summed device time)",
                      "kernel_ms_per_pass": k_ms, "zero_ms_per_pass": statistics.mean(zero_ms),
                      "exchange_ms_per_pass": statistics.mean(exch_ms),

@@ -315,75 +315,11 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
-  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj; P.fold_ord = ctx->d_fold_ord; P.nblk_g = ctx->nnz_x != ctx->nnz ? ctx->d_nblk_g : nullptr; P.fold_ld = ctx->fold_ld; P.node_order = ctx->d_node_order;
+  P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
   P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
   P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
-}
-
-static size_t row_owner_smem(gx_ctx const* ctx, int warps) {
-  return row_owner_smem_per_warp(ctx->max_nblk) * warps;
-}
-
-template <int MODEL, bool TRANSPOSE, bool SAVE>
-static cudaError_t launch_row_owner(gx_ctx* ctx, KParams& P) {
-  int const warps = (int)ctx->opt_row_warps;
-  size_t const smem = row_owner_smem(ctx, warps);
-  // 128-thread blocks; MINB blocks/SM bounds the registers: 2 -> 255, 3 -> 168 (12 warps/SM), 4 -> 128 (16 warps/SM)
-  auto kern = ctx->opt_row_minblocks == 4   ? row_owner_kernel<MODEL, TRANSPOSE, SAVE, 4>
-              : ctx->opt_row_minblocks == 3 ? row_owner_kernel<MODEL, TRANSPOSE, SAVE, 3>
-                                            : row_owner_kernel<MODEL, TRANSPOSE, SAVE, 2>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  kern<<<(ctx->nn + warps - 1) / warps, warps * 32, smem, ctx->stream>>>(P);
-  ctx->launches++;
-  return cudaGetLastError();
-}
-
-// two-kernel row-owner pass: element records, then node rows
-template <int MODEL>
-static cudaError_t launch_two_stage(gx_ctx* ctx, KParams& P, int pass, bool save) {
-  int const ne = ctx->ne;
-  if (save) elem_record_kernel<MODEL, true><<<(ne + 63) / 64, 64, 0, ctx->stream>>>(P, ctx->d_elemrec, ne);
-  else elem_record_kernel<MODEL, false><<<(ne + 63) / 64, 64, 0, ctx->stream>>>(P, ctx->d_elemrec, ne);
-  ctx->launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  int const warps = (int)ctx->opt_row_warps;
-  bool const tr = pass == PASS_JACOBIAN_T;
-  int const mb = (int)ctx->opt_fold_minblocks;
-  bool const sorted = ctx->opt_fold_sorted != 0;
-  if (sorted) {  // nodes with <= 32 incidences
-    size_t const smem = (size_t)64 * ctx->fold_ld * sizeof(double) * warps;
-    auto kern = tr ? (mb == 4 ? row_fold_sorted_kernel<true, 4> : mb == 3 ? row_fold_sorted_kernel<true, 3> : row_fold_sorted_kernel<true, 2>)
-                   : (mb == 4 ? row_fold_sorted_kernel<false, 4> : mb == 3 ? row_fold_sorted_kernel<false, 3> : row_fold_sorted_kernel<false, 2>);
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    int per_sm = 1;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
-    if (e != cudaSuccess) return e;
-    int const blocks = std::max(1, std::min((ctx->nn + warps - 1) / warps, ctx->num_sms * std::max(per_sm, 1) * (int)ctx->opt_fold_waves));
-    kern<<<blocks, warps * 32, smem, ctx->stream>>>(P, ctx->d_elemrec);
-    ctx->launches++;
-    e = cudaGetLastError();
-    if (e != cudaSuccess || ctx->max_deg <= 32) return e;
-  }
-  // generic fold: every node (sorted == 0) or only the nodes with more than 32 incidences
-  P.e0 = sorted ? 33 : 0;  // minimum number of incidences this launch handles
-  size_t const smem = row_owner_smem(ctx, warps);
-  auto kern = tr ? (mb == 4 ? row_fold_kernel<true, 4> : mb == 3 ? row_fold_kernel<true, 3> : row_fold_kernel<true, 2>)
-                 : (mb == 4 ? row_fold_kernel<false, 4> : mb == 3 ? row_fold_kernel<false, 3> : row_fold_kernel<false, 2>);
-  e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  // persistent warps: as many blocks as fit on the device at once (a multiple of the SM count)
-  int per_sm = 1;
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, warps * 32, smem);
-  if (e != cudaSuccess) return e;
-  int const blocks = std::max(1, std::min((ctx->nn + warps - 1) / warps, ctx->num_sms * std::max(per_sm, 1) * (int)ctx->opt_fold_waves));
-  kern<<<blocks, warps * 32, smem, ctx->stream>>>(P, ctx->d_elemrec);
-  ctx->launches++;
-  return cudaGetLastError();
 }
 
 // patch-gather form of the Jacobian pass: element records, then one thread block per patch
@@ -396,7 +332,7 @@ static cudaError_t launch_patch_gather(gx_ctx* ctx, KParams& P, int pass, bool s
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || ctx->n_patches == 0) return e;
   bool const tr = pass == PASS_JACOBIAN_T;
-  auto kern = tr ? patch_gather_kernel<true> : patch_gather_kernel<false>;
+  auto kern = tr ? patch_pair_kernel<true> : patch_pair_kernel<false>;
   size_t const smem = patch_smem_bytes();
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
@@ -407,7 +343,7 @@ static cudaError_t launch_patch_gather(gx_ctx* ctx, KParams& P, int pass, bool s
 
 static int upload_patch_schedule(gx_ctx* ctx) {
   if (ctx->patch_state != 0) return GX_OK;
-  if (!build_patch_schedule(ctx)) return GX_OK;  // patch_state = -1: the caller falls back to the row fold
+  if (!build_patch_schedule(ctx)) return GX_OK;  // patch_state = -1: the caller falls back to the coloured schedule
   if (ctx->d_patch_sched) { cudaFree(ctx->d_patch_sched); ctx->d_patch_sched = nullptr; }
   GX_CUDA(cudaMalloc(&ctx->d_patch_sched, sizeof(uint32_t) * std::max<size_t>(ctx->patch_sched.size(), 1)));
   GX_CUDA(cudaMemcpy(ctx->d_patch_sched, ctx->patch_sched.data(), sizeof(uint32_t) * ctx->patch_sched.size(), cudaMemcpyHostToDevice));
@@ -431,12 +367,6 @@ static cudaError_t launch_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
   return cudaGetLastError();
 }
 
-template <int MODEL>
-static cudaError_t launch_row_owner_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
-  if (pass == PASS_JACOBIAN) return save ? launch_row_owner<MODEL, false, true>(ctx, P) : launch_row_owner<MODEL, false, false>(ctx, P);
-  return save ? launch_row_owner<MODEL, true, true>(ctx, P) : launch_row_owner<MODEL, true, false>(ctx, P);
-}
-
 static int status_of_element_error(int code) {
   switch (code) {
     case ERR_INVERTED_ELEMENT: return GX_ERR_INVERTED_ELEMENT;
@@ -456,24 +386,22 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaMemcpyAsync(ctx->d_err, zero2, sizeof zero2, cudaMemcpyHostToDevice, ctx->stream));
   GX_CUDA(cudaMemsetAsync(ctx->d_plastic, 0, sizeof(unsigned long long), ctx->stream));
   GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
-  bool const row_owner = with_values && ctx->opt_kernel != 1 &&
-                         row_owner_smem(ctx, (int)ctx->opt_row_warps) <= 200 * 1024;
-  bool patch_gather = with_values && ctx->opt_kernel == 3;
+  // Jacobian pass: patch schedule (default) unless the coloured fallback is asked for or the mesh does not fit
+  bool patch_gather = with_values && ctx->opt_kernel != 1;
   if (patch_gather) {
-    if (ctx->ne >= (1 << 27)) ctx->patch_state = -1;  // element ids no longer fit the schedule words: row fold instead
+    if (ctx->ne >= (1 << 27)) ctx->patch_state = -1;  // element ids no longer fit the schedule words: coloured schedule instead
     int const rc = upload_patch_schedule(ctx);
     if (rc) return rc;
     patch_gather = ctx->patch_state == 1;
   }
-  bool const two_stage = row_owner && (ctx->opt_kernel == 0 || (ctx->opt_kernel == 3 && !patch_gather));
   bool const gather = !with_values && ctx->opt_kernel != 1;
-  if ((two_stage || gather || patch_gather) && !ctx->d_elemrec)
+  if ((gather || patch_gather) && !ctx->d_elemrec)
     GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
   if (patch_gather)  // nodes without elements have no work item
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
-  if (!row_owner && !gather && !patch_gather) {
-    // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The row-owner schedule writes every
-    // entry of R and of the CRS values exactly once, so it needs no zeroing pass.
+  if (!gather && !patch_gather) {
+    // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The owner-computes schedules write every
+    // entry of R and of the CRS values exactly once, so they need no zeroing pass.
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
     if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz_x, ctx->stream));
   }
@@ -486,12 +414,6 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   else if (patch_gather)
     le = ctx->model == GX_MODEL_J2 ? launch_patch_gather<MODEL_J2>(ctx, P, pass, save)
                                    : launch_patch_gather<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
-  else if (two_stage)
-    le = ctx->model == GX_MODEL_J2 ? launch_two_stage<MODEL_J2>(ctx, P, pass, save)
-                                   : launch_two_stage<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
-  else if (row_owner)
-    le = ctx->model == GX_MODEL_J2 ? launch_row_owner_model<MODEL_J2>(ctx, P, pass, save)
-                                   : launch_row_owner_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   else
     le = ctx->model == GX_MODEL_J2 ? launch_model<MODEL_J2>(ctx, P, pass, save)
                                    : launch_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
@@ -547,7 +469,7 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
 static void free_device(gx_ctx* ctx) {
   if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
-  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_fold_ord, ctx->d_node_order, ctx->d_diag_pos,
+  void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_diag_pos,
                   ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -626,10 +548,6 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemcpy(ctx->d_adj_off, ctx->adj_off.data(), sizeof(uint32_t) * (size_t)(nn + 1), cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_diag_pos, (size_t)nn));
     GX_CUDA(cudaMemcpy(ctx->d_diag_pos, ctx->diag_pos.data(), (size_t)nn, cudaMemcpyHostToDevice));
-    GX_CUDA(cudaMalloc(&ctx->d_node_order, sizeof(int32_t) * (size_t)nn));
-    GX_CUDA(cudaMemcpy(ctx->d_node_order, ctx->node_order.data(), sizeof(int32_t) * (size_t)nn, cudaMemcpyHostToDevice));
-    GX_CUDA(cudaMalloc(&ctx->d_fold_ord, sizeof(uint32_t) * std::max<size_t>(ctx->fold_ord.size(), 1)));
-    GX_CUDA(cudaMemcpy(ctx->d_fold_ord, ctx->fold_ord.data(), sizeof(uint32_t) * ctx->fold_ord.size(), cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj, sizeof(int2) * ctx->adj.size()));
     GX_CUDA(cudaMemcpy(ctx->d_adj, ctx->adj.data(), sizeof(int2) * ctx->adj.size(), cudaMemcpyHostToDevice));
     // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
@@ -1177,10 +1095,9 @@ int gx_patch_schedule(gx_ctx* ctx, const uint32_t** words, int32_t dims[4]) {
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (!ctx || !key) return GX_ERR_ARG;
   std::string k(key);
-  if (k == "kernel") {  // Jacobian pass: 3 = element records + patch gather (default), 0 = element records + row fold,
-                        // 1 = coloured elements, 2 = fused row-owner
-    if (value < 0 || value > 3) { ctx->err = "kernel must be 0..3"; return GX_ERR_ARG; }
-    ctx->opt_kernel = value;
+  if (k == "kernel") {  // every pass: 0 = owner-computes schedules (default; 3 is accepted as an alias), 1 = coloured elements
+    if (value != 0 && value != 1 && value != 3) { ctx->err = "kernel must be 0 (owner-computes) or 1 (coloured)"; return GX_ERR_ARG; }
+    ctx->opt_kernel = value == 1 ? 1 : 0;
     return GX_OK;
   }
   if (k == "patch_schedule_dryrun") {  // host-side build of the patch schedule (works on host-only contexts); GX_SCHED_STATS prints its statistics
@@ -1188,30 +1105,6 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
     std::vector<uint32_t>().swap(ctx->patch_sched);
     ctx->patch_state = 0;
     if (!ok) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
-    return GX_OK;
-  }
-  if (k == "fold_waves") {
-    if (value < 1 || value > 64) { ctx->err = "fold_waves must be 1..64"; return GX_ERR_ARG; }
-    ctx->opt_fold_waves = value;
-    return GX_OK;
-  }
-  if (k == "fold_sorted") {
-    ctx->opt_fold_sorted = value != 0;
-    return GX_OK;
-  }
-  if (k == "fold_minblocks") {
-    if (value < 2 || value > 4) { ctx->err = "fold_minblocks must be 2, 3 or 4"; return GX_ERR_ARG; }
-    ctx->opt_fold_minblocks = value;
-    return GX_OK;
-  }
-  if (k == "row_minblocks") {
-    if (value < 2 || value > 4) { ctx->err = "row_minblocks must be 2, 3 or 4"; return GX_ERR_ARG; }
-    ctx->opt_row_minblocks = value;
-    return GX_OK;
-  }
-  if (k == "row_warps") {
-    if (value < 1 || value > 4) { ctx->err = "row_warps must be 1..4"; return GX_ERR_ARG; }
-    ctx->opt_row_warps = value;
     return GX_OK;
   }
   if (k == "block_size") {

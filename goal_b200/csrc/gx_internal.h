@@ -80,12 +80,6 @@ struct gx_ctx {
   std::vector<uint32_t> adj_off;  // [nn+1]
   std::vector<int2> adj;          // [4*ne]  x = e*4+n, y = block positions of (a, a_m), m = 0..3, one byte each
   int max_nblk = 0, max_deg = 0;
-  // sorted fold schedule of row_fold_sorted_kernel: node a's list starts at 4*adj_off[a] + 8*a; word 0 is the
-  // number of words, the words start at index 4 (padded to groups of four); each names two staged blocks with the same target block, one per half-warp:
-  //   staging offset (m*16*33 + lane) of each [11 bits each] | target block << 22 | last-word-of-block << 30.
-  // Only built for nodes with at most 32 incidences.
-  std::vector<uint32_t> fold_ord;
-  int fold_ld = 33;  // staging row stride the schedule was built for
   // order in which stage B visits the nodes: Morton (Z-curve) order of the node coordinates, so that the four
   // incidences of an element are processed close in time and its tangent record is fetched from HBM once
   std::vector<int32_t> node_order;
@@ -116,8 +110,6 @@ struct gx_ctx {
   int32_t* d_perm = nullptr;    // colour schedule: slot -> user element
   uint32_t* d_adj_off = nullptr;
   int2* d_adj = nullptr;
-  uint32_t* d_fold_ord = nullptr;
-  int32_t* d_node_order = nullptr;
   uint8_t* d_diag_pos = nullptr;   // position of block (a,a) in node a's block row
   uint32_t* d_patch_sched = nullptr;
   // history state, one record per element (user order):
@@ -162,12 +154,7 @@ struct gx_ctx {
   bool have_result = false;
   bool have_values = false;
   int64_t opt_block = 128;
-  int64_t opt_kernel = 3;  // Jacobian pass: 0 = element records + row fold, 1 = coloured elements, 2 = fused row-owner
-  int64_t opt_row_warps = 4;
-  int64_t opt_row_minblocks = 2;
-  int64_t opt_fold_minblocks = 3;
-  int64_t opt_fold_sorted = 1;
-  int64_t opt_fold_waves = 1;
+  int64_t opt_kernel = 0;  // 0 = owner-computes schedules (patch pairs / gather form), 1 = coloured elements
   int num_sms = 148;
   std::string err;
 };
@@ -193,15 +180,17 @@ bool build_patch_schedule(gx_ctx* c);
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
 #ifndef GX_PATCH_THREADS
 #define GX_PATCH_THREADS 128
-#define GX_PATCH_RECS 120
-#define GX_PATCH_MINB 4
+#define GX_PATCH_RECS 176
+#define GX_PATCH_MINB 3
 #endif
 constexpr int PATCH_THREADS = GX_PATCH_THREADS;  // work items per patch, one per thread
-constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (272 B each)
+constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (336 B each); slots are 8 bit
 constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_PARTS = 32;     // secondary items (partial sums handed to a primary) per patch
-constexpr int PATCH_WORDS = 4 + PATCH_RECS + 4 * PATCH_THREADS + 4 * PATCH_THREADS + 2 * PATCH_RECS;  // uint32 words per patch
+constexpr int PATCH_PART_LD = 36;   // doubles per partial sum: two 4x4 blocks + the residual entries
+constexpr int PATCH_WORDS = 4 + 4 * PATCH_THREADS + 4 * PATCH_THREADS + 2 * PATCH_RECS;  // uint32 words per patch
+static_assert(PATCH_RECS <= 256, "record slots are 8 bit");
 // gx_comm.cu
 void comm_destroy(gx_ctx*);
 int comm_setup_lists(gx_ctx*, const gx_desc*);

@@ -16,25 +16,27 @@
 //   state_out double[Ne][20]  sigma[9], eqps, Fp[9], pad                     160 B record
 //   R         double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
 //
-// Two schedules, both free of atomics on the data path and bit-reproducible:
-//  (1) row-owner (Jacobian pass; default in its two-kernel form, see (1b) below): one warp per node a, one lane per incident element
-//      (a, e).  Each lane evaluates its element and the four 4x4 blocks of node a's rows, the warp
-//      sums them per target block through shared memory in a fixed order and writes node a's four
-//      CRS rows exactly once, fully coalesced.  No zeroing pass, no read-modify-write traffic.
-//  (2) gather form of the residual / error-localisation passes (default): element residual vectors, then one
-//      thread per node sums its incidences.
-//  (3) coloured elements (fallback for every pass, gx_set_option("kernel", 1)): one thread per
-//      element, launches cover one colour (no two elements of a colour share a node), plain
-//      read-modify-write into R / values.
+// Schedules, all free of atomics on the data path and bit-reproducible:
+//  (1) Jacobian pass (default): stage A elem_record_kernel (one thread per element: stress update, state save, the
+//      element's 42-double tangent record, tangent_record.cuh) + stage B patch_pair_kernel (one thread block per patch
+//      of nodes: the patch's records staged in shared memory by bulk copies, one work item per thread -- an edge's two
+//      mirror blocks or a diagonal block with the node's residual entries -- accumulated in registers and written once).
+//      No zeroing pass, no read-modify-write traffic.
+//  (2) gather form of the residual / error-localisation passes (default): element residual vectors, then 8 lanes
+//      per node sum its incidences.
+//  (3) coloured elements (fallback for every pass, gx_set_option("kernel", 1), and for meshes with a node that does
+//      not fit a patch): one thread per element, launches cover one colour (no two elements of a colour share a
+//      node), plain read-modify-write into R / values.
 //
-// The element bodies are __host__ __device__ so that tests/hostcheck can run schedule (2) exactly as
-// written, launch order included, on the CPU (test-only; there is no CPU product path).
+// The element bodies are __host__ __device__ so that tests/hostcheck can run schedule (3) exactly as written, launch
+// order included, and replay schedule (1) from its schedule words on the CPU (test-only; there is no CPU product path).
 #pragma once
 
 #include <stdint.h>
 
 #include "element_math.cuh"
 #include "gx_internal.h"
+#include "tangent_record.cuh"
 
 namespace gx {
 
@@ -47,10 +49,6 @@ struct KParams {
   int32_t const* elems; // colour schedule: slot -> element
   uint32_t const* adj_off;
   int2 const* adj;
-  uint32_t const* fold_ord;
-  int32_t const* nblk_g;  // partitioned contexts: local (ghost) block count per node; blocks beyond it are phantom
-  int fold_ld;            // row stride of the sorted fold's staging array: odd, > max incidences per node (<= 33)
-  int32_t const* node_order;  // stage B visiting order (Z-curve)
   double const* state_in;
   double const* fp_old;
   double* state_out;
@@ -255,211 +253,13 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 }
 
 // ---------------------------------------------------------------------------
-// Schedule (1): row-owner Jacobian kernel.  Warp = node a; lane = incidence (a, e) with a = local
-// node n of e.  Lane work: element core, then for each column node m the 4x4 block
-//   PRIMAL : K[(n,.),(m,.)]           -> block (a, a_m) of node a's rows
-//   ADJOINT: K[(m,.),(n,.)]^T         -> block (a, a_m) of the transposed operator
-// staged in shared memory (stg[16][33]).  The blocks are then folded into the node's row accumulator
-// by a fixed schedule: half-warp h = 0/1 walks the staged blocks of the lower / upper half of the active
-// lanes in ascending lane order (= ascending element id), lane t of the half adding entry t of each block into its own
-// accumulator copy acc[h][16 j + t]; the two copies are summed at the end.  Every CRS entry is therefore
-// produced by one thread in a fixed order: deterministic, atomics-free, written exactly once.
-// Nodes with more than 32 incident elements take several rounds.
-// Shared memory per warp: stg 16*33*8 B + wr 24*32*8 B + acc 2*128*max_nblk B.
+// Schedule (1), the default Jacobian pass.
+//   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the element's
+//            tangent record (tangent_record.cuh: w_n and tqw_n per node, s, G, 14 scalars -- 42 doubles).
+//   stage B  patch_pair_kernel  : one thread block per patch of the schedule built by build_patch_schedule
+//            (gx_setup.cpp); see below.
 // ---------------------------------------------------------------------------
-GX_HD int std_min_int(int a, int b) { return a < b ? a : b; }
-constexpr int STG_LD = 33;
-constexpr int WR_LD = 32;  // per-lane spatial vectors w_n, r_n (n = 0..3): wr[24][32]
-GX_HD size_t row_owner_smem_per_warp(int max_nblk) {
-  return (size_t)(16 * STG_LD + 24 * WR_LD + 2 * 16 * max_nblk) * sizeof(double);
-}
-
-template <int MODEL, bool TRANSPOSE, bool SAVE, int MINB>
-__global__ void __launch_bounds__(128, MINB) row_owner_kernel(const __grid_constant__ KParams P) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int const half = lane >> 4, t16 = lane & 15;
-  double* stg = reinterpret_cast<double*>(smem_raw + row_owner_smem_per_warp(P.max_nblk) * wib);
-  double* wr = stg + 16 * STG_LD + lane;  // this lane's column of wr[24][32]: w_n[k] at 3n+k, r_n[k] at 12+3n+k
-  double* acc = stg + 16 * STG_LD + 24 * WR_LD;  // [2][16*max_nblk], block-major: acc[h][16 j + 4 i + k]
-  int const accld = 16 * P.max_nblk;
-
-  int const a = blockIdx.x * (blockDim.x >> 5) + wib;
-  if (a >= P.nn) return;  // whole warp exits together
-  uint32_t const o0 = __ldg(P.adj_off + a), o1 = __ldg(P.adj_off + a + 1);
-  int blk0a, nblka;
-  {
-    double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
-    blk0a = __double2loint(d3.y);
-    nblka = __double2hiint(d3.y);
-  }
-  int const nent = 16 * nblka;
-  for (int g = lane; g < nent; g += 32) { acc[g] = 0.0; acc[accld + g] = 0.0; }
-  double racc[4] = {0.0, 0.0, 0.0, 0.0};
-  int nplastic = 0;
-
-  for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
-    int const nact = min(32, (int)(o1 - r0));  // active lanes of this round: 0 .. nact-1
-    bool const active = lane < nact;
-    int n = 0, e = 0;
-    uint32_t jpack = 0;
-    Core<double> c;
-    bool ok = false;
-    if (active) {
-      int2 const ad = __ldg(P.adj + r0 + lane);
-      e = ad.x >> 2;
-      n = ad.x & 3; jpack = (uint32_t)ad.y;
-      int nd[4], b0[4], nb[4];
-      Material const* matp;
-      int const rc = load_and_update<MODEL, SAVE>(P, e, n == 0, nd, b0, nb, matp, c);
-      if (rc != ERR_NONE) report_error(P.err, rc, e);
-      ok = rc == ERR_NONE;
-      if (ok && n == 0) nplastic += c.plastic;
-      // park the 24 spatial vectors in shared memory: frees 48 registers for the phases and lets the
-      // run-time node indices (n, m) address them directly
-#pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          wr[(3 * q + k) * WR_LD] = c.w[q][k];
-          wr[(12 + 3 * q + k) * WR_LD] = c.r[q][k];
-        }
-    }
-    double wn[3], rn3[3];
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      wn[k] = wr[(3 * n + k) * WR_LD];
-      rn3[k] = wr[(12 + 3 * n + k) * WR_LD];
-    }
-    RowNode<double> rown;  // PRIMAL: this lane's row node
-    ColNode<double> coln;  // ADJOINT: this lane's column node
-    if (ok) {
-      double r4[4];
-      element_residual_row(c, wn, r4);
-      racc[0] += r4[0]; racc[1] += r4[1]; racc[2] += r4[2]; racc[3] += r4[3];
-      if (!TRANSPOSE) row_node(c, wn, rown);
-      else column_node(c, wn, rn3, coln);
-    }
-#pragma unroll 1
-    for (int m = 0; m < 4; ++m) {
-      uint32_t jm = 0;
-      if (ok) {
-        // column node m of this phase
-        double wm[3], rm[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          wm[k] = wr[(3 * m + k) * WR_LD];
-          rm[k] = wr[(12 + 3 * m + k) * WR_LD];
-        }
-        double blk[16];
-        if (!TRANSPOSE) {
-          ColNode<double> cnm;
-          column_node(c, wm, rm, cnm);
-          jacobian_block(c, rown, cnm, blk);
-#pragma unroll
-          for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = blk[t];
-        } else {
-          RowNode<double> rnm;
-          row_node(c, wm, rnm);
-          jacobian_block(c, rnm, coln, blk);
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) stg[(4 * i + k) * STG_LD + lane] = blk[4 * k + i];
-        }
-        jm = (jpack >> (8 * m)) & 0xffu;
-      } else if (active) {
-#pragma unroll
-        for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = 0.0;  // failed element: contributes nothing
-      }
-      __syncwarp();
-      // fold: the staged blocks of lanes [0, split) go to half-warp 0, [split, nact) to half-warp 1,
-      // each in ascending lane order; lane t of a half adds entry t of every block it walks
-      {
-        int const split = (nact + 1) >> 1;
-        int const lbase = half ? split : 0;
-        int const lend = half ? nact : split;
-        double* my = acc + half * accld + t16;
-#pragma unroll 4
-        for (int it = 0; it < split; ++it) {
-          int const l = lbase + it;
-          uint32_t const j = __shfl_sync(0xffffffffu, jm, l & 31);
-          if (l < lend) my[16 * j] += stg[t16 * STG_LD + l];
-        }
-      }
-      __syncwarp();
-    }
-    if (SAVE && MODEL == MODEL_J2 && ok && n == 0 && c.plastic) save_plastic_Fp(P, e, c.dN);
-  }
-  // ---- R rows of node a: fixed butterfly over the lanes
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    double v = racc[i];
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    racc[i] = v;
-  }
-  if (lane == 0) {
-    double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
-    q[0] = make_double2(racc[0], racc[1]);
-    q[1] = make_double2(racc[2], racc[3]);
-  }
-  // ---- node a's four CRS rows, written once: row i = [4 nblk] contiguous doubles, gathered from the
-  //      block-major accumulators acc[h][16 j + 4 i + k]
-  double* out = P.values + 16 * (int64_t)blk0a;
-  int const rl = 4 * nblka;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    for (int cidx = lane; cidx < rl; cidx += 32) {
-      int const g = 16 * (cidx >> 2) + 4 * i + (cidx & 3);
-      out[i * rl + cidx] = acc[g] + acc[accld + g];
-    }
-  if (MODEL == MODEL_J2) {
-    unsigned const tot = __reduce_add_sync(0xffffffffu, (unsigned)nplastic);
-    if (lane == 0 && tot) atomicAdd(P.plastic, (unsigned long long)tot);
-  }
-}
-
-// ---------------------------------------------------------------------------
-// Schedule (1b), the default Jacobian pass: the row-owner schedule split in two kernels so that the
-// element core is evaluated once per element instead of once per incidence.
-//   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the
-//            34-double "tangent record" of the element (everything the 4x4 blocks are built from):
-//              w_n[3] x 4 nodes | s[6] | q[3] gwv A1v Jpv upc va tjv ppc vb gNs vgr rb rc1 tb3
-//            (r_n = F Cp^{-1} G_n is not stored: r_n = rc1 (s w_n) + tb3 w_n, element_math.cuh node_r)
-//   stage B  row_fold_kernel    : one warp per node, one lane per incidence.  Each lane reads its
-//            element's record (272 B, contiguous), builds the four blocks of the node's rows, and the
-//            warp folds and writes the node's CRS rows once, exactly like row_owner_kernel.
-// Costs 272 B written + read per element of extra HBM traffic and removes 3 of the 4 evaluations of the
-// element core (about 60 % of all instructions of the fused kernel).
-// ---------------------------------------------------------------------------
-constexpr int ELEM_REC = 34;  // doubles; 272 B = 17 x 16 B: an odd number of 16 B chunks, see patch_gather_kernel
-
-// chunks 6..16 of a record (16 B each) -> the tangent fields of Core
-template <bool GLOBAL>
-__device__ __forceinline__ void unpack_tangent(double2 const* q, Core<double>& c) {
-  auto ld = [&](int k) { return GLOBAL ? __ldg(q + k) : q[k]; };
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { double2 const v = ld(6 + k); c.s[2 * k] = v.x; c.s[2 * k + 1] = v.y; }
-  double2 v = ld(9); c.q[0] = v.x; c.q[1] = v.y;
-  v = ld(10); c.q[2] = v.x; c.gwv = v.y;
-  v = ld(11); c.A1v = v.x; c.Jpv = v.y;
-  v = ld(12); c.upc = v.x; c.va = v.y;
-  v = ld(13); c.tjv = v.x; c.ppc = v.y;
-  v = ld(14); c.vb = v.x; c.gNs = v.y;
-  v = ld(15); c.vgr = v.x; c.rb = v.y;
-  v = ld(16); c.rc1 = v.x; c.tb3 = v.y;
-}
-// chunks 0..5 of a record -> w_n of the four nodes
-template <bool GLOBAL>
-__device__ __forceinline__ void unpack_w(double2 const* q, double wv[4][3]) {
-  auto ld = [&](int k) { return GLOBAL ? __ldg(q + k) : q[k]; };
-  double2 const v0 = ld(0), v1 = ld(1), v2 = ld(2), v3 = ld(3), v4 = ld(4), v5 = ld(5);
-  wv[0][0] = v0.x; wv[0][1] = v0.y; wv[0][2] = v1.x;
-  wv[1][0] = v1.y; wv[1][1] = v2.x; wv[1][2] = v2.y;
-  wv[2][0] = v3.x; wv[2][1] = v3.y; wv[2][2] = v4.x;
-  wv[3][0] = v4.y; wv[3][1] = v5.x; wv[3][2] = v5.y;
-}
+constexpr int ELEM_REC = TREC;  // doubles; 336 B = 21 x 16 B: an odd number of 16 B chunks, see patch_pair_kernel
 
 // Warp-cooperative Fp update of 32 consecutive elements e0 .. e0+nrec-1 (lane = element), plastic branch only:
 // Fp = exp(dgam N) Fp_old (goal_J2.cpp:128-131); on the elastic branch the reference leaves Fp untouched (:135-136).
@@ -527,15 +327,12 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
       for (int k = 0; k < ELEM_REC; ++k) mine[k] = 0.0;
     } else {
       plastic = c.plastic;
+      {
+        double r[ELEM_REC];
+        pack_trec(c, r);
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int k = 0; k < 3; ++k) mine[3 * q + k] = c.w[q][k];
-#pragma unroll
-      for (int k = 0; k < 6; ++k) mine[12 + k] = c.s[k];
-      mine[18] = c.q[0]; mine[19] = c.q[1]; mine[20] = c.q[2]; mine[21] = c.gwv; mine[22] = c.A1v; mine[23] = c.Jpv;
-      mine[24] = c.upc; mine[25] = c.va; mine[26] = c.tjv; mine[27] = c.ppc; mine[28] = c.vb; mine[29] = c.gNs;
-      mine[30] = c.vgr; mine[31] = c.rb; mine[32] = c.rc1; mine[33] = c.tb3;
+        for (int k = 0; k < ELEM_REC; ++k) mine[k] = r[k];
+      }
       if (SAVE && MODEL == MODEL_J2 && plastic) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) dN[k] = c.dN[k];
@@ -563,395 +360,45 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
 }
 
 
-template <bool TRANSPOSE, int MINB>
-__global__ void __launch_bounds__(128, MINB) row_fold_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int const half = lane >> 4, t16 = lane & 15;
-  double* stg = reinterpret_cast<double*>(smem_raw + row_owner_smem_per_warp(P.max_nblk) * wib);
-  double* wr = stg + 16 * STG_LD + lane;
-  double* acc = stg + 16 * STG_LD + 24 * WR_LD;  // [2][16*max_nblk], one copy per half-warp
-  int const accld = 16 * P.max_nblk;
-
-  // Persistent warps: warp gw handles nodes gw, gw + W, gw + 2W, ...  The node -> incidence -> record chain is
-  // three dependent global loads; it is software-pipelined across nodes: while node a is processed the
-  // incidences of node a + 2W are being loaded and the records of node a + W are being pulled into L2.
-  int const W = gridDim.x * (blockDim.x >> 5);
-  int slot = blockIdx.x * (blockDim.x >> 5) + wib;  // position in the visiting order
-  int a = 0, ap = 0;
-  uint32_t o0 = 0, o1 = 0, p0 = 0, p1 = 0;
-  int2 ad = make_int2(0, 0), adp = make_int2(0, 0);
-  if (slot < P.nn) {
-    a = __ldg(P.node_order + slot);
-    o0 = __ldg(P.adj_off + a); o1 = __ldg(P.adj_off + a + 1);
-    if (o0 + lane < o1) ad = __ldg(P.adj + o0 + lane);
-  }
-  if (slot + W < P.nn) {
-    ap = __ldg(P.node_order + slot + W);
-    p0 = __ldg(P.adj_off + ap); p1 = __ldg(P.adj_off + ap + 1);
-    if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
-  }
-  for (; slot < P.nn; slot += W) {
-    // stage 1 of the pipeline: records of the next node -> L2 (3 lines cover the 272 B record)
-    if (p0 + lane < p1) {
-      char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
-#pragma unroll
-      for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
-    }
-    // stage 0: incidences of the node after next
-    uint32_t q0 = 0, q1 = 0;
-    int aq = 0;
-    int2 adq = make_int2(0, 0);
-    if (slot + 2 * W < P.nn) {
-      aq = __ldg(P.node_order + slot + 2 * W);
-      q0 = __ldg(P.adj_off + aq); q1 = __ldg(P.adj_off + aq + 1);
-      if (q0 + lane < q1) adq = __ldg(P.adj + q0 + lane);
-    }
-    if ((int)(o1 - o0) >= P.e0) {  // nodes below the threshold are left to row_fold_sorted_kernel
-      int blk0a, nblka;
-      {
-        double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
-        blk0a = __double2loint(d3.y);
-        nblka = __double2hiint(d3.y);
-      }
-      int const nent = 16 * nblka;
-      for (int g = lane; g < nent; g += 32) { acc[g] = 0.0; acc[accld + g] = 0.0; }
-      double racc[4] = {0.0, 0.0, 0.0, 0.0};
-
-      for (uint32_t r0 = o0; r0 < o1; r0 += 32) {
-        int const nact = min(32, (int)(o1 - r0));
-        bool const active = lane < nact;
-        int n = 0;
-        uint32_t jpack = 0;
-        Core<double> c;  // only the tangent fields are filled
-        if (active) {
-          int2 const adr = r0 == o0 ? ad : __ldg(P.adj + r0 + lane);
-          int const e = adr.x >> 2;
-          n = adr.x & 3; jpack = (uint32_t)adr.y;
-          double2 const* q = reinterpret_cast<double2 const*>(rec + (int64_t)ELEM_REC * e);
-          unpack_tangent<true>(q, c);
-          double wv[4][3];
-          unpack_w<true>(q, wv);
-#pragma unroll
-          for (int n4 = 0; n4 < 4; ++n4) {  // w, r -> shared memory (this lane's column)
-            double sw[3], r3[3];
-            node_r(c, wv[n4], sw, r3);
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { wr[(6 * n4 + k) * WR_LD] = wv[n4][k]; wr[(6 * n4 + 3 + k) * WR_LD] = r3[k]; }
-          }
-        }
-        double wn[3], rn3[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          wn[k] = wr[(6 * n + k) * WR_LD];
-          rn3[k] = wr[(6 * n + 3 + k) * WR_LD];
-        }
-        RowNode<double> rown;
-        ColNode<double> coln;
-        if (active) {
-          double r4[4];
-          element_residual_row(c, wn, r4);
-          racc[0] += r4[0]; racc[1] += r4[1]; racc[2] += r4[2]; racc[3] += r4[3];
-          if (!TRANSPOSE) row_node(c, wn, rown);
-          else column_node(c, wn, rn3, coln);
-        }
-#pragma unroll 1
-        for (int m = 0; m < 4; ++m) {
-          uint32_t jm = 0;
-          if (active) {
-            double wm[3], rm[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-              wm[k] = wr[(6 * m + k) * WR_LD];
-              rm[k] = wr[(6 * m + 3 + k) * WR_LD];
-            }
-            double blk[16];
-            if (!TRANSPOSE) {
-              ColNode<double> cnm;
-              column_node(c, wm, rm, cnm);
-              jacobian_block(c, rown, cnm, blk);
-#pragma unroll
-              for (int t = 0; t < 16; ++t) stg[t * STG_LD + lane] = blk[t];
-            } else {
-              RowNode<double> rnm;
-              row_node(c, wm, rnm);
-              jacobian_block(c, rnm, coln, blk);
-#pragma unroll
-              for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int k = 0; k < 4; ++k) stg[(4 * i + k) * STG_LD + lane] = blk[4 * k + i];
-            }
-            jm = (jpack >> (8 * m)) & 0xffu;
-          }
-          __syncwarp();
-          {
-            int const split = (nact + 1) >> 1;
-            int const lbase = half ? split : 0;
-            int const lend = half ? nact : split;
-            double* my = acc + half * accld + t16;
-#pragma unroll 4
-            for (int it = 0; it < split; ++it) {
-              int const l = lbase + it;
-              uint32_t const j = __shfl_sync(0xffffffffu, jm, l & 31);
-              if (l < lend) my[16 * j] += stg[t16 * STG_LD + l];
-            }
-          }
-          __syncwarp();
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double v = racc[i];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        racc[i] = v;
-      }
-      if (lane == 0) {
-        double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
-        q[0] = make_double2(racc[0], racc[1]);
-        q[1] = make_double2(racc[2], racc[3]);
-      }
-      double* out = P.values + 16 * (int64_t)blk0a;
-      int const rl = 4 * nblka;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        for (int cidx = lane; cidx < rl; cidx += 32) {
-          int const g = 16 * (cidx >> 2) + 4 * i + (cidx & 3);
-          out[i * rl + cidx] = acc[g] + acc[accld + g];
-        }
-      __syncwarp();
-    }
-    a = ap; o0 = p0; o1 = p1; ad = adp;
-    ap = aq; p0 = q0; p1 = q1; adp = adq;
-  }
-}
-
-// Stage B, sorted fold (nodes with at most 32 incidences -- every node of a Kuhn mesh).  All four blocks of
-// every incidence are staged (stg4[64][33] per warp); then the warp walks the node's precomputed schedule
-// (KParams::fold_ord, gx_setup.cpp): the staged blocks grouped by target block, two per word.  Half-warp 0
-// takes the first block of a word, half-warp 1 the second; lane t accumulates entry t in a register.  At the
-// end of a group the two halves are joined by one shuffle and half-warp 0 stores the finished 4x4 block
-// straight into the CRS rows.  Control flow is warp-uniform; no accumulator array, no zeroing, no second pass.
-GX_HD int fold_row_stride(int max_deg) {  // staging row stride: one pad column past the widest node, odd, <= 33
-  int const ld = (std_min_int(max_deg, 32) + 1) | 1;
-  return ld;
-}
-GX_HD size_t row_fold_smem_per_warp(int max_nblk, int fold_ld, bool need_generic) {
-  size_t const sorted = (size_t)64 * fold_ld * sizeof(double);
-  size_t const generic = need_generic ? row_owner_smem_per_warp(max_nblk) : 0;
-  return sorted > generic ? sorted : generic;
-}
-
-template <bool TRANSPOSE, int MINB>
-__global__ void __launch_bounds__(128, MINB) row_fold_sorted_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int const half = lane >> 4, t16 = lane & 15;
-  int const ld = P.fold_ld;
-  double* stg = reinterpret_cast<double*>(smem_raw + (size_t)64 * ld * sizeof(double) * wib);
-  stg[lane * ld + ld - 1] = 0.0;         // pad column: the schedule's "no block" slot reads as zero
-  stg[(32 + lane) * ld + ld - 1] = 0.0;
-
-  // persistent warps with the same three-deep software pipeline as row_fold_kernel
-  int const W = gridDim.x * (blockDim.x >> 5);
-  int slot = blockIdx.x * (blockDim.x >> 5) + wib;  // position in the visiting order
-  int a = 0, ap = 0;
-  uint32_t o0 = 0, o1 = 0, p0 = 0, p1 = 0;
-  int2 ad = make_int2(0, 0), adp = make_int2(0, 0);
-  if (slot < P.nn) {
-    a = __ldg(P.node_order + slot);
-    o0 = __ldg(P.adj_off + a); o1 = __ldg(P.adj_off + a + 1);
-    if (o0 + lane < o1) ad = __ldg(P.adj + o0 + lane);
-  }
-  if (slot + W < P.nn) {
-    ap = __ldg(P.node_order + slot + W);
-    p0 = __ldg(P.adj_off + ap); p1 = __ldg(P.adj_off + ap + 1);
-    if (p0 + lane < p1) adp = __ldg(P.adj + p0 + lane);
-  }
-  for (; slot < P.nn; slot += W) {
-    if (p0 + lane < p1) {
-      char const* r = reinterpret_cast<char const*>(rec + (int64_t)ELEM_REC * (adp.x >> 2));
-#pragma unroll
-      for (int k = 0; k < 3; ++k) asm volatile("prefetch.global.L2 [%0];" ::"l"(r + 128 * k));
-    }
-    if (lane < 4 && p1 - p0 <= 32) {  // next node's schedule (at most 132 words) -> L2
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.fold_ord + 4 * (int64_t)p0 + 8 * (int64_t)ap + 32 * lane));
-    }
-    uint32_t q0 = 0, q1 = 0;
-    int aq = 0;
-    int2 adq = make_int2(0, 0);
-    if (slot + 2 * W < P.nn) {
-      aq = __ldg(P.node_order + slot + 2 * W);
-      q0 = __ldg(P.adj_off + aq); q1 = __ldg(P.adj_off + aq + 1);
-      if (q0 + lane < q1) adq = __ldg(P.adj + q0 + lane);
-    }
-    int const deg = (int)(o1 - o0);
-    if (deg <= 32) {  // larger nodes are handled by row_fold_kernel
-      int blk0a, nblka;
-      {
-        double2 const d3 = __ldg(reinterpret_cast<double2 const*>(P.nodes + a) + 3);
-        blk0a = __double2loint(d3.y);
-        nblka = __double2hiint(d3.y);
-      }
-      uint4 const* ord = reinterpret_cast<uint4 const*>(P.fold_ord + 4 * (int64_t)o0 + 8 * (int64_t)a);
-      int nw = 0;
-      uint32_t const nop = (uint32_t)(ld - 1) | ((uint32_t)(ld - 1) << 11);
-      uint4 wq = make_uint4(nop, nop, nop, nop);
-      if (deg > 0) { nw = (int)__ldg(reinterpret_cast<uint32_t const*>(ord)); wq = __ldg(ord + 1); }  // issued early
-      double r4[4] = {0.0, 0.0, 0.0, 0.0};
-      if (lane < deg) {
-        int const e = ad.x >> 2, n = ad.x & 3;
-        double2 const* q = reinterpret_cast<double2 const*>(rec + (int64_t)ELEM_REC * e);
-        Core<double> c;  // only the tangent fields are filled
-        double wv[4][3], rv[4][3];
-        unpack_tangent<true>(q, c);
-        unpack_w<true>(q, wv);
-#pragma unroll
-        for (int n4 = 0; n4 < 4; ++n4) { double sw[3]; node_r(c, wv[n4], sw, rv[n4]); }
-        double wn[3], rn3[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          wn[k] = n == 0 ? wv[0][k] : n == 1 ? wv[1][k] : n == 2 ? wv[2][k] : wv[3][k];
-          rn3[k] = n == 0 ? rv[0][k] : n == 1 ? rv[1][k] : n == 2 ? rv[2][k] : rv[3][k];
-        }
-        element_residual_row(c, wn, r4);
-        RowNode<double> rown;
-        ColNode<double> coln;
-        if (!TRANSPOSE) row_node(c, wn, rown);
-        else column_node(c, wn, rn3, coln);
-#pragma unroll
-        for (int m = 0; m < 4; ++m) {
-          double blk[16];
-          double* dst = stg + (m * 16) * ld + lane;
-          if (!TRANSPOSE) {
-            ColNode<double> cnm;
-            column_node(c, wv[m], rv[m], cnm);
-            jacobian_block(c, rown, cnm, blk);
-#pragma unroll
-            for (int t = 0; t < 16; ++t) dst[t * ld] = blk[t];
-          } else {
-            RowNode<double> rnm;
-            row_node(c, wv[m], rnm);
-            jacobian_block(c, rnm, coln, blk);
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-              for (int k = 0; k < 4; ++k) dst[(4 * i + k) * ld] = blk[4 * k + i];
-          }
-        }
-      }
-      __syncwarp();
-      // ---- R rows of node a: fixed butterfly over the lanes
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        double v = r4[i];
-#pragma unroll
-        for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-        r4[i] = v;
-      }
-      if (lane == 0) {
-        double2* q = reinterpret_cast<double2*>(P.R + 4 * (int64_t)a);
-        q[0] = make_double2(r4[0], r4[1]);
-        q[1] = make_double2(r4[2], r4[3]);
-      }
-      // ---- sorted fold, warp-uniform control flow
-      double const* src = stg + t16 * ld;
-      double* out = P.values + 16 * (int64_t)blk0a + (int64_t)(t16 >> 2) * (4 * nblka) + (t16 & 3);
-      int const sh = half ? 11 : 0;
-      double acc = 0.0;
-      for (int i = 0; i < nw; i += 4) {
-        uint4 const w = wq;
-        if (i + 4 < nw) wq = __ldg(ord + 2 + (i >> 2));  // next group, in flight while this one is folded
-        // the four staged values first (independent shared loads), then the dependent adds
-        double const v0 = src[(w.x >> sh) & 0x7ffu], v1 = src[(w.y >> sh) & 0x7ffu];
-        double const v2 = src[(w.z >> sh) & 0x7ffu], v3 = src[(w.w >> sh) & 0x7ffu];
-        uint32_t const ws[4] = {w.x, w.y, w.z, w.w};
-        double const vs[4] = {v0, v1, v2, v3};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          acc += vs[k];
-          if (ws[k] & 0x40000000u) {  // same word in every lane: uniform branch
-            double const tot = acc + __shfl_xor_sync(0xffffffffu, acc, 16);
-            if (half == 0) out[4 * ((ws[k] >> 22) & 0xffu)] = tot;
-            acc = 0.0;
-          }
-        }
-      }
-      // phantom blocks (columns that live only on other parts) receive remote contributions later: start at zero
-      if (P.nblk_g)
-        for (int j = __ldg(P.nblk_g + a) + half; j < nblka; j += 2) out[4 * j] = 0.0;
-      __syncwarp();
-    }
-    a = ap; o0 = p0; o1 = p1; ad = adp;
-    ap = aq; p0 = q0; p1 = q1; adp = adq;
-  }
-}
-
 // ---------------------------------------------------------------------------
-// Schedule (1c), patch gather (option kernel = 3): stage A as above, then one thread block per patch of the
-// precomputed patch schedule (build_patch_schedule, gx_setup.cpp).  The block stages the records of the patch's
-// elements in shared memory with bulk asynchronous copies (cp.async.bulk, one per record: every record crosses
-// the L1 data pipe once per patch instead of once per incident node and lane), then every thread runs one work item: up to 8 contributions to
-// one 4x4 block, rebuilt from the staged records and accumulated in registers.  Blocks with more contributions
-// are finished by their primary item from the secondaries' partial sums (fixed order).  Every block of the patch's
-// rows, and the rows' residual entries, are written exactly once.
+// Stage B: one thread block per patch of the precomputed patch schedule (build_patch_schedule, gx_setup.cpp).
+// The block stages the tangent records of the patch's elements in shared memory with bulk asynchronous copies
+// (cp.async.bulk, one per run of consecutive elements, completion on an mbarrier: every record crosses the L1 data
+// pipe once per patch instead of once per incident node and lane), then every thread runs one work item:
+//   PAIR : the elements around one mesh edge (a,b).  Per element the two node quadruples, s, G and the scalars are
+//          read once (16 128-bit shared loads) and give BOTH mirror blocks (a,b) and (b,a), which share the node
+//          vectors s w, G w and the symmetric scalars -- 32 accumulators in registers;
+//   DIAG : the elements around one node: block (a,a) and the node's four residual entries;
+//   ZERO : a phantom block of a partitioned context, written as zeros.
+// Lists longer than PATCH_ITEM_LEN are finished by their primary item from the secondaries' partial sums (fixed
+// order).  Every block of the operator, and every residual entry, is written exactly once.
+// Bank conflicts: record stride 21 x 16 B (odd), so the bank group of chunk k of the record in slot s is
+// (5 s + k) mod 8; the host schedule gives the 8 lanes of a quarter-warp records in 8 different groups where it can.
 // ---------------------------------------------------------------------------
-constexpr int PATCH_REC_LD = ELEM_REC;  // staged records keep their global stride: 272 B = 17 x 16 B (odd), so the bank
-                                        // group of a record's chunk k is (slot + k) mod 8
-GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * 20) * sizeof(double); }
+constexpr int PATCH_REC_LD = ELEM_REC;
+GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * PATCH_PART_LD) * sizeof(double); }
 
-// One work item: up to PATCH_ITEM_LEN contributions to one 4x4 block (and, for diagonal items, to the node's residual
-// entries), rebuilt from the records staged at srec and accumulated in registers.
-template <bool TRANSPOSE>
-__device__ __forceinline__ void patch_item(double const* srec, uint4 const it, bool const diag, double acc[16], double r4[4]) {
+#if defined(__CUDACC__)
+// the pieces of a staged record as registers (128-bit shared loads)
+struct TRegs { double s[6], G[6], sc[14]; };
+__device__ __forceinline__ void trec_load_common(double2 const* q, TRegs& t, bool want_resid) {
 #pragma unroll
-  for (int k = 0; k < 16; ++k) acc[k] = 0.0;
-  r4[0] = r4[1] = r4[2] = r4[3] = 0.0;
-  uint64_t elo = (uint64_t)it.x | ((uint64_t)it.y << 32), ehi = (uint64_t)it.z | ((uint64_t)it.w << 32);
-#pragma unroll 1
-  for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
-    uint32_t const ent = (uint32_t)elo & 0xffffu;
-    elo = (elo >> 16) | (ehi << 48); ehi >>= 16;
-    if (!(ent & 0x8000u)) {  // an empty round of this item (bank-conflict avoidance), or the end of its list
-      if ((elo | ehi) == 0) break;
-      continue;
-    }
-    int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
-    double const* rp = srec + slot * PATCH_REC_LD;
-    Core<double> c;  // only the tangent fields are filled
-    unpack_tangent<false>(reinterpret_cast<double2 const*>(rp), c);
-    // Every lane reads the same 17 chunks of its record, so a quarter-warp whose records sit in 8 different bank
-    // groups (the host schedule sees to that) reads without conflicts; the two nodes the block needs are then
-    // selected in registers.  (Loading only w_n / w_m would put the chunk offset, and with it the bank group,
-    // at the mercy of the local node numbers.)
-    double wv[4][3];
-    unpack_w<false>(reinterpret_cast<double2 const*>(rp), wv);
-    // row node = the node of this block row in the primal operator; roles swap for the transpose
-    int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
-    double wr[3], wc[3];
+  for (int k = 0; k < 3; ++k) { double2 const v = q[8 + k]; t.s[2 * k] = v.x; t.s[2 * k + 1] = v.y; }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      double const a01 = (nr & 1) ? wv[1][k] : wv[0][k], a23 = (nr & 1) ? wv[3][k] : wv[2][k];
-      wr[k] = (nr & 2) ? a23 : a01;
-      double const b01 = (nc & 1) ? wv[1][k] : wv[0][k], b23 = (nc & 1) ? wv[3][k] : wv[2][k];
-      wc[k] = (nc & 2) ? b23 : b01;
-    }
-    RowNode<double> rown;
-    ColNode<double> coln;
-    row_node(c, wr, rown);
-    column_node_w(c, wc, coln);
-    jacobian_block_add<TRANSPOSE>(c, rown, coln, acc);
-    if (diag) {  // n == m: the residual entries of the node
-      double t4[4];
-      element_residual_row(c, wr, t4);
-      r4[0] += t4[0]; r4[1] += t4[1]; r4[2] += t4[2]; r4[3] += t4[3];
-    }
-  }
+  for (int k = 0; k < 3; ++k) { double2 const v = q[11 + k]; t.G[2 * k] = v.x; t.G[2 * k + 1] = v.y; }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) { double2 const v = q[14 + k]; t.sc[2 * k] = v.x; t.sc[2 * k + 1] = v.y; }
+  if (want_resid) { double2 const v = q[20]; t.sc[12] = v.x; t.sc[13] = v.y; }
+  else { t.sc[12] = 0.0; t.sc[13] = 0.0; }
+}
+__device__ __forceinline__ void trec_load_node(double2 const* q, int n, double nq[4]) {
+  double2 const a = q[2 * n], b = q[2 * n + 1];
+  nq[0] = a.x; nq[1] = a.y; nq[2] = b.x; nq[3] = b.y;
 }
 
 template <bool TRANSPOSE>
-__global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
-                                                                        uint32_t const* __restrict__ sched) {
+__global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(const __grid_constant__ KParams P, double const* __restrict__ rec,
+                                                                               uint32_t const* __restrict__ sched) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t mbar;
   double* srec = reinterpret_cast<double*>(smem_raw);
@@ -959,13 +406,12 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
   int const n_recs = (int)__ldg(w);
   int const n_runs = (int)__ldg(w + 2);
-  uint2 const my_run = __ldg(reinterpret_cast<uint2 const*>(w + 4 + PATCH_RECS + 8 * PATCH_THREADS) + min(tid, PATCH_RECS - 1));
-  uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS) + tid);
-  uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + PATCH_RECS + 4 * PATCH_THREADS) + tid);
-  // Record staging: thread r issues one bulk asynchronous copy (global -> shared) for run r of the schedule -- a run is
-  // a number of consecutive elements' records (272 B each, contiguous in global memory) that go to consecutive slots;
-  // the copies report their bytes to an mbarrier that the whole block then waits on.
-  static_assert(PATCH_RECS <= PATCH_THREADS, "one thread per run");
+  uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4) + tid);
+  uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + 4 * PATCH_THREADS) + tid);
+  uint2 const* runs = reinterpret_cast<uint2 const*>(w + 4 + 8 * PATCH_THREADS);
+  // Record staging: one bulk asynchronous copy (global -> shared) per run of the schedule -- a run is a number of
+  // consecutive elements' records (336 B each, contiguous in global memory) that go to consecutive slots; the copies
+  // report their bytes to an mbarrier that the whole block then waits on.
   uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
   if (tid == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
@@ -973,7 +419,8 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
   }
   __syncthreads();
   if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
-  if (tid < n_runs) {
+  for (int r = tid; r < n_runs; r += PATCH_THREADS) {
+    uint2 const my_run = __ldg(runs + r);
     uint32_t const sl = my_run.y & 0xffu, len = my_run.y >> 8;
     uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + sl * (uint32_t)(PATCH_REC_LD * 8);
     double const* src = rec + (int64_t)ELEM_REC * (int64_t)my_run.x;
@@ -987,47 +434,96 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_gather_kernel
       asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
     } while (!done);
   }
-  int const kind = (int)(ot.z >> 30);
-  bool const diag = (ot.w & 0x80000000u) != 0;
-  double acc[16], r4[4];
-  patch_item<TRANSPOSE>(srec, it, diag, acc, r4);
-  // Finish.  Items without secondaries write their block and leave; only the few items that exchange partial sums
-  // (diagonal blocks, edges of high valence: the longest items, i.e. the first warp) meet at the barrier.
-  int const part = (int)((ot.z >> 16) & 0xffu);
-  int const nsec = (int)((ot.z >> 24) & 0x3fu);
-  double* spart = srec + (size_t)PATCH_RECS * PATCH_REC_LD;  // [PATCH_PARTS][20]
-  auto write_out = [&]() {
-    int64_t const voff = (int64_t)(((uint64_t)ot.y << 32) | (uint64_t)ot.x);
-    int const rl = (int)(ot.z & 0xffffu);
-    double* out = P.values + voff;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) stg256(out + (int64_t)i * rl, acc[4 * i], acc[4 * i + 1], acc[4 * i + 2], acc[4 * i + 3]);  // one 32 B sector each
-    if (diag) stg256(P.R + 4 * (int64_t)(ot.w & 0x7fffffffu), r4[0], r4[1], r4[2], r4[3]);
-  };
+  int const kind = (int)(ot.w & 3u), type = (int)((ot.w >> 2) & 3u);
+  int const part = (int)((ot.w >> 4) & 0xffu), nsec = (int)((ot.w >> 12) & 0x3fu);
   if (kind == 0) return;
+  double acc1[16], acc2[16], r4[4];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { acc1[k] = 0.0; acc2[k] = 0.0; }
+  r4[0] = r4[1] = r4[2] = r4[3] = 0.0;
+  uint64_t elo = (uint64_t)it.x | ((uint64_t)it.y << 32), ehi = (uint64_t)it.z | ((uint64_t)it.w << 32);
+  if (type == 2) {
+#pragma unroll 1
+    for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
+      uint32_t const ent = (uint32_t)elo & 0xffffu;
+      elo = (elo >> 16) | (ehi << 48); ehi >>= 16;
+      if (!(ent & 0x8000u)) {  // an empty round of this item (bank-conflict avoidance), or the end of its list
+        if ((elo | ehi) == 0) break;
+        continue;
+      }
+      double2 const* q = reinterpret_cast<double2 const*>(srec + (ent & 0xffu) * PATCH_REC_LD);
+      double nq[4], mq[4];
+      trec_load_node(q, (int)((ent >> 10) & 3u), nq);
+      trec_load_node(q, (int)((ent >> 8) & 3u), mq);
+      TRegs t;
+      trec_load_common(q, t, false);
+      trec_pair_add<TRANSPOSE>(nq, mq, t.s, t.G, t.sc, acc1, acc2);
+    }
+  } else if (type == 1) {
+#pragma unroll 1
+    for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
+      uint32_t const ent = (uint32_t)elo & 0xffffu;
+      elo = (elo >> 16) | (ehi << 48); ehi >>= 16;
+      if (!(ent & 0x8000u)) {
+        if ((elo | ehi) == 0) break;
+        continue;
+      }
+      double2 const* q = reinterpret_cast<double2 const*>(srec + (ent & 0xffu) * PATCH_REC_LD);
+      double nq[4];
+      trec_load_node(q, (int)((ent >> 10) & 3u), nq);
+      TRegs t;
+      trec_load_common(q, t, true);
+      trec_diag_add<TRANSPOSE>(nq, t.s, t.G, t.sc, acc1, r4);
+    }
+  }
+  // Finish.  Items without secondaries write their block(s) and leave; only the few items that exchange partial sums
+  // (diagonal blocks, edges of high valence) meet at the barrier.
+  double* spart = srec + (size_t)PATCH_RECS * PATCH_REC_LD;  // [PATCH_PARTS][PATCH_PART_LD]
+  auto write_out = [&]() {
+    int const j1 = (int)(ot.z & 0xffu), nb1 = (int)((ot.z >> 8) & 0xffu);
+    double* out = P.values + 16 * (int64_t)ot.x + 4 * j1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) stg256(out + (int64_t)i * (4 * nb1), acc1[4 * i], acc1[4 * i + 1], acc1[4 * i + 2], acc1[4 * i + 3]);  // one 32 B sector each
+    if (type == 2) {
+      int const j2 = (int)((ot.z >> 16) & 0xffu), nb2 = (int)(ot.z >> 24);
+      double* out2 = P.values + 16 * (int64_t)ot.y + 4 * j2;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) stg256(out2 + (int64_t)i * (4 * nb2), acc2[4 * i], acc2[4 * i + 1], acc2[4 * i + 2], acc2[4 * i + 3]);
+    } else if (type == 1) {
+      stg256(P.R + 4 * (int64_t)ot.y, r4[0], r4[1], r4[2], r4[3]);
+    }
+  };
   if (kind == 1 && nsec == 0) { write_out(); return; }
   if (kind == 2) {
-    double2* d = reinterpret_cast<double2*>(spart + 20 * part);
+    double2* d = reinterpret_cast<double2*>(spart + PATCH_PART_LD * part);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) d[k] = make_double2(acc[2 * k], acc[2 * k + 1]);
-    d[8] = make_double2(r4[0], r4[1]);
-    d[9] = make_double2(r4[2], r4[3]);
+    for (int k = 0; k < 8; ++k) d[k] = make_double2(acc1[2 * k], acc1[2 * k + 1]);
+    if (type == 2) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) d[8 + k] = make_double2(acc2[2 * k], acc2[2 * k + 1]);
+    }
+    d[16] = make_double2(r4[0], r4[1]);
+    d[17] = make_double2(r4[2], r4[3]);
   }
   __syncthreads();  // the threads that are still here
   if (kind == 1) {
     for (int s2 = 0; s2 < nsec; ++s2) {
-      double2 const* d = reinterpret_cast<double2 const*>(spart + 20 * (part + s2));
+      double2 const* d = reinterpret_cast<double2 const*>(spart + PATCH_PART_LD * (part + s2));
 #pragma unroll
-      for (int k = 0; k < 8; ++k) { double2 const v = d[k]; acc[2 * k] += v.x; acc[2 * k + 1] += v.y; }
-      if (diag) {
-        double2 v = d[8]; r4[0] += v.x; r4[1] += v.y;
-        v = d[9]; r4[2] += v.x; r4[3] += v.y;
+      for (int k = 0; k < 8; ++k) { double2 const v = d[k]; acc1[2 * k] += v.x; acc1[2 * k + 1] += v.y; }
+      if (type == 2) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { double2 const v = d[8 + k]; acc2[2 * k] += v.x; acc2[2 * k + 1] += v.y; }
+      }
+      if (type == 1) {
+        double2 v = d[16]; r4[0] += v.x; r4[1] += v.y;
+        v = d[17]; r4[2] += v.x; r4[3] += v.y;
       }
     }
     write_out();
   }
 }
-
+#endif
 
 // ---------------------------------------------------------------------------
 // Residual and error-localisation passes, gather form (default): no colouring, no zeroing, no atomics.

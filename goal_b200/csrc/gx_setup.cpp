@@ -122,46 +122,6 @@ int build_graph_and_schedule(gx_ctx* c) {
       c->adj[k].y = (int)((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
     }
 
-  // ---- sorted fold schedule (see gx_internal.h): per node, its 4*deg staged blocks grouped by target block;
-  //      inside a group ascending incidence; two blocks per word (one per half-warp)
-  c->fold_ord.assign(4 * n2e.size() + 8 * (size_t)nn, 0u);
-  uint32_t const ld = (uint32_t)((std::min(c->max_deg, 32) + 1) | 1);  // == fold_row_stride(max_deg), gx_kernels.cuh
-  c->fold_ld = (int)ld;
-#pragma omp parallel
-  {
-    std::vector<uint32_t> keys;
-#pragma omp for schedule(dynamic, 4096)
-    for (int a = 0; a < nn; ++a) {
-      int const deg = (int)(n2e_off[a + 1] - n2e_off[a]);
-      if (deg == 0 || deg > 32) continue;
-      keys.clear();
-      for (int l = 0; l < deg; ++l) {
-        uint32_t const jp = (uint32_t)c->adj[n2e_off[a] + l].y;
-        for (int m = 0; m < 4; ++m) keys.push_back((((jp >> (8 * m)) & 0xffu) << 16) | ((uint32_t)l << 2) | (uint32_t)m);
-      }
-      std::sort(keys.begin(), keys.end());
-      uint32_t* dst = c->fold_ord.data() + 4 * n2e_off[a] + 8 * (size_t)a;  // [0] = word count, words from [4]
-      uint32_t nw = 0;
-      size_t t = 0;
-      while (t < keys.size()) {
-        uint32_t const j = keys[t] >> 16;
-        size_t e = t;
-        while (e < keys.size() && (keys[e] >> 16) == j) ++e;
-        for (size_t q = t; q < e; q += 2) {
-          auto off = [&](size_t i) -> uint32_t {
-            if (i >= e) return ld - 1u;  // the always-zero pad column of staging row 0
-            return (keys[i] & 3u) * 16u * ld + ((keys[i] >> 2) & 31u);
-          };
-          bool const last = q + 2 >= e;
-          dst[4 + nw++] = off(q) | (off(q + 1) << 11) | (j << 22) | (last ? 0x40000000u : 0u);
-        }
-        t = e;
-      }
-      dst[0] = nw;
-      for (uint32_t q = nw; q < ((nw + 3u) & ~3u); ++q) dst[4 + q] = (ld - 1u) | ((ld - 1u) << 11);  // pad to groups of 4 with no-ops
-    }
-  }
-
   // ---- diagonal block position per node (Dirichlet rows put their 1 there)
   c->diag_pos.assign(nn, 0);
 #pragma omp parallel for schedule(static)
@@ -244,7 +204,7 @@ void build_block_lists(gx_ctx* c) {
 #pragma omp parallel for schedule(static)
   for (int a = 0; a < nn; ++a) {
     for (int64_t t = nx[a]; t < nx[a + 1]; ++t) c->blk_row[t] = (uint32_t)a;
-    c->blk_row[nx[a] + c->diag_pos[a]] |= 0x80000000u;
+    if (nx[a + 1] > nx[a]) c->blk_row[nx[a] + c->diag_pos[a]] |= 0x80000000u;  // a node without elements has no blocks
     for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
       uint32_t const jp = (uint32_t)c->adj[k].y;
       for (int m = 0; m < 4; ++m) c->bc_off[nx[a] + ((jp >> (8 * m)) & 0xffu) + 1]++;  // blocks of one row: no races
@@ -268,20 +228,24 @@ void build_block_lists(gx_ctx* c) {
   c->block_lists_built = true;
 }
 
-// Patch schedule of the patch-gather Jacobian pass.  A patch is a run of nodes of the Z-curve visiting order whose
-// incident elements (at most PATCH_RECS) are staged once in shared memory by one thread block.  The patch's work is
-// cut into items of at most PATCH_ITEM_LEN contributions to one 4x4 block; a block with more contributions (the
-// diagonal block, edges of high valence) has one primary item and secondaries whose partial sums the primary adds
-// in a fixed order.  Layout per patch (uint32 words, PATCH_WORDS):
-//   [0..3]   n_recs, n_items, 0, 0
-//   [4..]    elems[PATCH_RECS]                      element id of each staged record
-//   then     items[PATCH_THREADS][4]                8 rounds x 16 bit: slot | m << 8 | n << 10 | 0x8000, 0 = sits the round out
-//   [0..3]   (cont.) word 2 = number of runs
-//   then     outs[PATCH_THREADS][4]                 x,y = value offset of block entry (0,0) (int64, doubles)
-//                                                   z = row stride | part slot << 16 | n secondaries << 24 | kind << 30
-//                                                   w = node id | diagonal << 31
-//            kind: 0 idle thread, 1 primary, 2 secondary
-//   then     runs[PATCH_RECS][2]                    bulk copies: first element id, first slot | number of records << 8
+// Patch schedule of the Jacobian pass (stage B, patch_pair_kernel).  A patch is a run of nodes of the Z-curve visiting
+// order whose incident elements (at most PATCH_RECS) are staged once in shared memory by one thread block.  The
+// patch's work is cut into items, one per thread:
+//   PAIR  an edge (a,b) of the mesh, owned by the patch of whichever end comes first in the visiting order (all
+//         elements around the edge are incident to that end, hence staged): the two mirror blocks (a,b) and (b,a),
+//         built from the same staged data of every element around the edge;
+//   DIAG  the diagonal block (a,a) and the four residual entries of node a;
+//   ZERO  a phantom block of a partitioned context (a column that lives on another part): written as zeros.
+// An item holds at most PATCH_ITEM_LEN contributions; longer lists (the diagonal: one per incident element, edges
+// of high valence) are cut into a primary item and secondaries whose partial sums the primary adds in a fixed
+// order.  Layout per patch (uint32 words, PATCH_WORDS):
+//   [0..3]   n_recs, n_items, n_runs, 0
+//   then     items[PATCH_THREADS][4]   8 rounds x 16 bit: slot | m << 8 | n << 10 | 0x8000; 0 = sits the round out
+//   then     outs[PATCH_THREADS][4]    w0 = first block of row a (extended block rows), w1 = first block of row b (PAIR)
+//                                      or the node id a (DIAG); w2 = j1 | nblk1 << 8 | j2 << 16 | nblk2 << 24 (position
+//                                      of the block in its row, blocks per row); w3 = kind | type << 2 | part << 4 | nsec << 12
+//            kind: 0 idle thread, 1 primary, 2 secondary;  type: 0 ZERO, 1 DIAG, 2 PAIR
+//   then     runs[PATCH_RECS][2]       bulk copies: first element id, first slot | number of records << 8
 bool build_patch_schedule(gx_ctx* c) {
   using namespace gx;
   if (!c->block_lists_built) build_block_lists(c);
@@ -292,65 +256,67 @@ bool build_patch_schedule(gx_ctx* c) {
   std::vector<std::vector<uint32_t>> out(nch);
   bool const stats = getenv("GX_SCHED_STATS") != nullptr;
   bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
-  bool const use_runs = getenv("GX_SCHED_RUNS") == nullptr || atoi(getenv("GX_SCHED_RUNS")) != 0;  // 0: one copy per record
-  std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0), st_runs(nch, 0), st_recs(nch, 0);
+  std::vector<int64_t> st_wave(nch, 0), st_rounds(nch, 0), st_runs(nch, 0), st_recs(nch, 0), st_items(nch, 0), st_contrib(nch, 0);
   bool ok = true;
-  // Blocks with many contributions (the diagonal block: one per incident element) are cut into items of at most
-  // `split` contributions, as evenly as possible.  A thread block lives as long as its longest item, so the cut
-  // follows the length of the ordinary items (an edge of a Kuhn mesh has 4 or 6 elements) rather than the capacity
-  // of an item: with 8 the first warp ran 8 rounds while the others had left after 5 or 6.
-  int split = 6;
+  // Long contribution lists are cut into items of at most `split` contributions, as evenly as possible.  A thread
+  // block lives as long as its longest item, so the cut follows the length of the ordinary items (an edge of a Kuhn
+  // mesh has 4 or 6 elements) rather than the capacity of an item.
+  int split = 6, split_diag = 6;
   if (char const* e = getenv("GX_SCHED_SPLIT")) split = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
-  auto n_parts = [&](int cnt) { return std::max(1, (cnt + split - 1) / split); };
+  if (char const* e = getenv("GX_SCHED_SPLIT_DIAG")) split_diag = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
+  auto n_parts = [&](int cnt, bool diag) { int const sp = diag ? split_diag : split; return std::max(1, (cnt + sp - 1) / sp); };
+  std::vector<int32_t> rank(nn);
+  for (int s2 = 0; s2 < nn; ++s2) rank[c->node_order[s2]] = s2;
 #pragma omp parallel for schedule(dynamic, 1)
   for (int ch = 0; ch < nch; ++ch) {
-    struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; int64_t voff; uint32_t rl, node; int kind, nsec, part; bool diag; };
+    struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; uint32_t w0, w1, w2; int kind, type, nsec, part; };
     std::vector<Item> items;
     std::vector<int32_t> recs;
-    int32_t hkey[512]; int16_t hval[512];
-    auto hclear = [&]() { for (int i = 0; i < 512; ++i) hkey[i] = -1; };
+    int32_t hkey[1024]; int16_t hval[1024];
+    auto hclear = [&]() { for (int i = 0; i < 1024; ++i) hkey[i] = -1; };
     auto hfind = [&](int32_t e) -> int {
-      uint32_t h = ((uint32_t)e * 2654435761u) >> 23;
-      while (hkey[h] != -1) { if (hkey[h] == e) return hval[h]; h = (h + 1) & 511u; }
+      uint32_t h = ((uint32_t)e * 2654435761u) >> 22;
+      while (hkey[h] != -1) { if (hkey[h] == e) return hval[h]; h = (h + 1) & 1023u; }
       return -1;
     };
     auto hput = [&](int32_t e, int v) {
-      uint32_t h = ((uint32_t)e * 2654435761u) >> 23;
-      while (hkey[h] != -1) h = (h + 1) & 511u;
+      uint32_t h = ((uint32_t)e * 2654435761u) >> 22;
+      while (hkey[h] != -1) h = (h + 1) & 1023u;
       hkey[h] = e; hval[h] = (int16_t)v;
     };
     int nparts = 0;
     auto flush = [&]() {
       if (items.empty()) return;
-      // longest items first: the lanes of a warp then run the same number of contributions
+      // pairs first, then diagonals, then zeros (a warp then runs one code path); inside a type the longest items
+      // first: the lanes of a warp then run the same number of contributions
       std::vector<int> ord(items.size());
       for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
-      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return items[x].n > items[y].n; });
+      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
+        if (items[x].type != items[y].type) return items[x].type > items[y].type;
+        return items[x].n > items[y].n;
+      });
       // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
-      // record is its slot modulo 8.  Bank groups are given to the records by a greedy colouring (records feeding the
-      // same item get different groups where possible); then, within every group of 8 lanes, each item's
-      // contributions are ordered so that the records read in the same round sit in different groups where possible
-      // (per round a bipartite matching of items to bank groups).
+      // record is its slot modulo 8 (record stride 21 x 16 B, odd).  Runs of records are placed where they meet the
+      // fewest records of the items they feed; then, within every group of 8 lanes, each item's contributions are
+      // ordered so that the records read in the same round sit in different groups where possible (per round a
+      // bipartite matching of items to bank groups).
       int const nrec = (int)recs.size();
       std::vector<int> res(nrec, -1);
-      std::vector<int> slot_of(nrec, -1);   // run placement only: final slot of every record
-      std::vector<uint32_t> run_e0, run_sl; // runs of consecutive elements in consecutive slots: one bulk copy each
+      std::vector<int> slot_of(nrec, -1);
+      std::vector<uint32_t> run_e0, run_sl;  // runs of consecutive elements in consecutive slots: one bulk copy each
       std::vector<std::vector<int>> in_items(nrec);
       for (size_t i = 0; i < items.size(); ++i)
         for (int q = 0; q < items[i].n; ++q) in_items[items[i].ent[q] & 0xff].push_back((int)i);
       // cnt8[l][r] = records already placed in bank group r that share an item with record l (with multiplicity)
       std::vector<std::array<int, 8>> cnt8(nrec, std::array<int, 8>{});
-      auto conflicts = [&](int l, int r) { return cnt8[l][r]; };
       auto place = [&](int l, int r) {
         res[l] = r;
         for (int i : in_items[l])
           for (int q = 0; q < items[i].n; ++q) cnt8[items[i].ent[q] & 0xff][r]++;
       };
-      if (use_runs) {
+      {
         // Records of consecutive elements are consecutive in global memory: placed in consecutive slots they arrive with
-        // ONE bulk copy.  A run's records then sit in consecutive bank groups, so the greedy colouring works on runs:
-        // longest first, each at the free position where its records meet the fewest already placed records of the
-        // items they feed (ties: the lowest slot).
+        // ONE bulk copy.  Longest runs first, each at the free position with the fewest conflicts (ties: lowest slot).
         std::vector<int> byel(nrec);
         for (int l = 0; l < nrec; ++l) byel[l] = l;
         std::sort(byel.begin(), byel.end(), [&](int x, int y) { return recs[x] < recs[y]; });
@@ -372,7 +338,7 @@ bool build_patch_schedule(gx_ctx* c) {
             for (int j = 0; j < run.len && free_; ++j) free_ = !taken[s0 + j];
             if (!free_) continue;
             int cost = 0;
-            for (int j = 0; j < run.len; ++j) cost += conflicts(byel[run.first + j], (s0 + j) & 7);
+            for (int j = 0; j < run.len; ++j) cost += cnt8[byel[run.first + j]][(s0 + j) & 7];
             if (cost < best_cost) { best_cost = cost; best = s0; }
             if (cost == 0) break;
           }
@@ -388,25 +354,14 @@ bool build_patch_schedule(gx_ctx* c) {
           run_e0.push_back((uint32_t)recs[byel[run.first]]);
           run_sl.push_back((uint32_t)best | ((uint32_t)run.len << 8));
         }
-      } else {
-        int cap[8];
-        for (int r = 0; r < 8; ++r) cap[r] = nrec / 8 + (r < nrec % 8 ? 1 : 0);  // slots r, r + 8, ...: no gaps
-        // bank groups first: records that contribute to the same item get different groups where possible
-        for (int l = 0; l < nrec; ++l) {
-          int cnt[8];
-          for (int r = 0; r < 8; ++r) cnt[r] = conflicts(l, r);
-          int best = -1;
-          for (int r = 0; r < 8; ++r)
-            if (cap[r] > 0 && (best < 0 || cnt[r] < cnt[best] || (cnt[r] == cnt[best] && cap[r] > cap[best]))) best = r;
-          place(l, best); cap[best]--;
-        }
       }
       for (size_t g0 = 0; g0 < ord.size() && !nomatch; g0 += 8) {
         int const gn = (int)std::min<size_t>(8, ord.size() - g0);
         // Rounds available to this group of 8 lanes: its warp runs as many rounds as its longest item, so an item
         // may sit out a round (an empty entry) as long as it still finishes -- which lets the schedule dodge
         // conflicts that a packed order cannot.
-        int const R = items[ord[(g0 / 32) * 32]].n;
+        int R = 0;
+        for (size_t t = (g0 / 32) * 32; t < std::min(ord.size(), (g0 / 32) * 32 + 32); ++t) R = std::max(R, items[ord[t]].n);
         bool used[8][PATCH_ITEM_LEN] = {};
         uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
         int remaining[8] = {};
@@ -469,25 +424,14 @@ bool build_patch_schedule(gx_ctx* c) {
           for (int k = 0; k < PATCH_ITEM_LEN; ++k) it.ent[k] = sched_ent[i][k];
         }
       }
-      {  // final slots: record with bank group r takes the next of r, r + 8, r + 16, ...
-        int next[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-        std::vector<int> slot(nrec);
-        std::vector<int32_t> recs2(use_runs ? PATCH_RECS : nrec, 0);
-        for (int l = 0; l < nrec; ++l) {
-          if (use_runs) slot[l] = slot_of[l];
-          else { slot[l] = next[res[l]]; next[res[l]] += 8; }
-          recs2[slot[l]] = recs[l];
-        }
-        if (!use_runs)  // one copy per record
-          for (int l = 0; l < nrec; ++l) { run_e0.push_back((uint32_t)recs[l]); run_sl.push_back((uint32_t)slot[l] | (1u << 8)); }
-        recs.swap(recs2);
-        for (auto& it : items)
-          for (int k = 0; k < PATCH_ITEM_LEN; ++k)
-            if (it.ent[k] & 0x8000) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot[it.ent[k] & 0xff]);
-      }
+      for (auto& it : items)  // provisional record numbers -> final slots
+        for (int k = 0; k < PATCH_ITEM_LEN; ++k)
+          if (it.ent[k] & 0x8000) it.ent[k] = (uint16_t)((it.ent[k] & 0xff00) | slot_of[it.ent[k] & 0xff]);
       if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
         st_runs[ch] += (int64_t)run_e0.size();
         st_recs[ch] += (int64_t)nrec;
+        st_items[ch] += (int64_t)items.size();
+        for (auto const& it : items) st_contrib[ch] += it.n;
         for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
           int const gn = (int)std::min<size_t>(8, ord.size() - g0);
           for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
@@ -515,34 +459,45 @@ bool build_patch_schedule(gx_ctx* c) {
       out[ch].resize(base + PATCH_WORDS, 0u);
       uint32_t* w = out[ch].data() + base;
       w[0] = (uint32_t)nrec; w[1] = (uint32_t)items.size(); w[2] = (uint32_t)run_e0.size();
-      for (size_t i = 0; i < recs.size(); ++i) w[4 + i] = (uint32_t)recs[i];
-      uint32_t* wr = w + 4 + PATCH_RECS + 8 * PATCH_THREADS;  // runs[2 PATCH_RECS]: first element, first slot | length << 8
-      for (size_t i = 0; i < run_e0.size(); ++i) { wr[2 * i] = run_e0[i]; wr[2 * i + 1] = run_sl[i]; }
-      uint32_t* wi = w + 4 + PATCH_RECS;
+      uint32_t* wi = w + 4;
       uint32_t* wo = wi + 4 * PATCH_THREADS;
+      uint32_t* wr = wo + 4 * PATCH_THREADS;  // runs[PATCH_RECS][2]: first element, first slot | length << 8
+      for (size_t i = 0; i < run_e0.size(); ++i) { wr[2 * i] = run_e0[i]; wr[2 * i + 1] = run_sl[i]; }
       for (size_t t = 0; t < ord.size(); ++t) {
         Item const& it = items[ord[t]];
         for (int k = 0; k < 4; ++k) wi[4 * t + k] = (uint32_t)it.ent[2 * k] | ((uint32_t)it.ent[2 * k + 1] << 16);
-        wo[4 * t] = (uint32_t)((uint64_t)it.voff & 0xffffffffu);
-        wo[4 * t + 1] = (uint32_t)((uint64_t)it.voff >> 32);
-        wo[4 * t + 2] = it.rl | ((uint32_t)it.part << 16) | ((uint32_t)it.nsec << 24) | ((uint32_t)it.kind << 30);
-        wo[4 * t + 3] = it.node | (it.diag ? 0x80000000u : 0u);
+        wo[4 * t] = it.w0; wo[4 * t + 1] = it.w1; wo[4 * t + 2] = it.w2;
+        wo[4 * t + 3] = (uint32_t)it.kind | ((uint32_t)it.type << 2) | ((uint32_t)it.part << 4) | ((uint32_t)it.nsec << 12);
       }
       items.clear(); recs.clear(); hclear(); nparts = 0;
     };
     hclear();
     bool bad = false;
     int const s1 = std::min(nn, (ch + 1) * CH);
+    // the items of node a: its diagonal block, the edges it owns, its phantom blocks
+    struct Blk { int64_t t; int type; int cnt; int parts; };
+    std::vector<Blk> blks;
     for (int s = ch * CH; s < s1; ++s) {
       int const a = c->node_order[s];
-      // new records this node would add
-      int add = 0;
+      if (nx[a + 1] == nx[a]) continue;  // a node without elements: no blocks, no work (its R entries are zeroed by the pass)
+      int add = 0;  // new records this node would add
       for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) if (hfind(c->adj[k].x >> 2) < 0) ++add;
-      // its items (slots filled in once the node is accepted)
+      blks.clear();
       int nit = 0, nsecs = 0;
+      int64_t const nloc = c->nrow[a + 1] - c->nrow[a];  // local blocks; the extended row may continue with phantom ones
       for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
         int const cnt = (int)(c->bc_off[t + 1] - c->bc_off[t]);
-        int const parts = n_parts(cnt);
+        int type;
+        if (c->blk_row[t] & 0x80000000u) type = 1;
+        else if (cnt == 0) type = 0;
+        else {
+          int const b = c->ncol[c->nrow[a] + (t - nx[a])];
+          (void)nloc;
+          if (rank[b] < s) continue;  // the edge belongs to the patch of b
+          type = 2;
+        }
+        int const parts = n_parts(cnt, type == 1);
+        blks.push_back({t, type, cnt, parts});
         nit += parts; nsecs += parts - 1;
       }
       if (nit > PATCH_THREADS || (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > PATCH_PARTS) { bad = true; break; }
@@ -551,28 +506,36 @@ bool build_patch_schedule(gx_ctx* c) {
         int32_t const e = c->adj[k].x >> 2;
         if (hfind(e) < 0) { hput(e, (int)recs.size()); recs.push_back(e); }
       }
-      int64_t const rl = 4 * (nx[a + 1] - nx[a]);
-      for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
-        uint32_t const c0 = c->bc_off[t], c1 = c->bc_off[t + 1];
-        int const cnt = (int)(c1 - c0);
-        int const parts = n_parts(cnt);
-        bool const diag = (c->blk_row[t] & 0x80000000u) != 0;
+      uint32_t const nblk_a = (uint32_t)(nx[a + 1] - nx[a]);
+      for (Blk const& bk : blks) {
+        uint32_t const c0 = c->bc_off[bk.t];
+        uint32_t const j1 = (uint32_t)(bk.t - nx[a]);
+        uint32_t w1 = 0, j2 = 0, nblk_b = 0;
+        if (bk.type == 1) w1 = (uint32_t)a;
+        if (bk.type == 2) {
+          int const b = c->ncol[c->nrow[a] + j1];
+          int32_t const* rb = c->ncol.data() + c->nrow[b];
+          j2 = (uint32_t)(std::lower_bound(rb, (int32_t const*)(c->ncol.data() + c->nrow[b + 1]), (int32_t)a) - rb);
+          nblk_b = (uint32_t)(nx[b + 1] - nx[b]);
+          w1 = (uint32_t)nx[b];
+        }
         int first = 0;  // contributions in ascending element order, cut into `parts` runs of almost equal length
-        for (int pi = 0; pi < parts; ++pi) {
+        for (int pi = 0; pi < bk.parts; ++pi) {
           Item it{};
-          it.n = cnt / parts + (pi < cnt % parts ? 1 : 0);
+          it.n = bk.cnt / bk.parts + (pi < bk.cnt % bk.parts ? 1 : 0);
           for (int q = 0; q < it.n; ++q) {
             int32_t const ent = c->bc[c0 + first + q];
             it.ent[q] = (uint16_t)(hfind(ent >> 4) | ((ent & 15) << 8) | 0x8000);  // n*4+m -> bits 8..11
           }
-          it.voff = 16 * nx[a] + 4 * (t - nx[a]);
-          it.rl = (uint32_t)rl; it.node = (uint32_t)a; it.diag = diag;
-          if (pi == 0) { it.kind = 1; it.nsec = parts - 1; it.part = nparts; }
+          it.w0 = (uint32_t)nx[a]; it.w1 = w1;
+          it.w2 = j1 | (nblk_a << 8) | (j2 << 16) | (nblk_b << 24);
+          it.type = bk.type;
+          if (pi == 0) { it.kind = 1; it.nsec = bk.parts - 1; it.part = nparts; }
           else { it.kind = 2; it.nsec = 0; it.part = nparts + pi - 1; }
           first += it.n;
           items.push_back(it);
         }
-        nparts += parts - 1;
+        nparts += bk.parts - 1;
       }
     }
     flush();
@@ -590,12 +553,12 @@ bool build_patch_schedule(gx_ctx* c) {
   c->n_patches = (int)(total / PATCH_WORDS);
   c->patch_state = 1;
   if (stats) {
-    int64_t wv = 0, rd = 0;
-    int64_t runs = 0, nrecs = 0;
-    for (int i = 0; i < nch; ++i) { wv += st_wave[i]; rd += st_rounds[i]; runs += st_runs[i]; nrecs += st_recs[i]; }
-    fprintf(stderr, "[gx] patch schedule: %d patches, %.2f nodes/patch, %.1f records/patch in %.1f runs, %.3f wavefronts per quarter-warp round\n",
-            c->n_patches, (double)nn / std::max(1, c->n_patches), (double)nrecs / std::max(1, c->n_patches),
-            (double)runs / std::max(1, c->n_patches), rd ? (double)wv / (double)rd : 0.0);
+    int64_t wv = 0, rd = 0, runs = 0, nrecs = 0, nit = 0, nco = 0;
+    for (int i = 0; i < nch; ++i) { wv += st_wave[i]; rd += st_rounds[i]; runs += st_runs[i]; nrecs += st_recs[i]; nit += st_items[i]; nco += st_contrib[i]; }
+    double const np = std::max(1, c->n_patches);
+    fprintf(stderr, "[gx] patch schedule: %d patches, %.2f nodes/patch, %.1f records/patch in %.1f runs (staging factor %.2f), %.1f items/patch, %.2f contributions/item, %.3f wavefronts per quarter-warp round\n",
+            c->n_patches, (double)nn / np, (double)nrecs / np, (double)runs / np, (double)nrecs / std::max(1, c->ne), (double)nit / np,
+            nit ? (double)nco / (double)nit : 0.0, rd ? (double)wv / (double)rd : 0.0);
   }
   return true;
 }

@@ -18,7 +18,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_launches.log 2>&1
 tail -1 $OUT/${TAG}_ncu_launches.log | cut -c1-120
 echo "== ncu full (both kernels of the Jacobian pass)"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"patch_gather_kernel|elem_record_kernel" -s 2 -c 2 -f -o $OUT/${TAG}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"patch_pair_kernel|elem_record_kernel" -s 2 -c 2 -f -o $OUT/${TAG}_prof \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > $OUT/${TAG}_ncu_full.log 2>&1
 tail -1 $OUT/${TAG}_ncu_full.log | cut -c1-120
 ls -la $OUT | grep ${TAG}

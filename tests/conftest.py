@@ -46,3 +46,16 @@ def relerr(a, b):
     """norm-wise relative error max|a-b| / max|b| (the 1e-12 parity bar of BASELINE.md 5)."""
     a, b = np.asarray(a), np.asarray(b)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def blockerr(A, B, bs=4):
+    """Largest relative error of any bs x bs block: max over blocks of max|A_blk - B_blk| / max|B_blk|.  Stricter than
+    relerr: entries orders of magnitude below the global maximum are still constrained by their own block's scale."""
+    A, B = np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64)
+    n0, n1 = A.shape[0] // bs, A.shape[1] // bs
+    a = A[:n0 * bs, :n1 * bs].reshape(n0, bs, n1, bs)
+    b = B[:n0 * bs, :n1 * bs].reshape(n0, bs, n1, bs)
+    num = np.abs(a - b).max(axis=(1, 3))
+    den = np.abs(b).max(axis=(1, 3))
+    ok = den > 0
+    return float((num[ok] / den[ok]).max()) if ok.any() else 0.0

@@ -2,7 +2,10 @@
 // Lets the CPU test-suite (no GPU in the build container) verify the arithmetic
 // every CUDA thread runs against the oracle.  Not linked into, nor reachable
 // from, the product library.
+#include <cmath>
+
 #include "../../goal_b200/csrc/element_math.cuh"
+#include "../../goal_b200/csrc/tangent_record.cuh"
 
 extern "C" int hc_element(int model, const double* x, const double* u, const double* p, const double* mat5,
                           const double* Fp_old, double eqps_old, int save, double* K /*16x16 row-major, dof=n*4+eq*/,
@@ -23,6 +26,29 @@ extern "C" int hc_element(int model, const double* x, const double* u, const dou
   double ru[12], rp[4];
   gx::element_residual(c, ru, rp);
   for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) R[4 * n + i] = ru[3 * n + i]; R[4 * n + 3] = rp[n]; }
+  if (save & 16) {  // the 42-double tangent record and the pair / diagonal contributions stage B builds from it
+    double rec[gx::TREC];
+    gx::pack_trec(c, rec);
+    bool const tr = (save & 8) != 0;
+    auto put = [&](int n, int mm, double const* b) {  // b = block (n,mm) of A, or of A^T when tr
+      for (int i = 0; i < 4; ++i) for (int k = 0; k < 4; ++k) {
+        if (!tr) K[(4 * n + i) * 16 + 4 * mm + k] = b[4 * i + k];
+        else K[(4 * mm + k) * 16 + 4 * n + i] = b[4 * i + k];  // undo the transpose: K(row dof of A, col dof of A)
+      }
+    };
+    for (int n = 0; n < 4; ++n) {
+      double a[16] = {}, r4[4] = {};
+      if (tr) gx::trec_diag_add_rec<true>(rec, n, a, r4); else gx::trec_diag_add_rec<false>(rec, n, a, r4);
+      put(n, n, a);
+      for (int i = 0; i < 4; ++i) R[4 * n + i] = r4[i];
+      for (int mm = n + 1; mm < 4; ++mm) {
+        double a1[16] = {}, a2[16] = {};
+        if (tr) gx::trec_pair_add_rec<true>(rec, n, mm, a1, a2); else gx::trec_pair_add_rec<false>(rec, n, mm, a1, a2);
+        put(n, mm, a1); put(mm, n, a2);
+      }
+    }
+    return 0;
+  }
   for (int mm = 0; mm < 4; ++mm) {
     gx::ColNode<double> cn;
     if (save & 2) gx::column_node_w(c, c.w[mm], cn);  // the form the tangent records use: r_m rebuilt from w_m
@@ -145,7 +171,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   unsigned long long pl = 0;
   gx::KParams P;
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
-  P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data(); P.fold_ord = c.fold_ord.data(); P.nblk_g = nullptr; P.fold_ld = c.fold_ld; P.node_order = c.node_order.data();
+  P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data();
   P.state_in = sin.data(); P.fp_old = fpo.data(); P.state_out = sout.data();
   P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
@@ -240,15 +266,15 @@ extern "C" int hc_count_ops(int model, int what, int save, const double* x, cons
 }
 
 // ---------------------------------------------------------------------------
-// CPU replay of the patch-gather Jacobian pass (the default GPU schedule): builds the patch schedule with the product's
-// own host code (gx_setup.cpp), then interprets its words the way patch_gather_kernel does -- staged record slots,
-// work items of up to 8 contributions, primaries adding their secondaries' partial sums in order, one writer per
-// 4x4 block and per node's residual entries -- with the device's element math compiled for the host.  The element
-// "records" are the Core structs themselves (the 34-double packing is device-only code).
-//   values [nnz] and R [4 nn] must come in zeroed; every entry the schedule owns is written exactly once.
+// CPU replay of the Jacobian pass's stage B (the default GPU schedule): builds the patch schedule with the product's
+// own host code (gx_setup.cpp), then interprets its words the way patch_pair_kernel does -- staged record slots from
+// the bulk-copy runs, PAIR / DIAG / ZERO work items of up to 8 contributions, primaries adding their secondaries'
+// partial sums in order, one writer per 4x4 block and per node's residual entries -- with the device's own record
+// packing and contribution arithmetic (tangent_record.cuh) compiled for the host.
+//   values [nnz] and R [4 nn] must come in NaN-filled; every entry the schedule owns is written exactly once.
 // ---------------------------------------------------------------------------
-template <int MODEL, bool TRANSPOSE>
-static int replay_patch_gather(gx_ctx& c, std::vector<gx::Core<double>> const& core, double* R, double* values) {
+template <bool TRANSPOSE>
+static int replay_patch_pairs(gx_ctx& c, std::vector<double> const& rec, double* R, double* values) {
   using namespace gx;
   uint32_t const* sched = c.patch_sched.data();
   for (int pch = 0; pch < c.n_patches; ++pch) {
@@ -256,62 +282,65 @@ static int replay_patch_gather(gx_ctx& c, std::vector<gx::Core<double>> const& c
     int const n_recs = (int)w[0], n_runs = (int)w[2];
     std::vector<int64_t> slot_elem(PATCH_RECS, -1);  // what the bulk copies stage: runs of consecutive elements
     int staged = 0;
-    uint32_t const* wr = w + 4 + PATCH_RECS + 8 * PATCH_THREADS;
-    for (int r = 0; r < n_runs; ++r)
-      for (uint32_t j = 0; j < (wr[2 * r + 1] >> 8); ++j) { slot_elem[(wr[2 * r + 1] & 0xffu) + j] = (int64_t)wr[2 * r] + j; ++staged; }
-    if (staged != n_recs) return 10;
-    uint32_t const* wi = w + 4 + PATCH_RECS;
+    uint32_t const* wi = w + 4;
     uint32_t const* wo = wi + 4 * PATCH_THREADS;
-    double acc[PATCH_THREADS][16], r4[PATCH_THREADS][4], parts[PATCH_PARTS][20];
+    uint32_t const* wr = wo + 4 * PATCH_THREADS;
+    for (int r = 0; r < n_runs; ++r)
+      for (uint32_t j = 0; j < (wr[2 * r + 1] >> 8); ++j) {
+        uint32_t const sl = (wr[2 * r + 1] & 0xffu) + j;
+        if (sl >= (uint32_t)PATCH_RECS || slot_elem[sl] >= 0) return 10;
+        slot_elem[sl] = (int64_t)wr[2 * r] + j; ++staged;
+      }
+    if (staged != n_recs) return 10;
+    static thread_local double acc1[PATCH_THREADS][16], acc2[PATCH_THREADS][16], r4[PATCH_THREADS][4], parts[PATCH_PARTS][PATCH_PART_LD];
     for (int t = 0; t < PATCH_THREADS; ++t) {
       uint32_t const* ot = wo + 4 * t;
-      int const kind = (int)(ot[2] >> 30);
-      bool const diag = (ot[3] & 0x80000000u) != 0;
-      for (int k = 0; k < 16; ++k) acc[t][k] = 0.0;
+      int const kind = (int)(ot[3] & 3u), type = (int)((ot[3] >> 2) & 3u);
+      for (int k = 0; k < 16; ++k) acc1[t][k] = acc2[t][k] = 0.0;
       for (int k = 0; k < 4; ++k) r4[t][k] = 0.0;
       if (kind == 0) continue;
       for (int k = 0; k < PATCH_ITEM_LEN; ++k) {
         uint32_t const ent = (wi[4 * t + k / 2] >> (16 * (k & 1))) & 0xffffu;
         if (!(ent & 0x8000u)) continue;
+        if (type == 0) return 14;  // a ZERO item has no contributions
         int const slot = (int)(ent & 0xffu), n = (int)((ent >> 10) & 3u), m = (int)((ent >> 8) & 3u);
         if (slot_elem[slot] < 0) return 11;
-        Core<double> const& cr = core[(size_t)slot_elem[slot]];
-        int const nr = TRANSPOSE ? m : n, nc = TRANSPOSE ? n : m;
-        RowNode<double> rn;
-        ColNode<double> cn;
-        row_node(cr, cr.w[nr], rn);
-        column_node_w(cr, cr.w[nc], cn);
-        jacobian_block_add<TRANSPOSE>(cr, rn, cn, acc[t]);
-        if (diag) {
-          double t4[4];
-          element_residual_row(cr, cr.w[nr], t4);
-          for (int q = 0; q < 4; ++q) r4[t][q] += t4[q];
-        }
+        double const* rp = rec.data() + (size_t)TREC * (size_t)slot_elem[slot];
+        if (type == 2) { if (n == m) return 15; trec_pair_add_rec<TRANSPOSE>(rp, n, m, acc1[t], acc2[t]); }
+        else { if (n != m) return 15; trec_diag_add_rec<TRANSPOSE>(rp, n, acc1[t], r4[t]); }
       }
       if (kind == 2) {
-        int const part = (int)((ot[2] >> 16) & 0xffu);
+        int const part = (int)((ot[3] >> 4) & 0xffu);
         if (part >= PATCH_PARTS) return 12;
-        for (int k = 0; k < 16; ++k) parts[part][k] = acc[t][k];
-        for (int k = 0; k < 4; ++k) parts[part][16 + k] = r4[t][k];
+        for (int k = 0; k < 16; ++k) { parts[part][k] = acc1[t][k]; parts[part][16 + k] = acc2[t][k]; }
+        for (int k = 0; k < 4; ++k) parts[part][32 + k] = r4[t][k];
       }
     }
     for (int t = 0; t < PATCH_THREADS; ++t) {
       uint32_t const* ot = wo + 4 * t;
-      if ((ot[2] >> 30) != 1u) continue;
-      bool const diag = (ot[3] & 0x80000000u) != 0;
-      int const part = (int)((ot[2] >> 16) & 0xffu), nsec = (int)((ot[2] >> 24) & 0x3fu);
+      if ((ot[3] & 3u) != 1u) continue;
+      int const type = (int)((ot[3] >> 2) & 3u);
+      int const part = (int)((ot[3] >> 4) & 0xffu), nsec = (int)((ot[3] >> 12) & 0x3fu);
       for (int s2 = 0; s2 < nsec; ++s2) {
-        for (int k = 0; k < 16; ++k) acc[t][k] += parts[part + s2][k];
-        if (diag) for (int k = 0; k < 4; ++k) r4[t][k] += parts[part + s2][16 + k];
+        for (int k = 0; k < 16; ++k) { acc1[t][k] += parts[part + s2][k]; acc2[t][k] += parts[part + s2][16 + k]; }
+        for (int k = 0; k < 4; ++k) r4[t][k] += parts[part + s2][32 + k];
       }
-      int64_t const voff = (int64_t)(((uint64_t)ot[1] << 32) | (uint64_t)ot[0]);
-      int const rl = (int)(ot[2] & 0xffffu);
-      for (int i = 0; i < 4; ++i)
-        for (int j = 0; j < 4; ++j) {
-          if (values[voff + (int64_t)i * rl + j] != 0.0) return 13;  // a second writer
-          values[voff + (int64_t)i * rl + j] = acc[t][4 * i + j];
-        }
-      if (diag) for (int k = 0; k < 4; ++k) R[4 * (size_t)(ot[3] & 0x7fffffffu) + k] = r4[t][k];
+      auto put = [&](int64_t blk0, int j, int nb, double const* a) -> bool {
+        for (int i = 0; i < 4; ++i)
+          for (int k = 0; k < 4; ++k) {
+            double& v = values[16 * blk0 + 4 * j + (int64_t)i * (4 * nb) + k];
+            if (v == v) return false;  // a second writer (the array comes in NaN-filled)
+            v = a[4 * i + k];
+          }
+        return true;
+      };
+      if (!put((int64_t)ot[0], (int)(ot[2] & 0xffu), (int)((ot[2] >> 8) & 0xffu), acc1[t])) return 13;
+      if (type == 2 && !put((int64_t)ot[1], (int)((ot[2] >> 16) & 0xffu), (int)(ot[2] >> 24), acc2[t])) return 13;
+      if (type == 1) for (int k = 0; k < 4; ++k) {
+        double& v = R[4 * (size_t)ot[1] + k];
+        if (v == v) return 13;
+        v = r4[t][k];
+      }
     }
   }
   return 0;
@@ -330,8 +359,8 @@ extern "C" int hc_patch_gather(int model, int transpose, int nn, int ne, const i
   c.nrow_x = c.nrow;  // single part: no phantom blocks (comm_setup_lists does this in the library)
   if (!gx::build_patch_schedule(&c)) return 20;
   *n_patches = c.n_patches;
-  std::vector<gx::Core<double>> core(ne);
-  for (int e = 0; e < ne; ++e) {  // stage A: the element core, once per element
+  std::vector<double> rec((size_t)gx::TREC * ne);
+  for (int e = 0; e < ne; ++e) {  // stage A: the element core and its tangent record, once per element
     double X[4][3], U[4][3], P4[4], Cp[6], sg[9], eq;
     for (int n = 0; n < 4; ++n) {
       int const a = conn[4 * (size_t)e + n];
@@ -339,12 +368,18 @@ extern "C" int hc_patch_gather(int model, int transpose, int nn, int ne, const i
       P4[n] = p[a];
     }
     if (model == 1) gx::cp_inverse(Fp_old + 9 * (size_t)e, Cp);
-    rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, P4, mat, Cp, 0.0, false, sg, eq, core[e])
-                    : gx::element_core<gx::MODEL_J2>(X, U, P4, mat, Cp, eqps_old[e], false, sg, eq, core[e]);
+    gx::Core<double> core;
+    rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, P4, mat, Cp, 0.0, false, sg, eq, core)
+                    : gx::element_core<gx::MODEL_J2>(X, U, P4, mat, Cp, eqps_old[e], false, sg, eq, core);
     if (rc) return rc;
+    gx::pack_trec(core, rec.data() + (size_t)gx::TREC * e);
   }
-  if (model == 0) return transpose ? replay_patch_gather<gx::MODEL_NEOHOOKEAN, true>(c, core, R, values)
-                                   : replay_patch_gather<gx::MODEL_NEOHOOKEAN, false>(c, core, R, values);
-  return transpose ? replay_patch_gather<gx::MODEL_J2, true>(c, core, R, values)
-                   : replay_patch_gather<gx::MODEL_J2, false>(c, core, R, values);
+  int64_t const nnz = c.nnz;
+  for (int64_t i = 0; i < nnz; ++i) values[i] = std::nan("");
+  for (int i = 0; i < 4 * nn; ++i) R[i] = std::nan("");
+  rc = transpose ? replay_patch_pairs<true>(c, rec, R, values) : replay_patch_pairs<false>(c, rec, R, values);
+  if (rc) return rc;
+  for (int64_t i = 0; i < nnz; ++i) if (values[i] != values[i]) return 16;  // an entry nobody wrote
+  for (int i = 0; i < 4 * nn; ++i) if (R[i] != R[i]) return 17;
+  return 0;
 }

@@ -6,7 +6,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from conftest import relerr
+from conftest import blockerr, relerr
 from goal_b200.synthetic import MATERIAL, fields, kuhn_cube
 from oracle.oracle import ADJOINT, PRIMAL, Oracle
 
@@ -55,6 +55,13 @@ def test_element_math_matches_fad_oracle(hostcheck, model):
                                       mode, dp(Ka), dp(np.zeros(16)), dp(np.zeros(9)), C.byref(C.c_double(0)), dp(np.zeros(9)),
                                       C.byref(C.c_int(0)), C.byref(C.c_int(0)))
             assert rc == 0 and relerr(Ka.reshape(16, 16), Ko) < 1e-12
+        for mode in (16, 16 | 8):  # the tangent record + pair / diagonal contributions (tangent_record.cuh), plain and transposed
+            Kt, Rt = np.zeros(256), np.zeros(16)
+            rc = hostcheck.hc_element(0 if model == "neohookean" else 1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eqo),
+                                      mode, dp(Kt), dp(Rt), dp(np.zeros(9)), C.byref(C.c_double(0)), dp(np.zeros(9)),
+                                      C.byref(C.c_int(0)), C.byref(C.c_int(0)))
+            assert rc == 0 and relerr(Kt.reshape(16, 16), Ko) < 1e-12 and relerr(Rt, R) < 1e-12
+            assert blockerr(Kt.reshape(16, 16), Ko) < 1e-10
         assert relerr(sig, o.state("sigma")[0]) < 1e-10
         if model == "J2":
             assert pl.value == o.plastic_count()
@@ -186,3 +193,6 @@ def test_patch_gather_replay_matches_oracle(hostcheck, cube, model, mesh):
                                        dp(eqo), dp(Fpo), dp(R), dp(A), C.byref(npch))
         assert rc == 0 and npch.value >= 1
         assert relerr(A, Ao) < 1e-12 and relerr(R, Ro) < 1e-12
+        be = blockerr(o.csr(A).toarray(), o.csr(Ao).toarray())
+        print(f"per-block relative error {model} {mesh} mode {tr}: {be:.2e}")
+        assert be < 1e-11  # every 4x4 block on its own scale (relerr is norm-wise)
