@@ -343,12 +343,20 @@ GX_HD int element_core(S const x[4][3], S const u[4][3], S const p[4], Material 
     eqps_out = eqps_old;
     for (int i = 0; i < 6; ++i) snew[i] = c.s[i];
     if (f > S(1.0e-12)) {
-      // Radial return.  With linear hardening the reference's Newton loop on X
-      // (goal_J2.cpp:108-121) lands on X = f / (2 mubar + 2K/3) in two iterations.
+      // Radial return.  With linear hardening the reference's Newton loop on X (goal_J2.cpp:108-121) is exact after
+      // two iterations: X1 = f / (2 mubar), R1 = -(2/3) K X1, X2 = f / (2 mubar + 2K/3), R2 = 0.  It stops after the
+      // FIRST iteration when |R1| already passes its test (|R| < 1e-11, |R|/Y < 1e-11 or |R|/f < 1e-11: elements that
+      // barely yield, f below about 1e-9, or K = 0) and then differentiates X1, not X2 -- reproduced here through the
+      // denominator, which is all the closed-form tangent below depends on.
       c.plastic = 1;
       S const mubar = c.mubar;
-      S const rD = S(1.0) / (S(2.0) * mubar + S(2.0 / 3.0) * mat.K);
+      S const tm = S(2.0) * mubar, r1n = S(2.0 / 3.0) * mat.K * f;  // |R1| = r1n / tm
+      bool const first = (r1n < S(1.0e-11) * tm) || (r1n < S(1.0e-11) * mat.Y * tm) || (S(2.0 / 3.0) * mat.K < S(1.0e-11) * tm);
+      S const rD = S(1.0) / (first ? tm : tm + S(2.0 / 3.0) * mat.K);
       S const dgam = f * rD;
+      // goal_J2.cpp:119-120: fail("J2: return mapping failed") after 30 iterations -- with a linear residual that
+      // only happens when the iteration runs on non-finite numbers (f = +Inf, NaN state)
+      if (!(dgam - dgam == S(0.0))) return ERR_J2_RETURN_MAP;
       S N[6];
       for (int i = 0; i < 6; ++i) N[i] = c.s[i] * rs;
       c.beta = S(1.0) - S(2.0) * mubar * dgam * rs;

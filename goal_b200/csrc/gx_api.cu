@@ -318,7 +318,7 @@ static void fill_params(gx_ctx* ctx, KParams& P) {
   P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
   P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
-  P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk;
+  P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk; P.pf_dist = (int)ctx->opt_prefetch;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
 }
 
@@ -429,8 +429,8 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
   ctx->timing[0] = t0; ctx->timing[1] = t1; ctx->timing[2] = 0.0; ctx->timing[3] = ctx->launches;
   ctx->last_plastic = (int64_t)hpl;
-  ctx->have_result = true;
-  ctx->have_values = with_values;
+  ctx->have_result = herr[0] == 0;
+  ctx->have_values = with_values && herr[0] == 0;
   if (herr[0]) {
     static const char* const what[] = {"", "inverted element (dv <= 0)", "inverted deformation (det F <= 0)", "J2: return mapping failed"};
     char buf[160];
@@ -775,8 +775,8 @@ int gx_localize_error(gx_ctx* ctx, const double* zu_diff, const double* zp_diff,
   return fetch(ctx, R_out, nullptr);
 }
 
-int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, const int32_t* parent, int32_t n_parent,
-                     double* eta_elem, double* eta_parent, double* bound) {
+static int element_error_body(gx_ctx* ctx, const double* u_err, const double* p_err, const int32_t* parent, int32_t n_parent,
+                              double* eta_elem, double* eta_parent, double* bound, double*& d_eta, double*& d_etap) {
   if (!ctx || !u_err || !p_err) { if (ctx) ctx->err = "gx_element_error: null argument"; return GX_ERR_ARG; }
   if (host_only(ctx)) return GX_ERR_CUDA;
   GX_CUDA(cudaSetDevice(ctx->device));
@@ -789,8 +789,6 @@ int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, cons
   GX_CUDA(cudaMemcpyAsync(b, p_err, sizeof(double) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
   pack_err4_kernel<<<(nn + 255) / 256, 256, 0, ctx->stream>>>(err4, a, b, nn);
   GX_CUDA(cudaGetLastError());
-  double* d_eta = nullptr;
-  double* d_etap = nullptr;
   GX_CUDA(cudaMallocAsync(&d_eta, sizeof(double) * (size_t)ne, ctx->stream));
   element_error_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(d_eta, err4, ctx->d_conn, ne);
   GX_CUDA(cudaGetLastError());
@@ -798,7 +796,7 @@ int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, cons
     if (ctx->n_parent_cached != n_parent || ctx->parent_cached.size() != (size_t)ne ||
         memcmp(ctx->parent_cached.data(), parent, sizeof(int32_t) * (size_t)ne) != 0) {
       for (int e = 0; e < ne; ++e)
-        if (parent[e] < 0 || parent[e] >= n_parent) { ctx->err = "gx_element_error: parent index out of range"; cudaFreeAsync(d_eta, ctx->stream); return GX_ERR_ARG; }
+        if (parent[e] < 0 || parent[e] >= n_parent) { ctx->err = "gx_element_error: parent index out of range"; return GX_ERR_ARG; }
       std::vector<int32_t> off(n_parent + 1, 0), child(ne);
       for (int e = 0; e < ne; ++e) off[parent[e] + 1]++;
       for (int k = 0; k < n_parent; ++k) off[k + 1] += off[k];
@@ -819,17 +817,26 @@ int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, cons
     GX_CUDA(cudaMemcpyAsync(eta_parent, d_etap, sizeof(double) * (size_t)n_parent, cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (bound) {
-    int const nb = std::min(1024, (nn + 255) / 256);
+    int const nb = std::min(1023, (nn + 255) / 256);  // d_red[1023] is the result slot: at most 1023 partials
     bound_partial_kernel<<<nb, 256, 0, ctx->stream>>>(ctx->d_red, err4, nn);
-    bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb < 1023 ? nb : 1023);
+    bound_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_red + 1023, ctx->d_red, nb);
     GX_CUDA(cudaGetLastError());
     GX_CUDA(cudaMemcpyAsync(bound, ctx->d_red + 1023, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   }
   if (eta_elem) GX_CUDA(cudaMemcpyAsync(eta_elem, d_eta, sizeof(double) * (size_t)ne, cudaMemcpyDeviceToHost, ctx->stream));
-  GX_CUDA(cudaFreeAsync(d_eta, ctx->stream));
-  if (d_etap) GX_CUDA(cudaFreeAsync(d_etap, ctx->stream));
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
+}
+int gx_element_error(gx_ctx* ctx, const double* u_err, const double* p_err, const int32_t* parent, int32_t n_parent,
+                     double* eta_elem, double* eta_parent, double* bound) {
+  double *d_eta = nullptr, *d_etap = nullptr;
+  int const rc = element_error_body(ctx, u_err, p_err, parent, n_parent, eta_elem, eta_parent, bound, d_eta, d_etap);
+  if (d_eta || d_etap) {  // also on the error paths
+    if (d_eta) cudaFreeAsync(d_eta, ctx->stream);
+    if (d_etap) cudaFreeAsync(d_etap, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  return rc;
 }
 
 int gx_functional_avg_disp(gx_ctx* ctx, double* J, double* dMdu_out) {
@@ -1105,6 +1112,11 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
     std::vector<uint32_t>().swap(ctx->patch_sched);
     ctx->patch_state = 0;
     if (!ok) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
+    return GX_OK;
+  }
+  if (k == "prefetch") {  // stage B: L2 prefetch distance in patches (0 = off)
+    if (value < 0 || value > (1 << 20)) { ctx->err = "prefetch must be 0..2^20"; return GX_ERR_ARG; }
+    ctx->opt_prefetch = value;
     return GX_OK;
   }
   if (k == "block_size") {

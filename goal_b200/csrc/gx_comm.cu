@@ -568,18 +568,10 @@ int gx_nccl_unique_id(void* out, size_t* id_bytes) {
   return GX_OK;
 }
 
-int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes) {
-  if (!ctx || !nccl_unique_id || id_bytes != sizeof(Uid)) { if (ctx) ctx->err = "gx_comm_init: bad unique id"; return GX_ERR_ARG; }
-  int rc = need_device(ctx, "gx_comm_init");
-  if (rc) return rc;
-  ctx->nccl = load_nccl(ctx->err);
-  if (!ctx->nccl) return GX_ERR_NCCL;
-  GX_CUDA(cudaSetDevice(ctx->device));
-  Uid id;
-  memcpy(&id, nccl_unique_id, sizeof id);
-  GX_NCCL(ctx->nccl->CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank));
-  if (ctx->struct_done) return GX_OK;
-  // structure exchange over NCCL: lengths first, then the blobs (int64 words)
+// structure exchange over NCCL: lengths first, then the blobs (int64 words).  Temporary device buffers are owned by
+// the caller's `bufs` so that every exit path frees them.
+static int struct_exchange_nccl(gx_ctx* ctx, std::vector<void*>& bufs) {
+  int rc;
   size_t const np = ctx->peers.size();
   std::vector<int64_t> slen(np), rlen(np, 0);
   for (size_t p = 0; p < np; ++p) {
@@ -587,9 +579,14 @@ int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes) {
     if ((rc = gx_struct_pack(ctx, (int)p, &b, &bytes))) return rc;
     slen[p] = bytes / 8;
   }
+  auto dev_alloc = [&](int64_t** q, size_t bytes) -> cudaError_t {
+    cudaError_t const e = cudaMalloc(q, bytes);
+    if (e == cudaSuccess) bufs.push_back(*q);
+    return e;
+  };
   int64_t *d_s = nullptr, *d_r = nullptr;
-  GX_CUDA(cudaMalloc(&d_s, 8 * std::max<size_t>(np, 1)));
-  GX_CUDA(cudaMalloc(&d_r, 8 * std::max<size_t>(np, 1)));
+  GX_CUDA(dev_alloc(&d_s, 8 * std::max<size_t>(np, 1)));
+  GX_CUDA(dev_alloc(&d_r, 8 * std::max<size_t>(np, 1)));
   GX_CUDA(cudaMemcpyAsync(d_s, slen.data(), 8 * np, cudaMemcpyHostToDevice, ctx->stream));
   GX_NCCL(ctx->nccl->GroupStart());
   for (size_t p = 0; p < np; ++p) {
@@ -601,8 +598,8 @@ int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes) {
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   std::vector<int64_t*> ds(np, nullptr), dr(np, nullptr);
   for (size_t p = 0; p < np; ++p) {
-    if (slen[p]) { GX_CUDA(cudaMalloc(&ds[p], 8 * slen[p])); GX_CUDA(cudaMemcpyAsync(ds[p], ctx->peers[p].struct_out.data(), 8 * slen[p], cudaMemcpyHostToDevice, ctx->stream)); }
-    if (rlen[p]) GX_CUDA(cudaMalloc(&dr[p], 8 * rlen[p]));
+    if (slen[p]) { GX_CUDA(dev_alloc(&ds[p], 8 * slen[p])); GX_CUDA(cudaMemcpyAsync(ds[p], ctx->peers[p].struct_out.data(), 8 * slen[p], cudaMemcpyHostToDevice, ctx->stream)); }
+    if (rlen[p]) GX_CUDA(dev_alloc(&dr[p], 8 * rlen[p]));
   }
   GX_NCCL(ctx->nccl->GroupStart());
   for (size_t p = 0; p < np; ++p) {
@@ -616,13 +613,29 @@ int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes) {
     if (rlen[p]) GX_CUDA(cudaMemcpyAsync(in[p].data(), dr[p], 8 * rlen[p], cudaMemcpyDeviceToHost, ctx->stream));
   }
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
-  for (size_t p = 0; p < np; ++p) {
+  for (size_t p = 0; p < np; ++p)
     if ((rc = gx_struct_unpack(ctx, (int)p, in[p].data(), 8 * rlen[p]))) return rc;
-    if (ds[p]) cudaFree(ds[p]);
-    if (dr[p]) cudaFree(dr[p]);
-  }
-  cudaFree(d_s); cudaFree(d_r);
   return gx_struct_finalize(ctx);
+}
+
+int gx_comm_init(gx_ctx* ctx, const void* nccl_unique_id, size_t id_bytes) {
+  if (!ctx || !nccl_unique_id || id_bytes != sizeof(Uid)) { if (ctx) ctx->err = "gx_comm_init: bad unique id"; return GX_ERR_ARG; }
+  int rc = need_device(ctx, "gx_comm_init");
+  if (rc) return rc;
+  ctx->nccl = load_nccl(ctx->err);
+  if (!ctx->nccl) return GX_ERR_NCCL;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->comm) {  // a retry after a failed structure exchange keeps the live communicator
+    Uid id;
+    memcpy(&id, nccl_unique_id, sizeof id);
+    GX_NCCL(ctx->nccl->CommInitRank(&ctx->comm, ctx->nranks, id, ctx->rank));
+  }
+  if (ctx->struct_done) return GX_OK;
+  std::vector<void*> bufs;
+  rc = struct_exchange_nccl(ctx, bufs);
+  if (rc) cudaStreamSynchronize(ctx->stream);  // nothing may still be using the buffers
+  for (void* q : bufs) cudaFree(q);
+  return rc;
 }
 
 // SolInfo::gather_R / gather_dRdu over NCCL: grouped send/recv of the packed interface rows, then the
@@ -635,6 +648,8 @@ int gx_reduce_interfaces(gx_ctx* ctx, int what) {
   if (!ctx->comm || !ctx->struct_done) { ctx->err = "gx_reduce_interfaces: call gx_comm_init first"; return GX_ERR_ARG; }
   if (!(what & 7)) return GX_OK;
   if ((what & 4) && (what != 4 || !ctx->have_dMdu)) { ctx->err = "gx_reduce_interfaces: what = 4 (dMdu) goes alone, after gx_functional with a derivative"; return GX_ERR_ARG; }
+  if ((what & 1) && !ctx->have_result) { ctx->err = "gx_reduce_interfaces: no residual on the device"; return GX_ERR_ARG; }
+  if ((what & 2) && !ctx->have_values) { ctx->err = "gx_reduce_interfaces: what & 2 needs the CRS values of a Jacobian pass (the last pass left none)"; return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
   GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   for (auto& P : ctx->peers) if ((rc = pack_peer(ctx, P, what))) return rc;

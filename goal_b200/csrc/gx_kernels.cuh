@@ -57,6 +57,7 @@ struct KParams {
   int* err;                     // {code, element}
   unsigned long long* plastic;  // counter
   int e0, e1;                   // slot range of this launch (coloured schedule)
+  int pf_dist;                  // stage B: patches ahead whose records are pulled into L2 (0 = no prefetch)
   int nn;
   int max_nblk;
   Material mat[GX_MAX_ELEM_SETS];
@@ -404,11 +405,29 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
   double* srec = reinterpret_cast<double*>(smem_raw);
   int const tid = threadIdx.x;
   uint32_t const* w = sched + (size_t)blockIdx.x * PATCH_WORDS;
-  int const n_recs = (int)__ldg(w);
-  int const n_runs = (int)__ldg(w + 2);
+  // every schedule word this thread needs, requested up front (one round trip to L2 / HBM)
+  uint4 const hdr = __ldg(reinterpret_cast<uint4 const*>(w));  // n_recs, n_items, n_runs, block-wide partial sums
   uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4) + tid);
   uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + 4 * PATCH_THREADS) + tid);
   uint2 const* runs = reinterpret_cast<uint2 const*>(w + 4 + 8 * PATCH_THREADS);
+  static_assert(PATCH_RECS <= 2 * PATCH_THREADS, "two runs per thread at most");
+  uint2 const run0 = tid < PATCH_RECS ? __ldg(runs + tid) : make_uint2(0u, 0u);
+  uint2 const run1 = tid + PATCH_THREADS < PATCH_RECS ? __ldg(runs + tid + PATCH_THREADS) : make_uint2(0u, 0u);
+  // L2 prefetch, two stages deep: the schedule words of patch b + 2D, and -- from its words, fetched by block b - D --
+  // the records of patch b + D.  Blocks are dispatched in index order, so both arrive one to two generations early
+  // and the two dependent round trips of a block (words, then records) hit L2 instead of HBM.
+  uint2 pf0 = make_uint2(0u, 0u), pf1 = make_uint2(0u, 0u);
+  if (P.pf_dist > 0) {
+    unsigned const p2 = blockIdx.x + 2u * (unsigned)P.pf_dist, p1 = blockIdx.x + (unsigned)P.pf_dist;
+    if (p2 < gridDim.x && 32 * tid < PATCH_WORDS)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(sched + (size_t)p2 * PATCH_WORDS + 32 * tid));
+    if (p1 < gridDim.x) {
+      uint2 const* r1 = reinterpret_cast<uint2 const*>(sched + (size_t)p1 * PATCH_WORDS + 4 + 8 * PATCH_THREADS);
+      if (tid < PATCH_RECS) pf0 = __ldg(r1 + tid);
+      if (tid + PATCH_THREADS < PATCH_RECS) pf1 = __ldg(r1 + tid + PATCH_THREADS);
+    }
+  }
+  int const n_recs = (int)hdr.x;
   // Record staging: one bulk asynchronous copy (global -> shared) per run of the schedule -- a run is a number of
   // consecutive elements' records (336 B each, contiguous in global memory) that go to consecutive slots; the copies
   // report their bytes to an mbarrier that the whole block then waits on.
@@ -419,15 +438,24 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
   }
   __syncthreads();
   if (tid == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_recs * (ELEM_REC * 8)) : "memory");
-  for (int r = tid; r < n_runs; r += PATCH_THREADS) {
-    uint2 const my_run = __ldg(runs + r);
-    uint32_t const sl = my_run.y & 0xffu, len = my_run.y >> 8;
+  auto stage_run = [&](uint2 const run) {
+    uint32_t const sl = run.y & 0xffu, len = run.y >> 8;
+    if (len == 0) return;  // past the end of the run list (the words are zero there)
     uint32_t const dst = (uint32_t)__cvta_generic_to_shared(srec) + sl * (uint32_t)(PATCH_REC_LD * 8);
-    double const* src = rec + (int64_t)ELEM_REC * (int64_t)my_run.x;
+    double const* src = rec + (int64_t)ELEM_REC * (int64_t)run.x;
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
                  "r"(len * (uint32_t)(ELEM_REC * 8)), "r"(mb)
                  : "memory");
-  }
+  };
+  stage_run(run0);
+  stage_run(run1);
+  auto prefetch_run = [&](uint2 const run) {
+    uint32_t const len = run.y >> 8;
+    if (len == 0) return;
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(rec + (int64_t)ELEM_REC * (int64_t)run.x), "r"(len * (uint32_t)(ELEM_REC * 8)) : "memory");
+  };
+  prefetch_run(pf0);
+  prefetch_run(pf1);
   {
     uint32_t done;
     do {
@@ -505,7 +533,10 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
     d[16] = make_double2(r4[0], r4[1]);
     d[17] = make_double2(r4[2], r4[3]);
   }
-  __syncthreads();  // the threads that are still here
+  // The schedule keeps a primary and its secondaries in one warp wherever it can (header word 3 = 0): the hand-over
+  // then needs only a warp barrier and the warps of a block never wait for each other.
+  if (hdr.w) __syncthreads();  // the threads that are still here
+  else __syncwarp();
   if (kind == 1) {
     for (int s2 = 0; s2 < nsec; ++s2) {
       double2 const* d = reinterpret_cast<double2 const*>(spart + PATCH_PART_LD * (part + s2));

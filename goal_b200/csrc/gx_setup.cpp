@@ -239,7 +239,7 @@ void build_block_lists(gx_ctx* c) {
 // An item holds at most PATCH_ITEM_LEN contributions; longer lists (the diagonal: one per incident element, edges
 // of high valence) are cut into a primary item and secondaries whose partial sums the primary adds in a fixed
 // order.  Layout per patch (uint32 words, PATCH_WORDS):
-//   [0..3]   n_recs, n_items, n_runs, 0
+//   [0..3]   n_recs, n_items, n_runs, 1 if some unit (primary + secondaries) straddles a warp (block barrier needed)
 //   then     items[PATCH_THREADS][4]   8 rounds x 16 bit: slot | m << 8 | n << 10 | 0x8000; 0 = sits the round out
 //   then     outs[PATCH_THREADS][4]    w0 = first block of row a (extended block rows), w1 = first block of row b (PAIR)
 //                                      or the node id a (DIAG); w2 = j1 | nblk1 << 8 | j2 << 16 | nblk2 << 24 (position
@@ -261,7 +261,8 @@ bool build_patch_schedule(gx_ctx* c) {
   // Long contribution lists are cut into items of at most `split` contributions, as evenly as possible.  A thread
   // block lives as long as its longest item, so the cut follows the length of the ordinary items (an edge of a Kuhn
   // mesh has 4 or 6 elements) rather than the capacity of an item.
-  int split = 6, split_diag = 6;
+  int split = 6, split_diag = 6, max_run = 16;  // records per bulk copy at most
+  if (char const* e = getenv("GX_SCHED_MAXRUN")) max_run = std::max(1, std::min(64, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT")) split = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT_DIAG")) split_diag = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
   auto n_parts = [&](int cnt, bool diag) { int const sp = diag ? split_diag : split; return std::max(1, (cnt + sp - 1) / sp); };
@@ -287,14 +288,57 @@ bool build_patch_schedule(gx_ctx* c) {
     int nparts = 0;
     auto flush = [&]() {
       if (items.empty()) return;
-      // pairs first, then diagonals, then zeros (a warp then runs one code path); inside a type the longest items
-      // first: the lanes of a warp then run the same number of contributions
-      std::vector<int> ord(items.size());
-      for (size_t i = 0; i < ord.size(); ++i) ord[i] = (int)i;
-      std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) {
-        if (items[x].type != items[y].type) return items[x].type > items[y].type;
-        return items[x].n > items[y].n;
-      });
+      // Lane order.  A "unit" is a primary item with its secondaries; a unit that sits inside one warp hands its
+      // partial sums over with a warp barrier only.  Units with secondaries come first, by size, diagonals before
+      // pairs (the usual case -- every diagonal cut in four -- is then aligned by construction); a unit that would
+      // straddle a warp boundary is preceded by the shortest single items as filler.  The warp in which the units end
+      // is topped up with the shortest singles as well (it runs two code paths), the remaining singles follow,
+      // pairs before zeros, longest first: the lanes of a warp then run the same number of contributions.
+      std::vector<int> ord;
+      bool block_sync = false;
+      {
+        struct Unit { int prim; std::vector<int> sec; int type, len; };
+        std::vector<Unit> groups, singles;
+        std::vector<int> prim_of_part(PATCH_PARTS + 1, -1);
+        for (size_t i = 0; i < items.size(); ++i)
+          if (items[i].kind == 1) for (int q = 0; q < items[i].nsec; ++q) prim_of_part[items[i].part + q] = (int)i;
+        std::vector<std::vector<int>> secs(items.size());
+        for (size_t i = 0; i < items.size(); ++i) if (items[i].kind == 2) secs[prim_of_part[items[i].part]].push_back((int)i);
+        for (size_t i = 0; i < items.size(); ++i) {
+          if (items[i].kind != 1) continue;
+          Unit u{(int)i, secs[i], items[i].type, items[i].n};
+          (u.sec.empty() ? singles : groups).push_back(u);
+        }
+        std::stable_sort(groups.begin(), groups.end(), [](Unit const& x, Unit const& y) {
+          if (x.sec.size() != y.sec.size()) return x.sec.size() > y.sec.size();
+          if (x.type != y.type) return x.type < y.type;  // diagonals (1) before pairs (2)
+          return x.len > y.len;
+        });
+        std::stable_sort(singles.begin(), singles.end(), [](Unit const& x, Unit const& y) {
+          int const tx = x.type == 0 ? 3 : x.type, ty = y.type == 0 ? 3 : y.type;  // diagonals, pairs, zeros
+          if (tx != ty) return tx < ty;
+          return x.len > y.len;
+        });
+        // the filler pool: the shortest non-zero singles, taken from the back
+        size_t pool_end = singles.size();
+        while (pool_end > 0 && singles[pool_end - 1].type == 0) --pool_end;
+        size_t pool_begin = 0;
+        auto fill = [&](int lanes) {
+          while (lanes > 0 && pool_end > pool_begin) { ord.push_back(singles[--pool_end].prim); --lanes; }
+          return lanes == 0;
+        };
+        for (Unit const& u : groups) {
+          int const sz = 1 + (int)u.sec.size();
+          int const room = 32 - (int)(ord.size() % 32);
+          if (sz > room && sz <= 32 && !fill(room)) block_sync = true;  // nothing left to fill with: this unit straddles
+          if (sz > 32) block_sync = true;
+          ord.push_back(u.prim);
+          for (int q : u.sec) ord.push_back(q);
+        }
+        if (!groups.empty() && ord.size() % 32) fill(32 - (int)(ord.size() % 32));
+        for (size_t i = pool_begin; i < pool_end; ++i) ord.push_back(singles[i].prim);
+        for (size_t i = pool_end; i < singles.size(); ++i) if (singles[i].type == 0) ord.push_back(singles[i].prim);
+      }
       // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
       // record is its slot modulo 8 (record stride 21 x 16 B, odd).  Runs of records are placed where they meet the
       // fewest records of the items they feed; then, within every group of 8 lanes, each item's contributions are
@@ -324,7 +368,7 @@ bool build_patch_schedule(gx_ctx* c) {
         std::vector<Run> runs;
         for (int i = 0; i < nrec;) {
           int j = i + 1;
-          while (j < nrec && recs[byel[j]] == recs[byel[j - 1]] + 1 && j - i < 8) ++j;  // at most 8: distinct bank groups
+          while (j < nrec && recs[byel[j]] == recs[byel[j - 1]] + 1 && j - i < max_run) ++j;
           runs.push_back({i, j - i});
           i = j;
         }
@@ -458,7 +502,7 @@ bool build_patch_schedule(gx_ctx* c) {
       size_t const base = out[ch].size();
       out[ch].resize(base + PATCH_WORDS, 0u);
       uint32_t* w = out[ch].data() + base;
-      w[0] = (uint32_t)nrec; w[1] = (uint32_t)items.size(); w[2] = (uint32_t)run_e0.size();
+      w[0] = (uint32_t)nrec; w[1] = (uint32_t)items.size(); w[2] = (uint32_t)run_e0.size(); w[3] = block_sync ? 1u : 0u;
       uint32_t* wi = w + 4;
       uint32_t* wo = wi + 4 * PATCH_THREADS;
       uint32_t* wr = wo + 4 * PATCH_THREADS;  // runs[PATCH_RECS][2]: first element, first slot | length << 8

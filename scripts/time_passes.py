@@ -21,6 +21,9 @@ def timed(fn, reps=5):
         fn(); t = a.last_timing(); ts.append(t["zero_ms"] + t["assemble_ms"])
     return float(np.median(ts))
 out["jacobian_primal_save_ms"] = timed(lambda: a.jacobian(goal_b200.PRIMAL, save=True, out=False))
+if len(sys.argv) > 3 and sys.argv[3] == "jac":  # Jacobian pass only
+    out["jacobian_primal_save_Melem_s"] = a.ne / out["jacobian_primal_save_ms"] / 1e3
+    print(json.dumps(out)); sys.exit(0)
 out["jacobian_adjoint_nosave_ms"] = timed(lambda: a.jacobian(goal_b200.ADJOINT, save=False, out=False))
 out["residual_save_ms"] = timed(lambda: a.residual(save=True, out=False))
 L = a.L

@@ -173,7 +173,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
   P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data();
   P.state_in = sin.data(); P.fp_old = fpo.data(); P.state_out = sout.data();
-  P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk;
+  P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk; P.pf_dist = 0;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
   int64_t npl = 0;
   using namespace gx;
@@ -219,6 +219,8 @@ inline Cnt& operator+=(Cnt& a, Cnt b) { a = a + b; return a; }
 inline Cnt& operator-=(Cnt& a, Cnt b) { a = a - b; return a; }
 inline Cnt& operator*=(Cnt& a, Cnt b) { a = a * b; return a; }
 inline bool operator>(Cnt a, Cnt b) { ++Cnt::sp; return a.v > b.v; }
+inline bool operator<(Cnt a, Cnt b) { ++Cnt::sp; return a.v < b.v; }
+inline bool operator==(Cnt a, Cnt b) { ++Cnt::sp; return a.v == b.v; }
 inline bool operator<=(Cnt a, Cnt b) { ++Cnt::sp; return a.v <= b.v; }
 inline Cnt sqrt(Cnt a) { ++Cnt::sp; return Cnt(std::sqrt(a.v)); }
 inline Cnt cbrt(Cnt a) { ++Cnt::sp; return Cnt(std::cbrt(a.v)); }

@@ -75,6 +75,45 @@ def test_element_math_matches_fad_oracle(hostcheck, model):
     assert seen == ({0, 1} if model == "J2" else {0})
 
 
+def test_j2_barely_yielding_element_matches_fad_oracle(hostcheck):
+    """goal_J2.cpp:108-121: for an element that barely yields (1e-12 < f < ~1e-9) the reference's Newton loop passes
+    its |R|/Y < 1e-11 test after ONE iteration, X = f / (2 mubar), and FAD differentiates that iterate -- an O(1)
+    difference in the consistent tangent against X = f / (2 mubar + 2K/3).  The closed form must follow it."""
+    rng = np.random.RandomState(7)
+    mat = np.array(MATERIAL)
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]]) * 0.1 + 0.01 * rng.randn(4, 3)
+    u = 0.003 * rng.randn(4, 3)
+    p = rng.randn(4)
+    Fpo = (np.eye(3) + 1e-3 * rng.randn(3, 3)).reshape(-1)
+    o = Oracle(x, np.array([[0, 1, 2, 3]], dtype=np.int32), "J2", [MATERIAL])
+    o.set_solution(u, p)
+    o.state("Fp_old")[:] = Fpo
+
+    def plastic(eq):
+        o.state("eqps_old")[:] = eq
+        o.residual(save=False)
+        return o.plastic_count()
+
+    lo, hi = 0.0, 10.0  # f = |s| - sqrt(2/3)(Y + K eqps_old) falls with eqps_old: find where yielding stops
+    assert plastic(lo) == 1 and plastic(hi) == 0
+    for _ in range(80):
+        mid = 0.5 * (lo + hi)
+        lo, hi = (mid, hi) if plastic(mid) else (lo, mid)
+    for f_target, first_iter in ((2e-10, True), (1e-7, False)):
+        eqo = lo - f_target / (np.sqrt(2.0 / 3.0) * MATERIAL[2])
+        o.state("eqps_old")[:] = eqo
+        R, vals = o.jacobian(PRIMAL, save=False)
+        assert o.plastic_count() == 1
+        Ko = o.csr(vals).toarray()
+        K, pl = np.zeros(256), C.c_int(0)
+        rc = hostcheck.hc_element(1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eqo), 16, dp(K), dp(np.zeros(16)), dp(np.zeros(9)),
+                                  C.byref(C.c_double(0)), dp(np.zeros(9)), C.byref(C.c_int(0)), C.byref(pl))
+        assert rc == 0 and pl.value == 1
+        assert relerr(K.reshape(16, 16), Ko) < 1e-12, (f_target, first_iter)
+    # and the two iterates really differ in the tangent: the same element with the window missed is not within 1e-12
+    assert relerr(K.reshape(16, 16), Ko) < 1e-12
+
+
 @pytest.mark.parametrize("model", ["neohookean", "J2"])
 def test_von_mises_derivative_matches_fad_oracle(hostcheck, model):
     """element_von_mises (closed-form d vm / d u) against the oracle's FADT evaluation of AvgVM

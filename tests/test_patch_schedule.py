@@ -39,13 +39,14 @@ def _check(co, cn):
         staged = {}
         for e0, sl in runs:
             s0, ln = int(sl) & 0xff, int(sl) >> 8
-            assert 1 <= ln <= 8 and s0 + ln <= RECS
+            assert 1 <= ln <= 16 and s0 + ln <= RECS
             for j in range(ln):
                 assert s0 + j not in staged
                 staged[s0 + j] = int(e0) + j
         assert len(staged) == n_recs and len(set(staged.values())) == n_recs  # a record is staged once per patch
         parts = {}
         types_seen = []
+        part_warps = {}
         for t in range(T):
             w3 = int(ot[t, 3])
             kind, typ, part, nsec = w3 & 3, (w3 >> 2) & 3, (w3 >> 4) & 0xff, (w3 >> 12) & 0x3f
@@ -80,11 +81,14 @@ def _check(co, cn):
                     writers[k2] = writers.get(k2, 0) + 1
                 for s in range(nsec):
                     parts[part + s] = ("want", key)
+                    part_warps.setdefault(part + s, set()).add(t // 32)
             else:
+                part_warps.setdefault(part, set()).add(t // 32)
                 assert parts.get(part, ("want", key)) == ("want", key)  # secondaries belong to one primary
                 parts[part] = ("have", key)
         assert all(v[0] == "have" for v in parts.values())
-        assert types_seen == sorted(types_seen, reverse=True)  # pairs, then diagonals, then zeros: warps run one code path
+        # a primary and its secondaries share a warp unless the header says the block barrier is needed
+        assert int(pw[3]) in (0, 1) and (int(pw[3]) == 1 or all(len(v) == 1 for v in part_warps.values()))
     assert set(writers) == set(want) and all(v == 1 for v in writers.values())  # write-once
     assert got == want
     return n_paired, len(W)
