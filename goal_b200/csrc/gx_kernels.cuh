@@ -410,9 +410,13 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
   uint4 const it = __ldg(reinterpret_cast<uint4 const*>(w + 4) + tid);
   uint4 const ot = __ldg(reinterpret_cast<uint4 const*>(w + 4 + 4 * PATCH_THREADS) + tid);
   uint2 const* runs = reinterpret_cast<uint2 const*>(w + 4 + 8 * PATCH_THREADS);
-  static_assert(PATCH_RECS <= 2 * PATCH_THREADS, "two runs per thread at most");
-  uint2 const run0 = tid < PATCH_RECS ? __ldg(runs + tid) : make_uint2(0u, 0u);
-  uint2 const run1 = tid + PATCH_THREADS < PATCH_RECS ? __ldg(runs + tid + PATCH_THREADS) : make_uint2(0u, 0u);
+  static_assert(PATCH_RECS <= 2 * PATCH_THREADS && PATCH_THREADS % 32 == 0, "two runs per thread at most");
+  // Run j goes to lane j / W of warp j % W (W warps): issuing a bulk copy is serialised over the lanes of a warp
+  // (uniform-datapath operands), so the patch's copies are spread over all warps instead of filling warp 0 first.
+  constexpr int NW = PATCH_THREADS / 32;
+  int const jrun = (tid & 31) * NW + (tid >> 5);
+  uint2 const run0 = jrun < PATCH_RECS ? __ldg(runs + jrun) : make_uint2(0u, 0u);
+  uint2 const run1 = jrun + PATCH_THREADS < PATCH_RECS ? __ldg(runs + jrun + PATCH_THREADS) : make_uint2(0u, 0u);
   // L2 prefetch, two stages deep: the schedule words of patch b + 2D, and -- from its words, fetched by block b - D --
   // the records of patch b + D.  Blocks are dispatched in index order, so both arrive one to two generations early
   // and the two dependent round trips of a block (words, then records) hit L2 instead of HBM.
@@ -423,8 +427,8 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
       asm volatile("prefetch.global.L2 [%0];" ::"l"(sched + (size_t)p2 * PATCH_WORDS + 32 * tid));
     if (p1 < gridDim.x) {
       uint2 const* r1 = reinterpret_cast<uint2 const*>(sched + (size_t)p1 * PATCH_WORDS + 4 + 8 * PATCH_THREADS);
-      if (tid < PATCH_RECS) pf0 = __ldg(r1 + tid);
-      if (tid + PATCH_THREADS < PATCH_RECS) pf1 = __ldg(r1 + tid + PATCH_THREADS);
+      if (jrun < PATCH_RECS) pf0 = __ldg(r1 + jrun);
+      if (jrun + PATCH_THREADS < PATCH_RECS) pf1 = __ldg(r1 + jrun + PATCH_THREADS);
     }
   }
   int const n_recs = (int)hdr.x;

@@ -401,10 +401,64 @@ def test_error_codes(cube):
     a.close()
 
 
+def _block_ids(nrow):
+    """block index of every CRS value (dof rows of node a hold its blocks side by side: entry i*(4 nb) + 4 j + k)."""
+    ids = np.empty(16 * int(nrow[-1]), dtype=np.int64)
+    nb_all = np.diff(nrow)
+    for nb in np.unique(nb_all):
+        rows = np.nonzero(nb_all == nb)[0]
+        if nb == 0:
+            continue
+        pat = np.tile(np.repeat(np.arange(nb), 4), 4)[None, :] + nrow[rows][:, None]
+        pos = (16 * nrow[rows])[:, None] + np.arange(16 * nb)[None, :]
+        ids[pos.reshape(-1)] = pat.reshape(-1)
+    return ids
+
+
+def blockerr_crs(A, B, nrow):
+    """max over 4x4 blocks of max|A_blk - B_blk| / max|B_blk| for CRS value arrays of the node-blocked graph."""
+    ids = _block_ids(nrow)
+    nblk = int(nrow[-1])
+    num = np.zeros(nblk); den = np.zeros(nblk)
+    np.maximum.at(num, ids, np.abs(A - B))
+    np.maximum.at(den, ids, np.abs(B))
+    ok = den > 0
+    return float((num[ok] / den[ok]).max())
+
+
+def test_full_size_oracle_parity_1M():
+    """N=55 -> 998,250 tets (BASELINE.json configs[4], the 1M mesh) with the BENCH fields (2 % strain, 99.6 % of the
+    elements plastic): the whole pass against the oracle -- R, every CRS value (norm-wise and per 4x4 block), sigma,
+    eqps, Fp -- primal with state save, and the transposed operator."""
+    import goal_b200
+    from oracle.oracle import Oracle
+    n = 55
+    co, cn = kuhn_cube(n)
+    f = fields(co, len(cn))
+    a, o = _pair(co, cn, "J2", f)
+    assert a.ne == 998250
+    R, A = a.jacobian(goal_b200.PRIMAL, save=True)
+    Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=True)
+    assert a.plastic_count() == o.plastic_count() and a.plastic_count() > 0.99 * a.ne
+    assert np.array_equal(a.rowptr, o.rowptr) and np.array_equal(a.colind, o.colind)
+    assert relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
+    nrow, _ = a.node_graph()
+    be = blockerr_crs(A, Ao, nrow)
+    assert be < 1e-11, be  # every 4x4 block on its own scale
+    assert relerr(a.get_state("sigma"), o.state("sigma")) < 1e-10
+    assert np.abs(a.get_state("eqps") - o.state("eqps")).max() < 1e-10
+    assert np.abs(a.get_state("Fp") - o.state("Fp")).max() < 1e-10
+    At = a.jacobian(goal_b200.ADJOINT, save=False)[1]
+    assert relerr(At, o.jacobian(goal_b200.ADJOINT, save=False)[1]) < 1e-12
+    assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12
+    assert relerr(a.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"]),
+                  o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])) < 1e-12
+    a.close()
+
+
 def test_full_size_properties_1M():
-    """N=55 -> 998,250 tets (BASELINE.json configs[4], 1M).  The oracle is too slow here, so check
-    size-independent properties: determinism, transpose, translation invariance / K*(rigid translation)=0,
-    a checksum against a strided oracle sample, and directional finite differences."""
+    """N=55 -> 998,250 tets: size-independent properties on top of the oracle comparison above -- determinism,
+    transpose, translation invariance / K*(rigid translation)=0, and directional finite differences."""
     import goal_b200
     from oracle.oracle import Oracle
     n = 55

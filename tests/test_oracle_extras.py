@@ -151,3 +151,79 @@ def test_traction_and_size_field_identities(cube):
     cnt = np.bincount(cube["tets"].reshape(-1), minlength=o.nn)
     want = np.bincount(cube["tets"].reshape(-1), weights=np.repeat(h, 4), minlength=o.nn) / cnt
     assert abs(G - o.ne * 3e-4 ** 1.2) < 1e-12 * G and np.abs(v - want).max() < 1e-13
+
+
+# ---------------------------------------------------------------------------
+# A16/A17 (error localisation) against an INDEPENDENT restatement.  The reference holds no value for this chain, so
+# the oracle's C++ restatement is checked against a second one written here in numpy straight from the reference's
+# text -- different code, different data layout, vectorised over elements:
+#   DisplacementAdjoint / PressureAdjoint weights   goal_displacement_adjoint.cpp:37-53, goal_pressure_adjoint.cpp:38-49
+#       w_n^i = z_i N_n,  d_j w_n^i = (grad z)_ij N_n + z_i d_j N_n   (z, grad z at the integration point)
+#   MResidual  R_u[n][i] += P_ij d_j w_n^i w dv                        goal_mresidual.cpp:26-32   (w = u_z_diff)
+#   PResidual  R_p[n] += (p/kappa - (J - 1/J)/2) w_n w dv              goal_presidual.cpp:54-59   (w = p_z_diff)
+#   Stabilization R_p[n] += tau J Cinv_ij d_i p d_j w_n w dv           goal_stabilization.cpp:59-81 (w = p_z_COARSE,
+#       build_error hands "pwc" to Stabilization: goal_mechanics.cpp:214)
+#   neo-Hookean + Mixed                                                goal_neohookean.cpp:60-86, goal_mixed.cpp:34-46
+# ---------------------------------------------------------------------------
+def _numpy_localize_neohookean(co, cn, u, p, zu, zp, zpc, mat=MATERIAL):
+    E, nu, _, _, c0 = mat
+    kappa, mu = E / (3 * (1 - 2 * nu)), E / (2 * (1 + nu))
+    x = co[cn]                                               # [e, n, 3]
+    Jg = x[:, 1:] - x[:, :1]                                 # rows x1-x0, x2-x0, x3-x0
+    dv = np.linalg.det(Jg)
+    Ji = np.linalg.inv(Jg)                                   # d xi / d x
+    G = np.concatenate([-Ji.sum(axis=2, keepdims=True).transpose(0, 2, 1), Ji.transpose(0, 2, 1)], axis=1)  # [e, n, 3] = grad N_n
+    N = 0.25
+    wdv = dv / 6.0                                           # order-1 rule: weight 1/6 at the centroid
+    ue, pe, zue, zpe, zce = u[cn], p[cn], zu[cn], zp[cn], zpc[cn]
+    F = np.eye(3)[None] + np.einsum("eni,enj->eij", ue, G)
+    J = np.linalg.det(F)
+    Finv = np.linalg.inv(F)
+    b = F @ F.transpose(0, 2, 1)
+    devb = b - np.trace(b, axis1=1, axis2=2)[:, None, None] / 3 * np.eye(3)
+    sigma = mu * J[:, None, None] ** (-5.0 / 3.0) * devb + 0.5 * kappa * (J - 1 / J)[:, None, None] * np.eye(3)
+    pq = pe.sum(1) * N
+    sigma = sigma + (pq - np.trace(sigma, axis1=1, axis2=2) / 3)[:, None, None] * np.eye(3)   # Mixed
+    P = J[:, None, None] * sigma @ Finv.transpose(0, 2, 1)
+    z = zue.sum(1) * N                                       # [e, 3]
+    gz = np.einsum("eni,enj->eij", zue, G)                   # (grad z)_ij = d_j z_i
+    # MResidual with the adjoint-weighted test functions
+    Ru = (np.einsum("eij,eij->ei", P, gz)[:, None, :] * N + np.einsum("eij,ei,enj->eni", P, z, G)) * wdv[:, None, None]
+    # PResidual with p_z_diff
+    zs = zpe.sum(1) * N
+    Rp = ((pq / kappa - 0.5 * (J - 1 / J)) * zs * wdv)[:, None] * N * np.ones((1, 4))
+    # Stabilization with p_z_coarse
+    h2 = sum(((x[:, a] - x[:, b]) ** 2).sum(1) for a, b in ((0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3))) / 6.0
+    tau = 0.5 * c0 * h2 / mu
+    Cinv = np.linalg.inv(F.transpose(0, 2, 1) @ F)
+    gp = np.einsum("en,enj->ej", pe, G)
+    zc = zce.sum(1) * N
+    gzc = np.einsum("en,enj->ej", zce, G)
+    gw = gzc[:, None, :] * N + zc[:, None, None] * G         # d_j of the n-th coarse-weighted test function
+    Rp = Rp + (tau * J * wdv)[:, None] * np.einsum("eij,ei,enj->en", Cinv, gp, gw)
+    R = np.zeros((len(co), 4))
+    np.add.at(R[:, :3], cn, Ru)
+    np.add.at(R[:, 3], cn, Rp)
+    return R.reshape(-1)
+
+
+def test_error_localisation_against_independent_numpy_restatement(cube):
+    co, cn = cube["coords"], cube["tets"]
+    f = fields(co, len(cn), strain=0.01)
+    o = Oracle(co, cn, "neohookean", [MATERIAL])
+    o.set_solution(f["u"], f["p"])
+    Ro = o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])
+    Rn = _numpy_localize_neohookean(co, cn, f["u"], f["p"], f["zu_diff"], f["zp_diff"], f["zp_coarse"])
+    assert np.abs(Ro - Rn).max() < 1e-12 * np.abs(Rn).max()
+    # per equation too: the pressure rows are orders of magnitude below the momentum rows
+    for eq in range(4):
+        assert np.abs(Ro[eq::4] - Rn[eq::4]).max() < 1e-11 * np.abs(Rn[eq::4]).max()
+    # the check has teeth: the same chain with Stabilization weighted by p_z_diff instead of p_z_coarse (pw for pwc,
+    # goal_mechanics.cpp:214) or PResidual by p_z_coarse is far outside the tolerance
+    Rw = _numpy_localize_neohookean(co, cn, f["u"], f["p"], f["zu_diff"], f["zp_diff"], f["zp_diff"])
+    assert np.abs(Ro[3::4] - Rw[3::4]).max() > 1e-3 * np.abs(Rn[3::4]).max()
+    Rw = _numpy_localize_neohookean(co, cn, f["u"], f["p"], f["zu_diff"], f["zp_coarse"], f["zp_coarse"])
+    assert np.abs(Ro[3::4] - Rw[3::4]).max() > 1e-3 * np.abs(Rn[3::4]).max()
+    # partition of unity: the nodal sum equals the directly integrated weighted residual
+    tot = Rn.sum()
+    assert abs(Ro.sum() - tot) < 1e-12 * np.abs(Rn).sum()
