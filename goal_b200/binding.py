@@ -28,7 +28,7 @@ SYMBOLS = [
     "gx_compute_jacobian", "gx_localize_error", "gx_element_error", "gx_comm_init", "gx_nccl_unique_id",
     "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
-    "gx_stream", "gx_last_timing", "gx_set_option", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
+    "gx_stream", "gx_last_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
     "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs", "gx_add_solution", "gx_get_solution", "gx_sync_solution",
@@ -107,6 +107,7 @@ def load_library():
     L.gx_stream.argtypes = [vp]
     L.gx_last_timing.argtypes = [vp, dp]
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.gx_measure_fp64_peak.argtypes = [vp, dp, dp]
     L.gx_functional_avg_disp.argtypes = [vp, dp, vp]
     L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
     L.gx_apply_tbcs.argtypes = [vp, C.c_int32, ip, dp]
@@ -407,6 +408,12 @@ class Assembler:
 
     def stream(self):
         return self.L.gx_stream(self.h)
+
+    def measure_fp64_peak(self):
+        """(TFLOP/s of a register-only DFMA kernel on this device, SM MHz it ran at): the measured FP64 roof."""
+        t, f = C.c_double(0), C.c_double(0)
+        self._ck(self.L.gx_measure_fp64_peak(self.h, C.byref(t), C.byref(f)))
+        return t.value, f.value
 
     def set_option(self, key, value):
         self._ck(self.L.gx_set_option(self.h, key.encode(), int(value)))

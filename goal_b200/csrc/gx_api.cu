@@ -1085,6 +1085,59 @@ int gx_last_timing(gx_ctx* ctx, double t[4]) {
   return GX_OK;
 }
 
+// FP64 roof measured on the device: DFMA chains in registers, no memory traffic
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, long long* cyc, int iters) {
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = 1e-3 * threadIdx.x + k;
+  double const b = 1.0000001, c = 1e-9;
+  long long const t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) a[k] = fma(a[k], b, c);
+  }
+  long long const t1 = clock64();
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+  out[blockIdx.x * (size_t)blockDim.x + threadIdx.x] = s;
+  if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
+int gx_measure_fp64_peak(gx_ctx* ctx, double* tflops, double* sm_mhz) {
+  if (!ctx || !tflops) { if (ctx) ctx->err = "gx_measure_fp64_peak: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const blocks = ctx->num_sms * 8, threads = 256, iters = 4096;  // 64 warps per SM
+  double* out = nullptr;
+  long long* cyc = nullptr;
+  GX_CUDA(cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads));
+  GX_CUDA(cudaMalloc(&cyc, sizeof(long long) * (size_t)blocks));
+  int rc = GX_OK;
+  auto body = [&]() -> int {
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, cyc, iters);  // warm-up
+    GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+    fp64_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(out, cyc, iters);
+    GX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
+    GX_CUDA(cudaGetLastError());
+    GX_CUDA(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    GX_CUDA(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    long long c0 = 0;
+    GX_CUDA(cudaMemcpy(&c0, cyc, sizeof c0, cudaMemcpyDeviceToHost));
+    double const fmas = (double)blocks * threads * (double)iters * 64.0;
+    *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
+    // a block's cycles cover its own run only (8 blocks share an SM and run concurrently): cycles / wall time of the launch
+    if (sm_mhz) *sm_mhz = (double)c0 / (ms * 1e-3) / 1e6;
+    return GX_OK;
+  };
+  rc = body();
+  cudaFree(out); cudaFree(cyc);
+  return rc;
+}
+
 // Introspection: the patch schedule as the device reads it (built on demand; host-only contexts keep it for the
 // CPU tests of the schedule's invariants).  dims = {n_patches, words per patch, records per patch, threads per patch}
 int gx_patch_schedule(gx_ctx* ctx, const uint32_t** words, int32_t dims[4]) {

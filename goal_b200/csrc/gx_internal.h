@@ -180,15 +180,17 @@ bool build_patch_schedule(gx_ctx* c);
 
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
 #ifndef GX_PATCH_THREADS
-#define GX_PATCH_THREADS 128
-#define GX_PATCH_RECS 176
-#define GX_PATCH_MINB 3
+#define GX_PATCH_THREADS 96
+#define GX_PATCH_RECS 144
+#define GX_PATCH_MINB 4
+#define GX_PATCH_PARTS 24
 #endif
 constexpr int PATCH_THREADS = GX_PATCH_THREADS;  // work items per patch, one per thread
 constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (336 B each); slots are 8 bit
 constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
-constexpr int PATCH_PARTS = 32;     // secondary items (partial sums handed to a primary) per patch
+constexpr int PATCH_PARTS = GX_PATCH_PARTS;  // secondary items (partial sums handed to a primary) per patch
+constexpr int PATCH_DIAG_LANES = 32;  // lanes [0, 32) run the DIAG items, the other warps the PAIR items
 constexpr int PATCH_PART_LD = 36;   // doubles per partial sum: two 4x4 blocks + the residual entries
 constexpr int PATCH_WORDS = 4 + 4 * PATCH_THREADS + 4 * PATCH_THREADS + 2 * PATCH_RECS;  // uint32 words per patch
 static_assert(PATCH_RECS <= 256, "record slots are 8 bit");

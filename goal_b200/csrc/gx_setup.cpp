@@ -239,7 +239,7 @@ void build_block_lists(gx_ctx* c) {
 // An item holds at most PATCH_ITEM_LEN contributions; longer lists (the diagonal: one per incident element, edges
 // of high valence) are cut into a primary item and secondaries whose partial sums the primary adds in a fixed
 // order.  Layout per patch (uint32 words, PATCH_WORDS):
-//   [0..3]   n_recs, n_items, n_runs, 1 if some unit (primary + secondaries) straddles a warp (block barrier needed)
+//   [0..3]   n_recs, lanes in use (idle lanes in between have kind 0), n_runs, 1 if some unit (primary + secondaries) straddles a warp (block barrier needed)
 //   then     items[PATCH_THREADS][4]   8 rounds x 16 bit: slot | m << 8 | n << 10 | 0x8000; 0 = sits the round out
 //   then     outs[PATCH_THREADS][4]    w0 = first block of row a (extended block rows), w1 = first block of row b (PAIR)
 //                                      or the node id a (DIAG); w2 = j1 | nblk1 << 8 | j2 << 16 | nblk2 << 24 (position
@@ -261,7 +261,7 @@ bool build_patch_schedule(gx_ctx* c) {
   // Long contribution lists are cut into items of at most `split` contributions, as evenly as possible.  A thread
   // block lives as long as its longest item, so the cut follows the length of the ordinary items (an edge of a Kuhn
   // mesh has 4 or 6 elements) rather than the capacity of an item.
-  int split = 6, split_diag = 6, max_run = 16;  // records per bulk copy at most
+  int split = 6, split_diag = 8, max_run = 16;  // records per bulk copy at most
   if (char const* e = getenv("GX_SCHED_MAXRUN")) max_run = std::max(1, std::min(64, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT")) split = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT_DIAG")) split_diag = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
@@ -285,60 +285,76 @@ bool build_patch_schedule(gx_ctx* c) {
       while (hkey[h] != -1) h = (h + 1) & 1023u;
       hkey[h] = e; hval[h] = (int16_t)v;
     };
-    int nparts = 0;
+    int nparts = 0, cur_d = 0, cur_p = 0;  // secondaries, DIAG lanes and PAIR lanes of the patch being filled
     auto flush = [&]() {
       if (items.empty()) return;
-      // Lane order.  A "unit" is a primary item with its secondaries; a unit that sits inside one warp hands its
-      // partial sums over with a warp barrier only.  Units with secondaries come first, by size, diagonals before
-      // pairs (the usual case -- every diagonal cut in four -- is then aligned by construction); a unit that would
-      // straddle a warp boundary is preceded by the shortest single items as filler.  The warp in which the units end
-      // is topped up with the shortest singles as well (it runs two code paths), the remaining singles follow,
-      // pairs before zeros, longest first: the lanes of a warp then run the same number of contributions.
+      // Lane order: typed warps.  The first PATCH_DIAG_LANES lanes (whole warps) hold the DIAG items, the rest the
+      // PAIR items, so that no warp runs both code paths (a warp that did would take twice as long and hold the
+      // block's shared memory while the others idle); ZERO items take whatever lanes stay free.  A "unit" is a
+      // primary item with its secondaries; a unit that sits inside one warp hands its partial sums over with a warp
+      // barrier only.  Inside a region: units with secondaries first, by size (equal power-of-two sizes are aligned by
+      // construction; a unit that would straddle a warp boundary is preceded by the shortest single items of the
+      // region as filler), then the single items, longest first: the lanes of a warp then run the same number of
+      // contributions.  ord[t] = item of lane t, -1 = idle lane.
       std::vector<int> ord;
       bool block_sync = false;
       {
-        struct Unit { int prim; std::vector<int> sec; int type, len; };
-        std::vector<Unit> groups, singles;
+        struct Unit { int prim; std::vector<int> sec; int len; };
         std::vector<int> prim_of_part(PATCH_PARTS + 1, -1);
         for (size_t i = 0; i < items.size(); ++i)
           if (items[i].kind == 1) for (int q = 0; q < items[i].nsec; ++q) prim_of_part[items[i].part + q] = (int)i;
         std::vector<std::vector<int>> secs(items.size());
         for (size_t i = 0; i < items.size(); ++i) if (items[i].kind == 2) secs[prim_of_part[items[i].part]].push_back((int)i);
-        for (size_t i = 0; i < items.size(); ++i) {
-          if (items[i].kind != 1) continue;
-          Unit u{(int)i, secs[i], items[i].type, items[i].n};
-          (u.sec.empty() ? singles : groups).push_back(u);
-        }
-        std::stable_sort(groups.begin(), groups.end(), [](Unit const& x, Unit const& y) {
-          if (x.sec.size() != y.sec.size()) return x.sec.size() > y.sec.size();
-          if (x.type != y.type) return x.type < y.type;  // diagonals (1) before pairs (2)
-          return x.len > y.len;
-        });
-        std::stable_sort(singles.begin(), singles.end(), [](Unit const& x, Unit const& y) {
-          int const tx = x.type == 0 ? 3 : x.type, ty = y.type == 0 ? 3 : y.type;  // diagonals, pairs, zeros
-          if (tx != ty) return tx < ty;
-          return x.len > y.len;
-        });
-        // the filler pool: the shortest non-zero singles, taken from the back
-        size_t pool_end = singles.size();
-        while (pool_end > 0 && singles[pool_end - 1].type == 0) --pool_end;
-        size_t pool_begin = 0;
-        auto fill = [&](int lanes) {
-          while (lanes > 0 && pool_end > pool_begin) { ord.push_back(singles[--pool_end].prim); --lanes; }
-          return lanes == 0;
+        std::vector<int> zeros;
+        auto layout = [&](int type, int first_lane, int n_lanes) {
+          std::vector<Unit> groups, singles;
+          for (size_t i = 0; i < items.size(); ++i) {
+            if (items[i].kind != 1 || items[i].type != type) continue;
+            Unit u{(int)i, secs[i], items[i].n};
+            (u.sec.empty() ? singles : groups).push_back(u);
+          }
+          std::stable_sort(groups.begin(), groups.end(), [](Unit const& x, Unit const& y) {
+            if (x.sec.size() != y.sec.size()) return x.sec.size() > y.sec.size();
+            return x.len > y.len;
+          });
+          std::stable_sort(singles.begin(), singles.end(), [](Unit const& x, Unit const& y) { return x.len > y.len; });
+          ord.resize(first_lane, -1);
+          size_t pool_end = singles.size();
+          auto fill = [&](int lanes) {  // the shortest singles, from the back; idle lanes when they run out
+            while (lanes > 0 && pool_end > 0) { ord.push_back(singles[--pool_end].prim); --lanes; }
+            while (lanes-- > 0) ord.push_back(-1);
+          };
+          for (Unit const& u : groups) {
+            int const sz = 1 + (int)u.sec.size();
+            int const room = 32 - (int)(ord.size() % 32);
+            if (sz > 32) block_sync = true;
+            else if (sz > room) fill(room);
+            ord.push_back(u.prim);
+            for (int q : u.sec) ord.push_back(q);
+          }
+          for (size_t i = 0; i < pool_end; ++i) ord.push_back(singles[i].prim);
+          (void)n_lanes;
         };
-        for (Unit const& u : groups) {
-          int const sz = 1 + (int)u.sec.size();
-          int const room = 32 - (int)(ord.size() % 32);
-          if (sz > room && sz <= 32 && !fill(room)) block_sync = true;  // nothing left to fill with: this unit straddles
-          if (sz > 32) block_sync = true;
-          ord.push_back(u.prim);
-          for (int q : u.sec) ord.push_back(q);
+        layout(1, 0, PATCH_DIAG_LANES);
+        int const diag_end = (int)ord.size();
+        layout(2, std::max(diag_end, PATCH_DIAG_LANES), PATCH_THREADS - PATCH_DIAG_LANES);
+        for (size_t i = 0; i < items.size(); ++i) if (items[i].type == 0) zeros.push_back((int)i);
+        // zeros into the idle lanes, then behind
+        size_t zi = 0;
+        for (size_t t = 0; t < ord.size() && zi < zeros.size(); ++t) if (ord[t] < 0) ord[t] = zeros[zi++];
+        while (zi < zeros.size()) ord.push_back(zeros[zi++]);
+        if ((int)ord.size() > PATCH_THREADS) {
+          // Alignment padding does not fit: drop it (lanes packed in region order) and let the block barrier
+          // hand the partial sums over.  Rare: needs units that straddle warps in an almost full patch.
+          std::vector<int> packed;
+          for (int v : ord) if (v >= 0) packed.push_back(v);
+          ord.swap(packed);
+          block_sync = true;
         }
-        if (!groups.empty() && ord.size() % 32) fill(32 - (int)(ord.size() % 32));
-        for (size_t i = pool_begin; i < pool_end; ++i) ord.push_back(singles[i].prim);
-        for (size_t i = pool_end; i < singles.size(); ++i) if (singles[i].type == 0) ord.push_back(singles[i].prim);
       }
+      int const n_real_items = (int)items.size();
+      items.push_back(Item{});  // the idle lane: kind 0, no contributions
+      for (int& v : ord) if (v < 0) v = n_real_items;
       // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
       // record is its slot modulo 8 (record stride 21 x 16 B, odd).  Runs of records are placed where they meet the
       // fewest records of the items they feed; then, within every group of 8 lanes, each item's contributions are
@@ -474,7 +490,7 @@ bool build_patch_schedule(gx_ctx* c) {
       if (stats) {  // wavefronts per 128-bit load and round: the fullest bank group (distinct records)
         st_runs[ch] += (int64_t)run_e0.size();
         st_recs[ch] += (int64_t)nrec;
-        st_items[ch] += (int64_t)items.size();
+        st_items[ch] += (int64_t)n_real_items;
         for (auto const& it : items) st_contrib[ch] += it.n;
         for (size_t g0 = 0; g0 < ord.size(); g0 += 8) {
           int const gn = (int)std::min<size_t>(8, ord.size() - g0);
@@ -502,7 +518,7 @@ bool build_patch_schedule(gx_ctx* c) {
       size_t const base = out[ch].size();
       out[ch].resize(base + PATCH_WORDS, 0u);
       uint32_t* w = out[ch].data() + base;
-      w[0] = (uint32_t)nrec; w[1] = (uint32_t)items.size(); w[2] = (uint32_t)run_e0.size(); w[3] = block_sync ? 1u : 0u;
+      w[0] = (uint32_t)nrec; w[1] = (uint32_t)ord.size(); w[2] = (uint32_t)run_e0.size(); w[3] = block_sync ? 1u : 0u;
       uint32_t* wi = w + 4;
       uint32_t* wo = wi + 4 * PATCH_THREADS;
       uint32_t* wr = wo + 4 * PATCH_THREADS;  // runs[PATCH_RECS][2]: first element, first slot | length << 8
@@ -513,7 +529,7 @@ bool build_patch_schedule(gx_ctx* c) {
         wo[4 * t] = it.w0; wo[4 * t + 1] = it.w1; wo[4 * t + 2] = it.w2;
         wo[4 * t + 3] = (uint32_t)it.kind | ((uint32_t)it.type << 2) | ((uint32_t)it.part << 4) | ((uint32_t)it.nsec << 12);
       }
-      items.clear(); recs.clear(); hclear(); nparts = 0;
+      items.clear(); recs.clear(); hclear(); nparts = 0; cur_d = 0; cur_p = 0;
     };
     hclear();
     bool bad = false;
@@ -527,7 +543,7 @@ bool build_patch_schedule(gx_ctx* c) {
       int add = 0;  // new records this node would add
       for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) if (hfind(c->adj[k].x >> 2) < 0) ++add;
       blks.clear();
-      int nit = 0, nsecs = 0;
+      int nit = 0, nsecs = 0, nd = 0, np = 0;  // items, secondaries, DIAG lanes, PAIR lanes this node needs
       int64_t const nloc = c->nrow[a + 1] - c->nrow[a];  // local blocks; the extended row may continue with phantom ones
       for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
         int const cnt = (int)(c->bc_off[t + 1] - c->bc_off[t]);
@@ -543,9 +559,15 @@ bool build_patch_schedule(gx_ctx* c) {
         int const parts = n_parts(cnt, type == 1);
         blks.push_back({t, type, cnt, parts});
         nit += parts; nsecs += parts - 1;
+        if (type == 1) nd += parts;
+        if (type == 2) np += parts;
       }
-      if (nit > PATCH_THREADS || (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > PATCH_PARTS) { bad = true; break; }
-      if ((int)items.size() + nit > PATCH_THREADS || (int)recs.size() + add > PATCH_RECS || nparts + nsecs > PATCH_PARTS) flush();
+      // a node must fit an empty patch; the lane regions are filled with a little slack for alignment padding
+      if (nd > PATCH_DIAG_LANES || np > PATCH_THREADS - PATCH_DIAG_LANES || nit > PATCH_THREADS ||
+          (int)(c->adj_off[a + 1] - c->adj_off[a]) > PATCH_RECS || nsecs > PATCH_PARTS) { bad = true; break; }
+      if (cur_d + nd > PATCH_DIAG_LANES || cur_p + np > PATCH_THREADS - PATCH_DIAG_LANES || (int)items.size() + nit > PATCH_THREADS ||
+          (int)recs.size() + add > PATCH_RECS || nparts + nsecs > PATCH_PARTS) flush();
+      cur_d += nd; cur_p += np;
       for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
         int32_t const e = c->adj[k].x >> 2;
         if (hfind(e) < 0) { hput(e, (int)recs.size()); recs.push_back(e); }

@@ -253,6 +253,10 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value);
  * build_patch_schedule); dims = {patches, words per patch, record slots per patch, threads per patch}.  Valid until
  * the next call on ctx.  Host-only contexts can build it too: the CPU tests check its invariants. */
 int gx_patch_schedule(gx_ctx* ctx, const uint32_t** words, int32_t dims[4]);
+/* Measurement aid ("the FP64 peak must be measured on the box in the same run"): a register-only
+ * DFMA kernel, 8 independent chains per thread, every SM full, timed with CUDA events on gx_stream.
+ * *tflops = 2 * fused multiply-adds / time; *sm_mhz = SM clock seen by the kernel (clock64 / elapsed). */
+int gx_measure_fp64_peak(gx_ctx* ctx, double* tflops, double* sm_mhz);
 
 #ifdef __cplusplus
 }

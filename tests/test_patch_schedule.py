@@ -29,6 +29,7 @@ def _check(co, cn):
     got = {}
     writers = {}
     n_paired = 0
+    n_mixed = 0
     for pw in W:
         n_recs, n_items, n_runs = int(pw[0]), int(pw[1]), int(pw[2])
         assert n_recs <= RECS and n_items <= T
@@ -50,9 +51,10 @@ def _check(co, cn):
         for t in range(T):
             w3 = int(ot[t, 3])
             kind, typ, part, nsec = w3 & 3, (w3 >> 2) & 3, (w3 >> 4) & 0xff, (w3 >> 12) & 0x3f
-            if kind == 0:
-                assert t >= n_items and not it[t].any()
+            if kind == 0:  # idle lane (alignment padding between the typed warps, or past the last item)
+                assert not it[t].any()
                 continue
+            assert t < n_items
             types_seen.append(typ)
             ents = []
             for k in range(4):
@@ -89,8 +91,14 @@ def _check(co, cn):
         assert all(v[0] == "have" for v in parts.values())
         # a primary and its secondaries share a warp unless the header says the block barrier is needed
         assert int(pw[3]) in (0, 1) and (int(pw[3]) == 1 or all(len(v) == 1 for v in part_warps.values()))
+        # typed warps: lanes [0, 32) hold no PAIR item, the other warps no DIAG item (when the schedule could align them)
+        lane_types = [(t, (int(ot[t, 3]) >> 2) & 3) for t in range(T) if int(ot[t, 3]) & 3]
+        if int(pw[3]) == 0:
+            mixed = {t // 32 for t, ty in lane_types if ty == 1} & {t // 32 for t, ty in lane_types if ty == 2}
+            n_mixed += len(mixed)
     assert set(writers) == set(want) and all(v == 1 for v in writers.values())  # write-once
     assert got == want
+    assert n_mixed <= max(1, len(W) // 10)  # warps that run both code paths are the exception
     return n_paired, len(W)
 
 
