@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
 // (cp.async.bulk, one per run of consecutive elements, completion on an mbarrier: every record crosses the L1 data
 // pipe once per patch instead of once per incident node and lane), then every thread runs one work item:
 //   PAIR : the elements around one mesh edge (a,b).  Per element the two node quadruples, s, G and the scalars are
-//          read once (16 128-bit shared loads) and give BOTH mirror blocks (a,b) and (b,a), which share the node
+//          read once (15 128-bit shared loads) and give BOTH mirror blocks (a,b) and (b,a), which share the node
 //          vectors s w, G w and the symmetric scalars -- 32 accumulators in registers;
 //   DIAG : the elements around one node: block (a,a) and the node's four residual entries;
 //   ZERO : a phantom block of a partitioned context, written as zeros.
@@ -381,16 +381,15 @@ GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (s
 
 #if defined(__CUDACC__)
 // the pieces of a staged record as registers (128-bit shared loads)
-struct TRegs { double s[6], G[6], sc[14]; };
+struct TRegs { double s[6], G[6], sc[SC_N]; };
 __device__ __forceinline__ void trec_load_common(double2 const* q, TRegs& t, bool want_resid) {
 #pragma unroll
   for (int k = 0; k < 3; ++k) { double2 const v = q[8 + k]; t.s[2 * k] = v.x; t.s[2 * k + 1] = v.y; }
 #pragma unroll
   for (int k = 0; k < 3; ++k) { double2 const v = q[11 + k]; t.G[2 * k] = v.x; t.G[2 * k + 1] = v.y; }
 #pragma unroll
-  for (int k = 0; k < 6; ++k) { double2 const v = q[14 + k]; t.sc[2 * k] = v.x; t.sc[2 * k + 1] = v.y; }
-  if (want_resid) { double2 const v = q[20]; t.sc[12] = v.x; t.sc[13] = v.y; }
-  else { t.sc[12] = 0.0; t.sc[13] = 0.0; }
+  for (int k = 0; k < 5; ++k) { double2 const v = q[14 + k]; t.sc[2 * k] = v.x; t.sc[2 * k + 1] = v.y; }
+  t.sc[SC_RB] = want_resid ? q[19].x : 0.0;
 }
 __device__ __forceinline__ void trec_load_node(double2 const* q, int n, double nq[4]) {
   double2 const a = q[2 * n], b = q[2 * n + 1];

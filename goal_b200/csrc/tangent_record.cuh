@@ -23,8 +23,8 @@
 //   [4n .. 4n+2] w_n   [4n+3] tqw_n            n = 0..3       chunks 0-7
 //   [16..21] s  (00 11 22 01 02 12)                           chunks 8-10
 //   [22..27] G                                                chunks 11-13
-//   [28..39] a0 b1 b0 vb a1 upc va ppc tjv tq0 tq1 tq2        chunks 14-19
-//   [40] rb  [41] Jpv                                         chunk 20 (residual rows of the diagonal items)
+//   [28..37] vb a1 Jpv upc va ppc tjv tq0 tq1 tq2             chunks 14-18   (a0, b1, b0 follow from vb, a1, Jpv)
+//   [38] rb  [39..41] unused                                  chunk 19 (residual rows of the diagonal items), chunk 20
 #pragma once
 
 #include "element_math.cuh"
@@ -48,20 +48,17 @@ template <class S> GX_HD void pack_trec(Core<S> const& c, S rec[TREC]) {
   rec[25] = k2 * (s[0] * s[3] + s[3] * s[1] + s[4] * s[5]) + k1 * s[3];
   rec[26] = k2 * (s[0] * s[4] + s[3] * s[5] + s[4] * s[2]) + k1 * s[4];
   rec[27] = k2 * (s[3] * s[4] + s[1] * s[5] + s[5] * s[2]) + k1 * s[5];
-  S const a1 = c.A1v * c.tb3;
-  rec[28] = a1 - c.Jpv;                        // a0
-  rec[29] = S(-2.0 / 3.0) * c.vb;              // b1
-  rec[30] = c.Jpv + S(-2.0 / 3.0) * a1;        // b0
-  rec[31] = c.vb;
-  rec[32] = a1;
-  rec[33] = c.upc; rec[34] = c.va; rec[35] = c.ppc; rec[36] = c.tjv;
-  rec[37] = c.tjv * c.q[0]; rec[38] = c.tjv * c.q[1]; rec[39] = c.tjv * c.q[2];
-  rec[40] = c.rb; rec[41] = c.Jpv;
+  rec[28] = c.vb;
+  rec[29] = c.A1v * c.tb3;  // a1
+  rec[30] = c.Jpv;
+  rec[31] = c.upc; rec[32] = c.va; rec[33] = c.ppc; rec[34] = c.tjv;
+  rec[35] = c.tjv * c.q[0]; rec[36] = c.tjv * c.q[1]; rec[37] = c.tjv * c.q[2];
+  rec[38] = c.rb; rec[39] = S(0.0); rec[40] = S(0.0); rec[41] = S(0.0);
 }
 
 // One node in its two roles.  Row role: w, sw = s w, cq = va + tqw.  Column role: w, aw = a0 w, B, g, tqw.
 // The functions below take the pieces of a record by pointer -- nq = rec + 4 n (node n), s = rec + 16, G = rec + 22,
-// sc = rec + 28 (the 14 scalars) -- so that the device code can hand them registers it filled with 128-bit shared loads.
+// sc = rec + 28 (the 11 scalars) -- so that the device code can hand them registers it filled with 128-bit shared loads.
 struct TNode {
   double w[3], tqw, sw[3], g[3];
 };
@@ -70,13 +67,14 @@ GX_HD void trec_node(double const* nq, double const* s, double const* G, TNode& 
   sym_mv(s, t.w, t.sw);
   sym_mv(G, t.w, t.g);
 }
-enum { SC_A0 = 0, SC_B1, SC_B0, SC_VB, SC_A1, SC_UPC, SC_VA, SC_PPC, SC_TJV, SC_TQ0, SC_TQ1, SC_TQ2, SC_RB, SC_JPV };
+enum { SC_VB = 0, SC_A1, SC_JPV, SC_UPC, SC_VA, SC_PPC, SC_TJV, SC_TQ0, SC_TQ1, SC_TQ2, SC_RB, SC_N };
 
 // acc += K[(row node),(col node)]  (TRANSPOSE: acc += its transpose).  d, W, Wtq are symmetric in the two nodes and
 // shared by the two blocks of a pair.
 template <bool TRANSPOSE>
 GX_HD void trec_block_add(double const* sc, TNode const& r, TNode const& c, double d, double W, double const Wtq[3], double acc[16]) {
-  double const a0 = sc[SC_A0], b1 = sc[SC_B1], b0 = sc[SC_B0];
+  double const m23 = -2.0 / 3.0;
+  double const a0 = sc[SC_A1] - sc[SC_JPV], b1 = m23 * sc[SC_VB], b0 = m23 * sc[SC_A1] + sc[SC_JPV];
   double aw[3], B[3];
   for (int k = 0; k < 3; ++k) { aw[k] = a0 * c.w[k]; B[k] = b1 * c.sw[k] + b0 * c.w[k]; }
   for (int i = 0; i < 3; ++i) {

@@ -35,20 +35,22 @@ def _finish(rank, n_ranks, coords, conn, node_gid, elem_gid, holders):
 
 
 def block_part(c, grid, rank):
-    """Part `rank` of a (grid[0]*c, grid[1]*c, grid[2]*c)-cell Kuhn box split into c^3-cell blocks.
+    """Part `rank` of a Kuhn box split into px*py*pz equal blocks.  c = cells per block edge: one int (cubic blocks of
+    c^3 cells, "weak scaling": every block sees the same element size h = 1/c) or (cx, cy, cz) (the blocks of a fixed
+    global mesh, "strong scaling").
 
-    Rank r sits at block (r % Px, (r // Px) % Py, r // (Px*Py)).  Coordinates are in units of the block
-    edge (h = 1/c), so every block sees the same element size (weak scaling)."""
+    Rank r sits at block (r % Px, (r // Px) % Py, r // (Px*Py)).  Coordinates are in units of the x block edge."""
     px, py, pz = grid
     n_ranks = px * py * pz
+    cx, cy, cz = (c, c, c) if np.isscalar(c) else c
     b = (rank % px, (rank // px) % py, rank // (px * py))
-    g = (px * c, py * c, pz * c)  # global cells per axis
-    coords, conn = kuhn_block(c, c, c, (b[0] * c, b[1] * c, b[2] * c), c)
-    k, j, i = np.meshgrid(np.arange(c + 1), np.arange(c + 1), np.arange(c + 1), indexing="ij")
-    gi, gj, gk = i + b[0] * c, j + b[1] * c, k + b[2] * c
+    g = (px * cx, py * cy, pz * cz)  # global cells per axis
+    coords, conn = kuhn_block(cx, cy, cz, (b[0] * cx, b[1] * cy, b[2] * cz), cx)
+    k, j, i = np.meshgrid(np.arange(cz + 1), np.arange(cy + 1), np.arange(cx + 1), indexing="ij")
+    gi, gj, gk = i + b[0] * cx, j + b[1] * cy, k + b[2] * cz
     node_gid = (gi + (g[0] + 1) * (gj + (g[1] + 1) * gk)).reshape(-1).astype(np.int64)
-    ck, cj, ci = np.meshgrid(np.arange(c), np.arange(c), np.arange(c), indexing="ij")
-    cell_gid = ((ci + b[0] * c) + g[0] * ((cj + b[1] * c) + g[1] * (ck + b[2] * c))).reshape(-1).astype(np.int64)
+    ck, cj, ci = np.meshgrid(np.arange(cz), np.arange(cy), np.arange(cx), indexing="ij")
+    cell_gid = ((ci + b[0] * cx) + g[0] * ((cj + b[1] * cy) + g[1] * (ck + b[2] * cz))).reshape(-1).astype(np.int64)
     elem_gid = (6 * cell_gid[:, None] + np.arange(6)[None, :]).reshape(-1)
     li, lj, lk = i.reshape(-1), j.reshape(-1), k.reshape(-1)
     holders = {}
@@ -62,11 +64,11 @@ def block_part(c, grid, rank):
                     continue
                 q = nb[0] + px * (nb[1] + py * nb[2])
                 m = np.ones(len(li), dtype=bool)
-                for d, l in ((dx, li), (dy, lj), (dz, lk)):
+                for d, l, cd in ((dx, li, cx), (dy, lj, cy), (dz, lk, cz)):
                     if d == -1:
                         m &= l == 0
                     elif d == 1:
-                        m &= l == c
+                        m &= l == cd
                 ids = np.nonzero(m)[0]
                 holders[q] = ids[np.argsort(node_gid[ids], kind="stable")]
     return _finish(rank, n_ranks, coords, conn, node_gid, elem_gid, holders)
