@@ -154,7 +154,7 @@ struct gx_ctx {
   bool have_result = false;
   bool have_values = false;
   int64_t opt_block = 128;
-  int64_t opt_prefetch = 592;  // stage B L2 prefetch distance in patches (about one generation of resident blocks: 148 SMs x 4)
+  int64_t opt_prefetch = 256;  // stage B L2 prefetch distance in patches (measured best on 12.6M tets: 150-300; one generation of resident blocks is 592)
   int64_t opt_kernel = 0;  // 0 = owner-computes schedules (patch pairs / gather form), 1 = coloured elements
   int num_sms = 148;
   std::string err;

@@ -355,24 +355,38 @@ bool build_patch_schedule(gx_ctx* c) {
       int const n_real_items = (int)items.size();
       items.push_back(Item{});  // the idle lane: kind 0, no contributions
       for (int& v : ord) if (v < 0) v = n_real_items;
-      // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp, and the bank group of a staged
-      // record is its slot modulo 8 (record stride 21 x 16 B, odd).  Runs of records are placed where they meet the
-      // fewest records of the items they feed; then, within every group of 8 lanes, each item's contributions are
-      // ordered so that the records read in the same round sit in different groups where possible (per round a
-      // bipartite matching of items to bank groups).
+      // Shared-memory bank conflicts: a 128-bit load is served per quarter-warp (8 lanes), and the bank group of a
+      // staged record is a permutation of its slot modulo 8 (record stride 21 x 16 B, odd).  The lanes of a quarter
+      // read one record each per round; they collide only when two of them read different records of one bank group
+      // in the same round.  So (1) the records get their bank groups such that, for every quarter-warp, the
+      // contributions of its eight items are spread evenly over the eight groups (no group more than the warp's
+      // rounds, if possible), and (2) every quarter-warp orders its contributions by an edge colouring (below).
       int const nrec = (int)recs.size();
       std::vector<int> res(nrec, -1);
       std::vector<int> slot_of(nrec, -1);
       std::vector<uint32_t> run_e0, run_sl;  // runs of consecutive elements in consecutive slots: one bulk copy each
-      std::vector<std::vector<int>> in_items(nrec);
-      for (size_t i = 0; i < items.size(); ++i)
-        for (int q = 0; q < items[i].n; ++q) in_items[items[i].ent[q] & 0xff].push_back((int)i);
-      // cnt8[l][r] = records already placed in bank group r that share an item with record l (with multiplicity)
-      std::vector<std::array<int, 8>> cnt8(nrec, std::array<int, 8>{});
+      int const nquart = ((int)ord.size() + 7) / 8;
+      std::vector<std::vector<int>> feeds(nrec);  // quarter-warps a record feeds, with multiplicity
+      for (size_t t = 0; t < ord.size(); ++t) {
+        Item const& it = items[ord[t]];
+        for (int q = 0; q < it.n; ++q) feeds[it.ent[q] & 0xff].push_back((int)(t / 8));
+      }
+      std::vector<std::array<int, 8>> qload(nquart, std::array<int, 8>{});  // contributions of quarter Q that read bank group r
+      std::vector<int> qcap(nquart, 0);  // rounds of the quarter's warp
+      for (int Q = 0; Q < nquart; ++Q) {
+        int R = 0;
+        for (size_t t = ((size_t)Q / 4) * 32; t < std::min(ord.size(), ((size_t)Q / 4) * 32 + 32); ++t) R = std::max(R, items[ord[t]].n);
+        qcap[Q] = R;
+      }
+      // cost of giving record l the bank group r: readers already there, and heavily, readers beyond the rounds
+      auto conflicts = [&](int l, int r) {
+        int c2 = 0;
+        for (int Q : feeds[l]) c2 += qload[Q][r] + (qload[Q][r] >= qcap[Q] ? 16 : 0);
+        return c2;
+      };
       auto place = [&](int l, int r) {
         res[l] = r;
-        for (int i : in_items[l])
-          for (int q = 0; q < items[i].n; ++q) cnt8[items[i].ent[q] & 0xff][r]++;
+        for (int Q : feeds[l]) qload[Q][r]++;
       };
       {
         // Records of consecutive elements are consecutive in global memory: placed in consecutive slots they arrive with
@@ -398,7 +412,7 @@ bool build_patch_schedule(gx_ctx* c) {
             for (int j = 0; j < run.len && free_; ++j) free_ = !taken[s0 + j];
             if (!free_) continue;
             int cost = 0;
-            for (int j = 0; j < run.len; ++j) cost += cnt8[byel[run.first + j]][(s0 + j) & 7];
+            for (int j = 0; j < run.len; ++j) cost += conflicts(byel[run.first + j], (s0 + j) & 7);
             if (cost < best_cost) { best_cost = cost; best = s0; }
             if (cost == 0) break;
           }
@@ -415,72 +429,70 @@ bool build_patch_schedule(gx_ctx* c) {
           run_sl.push_back((uint32_t)best | ((uint32_t)run.len << 8));
         }
       }
+      // Round assignment per quarter-warp (8 lanes): a proper edge colouring of the bipartite multigraph
+      // items x bank groups (one edge per contribution, colour = round).  Koenig: with R rounds available (the
+      // warp's longest item) a conflict-free assignment exists iff no bank group carries more than R of the eight
+      // items' contributions; the colouring below finds it (alternating-path recolouring).  Where a group is
+      // over-subscribed the surplus edges go to the round with the fewest readers of that group.  An item with
+      // fewer contributions than rounds sits the other rounds out (empty entries).
       for (size_t g0 = 0; g0 < ord.size() && !nomatch; g0 += 8) {
         int const gn = (int)std::min<size_t>(8, ord.size() - g0);
-        // Rounds available to this group of 8 lanes: its warp runs as many rounds as its longest item, so an item
-        // may sit out a round (an empty entry) as long as it still finishes -- which lets the schedule dodge
-        // conflicts that a packed order cannot.
         int R = 0;
         for (size_t t = (g0 / 32) * 32; t < std::min(ord.size(), (g0 / 32) * 32 + 32); ++t) R = std::max(R, items[ord[t]].n);
-        bool used[8][PATCH_ITEM_LEN] = {};
-        uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
-        int remaining[8] = {};
-        for (int i = 0; i < gn; ++i) remaining[i] = items[ord[g0 + i]].n;
-        for (int k = 0; k < R; ++k) {
-          int const left = R - k;
-          int match_res[8];   // bank group -> item
-          int pick[8];        // item -> contribution index
-          for (int r = 0; r < 8; ++r) match_res[r] = -1;
-          for (int i = 0; i < 8; ++i) pick[i] = -1;
-          // Kuhn's augmenting paths; items x bank groups, edges through unused contributions
-          int order[8][PATCH_ITEM_LEN], no[8] = {};
-          for (int i = 0; i < gn; ++i) {
-            Item const& it = items[ord[g0 + i]];
-            for (int q = 0; q < it.n; ++q) if (!used[i][q]) order[i][no[i]++] = q;
-          }
-          auto try_item = [&](auto&& self, int i, bool* seen) -> bool {
-            Item const& it = items[ord[g0 + i]];
-            for (int oq = 0; oq < no[i]; ++oq) {  // a free bank group first
-              int const q = order[i][oq], r = res[it.ent[q] & 0xff];
-              if (match_res[r] < 0) { seen[r] = true; match_res[r] = i; pick[i] = q; return true; }
-            }
-            for (int oq = 0; oq < no[i]; ++oq) {
-              int const q = order[i][oq], r = res[it.ent[q] & 0xff];
-              if (seen[r]) continue;
-              seen[r] = true;
-              if (self(self, match_res[r], seen)) { match_res[r] = i; pick[i] = q; return true; }
-            }
-            return false;
-          };
-          for (int pass = 0; pass < 2; ++pass)  // items that cannot wait first
-            for (int i = 0; i < gn; ++i) {
-              if (remaining[i] == 0 || (remaining[i] == left) != (pass == 0)) continue;
-              bool seen[8] = {};
-              try_item(try_item, i, seen);
-            }
-          bool matched[8] = {};
-          for (int r = 0; r < 8; ++r) if (match_res[r] >= 0) matched[match_res[r]] = true;
-          for (int i = 0; i < gn; ++i) {
-            Item const& it = items[ord[g0 + i]];
-            if (remaining[i] == 0) continue;
-            int q = matched[i] ? pick[i] : -1;
-            if (q < 0) {
-              if (remaining[i] < left) continue;  // sits this round out
-              // conflict: prefer a record that somebody else reads in this round (broadcast), else any
-              for (int c2 = 0; c2 < it.n && q < 0; ++c2) {
-                if (used[i][c2]) continue;
-                for (int j = 0; j < gn && q < 0; ++j)
-                  if (j != i && matched[j] && pick[j] >= 0 && (items[ord[g0 + j]].ent[pick[j]] & 0xff) == (it.ent[c2] & 0xff)) q = c2;
-              }
-              if (q < 0) for (q = 0; used[i][q]; ++q) {}
-            }
-            used[i][q] = true;
-            remaining[i]--;
-            sched_ent[i][k] = it.ent[q];
-          }
+        if (R == 0) continue;
+        struct Edge { int u, v, q, col; };
+        std::vector<Edge> edges;
+        int degv[8] = {};
+        for (int i = 0; i < gn; ++i) {
+          Item const& it = items[ord[g0 + i]];
+          for (int q = 0; q < it.n; ++q) { int const v = res[it.ent[q] & 0xff]; edges.push_back({i, v, q, -1}); degv[v]++; }
         }
+        int C = R;
+        for (int v = 0; v < 8; ++v) C = std::max(C, degv[v]);
+        C = std::min(C, 64);
+        std::vector<int> atu(8 * C, -1), atv(8 * C, -1);  // edge with colour c at item u / at bank group v
+        for (size_t ei = 0; ei < edges.size(); ++ei) {
+          Edge& e = edges[ei];
+          int ca = -1, cb = -1;
+          for (int c2 = 0; c2 < C && ca < 0; ++c2) if (atu[e.u * C + c2] < 0) ca = c2;
+          for (int c2 = 0; c2 < C && cb < 0; ++c2) if (atv[e.v * C + c2] < 0) cb = c2;
+          if (ca < 0 || cb < 0) { e.col = -2; continue; }  // more than 64 contributions in one bank group: placed below
+          if (atv[e.v * C + ca] >= 0) {
+            // colour ca is taken at v: swap ca <-> cb along the alternating path that starts at v with colour ca
+            std::vector<int> path;
+            int cur = atv[e.v * C + ca];
+            bool at_v = true;  // the path edge was reached through its v end
+            int want = ca;
+            while (cur >= 0) {
+              path.push_back(cur);
+              Edge const& pe = edges[cur];
+              want = want == ca ? cb : ca;
+              cur = at_v ? atu[pe.u * C + want] : atv[pe.v * C + want];
+              at_v = !at_v;
+            }
+            for (int pi : path) { Edge& pe = edges[pi]; atu[pe.u * C + pe.col] = -1; atv[pe.v * C + pe.col] = -1; }
+            for (int pi : path) { Edge& pe = edges[pi]; pe.col = pe.col == ca ? cb : ca; atu[pe.u * C + pe.col] = pi; atv[pe.v * C + pe.col] = pi; }
+          }
+          e.col = ca;
+          atu[e.u * C + ca] = (int)ei; atv[e.v * C + ca] = (int)ei;
+        }
+        uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
+        bool used_round[8][PATCH_ITEM_LEN] = {};
+        int readers[PATCH_ITEM_LEN][8] = {};  // readers of bank group v in round k (distinct records not tracked: a bound)
+        for (Edge const& e : edges)
+          if (e.col >= 0 && e.col < R) {
+            sched_ent[e.u][e.col] = items[ord[g0 + e.u]].ent[e.q]; used_round[e.u][e.col] = true; readers[e.col][e.v]++;
+          }
+        for (Edge const& e : edges)
+          if (e.col < 0 || e.col >= R) {  // surplus: the free round of this item where the group has the fewest readers
+            int best = -1;
+            for (int k = 0; k < R; ++k)
+              if (!used_round[e.u][k] && (best < 0 || readers[k][e.v] < readers[best][e.v])) best = k;
+            sched_ent[e.u][best] = items[ord[g0 + e.u]].ent[e.q]; used_round[e.u][best] = true; readers[best][e.v]++;
+          }
         for (int i = 0; i < gn; ++i) {
           Item& it = items[ord[g0 + i]];
+          if (it.n == 0) continue;
           for (int k = 0; k < PATCH_ITEM_LEN; ++k) it.ent[k] = sched_ent[i][k];
         }
       }
