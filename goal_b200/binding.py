@@ -28,7 +28,7 @@ SYMBOLS = [
     "gx_compute_jacobian", "gx_localize_error", "gx_element_error", "gx_comm_init", "gx_nccl_unique_id",
     "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
-    "gx_stream", "gx_last_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
+    "gx_stream", "gx_last_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_apply_bforce", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
     "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs", "gx_add_solution", "gx_get_solution", "gx_sync_solution",
@@ -108,6 +108,7 @@ def load_library():
     L.gx_last_timing.argtypes = [vp, dp]
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.gx_measure_fp64_peak.argtypes = [vp, dp, dp]
+    L.gx_apply_bforce.argtypes = [vp, dp, C.c_int]
     L.gx_functional_avg_disp.argtypes = [vp, dp, vp]
     L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
     L.gx_apply_tbcs.argtypes = [vp, C.c_int32, ip, dp]
@@ -382,6 +383,12 @@ class Assembler:
         sides = np.ascontiguousarray(sides, dtype=np.int32).reshape(-1, 3)
         T = np.ascontiguousarray(np.broadcast_to(np.asarray(traction, dtype=np.float64), (len(sides), 3)))
         self._ck(self.L.gx_apply_tbcs(self.h, len(sides), _ip(sides), _dp(T)))
+
+    def apply_bforce(self, b, error_weights=False):
+        """BForce on the device-resident ghost R (src/goal_bforce.cpp:58-68); b: [n_elems, 3] at the element centroids."""
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+        assert b.size == 3 * self.ne
+        self._ck(self.L.gx_apply_bforce(self.h, _dp(b), int(bool(error_weights))))
 
     def apply_ibcs(self, sides, scale, center):
         """set_ibcs (src/goal_ibcs.cpp:41-83): inward traction T = scale (x_c - center)."""

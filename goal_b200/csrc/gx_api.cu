@@ -288,6 +288,33 @@ __global__ void side_bcs_kernel(double* R, NodeRec const* nodes, int32_t const* 
   R[4 * (int64_t)a] = r[0]; R[4 * (int64_t)a + 1] = r[1]; R[4 * (int64_t)a + 2] = r[2];
 }
 
+// BForce<T>::at_point (src/goal_bforce.cpp:58-68): R_u[n][i] -= b_i w_n^i w dv, b given per element.  One thread per
+// node walks its incident elements in ascending element order -- no atomics, bit-reproducible.  z != nullptr: the
+// error chain's test functions w_n^i = z_i(xi_c) N_n with z = u_z_diff (goal_displacement_adjoint.cpp:48-49).
+__global__ void bforce_kernel(double* R, NodeRec const* nodes, ZRec const* z, int4 const* conn, uint32_t const* adj_off, int2 const* adj,
+                              double const* b, int nn) {
+  int const a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= nn) return;
+  double r[3] = {0.0, 0.0, 0.0};
+  for (uint32_t k = adj_off[a]; k < adj_off[a + 1]; ++k) {
+    int const e = adj[k].x >> 2;
+    int4 const cn = conn[e];
+    int const nd[4] = {cn.x, cn.y, cn.z, cn.w};
+    double x[4][3];
+    for (int n = 0; n < 4; ++n) { x[n][0] = nodes[nd[n]].x[0]; x[n][1] = nodes[nd[n]].x[1]; x[n][2] = nodes[nd[n]].x[2]; }
+    double e1[3], e2[3], e3[3], c23[3];
+    for (int j = 0; j < 3; ++j) { e1[j] = x[1][j] - x[0][j]; e2[j] = x[2][j] - x[0][j]; e3[j] = x[3][j] - x[0][j]; }
+    cross3(e2, e3, c23);
+    double const wdv = dot3(e1, c23) * (1.0 / 6.0);
+    for (int i = 0; i < 3; ++i) {
+      double zi = 1.0;
+      if (z) zi = 0.25 * z[nd[0]].zu[i] + 0.25 * z[nd[1]].zu[i] + 0.25 * z[nd[2]].zu[i] + 0.25 * z[nd[3]].zu[i];
+      r[i] += b[3 * (int64_t)e + i] * (zi * 0.25) * wdv;
+    }
+  }
+  R[4 * (int64_t)a] -= r[0]; R[4 * (int64_t)a + 1] -= r[1]; R[4 * (int64_t)a + 2] -= r[2];
+}
+
 // ---------------------------------------------------------------------------
 template <int MODEL, int PASS, bool SAVE>
 static cudaError_t launch_colours(gx_ctx* ctx, KParams& P) {
@@ -1048,6 +1075,25 @@ int gx_apply_tbcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, const
 int gx_apply_ibcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, double scale, const double* center) {
   if (ctx && !center) { ctx->err = "gx_apply_ibcs: null center"; return GX_ERR_ARG; }
   return side_bcs(ctx, "gx_apply_ibcs", n_sides, side_nodes, nullptr, scale, center);
+}
+
+int gx_apply_bforce(gx_ctx* ctx, const double* b, int error_weights) {
+  if (!ctx || !b) { if (ctx) ctx->err = "gx_apply_bforce: null argument"; return GX_ERR_ARG; }
+  if (host_only(ctx)) return GX_ERR_CUDA;
+  if (!ctx->have_result) { ctx->err = "gx_apply_bforce: no residual on the device"; return GX_ERR_ARG; }
+  GX_CUDA(cudaSetDevice(ctx->device));
+  double* d_b = nullptr;
+  GX_CUDA(cudaMallocAsync(&d_b, sizeof(double) * 3 * (size_t)ctx->ne, ctx->stream));
+  cudaError_t e = cudaMemcpyAsync(d_b, b, sizeof(double) * 3 * (size_t)ctx->ne, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) {
+    bforce_kernel<<<(ctx->nn + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_R, ctx->d_nodes, error_weights ? ctx->d_z : nullptr, ctx->d_conn,
+                                                                 ctx->d_adj_off, ctx->d_adj, d_b, ctx->nn);
+    e = cudaGetLastError();
+  }
+  cudaFreeAsync(d_b, ctx->stream);
+  cudaError_t const e2 = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess || e2 != cudaSuccess) { ctx->err = std::string("gx_apply_bforce: ") + cudaGetErrorString(e != cudaSuccess ? e : e2); return GX_ERR_CUDA; }
+  return GX_OK;
 }
 
 int gx_result_dev(gx_ctx* ctx, double** R_dev, double** values_dev) {

@@ -200,6 +200,12 @@ int gx_apply_dbcs(gx_ctx* ctx, int32_t n, const int32_t* rows, const double* g, 
  * (the reference's loop order), without atomics. */
 int gx_apply_tbcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, const double* traction);
 int gx_apply_ibcs(gx_ctx* ctx, int32_t n_sides, const int32_t* side_nodes, double scale, const double center[3]);
+/* BForce<T>::at_point (src/goal_bforce.cpp:58-68; wired behind MResidual, goal_mechanics.cpp:132-136 / 204-208):
+ * R_u[n][i] -= b_i w_n^i w dv on the device-resident ghost R of the last pass.  b: [n_elems * 3], the body force at
+ * each element's integration point (the reference evaluates a named expression there; the value is the caller's).
+ * error_weights = 0: w = N_n (residual / Jacobian pass; b does not depend on u, the Jacobian is unchanged);
+ * error_weights = 1: w_n^i = z_i N_n with the u_z_diff of the last gx_localize_error (error chain). */
+int gx_apply_bforce(gx_ctx* ctx, const double* b, int error_weights);
 
 /* ---- mesh parts ------------------------------------------------------------------------------
  * Structure exchange == the owned_graph Export/INSERT of Disc::compute_graphs (src/goal_disc.cpp:327-329):

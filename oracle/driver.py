@@ -45,8 +45,21 @@ def _inward_rhs(coords, sides, scale, center):
     return out
 
 
-def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_iters=5, log=None, device_bcs=False):
-    """dbcs: [(eq, node_ids, g(t))]; tbcs: [(side_tris, T(t) -> 3-vector)].
+def _bforce_rhs(coords, conn, b):
+    """BForce (src/goal_bforce.cpp:58-68) as a ghost-R increment: R[(n,i)] -= b_e[i] N_n w dv, N_n = 1/4, w dv = vol_e."""
+    x = coords[conn]
+    vol = np.linalg.det(x[:, 1:] - x[:, :1]) / 6.0
+    inc = np.zeros(4 * len(coords))
+    for n in range(4):
+        for i in range(3):
+            np.add.at(inc, 4 * conn[:, n] + i, -b[:, i] * 0.25 * vol)
+    return inc
+
+
+def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_iters=5, log=None, device_bcs=False,
+               bforce=None, conn=None):
+    """dbcs: [(eq, node_ids, g(t))]; tbcs: [(side_tris, T(t) -> 3-vector)]; bforce: b(centroids [Ne,3], t) -> [Ne,3]
+    (needs conn), the body force of `mechanics: body force` (src/goal_mechanics.cpp:57-59, goal_bforce.cpp).
     device_bcs: apply the traction terms and the Dirichlet rows with asm.apply_tbcs / asm.apply_dbcs (the CUDA path's
     gx_apply_tbcs / gx_apply_dbcs) on the device-resident result instead of on the host.
 
@@ -63,6 +76,11 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
         for sides, T in tbcs:
             for row, v in _traction_rhs(coords, sides, T(t)):
                 R[row] += v
+        if bforce is not None:
+            R += _bforce_rhs(coords, conn, bvals(t))
+
+    cen = None if bforce is None else coords[np.asarray(conn)].mean(axis=1)
+    bvals = lambda t: np.ascontiguousarray(bforce(cen, t))
 
     def dbc_rows(t):
         for eq, nodes, g in dbcs:
@@ -77,6 +95,8 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
                 asm.jacobian(save=True, out=False)
                 for sides, T in tbcs:
                     asm.apply_tbcs(sides, T(t_now))
+                if bforce is not None:
+                    asm.apply_bforce(bvals(t_now))
                 rows_g = [(4 * n + eq, g(t_now)) for eq, nodes, g in dbcs for n in nodes]
                 asm.apply_dbcs([r for r, _ in rows_g], [v for _, v in rows_g], True)
                 R, vals = asm.fetch()
@@ -99,6 +119,8 @@ def run_primal(asm, coords, dbcs, tbcs=(), num_steps=3, dt=1.0, tol=1e-8, max_it
                 asm.residual(save=True, out=False)
                 for sides, T in tbcs:
                     asm.apply_tbcs(sides, T(t_now))
+                if bforce is not None:
+                    asm.apply_bforce(bvals(t_now))
                 rows_g = [(4 * n + eq, g(t_now)) for eq, nodes, g in dbcs for n in nodes]
                 asm.apply_dbcs([r for r, _ in rows_g], [v for _, v in rows_g], False)
                 R = asm.fetch(values=False)[0]

@@ -773,6 +773,32 @@ int go_assemble_error(go_ctx* c, const double* zu_diff, const double* zp_diff, c
   return 0;
 }
 
+// BForce<T>::at_point (goal_bforce.cpp:58-68), wired behind MResidual in build_resid / build_error
+// (goal_mechanics.cpp:132-136, 204-208):  u->resid(n, i) -= b[i] * w->val(n, i) * ipw * dv.
+// The reference evaluates b from a named expression at the integration point ("elastic squared", a constant,
+// :51-56); here the caller hands the value per element (b is data of the problem, not of the path).
+// w = VectorWeight: val(n,i) = N_n (goal_vector_weight.cpp:13-28); in the error chain DisplacementAdjoint:
+// val(n,i) = z_i(xi) N_n (goal_displacement_adjoint.cpp:48-49) with z = u_z_diff.
+int go_apply_bforce(go_ctx* c, const double* b, const double* zu_diff, double* R) {
+  c->err.clear();
+  for (int e = 0; e < c->ne; ++e) {
+    TetGeom g;
+    if (!elem_geometry(*c, e, g)) return 1;
+    double z[3] = {1.0, 1.0, 1.0};
+    if (zu_diff) {
+      for (int i = 0; i < 3; ++i) {
+        z[i] = 0.0;
+        for (int n = 0; n < 4; ++n) z[i] += zu_diff[3 * (size_t)c->conn[4 * (size_t)e + n] + i] * g.BF[n];
+      }
+    }
+    for (int n = 0; n < 4; ++n) {
+      int const nd = c->conn[4 * (size_t)e + n];
+      for (int i = 0; i < 3; ++i) R[4 * (size_t)nd + i] -= b[3 * (size_t)e + i] * (z[i] * g.BF[n]) * g.w * g.dv;
+    }
+  }
+  return 0;
+}
+
 double go_element_error(go_ctx* c, const double* u_err, const double* p_err, double* eta_elem,
                         const int32_t* parent, int n_parent, double* eta_parent) {
   // compute_error (goal_error.cpp:7-35): |sum_d u_err_d(xi_c) + p_err(xi_c)|, N_n(xi_c) = 1/4

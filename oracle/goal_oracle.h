@@ -74,6 +74,9 @@ double go_functional(go_ctx*, int type, int elem_set, double rho, int point_node
  * functions (goal_displacement_adjoint.cpp:37-53, goal_pressure_adjoint.cpp:38-49) */
 int go_assemble_error(go_ctx*, const double* zu_diff /*[Nn*3]*/, const double* zp_diff /*[Nn]*/,
                       const double* zp_coarse /*[Nn]*/, double* R);
+/* BForce (src/goal_bforce.cpp:58-68): R_u[n][i] -= b_i w_n^i w dv with b[Ne*3] given per element; zu_diff != NULL
+ * selects the adjoint-weighted test functions of the error chain (src/goal_mechanics.cpp:204-208). */
+int go_apply_bforce(go_ctx*, const double* b /*[Ne*3]*/, const double* zu_diff /*[Nn*3] or NULL*/, double* R);
 /* src/goal_error.cpp:7-56 and goal_nested.cpp:395-412.  u_err[Nn*3], p_err[Nn];
  * eta_elem[Ne]; parent[Ne] -> eta_parent[n_parent] (zeroed here); returns bound. */
 double go_element_error(go_ctx*, const double* u_err, const double* p_err, double* eta_elem,

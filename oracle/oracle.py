@@ -58,6 +58,7 @@ def lib():
         L.go_last_plastic_count.argtypes = [C.c_void_p]
         L.go_last_error.restype = C.c_char_p
         L.go_last_error.argtypes = [C.c_void_p]
+        L.go_apply_bforce.argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.go_time_jacobian_elements.restype = C.c_double
         L.go_time_jacobian_elements.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int]
         _LIB = L
@@ -145,6 +146,13 @@ class Oracle:
         R = np.zeros(4 * self.nn) if R is None else R
         a = [np.ascontiguousarray(x, dtype=np.float64).reshape(-1) for x in (zu_diff, zp_diff, zp_coarse)]
         self._check(self.L.go_assemble_error(self.h, _dp(a[0]), _dp(a[1]), _dp(a[2]), _dp(R)))
+        return R
+
+    def apply_bforce(self, b, R, zu_diff=None):
+        """BForce (goal_bforce.cpp:58-68) added to the ghost R: b [Ne,3] per element; zu_diff selects the error chain's weights."""
+        b = np.ascontiguousarray(b, dtype=np.float64).reshape(-1)
+        z = None if zu_diff is None else np.ascontiguousarray(zu_diff, dtype=np.float64).reshape(-1)
+        self._check(self.L.go_apply_bforce(self.h, _dp(b), None if z is None else _dp(z), _dp(R)))
         return R
 
     def element_error(self, u_err, p_err, parent=None, n_parent=0):
