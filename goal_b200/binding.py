@@ -28,7 +28,7 @@ SYMBOLS = [
     "gx_compute_jacobian", "gx_localize_error", "gx_element_error", "gx_comm_init", "gx_nccl_unique_id",
     "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
-    "gx_stream", "gx_last_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_apply_bforce", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
+    "gx_stream", "gx_last_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_apply_bforce", "gx_owned_tpetra_graph", "gx_fetch_owned_tpetra", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
     "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs", "gx_add_solution", "gx_get_solution", "gx_sync_solution",
@@ -109,6 +109,8 @@ def load_library():
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.gx_measure_fp64_peak.argtypes = [vp, dp, dp]
     L.gx_apply_bforce.argtypes = [vp, dp, C.c_int]
+    L.gx_owned_tpetra_graph.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(lp), lp, C.POINTER(lp), C.POINTER(ip)]
+    L.gx_fetch_owned_tpetra.argtypes = [vp, C.c_void_p, C.c_void_p]
     L.gx_functional_avg_disp.argtypes = [vp, dp, vp]
     L.gx_apply_dbcs.argtypes = [vp, C.c_int32, ip, dp, C.c_int]
     L.gx_apply_tbcs.argtypes = [vp, C.c_int32, ip, dp]
@@ -500,6 +502,21 @@ class Assembler:
         return dict(nodes=np.ctypeslib.as_array(on, (no.value,)).copy(),
                     rowptr=np.ctypeslib.as_array(rp, (4 * no.value + 1,)).copy(),
                     col_gid=np.ctypeslib.as_array(cg, (nnz.value,)).copy())
+
+    def owned_tpetra_graph(self):
+        """The owned matrix in Tpetra's local layout: dict(n_owned, colmap [node gids in column-map order], rowptr, colind)."""
+        no, nc, nnz = C.c_int32(), C.c_int32(), C.c_int64()
+        cm, rp, ci = C.POINTER(C.c_int64)(), C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)()
+        self._ck(self.L.gx_owned_tpetra_graph(self.h, C.byref(no), C.byref(nc), C.byref(cm), C.byref(nnz), C.byref(rp), C.byref(ci)))
+        return dict(n_owned=no.value, colmap=np.ctypeslib.as_array(cm, (nc.value,)).copy(),
+                    rowptr=np.ctypeslib.as_array(rp, (4 * no.value + 1,)).copy(), colind=np.ctypeslib.as_array(ci, (nnz.value,)).copy())
+
+    def fetch_owned_tpetra(self, values=True):
+        g = self.owned_tpetra_graph()
+        R = np.zeros(4 * g["n_owned"])
+        V = np.zeros(len(g["colind"])) if values else None
+        self._ck(self.L.gx_fetch_owned_tpetra(self.h, _addr(R), _addr(V)))
+        return R, V, g
 
     def fetch_owned(self, values=True):
         g = self.owned_graph()

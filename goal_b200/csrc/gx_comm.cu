@@ -291,7 +291,10 @@ int gx_struct_pack(gx_ctx* ctx, int peer_index, const void** blob, int64_t* byte
   for (int a : P.send_nodes) {
     int64_t const nb = ctx->nrow[a + 1] - ctx->nrow[a];
     P.struct_out.push_back(nb);
-    for (int64_t k = ctx->nrow[a]; k < ctx->nrow[a + 1]; ++k) P.struct_out.push_back(ctx->node_gid[ctx->ncol[k]]);
+    for (int64_t k = ctx->nrow[a]; k < ctx->nrow[a + 1]; ++k) {  // (global column node, its owning rank)
+      P.struct_out.push_back(ctx->node_gid[ctx->ncol[k]]);
+      P.struct_out.push_back((int64_t)ctx->node_owner[ctx->ncol[k]]);
+    }
   }
   *blob = P.struct_out.data();
   *bytes = (int64_t)(P.struct_out.size() * sizeof(int64_t));
@@ -309,8 +312,8 @@ int gx_struct_unpack(gx_ctx* ctx, int peer_index, const void* blob, int64_t byte
   // validate framing against the receive list
   int64_t pos = 0;
   for (size_t s = 0; s < P.recv_nodes.size(); ++s) {
-    if (pos >= n || w[pos] < 0 || pos + 1 + w[pos] > n) { ctx->err = "structure blob does not match the shared-node list"; return GX_ERR_ARG; }
-    pos += 1 + w[pos];
+    if (pos >= n || w[pos] < 0 || pos + 1 + 2 * w[pos] > n) { ctx->err = "structure blob does not match the shared-node list"; return GX_ERR_ARG; }
+    pos += 1 + 2 * w[pos];
   }
   if (pos != n) { ctx->err = "structure blob has trailing data"; return GX_ERR_ARG; }
   P.struct_have = true;
@@ -328,6 +331,7 @@ int gx_struct_finalize(gx_ctx* ctx) {
   for (int a = 0; a < nn; ++a) g2l[ctx->node_gid[a]] = a;
   // phantom columns per owned node: global ids the senders have and this part's row lacks
   std::vector<std::vector<int64_t>> phantom(nn);
+  std::unordered_map<int64_t, int32_t> phantom_owner;  // owning rank of every column that lives only on other parts
   auto local_pos = [&](int a, int64_t gid) -> int {
     auto it = g2l.find(gid);
     if (it == g2l.end()) return -1;
@@ -342,7 +346,9 @@ int gx_struct_finalize(gx_ctx* ctx) {
       int64_t const nb = P.struct_in[pos++];
       for (int64_t k = 0; k < nb; ++k) {
         int64_t const gid = P.struct_in[pos++];
-        if (local_pos(a, gid) < 0) phantom[a].push_back(gid);
+        int64_t const own = P.struct_in[pos++];
+        if (own < 0 || own >= ctx->nranks) { ctx->err = "structure blob: column owner out of range"; return GX_ERR_ARG; }
+        if (local_pos(a, gid) < 0) { phantom[a].push_back(gid); phantom_owner[gid] = (int32_t)own; }
       }
     }
   }
@@ -361,10 +367,11 @@ int gx_struct_finalize(gx_ctx* ctx) {
   if (ctx->nrow_x[nn] > 0x7fffffffLL) { ctx->err = "more than 2^31 node blocks"; return GX_ERR_UNSUPPORTED; }
   ctx->nnz_x = 16 * ctx->nrow_x[nn];
   ctx->xcol_gid.resize(ctx->nrow_x[nn]);
+  ctx->xcol_owner.resize(ctx->nrow_x[nn]);
   for (int a = 0; a < nn; ++a) {
     int64_t o = ctx->nrow_x[a];
-    for (int64_t k = ctx->nrow[a]; k < ctx->nrow[a + 1]; ++k) ctx->xcol_gid[o++] = ctx->node_gid[ctx->ncol[k]];
-    for (int64_t g : phantom[a]) ctx->xcol_gid[o++] = g;
+    for (int64_t k = ctx->nrow[a]; k < ctx->nrow[a + 1]; ++k) { ctx->xcol_gid[o] = ctx->node_gid[ctx->ncol[k]]; ctx->xcol_owner[o++] = ctx->node_owner[ctx->ncol[k]]; }
+    for (int64_t g : phantom[a]) { ctx->xcol_gid[o] = g; ctx->xcol_owner[o++] = phantom_owner[g]; }
   }
   // exchange plan
   for (auto& P : ctx->peers) {
@@ -381,6 +388,7 @@ int gx_struct_finalize(gx_ctx* ctx) {
       int64_t const nloc = ctx->nrow[a + 1] - ctx->nrow[a];
       for (int64_t k = 0; k < nb; ++k) {
         int64_t const gid = P.struct_in[pos++];
+        ++pos;  // the column's owner (used above)
         int lp = local_pos(a, gid);
         if (lp < 0) lp = (int)(nloc + (std::lower_bound(phantom[a].begin(), phantom[a].end(), gid) - phantom[a].begin()));
         P.recv_map.push_back(lp);
@@ -397,6 +405,7 @@ int gx_struct_finalize(gx_ctx* ctx) {
     if (ctx->node_owner[a] == ctx->rank) ctx->owned_nodes.push_back(a);
   ctx->owned_rowptr.clear();
   ctx->owned_colgid.clear();
+  ctx->tp_rowptr.clear();
   ctx->struct_done = true;
   return upload_plan(ctx);
 }
@@ -434,6 +443,149 @@ int gx_owned_graph(gx_ctx* ctx, int32_t* n_owned_nodes, const int32_t** owned_no
   if (nnz_owned) *nnz_owned = ctx->owned_rowptr.back();
   if (rowptr) *rowptr = ctx->owned_rowptr.data();
   if (col_gid) *col_gid = ctx->owned_colgid.data();
+  return GX_OK;
+}
+
+// ---------------------------------------------------------------------------
+// The owned matrix in Tpetra's LOCAL layout, i.e. what sol_info->owned->dRdu holds after
+// owned_graph->fillComplete() (src/goal_disc.cpp:327-332) and gather_dRdu (src/goal_sol_info.cpp:41-43), so that
+// the values can be written straight into the matrix goal::solve consumes (src/goal_linear_solve.cpp:72-90).
+// Restated rule (Tpetra::CrsGraph::fillComplete -> Tpetra::Details::makeColMap; Trilinos is not in /root/reference,
+// version unpinned -- SURVEY.md 8c):
+//   rows     owned dofs in owned_map order = owned nodes in apf's owned numbering (mesh order, i.e. ascending
+//            overlap-local id restricted to owned nodes), dof = node * 4 + eq          (goal_disc.cpp:270-290)
+//   columns  column map = (1) the dofs of the domain map (= owned_map) in owned_map order, then (2) the remote dofs
+//            grouped by owning rank in ascending rank order and, inside a rank, in ascending global id;
+//            local column index = position in that list
+//   a row    its local column indices in ascending order
+// ---------------------------------------------------------------------------
+static void build_tpetra_view(gx_ctx* ctx) {
+  if (!ctx->tp_rowptr.empty()) return;
+  int const nn = ctx->nn;
+  if (ctx->owned_nodes.empty() && ctx->nranks <= 1) {
+    ctx->owned_nodes.resize(nn);
+    for (int a = 0; a < nn; ++a) ctx->owned_nodes[a] = a;
+  }
+  size_t const no = ctx->owned_nodes.size();
+  bool const parts = ctx->nranks > 1;
+  auto gid_of = [&](int64_t k) { return parts ? ctx->xcol_gid[k] : (int64_t)ctx->ncol[k]; };
+  auto own_of = [&](int64_t k) { return parts ? ctx->xcol_owner[k] : 0; };
+  std::unordered_map<int64_t, int32_t> lid;  // global node -> column-map node index
+  lid.reserve(2 * no);
+  ctx->tp_colmap.clear();
+  for (size_t s = 0; s < no; ++s) {
+    int64_t const g = parts ? ctx->node_gid[ctx->owned_nodes[s]] : (int64_t)ctx->owned_nodes[s];
+    lid[g] = (int32_t)s;
+    ctx->tp_colmap.push_back(g);
+  }
+  std::vector<std::pair<int32_t, int64_t>> remote;  // (owner, gid)
+  for (size_t s = 0; s < no; ++s) {
+    int const a = ctx->owned_nodes[s];
+    for (int64_t k = ctx->nrow_x[a]; k < ctx->nrow_x[a + 1]; ++k)
+      if (own_of(k) != ctx->rank) remote.emplace_back(own_of(k), gid_of(k));
+  }
+  std::sort(remote.begin(), remote.end());
+  remote.erase(std::unique(remote.begin(), remote.end()), remote.end());
+  for (auto const& r : remote) { lid[r.second] = (int32_t)ctx->tp_colmap.size(); ctx->tp_colmap.push_back(r.second); }
+  ctx->tp_rowptr.assign(4 * no + 1, 0);
+  for (size_t s = 0; s < no; ++s) {
+    int const a = ctx->owned_nodes[s];
+    int64_t const len = 4 * (ctx->nrow_x[a + 1] - ctx->nrow_x[a]);
+    for (int i = 0; i < 4; ++i) ctx->tp_rowptr[4 * s + i + 1] = ctx->tp_rowptr[4 * s + i] + len;
+  }
+  ctx->tp_colind.resize(ctx->tp_rowptr.back());
+  ctx->tp_perm.resize(ctx->nrow_x[nn], 0);  // per stored block of an owned row: its position in the Tpetra-ordered row
+  std::vector<std::pair<int32_t, int32_t>> ord;
+  for (size_t s = 0; s < no; ++s) {
+    int const a = ctx->owned_nodes[s];
+    int64_t const b0 = ctx->nrow_x[a], nb = ctx->nrow_x[a + 1] - b0;
+    ord.clear();
+    for (int64_t k = 0; k < nb; ++k) ord.emplace_back(lid[gid_of(b0 + k)], (int32_t)k);
+    std::sort(ord.begin(), ord.end());
+    for (int64_t j = 0; j < nb; ++j) {
+      ctx->tp_perm[b0 + ord[j].second] = (uint8_t)j;
+      for (int i = 0; i < 4; ++i)
+        for (int c = 0; c < 4; ++c) ctx->tp_colind[ctx->tp_rowptr[4 * s + i] + 4 * j + c] = 4 * ord[j].first + c;
+    }
+  }
+}
+
+// values of the owned rows, blocks permuted into the Tpetra order of each row: one thread block per owned node
+__global__ void tpetra_rows_kernel(double* out, double const* values, int32_t const* owned, int64_t const* out_off, int32_t const* blk0,
+                                   int32_t const* nblk, uint8_t const* perm, int n_owned) {
+  int const s = blockIdx.x;
+  if (s >= n_owned) return;
+  int const a = owned[s];
+  int const nb = nblk[a];
+  double const* src = values + 16 * (int64_t)blk0[a];
+  double* dst = out + out_off[s];
+  for (int t = threadIdx.x; t < 16 * nb; t += blockDim.x) {
+    int const i = t / (4 * nb), r = t - i * 4 * nb, k = r >> 2, c = r & 3;
+    dst[i * 4 * nb + 4 * perm[blk0[a] + k] + c] = src[t];
+  }
+}
+
+extern "C" int gx_owned_tpetra_graph(gx_ctx* ctx, int32_t* n_owned_nodes, int32_t* n_col_nodes, const int64_t** colmap_node_gid,
+                                     int64_t* nnz_owned, const int64_t** rowptr, const int32_t** colind) {
+  if (!ctx) return GX_ERR_ARG;
+  if (!ctx->struct_done) { ctx->err = "gx_owned_tpetra_graph: structure exchange not finished"; return GX_ERR_ARG; }
+  build_tpetra_view(ctx);
+  if (n_owned_nodes) *n_owned_nodes = (int32_t)ctx->owned_nodes.size();
+  if (n_col_nodes) *n_col_nodes = (int32_t)ctx->tp_colmap.size();
+  if (colmap_node_gid) *colmap_node_gid = ctx->tp_colmap.data();
+  if (nnz_owned) *nnz_owned = ctx->tp_rowptr.back();
+  if (rowptr) *rowptr = ctx->tp_rowptr.data();
+  if (colind) *colind = ctx->tp_colind.data();
+  return GX_OK;
+}
+
+extern "C" int gx_fetch_owned_tpetra(gx_ctx* ctx, double* R_owned, double* values_owned) {
+  if (!ctx) return GX_ERR_ARG;
+  if (ctx->device < 0) { ctx->err = "gx_fetch_owned_tpetra: host-only context (device = -1) cannot compute"; return GX_ERR_CUDA; }
+  if (!ctx->have_result || (values_owned && !ctx->have_values)) { ctx->err = "gx_fetch_owned_tpetra: no matching result on the device"; return GX_ERR_ARG; }
+  if (!ctx->struct_done) { ctx->err = "gx_fetch_owned_tpetra: structure exchange not finished"; return GX_ERR_ARG; }
+  build_tpetra_view(ctx);
+  GX_CUDA(cudaSetDevice(ctx->device));
+  int const no = (int)ctx->owned_nodes.size();
+  if (R_owned)
+    for (int s = 0; s < no;) {  // owned nodes come in runs of consecutive local ids
+      int e = s;
+      while (e + 1 < no && ctx->owned_nodes[e + 1] == ctx->owned_nodes[e] + 1) ++e;
+      GX_CUDA(cudaMemcpyAsync(R_owned + 4 * (size_t)s, ctx->d_R + 4 * (size_t)ctx->owned_nodes[s], sizeof(double) * 4 * (size_t)(e + 1 - s),
+                              cudaMemcpyDeviceToHost, ctx->stream));
+      s = e + 1;
+    }
+  if (values_owned && no > 0) {
+    int const nn = ctx->nn;
+    std::vector<int32_t> b0(nn), nbx(nn);
+    for (int a = 0; a < nn; ++a) { b0[a] = (int32_t)ctx->nrow_x[a]; nbx[a] = (int32_t)(ctx->nrow_x[a + 1] - ctx->nrow_x[a]); }
+    std::vector<int64_t> off(no);
+    for (int s = 0; s < no; ++s) off[s] = ctx->tp_rowptr[4 * (size_t)s];
+    double* d_out = nullptr; int32_t *d_owned = nullptr, *d_b0 = nullptr, *d_nb = nullptr; int64_t* d_off = nullptr; uint8_t* d_perm = nullptr;
+    auto body = [&]() -> int {
+      GX_CUDA(cudaMalloc(&d_out, sizeof(double) * (size_t)ctx->tp_rowptr.back()));
+      GX_CUDA(cudaMalloc(&d_owned, sizeof(int32_t) * (size_t)no));
+      GX_CUDA(cudaMalloc(&d_b0, sizeof(int32_t) * (size_t)nn));
+      GX_CUDA(cudaMalloc(&d_nb, sizeof(int32_t) * (size_t)nn));
+      GX_CUDA(cudaMalloc(&d_off, sizeof(int64_t) * (size_t)no));
+      GX_CUDA(cudaMalloc(&d_perm, ctx->tp_perm.size()));
+      GX_CUDA(cudaMemcpyAsync(d_owned, ctx->owned_nodes.data(), sizeof(int32_t) * (size_t)no, cudaMemcpyHostToDevice, ctx->stream));
+      GX_CUDA(cudaMemcpyAsync(d_b0, b0.data(), sizeof(int32_t) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+      GX_CUDA(cudaMemcpyAsync(d_nb, nbx.data(), sizeof(int32_t) * (size_t)nn, cudaMemcpyHostToDevice, ctx->stream));
+      GX_CUDA(cudaMemcpyAsync(d_off, off.data(), sizeof(int64_t) * (size_t)no, cudaMemcpyHostToDevice, ctx->stream));
+      GX_CUDA(cudaMemcpyAsync(d_perm, ctx->tp_perm.data(), ctx->tp_perm.size(), cudaMemcpyHostToDevice, ctx->stream));
+      tpetra_rows_kernel<<<no, 128, 0, ctx->stream>>>(d_out, ctx->d_values, d_owned, d_off, d_b0, d_nb, d_perm, no);
+      GX_CUDA(cudaGetLastError());
+      GX_CUDA(cudaMemcpyAsync(values_owned, d_out, sizeof(double) * (size_t)ctx->tp_rowptr.back(), cudaMemcpyDeviceToHost, ctx->stream));
+      GX_CUDA(cudaStreamSynchronize(ctx->stream));
+      return GX_OK;
+    };
+    int const rc = body();
+    cudaStreamSynchronize(ctx->stream);
+    for (void* q : {(void*)d_out, (void*)d_owned, (void*)d_b0, (void*)d_nb, (void*)d_off, (void*)d_perm}) if (q) cudaFree(q);
+    if (rc) return rc;
+  }
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
 

@@ -141,6 +141,12 @@ struct gx_ctx {
   // extended block rows: ghost row + phantom columns appended (owned interface nodes only)
   std::vector<int64_t> nrow_x;    // [nn+1]
   std::vector<int64_t> xcol_gid;  // [nrow_x[nn]] global node id of every block
+  std::vector<int32_t> xcol_owner;  // [nrow_x[nn]] owning rank of that node
+  // owned matrix in Tpetra's local layout (gx_owned_tpetra_graph): column-map node gids, dof-level rows, and per stored
+  // block of an owned row its position in the Tpetra-ordered row
+  std::vector<int64_t> tp_colmap, tp_rowptr;
+  std::vector<int32_t> tp_colind;
+  std::vector<uint8_t> tp_perm;
   int64_t nnz_x = 0;
   std::vector<int32_t> owned_nodes;
   std::vector<int64_t> owned_rowptr, owned_colgid;

@@ -223,6 +223,18 @@ int gx_struct_finalize(gx_ctx* ctx);
 int gx_owned_graph(gx_ctx* ctx, int32_t* n_owned_nodes, const int32_t** owned_nodes, int64_t* nnz_owned,
                    const int64_t** rowptr /*[4*n_owned+1]*/, const int64_t** col_gid /*[nnz_owned]*/);
 int gx_fetch_owned(gx_ctx* ctx, double* R_owned /*[4*n_owned]*/, double* values_owned /*[nnz_owned]*/);
+/* The owned matrix in Tpetra's LOCAL layout -- what sol_info->owned->dRdu holds after owned_graph->fillComplete()
+ * (src/goal_disc.cpp:327-332), so gx_fetch_owned_tpetra can fill the matrix goal::solve consumes
+ * (src/goal_sol_info.cpp:41-43, src/goal_linear_solve.cpp:72-90) value for value.  Rule restated from Tpetra
+ * (fillComplete -> makeColMap; Trilinos version unpinned by the reference): rows = owned dofs in owned_map order (owned
+ * nodes in ascending overlap-local id, dof = node * 4 + eq); column map = the owned dofs in that same order, then the
+ * remote dofs grouped by owning rank (ascending) and by global id inside a rank; every row's local column indices
+ * ascending.  colmap_node_gid[n_col_nodes] lists the column map at node level (dof = 4 * position + eq);
+ * rowptr[4 * n_owned + 1], colind[nnz_owned] are the local CRS arrays.  A single-part context gives the ghost
+ * layout of gx_graph. */
+int gx_owned_tpetra_graph(gx_ctx* ctx, int32_t* n_owned_nodes, int32_t* n_col_nodes, const int64_t** colmap_node_gid,
+                          int64_t* nnz_owned, const int64_t** rowptr, const int32_t** colind);
+int gx_fetch_owned_tpetra(gx_ctx* ctx, double* R_owned /*[4*n_owned]*/, double* values_owned /*[nnz_owned]*/);
 /* The exchange plan of one peer (for hosts that verify or emulate the exchange). counts = {n_send, n_recv};
  * recv_cnt[s] = sender's block count of receive node s, recv_map = concatenated block maps. */
 int gx_exchange_plan(gx_ctx* ctx, int peer_index, int32_t* peer_rank, int32_t counts[2], const int32_t** send_nodes,

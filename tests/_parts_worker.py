@@ -114,6 +114,26 @@ def main():
             assert sorted(cols.tolist()) == sorted(ref)
             worst = max(worst, max(abs(got[k] - ref[int(c)]) for k, c in enumerate(cols)))
     assert worst < 1e-12 * scale, worst
+    # ---- the owned matrix in Tpetra's local layout (gx_owned_tpetra_graph): the restated makeColMap rule
+    tp = a.owned_tpetra_graph()
+    no = len(g["nodes"])
+    owned_gids = me["node_gid"][g["nodes"]]
+    assert tp["n_owned"] == no and np.array_equal(tp["colmap"][:no], owned_gids)  # (1) the owned dofs, in owned_map order
+    pairs = [None] * world
+    dist.all_gather_object(pairs, (me["node_gid"].tolist(), me["node_owner"].tolist()))
+    owner_of = {}
+    for gids, owners in pairs:
+        owner_of.update(zip(gids, owners))
+    rem = tp["colmap"][no:].tolist()
+    assert len(set(rem)) == len(rem) and not set(rem) & set(owned_gids.tolist())
+    assert all(owner_of[x] != rank for x in rem)
+    assert rem == sorted(rem, key=lambda x: (owner_of[x], x))                     # (2) remotes by owning rank, then by global id
+    assert np.array_equal(tp["rowptr"], g["rowptr"])
+    for s in range(4 * no):
+        ci = tp["colind"][tp["rowptr"][s]:tp["rowptr"][s + 1]]
+        assert np.all(np.diff(ci) > 0)                                           # (3) local column indices ascending in every row
+        gdof = 4 * tp["colmap"][ci // 4] + ci % 4
+        assert sorted(gdof.tolist()) == sorted(g["col_gid"][g["rowptr"][s]:g["rowptr"][s + 1]].tolist())
     owned_total = torch.tensor([len(g["nodes"])])
     dist.all_reduce(owned_total)
     assert int(owned_total) == len(co_s)

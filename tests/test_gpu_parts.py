@@ -44,6 +44,26 @@ def _check_owned(a, part, o, Rs, Vs):
             assert max(abs(V[lo + k] - ref[int(c)]) for k, c in enumerate(cols)) < 1e-12 * scale
 
 
+def _check_owned_tpetra(a, part, o, Rs, Vs):
+    """gx_fetch_owned_tpetra: the owned rows in Tpetra's local layout (column map = owned dofs in owned order, then the
+    remote dofs by owning rank and global id; rows ascending) hold the serial operator's values."""
+    R, V, tp = a.fetch_owned_tpetra()
+    own = np.nonzero(part["node_owner"] == part["rank"])[0]
+    gid = part["node_gid"][own]
+    assert tp["n_owned"] == len(own) and np.array_equal(tp["colmap"][:len(own)], gid)
+    scale = np.abs(Vs).max()
+    for s, G in enumerate(gid):
+        assert np.abs(R[4 * s:4 * s + 4] - Rs[4 * G:4 * G + 4]).max() < 1e-12 * np.abs(Rs).max()
+        for i in range(4):
+            lo, hi = tp["rowptr"][4 * s + i], tp["rowptr"][4 * s + i + 1]
+            ci = tp["colind"][lo:hi]
+            assert np.all(np.diff(ci) > 0)
+            gdof = 4 * tp["colmap"][ci // 4] + ci % 4
+            ref = dict(zip(o.colind[o.rowptr[4 * G + i]:o.rowptr[4 * G + i + 1]].tolist(), Vs[o.rowptr[4 * G + i]:o.rowptr[4 * G + i + 1]].tolist()))
+            assert sorted(gdof.tolist()) == sorted(ref)
+            assert max(abs(V[lo + k] - ref[int(c)]) for k, c in enumerate(gdof)) < 1e-12 * scale
+
+
 @pytest.mark.parametrize("case,model,kernel", [("fixture", "J2", 0), ("blocks", "neohookean", 0), ("fixture", "J2", 1), ("blocks", "J2", 1)])
 def test_interface_exchange_host_transport(cube, case, model, kernel):
     """4 parts = 4 contexts on one GPU; the packed interface rows are handed from context to context
@@ -94,6 +114,7 @@ def test_interface_exchange_host_transport(cube, case, model, kernel):
     exchange(2)
     for r, a in enumerate(A):
         _check_owned(a, parts[r], o, Rs, Vs)
+        _check_owned_tpetra(a, parts[r], o, Rs, Vs)
     # functional + gather_dMdu (src/goal_sol_info.cpp:37-39): part values add up, owned dMdu rows equal the serial ones
     Jo, do = o.functional("avg vm", with_dMdu=True)
     Js = [a.functional("avg vm", with_dMdu=True)[0] for a in A]
