@@ -363,9 +363,32 @@ static cudaError_t launch_patch_gather(gx_ctx* ctx, KParams& P, int pass, bool s
   size_t const smem = patch_smem_bytes();
   e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<ctx->n_patches, PATCH_THREADS, smem, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_patch_sched);
+  int const n1 = ctx->n_patches_iface;
+  bool const overlap = ctx->overlap_now != 0 && n1 > 0;
+  if (!overlap) {
+    kern<<<ctx->n_patches, PATCH_THREADS, smem, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_patch_sched);
+    ctx->launches++;
+    return cudaGetLastError();
+  }
+  // Interface rows first (the leading n1 patches write every block of them, gx_setup.cpp), then the exchange
+  // (pack -> grouped NCCL send/recv -> unpack-add, == SolInfo::gather_*) on a second stream while the interior
+  // patches are assembled on this one; the streams join before the pass returns.
+  kern<<<n1, PATCH_THREADS, smem, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_patch_sched);
   ctx->launches++;
-  return cudaGetLastError();
+  if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_iface, ctx->stream)) != cudaSuccess) return e;
+  if (ctx->n_patches > n1) {
+    kern<<<ctx->n_patches - n1, PATCH_THREADS, smem, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_patch_sched + (size_t)n1 * PATCH_WORDS);
+    ctx->launches++;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+  }
+  if ((e = cudaEventRecord(ctx->ev_b2, ctx->stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_iface, 0)) != cudaSuccess) return e;
+  if (comm_enqueue_reduce(ctx, (int)ctx->overlap_now, ctx->comm_stream) != GX_OK) return cudaErrorUnknown;
+  if ((e = cudaEventRecord(ctx->ev_comm, ctx->comm_stream)) != cudaSuccess) return e;
+  if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0)) != cudaSuccess) return e;
+  ctx->overlapped = true;
+  return cudaSuccess;
 }
 
 static int upload_patch_schedule(gx_ctx* ctx) {
@@ -422,6 +445,15 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
     patch_gather = ctx->patch_state == 1;
   }
   bool const gather = !with_values && ctx->opt_kernel != 1;
+  ctx->overlapped = false;
+  ctx->overlap_now = 0;
+  if (patch_gather && ctx->opt_overlap && ctx->nranks > 1 && ctx->comm && !ctx->peers.empty()) {
+    if (!ctx->comm_stream) {
+      GX_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+      GX_CUDA(cudaEventCreate(&ctx->ev_iface)); GX_CUDA(cudaEventCreate(&ctx->ev_b2)); GX_CUDA(cudaEventCreate(&ctx->ev_comm));
+    }
+    ctx->overlap_now = ctx->opt_overlap & 3;
+  }
   if ((gather || patch_gather) && !ctx->d_elemrec)
     GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
   if (patch_gather)  // nodes without elements have no work item
@@ -444,7 +476,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   else
     le = ctx->model == GX_MODEL_J2 ? launch_model<MODEL_J2>(ctx, P, pass, save)
                                    : launch_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
-  if (le != cudaSuccess) { ctx->err = std::string("kernel launch: ") + cudaGetErrorString(le); return GX_ERR_CUDA; }
+  if (le != cudaSuccess) { if (ctx->err.empty() || le != cudaErrorUnknown) ctx->err = std::string("kernel launch: ") + cudaGetErrorString(le); return le == cudaErrorUnknown ? GX_ERR_NCCL : GX_ERR_CUDA; }
   GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
   int herr[2];
   unsigned long long hpl = 0;
@@ -455,6 +487,15 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
   GX_CUDA(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
   ctx->timing[0] = t0; ctx->timing[1] = t1; ctx->timing[2] = 0.0; ctx->timing[3] = ctx->launches;
+  if (ctx->overlapped) {
+    // the assembly kernels end at ev_b2; what the exchange adds to the pass is only what sticks out behind them
+    float tk = 0, tx = 0;
+    GX_CUDA(cudaEventElapsedTime(&tk, ctx->ev[1], ctx->ev_b2));
+    GX_CUDA(cudaEventElapsedTime(&tx, ctx->ev_b2, ctx->ev[2]));
+    ctx->timing[1] = tk;
+    ctx->timing[2] = tx > 0 ? tx : 0.0;
+    ctx->timing[3] = ctx->launches + 4 * (double)ctx->peers.size();  // + pack / unpack kernels (R and rows) per peer
+  }
   ctx->last_plastic = (int64_t)hpl;
   ctx->have_result = herr[0] == 0;
   ctx->have_values = with_values && herr[0] == 0;
@@ -501,6 +542,8 @@ static void free_device(gx_ctx* ctx) {
                   ctx->d_plastic, ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {ctx->ev_iface, ctx->ev_b2, ctx->ev_comm}) if (e) cudaEventDestroy(e);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
 }
 
@@ -1211,6 +1254,11 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
     std::vector<uint32_t>().swap(ctx->patch_sched);
     ctx->patch_state = 0;
     if (!ok) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
+    return GX_OK;
+  }
+  if (k == "overlap") {  // 0 = off; 1 = R, 2 = dRdu, 3 = both: reduce the interfaces inside the Jacobian pass, overlapped
+    if (value < 0 || value > 3) { ctx->err = "overlap must be 0..3"; return GX_ERR_ARG; }
+    ctx->opt_overlap = value;
     return GX_OK;
   }
   if (k == "prefetch") {  // stage B: L2 prefetch distance in patches (0 = off)

@@ -630,25 +630,46 @@ int gx_interface_bytes(gx_ctx* ctx, int peer_index, int what, int64_t* send_byte
   return GX_OK;
 }
 
-static int pack_peer(gx_ctx* ctx, Peer& P, int what) {
+static int pack_peer(gx_ctx* ctx, Peer& P, int what, cudaStream_t st) {
   int const ns = (int)P.send_nodes.size();
   if (!ns) return GX_OK;
   // what = 4: dMdu of the last gx_functional travels like R (gather_dMdu, goal_sol_info.cpp:37-39)
-  if (what & 5) pack_R_kernel<<<(4 * ns + 255) / 256, 256, 0, ctx->stream>>>(P.d_sendR, (what & 4) ? ctx->d_dMdu : ctx->d_R, P.d_send_nodes, ns);
-  if (what & 2) pack_rows_kernel<<<ns, 128, 0, ctx->stream>>>(P.d_send, ctx->d_values, P.d_send_nodes, P.d_send_off, ctx->d_blk0_x, ctx->d_nblk_g, ns);
+  if (what & 5) pack_R_kernel<<<(4 * ns + 255) / 256, 256, 0, st>>>(P.d_sendR, (what & 4) ? ctx->d_dMdu : ctx->d_R, P.d_send_nodes, ns);
+  if (what & 2) pack_rows_kernel<<<ns, 128, 0, st>>>(P.d_send, ctx->d_values, P.d_send_nodes, P.d_send_off, ctx->d_blk0_x, ctx->d_nblk_g, ns);
   GX_CUDA(cudaGetLastError());
   return GX_OK;
 }
-static int unpack_peer(gx_ctx* ctx, Peer& P, int what, double const* bufR, double const* bufV) {
+static int unpack_peer(gx_ctx* ctx, Peer& P, int what, double const* bufR, double const* bufV, cudaStream_t st) {
   int const nr = (int)P.recv_nodes.size();
   if (!nr) return GX_OK;
-  if (what & 5) unpack_R_kernel<<<(4 * nr + 255) / 256, 256, 0, ctx->stream>>>((what & 4) ? ctx->d_dMdu : ctx->d_R, bufR, P.d_recv_nodes, nr);
+  if (what & 5) unpack_R_kernel<<<(4 * nr + 255) / 256, 256, 0, st>>>((what & 4) ? ctx->d_dMdu : ctx->d_R, bufR, P.d_recv_nodes, nr);
   if (what & 2)
-    unpack_rows_kernel<<<nr, 128, 0, ctx->stream>>>(ctx->d_values, bufV, P.d_recv_nodes, P.d_recv_off, P.d_recv_cnt, P.d_recv_map,
-                                                    P.d_recv_moff, ctx->d_blk0_x, ctx->d_nblk_x, nr);
+    unpack_rows_kernel<<<nr, 128, 0, st>>>(ctx->d_values, bufV, P.d_recv_nodes, P.d_recv_off, P.d_recv_cnt, P.d_recv_map,
+                                           P.d_recv_moff, ctx->d_blk0_x, ctx->d_nblk_x, nr);
   GX_CUDA(cudaGetLastError());
   return GX_OK;
 }
+// SolInfo::gather_* over NCCL, enqueued on `st`: pack, grouped send/recv of the packed interface rows, then the
+// owner adds peer by peer in ascending rank order.  No synchronisation here.
+}  // extern "C"
+namespace gx {
+int comm_enqueue_reduce(gx_ctx* ctx, int what, cudaStream_t st) {
+  int rc;
+  for (auto& P : ctx->peers) if ((rc = pack_peer(ctx, P, what, st))) return rc;
+  GX_NCCL(ctx->nccl->GroupStart());
+  for (auto& P : ctx->peers) {
+    size_t const ns = P.send_nodes.size(), nr = P.recv_nodes.size();
+    if ((what & 5) && ns) GX_NCCL(ctx->nccl->Send(P.d_sendR, 4 * ns, kNcclFloat64, P.rank, ctx->comm, st));
+    if ((what & 5) && nr) GX_NCCL(ctx->nccl->Recv(P.d_recvR, 4 * nr, kNcclFloat64, P.rank, ctx->comm, st));
+    if ((what & 2) && P.send_vals) GX_NCCL(ctx->nccl->Send(P.d_send, (size_t)P.send_vals, kNcclFloat64, P.rank, ctx->comm, st));
+    if ((what & 2) && P.recv_vals) GX_NCCL(ctx->nccl->Recv(P.d_recv, (size_t)P.recv_vals, kNcclFloat64, P.rank, ctx->comm, st));
+  }
+  GX_NCCL(ctx->nccl->GroupEnd());
+  for (auto& P : ctx->peers) if ((rc = unpack_peer(ctx, P, what, P.d_recvR, P.d_recv, st))) return rc;  // ascending rank
+  return GX_OK;
+}
+}  // namespace gx
+extern "C" {
 
 // what must be 1 (R, 4 doubles per send node) or 2 (CRS rows); *send_dev is valid until the next pack
 int gx_pack_interface(gx_ctx* ctx, int peer_index, int what, void** send_dev) {
@@ -659,7 +680,7 @@ int gx_pack_interface(gx_ctx* ctx, int peer_index, int what, void** send_dev) {
   if (what == 4 && !ctx->have_dMdu) { ctx->err = "no functional derivative on the device"; return GX_ERR_ARG; }
   Peer& P = ctx->peers[peer_index];
   GX_CUDA(cudaSetDevice(ctx->device));
-  if ((rc = pack_peer(ctx, P, what))) return rc;
+  if ((rc = pack_peer(ctx, P, what, ctx->stream))) return rc;
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   if (send_dev) *send_dev = what != 2 ? (void*)P.d_sendR : (void*)P.d_send;
   return GX_OK;
@@ -673,7 +694,7 @@ int gx_unpack_add_interface(gx_ctx* ctx, int peer_index, int what, const void* r
   if (what == 4 && !ctx->have_dMdu) { ctx->err = "no functional derivative on the device"; return GX_ERR_ARG; }
   Peer& P = ctx->peers[peer_index];
   GX_CUDA(cudaSetDevice(ctx->device));
-  if ((rc = unpack_peer(ctx, P, what, (double const*)recv_dev, (double const*)recv_dev))) return rc;
+  if ((rc = unpack_peer(ctx, P, what, (double const*)recv_dev, (double const*)recv_dev, ctx->stream))) return rc;
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
@@ -804,17 +825,7 @@ int gx_reduce_interfaces(gx_ctx* ctx, int what) {
   if ((what & 2) && !ctx->have_values) { ctx->err = "gx_reduce_interfaces: what & 2 needs the CRS values of a Jacobian pass (the last pass left none)"; return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
   GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-  for (auto& P : ctx->peers) if ((rc = pack_peer(ctx, P, what))) return rc;
-  GX_NCCL(ctx->nccl->GroupStart());
-  for (auto& P : ctx->peers) {
-    size_t const ns = P.send_nodes.size(), nr = P.recv_nodes.size();
-    if ((what & 5) && ns) GX_NCCL(ctx->nccl->Send(P.d_sendR, 4 * ns, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
-    if ((what & 5) && nr) GX_NCCL(ctx->nccl->Recv(P.d_recvR, 4 * nr, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
-    if ((what & 2) && P.send_vals) GX_NCCL(ctx->nccl->Send(P.d_send, (size_t)P.send_vals, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
-    if ((what & 2) && P.recv_vals) GX_NCCL(ctx->nccl->Recv(P.d_recv, (size_t)P.recv_vals, kNcclFloat64, P.rank, ctx->comm, ctx->stream));
-  }
-  GX_NCCL(ctx->nccl->GroupEnd());
-  for (auto& P : ctx->peers) if ((rc = unpack_peer(ctx, P, what, P.d_recvR, P.d_recv))) return rc;  // ascending rank
+  if ((rc = comm_enqueue_reduce(ctx, what, ctx->stream))) return rc;
   GX_CUDA(cudaEventRecord(ctx->ev[3], ctx->stream));
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0;

@@ -94,6 +94,7 @@ struct gx_ctx {
   // ---- patch schedule of the patch-gather Jacobian pass (kernel = 3), see build_patch_schedule()
   std::vector<uint32_t> patch_sched;
   int n_patches = 0;
+  int n_patches_iface = 0;  // partitioned contexts: the leading patches that write every block of the interface rows
   int patch_state = 0;  // 0 = not built, 1 = built, -1 = mesh does not fit (a node exceeds a patch)
   // ---- schedule
   int ncolors = 0;
@@ -101,6 +102,8 @@ struct gx_ctx {
   std::vector<int32_t> perm;       // device slot -> user element
   // ---- device
   cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;  // interface exchange overlapped with the interior patches (option "overlap")
+  cudaEvent_t ev_iface = nullptr, ev_b2 = nullptr, ev_comm = nullptr;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   gx::NodeRec* d_nodes = nullptr;
   gx::ZRec* d_z = nullptr;
@@ -161,6 +164,10 @@ struct gx_ctx {
   bool have_values = false;
   int64_t opt_block = 128;
   int64_t opt_prefetch = 256;  // stage B L2 prefetch distance in patches (measured best on 12.6M tets: 150-300; one generation of resident blocks is 592)
+  int64_t overlap_now = 0;  // `what` of the exchange fused into the pass being enqueued (0: none)
+  bool overlapped = false;  // the last pass reduced the interfaces itself
+  int64_t opt_overlap = 0;  // bit mask like gx_reduce_interfaces' `what` (1 = R, 2 = dRdu): the Jacobian pass reduces the
+                            // interfaces itself, on a second stream, while the interior patches are still being assembled
   int64_t opt_kernel = 0;  // 0 = owner-computes schedules (patch pairs / gather form), 1 = coloured elements
   int num_sms = 148;
   std::string err;
@@ -204,4 +211,5 @@ static_assert(PATCH_RECS <= 256, "record slots are 8 bit");
 void comm_destroy(gx_ctx*);
 int comm_setup_lists(gx_ctx*, const gx_desc*);
 int ghost_values_dev(gx_ctx* ctx, double** out);
+int comm_enqueue_reduce(gx_ctx* ctx, int what, cudaStream_t stream);  // pack, send/recv, unpack-add: enqueued, not synchronised
 }  // namespace gx

@@ -252,7 +252,7 @@ bool build_patch_schedule(gx_ctx* c) {
   int const nn = c->nn;
   std::vector<int64_t> const& nx = c->nrow_x;
   int const CH = 4096;  // nodes per independent chunk of the visiting order
-  int const nch = (nn + CH - 1) / CH;
+  int const nch = (nn + CH - 1) / CH + 1;  // upper bound (the two node classes are chunked separately)
   std::vector<std::vector<uint32_t>> out(nch);
   bool const stats = getenv("GX_SCHED_STATS") != nullptr;
   bool const nomatch = getenv("GX_SCHED_NOMATCH") != nullptr;
@@ -266,10 +266,30 @@ bool build_patch_schedule(gx_ctx* c) {
   if (char const* e = getenv("GX_SCHED_SPLIT")) split = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT_DIAG")) split_diag = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
   auto n_parts = [&](int cnt, bool diag) { int const sp = diag ? split_diag : split; return std::max(1, (cnt + sp - 1) / sp); };
+  // Visiting order: the Z-curve order of the nodes; on a partitioned context the nodes on part boundaries and their
+  // neighbours come first (each class in Z-curve order).  Every block of an interface node's rows -- its diagonal, and
+  // its pairs, which belong to the earlier end of an edge whose two ends are both in that class -- is then written by
+  // the first n_patches_iface patches, so the interface exchange can start while the interior patches still run.
+  std::vector<int32_t> order(c->node_order);
+  int n_first = 0;
+  if (!c->peers.empty()) {
+    std::vector<char> mark(nn, 0);
+    for (auto const& P : c->peers) for (int a : P.nodes) mark[a] = 1;
+    std::vector<char> near(mark);
+    for (int a = 0; a < nn; ++a)
+      if (mark[a]) for (int64_t k = c->nrow[a]; k < c->nrow[a + 1]; ++k) near[c->ncol[k]] = 1;
+    std::stable_partition(order.begin(), order.end(), [&](int32_t a) { return near[a] != 0; });
+    for (int a = 0; a < nn; ++a) n_first += near[a] != 0;
+  }
   std::vector<int32_t> rank(nn);
-  for (int s2 = 0; s2 < nn; ++s2) rank[c->node_order[s2]] = s2;
+  for (int s2 = 0; s2 < nn; ++s2) rank[order[s2]] = s2;
+  // chunks of the visiting order, built independently; no chunk straddles the two classes
+  std::vector<std::pair<int, int>> chunk_rng;
+  for (int b0 = 0; b0 < n_first; b0 += CH) chunk_rng.emplace_back(b0, std::min(n_first, b0 + CH));
+  int const n_chunks_first = (int)chunk_rng.size();
+  for (int b0 = n_first; b0 < nn; b0 += CH) chunk_rng.emplace_back(b0, std::min(nn, b0 + CH));
 #pragma omp parallel for schedule(dynamic, 1)
-  for (int ch = 0; ch < nch; ++ch) {
+  for (int ch = 0; ch < (int)chunk_rng.size(); ++ch) {
     struct Item { uint16_t ent[PATCH_ITEM_LEN]; int n; uint32_t w0, w1, w2; int kind, type, nsec, part; };
     std::vector<Item> items;
     std::vector<int32_t> recs;
@@ -545,12 +565,12 @@ bool build_patch_schedule(gx_ctx* c) {
     };
     hclear();
     bool bad = false;
-    int const s1 = std::min(nn, (ch + 1) * CH);
+    int const s1 = chunk_rng[ch].second;
     // the items of node a: its diagonal block, the edges it owns, its phantom blocks
     struct Blk { int64_t t; int type; int cnt; int parts; };
     std::vector<Blk> blks;
-    for (int s = ch * CH; s < s1; ++s) {
-      int const a = c->node_order[s];
+    for (int s = chunk_rng[ch].first; s < s1; ++s) {
+      int const a = order[s];
       if (nx[a + 1] == nx[a]) continue;  // a node without elements: no blocks, no work (its R entries are zeroed by the pass)
       int add = 0;  // new records this node would add
       for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) if (hfind(c->adj[k].x >> 2) < 0) ++add;
@@ -624,11 +644,14 @@ bool build_patch_schedule(gx_ctx* c) {
   }
   if (!ok) { c->patch_state = -1; return false; }
   size_t total = 0;
-  for (auto& v : out) total += v.size();
+  std::vector<size_t> out_sizes;
+  for (auto& v : out) { total += v.size(); out_sizes.push_back(v.size()); }
   c->patch_sched.clear();
   c->patch_sched.reserve(total);
   for (auto& v : out) { c->patch_sched.insert(c->patch_sched.end(), v.begin(), v.end()); std::vector<uint32_t>().swap(v); }
   c->n_patches = (int)(total / PATCH_WORDS);
+  c->n_patches_iface = 0;
+  for (int ch = 0; ch < n_chunks_first; ++ch) c->n_patches_iface += (int)(out_sizes[ch] / PATCH_WORDS);
   c->patch_state = 1;
   if (stats) {
     int64_t wv = 0, rd = 0, runs = 0, nrecs = 0, nit = 0, nco = 0;

@@ -41,6 +41,16 @@ def main():
         R2, V2, _ = a.fetch_owned()
         assert np.array_equal(R1, R2) and np.array_equal(V1, V2)
         _check_owned(a, me, o, Rs, Vs)
+        # the same pass with the exchange fused in (option "overlap": interface patches first, pack -> NCCL -> unpack on a
+        # second stream while the interior patches run): bit-identical owned rows, no separate gx_reduce_interfaces
+        a.set_option("overlap", 3)
+        a.jacobian(goal_b200.PRIMAL, save=False, out=False)
+        R3, V3, _ = a.fetch_owned()
+        assert np.array_equal(R1, R3) and np.array_equal(V1, V3)
+        assert a.last_timing()["launches"] >= 3  # element records, interface patches, interior patches (+ pack / unpack)
+        Rt, Vt, tp = a.fetch_owned_tpetra()
+        assert np.array_equal(Rt, R3) and np.isclose(np.abs(Vt).sum(), np.abs(V3).sum(), rtol=1e-13)
+        a.set_option("overlap", 0)
         # Disc::add_soln + apf::synchronize over NCCL (gx_add_solution, gx_sync_solution): right on owned nodes,
         # garbage on copies, the owner's value wins everywhere
         dug = 1e-3 * np.random.RandomState(9).randn(len(fs["u"]), 4)
