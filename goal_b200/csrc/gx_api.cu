@@ -40,6 +40,17 @@ __global__ void pack_z_kernel(ZRec* z, double const* zu, double const* zp, doubl
   z[n].zpc = zpc[n];
 }
 
+// Mechanics::make_states (goal_mechanics.cpp:87-95) with the identity initialisation of goal_states.cpp:87-128:
+// sigma = 0, eqps = eqps_old = 0, Fp = Fp_old = I (J2), cached Cp^{-1} = I
+__global__ void init_states_kernel(double* state_in, double* fp_old, double* state_out, int ne, int j2) {
+  int const e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= ne) return;
+  double const one = j2 ? 1.0 : 0.0;
+  for (int k = 0; k < STATE_IN; ++k) state_in[(int64_t)STATE_IN * e + k] = k < 3 ? one : 0.0;
+  for (int k = 0; k < 9; ++k) fp_old[(int64_t)9 * e + k] = (k % 4 == 0) ? one : 0.0;
+  for (int k = 0; k < STATE_OUT; ++k) state_out[(int64_t)STATE_OUT * e + k] = (k >= SO_FP && k < SO_FP + 9 && (k - SO_FP) % 4 == 0) ? one : 0.0;
+}
+
 // user field array [ne][ncomp] <-> a slice of the per-element state records
 __global__ void field_to_record_kernel(double* rec, int stride, int off, double const* field, int ne, int ncomp) {
   int64_t const i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -377,15 +388,17 @@ static cudaError_t launch_patch_gather(gx_ctx* ctx, KParams& P, int pass, bool s
   ctx->launches++;
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if ((e = cudaEventRecord(ctx->ev_iface, ctx->stream)) != cudaSuccess) return e;
+  // the exchange is enqueued (on the high-priority stream) before the interior patches are launched, so that its
+  // kernels are picked as soon as blocks of this stream retire instead of waiting for the interior launch to drain
+  if ((e = cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_iface, 0)) != cudaSuccess) return e;
+  if (comm_enqueue_reduce(ctx, (int)ctx->overlap_now, ctx->comm_stream) != GX_OK) return cudaErrorUnknown;
+  if ((e = cudaEventRecord(ctx->ev_comm, ctx->comm_stream)) != cudaSuccess) return e;
   if (ctx->n_patches > n1) {
     kern<<<ctx->n_patches - n1, PATCH_THREADS, smem, ctx->stream>>>(P, ctx->d_elemrec, ctx->d_patch_sched + (size_t)n1 * PATCH_WORDS);
     ctx->launches++;
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
   }
   if ((e = cudaEventRecord(ctx->ev_b2, ctx->stream)) != cudaSuccess) return e;
-  if ((e = cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_iface, 0)) != cudaSuccess) return e;
-  if (comm_enqueue_reduce(ctx, (int)ctx->overlap_now, ctx->comm_stream) != GX_OK) return cudaErrorUnknown;
-  if ((e = cudaEventRecord(ctx->ev_comm, ctx->comm_stream)) != cudaSuccess) return e;
   if ((e = cudaStreamWaitEvent(ctx->stream, ctx->ev_comm, 0)) != cudaSuccess) return e;
   ctx->overlapped = true;
   return cudaSuccess;
@@ -395,9 +408,16 @@ static int upload_patch_schedule(gx_ctx* ctx) {
   if (ctx->patch_state != 0) return GX_OK;
   if (!build_patch_schedule(ctx)) return GX_OK;  // patch_state = -1: the caller falls back to the coloured schedule
   if (ctx->d_patch_sched) { cudaFree(ctx->d_patch_sched); ctx->d_patch_sched = nullptr; }
-  GX_CUDA(cudaMalloc(&ctx->d_patch_sched, sizeof(uint32_t) * std::max<size_t>(ctx->patch_sched.size(), 1)));
-  GX_CUDA(cudaMemcpy(ctx->d_patch_sched, ctx->patch_sched.data(), sizeof(uint32_t) * ctx->patch_sched.size(), cudaMemcpyHostToDevice));
-  std::vector<uint32_t>().swap(ctx->patch_sched);
+  size_t total = 0;
+  for (auto const& v : ctx->patch_chunks) total += v.size();
+  GX_CUDA(cudaMalloc(&ctx->d_patch_sched, sizeof(uint32_t) * std::max<size_t>(total, 1)));
+  size_t off = 0;
+  for (auto& v : ctx->patch_chunks) {  // chunk by chunk: no flat host copy of the (up to GB-sized) schedule
+    if (!v.empty()) GX_CUDA(cudaMemcpyAsync(ctx->d_patch_sched + off, v.data(), sizeof(uint32_t) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+    off += v.size();
+  }
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<std::vector<uint32_t>>().swap(ctx->patch_chunks);
   return GX_OK;
 }
 
@@ -449,7 +469,9 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   ctx->overlap_now = 0;
   if (patch_gather && ctx->opt_overlap && ctx->nranks > 1 && ctx->comm && !ctx->peers.empty()) {
     if (!ctx->comm_stream) {
-      GX_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+      int lo = 0, hi = 0;
+      GX_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));  // hi = the numerically lowest value = highest priority
+      GX_CUDA(cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, hi));
       GX_CUDA(cudaEventCreate(&ctx->ev_iface)); GX_CUDA(cudaEventCreate(&ctx->ev_b2)); GX_CUDA(cudaEventCreate(&ctx->ev_comm));
     }
     ctx->overlap_now = ctx->opt_overlap & 3;
@@ -598,19 +620,31 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     for (auto& e : ctx->ev) GX_CUDA(cudaEventCreate(&e));
     int const nn = ctx->nn, ne = ctx->ne;
     // ---- nodes and elements (device element order = colour-sorted)
-    HostPack hp;
-    pack_host(ctx, hp);
-    GX_CUDA(cudaMalloc(&ctx->d_nodes, sizeof(NodeRec) * (size_t)nn));
-    GX_CUDA(cudaMemcpy(ctx->d_nodes, hp.nodes.data(), sizeof(NodeRec) * (size_t)nn, cudaMemcpyHostToDevice));
+    {  // node records; conn (int32 x 4) and the scatter map (uint8 x 16) already have the device layout
+      std::vector<NodeRec> nodes(nn);
+#pragma omp parallel for schedule(static)
+      for (int n = 0; n < nn; ++n) {
+        NodeRec& r = nodes[n];
+        for (int j = 0; j < 3; ++j) { r.x[j] = ctx->coords[3 * (size_t)n + j]; r.u[j] = 0.0; }
+        r.p = 0.0;
+        r.blk0 = (int32_t)ctx->nrow[n];
+        r.nblk = (int32_t)(ctx->nrow[n + 1] - ctx->nrow[n]);
+      }
+      GX_CUDA(cudaMalloc(&ctx->d_nodes, sizeof(NodeRec) * (size_t)nn));
+      GX_CUDA(cudaMemcpy(ctx->d_nodes, nodes.data(), sizeof(NodeRec) * (size_t)nn, cudaMemcpyHostToDevice));
+    }
     GX_CUDA(cudaMalloc(&ctx->d_z, sizeof(ZRec) * (size_t)nn));
     GX_CUDA(cudaMemset(ctx->d_z, 0, sizeof(ZRec) * (size_t)nn));
+    static_assert(sizeof(int4) == 4 * sizeof(int32_t) && sizeof(uint4) == 16, "conn / bpos are uploaded as they are");
     GX_CUDA(cudaMalloc(&ctx->d_conn, sizeof(int4) * (size_t)ne));
-    GX_CUDA(cudaMemcpy(ctx->d_conn, hp.conn4.data(), sizeof(int4) * (size_t)ne, cudaMemcpyHostToDevice));
+    GX_CUDA(cudaMemcpy(ctx->d_conn, ctx->conn.data(), sizeof(int4) * (size_t)ne, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_bpos, sizeof(uint4) * (size_t)ne));
-    GX_CUDA(cudaMemcpy(ctx->d_bpos, hp.bpos.data(), sizeof(uint4) * (size_t)ne, cudaMemcpyHostToDevice));
-    if (!hp.eset.empty()) {
+    GX_CUDA(cudaMemcpy(ctx->d_bpos, ctx->bpos.data(), sizeof(uint4) * (size_t)ne, cudaMemcpyHostToDevice));
+    if (!ctx->eset.empty()) {
+      std::vector<uint8_t> es(ne);
+      for (int e = 0; e < ne; ++e) es[e] = (uint8_t)ctx->eset[e];
       GX_CUDA(cudaMalloc(&ctx->d_eset, (size_t)ne));
-      GX_CUDA(cudaMemcpy(ctx->d_eset, hp.eset.data(), (size_t)ne, cudaMemcpyHostToDevice));
+      GX_CUDA(cudaMemcpy(ctx->d_eset, es.data(), (size_t)ne, cudaMemcpyHostToDevice));
     }
     GX_CUDA(cudaMalloc(&ctx->d_perm, sizeof(int32_t) * (size_t)ne));
     GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
@@ -622,18 +656,11 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemcpy(ctx->d_adj, ctx->adj.data(), sizeof(int2) * ctx->adj.size(), cudaMemcpyHostToDevice));
     // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
     {
-      std::vector<double> sin((size_t)STATE_IN * ne, 0.0), sout((size_t)STATE_OUT * ne, 0.0), fpo((size_t)9 * ne, 0.0);
-      if (ctx->model == GX_MODEL_J2)
-        for (int e = 0; e < ne; ++e) {
-          for (int k = 0; k < 3; ++k) sin[(size_t)STATE_IN * e + k] = 1.0;  // Cp^{-1} of Fp_old = I
-          for (int k = 0; k < 9; k += 4) { fpo[(size_t)9 * e + k] = 1.0; sout[(size_t)STATE_OUT * e + SO_FP + k] = 1.0; }
-        }
-      GX_CUDA(cudaMalloc(&ctx->d_state_in, sizeof(double) * sin.size()));
-      GX_CUDA(cudaMalloc(&ctx->d_fp_old, sizeof(double) * fpo.size()));
-      GX_CUDA(cudaMalloc(&ctx->d_state_out, sizeof(double) * sout.size()));
-      GX_CUDA(cudaMemcpy(ctx->d_state_in, sin.data(), sizeof(double) * sin.size(), cudaMemcpyHostToDevice));
-      GX_CUDA(cudaMemcpy(ctx->d_fp_old, fpo.data(), sizeof(double) * fpo.size(), cudaMemcpyHostToDevice));
-      GX_CUDA(cudaMemcpy(ctx->d_state_out, sout.data(), sizeof(double) * sout.size(), cudaMemcpyHostToDevice));
+      GX_CUDA(cudaMalloc(&ctx->d_state_in, sizeof(double) * (size_t)STATE_IN * ne));
+      GX_CUDA(cudaMalloc(&ctx->d_fp_old, sizeof(double) * (size_t)9 * ne));
+      GX_CUDA(cudaMalloc(&ctx->d_state_out, sizeof(double) * (size_t)STATE_OUT * ne));
+      init_states_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ne, ctx->model == GX_MODEL_J2);
+      GX_CUDA(cudaGetLastError());
     }
     // ---- linear objects (SolInfo ghost R / dRdu, src/goal_sol_info.cpp:6-22)
     GX_CUDA(cudaMalloc(&ctx->d_R, sizeof(double) * 4 * (size_t)nn));
@@ -1234,6 +1261,7 @@ int gx_patch_schedule(gx_ctx* ctx, const uint32_t** words, int32_t dims[4]) {
   if (ctx->patch_sched.empty()) {
     ctx->patch_state = 0;
     if (!build_patch_schedule(ctx)) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
+    flatten_patch_schedule(ctx);
     if (ctx->device >= 0) ctx->patch_state = 0;  // the device copy is (re)built by the next Jacobian pass
   }
   *words = ctx->patch_sched.data();
@@ -1252,6 +1280,7 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (k == "patch_schedule_dryrun") {  // host-side build of the patch schedule (works on host-only contexts); GX_SCHED_STATS prints its statistics
     bool const ok = build_patch_schedule(ctx);
     std::vector<uint32_t>().swap(ctx->patch_sched);
+    std::vector<std::vector<uint32_t>>().swap(ctx->patch_chunks);
     ctx->patch_state = 0;
     if (!ok) { ctx->err = "mesh does not fit the patch schedule"; return GX_ERR_UNSUPPORTED; }
     return GX_OK;

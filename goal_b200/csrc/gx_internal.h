@@ -92,7 +92,8 @@ struct gx_ctx {
   std::vector<int32_t> bc;
   bool block_lists_built = false;
   // ---- patch schedule of the patch-gather Jacobian pass (kernel = 3), see build_patch_schedule()
-  std::vector<uint32_t> patch_sched;
+  std::vector<uint32_t> patch_sched;                  // flat (flatten_patch_schedule), or empty while ...
+  std::vector<std::vector<uint32_t>> patch_chunks;    // ... the builder's chunks are still waiting for the upload
   int n_patches = 0;
   int n_patches_iface = 0;  // partitioned contexts: the leading patches that write every block of the interface rows
   int patch_state = 0;  // 0 = not built, 1 = built, -1 = mesh does not fit (a node exceeds a patch)
@@ -190,6 +191,7 @@ constexpr int SO_SIGMA = 0, SO_EQPS = 9, SO_FP = 10;
 void pack_host(gx_ctx const* c, HostPack& h);
 void build_block_lists(gx_ctx* c);
 bool build_patch_schedule(gx_ctx* c);
+void flatten_patch_schedule(gx_ctx* c);
 
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
 #ifndef GX_PATCH_THREADS

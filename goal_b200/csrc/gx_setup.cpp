@@ -19,13 +19,24 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <numeric>
 
 #include "gx_internal.h"
 
 namespace gx {
 
+namespace {
+struct SetupTimer {  // GX_SETUP_TIMING=1 prints the wall time of every setup section to stderr
+  bool on = getenv("GX_SETUP_TIMING") != nullptr;
+  double t0 = now();
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  void lap(char const* what) { if (!on) return; double const t = now(); fprintf(stderr, "[gx setup] %-28s %.3f s\n", what, t - t0); t0 = t; }
+};
+}  // namespace
+
 int build_graph_and_schedule(gx_ctx* c) {
+  SetupTimer tm;
   int const nn = c->nn, ne = c->ne;
   int32_t const* conn = c->conn.data();
   for (int64_t i = 0; i < 4 * (int64_t)ne; ++i)
@@ -38,6 +49,7 @@ int build_graph_and_schedule(gx_ctx* c) {
   }
   if ((int64_t)ne >= (1ll << 29)) { c->err = "more than 2^29 elements per part"; return GX_ERR_UNSUPPORTED; }
 
+  tm.lap("validate");
   // ---- node -> elements (counting sort)
   std::vector<int64_t> n2e_off(nn + 1, 0);
   for (int64_t i = 0; i < 4 * (int64_t)ne; ++i) n2e_off[conn[i] + 1]++;
@@ -49,6 +61,7 @@ int build_graph_and_schedule(gx_ctx* c) {
       for (int a = 0; a < 4; ++a) n2e[cur[conn[4 * (int64_t)e + a]]++] = e;
   }
 
+  tm.lap("node->elements");
   // ---- row-owner work list: incidences (e, n) of every node, elements ascending
   c->adj_off.resize(nn + 1);
   c->max_deg = 0;
@@ -95,6 +108,7 @@ int build_graph_and_schedule(gx_ctx* c) {
     }
   }
 
+  tm.lap("node adjacency");
   // ---- scatter map: position of block (a_n, a_m) in a_n's block row
   c->bpos.resize(16 * (size_t)ne);
 #pragma omp parallel for schedule(static)
@@ -122,6 +136,7 @@ int build_graph_and_schedule(gx_ctx* c) {
       c->adj[k].y = (int)((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
     }
 
+  tm.lap("scatter map + incidences");
   // ---- diagonal block position per node (Dirichlet rows put their 1 there)
   c->diag_pos.assign(nn, 0);
 #pragma omp parallel for schedule(static)
@@ -163,6 +178,7 @@ int build_graph_and_schedule(gx_ctx* c) {
     for (int a = 0; a < nn; ++a) c->node_order[a] = (int32_t)(key[a] & 0xffffffffu);
   }
 
+  tm.lap("diag + Z-curve order");
   // ---- greedy colouring over node conflicts (elements sharing a node get different colours)
   constexpr int W = 4;  // 256 colours at most
   std::vector<uint64_t> used((size_t)nn * W, 0);
@@ -190,6 +206,7 @@ int build_graph_and_schedule(gx_ctx* c) {
     std::vector<int32_t> cur(c->color_off.begin(), c->color_off.end() - 1);
     for (int e = 0; e < ne; ++e) c->perm[cur[color[e]]++] = e;  // stable: natural order inside a colour
   }
+  tm.lap("colouring");
   return GX_OK;
 }
 
@@ -248,7 +265,9 @@ void build_block_lists(gx_ctx* c) {
 //   then     runs[PATCH_RECS][2]       bulk copies: first element id, first slot | number of records << 8
 bool build_patch_schedule(gx_ctx* c) {
   using namespace gx;
+  SetupTimer tm;
   if (!c->block_lists_built) build_block_lists(c);
+  tm.lap("block lists");
   int const nn = c->nn;
   std::vector<int64_t> const& nx = c->nrow_x;
   int const CH = 4096;  // nodes per independent chunk of the visiting order
@@ -306,6 +325,12 @@ bool build_patch_schedule(gx_ctx* c) {
       hkey[h] = e; hval[h] = (int16_t)v;
     };
     int nparts = 0, cur_d = 0, cur_p = 0;  // secondaries, DIAG lanes and PAIR lanes of the patch being filled
+    // scratch of flush(), allocated once per chunk
+    struct UnitS { int prim, nsec, len; };
+    std::vector<int> ord, zeros, res, slot_of, byel, feed_off, feed_q, qcap;
+    std::vector<uint32_t> run_e0, run_sl;
+    std::vector<std::array<int, 8>> qload;
+    std::vector<UnitS> groups_s, singles_s;
     auto flush = [&]() {
       if (items.empty()) return;
       // Lane order: typed warps.  The first PATCH_DIAG_LANES lanes (whole warps) hold the DIAG items, the rest the
@@ -316,25 +341,20 @@ bool build_patch_schedule(gx_ctx* c) {
       // construction; a unit that would straddle a warp boundary is preceded by the shortest single items of the
       // region as filler), then the single items, longest first: the lanes of a warp then run the same number of
       // contributions.  ord[t] = item of lane t, -1 = idle lane.
-      std::vector<int> ord;
+      ord.clear();
       bool block_sync = false;
       {
-        struct Unit { int prim; std::vector<int> sec; int len; };
-        std::vector<int> prim_of_part(PATCH_PARTS + 1, -1);
-        for (size_t i = 0; i < items.size(); ++i)
-          if (items[i].kind == 1) for (int q = 0; q < items[i].nsec; ++q) prim_of_part[items[i].part + q] = (int)i;
-        std::vector<std::vector<int>> secs(items.size());
-        for (size_t i = 0; i < items.size(); ++i) if (items[i].kind == 2) secs[prim_of_part[items[i].part]].push_back((int)i);
-        std::vector<int> zeros;
-        auto layout = [&](int type, int first_lane, int n_lanes) {
-          std::vector<Unit> groups, singles;
+        using Unit = UnitS;  // the secondaries of item i are items i+1 .. i+nsec (pushed right behind it)
+        std::vector<Unit>& groups = groups_s; std::vector<Unit>& singles = singles_s;
+        auto layout = [&](int type, int first_lane) {
+          groups.clear(); singles.clear();
           for (size_t i = 0; i < items.size(); ++i) {
             if (items[i].kind != 1 || items[i].type != type) continue;
-            Unit u{(int)i, secs[i], items[i].n};
-            (u.sec.empty() ? singles : groups).push_back(u);
+            Unit const u{(int)i, items[i].nsec, items[i].n};
+            (u.nsec == 0 ? singles : groups).push_back(u);
           }
           std::stable_sort(groups.begin(), groups.end(), [](Unit const& x, Unit const& y) {
-            if (x.sec.size() != y.sec.size()) return x.sec.size() > y.sec.size();
+            if (x.nsec != y.nsec) return x.nsec > y.nsec;
             return x.len > y.len;
           });
           std::stable_sort(singles.begin(), singles.end(), [](Unit const& x, Unit const& y) { return x.len > y.len; });
@@ -345,19 +365,18 @@ bool build_patch_schedule(gx_ctx* c) {
             while (lanes-- > 0) ord.push_back(-1);
           };
           for (Unit const& u : groups) {
-            int const sz = 1 + (int)u.sec.size();
+            int const sz = 1 + u.nsec;
             int const room = 32 - (int)(ord.size() % 32);
             if (sz > 32) block_sync = true;
             else if (sz > room) fill(room);
-            ord.push_back(u.prim);
-            for (int q : u.sec) ord.push_back(q);
+            for (int q = 0; q < sz; ++q) ord.push_back(u.prim + q);
           }
           for (size_t i = 0; i < pool_end; ++i) ord.push_back(singles[i].prim);
-          (void)n_lanes;
         };
-        layout(1, 0, PATCH_DIAG_LANES);
+        layout(1, 0);
         int const diag_end = (int)ord.size();
-        layout(2, std::max(diag_end, PATCH_DIAG_LANES), PATCH_THREADS - PATCH_DIAG_LANES);
+        layout(2, std::max(diag_end, PATCH_DIAG_LANES));
+        zeros.clear();
         for (size_t i = 0; i < items.size(); ++i) if (items[i].type == 0) zeros.push_back((int)i);
         // zeros into the idle lanes, then behind
         size_t zi = 0;
@@ -382,17 +401,28 @@ bool build_patch_schedule(gx_ctx* c) {
       // contributions of its eight items are spread evenly over the eight groups (no group more than the warp's
       // rounds, if possible), and (2) every quarter-warp orders its contributions by an edge colouring (below).
       int const nrec = (int)recs.size();
-      std::vector<int> res(nrec, -1);
-      std::vector<int> slot_of(nrec, -1);
-      std::vector<uint32_t> run_e0, run_sl;  // runs of consecutive elements in consecutive slots: one bulk copy each
+      res.assign(nrec, -1);
+      slot_of.assign(nrec, -1);
+      run_e0.clear(); run_sl.clear();  // runs of consecutive elements in consecutive slots: one bulk copy each
       int const nquart = ((int)ord.size() + 7) / 8;
-      std::vector<std::vector<int>> feeds(nrec);  // quarter-warps a record feeds, with multiplicity
+      // quarter-warps a record feeds, with multiplicity (CRS: feed_off / feed_q)
+      feed_off.assign(nrec + 1, 0);
       for (size_t t = 0; t < ord.size(); ++t) {
         Item const& it = items[ord[t]];
-        for (int q = 0; q < it.n; ++q) feeds[it.ent[q] & 0xff].push_back((int)(t / 8));
+        for (int q = 0; q < it.n; ++q) feed_off[(it.ent[q] & 0xff) + 1]++;
       }
-      std::vector<std::array<int, 8>> qload(nquart, std::array<int, 8>{});  // contributions of quarter Q that read bank group r
-      std::vector<int> qcap(nquart, 0);  // rounds of the quarter's warp
+      for (int l = 0; l < nrec; ++l) feed_off[l + 1] += feed_off[l];
+      feed_q.resize(feed_off[nrec]);
+      {
+        int cur[PATCH_RECS];
+        for (int l = 0; l < nrec; ++l) cur[l] = feed_off[l];
+        for (size_t t = 0; t < ord.size(); ++t) {
+          Item const& it = items[ord[t]];
+          for (int q = 0; q < it.n; ++q) feed_q[cur[it.ent[q] & 0xff]++] = (int)(t / 8);
+        }
+      }
+      qload.assign(nquart, std::array<int, 8>{});  // contributions of quarter Q that read bank group r
+      qcap.assign(nquart, 0);                       // rounds of the quarter's warp
       for (int Q = 0; Q < nquart; ++Q) {
         int R = 0;
         for (size_t t = ((size_t)Q / 4) * 32; t < std::min(ord.size(), ((size_t)Q / 4) * 32 + 32); ++t) R = std::max(R, items[ord[t]].n);
@@ -401,17 +431,17 @@ bool build_patch_schedule(gx_ctx* c) {
       // cost of giving record l the bank group r: readers already there, and heavily, readers beyond the rounds
       auto conflicts = [&](int l, int r) {
         int c2 = 0;
-        for (int Q : feeds[l]) c2 += qload[Q][r] + (qload[Q][r] >= qcap[Q] ? 16 : 0);
+        for (int k = feed_off[l]; k < feed_off[l + 1]; ++k) { int const Q = feed_q[k]; c2 += qload[Q][r] + (qload[Q][r] >= qcap[Q] ? 16 : 0); }
         return c2;
       };
       auto place = [&](int l, int r) {
         res[l] = r;
-        for (int Q : feeds[l]) qload[Q][r]++;
+        for (int k = feed_off[l]; k < feed_off[l + 1]; ++k) qload[feed_q[k]][r]++;
       };
       {
         // Records of consecutive elements are consecutive in global memory: placed in consecutive slots they arrive with
         // ONE bulk copy.  Longest runs first, each at the free position with the fewest conflicts (ties: lowest slot).
-        std::vector<int> byel(nrec);
+        byel.resize(nrec);
         for (int l = 0; l < nrec; ++l) byel[l] = l;
         std::sort(byel.begin(), byel.end(), [&](int x, int y) { return recs[x] < recs[y]; });
         struct Run { int first, len; };
@@ -426,15 +456,21 @@ bool build_patch_schedule(gx_ctx* c) {
         bool taken[PATCH_RECS] = {};
         for (size_t ri = 0; ri < runs.size(); ++ri) {
           Run const run = runs[ri];
+          // the cost of a position depends on its residue modulo 8 only: rate the eight residues, then take the
+          // first free position of the best residue that has one
+          int rcost[8];
+          for (int r0 = 0; r0 < 8; ++r0) {
+            rcost[r0] = 0;
+            for (int j = 0; j < run.len; ++j) rcost[r0] += conflicts(byel[run.first + j], (r0 + j) & 7);
+          }
           int best = -1, best_cost = 1 << 30;
           for (int s0 = 0; s0 + run.len <= PATCH_RECS; ++s0) {
+            if (rcost[s0 & 7] >= best_cost) continue;
             bool free_ = true;
             for (int j = 0; j < run.len && free_; ++j) free_ = !taken[s0 + j];
             if (!free_) continue;
-            int cost = 0;
-            for (int j = 0; j < run.len; ++j) cost += conflicts(byel[run.first + j], (s0 + j) & 7);
-            if (cost < best_cost) { best_cost = cost; best = s0; }
-            if (cost == 0) break;
+            best_cost = rcost[s0 & 7]; best = s0;
+            if (best_cost == 0) break;
           }
           if (best < 0) {  // fragmented: cut the run in two and place the halves
             runs.push_back({run.first, run.len / 2});
@@ -461,55 +497,60 @@ bool build_patch_schedule(gx_ctx* c) {
         for (size_t t = (g0 / 32) * 32; t < std::min(ord.size(), (g0 / 32) * 32 + 32); ++t) R = std::max(R, items[ord[t]].n);
         if (R == 0) continue;
         struct Edge { int u, v, q, col; };
-        std::vector<Edge> edges;
+        Edge edges[8 * PATCH_ITEM_LEN];
+        int n_edges = 0;
         int degv[8] = {};
         for (int i = 0; i < gn; ++i) {
           Item const& it = items[ord[g0 + i]];
-          for (int q = 0; q < it.n; ++q) { int const v = res[it.ent[q] & 0xff]; edges.push_back({i, v, q, -1}); degv[v]++; }
+          for (int q = 0; q < it.n; ++q) { int const v = res[it.ent[q] & 0xff]; edges[n_edges++] = {i, v, q, -1}; degv[v]++; }
         }
         int C = R;
-        for (int v = 0; v < 8; ++v) C = std::max(C, degv[v]);
-        C = std::min(C, 64);
-        std::vector<int> atu(8 * C, -1), atv(8 * C, -1);  // edge with colour c at item u / at bank group v
-        for (size_t ei = 0; ei < edges.size(); ++ei) {
+        for (int v = 0; v < 8; ++v) C = std::max(C, degv[v]);  // <= 8 * PATCH_ITEM_LEN
+        int atu[8 * 8 * PATCH_ITEM_LEN], atv[8 * 8 * PATCH_ITEM_LEN];  // edge with colour c at item u / at bank group v
+        for (int k = 0; k < 8 * C; ++k) { atu[k] = -1; atv[k] = -1; }
+        for (int ei = 0; ei < n_edges; ++ei) {
           Edge& e = edges[ei];
           int ca = -1, cb = -1;
           for (int c2 = 0; c2 < C && ca < 0; ++c2) if (atu[e.u * C + c2] < 0) ca = c2;
           for (int c2 = 0; c2 < C && cb < 0; ++c2) if (atv[e.v * C + c2] < 0) cb = c2;
-          if (ca < 0 || cb < 0) { e.col = -2; continue; }  // more than 64 contributions in one bank group: placed below
+          if (ca < 0 || cb < 0) { e.col = -2; continue; }  // cannot happen (C >= every degree); placed below if it does
           if (atv[e.v * C + ca] >= 0) {
             // colour ca is taken at v: swap ca <-> cb along the alternating path that starts at v with colour ca
-            std::vector<int> path;
+            int path[8 * PATCH_ITEM_LEN], n_path = 0;
             int cur = atv[e.v * C + ca];
             bool at_v = true;  // the path edge was reached through its v end
             int want = ca;
             while (cur >= 0) {
-              path.push_back(cur);
+              path[n_path++] = cur;
               Edge const& pe = edges[cur];
               want = want == ca ? cb : ca;
               cur = at_v ? atu[pe.u * C + want] : atv[pe.v * C + want];
               at_v = !at_v;
             }
-            for (int pi : path) { Edge& pe = edges[pi]; atu[pe.u * C + pe.col] = -1; atv[pe.v * C + pe.col] = -1; }
-            for (int pi : path) { Edge& pe = edges[pi]; pe.col = pe.col == ca ? cb : ca; atu[pe.u * C + pe.col] = pi; atv[pe.v * C + pe.col] = pi; }
+            for (int k = 0; k < n_path; ++k) { Edge& pe = edges[path[k]]; atu[pe.u * C + pe.col] = -1; atv[pe.v * C + pe.col] = -1; }
+            for (int k = 0; k < n_path; ++k) { Edge& pe = edges[path[k]]; pe.col = pe.col == ca ? cb : ca; atu[pe.u * C + pe.col] = path[k]; atv[pe.v * C + pe.col] = path[k]; }
           }
           e.col = ca;
-          atu[e.u * C + ca] = (int)ei; atv[e.v * C + ca] = (int)ei;
+          atu[e.u * C + ca] = ei; atv[e.v * C + ca] = ei;
         }
         uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
         bool used_round[8][PATCH_ITEM_LEN] = {};
         int readers[PATCH_ITEM_LEN][8] = {};  // readers of bank group v in round k (distinct records not tracked: a bound)
-        for (Edge const& e : edges)
+        for (int ei = 0; ei < n_edges; ++ei) {
+          Edge const& e = edges[ei];
           if (e.col >= 0 && e.col < R) {
             sched_ent[e.u][e.col] = items[ord[g0 + e.u]].ent[e.q]; used_round[e.u][e.col] = true; readers[e.col][e.v]++;
           }
-        for (Edge const& e : edges)
+        }
+        for (int ei = 0; ei < n_edges; ++ei) {
+          Edge const& e = edges[ei];
           if (e.col < 0 || e.col >= R) {  // surplus: the free round of this item where the group has the fewest readers
             int best = -1;
             for (int k = 0; k < R; ++k)
               if (!used_round[e.u][k] && (best < 0 || readers[k][e.v] < readers[best][e.v])) best = k;
             sched_ent[e.u][best] = items[ord[g0 + e.u]].ent[e.q]; used_round[e.u][best] = true; readers[best][e.v]++;
           }
+        }
         for (int i = 0; i < gn; ++i) {
           Item& it = items[ord[g0 + i]];
           if (it.n == 0) continue;
@@ -642,17 +683,20 @@ bool build_patch_schedule(gx_ctx* c) {
       ok = false;
     }
   }
+  tm.lap("patches");
   if (!ok) { c->patch_state = -1; return false; }
   size_t total = 0;
   std::vector<size_t> out_sizes;
   for (auto& v : out) { total += v.size(); out_sizes.push_back(v.size()); }
+  // the chunks stay as they are: the device upload copies them one by one (upload_patch_schedule), a flat host copy
+  // is made only on request (flatten_patch_schedule: gx_patch_schedule, the CPU replay of tests/hostcheck)
   c->patch_sched.clear();
-  c->patch_sched.reserve(total);
-  for (auto& v : out) { c->patch_sched.insert(c->patch_sched.end(), v.begin(), v.end()); std::vector<uint32_t>().swap(v); }
+  c->patch_chunks.swap(out);
   c->n_patches = (int)(total / PATCH_WORDS);
   c->n_patches_iface = 0;
   for (int ch = 0; ch < n_chunks_first; ++ch) c->n_patches_iface += (int)(out_sizes[ch] / PATCH_WORDS);
   c->patch_state = 1;
+  tm.lap("concatenate");
   if (stats) {
     int64_t wv = 0, rd = 0, runs = 0, nrecs = 0, nit = 0, nco = 0;
     for (int i = 0; i < nch; ++i) { wv += st_wave[i]; rd += st_rounds[i]; runs += st_runs[i]; nrecs += st_recs[i]; nit += st_items[i]; nco += st_contrib[i]; }
@@ -662,6 +706,17 @@ bool build_patch_schedule(gx_ctx* c) {
             nit ? (double)nco / (double)nit : 0.0, rd ? (double)wv / (double)rd : 0.0);
   }
   return true;
+}
+
+void flatten_patch_schedule(gx_ctx* c) {
+  if (!c->patch_sched.empty() || c->patch_chunks.empty()) return;
+  std::vector<size_t> off(c->patch_chunks.size() + 1, 0);
+  for (size_t i = 0; i < c->patch_chunks.size(); ++i) off[i + 1] = off[i] + c->patch_chunks[i].size();
+  c->patch_sched.resize(off.back());
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int i = 0; i < (int)c->patch_chunks.size(); ++i)
+    if (!c->patch_chunks[i].empty()) memcpy(c->patch_sched.data() + off[i], c->patch_chunks[i].data(), sizeof(uint32_t) * c->patch_chunks[i].size());
+  std::vector<std::vector<uint32_t>>().swap(c->patch_chunks);
 }
 
 void pack_host(gx_ctx const* c, HostPack& h) {

@@ -360,6 +360,7 @@ extern "C" int hc_patch_gather(int model, int transpose, int nn, int ne, const i
   if (rc) return rc;
   c.nrow_x = c.nrow;  // single part: no phantom blocks (comm_setup_lists does this in the library)
   if (!gx::build_patch_schedule(&c)) return 20;
+  gx::flatten_patch_schedule(&c);
   *n_patches = c.n_patches;
   std::vector<double> rec((size_t)gx::TREC * ne);
   for (int e = 0; e < ne; ++e) {  // stage A: the element core and its tangent record, once per element
