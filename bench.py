@@ -243,6 +243,11 @@ def _pass_times(a, fn, reps=5):
 
 
 def run_b200(args):
+    # torchrun pins OMP_NUM_THREADS=1 for multi-process launches; the once-per-mesh host setup (graph, patch schedule)
+    # is OpenMP code, so give every rank its share of the host cores (must happen before libgomp is loaded)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if world_env > 1:
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 1) // world_env))
     import torch
     import torch.distributed as dist
     import goal_b200

@@ -196,12 +196,12 @@ void flatten_patch_schedule(gx_ctx* c);
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
 #ifndef GX_PATCH_THREADS
 #define GX_PATCH_THREADS 96
-#define GX_PATCH_RECS 144
+#define GX_PATCH_RECS 160
 #define GX_PATCH_MINB 4
 #define GX_PATCH_PARTS 24
 #endif
 constexpr int PATCH_THREADS = GX_PATCH_THREADS;  // work items per patch, one per thread
-constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (336 B each); slots are 8 bit
+constexpr int PATCH_RECS = GX_PATCH_RECS;        // element records staged per patch (304 B each); slots are 8 bit
 constexpr int PATCH_MINB = GX_PATCH_MINB;        // thread blocks per SM the kernel is compiled for
 constexpr int PATCH_ITEM_LEN = 8;   // contributions per work item
 constexpr int PATCH_PARTS = GX_PATCH_PARTS;  // secondary items (partial sums handed to a primary) per patch

@@ -18,7 +18,7 @@
 //
 // Schedules, all free of atomics on the data path and bit-reproducible:
 //  (1) Jacobian pass (default): stage A elem_record_kernel (one thread per element: stress update, state save, the
-//      element's 42-double tangent record, tangent_record.cuh) + stage B patch_pair_kernel (one thread block per patch
+//      element's 38-double tangent record, tangent_record.cuh) + stage B patch_pair_kernel (one thread block per patch
 //      of nodes: the patch's records staged in shared memory by bulk copies, one work item per thread -- an edge's two
 //      mirror blocks or a diagonal block with the node's residual entries -- accumulated in registers and written once).
 //      No zeroing pass, no read-modify-write traffic.
@@ -256,11 +256,11 @@ __global__ void __launch_bounds__(128) assemble_kernel(const __grid_constant__ K
 // ---------------------------------------------------------------------------
 // Schedule (1), the default Jacobian pass.
 //   stage A  elem_record_kernel : one thread per element.  Gather, stress update, state save, and the element's
-//            tangent record (tangent_record.cuh: w_n and tqw_n per node, s, G, 14 scalars -- 42 doubles).
+//            tangent record (tangent_record.cuh: w_n and tqw_n per node, s, G, 11 scalars -- 38 doubles).
 //   stage B  patch_pair_kernel  : one thread block per patch of the schedule built by build_patch_schedule
 //            (gx_setup.cpp); see below.
 // ---------------------------------------------------------------------------
-constexpr int ELEM_REC = TREC;  // doubles; 336 B = 21 x 16 B: an odd number of 16 B chunks, see patch_pair_kernel
+constexpr int ELEM_REC = TREC;  // doubles; 304 B = 19 x 16 B: an odd number of 16 B chunks, see patch_pair_kernel
 
 // Warp-cooperative Fp update of 32 consecutive elements e0 .. e0+nrec-1 (lane = element), plastic branch only:
 // Fp = exp(dgam N) Fp_old (goal_J2.cpp:128-131); on the elastic branch the reference leaves Fp untouched (:135-136).
@@ -367,14 +367,14 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
 // (cp.async.bulk, one per run of consecutive elements, completion on an mbarrier: every record crosses the L1 data
 // pipe once per patch instead of once per incident node and lane), then every thread runs one work item:
 //   PAIR : the elements around one mesh edge (a,b).  Per element the two node quadruples, s, G and the scalars are
-//          read once (15 128-bit shared loads) and give BOTH mirror blocks (a,b) and (b,a), which share the node
+//          read once (4 + 11 = 15 128-bit shared loads) and give BOTH mirror blocks (a,b) and (b,a), which share the node
 //          vectors s w, G w and the symmetric scalars -- 32 accumulators in registers;
 //   DIAG : the elements around one node: block (a,a) and the node's four residual entries;
 //   ZERO : a phantom block of a partitioned context, written as zeros.
 // Lists longer than PATCH_ITEM_LEN are finished by their primary item from the secondaries' partial sums (fixed
 // order).  Every block of the operator, and every residual entry, is written exactly once.
-// Bank conflicts: record stride 21 x 16 B (odd), so the bank group of chunk k of the record in slot s is
-// (5 s + k) mod 8; the host schedule gives the 8 lanes of a quarter-warp records in 8 different groups where it can.
+// Bank conflicts: record stride 19 x 16 B (odd), so the bank group of chunk k of the record in slot s is
+// (3 s + k) mod 8; the host schedule gives the 8 lanes of a quarter-warp records in 8 different groups where it can.
 // ---------------------------------------------------------------------------
 constexpr int PATCH_REC_LD = ELEM_REC;
 GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (size_t)PATCH_PARTS * PATCH_PART_LD) * sizeof(double); }
@@ -382,14 +382,14 @@ GX_HD size_t patch_smem_bytes() { return ((size_t)PATCH_RECS * PATCH_REC_LD + (s
 #if defined(__CUDACC__)
 // the pieces of a staged record as registers (128-bit shared loads)
 struct TRegs { double s[6], G[6], sc[SC_N]; };
-__device__ __forceinline__ void trec_load_common(double2 const* q, TRegs& t, bool want_resid) {
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { double2 const v = q[8 + k]; t.s[2 * k] = v.x; t.s[2 * k + 1] = v.y; }
-#pragma unroll
-  for (int k = 0; k < 3; ++k) { double2 const v = q[11 + k]; t.G[2 * k] = v.x; t.G[2 * k + 1] = v.y; }
-#pragma unroll
-  for (int k = 0; k < 5; ++k) { double2 const v = q[14 + k]; t.sc[2 * k] = v.x; t.sc[2 * k + 1] = v.y; }
-  t.sc[SC_RB] = want_resid ? q[19].x : 0.0;
+// chunks 8..18 of a staged record: (s00 s11)(s01 s02)(s12 G0)(G1 G2)(G3 G4)(G5 vb)(a1 Jpv)(upc va)(ppc tjv)(tq0 tq1)(tq2 rb)
+__device__ __forceinline__ void trec_load_common(double2 const* q, TRegs& t) {
+  double2 const c8 = q[8], c9 = q[9], c10 = q[10], c11 = q[11], c12 = q[12], c13 = q[13], c14 = q[14], c15 = q[15], c16 = q[16],
+                c17 = q[17], c18 = q[18];
+  t.s[0] = c8.x; t.s[1] = c8.y; t.s[2] = -(c8.x + c8.y); t.s[3] = c9.x; t.s[4] = c9.y; t.s[5] = c10.x;
+  t.G[0] = c10.y; t.G[1] = c11.x; t.G[2] = c11.y; t.G[3] = c12.x; t.G[4] = c12.y; t.G[5] = c13.x;
+  t.sc[SC_VB] = c13.y; t.sc[SC_A1] = c14.x; t.sc[SC_JPV] = c14.y; t.sc[SC_UPC] = c15.x; t.sc[SC_VA] = c15.y;
+  t.sc[SC_PPC] = c16.x; t.sc[SC_TJV] = c16.y; t.sc[SC_TQ0] = c17.x; t.sc[SC_TQ1] = c17.y; t.sc[SC_TQ2] = c18.x; t.sc[SC_RB] = c18.y;
 }
 __device__ __forceinline__ void trec_load_node(double2 const* q, int n, double nq[4]) {
   double2 const a = q[2 * n], b = q[2 * n + 1];
@@ -432,7 +432,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
   }
   int const n_recs = (int)hdr.x;
   // Record staging: one bulk asynchronous copy (global -> shared) per run of the schedule -- a run is a number of
-  // consecutive elements' records (336 B each, contiguous in global memory) that go to consecutive slots; the copies
+  // consecutive elements' records (304 B each, contiguous in global memory) that go to consecutive slots; the copies
   // report their bytes to an mbarrier that the whole block then waits on.
   uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
   if (tid == 0) {
@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
       trec_load_node(q, (int)((ent >> 10) & 3u), nq);
       trec_load_node(q, (int)((ent >> 8) & 3u), mq);
       TRegs t;
-      trec_load_common(q, t, false);
+      trec_load_common(q, t);
       trec_pair_add<TRANSPOSE>(nq, mq, t.s, t.G, t.sc, acc1, acc2);
     }
   } else if (type == 1) {
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(PATCH_THREADS, PATCH_MINB) patch_pair_kernel(c
       double nq[4];
       trec_load_node(q, (int)((ent >> 10) & 3u), nq);
       TRegs t;
-      trec_load_common(q, t, true);
+      trec_load_common(q, t);
       trec_diag_add<TRANSPOSE>(nq, t.s, t.G, t.sc, acc1, r4);
     }
   }

@@ -1,6 +1,6 @@
 // tangent_record.cuh -- the per-element tangent record of the Jacobian pass and the block contributions built from it.
 //
-// Stage A (elem_record_kernel) evaluates an element once and leaves a 42-double record; stage B (patch_pair_kernel)
+// Stage A (elem_record_kernel) evaluates an element once and leaves a 38-double record; stage B (patch_pair_kernel)
 // stages the records of a patch in shared memory and every work item adds, per contributing element, either
 //   * a PAIR   : the two 4x4 blocks K[(n,.),(m,.)] and K[(m,.),(n,.)] of an edge (n != m), or
 //   * a DIAGONAL: the block K[(n,.),(n,.)] and the node's four residual entries,
@@ -18,20 +18,22 @@
 // Reference: Displacement/Pressure::scatter_primal / scatter_adjoint (goal_displacement.cpp:177-214,
 // goal_pressure.cpp:166-203) receive exactly these blocks from the FAD chain.
 //
-// Record layout (doubles; 21 chunks of 16 B -- an odd number, so consecutive staged records start in different
+// Record layout (38 doubles = 19 chunks of 16 B -- an odd number, so consecutive staged records start in different
 // shared-memory bank groups):
 //   [4n .. 4n+2] w_n   [4n+3] tqw_n            n = 0..3       chunks 0-7
-//   [16..21] s  (00 11 22 01 02 12)                           chunks 8-10
-//   [22..27] G                                                chunks 11-13
-//   [28..37] vb a1 Jpv upc va ppc tjv tq0 tq1 tq2             chunks 14-18   (a0, b1, b0 follow from vb, a1, Jpv)
-//   [38] rb  [39..41] unused                                  chunk 19 (residual rows of the diagonal items), chunk 20
+//   [16..20] s00 s11 s01 s02 s12  (s is deviatoric: s22 = -s00 - s11 is not stored)
+//   [21..26] G  (00 11 22 01 02 12)
+//   [27..36] vb a1 Jpv upc va ppc tjv tq0 tq1 tq2             (a0, b1, b0 follow from vb, a1, Jpv)
+//   [37] rb                                                   (residual rows of the diagonal items)
+// chunks 8-18 are the same for every block of the element ("common"): 11 loads, plus 2 per node.
 #pragma once
 
 #include "element_math.cuh"
 
 namespace gx {
 
-constexpr int TREC = 42;  // doubles per record; 336 B = 21 x 16 B
+constexpr int TREC = 38;  // doubles per record; 304 B = 19 x 16 B
+constexpr int TREC_S = 16, TREC_G = 21, TREC_SC = 27;  // offsets of s (5 stored), G (6), the 11 scalars
 
 // Core -> record
 template <class S> GX_HD void pack_trec(Core<S> const& c, S rec[TREC]) {
@@ -40,25 +42,30 @@ template <class S> GX_HD void pack_trec(Core<S> const& c, S rec[TREC]) {
     rec[4 * n + 3] = c.tjv * dot3(c.q, c.w[n]);
   }
   S const* s = c.s;
-  for (int k = 0; k < 6; ++k) rec[16 + k] = s[k];
+  rec[16] = s[0]; rec[17] = s[1]; rec[18] = s[3]; rec[19] = s[4]; rec[20] = s[5];
   S const k2 = c.gNs * c.rc1, k1 = c.gNs * c.tb3 + c.vgr * c.rc1, k0 = c.vgr * c.tb3 + c.gwv;
-  rec[22] = k2 * (s[0] * s[0] + s[3] * s[3] + s[4] * s[4]) + k1 * s[0] + k0;
-  rec[23] = k2 * (s[3] * s[3] + s[1] * s[1] + s[5] * s[5]) + k1 * s[1] + k0;
-  rec[24] = k2 * (s[4] * s[4] + s[5] * s[5] + s[2] * s[2]) + k1 * s[2] + k0;
-  rec[25] = k2 * (s[0] * s[3] + s[3] * s[1] + s[4] * s[5]) + k1 * s[3];
-  rec[26] = k2 * (s[0] * s[4] + s[3] * s[5] + s[4] * s[2]) + k1 * s[4];
-  rec[27] = k2 * (s[3] * s[4] + s[1] * s[5] + s[5] * s[2]) + k1 * s[5];
-  rec[28] = c.vb;
-  rec[29] = c.A1v * c.tb3;  // a1
-  rec[30] = c.Jpv;
-  rec[31] = c.upc; rec[32] = c.va; rec[33] = c.ppc; rec[34] = c.tjv;
-  rec[35] = c.tjv * c.q[0]; rec[36] = c.tjv * c.q[1]; rec[37] = c.tjv * c.q[2];
-  rec[38] = c.rb; rec[39] = S(0.0); rec[40] = S(0.0); rec[41] = S(0.0);
+  rec[21] = k2 * (s[0] * s[0] + s[3] * s[3] + s[4] * s[4]) + k1 * s[0] + k0;
+  rec[22] = k2 * (s[3] * s[3] + s[1] * s[1] + s[5] * s[5]) + k1 * s[1] + k0;
+  rec[23] = k2 * (s[4] * s[4] + s[5] * s[5] + s[2] * s[2]) + k1 * s[2] + k0;
+  rec[24] = k2 * (s[0] * s[3] + s[3] * s[1] + s[4] * s[5]) + k1 * s[3];
+  rec[25] = k2 * (s[0] * s[4] + s[3] * s[5] + s[4] * s[2]) + k1 * s[4];
+  rec[26] = k2 * (s[3] * s[4] + s[1] * s[5] + s[5] * s[2]) + k1 * s[5];
+  rec[27] = c.vb;
+  rec[28] = c.A1v * c.tb3;  // a1
+  rec[29] = c.Jpv;
+  rec[30] = c.upc; rec[31] = c.va; rec[32] = c.ppc; rec[33] = c.tjv;
+  rec[34] = c.tjv * c.q[0]; rec[35] = c.tjv * c.q[1]; rec[36] = c.tjv * c.q[2];
+  rec[37] = c.rb;
+}
+// the stored five entries of s -> symmetric storage (00 11 22 01 02 12)
+GX_HD void trec_s6(double const* s5, double s[6]) {
+  s[0] = s5[0]; s[1] = s5[1]; s[2] = -(s5[0] + s5[1]); s[3] = s5[2]; s[4] = s5[3]; s[5] = s5[4];
 }
 
 // One node in its two roles.  Row role: w, sw = s w, cq = va + tqw.  Column role: w, aw = a0 w, B, g, tqw.
-// The functions below take the pieces of a record by pointer -- nq = rec + 4 n (node n), s = rec + 16, G = rec + 22,
-// sc = rec + 28 (the 11 scalars) -- so that the device code can hand them registers it filled with 128-bit shared loads.
+// The functions below take the pieces of a record by pointer -- nq = rec + 4 n (node n), s[6] (trec_s6 of rec + 16),
+// G = rec + 21, sc = rec + 27 (the 11 scalars) -- so that the device code can hand them registers it filled with
+// 128-bit shared loads.
 struct TNode {
   double w[3], tqw, sw[3], g[3];
 };
@@ -141,11 +148,15 @@ GX_HD void trec_diag_add(double const* nq, double const* s, double const* G, dou
 // host-side convenience (tests/hostcheck): the same two calls on a whole record
 template <bool TRANSPOSE>
 GX_HD void trec_pair_add_rec(double const* rec, int n, int m, double acc1[16], double acc2[16]) {
-  trec_pair_add<TRANSPOSE>(rec + 4 * n, rec + 4 * m, rec + 16, rec + 22, rec + 28, acc1, acc2);
+  double s[6];
+  trec_s6(rec + TREC_S, s);
+  trec_pair_add<TRANSPOSE>(rec + 4 * n, rec + 4 * m, s, rec + TREC_G, rec + TREC_SC, acc1, acc2);
 }
 template <bool TRANSPOSE>
 GX_HD void trec_diag_add_rec(double const* rec, int n, double acc[16], double r4[4]) {
-  trec_diag_add<TRANSPOSE>(rec + 4 * n, rec + 16, rec + 22, rec + 28, acc, r4);
+  double s[6];
+  trec_s6(rec + TREC_S, s);
+  trec_diag_add<TRANSPOSE>(rec + 4 * n, s, rec + TREC_G, rec + TREC_SC, acc, r4);
 }
 
 }  // namespace gx
