@@ -42,12 +42,11 @@ __global__ void pack_z_kernel(ZRec* z, double const* zu, double const* zp, doubl
 
 // Mechanics::make_states (goal_mechanics.cpp:87-95) with the identity initialisation of goal_states.cpp:87-128:
 // sigma = 0, eqps = eqps_old = 0, Fp = Fp_old = I (J2), cached Cp^{-1} = I
-__global__ void init_states_kernel(double* state_in, double* fp_old, double* state_out, int ne, int j2) {
+__global__ void init_states_kernel(double* state_in, double* state_out, int ne, int j2) {
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
   double const one = j2 ? 1.0 : 0.0;
-  for (int k = 0; k < STATE_IN; ++k) state_in[(int64_t)STATE_IN * e + k] = k < 3 ? one : 0.0;
-  for (int k = 0; k < 9; ++k) fp_old[(int64_t)9 * e + k] = (k % 4 == 0) ? one : 0.0;
+  for (int k = 0; k < STATE_IN; ++k) state_in[(int64_t)STATE_IN * e + k] = (k < 9 && k % 4 == 0) ? one : 0.0;
   for (int k = 0; k < STATE_OUT; ++k) state_out[(int64_t)STATE_OUT * e + k] = (k >= SO_FP && k < SO_FP + 9 && (k - SO_FP) % 4 == 0) ? one : 0.0;
 }
 
@@ -66,18 +65,12 @@ __global__ void record_to_field_kernel(double* field, double const* rec, int str
   int const k = (int)(i % ncomp);
   field[i] = rec[e * stride + off + k];
 }
-// States::update (src/goal_states.cpp:130-141): Fp_old <- Fp, eqps_old <- eqps; refresh the cached Cp^{-1}
-__global__ void update_states_kernel(double* sin, double* fp_old, double const* sout, int ne, int copy) {
+// States::update (src/goal_states.cpp:130-141): Fp_old <- Fp, eqps_old <- eqps
+__global__ void update_states_kernel(double* sin, double const* sout, int ne) {
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= ne) return;
-  double Fp[9], Cp[6];
-  for (int k = 0; k < 9; ++k) {
-    if (copy) fp_old[9 * (int64_t)e + k] = sout[(int64_t)STATE_OUT * e + SO_FP + k];
-    Fp[k] = fp_old[9 * (int64_t)e + k];
-  }
-  cp_inverse(Fp, Cp);
-  for (int k = 0; k < 6; ++k) sin[(int64_t)STATE_IN * e + k] = Cp[k];
-  if (copy) sin[(int64_t)STATE_IN * e + 6] = sout[(int64_t)STATE_OUT * e + SO_EQPS];
+  for (int k = 0; k < 9; ++k) sin[(int64_t)STATE_IN * e + k] = sout[(int64_t)STATE_OUT * e + SO_FP + k];
+  sin[(int64_t)STATE_IN * e + 9] = sout[(int64_t)STATE_OUT * e + SO_EQPS];
 }
 
 // compute_error (src/goal_error.cpp:7-35): |sum_d u_err_d(xi_c) + p_err(xi_c)|; err4 = [Nn][4] (u0,u1,u2,p)
@@ -354,7 +347,7 @@ static cudaError_t launch_model(gx_ctx* ctx, KParams& P, int pass, bool save) {
 static void fill_params(gx_ctx* ctx, KParams& P) {
   P.nodes = ctx->d_nodes; P.z = ctx->d_z; P.conn = ctx->d_conn; P.bpos = ctx->d_bpos; P.eset = ctx->d_eset;
   P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
-  P.state_in = ctx->d_state_in; P.fp_old = ctx->d_fp_old; P.state_out = ctx->d_state_out;
+  P.state_in = ctx->d_state_in; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
   P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk; P.pf_dist = (int)ctx->opt_prefetch;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
@@ -551,8 +544,8 @@ static bool state_loc(gx_ctx* ctx, const char* name, StateLoc& L) {
   if (ctx->model != GX_MODEL_J2) return false;  // only J2 registers eqps / Fp (goal_mechanics.cpp:90-93)
   if (n == "Fp") { L = {ctx->d_state_out, STATE_OUT, SO_FP, 9}; return true; }
   if (n == "eqps") { L = {ctx->d_state_out, STATE_OUT, SO_EQPS, 1}; return true; }
-  if (n == "Fp_old") { L = {ctx->d_fp_old, 9, 0, 9}; return true; }
-  if (n == "eqps_old") { L = {ctx->d_state_in, STATE_IN, 6, 1}; return true; }
+  if (n == "Fp_old") { L = {ctx->d_state_in, STATE_IN, 0, 9}; return true; }
+  if (n == "eqps_old") { L = {ctx->d_state_in, STATE_IN, 9, 1}; return true; }
   return false;
 }
 
@@ -560,7 +553,7 @@ static void free_device(gx_ctx* ctx) {
   if (ctx->device < 0) return;
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_diag_pos,
-                  ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
+                  ctx->d_state_in, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
                   ctx->d_plastic, ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
   for (void* p : ptrs) if (p) cudaFree(p);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -657,9 +650,8 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     // ---- states: Mechanics::make_states (goal_mechanics.cpp:87-95), identity init (goal_states.cpp:87-128)
     {
       GX_CUDA(cudaMalloc(&ctx->d_state_in, sizeof(double) * (size_t)STATE_IN * ne));
-      GX_CUDA(cudaMalloc(&ctx->d_fp_old, sizeof(double) * (size_t)9 * ne));
       GX_CUDA(cudaMalloc(&ctx->d_state_out, sizeof(double) * (size_t)STATE_OUT * ne));
-      init_states_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ne, ctx->model == GX_MODEL_J2);
+      init_states_kernel<<<(ne + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_state_out, ne, ctx->model == GX_MODEL_J2);
       GX_CUDA(cudaGetLastError());
     }
     // ---- linear objects (SolInfo ghost R / dRdu, src/goal_sol_info.cpp:6-22)
@@ -820,10 +812,6 @@ int gx_set_state(gx_ctx* ctx, const char* name, const double* in) {
   GX_CUDA(cudaMemcpyAsync(ctx->d_stage, in, sizeof(double) * (size_t)tot, cudaMemcpyHostToDevice, ctx->stream));
   field_to_record_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(L.rec, L.stride, L.off, ctx->d_stage, ctx->ne, L.ncomp);
   GX_CUDA(cudaGetLastError());
-  if (L.rec == ctx->d_fp_old) {  // Fp_old changed: refresh the cached Cp^{-1}
-    update_states_kernel<<<(ctx->ne + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->ne, 0);
-    GX_CUDA(cudaGetLastError());
-  }
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;
 }
@@ -833,7 +821,7 @@ int gx_update_states(gx_ctx* ctx) {
   if (host_only(ctx)) return GX_ERR_CUDA;
   if (ctx->model != GX_MODEL_J2) return GX_OK;  // only J2 registers old states (goal_mechanics.cpp:90-93)
   GX_CUDA(cudaSetDevice(ctx->device));
-  update_states_kernel<<<(ctx->ne + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_fp_old, ctx->d_state_out, ctx->ne, 1);
+  update_states_kernel<<<(ctx->ne + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_state_in, ctx->d_state_out, ctx->ne);
   GX_CUDA(cudaGetLastError());
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
   return GX_OK;

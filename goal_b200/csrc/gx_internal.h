@@ -117,11 +117,9 @@ struct gx_ctx {
   uint8_t* d_diag_pos = nullptr;   // position of block (a,a) in node a's block row
   uint32_t* d_patch_sched = nullptr;
   // history state, one record per element (user order):
-  //   in    : Cp^{-1}[6] (of Fp_old, cached), eqps_old, pad   (64 B)  read by every incidence of the element
-  //   fp_old: Fp_old[9]                                       (72 B)  read only when a plastic element saves Fp
-  //   out   : sigma[9], Fp[9], eqps, pad                      (160 B)
+  //   in  : Fp_old[9], eqps_old                              (80 B)  read once per element and pass
+  //   out : sigma[9], eqps, Fp[9], pad                       (160 B)
   double* d_state_in = nullptr;
-  double* d_fp_old = nullptr;
   double* d_state_out = nullptr;
   double* d_elemrec = nullptr;  // [ne][ELEM_REC] tangent records of the two-kernel Jacobian pass (lazy)
   double* d_R = nullptr;
@@ -185,7 +183,7 @@ struct HostPack {
   std::vector<uint4> bpos;   // user element order
   std::vector<uint8_t> eset;
 };
-constexpr int STATE_IN = 8;    // doubles per element
+constexpr int STATE_IN = 10;   // doubles per element: Fp_old[9], eqps_old
 constexpr int STATE_OUT = 20;   // sigma[9] | eqps | Fp[9] | pad: 16 B pairs 0-4 are always written, pairs 5-9 only on the plastic branch
 constexpr int SO_SIGMA = 0, SO_EQPS = 9, SO_FP = 10;
 void pack_host(gx_ctx const* c, HostPack& h);

@@ -11,8 +11,8 @@
 //   bpos      uint4[Ne]    element -> nonzero scatter map, 16 x uint8 block positions
 //   adj       int2[4 Ne]   node -> (element, local node) incidences + the 4 block positions that
 //                          incidence writes, grouped by node (adj_off[Nn+1]); the row-owner work list
-//   state_in  double[Ne][8]   Cp^{-1}[6] of Fp_old (cached), eqps_old, pad   64 B record (4 LDG.128)
-//   fp_old    double[Ne][9]   read only by the one incidence that saves a plastic element's Fp
+//   state_in  double[Ne][10]  Fp_old[9], eqps_old                             80 B record (5 LDG.128); Cp^{-1} is
+//                             formed in registers (cp_inverse): the old state is read once per element and pass
 //   state_out double[Ne][20]  sigma[9], eqps, Fp[9], pad                     160 B record
 //   R         double[4 Nn] ghost layout;   values  double[nnz]  CRS order of gx_graph
 //
@@ -50,7 +50,6 @@ struct KParams {
   uint32_t const* adj_off;
   int2 const* adj;
   double const* state_in;
-  double const* fp_old;
   double* state_out;
   double* R;
   double* values;
@@ -133,11 +132,12 @@ GX_HD int load_element(KParams const& P, int e, bool want_state, int nd[4], int 
   for (int n = 0; n < 4; ++n) load_node(P.nodes, nd[n], x[n], u[n], p[n], blk0[n], nblk[n]);
   mat = &P.mat[P.eset ? P.eset[e] : 0];
   double Cp[6], eqps_old = 0.0;
-  if (MODEL == MODEL_J2) {
-    double const* q = P.state_in + (int64_t)STATE_IN * e;
-    double pad;
-    ldg256(q, Cp[0], Cp[1], Cp[2], Cp[3]);
-    ldg256(q + 4, Cp[4], Cp[5], eqps_old, pad);
+  if (MODEL == MODEL_J2) {  // Fp_old, eqps_old: one 80 B record (16 B aligned); Cp^{-1} = Fp^{-1} Fp^{-T} (goal_J2.cpp:84-87)
+    double2 const* q = reinterpret_cast<double2 const*>(P.state_in + (int64_t)STATE_IN * e);
+    double2 const a = ldg(q), b = ldg(q + 1), c2 = ldg(q + 2), d = ldg(q + 3), f = ldg(q + 4);
+    double const Fp[9] = {a.x, a.y, b.x, b.y, c2.x, c2.y, d.x, d.y, f.x};
+    eqps_old = f.y;
+    cp_inverse(Fp, Cp);
   }
   eqps_new = 0.0;
   return element_core<MODEL>(x, u, p, *mat, Cp, eqps_old, want_state, sig, eqps_new, c);
@@ -167,7 +167,7 @@ GX_HD int load_and_update(KParams const& P, int e, bool write_state, int nd[4], 
 // Fp of a plastic element, done after the Jacobian work; elastic elements leave Fp untouched (goal_J2.cpp:135-136)
 GX_HD void save_plastic_Fp(KParams const& P, int e, double const dN[6]) {
   double Fpo[9], Fpn[9];
-  double const* src = P.fp_old + 9 * (int64_t)e;
+  double const* src = P.state_in + (int64_t)STATE_IN * e;
 #pragma unroll
   for (int k = 0; k < 9; ++k) Fpo[k] = ldg(src + k);
   plastic_update(dN, Fpo, Fpn);
@@ -264,26 +264,24 @@ constexpr int ELEM_REC = TREC;  // doubles; 304 B = 19 x 16 B: an odd number of 
 
 // Warp-cooperative Fp update of 32 consecutive elements e0 .. e0+nrec-1 (lane = element), plastic branch only:
 // Fp = exp(dgam N) Fp_old (goal_J2.cpp:128-131); on the elastic branch the reference leaves Fp untouched (:135-136).
-// Per-thread accesses of the 72 B Fp_old / Fp records touch 32 different 128 B lines per instruction (9 + 9
-// instructions); staged through shared memory the warp reads its 2.3 KB of Fp_old with 5 coalesced 128-bit loads and
-// writes the Fp halves of its state records (pairs 5-9, 80 B each) with 5 coalesced 128-bit stores.
+// Per-thread stores of the 72 B Fp records touch 32 different 128 B lines per instruction (9 instructions); staged
+// through shared memory the warp re-reads its 2.5 KB of old-state records (just gathered by its threads: L1 / L2
+// hits) with 5 coalesced 128-bit loads and writes the Fp halves of its state records (pairs 5-9, 80 B each) with 5
+// coalesced 128-bit stores.
 // buf: >= WSAVE_DOUBLES doubles of shared memory that belong to the warp and are free (callers __syncwarp first).
-constexpr int WSAVE_ST = 288, WSAVE_LD = 11;  // Fp_old block at [0, 288), Fp rows of 11 doubles (odd: conflict-free) behind it
+constexpr int WSAVE_ST = 32 * STATE_IN, WSAVE_LD = 11;  // old-state block at [0, 320), Fp rows of 11 doubles (odd: conflict-free) behind it
 constexpr int WSAVE_DOUBLES = WSAVE_ST + 32 * WSAVE_LD;
 __device__ __forceinline__ void warp_save_Fp(KParams const& P, int e0, int nrec, int lane, int plastic, double const dN[6], double* buf) {
   unsigned const pmask = __ballot_sync(0xffffffffu, plastic != 0);
   if (!pmask) return;
-  double const* src = P.fp_old + 9 * (int64_t)e0;  // 72 B * e0, e0 a multiple of 32: 16 B aligned
-  int const tot = 9 * nrec;
-  for (int g = 2 * lane; g < tot; g += 64) {
-    if (g + 1 < tot) { double2 const v = __ldg(reinterpret_cast<double2 const*>(src + g)); buf[g] = v.x; buf[g + 1] = v.y; }
-    else buf[g] = __ldg(src + g);
-  }
+  double const* src = P.state_in + (int64_t)STATE_IN * e0;  // 80 B records: 16 B aligned
+  int const tot = STATE_IN * nrec;                           // even
+  for (int g = 2 * lane; g < tot; g += 64) { double2 const v = __ldg(reinterpret_cast<double2 const*>(src + g)); buf[g] = v.x; buf[g + 1] = v.y; }
   __syncwarp();
   if (plastic) {
     double Fpo[9], Fpn[9];
 #pragma unroll
-    for (int k = 0; k < 9; ++k) Fpo[k] = buf[9 * lane + k];
+    for (int k = 0; k < 9; ++k) Fpo[k] = buf[STATE_IN * lane + k];
     plastic_update(dN, Fpo, Fpn);
     double* st = buf + WSAVE_ST + lane * WSAVE_LD;
 #pragma unroll
@@ -313,10 +311,6 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
   double* mine = &srec[wib][lane * (ELEM_REC + 1)];
   int plastic = 0;
   double dN[6];
-  if (SAVE && MODEL == MODEL_J2 && nrec > 0 && lane < 19) {  // the warp's Fp_old block is read last: have it in L2 by then
-    char const* f = reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)e0) + 128 * lane;
-    if (f < reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)(e0 + nrec))) asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
-  }
   if (e < ne) {
     int nd[4], b0[4], nb[4];
     Material const* matp;
@@ -580,10 +574,6 @@ __global__ void __launch_bounds__(128, 4) elem_residual_kernel(const __grid_cons
   double* buf = sbuf[wib];
   int plastic = 0;
   double dN[6];
-  if (SAVE && MODEL == MODEL_J2 && nrec > 0 && lane < 19) {
-    char const* f = reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)e0) + 128 * lane;
-    if (f < reinterpret_cast<char const*>(P.fp_old + 9 * (int64_t)(e0 + nrec))) asm volatile("prefetch.global.L2 [%0];" ::"l"(f));
-  }
   if (e < ne) {
     int nd[4], b0[4], nb[4];
     Material const* matp;

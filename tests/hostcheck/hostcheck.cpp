@@ -158,13 +158,12 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   }
   std::vector<gx::ZRec> z(nn);
   if (z5) for (int n = 0; n < nn; ++n) { for (int j = 0; j < 3; ++j) z[n].zu[j] = z5[5 * (size_t)n + j]; z[n].zp = z5[5 * (size_t)n + 3]; z[n].zpc = z5[5 * (size_t)n + 4]; }
-  std::vector<double> sin((size_t)gx::STATE_IN * ne, 0.0), sout((size_t)gx::STATE_OUT * ne, 0.0), fpo((size_t)9 * ne, 0.0);
+  std::vector<double> sin((size_t)gx::STATE_IN * ne, 0.0), sout((size_t)gx::STATE_OUT * ne, 0.0);
   for (int e = 0; e < ne; ++e) {
     for (int k = 0; k < 9; ++k) sout[(size_t)gx::STATE_OUT * e + k] = sigma[9 * (size_t)e + k];
     if (model == 1) {
-      sout[(size_t)gx::STATE_OUT * e + gx::SO_EQPS] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 6] = eqps_old[e];
-      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + gx::SO_FP + k] = Fp[9 * (size_t)e + k]; fpo[(size_t)9 * e + k] = Fp_old[9 * (size_t)e + k]; }
-      gx::cp_inverse(&fpo[(size_t)9 * e], &sin[(size_t)gx::STATE_IN * e]);
+      sout[(size_t)gx::STATE_OUT * e + gx::SO_EQPS] = eqps[e]; sin[(size_t)gx::STATE_IN * e + 9] = eqps_old[e];
+      for (int k = 0; k < 9; ++k) { sout[(size_t)gx::STATE_OUT * e + gx::SO_FP + k] = Fp[9 * (size_t)e + k]; sin[(size_t)gx::STATE_IN * e + k] = Fp_old[9 * (size_t)e + k]; }
     }
   }
   int err[2] = {0, 0};
@@ -172,7 +171,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   gx::KParams P;
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
   P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data();
-  P.state_in = sin.data(); P.fp_old = fpo.data(); P.state_out = sout.data();
+  P.state_in = sin.data(); P.state_out = sout.data();
   P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk; P.pf_dist = 0;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
   int64_t npl = 0;
