@@ -280,7 +280,7 @@ bool build_patch_schedule(gx_ctx* c) {
   // Long contribution lists are cut into items of at most `split` contributions, as evenly as possible.  A thread
   // block lives as long as its longest item, so the cut follows the length of the ordinary items (an edge of a Kuhn
   // mesh has 4 or 6 elements) rather than the capacity of an item.
-  int split = 6, split_diag = 8, max_run = 16;  // records per bulk copy at most
+  int split = 6, split_diag = 6, max_run = 32;  // records per bulk copy at most
   if (char const* e = getenv("GX_SCHED_MAXRUN")) max_run = std::max(1, std::min(64, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT")) split = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));
   if (char const* e = getenv("GX_SCHED_SPLIT_DIAG")) split_diag = std::max(1, std::min(PATCH_ITEM_LEN, atoi(e)));

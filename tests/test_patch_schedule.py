@@ -40,7 +40,7 @@ def _check(co, cn):
         staged = {}
         for e0, sl in runs:
             s0, ln = int(sl) & 0xff, int(sl) >> 8
-            assert 1 <= ln <= 16 and s0 + ln <= RECS
+            assert 1 <= ln <= 32 and s0 + ln <= RECS
             for j in range(ln):
                 assert s0 + j not in staged
                 staged[s0 + j] = int(e0) + j
