@@ -455,6 +455,7 @@ def run_b200(args):
         traffic = json.load(open(tp)).get(f"{args.model}_bytes_per_element")
         traffic = None if traffic is None else traffic * ne_local
     fp64_tflops, fp64_mhz = fp64
+    exec_flop = json.load(open(tp)).get(f"{args.model}_executed_fp64_flop_per_element") if os.path.exists(tp) else None
     hbm_roof = hbm_peak * 1e9 / B_ALG[args.model] / 1e6            # Melem/s
     fp64_roof = fp64_tflops * 1e12 / F_ALG[args.model] / 1e6       # Melem/s
     line = {
@@ -472,9 +473,10 @@ def run_b200(args):
                                   "last assembly kernel" if overlap else "after the pass, on the compute stream") if world > 1 else None,
                      "algorithmic_bytes_per_element": B_ALG[args.model],
                      "fp64_peak_tflops": fp64_tflops, "fp64_peak_source": "measured in this run (gx_measure_fp64_peak: register-only DFMA chains)",
-                     "fp64_peak_sm_mhz": fp64_mhz, "counted_flop_per_element": F_ALG[args.model],
-                     "executed_fp64_flop_per_element": json.load(open(tp)).get(f"{args.model}_executed_fp64_flop_per_element") if os.path.exists(tp) else None,
+                     "counted_flop_per_element": F_ALG[args.model],
+                     "executed_fp64_flop_per_element": exec_flop,
                      "hbm_roof_Melem_s": hbm_roof, "fp64_roof_Melem_s": fp64_roof,
+                     "fp64_roof_executed_Melem_s": (fp64_tflops * 1e12 / exec_flop / 1e6) if exec_flop else None,
                      "frac_of_binding_roof": value / world / min(hbm_roof, fp64_roof)},
         "clocks": clk, "gpu_launches": launches, "e2e": e2e, "checks": checks, "passes": passes, "sizes": sizes,
         "setup_s": {"total": setup_s, "gx_create": create_s, "patch_schedule_and_upload": max(0.0, first_pass_s - ms * 1e-3 / args.steps),

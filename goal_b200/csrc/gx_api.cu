@@ -445,9 +445,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   if (!ctx->struct_done) { ctx->err = "partitioned context: finish the structure exchange (gx_comm_init or gx_struct_*) first"; return GX_ERR_ARG; }
   GX_CUDA(cudaSetDevice(ctx->device));
   ctx->launches = 0;
-  int const zero2[2] = {0, 0};
-  GX_CUDA(cudaMemcpyAsync(ctx->d_err, zero2, sizeof zero2, cudaMemcpyHostToDevice, ctx->stream));
-  GX_CUDA(cudaMemsetAsync(ctx->d_plastic, 0, sizeof(unsigned long long), ctx->stream));
+  GX_CUDA(cudaMemsetAsync(ctx->d_err, 0, 16, ctx->stream));
   GX_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
   // Jacobian pass: patch schedule (default) unless the coloured fallback is asked for or the mesh does not fit
   bool patch_gather = with_values && ctx->opt_kernel != 1;
@@ -493,11 +491,11 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
                                    : launch_model<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   if (le != cudaSuccess) { if (ctx->err.empty() || le != cudaErrorUnknown) ctx->err = std::string("kernel launch: ") + cudaGetErrorString(le); return le == cudaErrorUnknown ? GX_ERR_NCCL : GX_ERR_CUDA; }
   GX_CUDA(cudaEventRecord(ctx->ev[2], ctx->stream));
-  int herr[2];
-  unsigned long long hpl = 0;
-  GX_CUDA(cudaMemcpyAsync(herr, ctx->d_err, sizeof herr, cudaMemcpyDeviceToHost, ctx->stream));
-  GX_CUDA(cudaMemcpyAsync(&hpl, ctx->d_plastic, sizeof hpl, cudaMemcpyDeviceToHost, ctx->stream));
+  GX_CUDA(cudaMemcpyAsync(ctx->h_status, ctx->d_err, 16, cudaMemcpyDeviceToHost, ctx->stream));
   GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  int const herr[2] = {ctx->h_status[0], ctx->h_status[1]};
+  unsigned long long hpl = 0;
+  memcpy(&hpl, ctx->h_status + 2, sizeof hpl);
   float t0 = 0, t1 = 0;
   GX_CUDA(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
   GX_CUDA(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
@@ -554,8 +552,9 @@ static void free_device(gx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_diag_pos,
                   ctx->d_state_in, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
-                  ctx->d_plastic, ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
+                  ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->h_status) cudaFreeHost(ctx->h_status);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : {ctx->ev_iface, ctx->ev_b2, ctx->ev_comm}) if (e) cudaEventDestroy(e);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -661,8 +660,11 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaMemset(ctx->d_values, 0, sizeof(double) * (size_t)std::max<int64_t>(ctx->nnz, 1)));
     ctx->stage_len = std::max<int64_t>(8 * (int64_t)nn, 9 * (int64_t)ne) + 64;
     GX_CUDA(cudaMalloc(&ctx->d_stage, sizeof(double) * (size_t)ctx->stage_len));
-    GX_CUDA(cudaMalloc(&ctx->d_err, 2 * sizeof(int)));
-    GX_CUDA(cudaMalloc(&ctx->d_plastic, sizeof(unsigned long long)));
+    // {error code, element, plastic count}: one 16-byte status word block, cleared with one memset and read back with
+    // one copy into pinned host memory per pass
+    GX_CUDA(cudaMalloc(&ctx->d_err, 16));
+    ctx->d_plastic = reinterpret_cast<unsigned long long*>(ctx->d_err + 2);
+    GX_CUDA(cudaHostAlloc(&ctx->h_status, 16, cudaHostAllocDefault));
     GX_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * 1024));
     return GX_OK;
   };

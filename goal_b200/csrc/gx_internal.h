@@ -126,8 +126,9 @@ struct gx_ctx {
   double* d_values = nullptr;
   double* d_stage = nullptr;  // staging for host<->device field copies, >= max(4*nn, 10*ne) doubles
   int64_t stage_len = 0;
-  int* d_err = nullptr;                 // {code, element}
-  unsigned long long* d_plastic = nullptr;
+  int* d_err = nullptr;                 // {code, element} + the plastic counter behind it (one 16-byte block)
+  unsigned long long* d_plastic = nullptr;  // = d_err + 2
+  int* h_status = nullptr;              // pinned host copy of that block
   double* d_red = nullptr;              // reduction scratch
   double* d_dMdu = nullptr;             // [4 nn] ghost dMdu of the last gx_functional (lazy)
   bool have_dMdu = false;

@@ -401,6 +401,29 @@ def test_error_codes(cube):
     a.close()
 
 
+def test_j2_return_map_failure():
+    """goal_J2.cpp:119-120: the reference fail()s when the Newton loop on X does not converge -- with linear hardening
+    that only happens on non-finite numbers.  A state that makes the yield function infinite must come back as
+    GX_ERR_J2_RETURN_MAP with the element id, and the failed pass must leave no usable result (the reference aborts)."""
+    import goal_b200
+    co, cn = kuhn_cube(3)
+    f = fields(co, len(cn), strain=0.004)
+    a = goal_b200.Assembler(co, cn, "J2", [MATERIAL])
+    a.set_solution(f["u"], f["p"])
+    bad = f["eqps_old"].copy()
+    bad[17] = -np.inf  # f = |s| - sqrt(2/3)(Y + K eqps_old) = +inf
+    a.set_state("Fp_old", f["Fp_old"]); a.set_state("eqps_old", bad)
+    for call in (lambda: a.jacobian(goal_b200.PRIMAL, save=False), lambda: a.residual(save=False)):
+        with pytest.raises(goal_b200.GxError) as e:
+            call()
+        assert e.value.status == 5 and "element 17" in str(e.value)
+        with pytest.raises(goal_b200.GxError):
+            a.fetch()  # no result after a failed pass
+    a.set_state("eqps_old", f["eqps_old"])
+    a.jacobian(goal_b200.PRIMAL, save=False)  # the context recovers
+    a.close()
+
+
 def _block_ids(nrow):
     """block index of every CRS value (dof rows of node a hold its blocks side by side: entry i*(4 nb) + 4 j + k)."""
     ids = np.empty(16 * int(nrow[-1]), dtype=np.int64)

@@ -114,6 +114,17 @@ def test_j2_barely_yielding_element_matches_fad_oracle(hostcheck):
     assert relerr(K.reshape(16, 16), Ko) < 1e-12
 
 
+def test_j2_return_map_failure_code(hostcheck):
+    """non-finite plastic increment -> ERR_J2_RETURN_MAP (3), the reference's fail("J2: return mapping failed")"""
+    x = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1.0]])
+    u = 1e-3 * np.arange(12.0).reshape(4, 3)
+    p, mat, Fpo = np.zeros(4), np.array(MATERIAL), np.eye(3).reshape(-1).copy()
+    args = lambda eq: (1, dp(x), dp(u), dp(p), dp(mat), dp(Fpo), C.c_double(eq), 1, dp(np.zeros(256)), dp(np.zeros(16)), dp(np.zeros(9)),
+                       C.byref(C.c_double(0)), dp(np.zeros(9)), C.byref(C.c_int(0)), C.byref(C.c_int(0)))
+    assert hostcheck.hc_element(*args(0.0)) == 0
+    assert hostcheck.hc_element(*args(-np.inf)) == 3
+
+
 @pytest.mark.parametrize("model", ["neohookean", "J2"])
 def test_von_mises_derivative_matches_fad_oracle(hostcheck, model):
     """element_von_mises (closed-form d vm / d u) against the oracle's FADT evaluation of AvgVM
