@@ -469,7 +469,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   }
   if ((gather || patch_gather) && !ctx->d_elemrec)
     GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
-  if (patch_gather)  // nodes without elements have no work item
+  if (patch_gather && ctx->has_isolated_nodes)  // nodes without elements have no work item: their R entries are zero
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
   if (!gather && !patch_gather) {
     // SolInfo::zero_R / zero_all (src/goal_sol_info.cpp:51-64).  The owner-computes schedules write every

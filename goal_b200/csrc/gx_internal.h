@@ -80,6 +80,7 @@ struct gx_ctx {
   std::vector<uint32_t> adj_off;  // [nn+1]
   std::vector<int2> adj;          // [4*ne]  x = e*4+n, y = block positions of (a, a_m), m = 0..3, one byte each
   int max_nblk = 0, max_deg = 0;
+  bool has_isolated_nodes = false;  // some node belongs to no element (its R entries must be zeroed by the pass)
   // order in which stage B visits the nodes: Morton (Z-curve) order of the node coordinates, so that the four
   // incidences of an element are processed close in time and its tangent record is fetched from HBM once
   std::vector<int32_t> node_order;

@@ -66,7 +66,11 @@ int build_graph_and_schedule(gx_ctx* c) {
   c->adj_off.resize(nn + 1);
   c->max_deg = 0;
   for (int n = 0; n <= nn; ++n) c->adj_off[n] = (uint32_t)n2e_off[n];
-  for (int n = 0; n < nn; ++n) c->max_deg = std::max<int>(c->max_deg, (int)(n2e_off[n + 1] - n2e_off[n]));
+  c->has_isolated_nodes = false;
+  for (int n = 0; n < nn; ++n) {
+    c->max_deg = std::max<int>(c->max_deg, (int)(n2e_off[n + 1] - n2e_off[n]));
+    if (n2e_off[n + 1] == n2e_off[n]) c->has_isolated_nodes = true;
+  }
 
   // ---- node adjacency, sorted unique per row (two passes: count, fill)
   c->nrow.assign(nn + 1, 0);

@@ -47,3 +47,16 @@ def test_product_does_not_touch_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
                 txt = open(os.path.join(dirpath, fn)).read()
                 assert "goal_oracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_single_part_tpetra_view_is_the_ghost_graph(gxlib):
+    """gx_owned_tpetra_graph on a one-part context: every node is owned, the column map is the row map, and the local
+    CRS arrays are exactly gx_graph's (the ghost layout the reference's get_lids index into, goal_disc.cpp:209-222)."""
+    import numpy as np
+    import goal_b200
+    from goal_b200.synthetic import MATERIAL, kuhn_cube
+    co, cn = kuhn_cube(3)
+    a = goal_b200.Assembler(co, cn, "J2", [MATERIAL], device=-1)
+    tp = a.owned_tpetra_graph()
+    assert tp["n_owned"] == len(co) and np.array_equal(tp["colmap"], np.arange(len(co)))
+    assert np.array_equal(tp["rowptr"], a.rowptr) and np.array_equal(tp["colind"], a.colind)

@@ -401,6 +401,28 @@ def test_error_codes(cube):
     a.close()
 
 
+def test_isolated_nodes_are_accepted():
+    """Nodes that belong to no element (the last node, and one in the middle): no blocks, zero R, and the rest
+    of the operator unchanged -- through the patch schedule, whose diagonal flag must not be set for them."""
+    import goal_b200
+    co, cn = kuhn_cube(4)
+    mid = 40
+    co2 = np.concatenate([co[:mid], [[9.0, 9.0, 9.0]], co[mid:], [[7.0, 7.0, 7.0]]])
+    cn2 = np.where(cn >= mid, cn + 1, cn).astype(np.int32)
+    f = fields(co, len(cn), strain=0.004)
+    f2 = dict(f)
+    f2["u"] = np.concatenate([f["u"][:mid], [[0.0, 0.0, 0.0]], f["u"][mid:], [[0.0, 0.0, 0.0]]])
+    f2["p"] = np.concatenate([f["p"][:mid], [0.0], f["p"][mid:], [0.0]])
+    a, o = _pair(co2, cn2, "J2", f2)
+    for _ in range(2):
+        R, A = a.jacobian(goal_b200.PRIMAL, save=False)
+    Ro, Ao = o.jacobian(goal_b200.PRIMAL, save=False)
+    assert np.array_equal(a.rowptr, o.rowptr) and relerr(R, Ro) < 1e-12 and relerr(A, Ao) < 1e-12
+    assert np.all(R.reshape(-1, 4)[[mid, len(co2) - 1]] == 0.0)
+    assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12
+    a.close()
+
+
 def test_j2_return_map_failure():
     """goal_J2.cpp:119-120: the reference fail()s when the Newton loop on X does not converge -- with linear hardening
     that only happens on non-finite numbers.  A state that makes the yield function infinite must come back as
