@@ -70,6 +70,7 @@ def parse():
     ap.add_argument("--no-passes", action="store_true", help="skip the residual / localisation / adjoint pass timings")
     ap.add_argument("--no-sizes", action="store_true", help="skip the 1M / 10M mesh timings (N = 1 only)")
     ap.add_argument("--no-checks", action="store_true", help="skip the result checks after the timed loop")
+    ap.add_argument("--clock-interval-ms", type=int, default=50, help="nvidia-smi sampling interval during the timed region (0: no sampling)")
     return ap.parse_args()
 
 
@@ -173,13 +174,13 @@ class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.proc = index, None
+    def __init__(self, index, interval_ms=50):
+        self.index, self.proc, self.interval_ms = index, None, interval_ms
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "20", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", str(self.interval_ms), "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -325,9 +326,10 @@ def run_b200(args):
     first_pass_s = time.perf_counter() - ts
     for _ in range(max(0, args.warmup - 1)):
         step()
-    clocks = ClockSampler(local)
-    if rank == 0:
+    clocks = ClockSampler(local, args.clock_interval_ms)
+    if rank == 0 and args.clock_interval_ms > 0:
         clocks.start()
+    t_clk0 = time.perf_counter()
     kern_ms, zero_ms, exch_ms, launches = [], [], [], 0
 
     def step_dev():
@@ -338,7 +340,14 @@ def run_b200(args):
         launches += t["launches"] + (2 * 2 * a.num_peers if world > 1 and not overlap else 0)  # + pack/unpack kernels (R and rows) per peer
 
     ms = timed(step_dev, args.steps)
-    clk = clocks.stop() if rank == 0 else None
+    # nvidia-smi polls at tens of milliseconds and the timed region may be shorter than that: keep the same steps running
+    # (untimed) until the sampler has seen about half a second of this load -- every rank, to keep the load the same
+    if args.clock_interval_ms > 0:
+        while time.perf_counter() - t_clk0 < 0.5:
+            step()
+    clk = clocks.stop() if rank == 0 and args.clock_interval_ms > 0 else None
+    if clk is not None:
+        clk["window"] = "the timed region and the same steps continued, untimed, to 0.5 s of sampling"
     plastic = a.plastic_count()
     ne_total = ne_local * world
     value = ne_total * args.steps / (ms * 1e-3) / 1e6
