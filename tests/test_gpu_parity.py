@@ -401,6 +401,23 @@ def test_error_codes(cube):
     a.close()
 
 
+def test_error_bound_on_more_than_262144_nodes():
+    """sum_contribs (goal_error.cpp:37-56) on a mesh whose node count exceeds what 1023 partial blocks of 256 cover in
+    one sweep (the 1024th partial used to be dropped): bound == numpy sum, indicators == the definition."""
+    import goal_b200
+    co, cn = kuhn_cube(64)
+    assert len(co) == 65 ** 3 > 262144
+    a = goal_b200.Assembler(co, cn, "neohookean", [MATERIAL])
+    rng = np.random.RandomState(3)
+    ue, pe = rng.randn(len(co), 3), rng.randn(len(co))
+    eta, _, bound = a.element_error(ue, pe)
+    want = np.abs(ue.sum(1) + pe).sum()
+    assert abs(bound - want) < 1e-12 * want
+    e4 = np.concatenate([ue, pe[:, None]], 1)
+    assert np.abs(eta - np.abs(0.25 * e4[cn].sum(axis=(1, 2)))).max() < 1e-12 * np.abs(eta).max()
+    a.close()
+
+
 def test_isolated_nodes_are_accepted():
     """Nodes that belong to no element (the last node, and one in the middle): no blocks, zero R, and the rest
     of the operator unchanged -- through the patch schedule, whose diagonal flag must not be set for them."""
