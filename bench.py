@@ -428,7 +428,6 @@ def run_b200(args):
                   "unit": "device ms per pass on one rank's block (CUDA events on the library stream), frac = of the measured HBM roof"}
 
     fp64 = a.measure_fp64_peak() if rank == 0 else None
-    colours = a.num_colors
     a.close()
     if rank != 0:
         if world > 1:
@@ -471,7 +470,7 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": "Melem/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic", "config": workload_config(args, grid),
-        "plastic_fraction": plastic / ne_local, "colours": colours,
+        "plastic_fraction": plastic / ne_local,
         "roofline": {"bound": "hbm" if hbm_roof <= fp64_roof else "fp64", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
                      "kernel": f"gx::elem_record_kernel<{args.model},save> + gx::patch_pair_kernel<primal> "

@@ -320,6 +320,16 @@ __global__ void bforce_kernel(double* R, NodeRec const* nodes, ZRec const* z, in
 }
 
 // ---------------------------------------------------------------------------
+// the coloured schedule on the device, built on first use
+static int ensure_colouring(gx_ctx* ctx) {
+  if (ctx->d_perm) return GX_OK;
+  int const rc = build_colouring(ctx);
+  if (rc) return rc;
+  GX_CUDA(cudaMalloc(&ctx->d_perm, sizeof(int32_t) * (size_t)ctx->ne));
+  GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ctx->ne, cudaMemcpyHostToDevice));
+  return GX_OK;
+}
+
 template <int MODEL, int PASS, bool SAVE>
 static cudaError_t launch_colours(gx_ctx* ctx, KParams& P) {
   int const bs = (int)ctx->opt_block;
@@ -476,6 +486,10 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
     // entry of R and of the CRS values exactly once, so they need no zeroing pass.
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
     if (with_values) GX_CUDA(cudaMemsetAsync(ctx->d_values, 0, sizeof(double) * (size_t)ctx->nnz_x, ctx->stream));
+  }
+  if (!gather && !patch_gather) {  // coloured schedule
+    int const rc = ensure_colouring(ctx);
+    if (rc) return rc;
   }
   GX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   KParams P;
@@ -638,8 +652,6 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
       GX_CUDA(cudaMalloc(&ctx->d_eset, (size_t)ne));
       GX_CUDA(cudaMemcpy(ctx->d_eset, es.data(), (size_t)ne, cudaMemcpyHostToDevice));
     }
-    GX_CUDA(cudaMalloc(&ctx->d_perm, sizeof(int32_t) * (size_t)ne));
-    GX_CUDA(cudaMemcpy(ctx->d_perm, ctx->perm.data(), sizeof(int32_t) * (size_t)ne, cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_adj_off, sizeof(uint32_t) * (size_t)(nn + 1)));
     GX_CUDA(cudaMemcpy(ctx->d_adj_off, ctx->adj_off.data(), sizeof(uint32_t) * (size_t)(nn + 1), cudaMemcpyHostToDevice));
     GX_CUDA(cudaMalloc(&ctx->d_diag_pos, (size_t)nn));
@@ -1179,6 +1191,8 @@ int gx_plastic_count(gx_ctx* ctx, int64_t* n) {
 
 int gx_num_colors(gx_ctx* ctx, int32_t* n) {
   if (!ctx || !n) return GX_ERR_ARG;
+  int const rc = build_colouring(ctx);
+  if (rc) return rc;
   *n = ctx->ncolors;
   return GX_OK;
 }

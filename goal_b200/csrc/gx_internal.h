@@ -85,12 +85,6 @@ struct gx_ctx {
   // incidences of an element are processed close in time and its tangent record is fetched from HBM once
   std::vector<int32_t> node_order;
   std::vector<uint8_t> diag_pos;  // position of block (a,a) in node a's block row
-  // ---- per-block contribution lists (host only, input of the patch schedule; built lazily on the extended graph):
-  //   blk_row[t]  : row node of block t (bit 31 set for the diagonal block)
-  //   bc_off/bc   : per block the contributing (element, row-local node n, column-local node m) = e*16 + n*4 + m,
-  //                 ascending element; phantom blocks have none
-  std::vector<uint32_t> blk_row, bc_off;
-  std::vector<int32_t> bc;
   bool block_lists_built = false;
   // ---- patch schedule of the patch-gather Jacobian pass (kernel = 3), see build_patch_schedule()
   std::vector<uint32_t> patch_sched;                  // flat (flatten_patch_schedule), or empty while ...
@@ -177,6 +171,7 @@ struct gx_ctx {
 namespace gx {
 // host setup (gx_setup.cpp)
 int build_graph_and_schedule(gx_ctx* c);
+int build_colouring(gx_ctx* c);  // lazily: only the coloured fallback needs it
 void materialise_crs(gx_ctx* c);
 // host images of the device arrays, in device (colour-sorted) element order
 struct HostPack {

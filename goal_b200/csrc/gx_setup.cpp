@@ -72,21 +72,20 @@ int build_graph_and_schedule(gx_ctx* c) {
     if (n2e_off[n + 1] == n2e_off[n]) c->has_isolated_nodes = true;
   }
 
-  // ---- node adjacency, sorted unique per row (two passes: count, fill)
+  // ---- node adjacency, sorted unique per row (two passes: count, fill).  Duplicates are recognised with a per-thread
+  //      stamp array (stamp[b] == a: b already seen for row a), so only the unique neighbours are ever sorted.
   c->nrow.assign(nn + 1, 0);
   int bad_row = 0;
 #pragma omp parallel
   {
-    std::vector<int32_t> tmp;
+    std::vector<int32_t> stamp(nn, -1);
 #pragma omp for schedule(dynamic, 4096)
     for (int n = 0; n < nn; ++n) {
-      tmp.clear();
+      int64_t cnt = 0;
       for (int64_t k = n2e_off[n]; k < n2e_off[n + 1]; ++k) {
         int32_t const* en = conn + 4 * (int64_t)n2e[k];
-        tmp.insert(tmp.end(), en, en + 4);
+        for (int q = 0; q < 4; ++q) if (stamp[en[q]] != n) { stamp[en[q]] = n; ++cnt; }
       }
-      std::sort(tmp.begin(), tmp.end());
-      int64_t const cnt = std::unique(tmp.begin(), tmp.end()) - tmp.begin();
       if (cnt > 255) bad_row = 1;
       c->nrow[n + 1] = cnt;
     }
@@ -98,20 +97,18 @@ int build_graph_and_schedule(gx_ctx* c) {
   c->nnz = 16 * c->nrow[nn];
 #pragma omp parallel
   {
-    std::vector<int32_t> tmp;
+    std::vector<int32_t> stamp(nn, -1);
 #pragma omp for schedule(dynamic, 4096)
     for (int n = 0; n < nn; ++n) {
-      tmp.clear();
+      int32_t* dst = c->ncol.data() + c->nrow[n];
+      int cnt = 0;
       for (int64_t k = n2e_off[n]; k < n2e_off[n + 1]; ++k) {
         int32_t const* en = conn + 4 * (int64_t)n2e[k];
-        tmp.insert(tmp.end(), en, en + 4);
+        for (int q = 0; q < 4; ++q) if (stamp[en[q]] != n) { stamp[en[q]] = n; dst[cnt++] = en[q]; }
       }
-      std::sort(tmp.begin(), tmp.end());
-      tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-      std::copy(tmp.begin(), tmp.end(), c->ncol.begin() + c->nrow[n]);
+      std::sort(dst, dst + cnt);
     }
   }
-
   tm.lap("node adjacency");
   // ---- scatter map: position of block (a_n, a_m) in a_n's block row
   c->bpos.resize(16 * (size_t)ne);
@@ -183,6 +180,15 @@ int build_graph_and_schedule(gx_ctx* c) {
   }
 
   tm.lap("diag + Z-curve order");
+  return GX_OK;
+}
+
+// The coloured element schedule (fallback / cross-check path only): built on first use.
+int build_colouring(gx_ctx* c) {
+  if (c->ncolors > 0) return GX_OK;
+  SetupTimer tm;
+  int const nn = c->nn, ne = c->ne;
+  int32_t const* conn = c->conn.data();
   // ---- greedy colouring over node conflicts (elements sharing a node get different colours)
   constexpr int W = 4;  // 256 colours at most
   std::vector<uint64_t> used((size_t)nn * W, 0);
@@ -214,40 +220,10 @@ int build_graph_and_schedule(gx_ctx* c) {
   return GX_OK;
 }
 
-// Contribution lists of the gather-form Jacobian pass, on the extended block rows (nrow_x): local blocks keep their
-// positions, phantom blocks (partitioned contexts) follow and receive nothing locally.
-void build_block_lists(gx_ctx* c) {
-  int const nn = c->nn;
-  std::vector<int64_t> const& nx = c->nrow_x;
-  size_t const nblocks = (size_t)nx[nn];
-  c->blk_row.assign(nblocks, 0u);
-  c->bc_off.assign(nblocks + 1, 0u);
-#pragma omp parallel for schedule(static)
-  for (int a = 0; a < nn; ++a) {
-    for (int64_t t = nx[a]; t < nx[a + 1]; ++t) c->blk_row[t] = (uint32_t)a;
-    if (nx[a + 1] > nx[a]) c->blk_row[nx[a] + c->diag_pos[a]] |= 0x80000000u;  // a node without elements has no blocks
-    for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
-      uint32_t const jp = (uint32_t)c->adj[k].y;
-      for (int m = 0; m < 4; ++m) c->bc_off[nx[a] + ((jp >> (8 * m)) & 0xffu) + 1]++;  // blocks of one row: no races
-    }
-  }
-  for (size_t t = 0; t < nblocks; ++t) c->bc_off[t + 1] += c->bc_off[t];
-  c->bc.assign(c->bc_off[nblocks], 0);
-#pragma omp parallel
-  {
-    std::vector<uint32_t> cur;
-#pragma omp for schedule(static)
-    for (int a = 0; a < nn; ++a) {
-      cur.assign(c->bc_off.begin() + nx[a], c->bc_off.begin() + nx[a + 1]);
-      for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {  // incidences are in ascending element order
-        int const en = c->adj[k].x;                                    // e*4 + n
-        uint32_t const jp = (uint32_t)c->adj[k].y;
-        for (int m = 0; m < 4; ++m) c->bc[cur[(jp >> (8 * m)) & 0xffu]++] = (int32_t)(4 * en + m);
-      }
-    }
-  }
-  c->block_lists_built = true;
-}
+// (The per-block contribution lists the patch schedule needs -- for block (a,b) the (element, n, m) with node n = a, node
+// m = b -- are built node by node inside build_patch_schedule from the node's incidences; a global list would be 16
+// entries per element.)
+void build_block_lists(gx_ctx* c) { c->block_lists_built = true; }
 
 // Patch schedule of the Jacobian pass (stage B, patch_pair_kernel).  A patch is a run of nodes of the Z-curve visiting
 // order whose incident elements (at most PATCH_RECS) are staged once in shared memory by one thread block.  The
@@ -614,6 +590,8 @@ bool build_patch_schedule(gx_ctx* c) {
     // the items of node a: its diagonal block, the edges it owns, its phantom blocks
     struct Blk { int64_t t; int type; int cnt; int parts; };
     std::vector<Blk> blks;
+    std::vector<int> lc_off, lc_cur;
+    std::vector<int32_t> lc;
     for (int s = chunk_rng[ch].first; s < s1; ++s) {
       int const a = order[s];
       if (nx[a + 1] == nx[a]) continue;  // a node without elements: no blocks, no work (its R entries are zeroed by the pass)
@@ -622,13 +600,31 @@ bool build_patch_schedule(gx_ctx* c) {
       blks.clear();
       int nit = 0, nsecs = 0, nd = 0, np = 0;  // items, secondaries, DIAG lanes, PAIR lanes this node needs
       int64_t const nloc = c->nrow[a + 1] - c->nrow[a];  // local blocks; the extended row may continue with phantom ones
-      for (int64_t t = nx[a]; t < nx[a + 1]; ++t) {
-        int const cnt = (int)(c->bc_off[t + 1] - c->bc_off[t]);
+      int const nb_x = (int)(nx[a + 1] - nx[a]);
+      // contributions of this node's blocks, grouped by block position, elements ascending (the incidences are):
+      // lc_off[j] .. lc_off[j+1] index lc[], an entry is e*16 + n*4 + m
+      lc_off.assign(nb_x + 1, 0);
+      for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
+        uint32_t const jp = (uint32_t)c->adj[k].y;
+        for (int m = 0; m < 4; ++m) lc_off[((jp >> (8 * m)) & 0xffu) + 1]++;
+      }
+      for (int j = 0; j < nb_x; ++j) lc_off[j + 1] += lc_off[j];
+      lc.resize(lc_off[nb_x]);
+      lc_cur.assign(lc_off.begin(), lc_off.end() - 1);
+      for (uint32_t k = c->adj_off[a]; k < c->adj_off[a + 1]; ++k) {
+        int const en = c->adj[k].x;  // e*4 + n
+        uint32_t const jp = (uint32_t)c->adj[k].y;
+        for (int m = 0; m < 4; ++m) lc[lc_cur[(jp >> (8 * m)) & 0xffu]++] = (int32_t)(4 * en + m);
+      }
+      int const jdiag = c->diag_pos[a];
+      for (int j = 0; j < nb_x; ++j) {
+        int64_t const t = nx[a] + j;
+        int const cnt = lc_off[j + 1] - lc_off[j];
         int type;
-        if (c->blk_row[t] & 0x80000000u) type = 1;
+        if (j == jdiag) type = 1;
         else if (cnt == 0) type = 0;
         else {
-          int const b = c->ncol[c->nrow[a] + (t - nx[a])];
+          int const b = c->ncol[c->nrow[a] + j];
           (void)nloc;
           if (rank[b] < s) continue;  // the edge belongs to the patch of b
           type = 2;
@@ -651,8 +647,8 @@ bool build_patch_schedule(gx_ctx* c) {
       }
       uint32_t const nblk_a = (uint32_t)(nx[a + 1] - nx[a]);
       for (Blk const& bk : blks) {
-        uint32_t const c0 = c->bc_off[bk.t];
         uint32_t const j1 = (uint32_t)(bk.t - nx[a]);
+        int const c0 = lc_off[j1];
         uint32_t w1 = 0, j2 = 0, nblk_b = 0;
         if (bk.type == 1) w1 = (uint32_t)a;
         if (bk.type == 2) {
@@ -667,7 +663,7 @@ bool build_patch_schedule(gx_ctx* c) {
           Item it{};
           it.n = bk.cnt / bk.parts + (pi < bk.cnt % bk.parts ? 1 : 0);
           for (int q = 0; q < it.n; ++q) {
-            int32_t const ent = c->bc[c0 + first + q];
+            int32_t const ent = lc[c0 + first + q];
             it.ent[q] = (uint16_t)(hfind(ent >> 4) | ((ent & 15) << 8) | 0x8000);  // n*4+m -> bits 8..11
           }
           it.w0 = (uint32_t)nx[a]; it.w1 = w1;

@@ -143,6 +143,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   c.mats[0] = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
   int rc = gx::build_graph_and_schedule(&c);
   if (rc) return rc;
+  if ((rc = gx::build_colouring(&c))) return rc;
   *nnz_out = c.nnz; *ncolors = c.ncolors;
   if (rowptr_out) {
     gx::materialise_crs(&c);
