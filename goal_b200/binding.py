@@ -28,7 +28,7 @@ SYMBOLS = [
     "gx_compute_jacobian", "gx_localize_error", "gx_element_error", "gx_comm_init", "gx_nccl_unique_id",
     "gx_reduce_interfaces", "gx_allreduce_sum", "gx_interface_bytes", "gx_pack_interface",
     "gx_unpack_add_interface", "gx_result_dev", "gx_fetch", "gx_plastic_count", "gx_num_colors",
-    "gx_stream", "gx_last_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_apply_bforce", "gx_owned_tpetra_graph", "gx_fetch_owned_tpetra", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
+    "gx_stream", "gx_last_timing", "gx_last_stage_timing", "gx_set_option", "gx_measure_fp64_peak", "gx_apply_bforce", "gx_owned_tpetra_graph", "gx_fetch_owned_tpetra", "gx_num_peers", "gx_struct_pack", "gx_struct_unpack",
     "gx_struct_finalize", "gx_owned_graph", "gx_fetch_owned", "gx_exchange_plan", "gx_functional_avg_disp",
     "gx_apply_dbcs", "gx_node_graph", "gx_functional", "gx_ks_vm_max", "gx_ks_vm_scale", "gx_dmdu_dev",
     "gx_fetch_dmdu", "gx_apply_tbcs", "gx_apply_ibcs", "gx_add_solution", "gx_get_solution", "gx_sync_solution",
@@ -106,6 +106,7 @@ def load_library():
     L.gx_stream.restype = vp
     L.gx_stream.argtypes = [vp]
     L.gx_last_timing.argtypes = [vp, dp]
+    L.gx_last_stage_timing.argtypes = [vp, dp]
     L.gx_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
     L.gx_measure_fp64_peak.argtypes = [vp, dp, dp]
     L.gx_apply_bforce.argtypes = [vp, dp, C.c_int]
@@ -414,6 +415,12 @@ class Assembler:
         t = (C.c_double * 4)()
         self._ck(self.L.gx_last_timing(self.h, t))
         return dict(zero_ms=t[0], assemble_ms=t[1], exchange_ms=t[2], launches=int(t[3]))
+
+    def last_stage_timing(self):
+        """assemble_ms of last_timing() split into the element kernel and the gather kernel(s)"""
+        t = (C.c_double * 2)()
+        self._ck(self.L.gx_last_stage_timing(self.h, t))
+        return dict(element_ms=t[0], gather_ms=t[1])
 
     def stream(self):
         return self.L.gx_stream(self.h)

@@ -359,7 +359,7 @@ static void fill_params(gx_ctx* ctx, KParams& P) {
   P.elems = ctx->d_perm; P.adj_off = ctx->d_adj_off; P.adj = ctx->d_adj;
   P.state_in = ctx->d_state_in; P.state_out = ctx->d_state_out;
   P.R = ctx->d_R; P.values = ctx->d_values; P.err = ctx->d_err; P.plastic = ctx->d_plastic;
-  P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk; P.pf_dist = (int)ctx->opt_prefetch;
+  P.e0 = 0; P.e1 = 0; P.nn = ctx->nn; P.max_nblk = ctx->max_nblk; P.pf_dist = (int)ctx->opt_prefetch; P.pf_elems = (int)ctx->opt_prefetch_elems[0];
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = ctx->mats[s < ctx->nsets ? s : 0];
 }
 
@@ -372,6 +372,8 @@ static cudaError_t launch_patch_gather(gx_ctx* ctx, KParams& P, int pass, bool s
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess || ctx->n_patches == 0) return e;
+  if ((e = cudaEventRecord(ctx->ev_stage, ctx->stream)) != cudaSuccess) return e;
+  ctx->staged = true;
   bool const tr = pass == PASS_JACOBIAN_T;
   auto kern = tr ? patch_pair_kernel<true> : patch_pair_kernel<false>;
   size_t const smem = patch_smem_bytes();
@@ -435,6 +437,8 @@ static cudaError_t launch_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_stage, ctx->stream)) != cudaSuccess) return e;
+  ctx->staged = true;
   node_gather_kernel<<<(unsigned)((8 * (int64_t)ctx->nn + 255) / 256), 256, 0, ctx->stream>>>(P, rvec);
   ctx->launches++;
   return cudaGetLastError();
@@ -467,6 +471,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   }
   bool const gather = !with_values && ctx->opt_kernel != 1;
   ctx->overlapped = false;
+  ctx->staged = false;
   ctx->overlap_now = 0;
   if (patch_gather && ctx->opt_overlap && ctx->nranks > 1 && ctx->comm && !ctx->peers.empty()) {
     if (!ctx->comm_stream) {
@@ -494,6 +499,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaEventRecord(ctx->ev[1], ctx->stream));
   KParams P;
   fill_params(ctx, P);
+  P.pf_elems = (int)ctx->opt_prefetch_elems[save ? 0 : 1];
   cudaError_t le;
   if (gather)
     le = ctx->model == GX_MODEL_J2 ? launch_gather<MODEL_J2>(ctx, P, pass, save) : launch_gather<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
@@ -514,6 +520,13 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   GX_CUDA(cudaEventElapsedTime(&t0, ctx->ev[0], ctx->ev[1]));
   GX_CUDA(cudaEventElapsedTime(&t1, ctx->ev[1], ctx->ev[2]));
   ctx->timing[0] = t0; ctx->timing[1] = t1; ctx->timing[2] = 0.0; ctx->timing[3] = ctx->launches;
+  ctx->stage_ms[0] = t1; ctx->stage_ms[1] = 0.0;
+  if (ctx->staged) {  // element kernel | gather kernel(s)
+    float ta = 0, tb = 0;
+    GX_CUDA(cudaEventElapsedTime(&ta, ctx->ev[1], ctx->ev_stage));
+    GX_CUDA(cudaEventElapsedTime(&tb, ctx->ev_stage, ctx->overlapped ? ctx->ev_b2 : ctx->ev[2]));
+    ctx->stage_ms[0] = ta; ctx->stage_ms[1] = tb;
+  }
   if (ctx->overlapped) {
     // the assembly kernels end at ev_b2; what the exchange adds to the pass is only what sticks out behind them
     float tk = 0, tx = 0;
@@ -570,7 +583,7 @@ static void free_device(gx_ctx* ctx) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
-  for (cudaEvent_t e : {ctx->ev_iface, ctx->ev_b2, ctx->ev_comm}) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : {ctx->ev_iface, ctx->ev_b2, ctx->ev_comm, ctx->ev_stage}) if (e) cudaEventDestroy(e);
   if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
 }
@@ -614,16 +627,21 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
   auto fail = [&](int rc) { g_create_err = ctx->err; free_device(ctx); comm_destroy(ctx); delete ctx; return rc; };
   for (int e = 0; e < ctx->ne && !ctx->eset.empty(); ++e)
     if (ctx->eset[e] < 0 || ctx->eset[e] >= ctx->nsets) { ctx->err = "elem_set entry out of range"; return fail(GX_ERR_ARG); }
+  SetupTimer tm;
   int rc = build_graph_and_schedule(ctx);
   if (rc) return fail(rc);
+  tm.t0 = SetupTimer::now();
   rc = comm_setup_lists(ctx, d);
   if (rc) return fail(rc);
+  tm.lap("exchange lists");
 
   auto body = [&]() -> int {
     GX_CUDA(cudaSetDevice(ctx->device));
     GX_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     GX_CUDA(cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, ctx->device));
     for (auto& e : ctx->ev) GX_CUDA(cudaEventCreate(&e));
+    GX_CUDA(cudaEventCreate(&ctx->ev_stage));
+    tm.lap("CUDA context");
     int const nn = ctx->nn, ne = ctx->ne;
     // ---- nodes and elements (device element order = colour-sorted)
     {  // node records; conn (int32 x 4) and the scatter map (uint8 x 16) already have the device layout
@@ -678,6 +696,8 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     ctx->d_plastic = reinterpret_cast<unsigned long long*>(ctx->d_err + 2);
     GX_CUDA(cudaHostAlloc(&ctx->h_status, 16, cudaHostAllocDefault));
     GX_CUDA(cudaMalloc(&ctx->d_red, sizeof(double) * 1024));
+    GX_CUDA(cudaStreamSynchronize(ctx->stream));
+    tm.lap("device arrays");
     return GX_OK;
   };
   if (ctx->device >= 0) {
@@ -1205,6 +1225,12 @@ int gx_last_timing(gx_ctx* ctx, double t[4]) {
   return GX_OK;
 }
 
+int gx_last_stage_timing(gx_ctx* ctx, double t[2]) {
+  if (!ctx || !t) return GX_ERR_ARG;
+  t[0] = ctx->stage_ms[0]; t[1] = ctx->stage_ms[1];
+  return GX_OK;
+}
+
 // FP64 roof measured on the device: DFMA chains in registers, no memory traffic
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, long long* cyc, int iters) {
   double a[8];
@@ -1297,6 +1323,11 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (k == "prefetch") {  // stage B: L2 prefetch distance in patches (0 = off)
     if (value < 0 || value > (1 << 20)) { ctx->err = "prefetch must be 0..2^20"; return GX_ERR_ARG; }
     ctx->opt_prefetch = value;
+    return GX_OK;
+  }
+  if (k == "prefetch_elems" || k == "prefetch_elems_nosave") {  // element kernels: L2 prefetch distance in elements (0 = off); rounded to whole warps
+    if (value < 0 || value > (1 << 24)) { ctx->err = k + " must be 0..2^24"; return GX_ERR_ARG; }
+    ctx->opt_prefetch_elems[k == "prefetch_elems" ? 0 : 1] = value & ~(int64_t)31;
     return GX_OK;
   }
   if (k == "block_size") {

@@ -3,6 +3,9 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <time.h>
 
 #include <string>
 #include <vector>
@@ -100,6 +103,9 @@ struct gx_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t comm_stream = nullptr;  // interface exchange overlapped with the interior patches (option "overlap")
   cudaEvent_t ev_iface = nullptr, ev_b2 = nullptr, ev_comm = nullptr;
+  cudaEvent_t ev_stage = nullptr;  // between the two kernels of a two-stage pass (stage_ms)
+  bool staged = false;
+  double stage_ms[2] = {0, 0};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   gx::NodeRec* d_nodes = nullptr;
   gx::ZRec* d_z = nullptr;
@@ -158,6 +164,10 @@ struct gx_ctx {
   bool have_result = false;
   bool have_values = false;
   int64_t opt_block = 128;
+  // element kernels: L2 prefetch distance in elements, {passes that save the state, passes that do not}.  Measured on
+  // 12.6M tets (profiles/r02u_stage_a_prefetch.txt): saving passes are best at 9.5k-57k (the prefetched lines must survive
+  // 574 B/element of streaming traffic in L2), the others at 150k-200k.
+  int64_t opt_prefetch_elems[2] = {18944, 151552};
   int64_t opt_prefetch = 256;  // stage B L2 prefetch distance in patches (measured best on 12.6M tets: 150-300; one generation of resident blocks is 592)
   int64_t overlap_now = 0;  // `what` of the exchange fused into the pass being enqueued (0: none)
   bool overlapped = false;  // the last pass reduced the interfaces itself
@@ -170,6 +180,13 @@ struct gx_ctx {
 
 namespace gx {
 // host setup (gx_setup.cpp)
+struct SetupTimer {  // GX_SETUP_TIMING=1 prints the wall time of every setup section to stderr
+  bool on = getenv("GX_SETUP_TIMING") != nullptr;
+  double t0 = now();
+  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
+  void lap(char const* what) { if (!on) return; double const t = now(); fprintf(stderr, "[gx setup] %-28s %.3f s\n", what, t - t0); t0 = t; }
+};
+
 int build_graph_and_schedule(gx_ctx* c);
 int build_colouring(gx_ctx* c);  // lazily: only the coloured fallback needs it
 void materialise_crs(gx_ctx* c);

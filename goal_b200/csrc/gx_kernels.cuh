@@ -57,6 +57,7 @@ struct KParams {
   unsigned long long* plastic;  // counter
   int e0, e1;                   // slot range of this launch (coloured schedule)
   int pf_dist;                  // stage B: patches ahead whose records are pulled into L2 (0 = no prefetch)
+  int pf_elems;                 // element kernels: elements ahead whose connectivity / old state are pulled into L2 (0 = off)
   int nn;
   int max_nblk;
   Material mat[GX_MAX_ELEM_SETS];
@@ -267,21 +268,27 @@ constexpr int ELEM_REC = TREC;  // doubles; 304 B = 19 x 16 B: an odd number of 
 // Per-thread stores of the 72 B Fp records touch 32 different 128 B lines per instruction (9 instructions); staged
 // through shared memory the warp re-reads its 2.5 KB of old-state records (just gathered by its threads: L1 / L2
 // hits) with 5 coalesced 128-bit loads and writes the Fp halves of its state records (pairs 5-9, 80 B each) with 5
-// coalesced 128-bit stores.
-// buf: >= WSAVE_DOUBLES doubles of shared memory that belong to the warp and are free (callers __syncwarp first).
+// coalesced 128-bit stores.  The block load (wsave_load) is split from the rest so that callers can issue it before
+// they wait for the staging buffer to become free.
+// buf: >= WSAVE_DOUBLES doubles of shared memory, 16 B aligned, that belong to the warp and are free.
 constexpr int WSAVE_ST = 32 * STATE_IN, WSAVE_LD = 11;  // old-state block at [0, 320), Fp rows of 11 doubles (odd: conflict-free) behind it
 constexpr int WSAVE_DOUBLES = WSAVE_ST + 32 * WSAVE_LD;
-__device__ __forceinline__ void warp_save_Fp(KParams const& P, int e0, int nrec, int lane, int plastic, double const dN[6], double* buf) {
-  unsigned const pmask = __ballot_sync(0xffffffffu, plastic != 0);
-  if (!pmask) return;
-  double const* src = P.state_in + (int64_t)STATE_IN * e0;  // 80 B records: 16 B aligned
-  int const tot = STATE_IN * nrec;                           // even
-  for (int g = 2 * lane; g < tot; g += 64) { double2 const v = __ldg(reinterpret_cast<double2 const*>(src + g)); buf[g] = v.x; buf[g + 1] = v.y; }
+__device__ __forceinline__ void wsave_load(KParams const& P, int e0, int nrec, int lane, double2 v[5]) {
+  double2 const* src = reinterpret_cast<double2 const*>(P.state_in + (int64_t)STATE_IN * e0);  // 80 B records: 16 B aligned
+  int const tot = (STATE_IN / 2) * nrec;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { int const g = lane + 32 * i; v[i] = g < tot ? __ldg(src + g) : make_double2(0.0, 0.0); }
+}
+__device__ __forceinline__ void wsave_finish(KParams const& P, int e0, int nrec, int lane, unsigned pmask, int plastic, double const dN[6],
+                                             double2 const v[5], double* buf) {
+#pragma unroll
+  for (int i = 0; i < 5; ++i) reinterpret_cast<double2*>(buf)[lane + 32 * i] = v[i];
   __syncwarp();
   if (plastic) {
-    double Fpo[9], Fpn[9];
-#pragma unroll
-    for (int k = 0; k < 9; ++k) Fpo[k] = buf[STATE_IN * lane + k];
+    double2 const* q = reinterpret_cast<double2 const*>(buf + STATE_IN * lane);  // stride 5 x 16 B (odd): conflict-free
+    double2 const a = q[0], b = q[1], c = q[2], d = q[3], f = q[4];
+    double const Fpo[9] = {a.x, a.y, b.x, b.y, c.x, c.y, d.x, d.y, f.x};
+    double Fpn[9];
     plastic_update(dN, Fpo, Fpn);
     double* st = buf + WSAVE_ST + lane * WSAVE_LD;
 #pragma unroll
@@ -297,18 +304,31 @@ __device__ __forceinline__ void warp_save_Fp(KParams const& P, int e0, int nrec,
     *reinterpret_cast<double2*>(dst + STATE_OUT * r + 2 * j) = make_double2(q[0], q[1]);
   }
 }
+// L2 prefetch of the streamed inputs (connectivity, old state) of the 32 elements starting at ep: two bulk prefetches
+// issued by one warp.  The element kernels are latency-bound at their register-limited occupancy (conn -> nodes is a
+// dependent chain of two DRAM round trips); with the first link served from L2 the chain is one DRAM trip shorter.
+template <int MODEL>
+__device__ __forceinline__ void prefetch_elements(KParams const& P, int ep, int ne, int lane) {
+  if (ep >= ne) return;
+  uint32_t const n = (uint32_t)min(32, ne - ep);
+  if (lane == 0) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.conn + ep), "r"(n * 16u) : "memory");
+  if (MODEL == MODEL_J2 && lane == 1)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.state_in + (int64_t)STATE_IN * ep), "r"(n * (uint32_t)(STATE_IN * 8)) : "memory");
+}
 
 template <int MODEL, bool SAVE>
 __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
-  // records leave through shared memory so that a warp writes its 32 records (8.5 KB, contiguous) with
-  // fully coalesced 128-bit stores instead of 17 stride-272 B stores per thread; the Fp update reuses the buffer
-  __shared__ double srec[2][32 * ELEM_REC + 32];  // 64-thread blocks; row stride 35 doubles (odd): conflict-free column writes
-  static_assert(32 * ELEM_REC + 32 >= WSAVE_DOUBLES, "state staging must fit the record buffer");
+  // A warp's 32 records are contiguous in global memory (9.5 KB): the threads put them into shared memory (record
+  // stride 19 x 16 B, odd: conflict-free 128-bit stores) and one bulk asynchronous copy writes the block -- no
+  // per-thread stride-304 B stores, no copy loop through the LSU.  The Fp update reuses the buffer afterwards.
+  __shared__ __align__(128) double srec[2][32 * ELEM_REC];  // 64-thread blocks
+  static_assert(32 * ELEM_REC >= WSAVE_DOUBLES, "state staging must fit the record buffer");
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int const e0 = blockIdx.x * blockDim.x + wib * 32;  // first element of this warp
   int const nrec = min(32, ne - e0);
-  double* mine = &srec[wib][lane * (ELEM_REC + 1)];
+  if (P.pf_elems > 0) prefetch_elements<MODEL>(P, e0 + P.pf_elems, ne, lane);
+  double2* mine = reinterpret_cast<double2*>(&srec[wib][lane * ELEM_REC]);
   int plastic = 0;
   double dN[6];
   if (e < ne) {
@@ -319,14 +339,14 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
     if (rc != ERR_NONE) {
       report_error(P.err, rc, e);
 #pragma unroll
-      for (int k = 0; k < ELEM_REC; ++k) mine[k] = 0.0;
+      for (int k = 0; k < ELEM_REC / 2; ++k) mine[k] = make_double2(0.0, 0.0);
     } else {
       plastic = c.plastic;
       {
         double r[ELEM_REC];
         pack_trec(c, r);
 #pragma unroll
-        for (int k = 0; k < ELEM_REC; ++k) mine[k] = r[k];
+        for (int k = 0; k < ELEM_REC / 2; ++k) mine[k] = make_double2(r[2 * k], r[2 * k + 1]);
       }
       if (SAVE && MODEL == MODEL_J2 && plastic) {
 #pragma unroll
@@ -334,19 +354,21 @@ __global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constan
       }
     }
   }
-  __syncwarp();
   if (nrec > 0) {
-    double* dst = rec + (int64_t)ELEM_REC * e0;
-    int const total = nrec * ELEM_REC;  // doubles, contiguous in global memory
-    for (int g = 2 * lane; g < total; g += 64) {
-      int const r = g / ELEM_REC, k = g - r * ELEM_REC;  // ELEM_REC is even: the pair stays inside one record
-      double const* src = &srec[wib][r * (ELEM_REC + 1) + k];
-      *reinterpret_cast<double2*>(dst + g) = make_double2(src[0], src[1]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes above -> visible to the bulk copy
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(rec + (int64_t)ELEM_REC * e0),
+                   "r"((uint32_t)__cvta_generic_to_shared(srec[wib])), "r"((uint32_t)nrec * (uint32_t)(ELEM_REC * 8))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     }
-    if (SAVE && MODEL == MODEL_J2) {
-      __syncwarp();  // the record buffer is free again
-      warp_save_Fp(P, e0, nrec, lane, plastic, dN, srec[wib]);
-    }
+    unsigned const pmask = SAVE && MODEL == MODEL_J2 ? __ballot_sync(0xffffffffu, plastic != 0) : 0u;
+    double2 v[5];
+    if (pmask) wsave_load(P, e0, nrec, lane, v);  // in flight while the bulk copy drains the buffer
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the buffer has been read: free (and safe to exit)
+    __syncwarp();
+    if (pmask) wsave_finish(P, e0, nrec, lane, pmask, plastic, dN, v, srec[wib]);
   }
   if (MODEL == MODEL_J2) {
     unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
@@ -565,12 +587,13 @@ template <int MODEL, bool SAVE, bool ERROR>
 __global__ void __launch_bounds__(128, 4) elem_residual_kernel(const __grid_constant__ KParams P, double* __restrict__ rvec, int ne) {
   // the element residual lines (128 B each) and the state leave through shared memory: coalesced 128-bit stores
   // instead of 32 different 128 B lines per store instruction
-  __shared__ double sbuf[4][WSAVE_DOUBLES];
-  static_assert(WSAVE_DOUBLES >= 32 * 17, "residual staging must fit");
+  __shared__ __align__(16) double sbuf[4][WSAVE_DOUBLES];
+  static_assert(WSAVE_DOUBLES >= 32 * 17 && WSAVE_DOUBLES % 2 == 0, "residual staging must fit");
   int const e = blockIdx.x * blockDim.x + threadIdx.x;
   int const wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int const e0 = blockIdx.x * blockDim.x + wib * 32;
   int const nrec = min(32, ne - e0);
+  if (P.pf_elems > 0) prefetch_elements<MODEL>(P, e0 + P.pf_elems, ne, lane);
   double* buf = sbuf[wib];
   int plastic = 0;
   double dN[6];
@@ -611,14 +634,17 @@ __global__ void __launch_bounds__(128, 4) elem_residual_kernel(const __grid_cons
   }
   __syncwarp();
   if (nrec > 0) {
+    unsigned const pmask = SAVE && MODEL == MODEL_J2 ? __ballot_sync(0xffffffffu, plastic != 0) : 0u;
+    double2 v[5];
+    if (pmask) wsave_load(P, e0, nrec, lane, v);  // in flight during the copy loop
     double* dst = rvec + 16 * (int64_t)e0;
     for (int g = lane; g < nrec * 8; g += 32) {
       double const* q = buf + 17 * (g >> 3) + 2 * (g & 7);
       *reinterpret_cast<double2*>(dst + 2 * g) = make_double2(q[0], q[1]);
     }
-    if (SAVE && MODEL == MODEL_J2) {
+    if (pmask) {
       __syncwarp();
-      warp_save_Fp(P, e0, nrec, lane, plastic, dN, buf);
+      wsave_finish(P, e0, nrec, lane, pmask, plastic, dN, v, buf);
     }
   }
   if (MODEL == MODEL_J2) {

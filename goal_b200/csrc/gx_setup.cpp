@@ -26,15 +26,6 @@
 
 namespace gx {
 
-namespace {
-struct SetupTimer {  // GX_SETUP_TIMING=1 prints the wall time of every setup section to stderr
-  bool on = getenv("GX_SETUP_TIMING") != nullptr;
-  double t0 = now();
-  static double now() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
-  void lap(char const* what) { if (!on) return; double const t = now(); fprintf(stderr, "[gx setup] %-28s %.3f s\n", what, t - t0); t0 = t; }
-};
-}  // namespace
-
 int build_graph_and_schedule(gx_ctx* c) {
   SetupTimer tm;
   int const nn = c->nn, ne = c->ne;

@@ -266,6 +266,9 @@ void* gx_stream(gx_ctx* ctx);                   /* the cudaStream_t every kernel
 /* Device time (ms, CUDA events on gx_stream) of the last compute call:
  * t[0] zeroing, t[1] assembly kernels, t[2] interface exchange, t[3] kernel launches counted */
 int gx_last_timing(gx_ctx* ctx, double t[4]);
+/* t[1] of gx_last_timing split at the boundary between the element kernel (t[0]: stress update, state save, element
+ * records) and the kernels that gather the records into R / the CRS values (t[1]); {t[1], 0} for a one-kernel pass */
+int gx_last_stage_timing(gx_ctx* ctx, double t[2]);
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value);
 /* The work list of the patch-gather Jacobian pass as the device reads it (layout: goal_b200/csrc/gx_setup.cpp,
  * build_patch_schedule); dims = {patches, words per patch, record slots per patch, threads per patch}.  Valid until
