@@ -426,7 +426,56 @@ static int upload_patch_schedule(gx_ctx* ctx) {
   return GX_OK;
 }
 
-// gather form of the residual / error-localisation passes
+static int upload_residual_schedule(gx_ctx* ctx) {
+  if (ctx->res_state != 0) return GX_OK;
+  if (!build_residual_schedule(ctx)) return GX_OK;  // res_state = -1: the caller falls back to the element-line form
+  size_t total = 0;
+  for (auto const& v : ctx->res_chunks) total += v.size();
+  GX_CUDA(cudaMalloc(&ctx->d_res_sched, sizeof(uint32_t) * std::max<size_t>(total, 4)));
+  size_t off = 0;
+  for (auto& v : ctx->res_chunks) {
+    if (!v.empty()) GX_CUDA(cudaMemcpyAsync(ctx->d_res_sched + off, v.data(), sizeof(uint32_t) * v.size(), cudaMemcpyHostToDevice, ctx->stream));
+    off += v.size();
+  }
+  auto up = [&](auto*& d, auto const& h) -> int {
+    GX_CUDA(cudaMalloc(&d, sizeof(h[0]) * std::max<size_t>(h.size(), 1)));
+    if (!h.empty()) GX_CUDA(cudaMemcpyAsync(d, h.data(), sizeof(h[0]) * h.size(), cudaMemcpyHostToDevice, ctx->stream));
+    return GX_OK;
+  };
+  int rc;
+  if ((rc = up(ctx->d_res_boff, ctx->res_boff)) || (rc = up(ctx->d_res_pnode, ctx->res_pnode)) || (rc = up(ctx->d_res_poff, ctx->res_poff))) return rc;
+  GX_CUDA(cudaMalloc(&ctx->d_res_partial, sizeof(double) * 4 * (size_t)std::max<int64_t>(ctx->res_npartial, 1)));
+  GX_CUDA(cudaStreamSynchronize(ctx->stream));
+  std::vector<std::vector<uint32_t>>().swap(ctx->res_chunks);
+  std::vector<uint32_t>().swap(ctx->res_boff);
+  std::vector<uint32_t>().swap(ctx->res_poff);
+  return GX_OK;
+}
+
+// block-reduced form of the residual / error-localisation passes (default)
+template <int MODEL>
+static cudaError_t launch_block_residual(gx_ctx* ctx, KParams& P, int pass, bool save) {
+  int const ne = ctx->ne, nb = (ne + RES_BLOCK - 1) / RES_BLOCK;
+  uint32_t const* sc = ctx->d_res_sched;
+  uint32_t const* bo = ctx->d_res_boff;
+  double* pa = ctx->d_res_partial;
+  if (pass == PASS_ERROR) elem_residual_block_kernel<MODEL, false, true><<<nb, RES_BLOCK, 0, ctx->stream>>>(P, sc, bo, pa, ne);
+  else if (save) elem_residual_block_kernel<MODEL, true, false><<<nb, RES_BLOCK, 0, ctx->stream>>>(P, sc, bo, pa, ne);
+  else elem_residual_block_kernel<MODEL, false, false><<<nb, RES_BLOCK, 0, ctx->stream>>>(P, sc, bo, pa, ne);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if ((e = cudaEventRecord(ctx->ev_stage, ctx->stream)) != cudaSuccess) return e;
+  ctx->staged = true;
+  int const np = (int)ctx->res_pnode.size();
+  if (np > 0) {
+    node_partial_sum_kernel<<<(unsigned)((2 * (int64_t)np + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_res_pnode, ctx->d_res_poff, pa, P.R, np);
+    ctx->launches++;
+  }
+  return cudaGetLastError();
+}
+
+// element-line form of the residual / error-localisation passes (option residual_kernel = 1; also what dMdu uses)
 template <int MODEL>
 static cudaError_t launch_gather(gx_ctx* ctx, KParams& P, int pass, bool save) {
   int const ne = ctx->ne, nb = (ne + 127) / 128;
@@ -470,6 +519,12 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
     patch_gather = ctx->patch_state == 1;
   }
   bool const gather = !with_values && ctx->opt_kernel != 1;
+  bool block_residual = gather && ctx->opt_residual == 0;
+  if (block_residual) {
+    int const rc = upload_residual_schedule(ctx);
+    if (rc) return rc;
+    block_residual = ctx->res_state == 1;
+  }
   ctx->overlapped = false;
   ctx->staged = false;
   ctx->overlap_now = 0;
@@ -482,7 +537,7 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
     }
     ctx->overlap_now = ctx->opt_overlap & 3;
   }
-  if ((gather || patch_gather) && !ctx->d_elemrec)
+  if (((gather && !block_residual) || patch_gather) && !ctx->d_elemrec)
     GX_CUDA(cudaMalloc(&ctx->d_elemrec, sizeof(double) * (size_t)ELEM_REC * (size_t)ctx->ne));
   if (patch_gather && ctx->has_isolated_nodes)  // nodes without elements have no work item: their R entries are zero
     GX_CUDA(cudaMemsetAsync(ctx->d_R, 0, sizeof(double) * 4 * (size_t)ctx->nn, ctx->stream));
@@ -501,7 +556,9 @@ static int run_pass(gx_ctx* ctx, int pass, bool save, bool with_values) {
   fill_params(ctx, P);
   P.pf_elems = (int)ctx->opt_prefetch_elems[save ? 0 : 1];
   cudaError_t le;
-  if (gather)
+  if (block_residual)
+    le = ctx->model == GX_MODEL_J2 ? launch_block_residual<MODEL_J2>(ctx, P, pass, save) : launch_block_residual<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
+  else if (gather)
     le = ctx->model == GX_MODEL_J2 ? launch_gather<MODEL_J2>(ctx, P, pass, save) : launch_gather<MODEL_NEOHOOKEAN>(ctx, P, pass, save);
   else if (patch_gather)
     le = ctx->model == GX_MODEL_J2 ? launch_patch_gather<MODEL_J2>(ctx, P, pass, save)
@@ -579,7 +636,8 @@ static void free_device(gx_ctx* ctx) {
   cudaSetDevice(ctx->device);
   void* ptrs[] = {ctx->d_nodes, ctx->d_z, ctx->d_conn, ctx->d_bpos, ctx->d_eset, ctx->d_perm, ctx->d_adj_off, ctx->d_adj, ctx->d_diag_pos,
                   ctx->d_state_in, ctx->d_state_out, ctx->d_elemrec, ctx->d_R, ctx->d_values, ctx->d_stage, ctx->d_err,
-                  ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched};
+                  ctx->d_red, ctx->d_dMdu, ctx->d_child_off, ctx->d_child, ctx->d_patch_sched,
+                  ctx->d_res_sched, ctx->d_res_boff, ctx->d_res_pnode, ctx->d_res_poff, ctx->d_res_partial};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_status) cudaFreeHost(ctx->h_status);
   for (auto& e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -1305,6 +1363,11 @@ int gx_set_option(gx_ctx* ctx, const char* key, int64_t value) {
   if (k == "kernel") {  // every pass: 0 = owner-computes schedules (default; 3 is accepted as an alias), 1 = coloured elements
     if (value != 0 && value != 1 && value != 3) { ctx->err = "kernel must be 0 (owner-computes) or 1 (coloured)"; return GX_ERR_ARG; }
     ctx->opt_kernel = value == 1 ? 1 : 0;
+    return GX_OK;
+  }
+  if (k == "residual_kernel") {  // residual / localisation passes: 0 = block-reduced (default), 1 = element lines + node gather
+    if (value != 0 && value != 1) { ctx->err = "residual_kernel must be 0 (block-reduced) or 1 (element lines)"; return GX_ERR_ARG; }
+    ctx->opt_residual = value;
     return GX_OK;
   }
   if (k == "patch_schedule_dryrun") {  // host-side build of the patch schedule (works on host-only contexts); GX_SCHED_STATS prints its statistics

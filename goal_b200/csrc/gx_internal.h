@@ -95,6 +95,13 @@ struct gx_ctx {
   int n_patches = 0;
   int n_patches_iface = 0;  // partitioned contexts: the leading patches that write every block of the interface rows
   int patch_state = 0;  // 0 = not built, 1 = built, -1 = mesh does not fit (a node exceeds a patch)
+  // ---- block-reduced schedule of the residual / error-localisation passes, see build_residual_schedule()
+  std::vector<std::vector<uint32_t>> res_chunks;  // the blocks' words, one chunk per builder thread (concatenated = the schedule)
+  std::vector<uint32_t> res_boff;                 // [blocks + 1] first word of every block
+  std::vector<int32_t> res_pnode;                 // nodes finished by node_partial_sum_kernel (shared between blocks, or without elements)
+  std::vector<uint32_t> res_poff;                 // [res_pnode.size() + 1] their runs in the partial-sum buffer
+  int64_t res_npartial = 0;
+  int res_state = 0;  // 0 = not built, 1 = built, -1 = does not fit
   // ---- schedule
   int ncolors = 0;
   std::vector<int32_t> color_off;  // [ncolors+1] in device element order
@@ -117,6 +124,11 @@ struct gx_ctx {
   int2* d_adj = nullptr;
   uint8_t* d_diag_pos = nullptr;   // position of block (a,a) in node a's block row
   uint32_t* d_patch_sched = nullptr;
+  uint32_t* d_res_sched = nullptr;
+  uint32_t* d_res_boff = nullptr;
+  int32_t* d_res_pnode = nullptr;
+  uint32_t* d_res_poff = nullptr;
+  double* d_res_partial = nullptr;  // [res_npartial][4]
   // history state, one record per element (user order):
   //   in  : Fp_old[9], eqps_old                              (80 B)  read once per element and pass
   //   out : sigma[9], eqps, Fp[9], pad                       (160 B)
@@ -173,6 +185,7 @@ struct gx_ctx {
   bool overlapped = false;  // the last pass reduced the interfaces itself
   int64_t opt_overlap = 0;  // bit mask like gx_reduce_interfaces' `what` (1 = R, 2 = dRdu): the Jacobian pass reduces the
                             // interfaces itself, on a second stream, while the interior patches are still being assembled
+  int64_t opt_residual = 0;  // residual / localisation passes: 0 = block-reduced, 1 = element lines + node gather
   int64_t opt_kernel = 0;  // 0 = owner-computes schedules (patch pairs / gather form), 1 = coloured elements
   int num_sms = 148;
   std::string err;
@@ -203,6 +216,7 @@ constexpr int SO_SIGMA = 0, SO_EQPS = 9, SO_FP = 10;
 void pack_host(gx_ctx const* c, HostPack& h);
 void build_block_lists(gx_ctx* c);
 bool build_patch_schedule(gx_ctx* c);
+bool build_residual_schedule(gx_ctx* c);
 void flatten_patch_schedule(gx_ctx* c);
 
 // patch schedule geometry (shared by gx_setup.cpp and the kernel)
@@ -221,6 +235,20 @@ constexpr int PATCH_DIAG_LANES = 32;  // lanes [0, 32) run the DIAG items, the o
 constexpr int PATCH_PART_LD = 36;   // doubles per partial sum: two 4x4 blocks + the residual entries
 constexpr int PATCH_WORDS = 4 + 4 * PATCH_THREADS + 4 * PATCH_THREADS + 2 * PATCH_RECS;  // uint32 words per patch
 static_assert(PATCH_RECS <= 256, "record slots are 8 bit");
+// Block-reduced schedule of the residual / error-localisation passes (build_residual_schedule, gx_setup.cpp): blocks of
+// RES_BLOCK consecutive elements.  Words of one block: {slots S, words of this block, 0, 0}, then per slot (= distinct
+// node of the block, in order of first appearance) {target | complete << 31, first | count << 16}, then the block's
+// 4 * elements incidence entries grouped by slot, ascending elements inside a slot (uint16 = 8 * local element +
+// ((2 * local node) ^ (local element & 7)): the 16 B chunk, in the kernel's swizzled shared-memory rows, that holds
+// the first two of the node's four residual entries; the other two sit in chunk ^ 1); padded to a multiple of 4 words.  target = the node when the block holds all its elements (the block writes R), else
+// the position of this block's partial sum in the partial buffer (node_partial_sum_kernel adds those in block order).
+#ifndef GX_RES_BLOCK
+#define GX_RES_BLOCK 128
+#endif
+constexpr int RES_BLOCK = GX_RES_BLOCK;  // 64, 128 or 256
+constexpr int RES_MINB = 512 / RES_BLOCK;  // thread blocks per SM the kernel is compiled for
+constexpr int RES_HDR = 4;
+constexpr int RES_MAX_WORDS = RES_HDR + 2 * 4 * RES_BLOCK + 2 * RES_BLOCK;  // every incidence a slot of its own
 // gx_comm.cu
 void comm_destroy(gx_ctx*);
 int comm_setup_lists(gx_ctx*, const gx_desc*);

@@ -679,6 +679,139 @@ __global__ void __launch_bounds__(256) node_gather_kernel(const __grid_constant_
   if (a < P.nn && sub == 0) stg256(P.R + 4 * (int64_t)a, r0, r1, r2, r3);
 }
 // ---------------------------------------------------------------------------
+// Residual and error-localisation passes, block-reduced form (default; schedule: build_residual_schedule, gx_setup.cpp).
+//   elem_residual_block_kernel : RES_BLOCK consecutive elements per thread block, one per thread.  The 16 residual
+//                          entries of every element stay in shared memory; after a block barrier the threads sum them
+//                          per node of the block in the schedule's fixed order and write R (node complete in this
+//                          block) or one 32 B partial sum (node shared with other blocks).  State save as in stage A.
+//   node_partial_sum_kernel    : adds the partial sums of every shared node in ascending block order and writes R.
+// Against the element-line form above, the 128 B per element written and read back (plus the 32 B of adjacency) shrink
+// to the partial sums and the schedule words: about 2 x 22 + 14 B per element on an x-fastest numbered Kuhn cube.
+// ---------------------------------------------------------------------------
+template <int MODEL, bool SAVE, bool ERROR>
+__global__ void __launch_bounds__(RES_BLOCK, RES_MINB) elem_residual_block_kernel(const __grid_constant__ KParams P, uint32_t const* __restrict__ sched,
+                                                                          uint32_t const* __restrict__ boff, double* __restrict__ partial, int ne) {
+  __shared__ __align__(16) double srv[RES_BLOCK * 16];                   // [local element][local node][4]
+  __shared__ __align__(16) double sbuf[RES_BLOCK / 32][WSAVE_DOUBLES];   // Fp staging, one buffer per warp
+  __shared__ __align__(16) uint32_t ssched[RES_MAX_WORDS];
+  __shared__ __align__(8) unsigned long long mbar;
+  int const tid = threadIdx.x, wib = tid >> 5, lane = tid & 31;
+  int const e = blockIdx.x * RES_BLOCK + tid;
+  int const e0 = blockIdx.x * RES_BLOCK + wib * 32;
+  int const nrec = min(32, ne - e0);
+  // the block's schedule words arrive by one bulk copy while the elements are evaluated
+  uint32_t const mb = (uint32_t)__cvta_generic_to_shared(&mbar);
+  if (tid == 0) {
+    uint32_t const w0 = __ldg(boff + blockIdx.x), w1 = __ldg(boff + blockIdx.x + 1);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mb) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"((w1 - w0) * 4u) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (uint32_t)__cvta_generic_to_shared(ssched)),
+                 "l"(sched + w0), "r"((w1 - w0) * 4u), "r"(mb)
+                 : "memory");
+  }
+  if (P.pf_elems > 0) {
+    prefetch_elements<MODEL>(P, e0 + P.pf_elems, ne, lane);
+    int const bp = blockIdx.x + P.pf_elems / RES_BLOCK;
+    if (tid == 2 && bp < (int)gridDim.x) {
+      uint32_t const w0 = __ldg(boff + bp), w1 = __ldg(boff + bp + 1);
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(sched + w0), "r"((w1 - w0) * 4u) : "memory");
+    }
+  }
+  int plastic = 0;
+  double dN[6];
+  if (e < ne) {
+    int nd[4], b0[4], nb[4];
+    Material const* matp;
+    Core<double> c;
+    int const rc = load_and_update<MODEL, SAVE>(P, e, true, nd, b0, nb, matp, c);
+    double ru[12], rp[4];
+    if (rc != ERR_NONE) {
+      report_error(P.err, rc, e);
+#pragma unroll
+      for (int k = 0; k < 12; ++k) ru[k] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) rp[k] = 0.0;
+    } else {
+      plastic = c.plastic;
+      if (ERROR) {
+        double zu[4][3], zp[4], zpc[4];
+#pragma unroll
+        for (int n = 0; n < 4; ++n) {
+          double2 const* q = reinterpret_cast<double2 const*>(P.z + nd[n]);
+          double2 const a = ldg(q), b = ldg(q + 1), d = ldg(q + 2);
+          zu[n][0] = a.x; zu[n][1] = a.y; zu[n][2] = b.x; zp[n] = b.y; zpc[n] = d.x;
+        }
+        element_error_residual(c, zu, zp, zpc, ru, rp);
+      } else {
+        element_residual(c, ru, rp);
+      }
+      if (SAVE && MODEL == MODEL_J2 && plastic) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dN[k] = c.dN[k];
+      }
+    }
+    // 128 B rows: chunk k of row r sits at k ^ (r & 7), so that the 8 lanes of a quarter-warp store to 8 different bank
+    // groups; the schedule's entries are the swizzled chunk numbers
+    double2* o = reinterpret_cast<double2*>(srv + 16 * tid);
+    int const x = tid & 7;
+#pragma unroll
+    for (int n = 0; n < 4; ++n) {
+      o[(2 * n) ^ x] = make_double2(ru[3 * n], ru[3 * n + 1]);
+      o[(2 * n + 1) ^ x] = make_double2(ru[3 * n + 2], rp[n]);
+    }
+  }
+  if (SAVE && MODEL == MODEL_J2 && nrec > 0) {  // warp-local, before the block barrier: its loads overlap the other warps' work
+    unsigned const pmask = __ballot_sync(0xffffffffu, plastic != 0);
+    if (pmask) {
+      double2 v[5];
+      wsave_load(P, e0, nrec, lane, v);
+      wsave_finish(P, e0, nrec, lane, pmask, plastic, dN, v, sbuf[wib]);
+    }
+  }
+  __syncthreads();
+  {
+    uint32_t done;
+    do {
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(mb) : "memory");
+    } while (!done);
+  }
+  int const S = (int)ssched[0];
+  uint16_t const* ent = reinterpret_cast<uint16_t const*>(ssched + RES_HDR + 2 * S);
+  double2 const* sv = reinterpret_cast<double2 const*>(srv);
+  for (int item = tid; item < 2 * S; item += RES_BLOCK) {  // 2 threads per node: residual entries {0, 1} and {2, 3}
+    int const s = item >> 1, h = item & 1;
+    uint32_t const w0 = ssched[RES_HDR + 2 * s], w1 = ssched[RES_HDR + 2 * s + 1];
+    uint32_t const first = w1 & 0xffffu, cnt = w1 >> 16;
+    double2 acc = make_double2(0.0, 0.0);
+    for (uint32_t k = first; k < first + cnt; ++k) {
+      double2 const v = sv[(uint32_t)ent[k] ^ (uint32_t)h];  // the entry is the (swizzled) chunk of the node's first half
+      acc.x += v.x; acc.y += v.y;
+    }
+    double* dst = (w0 & 0x80000000u) ? P.R : partial;
+    *reinterpret_cast<double2*>(dst + 4 * (int64_t)(w0 & 0x7fffffffu) + 2 * h) = acc;
+  }
+  if (MODEL == MODEL_J2) {
+    unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
+    if (lane == 0 && b) atomicAdd(P.plastic, (unsigned long long)__popc(b));
+  }
+}
+
+__global__ void __launch_bounds__(256) node_partial_sum_kernel(int32_t const* __restrict__ pnode, uint32_t const* __restrict__ poff,
+                                                               double const* __restrict__ partial, double* __restrict__ R, int np) {
+  int const t = blockIdx.x * blockDim.x + threadIdx.x;
+  int const i = t >> 1, h = t & 1;  // 2 threads per node
+  if (i >= np) return;
+  uint32_t const p0 = __ldg(poff + i), p1 = __ldg(poff + i + 1);
+  double2 acc = make_double2(0.0, 0.0);
+  for (uint32_t p = p0; p < p1; ++p) {
+    double2 const v = __ldg(reinterpret_cast<double2 const*>(partial + 4 * (int64_t)p) + h);
+    acc.x += v.x; acc.y += v.y;
+  }
+  *reinterpret_cast<double2*>(R + 4 * (int64_t)__ldg(pnode + i) + 2 * h) = acc;
+}
+// ---------------------------------------------------------------------------
 // Functionals (Mechanics::build_functional, goal_mechanics.cpp:149-167; QoI<T> goal_qoi.cpp:21-82): one thread per
 // element evaluates the QoI evaluator behind the save=false chain and writes the element value ev[e] and, when
 // rvec != nullptr, d elem_value / d dof as one 128 B line rvec[e][n][4] -- node_gather_kernel then sums them per

@@ -21,6 +21,7 @@
 #include <cstring>
 #include <ctime>
 #include <numeric>
+#include <omp.h>
 
 #include "gx_internal.h"
 
@@ -708,6 +709,101 @@ void flatten_patch_schedule(gx_ctx* c) {
   for (int i = 0; i < (int)c->patch_chunks.size(); ++i)
     if (!c->patch_chunks[i].empty()) memcpy(c->patch_sched.data() + off[i], c->patch_chunks[i].data(), sizeof(uint32_t) * c->patch_chunks[i].size());
   std::vector<std::vector<uint32_t>>().swap(c->patch_chunks);
+}
+
+// ---------------------------------------------------------------------------
+// Block-reduced schedule of the residual / error-localisation passes (layout: gx_internal.h, RES_*).
+// A thread block evaluates RES_BLOCK consecutive elements, leaves their 16 residual entries in shared memory and sums
+// them per node there, in a fixed order; only one 32 B partial sum per (block, node shared with another block) goes
+// through global memory instead of the 128 B per element of an element-by-element record (SolInfo ghost R,
+// src/goal_sol_info.cpp:51-64 is what both produce).  Nodes whose elements all sit in one block are written by it.
+// ---------------------------------------------------------------------------
+bool build_residual_schedule(gx_ctx* c) {
+  if (c->res_state != 0) return c->res_state == 1;
+  SetupTimer tm;
+  int const ne = c->ne, nn = c->nn;
+  if (4 * (int64_t)ne >= ((int64_t)1 << 31)) { c->res_state = -1; return false; }  // partial positions are 31 bit
+  int const nb = (ne + RES_BLOCK - 1) / RES_BLOCK;
+  int const T = std::max(1, omp_get_max_threads());
+  c->res_chunks.assign(T, std::vector<uint32_t>());
+  c->res_boff.assign((size_t)nb + 1, 0);
+  std::vector<uint32_t> npart(nn, 0);  // blocks that hold some, not all, elements of the node
+#pragma omp parallel for schedule(static, 1)
+  for (int t = 0; t < T; ++t) {  // chunk t = a contiguous range of blocks, whatever thread runs it
+    int const b0 = (int)((int64_t)nb * t / T), b1 = (int)((int64_t)nb * (t + 1) / T);
+    std::vector<uint32_t>& out = c->res_chunks[t];
+    std::vector<int32_t> stamp(nn, -1);
+    std::vector<uint16_t> slot_of(nn, 0);
+    uint32_t snode[4 * RES_BLOCK], scnt[4 * RES_BLOCK], sfirst[4 * RES_BLOCK];
+    out.reserve((size_t)(b1 - b0) * 512);
+    for (int b = b0; b < b1; ++b) {
+      int const e0 = b * RES_BLOCK, cnt = std::min(RES_BLOCK, ne - e0);
+      int S = 0;
+      for (int i = 0; i < 4 * cnt; ++i) {
+        int32_t const a = c->conn[4 * (size_t)e0 + i];
+        if (stamp[a] != b) { stamp[a] = b; slot_of[a] = (uint16_t)S; snode[S] = (uint32_t)a; scnt[S] = 0; ++S; }
+        ++scnt[slot_of[a]];
+      }
+      uint32_t run = 0;
+      for (int s = 0; s < S; ++s) { sfirst[s] = run; run += scnt[s]; }
+      size_t const base = out.size();
+      uint32_t const nw = (uint32_t)((RES_HDR + 2 * S + (4 * cnt + 1) / 2 + 3) & ~3);
+      out.resize(base + nw, 0u);
+      uint32_t* w = out.data() + base;
+      w[0] = (uint32_t)S; w[1] = nw;
+      uint16_t* ent = reinterpret_cast<uint16_t*>(w + RES_HDR + 2 * S);
+      for (int s = 0; s < S; ++s) {
+        int32_t const a = (int32_t)snode[s];
+        bool const complete = c->adj_off[a + 1] - c->adj_off[a] == scnt[s];
+        w[RES_HDR + 2 * s] = snode[s] | (complete ? 0x80000000u : 0u);
+        w[RES_HDR + 2 * s + 1] = sfirst[s] | (scnt[s] << 16);
+        if (!complete) {
+#pragma omp atomic
+          ++npart[a];
+        }
+        scnt[s] = 0;  // reused as the fill cursor
+      }
+      for (int i = 0; i < 4 * cnt; ++i) {  // ascending (element, local node): ascending elements inside every slot
+        int const s = slot_of[c->conn[4 * (size_t)e0 + i]];
+        int const row = i >> 2, n = i & 3;
+        ent[sfirst[s] + scnt[s]++] = (uint16_t)(8 * row + ((2 * n) ^ (row & 7)));  // 16 B chunk of the kernel's swizzled rows
+      }
+      c->res_boff[b + 1] = nw;  // block sizes; prefix sum below
+    }
+  }
+  uint64_t total_words = 0;
+  for (int b = 0; b < nb; ++b) { total_words += c->res_boff[b + 1]; c->res_boff[b + 1] = (uint32_t)total_words; }
+  if (total_words >= ((uint64_t)1 << 32)) {  // block offsets are 32 bit
+    std::vector<std::vector<uint32_t>>().swap(c->res_chunks);
+    c->res_state = -1;
+    return false;
+  }
+  tm.lap("residual blocks");
+  // nodes finished by the second kernel: shared between blocks, or without any element (their R entries are zero)
+  c->res_pnode.clear();
+  for (int a = 0; a < nn; ++a)
+    if (npart[a] > 0 || c->adj_off[a + 1] == c->adj_off[a]) c->res_pnode.push_back(a);
+  c->res_poff.assign(c->res_pnode.size() + 1, 0);
+  for (size_t i = 0; i < c->res_pnode.size(); ++i) {
+    int32_t const a = c->res_pnode[i];
+    c->res_poff[i + 1] = c->res_poff[i] + npart[a];
+    npart[a] = c->res_poff[i];  // from here on: the node's cursor into the partial buffer
+  }
+  c->res_npartial = c->res_poff.back();
+  // positions in block order: the second kernel adds a node's partial sums in ascending block order
+  for (int t = 0; t < T; ++t) {
+    std::vector<uint32_t>& ch = c->res_chunks[t];
+    for (size_t o = 0; o < ch.size(); o += ch[o + 1]) {
+      int const S = (int)ch[o];
+      for (int s = 0; s < S; ++s) {
+        uint32_t& w0 = ch[o + RES_HDR + 2 * s];
+        if (!(w0 & 0x80000000u)) w0 = npart[w0]++;
+      }
+    }
+  }
+  tm.lap("partial positions");
+  c->res_state = 1;
+  return true;
 }
 
 void pack_host(gx_ctx const* c, HostPack& h) {

@@ -173,7 +173,7 @@ extern "C" int hc_assemble(int model, int pass, int save, int nn, int ne, const 
   P.nodes = hp.nodes.data(); P.z = z.data(); P.conn = hp.conn4.data(); P.bpos = hp.bpos.data(); P.eset = nullptr;
   P.elems = c.perm.data(); P.adj_off = c.adj_off.data(); P.adj = c.adj.data();
   P.state_in = sin.data(); P.state_out = sout.data();
-  P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk; P.pf_dist = 0;
+  P.R = R; P.values = values; P.err = err; P.plastic = &pl; P.e0 = 0; P.e1 = ne; P.nn = nn; P.max_nblk = c.max_nblk; P.pf_dist = 0; P.pf_elems = 0;
   for (int s = 0; s < GX_MAX_ELEM_SETS; ++s) P.mat[s] = c.mats[0];
   int64_t npl = 0;
   using namespace gx;
@@ -384,5 +384,84 @@ extern "C" int hc_patch_gather(int model, int transpose, int nn, int ne, const i
   if (rc) return rc;
   for (int64_t i = 0; i < nnz; ++i) if (values[i] != values[i]) return 16;  // an entry nobody wrote
   for (int i = 0; i < 4 * nn; ++i) if (R[i] != R[i]) return 17;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// CPU replay of the block-reduced residual schedule (build_residual_schedule; elem_residual_block_kernel +
+// node_partial_sum_kernel read it exactly like this): rvec [ne][4][4] are the element residual lines (any numbers),
+// R [4 nn] comes back as their per-node sums.  Every entry of R and of the partial buffer must be written exactly once,
+// every incidence used exactly once.  stats = {blocks, schedule words, partial sums, nodes finished by the second kernel}.
+// ---------------------------------------------------------------------------
+extern "C" int hc_residual_schedule(int nn, int ne, const int32_t* conn, const double* coords, const double* rvec, double* R,
+                                    int64_t* stats) {
+  using namespace gx;
+  gx_ctx c;
+  c.nn = nn; c.ne = ne; c.model = 0; c.nsets = 1;
+  c.conn.assign(conn, conn + 4 * (size_t)ne);
+  c.coords.assign(coords, coords + 3 * (size_t)nn);
+  int rc = build_graph_and_schedule(&c);
+  if (rc) return rc;
+  if (!build_residual_schedule(&c)) return 20;
+  int const nb = (ne + RES_BLOCK - 1) / RES_BLOCK;
+  std::vector<uint32_t> sched;
+  for (auto const& v : c.res_chunks) sched.insert(sched.end(), v.begin(), v.end());
+  if (c.res_boff.size() != (size_t)nb + 1 || c.res_boff[nb] != sched.size()) return 21;
+  stats[0] = nb; stats[1] = (int64_t)sched.size(); stats[2] = c.res_npartial; stats[3] = (int64_t)c.res_pnode.size();
+  std::vector<double> partial(4 * (size_t)std::max<int64_t>(c.res_npartial, 1), std::nan(""));
+  for (int i = 0; i < 4 * nn; ++i) R[i] = std::nan("");
+  std::vector<uint8_t> used(4 * (size_t)ne, 0);
+  for (int b = 0; b < nb; ++b) {
+    uint32_t const* w = sched.data() + c.res_boff[b];
+    int const S = (int)w[0], cnt = std::min(RES_BLOCK, ne - b * RES_BLOCK);
+    if (w[1] != c.res_boff[b + 1] - c.res_boff[b] || (w[1] & 3u) || w[1] > (uint32_t)RES_MAX_WORDS || S > 4 * cnt) return 22;
+    uint16_t const* ent = reinterpret_cast<uint16_t const*>(w + RES_HDR + 2 * S);
+    uint32_t covered = 0;
+    for (int s = 0; s < S; ++s) {
+      uint32_t const w0 = w[RES_HDR + 2 * s], w1 = w[RES_HDR + 2 * s + 1], first = w1 & 0xffffu, n = w1 >> 16;
+      if (first != covered || n == 0) return 23;  // slots tile the entry list
+      covered += n;
+      bool const complete = (w0 & 0x80000000u) != 0;
+      uint32_t const tgt = w0 & 0x7fffffffu;
+      int32_t node = -1;
+      double acc[4] = {0, 0, 0, 0};
+      uint32_t prev = 0;
+      for (uint32_t k = first; k < first + n; ++k) {
+        uint32_t const row = ent[k] >> 3, n2 = (ent[k] & 7u) ^ (row & 7u);  // swizzled chunk -> local element, 2 * local node
+        if (row >= (uint32_t)cnt || (n2 & 1u) || (k > first && row <= prev)) return 24;  // ascending elements inside a slot
+        prev = row;
+        size_t const g = 4 * (size_t)b * RES_BLOCK + 4 * row + (n2 >> 1);  // 4 * element + local node
+        if (used[g]++) return 25;
+        if (node < 0) node = conn[g]; else if (node != conn[g]) return 26;  // one node per slot
+        for (int q = 0; q < 4; ++q) acc[q] += rvec[4 * g + q];
+      }
+      if (complete) {
+        if ((int32_t)tgt != node || (uint32_t)(c.adj_off[node + 1] - c.adj_off[node]) != n) return 27;
+        for (int q = 0; q < 4; ++q) { if (R[4 * (size_t)node + q] == R[4 * (size_t)node + q]) return 28; R[4 * (size_t)node + q] = acc[q]; }
+      } else {
+        if ((int64_t)tgt >= c.res_npartial) return 29;
+        auto it = std::lower_bound(c.res_pnode.begin(), c.res_pnode.end(), node);
+        if (it == c.res_pnode.end() || *it != node) return 30;
+        size_t const pi = it - c.res_pnode.begin();
+        if (tgt < c.res_poff[pi] || tgt >= c.res_poff[pi + 1]) return 31;  // inside the node's run
+        for (int q = 0; q < 4; ++q) { if (partial[4 * (size_t)tgt + q] == partial[4 * (size_t)tgt + q]) return 32; partial[4 * (size_t)tgt + q] = acc[q]; }
+      }
+    }
+    if (covered != 4u * (uint32_t)cnt) return 33;
+  }
+  for (size_t i = 0; i < c.res_pnode.size(); ++i) {
+    int32_t const a = c.res_pnode[i];
+    for (int q = 0; q < 4; ++q) {
+      double acc = 0.0;
+      for (uint32_t p = c.res_poff[i]; p < c.res_poff[i + 1]; ++p) {
+        if (partial[4 * (size_t)p + q] != partial[4 * (size_t)p + q]) return 34;  // a partial sum nobody wrote
+        acc += partial[4 * (size_t)p + q];
+      }
+      if (R[4 * (size_t)a + q] == R[4 * (size_t)a + q]) return 35;
+      R[4 * (size_t)a + q] = acc;
+    }
+  }
+  for (size_t g = 0; g < 4 * (size_t)ne; ++g) if (used[g] != 1) return 36;
+  for (int i = 0; i < 4 * nn; ++i) if (R[i] != R[i]) return 37;
   return 0;
 }

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from conftest import blockerr, relerr
-from goal_b200.synthetic import MATERIAL, fields, kuhn_cube
+from goal_b200.synthetic import MATERIAL, fields, kuhn_block, kuhn_cube
 
 pytestmark = pytest.mark.gpu
 
@@ -84,7 +84,7 @@ def test_jacobian_residual_state_parity(cube, model, mesh):
     a.close()
 
 
-@pytest.mark.parametrize("opts", [dict(), dict(kernel=1)])
+@pytest.mark.parametrize("opts", [dict(), dict(kernel=1), dict(residual_kernel=1)])
 @pytest.mark.parametrize("mesh", ["cube", "kuhn7"])
 def test_kernel_variants_parity(cube, mesh, opts):
     """Both schedules (owner-computes: element records + patch pairs / gather form = default; coloured elements) against
@@ -108,11 +108,45 @@ def test_kernel_variants_parity(cube, mesh, opts):
     R1, A1 = [x.copy() for x in a.jacobian(goal_b200.PRIMAL, save=False)]
     R2, A2 = a.jacobian(goal_b200.PRIMAL, save=False)
     assert np.array_equal(R1, R2) and np.array_equal(A1, A2)  # bit-reproducible
-    # residual and error-localisation passes under the same option (kernel=1: coloured, otherwise gather form)
+    # residual and error-localisation passes under the same option (kernel=1: coloured; residual_kernel=1: element
+    # lines + node gather; default: block-reduced)
     assert relerr(a.residual(save=False), o.residual(save=False)) < 1e-12
+    if not opts:
+        assert a.last_timing()["launches"] == 2  # element blocks + partial sums of the shared nodes
     assert relerr(a.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"]),
                   o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"])) < 1e-12
     a.close()
+
+
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+@pytest.mark.parametrize("form", [0, 1])
+def test_residual_pass_with_state_save(model, form):
+    """Primal::compute_resid (src/goal_primal.cpp:75-90) = the residual pass that also saves the state: R, sigma, eqps and
+    Fp against the oracle under both forms of the pass, on a mesh of 16 element blocks (ragged last block), elastic and
+    plastic elements mixed, twice (bit-identical), and after a shuffle of the element order (no locality: every node is
+    finished by the partial-sum kernel)."""
+    import goal_b200
+    co, cn = kuhn_block(7, 6, 8)
+    for shuffle in (False, True):
+        if shuffle:
+            cn = cn[np.random.default_rng(5).permutation(len(cn))]
+        f = fields(co, len(cn), strain=0.004)
+        a, o = _pair(co, cn, model, f)
+        a.set_option("residual_kernel", form)
+        R1 = a.residual(save=True).copy()
+        Ro = o.residual(save=True)
+        assert relerr(R1, Ro) < 1e-12
+        nodal = np.abs(Ro.reshape(-1, 4)).max(axis=0)  # per component (u rows and p rows differ in scale)
+        assert (np.abs(R1 - Ro).reshape(-1, 4).max(axis=0) < 1e-12 * nodal).all()
+        assert relerr(a.get_state("sigma"), o.state("sigma")) < 1e-10
+        if model == "J2":
+            assert 0 < a.plastic_count() < a.ne and a.plastic_count() == o.plastic_count()
+            assert np.abs(a.get_state("Fp") - o.state("Fp")).max() < 1e-10
+            assert np.abs(a.get_state("eqps") - o.state("eqps")).max() < 1e-10
+        assert np.array_equal(a.residual(save=True), R1)
+        zu, zp, zc = f["zu_diff"], f["zp_diff"], f["zp_coarse"]
+        assert relerr(a.localize(zu, zp, zc), o.localize(zu, zp, zc)) < 1e-12
+        a.close()
 
 
 def _fan(k=9):
