@@ -246,7 +246,10 @@ static_assert(PATCH_RECS <= 256, "record slots are 8 bit");
 #define GX_RES_BLOCK 128
 #endif
 constexpr int RES_BLOCK = GX_RES_BLOCK;  // 64, 128 or 256
-constexpr int RES_MINB = 512 / RES_BLOCK;  // thread blocks per SM the kernel is compiled for
+#ifndef GX_RES_MINB
+#define GX_RES_MINB (512 / GX_RES_BLOCK)
+#endif
+constexpr int RES_MINB = GX_RES_MINB;  // thread blocks per SM the kernel is compiled for (4 x 128 threads x 128 registers)
 constexpr int RES_HDR = 4;
 constexpr int RES_MAX_WORDS = RES_HDR + 2 * 4 * RES_BLOCK + 2 * RES_BLOCK;  // every incidence a slot of its own
 // gx_comm.cu

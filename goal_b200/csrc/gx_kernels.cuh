@@ -316,8 +316,11 @@ __device__ __forceinline__ void prefetch_elements(KParams const& P, int ep, int 
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(P.state_in + (int64_t)STATE_IN * ep), "r"(n * (uint32_t)(STATE_IN * 8)) : "memory");
 }
 
+#ifndef GX_ELEM_MINB
+#define GX_ELEM_MINB 8
+#endif
 template <int MODEL, bool SAVE>
-__global__ void __launch_bounds__(64, 8) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
+__global__ void __launch_bounds__(64, GX_ELEM_MINB) elem_record_kernel(const __grid_constant__ KParams P, double* __restrict__ rec, int ne) {
   // A warp's 32 records are contiguous in global memory (9.5 KB): the threads put them into shared memory (record
   // stride 19 x 16 B, odd: conflict-free 128-bit stores) and one bulk asynchronous copy writes the block -- no
   // per-thread stride-304 B stores, no copy loop through the LSU.  The Fp update reuses the buffer afterwards.
@@ -770,6 +773,12 @@ __global__ void __launch_bounds__(RES_BLOCK, RES_MINB) elem_residual_block_kerne
       wsave_finish(P, e0, nrec, lane, pmask, plastic, dN, v, sbuf[wib]);
     }
   }
+  if (MODEL == MODEL_J2) {
+    unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
+    if (lane == 0 && b) atomicAdd(P.plastic, (unsigned long long)__popc(b));
+  }
+  // Block barrier, then all warps share the reduction.  (Measured alternative: the last warp to arrive reduces alone
+  // and the others leave -- 1.37 instead of 1.09 ms, the lone warp's six serial rounds hold the block's resources.)
   __syncthreads();
   {
     uint32_t done;
@@ -784,17 +793,19 @@ __global__ void __launch_bounds__(RES_BLOCK, RES_MINB) elem_residual_block_kerne
     int const s = item >> 1, h = item & 1;
     uint32_t const w0 = ssched[RES_HDR + 2 * s], w1 = ssched[RES_HDR + 2 * s + 1];
     uint32_t const first = w1 & 0xffffu, cnt = w1 >> 16;
-    double2 acc = make_double2(0.0, 0.0);
-    for (uint32_t k = first; k < first + cnt; ++k) {
-      double2 const v = sv[(uint32_t)ent[k] ^ (uint32_t)h];  // the entry is the (swizzled) chunk of the node's first half
-      acc.x += v.x; acc.y += v.y;
+    // the entry is the (swizzled) chunk of the node's first half.  Two independent chains (even / odd entries), added
+    // at the end: a fixed order, half the dependent shared-memory latency
+    double2 acc = make_double2(0.0, 0.0), acc1 = make_double2(0.0, 0.0);
+    uint32_t k = first;
+    uint32_t const end = first + cnt;
+    for (; k + 1 < end; k += 2) {
+      double2 const v0 = sv[(uint32_t)ent[k] ^ (uint32_t)h], v1 = sv[(uint32_t)ent[k + 1] ^ (uint32_t)h];
+      acc.x += v0.x; acc.y += v0.y; acc1.x += v1.x; acc1.y += v1.y;
     }
+    if (k < end) { double2 const v0 = sv[(uint32_t)ent[k] ^ (uint32_t)h]; acc.x += v0.x; acc.y += v0.y; }
+    acc.x += acc1.x; acc.y += acc1.y;
     double* dst = (w0 & 0x80000000u) ? P.R : partial;
     *reinterpret_cast<double2*>(dst + 4 * (int64_t)(w0 & 0x7fffffffu) + 2 * h) = acc;
-  }
-  if (MODEL == MODEL_J2) {
-    unsigned const b = __ballot_sync(0xffffffffu, plastic != 0);
-    if (lane == 0 && b) atomicAdd(P.plastic, (unsigned long long)__popc(b));
   }
 }
 

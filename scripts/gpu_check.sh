@@ -20,7 +20,7 @@ echo "== ncu full (both kernels of the Jacobian pass, then the residual / locali
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:"patch_pair_kernel|elem_record_kernel" -s 2 -c 2 -f -o $OUT/${TAG}_prof \
   python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu-baseline --no-sizes --no-passes --no-checks > $OUT/${TAG}_ncu_full.log 2>&1
 tail -1 $OUT/${TAG}_ncu_full.log | cut -c1-120
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"elem_residual_kernel|node_gather_kernel" -s 2 -c 2 -f -o $OUT/${TAG}_prof_res \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"elem_residual_block_kernel|node_partial_sum_kernel" -s 2 -c 2 -f -o $OUT/${TAG}_prof_res \
   python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu-baseline --no-sizes --no-checks > $OUT/${TAG}_ncu_full_res.log 2>&1
 tail -1 $OUT/${TAG}_ncu_full_res.log | cut -c1-120
 ls -la $OUT | grep ${TAG}
