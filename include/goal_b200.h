@@ -269,6 +269,16 @@ int gx_last_timing(gx_ctx* ctx, double t[4]);
 /* t[1] of gx_last_timing split at the boundary between the element kernel (t[0]: stress update, state save, element
  * records) and the kernels that gather the records into R / the CRS values (t[1]); {t[1], 0} for a one-kernel pass */
 int gx_last_stage_timing(gx_ctx* ctx, double t[2]);
+/* Tuning / cross-check switches (defaults in brackets; everything else is GX_ERR_ARG):
+ *   "kernel"                 [0] owner-computes schedules; 1 = coloured element schedule for every pass (fallback, cross-check)
+ *   "residual_kernel"        [0] block-reduced residual / localisation passes; 1 = element lines + node gather
+ *   "overlap"                [0] 1 = R, 2 = dRdu, 3 = both: the Jacobian pass reduces the interfaces itself, hidden
+ *                            behind the interior patches (== SolInfo::gather_R / gather_dRdu, goal_sol_info.cpp:33-43)
+ *   "prefetch"               [256] stage B: L2 prefetch distance in patches (0 = off)
+ *   "prefetch_elems"         [18944] element kernels of passes that save the state: L2 prefetch distance in elements
+ *   "prefetch_elems_nosave"  [151552] the same for passes that do not save
+ *   "block_size"             [128] threads per block of the coloured schedule
+ *   "patch_schedule_dryrun"  builds the patch schedule on the host only (works on host-only contexts) */
 int gx_set_option(gx_ctx* ctx, const char* key, int64_t value);
 /* The work list of the patch-gather Jacobian pass as the device reads it (layout: goal_b200/csrc/gx_setup.cpp,
  * build_patch_schedule); dims = {patches, words per patch, record slots per patch, threads per patch}.  Valid until
