@@ -701,7 +701,7 @@ int gx_create(const gx_desc* d, gx_ctx** out) {
     GX_CUDA(cudaEventCreate(&ctx->ev_stage));
     tm.lap("CUDA context");
     int const nn = ctx->nn, ne = ctx->ne;
-    // ---- nodes and elements (device element order = colour-sorted)
+    // ---- nodes and elements (user element order)
     {  // node records; conn (int32 x 4) and the scatter map (uint8 x 16) already have the device layout
       std::vector<NodeRec> nodes(nn);
 #pragma omp parallel for schedule(static)

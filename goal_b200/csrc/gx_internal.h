@@ -89,7 +89,7 @@ struct gx_ctx {
   std::vector<int32_t> node_order;
   std::vector<uint8_t> diag_pos;  // position of block (a,a) in node a's block row
   bool block_lists_built = false;
-  // ---- patch schedule of the patch-gather Jacobian pass (kernel = 3), see build_patch_schedule()
+  // ---- patch schedule of the Jacobian pass (stage B, patch_pair_kernel), see build_patch_schedule()
   std::vector<uint32_t> patch_sched;                  // flat (flatten_patch_schedule), or empty while ...
   std::vector<std::vector<uint32_t>> patch_chunks;    // ... the builder's chunks are still waiting for the upload
   int n_patches = 0;
@@ -203,7 +203,7 @@ struct SetupTimer {  // GX_SETUP_TIMING=1 prints the wall time of every setup se
 int build_graph_and_schedule(gx_ctx* c);
 int build_colouring(gx_ctx* c);  // lazily: only the coloured fallback needs it
 void materialise_crs(gx_ctx* c);
-// host images of the device arrays, in device (colour-sorted) element order
+// host images of the device arrays (user element order; the colour schedule indexes them through perm)
 struct HostPack {
   std::vector<NodeRec> nodes;
   std::vector<int4> conn4;   // user element order

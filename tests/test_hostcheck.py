@@ -223,7 +223,7 @@ def test_whole_mesh_emulation_matches_oracle(hostcheck, cube, model, mesh):
 @pytest.mark.parametrize("mesh", ["cube", "kuhn5"])
 def test_patch_gather_replay_matches_oracle(hostcheck, cube, model, mesh):
     """The default GPU schedule of the Jacobian pass, replayed on the CPU: the patch schedule built by the product's
-    host code and interpreted like patch_gather_kernel (record slots from the bulk-copy runs, work items, partial
+    host code and interpreted like patch_pair_kernel (record slots from the bulk-copy runs, work items, partial
     sums, one writer per block) with the device's element math -> the oracle's operator, primal and transposed."""
     co, cn = (cube["coords"], cube["tets"]) if mesh == "cube" else kuhn_cube(5)
     co, cn = np.ascontiguousarray(co, dtype=np.float64), np.ascontiguousarray(cn, dtype=np.int32)
