@@ -9,8 +9,8 @@
 //                          gathers 4 records = 4 aligned 64 B segments (4 LDG.128 each)
 //   conn      int4[Ne]     one 128-bit load per element
 //   bpos      uint4[Ne]    element -> nonzero scatter map, 16 x uint8 block positions
-//   adj       int2[4 Ne]   node -> (element, local node) incidences + the 4 block positions that
-//                          incidence writes, grouped by node (adj_off[Nn+1]); the row-owner work list
+//   adj       int2[4 Ne]   node -> (element, local node) incidences, grouped by node (adj_off[Nn+1]): work list of the
+//                          element-line gather (node_gather_kernel) and of the host-side schedule builders
 //   state_in  double[Ne][10]  Fp_old[9], eqps_old                             80 B record (5 LDG.128); Cp^{-1} is
 //                             formed in registers (cp_inverse): the old state is read once per element and pass
 //   state_out double[Ne][20]  sigma[9], eqps, Fp[9], pad                     160 B record
@@ -22,8 +22,11 @@
 //      of nodes: the patch's records staged in shared memory by bulk copies, one work item per thread -- an edge's two
 //      mirror blocks or a diagonal block with the node's residual entries -- accumulated in registers and written once).
 //      No zeroing pass, no read-modify-write traffic.
-//  (2) gather form of the residual / error-localisation passes (default): element residual vectors, then 8 lanes
-//      per node sum its incidences.
+//  (2) residual / error-localisation passes (default): block-reduced -- elem_residual_block_kernel keeps the residual
+//      lines of 128 consecutive elements in shared memory, sums them per node there and writes R or one 32 B partial
+//      sum per node shared with other blocks; node_partial_sum_kernel adds those.  The element-line form
+//      (elem_residual_kernel + node_gather_kernel: a 128 B line per element through global memory, 8 lanes per node
+//      sum its incidences) remains as gx_set_option("residual_kernel", 1) and carries the functionals' dMdu.
 //  (3) coloured elements (fallback for every pass, gx_set_option("kernel", 1), and for meshes with a node that does
 //      not fit a patch): one thread per element, launches cover one colour (no two elements of a colour share a
 //      node), plain read-modify-write into R / values.
