@@ -60,3 +60,25 @@ def test_single_part_tpetra_view_is_the_ghost_graph(gxlib):
     tp = a.owned_tpetra_graph()
     assert tp["n_owned"] == len(co) and np.array_equal(tp["colmap"], np.arange(len(co)))
     assert np.array_equal(tp["rowptr"], a.rowptr) and np.array_equal(tp["colind"], a.colind)
+
+
+def test_option_keys_of_the_header_are_the_ones_the_library_takes(gxlib):
+    """include/goal_b200.h lists the gx_set_option keys with their defaults: every listed key is accepted with its
+    default, out-of-range values and unknown keys are GX_ERR_ARG with a message (no silent ignore)."""
+    import re
+    import pytest
+    import goal_b200
+    from goal_b200.synthetic import MATERIAL, kuhn_cube
+    hdr = open(os.path.join(ROOT, "include", "goal_b200.h")).read()
+    block = hdr[hdr.index("Tuning / cross-check switches"):hdr.index("int gx_set_option")]
+    keys = dict(re.findall(r'"(\w+)"\s+\[(\d+)\]', block))
+    assert set(keys) == {"kernel", "residual_kernel", "overlap", "prefetch", "prefetch_elems", "prefetch_elems_nosave", "block_size"}
+    co, cn = kuhn_cube(2)
+    a = goal_b200.Assembler(co, cn, "J2", [MATERIAL], device=-1)
+    for k, v in keys.items():
+        a.set_option(k, int(v))
+    a.set_option("patch_schedule_dryrun", 1)
+    for k, bad in [("kernel", 2), ("residual_kernel", 2), ("overlap", 4), ("prefetch", -1), ("prefetch_elems", -1), ("block_size", 100), ("no_such_key", 0)]:
+        with pytest.raises(RuntimeError, match="GX_ERR_ARG"):
+            a.set_option(k, bad)
+    a.close()
