@@ -237,6 +237,12 @@ inline void set_tbcs(Disc* d, std::vector<LO> const& side_nodes, std::vector<dou
 inline void set_ibcs(Disc* d, std::vector<LO> const& side_nodes, double scale, double const center[3]) {
   if (gx_apply_ibcs(d->ctx, (LO)(side_nodes.size() / 3), side_nodes.data(), scale, center)) fail(gx_last_error(d->ctx));
 }
+// BForce<T>::at_point behind MResidual (src/goal_bforce.cpp:58-68, goal_mechanics.cpp:132-136; error chain :204-208):
+// b = the body-force expression at every element's integration point, [n_elems * 3]
+inline void set_bforce(Disc* d, std::vector<double> const& b, bool error_weights = false) {
+  if (b.size() != 3 * (size_t)d->get_num_elems()) fail("set_bforce: one force vector per element expected");
+  if (gx_apply_bforce(d->ctx, b.data(), error_weights ? 1 : 0)) fail(gx_last_error(d->ctx));
+}
 inline void set_resid_dbcs(Disc* d, std::vector<LO> const& rows, std::vector<double> const& g) {
   if (gx_apply_dbcs(d->ctx, (LO)rows.size(), rows.data(), g.data(), 0)) fail(gx_last_error(d->ctx));
 }
