@@ -393,21 +393,16 @@ extern "C" int hc_patch_gather(int model, int transpose, int nn, int ne, const i
 // R [4 nn] comes back as their per-node sums.  Every entry of R and of the partial buffer must be written exactly once,
 // every incidence used exactly once.  stats = {blocks, schedule words, partial sums, nodes finished by the second kernel}.
 // ---------------------------------------------------------------------------
-extern "C" int hc_residual_schedule(int nn, int ne, const int32_t* conn, const double* coords, const double* rvec, double* R,
-                                    int64_t* stats) {
+static int replay_residual_schedule(gx_ctx& c, const double* rvec, double* R, int64_t* stats) {
   using namespace gx;
-  gx_ctx c;
-  c.nn = nn; c.ne = ne; c.model = 0; c.nsets = 1;
-  c.conn.assign(conn, conn + 4 * (size_t)ne);
-  c.coords.assign(coords, coords + 3 * (size_t)nn);
-  int rc = build_graph_and_schedule(&c);
-  if (rc) return rc;
+  int const nn = c.nn, ne = c.ne;
+  int32_t const* conn = c.conn.data();
   if (!build_residual_schedule(&c)) return 20;
   int const nb = (ne + RES_BLOCK - 1) / RES_BLOCK;
   std::vector<uint32_t> sched;
   for (auto const& v : c.res_chunks) sched.insert(sched.end(), v.begin(), v.end());
   if (c.res_boff.size() != (size_t)nb + 1 || c.res_boff[nb] != sched.size()) return 21;
-  stats[0] = nb; stats[1] = (int64_t)sched.size(); stats[2] = c.res_npartial; stats[3] = (int64_t)c.res_pnode.size();
+  if (stats) { stats[0] = nb; stats[1] = (int64_t)sched.size(); stats[2] = c.res_npartial; stats[3] = (int64_t)c.res_pnode.size(); }
   std::vector<double> partial(4 * (size_t)std::max<int64_t>(c.res_npartial, 1), std::nan(""));
   for (int i = 0; i < 4 * nn; ++i) R[i] = std::nan("");
   std::vector<uint8_t> used(4 * (size_t)ne, 0);
@@ -464,4 +459,50 @@ extern "C" int hc_residual_schedule(int nn, int ne, const int32_t* conn, const d
   for (size_t g = 0; g < 4 * (size_t)ne; ++g) if (used[g] != 1) return 36;
   for (int i = 0; i < 4 * nn; ++i) if (R[i] != R[i]) return 37;
   return 0;
+}
+
+extern "C" int hc_residual_schedule(int nn, int ne, const int32_t* conn, const double* coords, const double* rvec, double* R,
+                                    int64_t* stats) {
+  gx_ctx c;
+  c.nn = nn; c.ne = ne; c.model = 0; c.nsets = 1;
+  c.conn.assign(conn, conn + 4 * (size_t)ne);
+  c.coords.assign(coords, coords + 3 * (size_t)nn);
+  int rc = gx::build_graph_and_schedule(&c);
+  if (rc) return rc;
+  return replay_residual_schedule(c, rvec, R, stats);
+}
+
+// The whole block-reduced residual / error-localisation pass on the CPU: the element residual lines from the device's
+// own element code (element_core + element_residual, or element_error_residual with the adjoint weights z5 =
+// [nn][zu(3), zp, zpc]), summed through the schedule exactly as the two kernels do.
+extern "C" int hc_residual_blocks(int model, int nn, int ne, const int32_t* conn, const double* coords, const double* mat5,
+                                  const double* u, const double* p, const double* z5, const double* eqps_old,
+                                  const double* Fp_old, double* R) {
+  gx_ctx c;
+  c.nn = nn; c.ne = ne; c.model = model; c.nsets = 1;
+  c.conn.assign(conn, conn + 4 * (size_t)ne);
+  c.coords.assign(coords, coords + 3 * (size_t)nn);
+  gx::Material const mat = gx::make_material(mat5[0], mat5[1], mat5[2], mat5[3], mat5[4]);
+  int rc = gx::build_graph_and_schedule(&c);
+  if (rc) return rc;
+  std::vector<double> rvec(16 * (size_t)ne);
+  for (int e = 0; e < ne; ++e) {
+    double X[4][3], U[4][3], P4[4], Cp[6], sg[9], eq, zu[4][3], zp[4], zpc[4];
+    for (int n = 0; n < 4; ++n) {
+      int const a = conn[4 * (size_t)e + n];
+      for (int j = 0; j < 3; ++j) { X[n][j] = coords[3 * (size_t)a + j]; U[n][j] = u[3 * (size_t)a + j]; }
+      P4[n] = p[a];
+      if (z5) { for (int j = 0; j < 3; ++j) zu[n][j] = z5[5 * (size_t)a + j]; zp[n] = z5[5 * (size_t)a + 3]; zpc[n] = z5[5 * (size_t)a + 4]; }
+    }
+    if (model == 1) gx::cp_inverse(Fp_old + 9 * (size_t)e, Cp);
+    gx::Core<double> core;
+    rc = model == 0 ? gx::element_core<gx::MODEL_NEOHOOKEAN>(X, U, P4, mat, Cp, 0.0, false, sg, eq, core)
+                    : gx::element_core<gx::MODEL_J2>(X, U, P4, mat, Cp, eqps_old[e], false, sg, eq, core);
+    if (rc) return rc;
+    double ru[12], rp[4];
+    if (z5) gx::element_error_residual(core, zu, zp, zpc, ru, rp);
+    else gx::element_residual(core, ru, rp);
+    for (int n = 0; n < 4; ++n) { for (int i = 0; i < 3; ++i) rvec[16 * (size_t)e + 4 * n + i] = ru[3 * n + i]; rvec[16 * (size_t)e + 4 * n + 3] = rp[n]; }
+  }
+  return replay_residual_schedule(c, rvec.data(), R, nullptr);
 }

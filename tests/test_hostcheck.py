@@ -246,3 +246,35 @@ def test_patch_gather_replay_matches_oracle(hostcheck, cube, model, mesh):
         be = blockerr(o.csr(A).toarray(), o.csr(Ao).toarray())
         print(f"per-block relative error {model} {mesh} mode {tr}: {be:.2e}")
         assert be < 1e-11  # every 4x4 block on its own scale (relerr is norm-wise)
+
+
+@pytest.mark.parametrize("model", ["neohookean", "J2"])
+@pytest.mark.parametrize("mesh", ["cube", "kuhn5"])
+def test_block_reduced_residual_replay_matches_oracle(hostcheck, cube, model, mesh):
+    """The default GPU schedule of the residual and error-localisation passes, replayed on the CPU: the element lines
+    from the device's element code, summed through the block schedule built by the product's host code and read like
+    elem_residual_block_kernel + node_partial_sum_kernel do (slots, pre-swizzled chunk entries, partial sums in block
+    order, one writer per entry) -> the oracle's residual (Primal::compute_resid, src/goal_primal.cpp:75-90) and its
+    localised error residual (NestedAdjoint::localize, src/goal_nested_adjoint.cpp:217-234)."""
+    co, cn = (cube["coords"], cube["tets"]) if mesh == "cube" else kuhn_cube(5)
+    co, cn = np.ascontiguousarray(co, dtype=np.float64), np.ascontiguousarray(cn, dtype=np.int32)
+    f = fields(co, len(cn), strain=0.004)
+    o = Oracle(co, cn, model, [MATERIAL])
+    o.set_solution(f["u"], f["p"])
+    if model == "J2":
+        o.state("Fp_old")[:] = f["Fp_old"]
+        o.state("eqps_old")[:] = f["eqps_old"]
+    mat = np.array(MATERIAL)
+    u, p = np.ascontiguousarray(f["u"]), np.ascontiguousarray(f["p"])
+    eqo, Fpo = np.ascontiguousarray(f["eqps_old"]), np.ascontiguousarray(f["Fp_old"])
+    z5 = np.ascontiguousarray(np.concatenate([f["zu_diff"], f["zp_diff"][:, None], f["zp_coarse"][:, None]], axis=1))
+    m = 0 if model == "neohookean" else 1
+    hostcheck.hc_residual_blocks.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)] + [C.POINTER(C.c_double)] * 8
+    for z, want in ((None, o.residual(save=False).copy()), (z5, o.localize(f["zu_diff"], f["zp_diff"], f["zp_coarse"]).copy())):
+        R = np.zeros(4 * len(co))
+        rc = hostcheck.hc_residual_blocks(m, len(co), len(cn), ip(cn), dp(co), dp(mat), dp(u), dp(p), dp(z) if z is not None else None,
+                                          dp(eqo), dp(Fpo), dp(R))
+        assert rc == 0
+        assert relerr(R, want) < 1e-12
+        comp = np.abs(want.reshape(-1, 4)).max(axis=0)  # u rows and p rows on their own scales
+        assert (np.abs(R - want).reshape(-1, 4).max(axis=0) < 1e-12 * comp).all()
