@@ -20,8 +20,10 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <memory>
 #include <numeric>
 #include <omp.h>
+#include <parallel/algorithm>
 
 #include "gx_internal.h"
 
@@ -31,26 +33,56 @@ int build_graph_and_schedule(gx_ctx* c) {
   SetupTimer tm;
   int const nn = c->nn, ne = c->ne;
   int32_t const* conn = c->conn.data();
-  for (int64_t i = 0; i < 4 * (int64_t)ne; ++i)
-    if (conn[i] < 0 || conn[i] >= nn) { c->err = "conn entry out of range"; return GX_ERR_ARG; }
-  for (int e = 0; e < ne; ++e) {
-    int32_t const* en = conn + 4 * (int64_t)e;
-    if (en[0] == en[1] || en[0] == en[2] || en[0] == en[3] || en[1] == en[2] || en[1] == en[3] || en[2] == en[3]) {
-      c->err = "element " + std::to_string(e) + " repeats a node"; return GX_ERR_ARG;
+  {
+    int64_t const none = INT64_MAX;
+    int64_t bad_range = none, bad_rep = none;  // first offending element of either kind (deterministic: min over threads)
+#pragma omp parallel for schedule(static) reduction(min : bad_range, bad_rep)
+    for (int e = 0; e < ne; ++e) {
+      int32_t const* en = conn + 4 * (int64_t)e;
+      bool const out = en[0] < 0 || en[0] >= nn || en[1] < 0 || en[1] >= nn || en[2] < 0 || en[2] >= nn || en[3] < 0 || en[3] >= nn;
+      bool const rep = en[0] == en[1] || en[0] == en[2] || en[0] == en[3] || en[1] == en[2] || en[1] == en[3] || en[2] == en[3];
+      if (out) bad_range = std::min<int64_t>(bad_range, e);
+      if (rep) bad_rep = std::min<int64_t>(bad_rep, e);
     }
+    if (bad_range != none) { c->err = "conn entry out of range"; return GX_ERR_ARG; }
+    if (bad_rep != none) { c->err = "element " + std::to_string(bad_rep) + " repeats a node"; return GX_ERR_ARG; }
   }
   if ((int64_t)ne >= (1ll << 29)) { c->err = "more than 2^29 elements per part"; return GX_ERR_UNSUPPORTED; }
 
   tm.lap("validate");
-  // ---- node -> elements (counting sort)
+  // ---- node -> elements (counting sort, elements ascending per node).  Parallel over contiguous element chunks with one
+  //      histogram per chunk: chunk t's entries of a node go behind those of the chunks before it, so the result is
+  //      the serial one whatever the number of chunks (which is capped to keep the histograms below 256 MB).
   std::vector<int64_t> n2e_off(nn + 1, 0);
-  for (int64_t i = 0; i < 4 * (int64_t)ne; ++i) n2e_off[conn[i] + 1]++;
-  for (int n = 0; n < nn; ++n) n2e_off[n + 1] += n2e_off[n];
-  std::vector<int32_t> n2e(n2e_off[nn]);
+  std::vector<int32_t> n2e(4 * (size_t)ne);
   {
-    std::vector<int64_t> cur(n2e_off.begin(), n2e_off.end() - 1);
-    for (int e = 0; e < ne; ++e)
-      for (int a = 0; a < 4; ++a) n2e[cur[conn[4 * (int64_t)e + a]]++] = e;
+    int const Tc = (int)std::max<int64_t>(1, std::min<int64_t>(omp_get_max_threads(), ((int64_t)64 << 20) / std::max(nn, 1)));
+    std::unique_ptr<uint32_t[]> hist(new uint32_t[(size_t)Tc * nn]);
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < Tc; ++t) {
+      uint32_t* h = hist.get() + (size_t)t * nn;
+      memset(h, 0, sizeof(uint32_t) * (size_t)nn);
+      int64_t const i0 = 4 * ((int64_t)ne * t / Tc), i1 = 4 * ((int64_t)ne * (t + 1) / Tc);
+      for (int64_t i = i0; i < i1; ++i) h[conn[i]]++;
+    }
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < nn; ++n) {
+      int64_t tot = 0;
+      for (int t = 0; t < Tc; ++t) tot += hist[(size_t)t * nn + n];
+      n2e_off[n + 1] = tot;
+    }
+    for (int n = 0; n < nn; ++n) n2e_off[n + 1] += n2e_off[n];
+#pragma omp parallel for schedule(static)
+    for (int n = 0; n < nn; ++n) {  // counts -> start positions (fits 32 bits: 4 ne < 2^31)
+      uint32_t off = (uint32_t)n2e_off[n];
+      for (int t = 0; t < Tc; ++t) { uint32_t const k = hist[(size_t)t * nn + n]; hist[(size_t)t * nn + n] = off; off += k; }
+    }
+#pragma omp parallel for schedule(static, 1)
+    for (int t = 0; t < Tc; ++t) {
+      uint32_t* h = hist.get() + (size_t)t * nn;
+      int64_t const i0 = 4 * ((int64_t)ne * t / Tc), i1 = 4 * ((int64_t)ne * (t + 1) / Tc);
+      for (int64_t i = i0; i < i1; ++i) n2e[h[conn[i]]++] = (int32_t)(i >> 2);
+    }
   }
 
   tm.lap("node->elements");
@@ -102,32 +134,34 @@ int build_graph_and_schedule(gx_ctx* c) {
     }
   }
   tm.lap("node adjacency");
-  // ---- scatter map: position of block (a_n, a_m) in a_n's block row
+  // ---- scatter map: position of block (a_n, a_m) in a_n's block row, and the node -> (element, local node) incidences.
+  //      One pass over the nodes: pos[b] = position of b in the current row (every node of an element incident to a is
+  //      in a's row), so a block position is an array read instead of a binary search.  The four bytes of (e, n) are
+  //      written by the thread that owns node a_n: distinct bytes, no two threads write the same one.
   c->bpos.resize(16 * (size_t)ne);
-#pragma omp parallel for schedule(static)
-  for (int e = 0; e < ne; ++e) {
-    int32_t const* en = conn + 4 * (int64_t)e;
-    for (int n = 0; n < 4; ++n) {
-      int32_t const* b = c->ncol.data() + c->nrow[en[n]];
-      int32_t const* end = c->ncol.data() + c->nrow[en[n] + 1];
-      for (int m = 0; m < 4; ++m) c->bpos[16 * (size_t)e + 4 * n + m] = (uint8_t)(std::lower_bound(b, end, en[m]) - b);
-    }
-  }
-
+  c->adj.resize(n2e.size());
   c->max_nblk = 0;
   for (int n = 0; n < nn; ++n) c->max_nblk = std::max<int>(c->max_nblk, (int)(c->nrow[n + 1] - c->nrow[n]));
-  c->adj.resize(n2e.size());
-#pragma omp parallel for schedule(static)
-  for (int a = 0; a < nn; ++a)
-    for (int64_t k = n2e_off[a]; k < n2e_off[a + 1]; ++k) {
-      int const e = n2e[k];
-      int32_t const* en = conn + 4 * (int64_t)e;
-      int n = 0;
-      while (en[n] != a) ++n;
-      uint8_t const* b = &c->bpos[16 * (size_t)e + 4 * n];
-      c->adj[k].x = e * 4 + n;
-      c->adj[k].y = (int)((uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24));
+#pragma omp parallel
+  {
+    std::vector<uint8_t> pos(nn, 0);
+#pragma omp for schedule(dynamic, 4096)
+    for (int a = 0; a < nn; ++a) {
+      int32_t const* b = c->ncol.data() + c->nrow[a];
+      int const nb = (int)(c->nrow[a + 1] - c->nrow[a]);
+      for (int j = 0; j < nb; ++j) pos[b[j]] = (uint8_t)j;
+      for (int64_t k = n2e_off[a]; k < n2e_off[a + 1]; ++k) {
+        int const e = n2e[k];
+        int32_t const* en = conn + 4 * (int64_t)e;
+        int n = 0;
+        while (en[n] != a) ++n;
+        uint8_t* d = &c->bpos[16 * (size_t)e + 4 * n];
+        for (int m = 0; m < 4; ++m) d[m] = pos[en[m]];
+        c->adj[k].x = e * 4 + n;
+        c->adj[k].y = (int)((uint32_t)d[0] | ((uint32_t)d[1] << 8) | ((uint32_t)d[2] << 16) | ((uint32_t)d[3] << 24));
+      }
     }
+  }
 
   tm.lap("scatter map + incidences");
   // ---- diagonal block position per node (Dirichlet rows put their 1 there)
@@ -166,7 +200,7 @@ int build_graph_and_schedule(gx_ctx* c) {
       }
       key[a] = (code << 32) | (uint32_t)a;
     }
-    std::sort(key.begin(), key.end());
+    __gnu_parallel::sort(key.begin(), key.end());  // keys are unique (node id in the low word): the order is the serial one
     c->node_order.resize(nn);
     for (int a = 0; a < nn; ++a) c->node_order[a] = (int32_t)(key[a] & 0xffffffffu);
   }

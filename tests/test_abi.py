@@ -82,3 +82,22 @@ def test_option_keys_of_the_header_are_the_ones_the_library_takes(gxlib):
         with pytest.raises(RuntimeError, match="GX_ERR_ARG"):
             a.set_option(k, bad)
     a.close()
+
+
+def test_invalid_connectivity_is_rejected_with_the_first_offender(gxlib):
+    """gx_create validates the connectivity before anything is built: an out-of-range node id, or an element that
+    lists a node twice (the message names the first such element -- the check runs in parallel and must stay deterministic)."""
+    import goal_b200
+    from goal_b200.synthetic import MATERIAL, kuhn_cube
+    co, cn = kuhn_cube(6)
+    bad = cn.copy(); bad[700, 2] = len(co)
+    with pytest.raises(RuntimeError, match="out of range"):
+        goal_b200.Assembler(co, bad, "J2", [MATERIAL], device=-1)
+    bad = cn.copy(); bad[5, 0] = -1
+    with pytest.raises(RuntimeError, match="out of range"):
+        goal_b200.Assembler(co, bad, "J2", [MATERIAL], device=-1)
+    bad = cn.copy()
+    for e in (1200, 333, 901):
+        bad[e, 3] = bad[e, 1]
+    with pytest.raises(RuntimeError, match="element 333 repeats a node"):
+        goal_b200.Assembler(co, bad, "J2", [MATERIAL], device=-1)
