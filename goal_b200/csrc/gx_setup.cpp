@@ -434,12 +434,8 @@ bool build_patch_schedule(gx_ctx* c) {
         for (size_t t = ((size_t)Q / 4) * 32; t < std::min(ord.size(), ((size_t)Q / 4) * 32 + 32); ++t) R = std::max(R, items[ord[t]].n);
         qcap[Q] = R;
       }
-      // cost of giving record l the bank group r: readers already there, and heavily, readers beyond the rounds
-      auto conflicts = [&](int l, int r) {
-        int c2 = 0;
-        for (int k = feed_off[l]; k < feed_off[l + 1]; ++k) { int const Q = feed_q[k]; c2 += qload[Q][r] + (qload[Q][r] >= qcap[Q] ? 16 : 0); }
-        return c2;
-      };
+      // cost of giving record l the bank group r (computed below for all eight r at once): readers already there, and
+      // heavily (+16 each), readers beyond the rounds of their warp
       auto place = [&](int l, int r) {
         res[l] = r;
         for (int k = feed_off[l]; k < feed_off[l + 1]; ++k) qload[feed_q[k]][r]++;
@@ -460,23 +456,36 @@ bool build_patch_schedule(gx_ctx* c) {
         }
         std::stable_sort(runs.begin(), runs.end(), [](Run const& a, Run const& b) { return a.len > b.len; });
         bool taken[PATCH_RECS] = {};
+        int free_len[PATCH_RECS + 1];  // free slots in a row starting at s
+        for (int s0 = 0; s0 <= PATCH_RECS; ++s0) free_len[s0] = PATCH_RECS - s0;
         for (size_t ri = 0; ri < runs.size(); ++ri) {
           Run const run = runs[ri];
           // the cost of a position depends on its residue modulo 8 only: rate the eight residues, then take the
           // first free position of the best residue that has one
-          int rcost[8];
-          for (int r0 = 0; r0 < 8; ++r0) {
-            rcost[r0] = 0;
-            for (int j = 0; j < run.len; ++j) rcost[r0] += conflicts(byel[run.first + j], (r0 + j) & 7);
+          int rcost[8] = {};
+          for (int j = 0; j < run.len; ++j) {
+            int const l = byel[run.first + j];
+            int cl[8] = {};  // conflicts(l, r) for the eight bank groups at once
+            for (int k = feed_off[l]; k < feed_off[l + 1]; ++k) {
+              int const Q = feed_q[k], cap = qcap[Q];
+              for (int r = 0; r < 8; ++r) cl[r] += qload[Q][r] + (qload[Q][r] >= cap ? 16 : 0);
+            }
+            for (int r0 = 0; r0 < 8; ++r0) rcost[r0] += cl[(r0 + j) & 7];
           }
-          int best = -1, best_cost = 1 << 30;
-          for (int s0 = 0; s0 + run.len <= PATCH_RECS; ++s0) {
-            if (rcost[s0 & 7] >= best_cost) continue;
-            bool free_ = true;
-            for (int j = 0; j < run.len && free_; ++j) free_ = !taken[s0 + j];
-            if (!free_) continue;
-            best_cost = rcost[s0 & 7]; best = s0;
-            if (best_cost == 0) break;
+          // = the feasible position with the smallest (cost of its residue, slot): residues in order of cost, and among
+          // residues of equal cost the one whose first free position comes first
+          int best = -1;
+          {
+            int byc[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+            std::stable_sort(byc, byc + 8, [&](int x, int y) { return rcost[x] < rcost[y]; });
+            for (int g = 0; g < 8 && best < 0;) {
+              int h = g;
+              while (h < 8 && rcost[byc[h]] == rcost[byc[g]]) ++h;
+              for (int q = g; q < h; ++q)
+                for (int s0 = byc[q]; s0 + run.len <= PATCH_RECS && (best < 0 || s0 < best); s0 += 8)
+                  if (free_len[s0] >= run.len) { best = s0; break; }
+              g = h;
+            }
           }
           if (best < 0) {  // fragmented: cut the run in two and place the halves
             runs.push_back({run.first, run.len / 2});
@@ -487,6 +496,8 @@ bool build_patch_schedule(gx_ctx* c) {
             int const l = byel[run.first + j];
             taken[best + j] = true; slot_of[l] = best + j; place(l, (best + j) & 7);
           }
+          for (int s0 = best; s0 < best + run.len; ++s0) free_len[s0] = 0;
+          for (int s0 = best - 1; s0 >= 0 && !taken[s0]; --s0) free_len[s0] = best - s0;  // the free stretch in front now ends at best
           run_e0.push_back((uint32_t)recs[byel[run.first]]);
           run_sl.push_back((uint32_t)best | ((uint32_t)run.len << 8));
         }
