@@ -525,12 +525,24 @@ bool build_patch_schedule(gx_ctx* c) {
         for (int v = 0; v < 8; ++v) C = std::max(C, degv[v]);  // <= 8 * PATCH_ITEM_LEN
         int atu[8 * 8 * PATCH_ITEM_LEN], atv[8 * 8 * PATCH_ITEM_LEN];  // edge with colour c at item u / at bank group v
         for (int k = 0; k < 8 * C; ++k) { atu[k] = -1; atv[k] = -1; }
+        uint64_t const all = C >= 64 ? ~(uint64_t)0 : (((uint64_t)1 << C) - 1);
+        uint64_t freeu[8], freev[8];  // bit c set = colour c unused at the item / at the bank group (mirrors atu / atv)
+        for (int k = 0; k < 8; ++k) { freeu[k] = all; freev[k] = all; }
+        auto put = [&](int ei, int col) {
+          Edge& pe = edges[ei];
+          pe.col = col;
+          atu[pe.u * C + col] = ei; atv[pe.v * C + col] = ei;
+          freeu[pe.u] &= ~((uint64_t)1 << col); freev[pe.v] &= ~((uint64_t)1 << col);
+        };
+        auto take = [&](int ei) {
+          Edge const& pe = edges[ei];
+          atu[pe.u * C + pe.col] = -1; atv[pe.v * C + pe.col] = -1;
+          freeu[pe.u] |= (uint64_t)1 << pe.col; freev[pe.v] |= (uint64_t)1 << pe.col;
+        };
         for (int ei = 0; ei < n_edges; ++ei) {
           Edge& e = edges[ei];
-          int ca = -1, cb = -1;
-          for (int c2 = 0; c2 < C && ca < 0; ++c2) if (atu[e.u * C + c2] < 0) ca = c2;
-          for (int c2 = 0; c2 < C && cb < 0; ++c2) if (atv[e.v * C + c2] < 0) cb = c2;
-          if (ca < 0 || cb < 0) { e.col = -2; continue; }  // cannot happen (C >= every degree); placed below if it does
+          if (!freeu[e.u] || !freev[e.v]) { e.col = -2; continue; }  // cannot happen (C >= every degree); placed below if it does
+          int const ca = __builtin_ctzll(freeu[e.u]), cb = __builtin_ctzll(freev[e.v]);  // lowest free colour at either end
           if (atv[e.v * C + ca] >= 0) {
             // colour ca is taken at v: swap ca <-> cb along the alternating path that starts at v with colour ca
             int path[8 * PATCH_ITEM_LEN], n_path = 0;
@@ -544,11 +556,11 @@ bool build_patch_schedule(gx_ctx* c) {
               cur = at_v ? atu[pe.u * C + want] : atv[pe.v * C + want];
               at_v = !at_v;
             }
-            for (int k = 0; k < n_path; ++k) { Edge& pe = edges[path[k]]; atu[pe.u * C + pe.col] = -1; atv[pe.v * C + pe.col] = -1; }
-            for (int k = 0; k < n_path; ++k) { Edge& pe = edges[path[k]]; pe.col = pe.col == ca ? cb : ca; atu[pe.u * C + pe.col] = path[k]; atv[pe.v * C + pe.col] = path[k]; }
+            int newcol[8 * PATCH_ITEM_LEN];
+            for (int k = 0; k < n_path; ++k) { newcol[k] = edges[path[k]].col == ca ? cb : ca; take(path[k]); }
+            for (int k = 0; k < n_path; ++k) put(path[k], newcol[k]);
           }
-          e.col = ca;
-          atu[e.u * C + ca] = ei; atv[e.v * C + ca] = ei;
+          put(ei, ca);
         }
         uint16_t sched_ent[8][PATCH_ITEM_LEN] = {};
         bool used_round[8][PATCH_ITEM_LEN] = {};
