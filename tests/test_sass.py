@@ -59,3 +59,23 @@ def test_residual_block_kernel_reads_its_schedule_by_bulk_copy(sass):
         assert "UBLKCP.S.G" in body and "TRYWAIT" in body and "BAR.SYNC" in body
     for body in _of(sass, "node_partial_sum_kernel"):
         assert "DADD" in body
+
+
+def test_register_budgets_of_the_hot_kernels(gxlib):
+    """The occupancies DESIGN.md 5 quotes rest on register counts: stage B at most 160 (4 blocks of 96 threads per SM),
+    the element kernels at most 128 (8 x 64 or 4 x 128 threads per SM).  Read from the build's ptxas log."""
+    log = os.path.join(ROOT, "goal_b200", "csrc", "ptxas.log")
+    if not os.path.exists(log):
+        pytest.skip("no ptxas.log (library not built by the Makefile)")
+    txt = open(log).read()
+    regs = {}
+    for m in re.finditer(r"Compiling entry function '(\S+)' for 'sm_100a'.*?Used (\d+) registers", txt, re.S):
+        regs[m.group(1)] = int(m.group(2))
+    def worst(part):
+        v = [r for k, r in regs.items() if part in k]
+        assert v, part
+        return max(v)
+    assert worst("patch_pair_kernel") <= 160
+    assert worst("elem_record_kernel") <= 128
+    assert worst("elem_residual_block_kernel") <= 128
+    assert worst("elem_residual_kernel") <= 128
